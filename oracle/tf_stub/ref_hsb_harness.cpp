@@ -1,0 +1,57 @@
+// ref_hsb_harness.cpp -- drives the reference's (unmodified) HSB / InvHSB / InvHSBGrad OpKernels
+// through the stub TF API with raw pointers.  TEST INFRASTRUCTURE ONLY.  Linked together with
+// /root/reference/src/tensorflow_ext/hsb_ops.cpp into oracle/_ref/libref_hsb_ops.so.
+#include <cstring>
+#include <memory>
+#include "tf_stub_core.h"
+
+using namespace tensorflow;
+
+static int run_op(const char* name, std::vector<const Tensor*> inputs, std::vector<DataType> out_types,
+                  std::vector<void*> out_ptrs, std::vector<size_t> out_bytes, int threads) {
+  auto& reg = OpRegistryStub::Global();
+  auto it = reg.kernels.find(std::string(name) + "/CPU");
+  if (it == reg.kernels.end()) return -1;
+  OpKernelConstruction c;
+  std::unique_ptr<OpKernel> k(it->second(&c));
+  OpKernelContext ctx;
+  ctx.inputs = inputs;
+  ctx.output_types = out_types;
+  ctx.dev.w_.num_threads = threads;
+  ctx.dev.w_.workers = nullptr;
+  k->Compute(&ctx);
+  if (!ctx.status.ok()) return -2;
+  for (size_t i = 0; i < out_ptrs.size(); ++i) std::memcpy(out_ptrs[i], ctx.outputs[i]->raw(), out_bytes[i]);
+  return 0;
+}
+
+extern "C" {
+
+int ref_hsb(int64_t B, int64_t n, const float* y_logit, const int32_t* left, const int32_t* right,
+            const int32_t* leaf, float* x, int threads) {
+  int64_t N = 2 * n - 1;
+  Tensor a(DT_FLOAT, TensorShape({B, n - 1}), (void*)y_logit), l(DT_INT32, TensorShape({B, N}), (void*)left),
+      r(DT_INT32, TensorShape({B, N}), (void*)right), f(DT_INT32, TensorShape({B, N}), (void*)leaf);
+  return run_op("HSB", {&a, &l, &r, &f}, {DT_FLOAT}, {x}, {(size_t)(B * n) * 4}, threads);
+}
+
+int ref_inv_hsb(int64_t B, int64_t n, const float* x, const int32_t* left, const int32_t* right,
+                const int32_t* leaf, double* y, float* ladj, int threads) {
+  int64_t N = 2 * n - 1;
+  Tensor a(DT_FLOAT, TensorShape({B, n}), (void*)x), l(DT_INT32, TensorShape({B, N}), (void*)left),
+      r(DT_INT32, TensorShape({B, N}), (void*)right), f(DT_INT32, TensorShape({B, N}), (void*)leaf);
+  return run_op("InvHSB", {&a, &l, &r, &f}, {DT_DOUBLE, DT_FLOAT}, {y, ladj},
+                {(size_t)(B * (n - 1)) * 8, (size_t)B * 4}, threads);
+}
+
+int ref_inv_hsb_grad(int64_t B, int64_t n, const double* y_grad, const float* ladj_grad, const double* y,
+                     const float* ladj, const int32_t* left, const int32_t* right, const int32_t* leaf,
+                     float* backprops, int threads) {
+  int64_t N = 2 * n - 1;
+  Tensor a(DT_DOUBLE, TensorShape({B, n - 1}), (void*)y_grad), b(DT_FLOAT, TensorShape({B, 1}), (void*)ladj_grad),
+      c(DT_DOUBLE, TensorShape({B, n - 1}), (void*)y), d(DT_FLOAT, TensorShape({B, 1}), (void*)ladj),
+      l(DT_INT32, TensorShape({B, N}), (void*)left), r(DT_INT32, TensorShape({B, N}), (void*)right),
+      f(DT_INT32, TensorShape({B, N}), (void*)leaf);
+  return run_op("InvHSBGrad", {&a, &b, &c, &d, &l, &r, &f}, {DT_FLOAT}, {backprops}, {(size_t)(B * n) * 4}, threads);
+}
+}
