@@ -120,8 +120,11 @@ class PTT:
         self.h = lib().orc_ptt_new(_p(self.parent_idxs), _p(self.js), c_i64(self.N))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_ptt_free(P(self.h)); self.h = None
+        try:
+            if getattr(self, "h", None):
+                lib().orc_ptt_free(P(self.h)); self.h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def index(self):
         buf = (C.c_int32 * (4 * self.N)).from_address(lib().orc_ptt_index(P(self.h)))

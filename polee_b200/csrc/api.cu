@@ -1,0 +1,735 @@
+// api.cu -- the extern "C" surface of libpolee_b200.so (include/polee_b200.h) and the per-step
+// launch sequence.  No CPU fallback anywhere: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+using namespace polee;
+
+static std::string g_create_error;
+static std::mutex g_err_mu;
+
+#define CK(expr) POLEE_CUDA_CHECK(h, expr)
+#define CHECK_H(h)                    \
+    if (!(h)) return POLEE_EINVAL;    \
+    (h)->err.clear();                 \
+    if (cudaSetDevice((h)->device) != cudaSuccess) return (h)->fail(POLEE_ECUDA, "cudaSetDevice failed")
+
+constexpr int TREE_BIN_NODES = 1024;
+
+static void drop_graph(polee_handle *h) {
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    h->graph_exec = nullptr;
+    h->graph = nullptr;
+}
+
+extern "C" int polee_opts_default(polee_opts *o) {
+    if (!o) return POLEE_EINVAL;
+    std::memset(o, 0, sizeof(*o));
+    o->device = 0;
+    o->approx = POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
+    o->num_steps = 500;       // LIKAP_NUM_STEPS       constants.jl:64
+    o->num_mc_samples = 6;    // LIKAP_NUM_MC_SAMPLES  constants.jl:65
+    o->gradonly = 1;          // Val(gradonly)=Val(true)  likelihood-approximation.jl:397
+    o->use_efflen_jacobian = 1;
+    o->noise_mode = POLEE_NOISE_PHILOX;
+    o->seed = 123456789ull;   // main.jl:123-127
+    o->max_step_mu = 2e-1;    // likelihood-approximation.jl:421-423
+    o->max_step_omega = 2e-1;
+    o->max_step_alpha = 2e-2;
+    o->max_step_z = 1e-1;     // :166
+    o->use_cuda_graph = 1;
+    return POLEE_OK;
+}
+
+extern "C" int polee_device_info(int32_t device, int32_t *sm, int32_t *num_sms, int64_t *hbm_bytes) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return POLEE_ECUDA;
+    if (sm) *sm = p.major * 10 + p.minor;
+    if (num_sms) *num_sms = p.multiProcessorCount;
+    if (hbm_bytes) *hbm_bytes = (int64_t)p.totalGlobalMem;
+    return POLEE_OK;
+}
+
+extern "C" int polee_create(polee_handle **out, const polee_opts *opts) {
+    if (!out) return POLEE_EINVAL;
+    *out = nullptr;
+    polee_opts o;
+    if (opts) o = *opts; else polee_opts_default(&o);
+    auto fail = [&](int code, const std::string &msg) {
+        std::lock_guard<std::mutex> lk(g_err_mu);
+        g_create_error = msg;
+        return code;
+    };
+    if (o.num_mc_samples < 1 || o.num_mc_samples > 16) return fail(POLEE_EINVAL, "num_mc_samples must be in 1..16");
+    if (o.approx == POLEE_APPROX_OPTIMIZE_PTT) o.num_mc_samples = 1;
+    if (o.num_steps < 0) return fail(POLEE_EINVAL, "num_steps must be >= 0");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(POLEE_ECUDA, std::string("no CUDA device (libpolee_b200 has no CPU fallback): ") +
+                                     cudaGetErrorString(e));
+    if (o.device < 0 || o.device >= count) return fail(POLEE_EINVAL, "device ordinal out of range");
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, o.device) != cudaSuccess) return fail(POLEE_ECUDA, "cudaGetDeviceProperties failed");
+    if (p.major != 10) return fail(POLEE_ECUDA, "libpolee_b200 is built for sm_100a only (B200); found another GPU");
+    if (cudaSetDevice(o.device) != cudaSuccess) return fail(POLEE_ECUDA, "cudaSetDevice failed");
+    polee_handle *h = new polee_handle();
+    h->o = o;
+    h->device = o.device;
+    h->num_sms = p.multiProcessorCount;
+    h->K = o.num_mc_samples;
+    h->KP = pad_k(h->K);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_step, sizeof(StepCtl)) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_bad_step, sizeof(int)) != cudaSuccess) {
+        delete h;
+        return fail(POLEE_ECUDA, "stream / control block allocation failed");
+    }
+    *out = h;
+    return POLEE_OK;
+}
+
+static void release_params(polee_handle *h) {
+    float *ptrs[] = {h->mu, h->omega, h->alpha, h->m_mu, h->m_omega, h->m_alpha, h->v_mu, h->v_omega, h->v_alpha};
+    for (float *p : ptrs) cudaFree(p);
+    h->mu = h->omega = h->alpha = h->m_mu = h->m_omega = h->m_alpha = h->v_mu = h->v_omega = h->v_alpha = nullptr;
+}
+
+extern "C" int polee_destroy(polee_handle *h) {
+    if (!h) return POLEE_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_graph(h);
+#ifdef POLEE_WITH_NCCL
+    if (h->comm) ncclCommDestroy(h->comm);
+#endif
+    release_work_buffers(h);
+    release_matrix(h);
+    release_params(h);
+    h->td.release();
+    cudaFree(h->efflen); cudaFree(h->efflen_adj); cudaFree(h->elbo); cudaFree(h->noise);
+    cudaFree(h->d_step); cudaFree(h->d_bad_step);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return POLEE_OK;
+}
+
+extern "C" const char *polee_last_error(const polee_handle *h) {
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    return g_create_error.c_str();
+}
+
+// ------------------------------------------------------------------ inputs
+static int check_dims(polee_handle *h, int64_t n) {
+    if (h->have_matrix && h->n != n) return h->fail(POLEE_EINVAL, "n differs from the matrix already set");
+    if (h->have_tree && h->td.n != n) return h->fail(POLEE_EINVAL, "n differs from the tree already set");
+    return POLEE_OK;
+}
+
+extern "C" int polee_set_matrix_csc_device(polee_handle *h, int64_t m, int64_t n, const uint32_t *d_colptr,
+                                           const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks) {
+    CHECK_H(h);
+    if (!d_colptr || (!d_rowval && m > 0) || !d_nzval) return h->fail(POLEE_EINVAL, "set_matrix: null pointer");
+    if (h->have_tree && h->td.n != n) return h->fail(POLEE_EINVAL, "n differs from the tree already set");
+    drop_graph(h);
+    release_work_buffers(h);
+    return setup_matrix_from_device_csc(h, m, n, d_colptr, d_rowval, d_nzval, d_ks, nullptr);
+}
+
+extern "C" int polee_set_matrix_csc(polee_handle *h, int64_t m, int64_t n, const uint32_t *colptr,
+                                    const uint32_t *rowval, const float *nzval, const int64_t *ks) {
+    CHECK_H(h);
+    if (!colptr || !rowval || !nzval) return h->fail(POLEE_EINVAL, "set_matrix: null pointer");
+    if (n < 1 || m < 1) return h->fail(POLEE_EINVAL, "set_matrix: m and n must be >= 1");
+    if (h->have_tree && h->td.n != n) return h->fail(POLEE_EINVAL, "n differs from the tree already set");
+    if (colptr[0] != 1) return h->fail(POLEE_EINVAL, "set_matrix: colptr must be 1-based (colptr[1] == 1)");
+    const int64_t nnz = (int64_t)colptr[n] - 1;
+    drop_graph(h);
+    release_work_buffers(h);
+    uint32_t *d_colptr = nullptr, *d_rowval = nullptr;
+    float *d_nzval = nullptr;
+    int64_t *d_ks = nullptr;
+    int rc = POLEE_OK;
+    auto cleanup = [&]() { cudaFree(d_colptr); cudaFree(d_rowval); cudaFree(d_nzval); cudaFree(d_ks); };
+#define CKC(expr)                                                                                     \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            cleanup();                                                                                \
+            return h->fail(POLEE_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+        }                                                                                             \
+    } while (0)
+    CKC(cudaMalloc((void **)&d_colptr, sizeof(uint32_t) * (n + 1)));
+    CKC(cudaMalloc((void **)&d_rowval, sizeof(uint32_t) * std::max<int64_t>(nnz, 1)));
+    CKC(cudaMalloc((void **)&d_nzval, sizeof(float) * std::max<int64_t>(nnz, 1)));
+    CKC(cudaMemcpyAsync(d_colptr, colptr, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, h->stream));
+    CKC(cudaMemcpyAsync(d_rowval, rowval, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice, h->stream));
+    CKC(cudaMemcpyAsync(d_nzval, nzval, sizeof(float) * nnz, cudaMemcpyHostToDevice, h->stream));
+    if (ks) {
+        CKC(cudaMalloc((void **)&d_ks, sizeof(int64_t) * m));
+        CKC(cudaMemcpyAsync(d_ks, ks, sizeof(int64_t) * m, cudaMemcpyHostToDevice, h->stream));
+    }
+#undef CKC
+    rc = setup_matrix_from_device_csc(h, m, n, d_colptr, d_rowval, d_nzval, d_ks, colptr);
+    cleanup();
+    return rc;
+}
+
+extern "C" int polee_set_efflens(polee_handle *h, const float *efflens) {
+    CHECK_H(h);
+    if (!efflens) return h->fail(POLEE_EINVAL, "set_efflens: null pointer");
+    int64_t n = h->have_matrix ? h->n : (h->have_tree ? h->td.n : 0);
+    if (n < 1) return h->fail(POLEE_EINVAL, "set_efflens: set the matrix or the tree first (n unknown)");
+    cudaFree(h->efflen); cudaFree(h->efflen_adj);
+    h->efflen = h->efflen_adj = nullptr;
+    std::vector<float> adj(n);
+    for (int64_t j = 0; j < n; ++j) adj[j] = (float)n * (1.0f / efflens[j]);  // likelihood.jl:105, Float32
+    CK(cudaMalloc((void **)&h->efflen, sizeof(float) * n));
+    CK(cudaMalloc((void **)&h->efflen_adj, sizeof(float) * n));
+    CK(cudaMemcpy(h->efflen, efflens, sizeof(float) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->efflen_adj, adj.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+    h->have_efflen = true;
+    return POLEE_OK;
+}
+
+static int alloc_params(polee_handle *h) {
+    release_params(h);
+    const int64_t nm1 = std::max<int64_t>(h->td.n - 1, 1);
+    float **ptrs[] = {&h->mu, &h->omega, &h->alpha, &h->m_mu, &h->m_omega, &h->m_alpha, &h->v_mu, &h->v_omega, &h->v_alpha};
+    for (float **p : ptrs) {
+        CK(cudaMalloc((void **)p, sizeof(float) * nm1));
+        CK(cudaMemset(*p, 0, sizeof(float) * nm1));
+    }
+    return POLEE_OK;
+}
+
+static int finish_tree(polee_handle *h, const std::string &err) {
+    if (!err.empty()) return h->fail(POLEE_EBADTREE, err);
+    std::string e2 = upload_tree(h->th, h->td);
+    if (!e2.empty()) return h->fail(POLEE_ECUDA, e2);
+    h->th.initial_mu(h->mu0);
+    h->have_tree = true;
+    int rc = alloc_params(h);
+    if (rc) return rc;
+    return polee_init_params(h);
+}
+
+extern "C" int polee_set_tree(polee_handle *h, int64_t n, const int32_t *node_parent_idxs, const int32_t *node_js) {
+    CHECK_H(h);
+    if (!node_parent_idxs || !node_js) return h->fail(POLEE_EINVAL, "set_tree: null pointer");
+    if (h->have_matrix && h->n != n) return h->fail(POLEE_EINVAL, "set_tree: n differs from the matrix already set");
+    drop_graph(h);
+    release_work_buffers(h);
+    h->have_tree = false;
+    return finish_tree(h, h->th.build_from_parents(n, node_parent_idxs, node_js, TREE_BIN_NODES));
+}
+
+extern "C" int polee_set_tree_sequential(polee_handle *h, int64_t n) {
+    CHECK_H(h);
+    if (n < 1) return h->fail(POLEE_EINVAL, "set_tree_sequential: n must be >= 1");
+    // list_nodes + order_nodes (hclust.jl:477-489, 361-389): root, leaf 1, I, leaf 2, ..., leaf n-1, leaf n
+    const int64_t N = 2 * n - 1;
+    std::vector<int32_t> pi(N), js(N);
+    int64_t pos = 0;
+    int32_t parent = 0;
+    for (int64_t leaf = 1; leaf <= n - 1; ++leaf) {
+        pi[pos] = parent; js[pos] = 0;
+        int32_t me = (int32_t)(pos + 1);
+        ++pos;
+        pi[pos] = me; js[pos] = (int32_t)leaf;
+        ++pos;
+        parent = me;
+    }
+    pi[pos] = parent; js[pos] = (int32_t)n;
+    return polee_set_tree(h, n, pi.data(), js.data());
+}
+
+// ------------------------------------------------------------------ parameters
+extern "C" int polee_init_params(polee_handle *h) {
+    CHECK_H(h);
+    if (!h->have_tree) return h->fail(POLEE_EINVAL, "init_params: set the tree first");
+    const int64_t nm1 = h->td.n - 1;
+    if (nm1 > 0) {
+        std::vector<float> om(nm1, logf(0.1f)), al(nm1, 0.0f);  // likelihood-approximation.jl:455-456
+        CK(cudaMemcpy(h->mu, h->mu0.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->omega, om.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->alpha, al.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        float *st[] = {h->m_mu, h->m_omega, h->m_alpha, h->v_mu, h->v_omega, h->v_alpha};
+        for (float *p : st) CK(cudaMemset(p, 0, sizeof(float) * nm1));
+    }
+    StepCtl c{1, 1};
+    CK(cudaMemcpy(h->d_step, &c, sizeof(c), cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->d_bad_step, 0, sizeof(int)));
+    h->steps_enqueued = 0;
+    return POLEE_OK;
+}
+
+extern "C" int polee_get_params(polee_handle *h, float *mu, float *omega, float *alpha) {
+    CHECK_H(h);
+    if (!h->have_tree) return h->fail(POLEE_EINVAL, "get_params: set the tree first");
+    const int64_t nm1 = h->td.n - 1;
+    CK(cudaStreamSynchronize(h->stream));
+    if (nm1 > 0) {
+        if (mu) CK(cudaMemcpy(mu, h->mu, sizeof(float) * nm1, cudaMemcpyDeviceToHost));
+        if (omega) CK(cudaMemcpy(omega, h->omega, sizeof(float) * nm1, cudaMemcpyDeviceToHost));
+        if (alpha) CK(cudaMemcpy(alpha, h->alpha, sizeof(float) * nm1, cudaMemcpyDeviceToHost));
+    }
+    return POLEE_OK;
+}
+
+extern "C" int polee_set_params(polee_handle *h, const float *mu, const float *omega, const float *alpha) {
+    CHECK_H(h);
+    if (!h->have_tree) return h->fail(POLEE_EINVAL, "set_params: set the tree first");
+    const int64_t nm1 = h->td.n - 1;
+    CK(cudaStreamSynchronize(h->stream));
+    if (nm1 > 0) {
+        if (mu) CK(cudaMemcpy(h->mu, mu, sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        if (omega) CK(cudaMemcpy(h->omega, omega, sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        if (alpha) CK(cudaMemcpy(h->alpha, alpha, sizeof(float) * nm1, cudaMemcpyHostToDevice));
+    }
+    return POLEE_OK;
+}
+
+extern "C" int polee_set_noise(polee_handle *h, const float *noise, int64_t num_steps) {
+    CHECK_H(h);
+    if (!h->have_tree) return h->fail(POLEE_EINVAL, "set_noise: set the tree first");
+    drop_graph(h);
+    cudaFree(h->noise);
+    h->noise = nullptr;
+    h->noise_steps = 0;
+    if (!noise || num_steps <= 0) return POLEE_OK;
+    const size_t count = (size_t)num_steps * h->K * (size_t)std::max<int64_t>(h->td.n - 1, 1);
+    CK(cudaMalloc((void **)&h->noise, sizeof(float) * count));
+    CK(cudaMemcpy(h->noise, noise, sizeof(float) * count, cudaMemcpyHostToDevice));
+    h->noise_steps = num_steps;
+    return POLEE_OK;
+}
+
+extern "C" void *polee_stream(polee_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+// ------------------------------------------------------------------ one ADAM step
+static int ready_for_steps(polee_handle *h) {
+    if (!h->have_matrix) return h->fail(POLEE_EINVAL, "no matrix: call polee_set_matrix_csc first");
+    if (!h->have_tree) return h->fail(POLEE_EINVAL, "no tree: call polee_set_tree first");
+    if (h->n != h->td.n) return h->fail(POLEE_EINVAL, "matrix and tree disagree on n");
+    const bool need_eff = h->o.use_efflen_jacobian || h->o.approx == POLEE_APPROX_OPTIMIZE_PTT;
+    if (need_eff && !h->have_efflen) return h->fail(POLEE_EINVAL, "no effective lengths: call polee_set_efflens first");
+    if (h->o.noise_mode == POLEE_NOISE_INJECTED && h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT && !h->noise)
+        return h->fail(POLEE_EINVAL, "noise_mode is INJECTED but no noise was supplied");
+    int rc = ensure_work_buffers(h, h->KP);
+    if (rc) return rc;
+    if (!h->elbo) {
+        CK(cudaMalloc((void **)&h->elbo, sizeof(double) * std::max(h->o.num_steps, 1)));
+        CK(cudaMemset(h->elbo, 0, sizeof(double) * std::max(h->o.num_steps, 1)));
+    }
+    return POLEE_OK;
+}
+
+// the launch sequence of one step (SURVEY 3a inner loop, batched over the K draws)
+static int launch_step_sequence(polee_handle *h, bool do_adam, float *grad_out, double *xgrad_out, const float *noise,
+                                int64_t noise_steps) {
+    const int KP = h->KP, K = h->K;
+    const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
+    const bool want_vals = lsn && !h->o.gradonly;
+    const bool apply_eff = lsn ? (h->o.use_efflen_jacobian != 0) : true;
+    int rc;
+    if ((rc = launch_reparam_fwd(h, KP, K, noise, noise_steps, want_vals))) return rc;
+    if ((rc = launch_tree_fwd(h, KP, 1, apply_eff, want_vals))) return rc;
+    if ((rc = launch_mid(h, KP, do_adam ? 1 : 0))) return rc;
+    if ((rc = launch_k1(h, h->x, h->w, want_vals, h->lp_partial, KP))) return rc;
+    if ((rc = launch_k2(h, h->w, h->g, KP))) return rc;
+    if (want_vals && (rc = launch_reduce_lp(h, h->lp_partial, h->g + (size_t)h->n * KP, KP))) return rc;
+#ifdef POLEE_WITH_NCCL
+    if (h->nranks > 1) {
+        size_t count = (size_t)(h->n + (want_vals ? 1 : 0)) * KP;
+        ncclResult_t r = ncclAllReduce(h->g, h->g, count, ncclDouble, ncclSum, h->comm, h->stream);
+        if (r != ncclSuccess) return h->fail(POLEE_ENCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+    }
+#endif
+    if ((rc = launch_tree_bwd(h, KP, lsn, apply_eff, xgrad_out))) return rc;
+    if (want_vals && (rc = launch_elbo(h, KP, K, true))) return rc;
+    if ((rc = launch_update(h, KP, K, do_adam, grad_out))) return rc;
+    return POLEE_OK;
+}
+
+static int enqueue_step(polee_handle *h) {
+    const float *noise = h->o.noise_mode == POLEE_NOISE_INJECTED ? h->noise : nullptr;
+    if (!h->o.use_cuda_graph) {
+        int rc = launch_step_sequence(h, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
+        if (rc) return rc;
+        CK(cudaGetLastError());
+        return POLEE_OK;
+    }
+    if (!h->graph_exec) {
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = launch_step_sequence(h, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
+        cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
+        if (rc) return rc;
+        if (e != cudaSuccess) return h->fail(POLEE_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+    }
+    CK(cudaGraphLaunch(h->graph_exec, h->stream));
+    return POLEE_OK;
+}
+
+extern "C" int polee_run_steps(polee_handle *h, int32_t nsteps) {
+    CHECK_H(h);
+    int rc = ready_for_steps(h);
+    if (rc) return rc;
+    for (int s = 0; s < nsteps; ++s) {
+        if ((rc = enqueue_step(h))) return rc;
+        h->steps_enqueued++;
+    }
+    return POLEE_OK;
+}
+
+extern "C" int polee_sync(polee_handle *h) {
+    CHECK_H(h);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    int bad = 0;
+    CK(cudaMemcpy(&bad, h->d_bad_step, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) return h->fail(POLEE_ENONFINITE, "non-finite gradient at step " + std::to_string(bad));
+    return POLEE_OK;
+}
+
+extern "C" int polee_get_elbo(polee_handle *h, double *elbo, int32_t nsteps) {
+    CHECK_H(h);
+    if (!h->elbo || !elbo) return h->fail(POLEE_EINVAL, "get_elbo: nothing recorded");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(elbo, h->elbo, sizeof(double) * std::min(nsteps, std::max(h->o.num_steps, 1)), cudaMemcpyDeviceToHost));
+    return POLEE_OK;
+}
+
+extern "C" int polee_fit(polee_handle *h, float *mu, float *omega, float *alpha, double *elbo_traj, const float *noise) {
+    CHECK_H(h);
+    if (h->o.approx != POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT) return h->fail(POLEE_EINVAL, "polee_fit: handle was created for OptimizePTTApprox");
+    int rc;
+    if (h->o.noise_mode == POLEE_NOISE_INJECTED) {
+        if (!noise && !h->noise) return h->fail(POLEE_EINVAL, "polee_fit: noise_mode is INJECTED but noise == NULL");
+        if (noise && (rc = polee_set_noise(h, noise, h->o.num_steps))) return rc;
+    }
+    if ((rc = polee_init_params(h))) return rc;
+    if ((rc = polee_run_steps(h, h->o.num_steps))) return rc;
+    if ((rc = polee_sync(h))) return rc;
+    if ((rc = polee_get_params(h, mu, omega, alpha))) return rc;
+    if (elbo_traj) {
+        if (h->o.gradonly)
+            std::fill(elbo_traj, elbo_traj + h->o.num_steps, 0.0);  // reference: elbo == 0 when gradonly
+        else if ((rc = polee_get_elbo(h, elbo_traj, h->o.num_steps)))
+            return rc;
+    }
+    return POLEE_OK;
+}
+
+// ------------------------------------------------------------------ layout helpers ([K][len] host <-> [len][KP] device)
+template <typename T>
+static int upload_kmajor(polee_handle *h, const T *host, int K, int KP, int64_t len, T *dev, T pad) {
+    std::vector<T> tmp((size_t)len * KP, pad);
+    for (int k = 0; k < K; ++k)
+        for (int64_t i = 0; i < len; ++i) tmp[(size_t)i * KP + k] = host[(size_t)k * len + i];
+    CK(cudaMemcpyAsync(dev, tmp.data(), sizeof(T) * tmp.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return POLEE_OK;
+}
+template <typename T, typename U>
+static int download_kmajor(polee_handle *h, const T *dev, int K, int KP, int64_t len, U *host) {
+    std::vector<T> tmp((size_t)len * KP);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(tmp.data(), dev, sizeof(T) * tmp.size(), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < K; ++k)
+        for (int64_t i = 0; i < len; ++i) host[(size_t)k * len + i] = (U)tmp[(size_t)i * KP + k];
+    return POLEE_OK;
+}
+
+static int use_kp(polee_handle *h, int K, int *KP) {
+    if (K < 1 || K > 16) return h->fail(POLEE_EINVAL, "K must be in 1..16");
+    *KP = pad_k(K);
+    drop_graph(h);
+    return ensure_work_buffers(h, *KP);
+}
+
+// after a piecewise call with a different KP, the fit's buffers are re-created lazily
+extern "C" int polee_fit_optimize_ptt(polee_handle *h, float *xs) {
+    CHECK_H(h);
+    if (h->o.approx != POLEE_APPROX_OPTIMIZE_PTT) return h->fail(POLEE_EINVAL, "handle was not created with POLEE_APPROX_OPTIMIZE_PTT");
+    if (!h->have_matrix) return h->fail(POLEE_EINVAL, "no matrix: call polee_set_matrix_csc first");
+    int rc;
+    if ((rc = polee_set_tree_sequential(h, h->n))) return rc;   // PolyaTreeTransform(X, :sequential)  l-a.jl:160
+    if ((rc = polee_run_steps(h, h->o.num_steps))) return rc;
+    if ((rc = polee_sync(h))) return rc;
+    // final transform of the optimised zs  (l-a.jl:237-241)
+    if ((rc = launch_reparam_fwd(h, h->KP, h->K, nullptr, 1, 0))) return rc;
+    if ((rc = launch_tree_fwd(h, h->KP, 1, 0, 0))) return rc;
+    return download_kmajor<float, float>(h, h->x, 1, h->KP, h->n, xs);
+}
+
+// ------------------------------------------------------------------ piecewise entry points
+extern "C" int polee_loglik_grad(polee_handle *h, const float *xs, int32_t K, int32_t gradonly, double *lp, double *x_grad) {
+    CHECK_H(h);
+    if (!h->have_matrix) return h->fail(POLEE_EINVAL, "no matrix: call polee_set_matrix_csc first");
+    if (!h->have_tree) return h->fail(POLEE_EINVAL, "loglik_grad: set a tree first (work buffers are sized from it)");
+    int KP, rc;
+    if ((rc = use_kp(h, K, &KP))) return rc;
+    if ((rc = upload_kmajor<float>(h, xs, K, KP, h->n, h->x, 1.0f))) return rc;
+    if ((rc = launch_k1(h, h->x, h->w, !gradonly, h->lp_partial, KP))) return rc;
+    if ((rc = launch_k2(h, h->w, h->g, KP))) return rc;
+    if (!gradonly && (rc = launch_reduce_lp(h, h->lp_partial, h->g + (size_t)h->n * KP, KP))) return rc;
+    CK(cudaGetLastError());
+    if (x_grad && (rc = download_kmajor<double, double>(h, h->g, K, KP, h->n, x_grad))) return rc;
+    if (lp) {
+        if (gradonly) {
+            std::fill(lp, lp + K, 0.0);
+        } else {
+            std::vector<double> t(KP);
+            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaMemcpy(t.data(), h->g + (size_t)h->n * KP, sizeof(double) * KP, cudaMemcpyDeviceToHost));
+            std::copy(t.begin(), t.begin() + K, lp);
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return POLEE_OK;
+}
+
+extern "C" int polee_frag_prob_recip(polee_handle *h, const float *xs, float *w) {
+    CHECK_H(h);
+    if (!h->have_matrix || !h->have_tree) return h->fail(POLEE_EINVAL, "frag_prob_recip: set the matrix and a tree first");
+    int KP, rc;
+    if ((rc = use_kp(h, 1, &KP))) return rc;
+    if ((rc = upload_kmajor<float>(h, xs, 1, KP, h->n, h->x, 1.0f))) return rc;
+    if ((rc = launch_k1(h, h->x, h->w, false, h->lp_partial, KP))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<float> wp(h->m_pad);
+    std::vector<uint32_t> perm(h->m);
+    CK(cudaMemcpy(wp.data(), h->w, sizeof(float) * h->m_pad, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(perm.data(), h->row_perm, sizeof(uint32_t) * h->m, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < h->m; ++i) w[i] = wp[perm[i]];
+    return POLEE_OK;
+}
+
+extern "C" int polee_ptt_transform(polee_handle *h, const double *ys, int32_t K, float *xs, double *ladj) {
+    CHECK_H(h);
+    if (!h->have_tree) return h->fail(POLEE_EINVAL, "no tree: call polee_set_tree first");
+    h->n = h->td.n;
+    int KP, rc;
+    if ((rc = use_kp(h, K, &KP))) return rc;
+    if ((rc = upload_kmajor<double>(h, ys, K, KP, h->n - 1, h->ys, 0.5))) return rc;
+    if ((rc = launch_tree_fwd(h, KP, 0, 0, ladj ? 1 : 0))) return rc;
+    CK(cudaGetLastError());
+    if ((rc = download_kmajor<float, float>(h, h->x, K, KP, h->n, xs))) return rc;
+    if (ladj) {
+        const int ne = (int)std::max<int64_t>(1, ((h->n - 1) * (int64_t)KP + 255) / 256);
+        std::vector<double> part((size_t)h->n_tree_ctas * KP);
+        CK(cudaMemcpy(part.data(), h->ladj_partial + (size_t)2 * ne * KP, sizeof(double) * part.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < K; ++k) {
+            double s = 0.0;
+            for (int t = 0; t < h->n_tree_ctas; ++t) s += part[(size_t)t * KP + k];
+            ladj[k] = s;
+        }
+    }
+    return POLEE_OK;
+}
+
+extern "C" int polee_ptt_transform_gradients(polee_handle *h, const double *ys, const double *x_grad, int32_t K,
+                                             int32_t with_ladj, float *y_grad) {
+    CHECK_H(h);
+    if (!h->have_tree) return h->fail(POLEE_EINVAL, "no tree: call polee_set_tree first");
+    h->n = h->td.n;
+    int KP, rc;
+    if ((rc = use_kp(h, K, &KP))) return rc;
+    if ((rc = upload_kmajor<double>(h, ys, K, KP, h->n - 1, h->ys, 0.5))) return rc;
+    if ((rc = upload_kmajor<double>(h, x_grad, K, KP, h->n, h->g, 0.0))) return rc;
+    if ((rc = launch_tree_fwd(h, KP, 0, 0, 0))) return rc;  // us, as transform! leaves them in t.us
+    if ((rc = launch_tree_bwd(h, KP, with_ladj != 0, false, nullptr))) return rc;
+    CK(cudaGetLastError());
+    return download_kmajor<double, float>(h, h->ygrad, K, KP, h->n - 1, y_grad);
+}
+
+// inverse_transform!  ptt.jl:257-285.  Bottom-up sums are a host-side O(n) sweep per draw: this entry
+// point exists for initialisation and tests, not for the per-step path (the fit never calls it per step).
+extern "C" int polee_ptt_inverse_transform(polee_handle *h, const float *xs, int32_t K, double *ys, double *ladj) {
+    CHECK_H(h);
+    if (!h->have_tree) return h->fail(POLEE_EINVAL, "no tree: call polee_set_tree first");
+    const TreeHost &t = h->th;
+    std::vector<double> us(t.N);
+    for (int k = 0; k < K; ++k) {
+        double l = 0.0;
+        for (int64_t i = t.N - 1; i >= 0; --i) {
+            const TreeNode &nd = t.nodes[i];
+            if (nd.leaf >= 0) {
+                us[i] = (double)xs[(size_t)k * t.n + nd.leaf];
+            } else {
+                us[i] = us[nd.left] + us[nd.right];
+                l -= (double)logf((float)us[i]);
+                ys[(size_t)k * (t.n - 1) + nd.k] = us[nd.left] / us[i];
+            }
+        }
+        if (ladj) ladj[k] = l;
+    }
+    return POLEE_OK;
+}
+
+extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, float *xs, double *ys, double *x_grad,
+                               float *y_grad, float *mu_grad, float *omega_grad, float *alpha_grad, double *elbo) {
+    CHECK_H(h);
+    if (K != h->K) return h->fail(POLEE_EINVAL, "lsn_draws: K must equal opts.num_mc_samples");
+    if (!zs0) return h->fail(POLEE_EINVAL, "lsn_draws: zs0 == NULL");
+    int rc = ready_for_steps(h);
+    if (rc == POLEE_EINVAL && !h->noise && h->o.noise_mode == POLEE_NOISE_INJECTED && h->have_matrix && h->have_tree) {
+        h->err.clear();
+        rc = ensure_work_buffers(h, h->KP);
+        if (!rc && !h->elbo) {
+            CK(cudaMalloc((void **)&h->elbo, sizeof(double) * std::max(h->o.num_steps, 1)));
+            CK(cudaMemset(h->elbo, 0, sizeof(double) * std::max(h->o.num_steps, 1)));
+        }
+    }
+    if (rc) return rc;
+    const int KP = h->KP;
+    const int64_t n = h->n, nm1 = n - 1;
+    float *d_noise = nullptr;
+    double *d_xg = nullptr;
+    CK(cudaMalloc((void **)&d_noise, sizeof(float) * (size_t)K * std::max<int64_t>(nm1, 1)));
+    CK(cudaMalloc((void **)&d_xg, sizeof(double) * (size_t)n * KP));
+    CK(cudaMemcpy(d_noise, zs0, sizeof(float) * (size_t)K * nm1, cudaMemcpyHostToDevice));
+    StepCtl saved, one{1, 1};
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(&saved, h->d_step, sizeof(saved), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h->d_step, &one, sizeof(one), cudaMemcpyHostToDevice));
+    rc = launch_step_sequence(h, false, h->grad_out, d_xg, d_noise, 1);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (!rc && e != cudaSuccess) rc = h->fail(POLEE_ECUDA, std::string("lsn_draws: ") + cudaGetErrorString(e));
+    if (!rc && xs) rc = download_kmajor<float, float>(h, h->x, K, KP, n, xs);
+    if (!rc && ys) rc = download_kmajor<double, double>(h, h->ys, K, KP, nm1, ys);
+    if (!rc && x_grad) rc = download_kmajor<double, double>(h, d_xg, K, KP, n, x_grad);
+    if (!rc && y_grad) rc = download_kmajor<double, float>(h, h->ygrad, K, KP, nm1, y_grad);
+    if (!rc && nm1 > 0) {
+        if (mu_grad) cudaMemcpy(mu_grad, h->grad_out, sizeof(float) * nm1, cudaMemcpyDeviceToHost);
+        if (omega_grad) cudaMemcpy(omega_grad, h->grad_out + nm1, sizeof(float) * nm1, cudaMemcpyDeviceToHost);
+        if (alpha_grad) cudaMemcpy(alpha_grad, h->grad_out + 2 * nm1, sizeof(float) * nm1, cudaMemcpyDeviceToHost);
+    }
+    if (!rc && elbo) {
+        *elbo = 0.0;
+        if (!h->o.gradonly) cudaMemcpy(elbo, h->elbo, sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    cudaMemcpy(h->d_step, &saved, sizeof(saved), cudaMemcpyHostToDevice);
+    cudaMemset(h->d_bad_step, 0, sizeof(int));
+    cudaFree(d_noise);
+    cudaFree(d_xg);
+    return rc;
+}
+
+// ------------------------------------------------------------------ measurement helpers
+extern "C" int polee_step_stats(polee_handle *h, double *b1, double *b2, double *b3, int32_t *launches) {
+    CHECK_H(h);
+    if (!h->have_matrix || !h->have_tree) return h->fail(POLEE_EINVAL, "step_stats: set the matrix and the tree first");
+    // SURVEY 8(d) / BASELINE.md section 2 formulas with the padded draw count actually streamed
+    const double nnz = (double)h->nnz, m = (double)h->m, n = (double)h->n, K = (double)h->KP, N = 2 * n - 1;
+    if (b1) *b1 = nnz * 8 + (m + 1) * 4 + K * n * 4 + K * m * 4;
+    if (b2) *b2 = nnz * 8 + (n + 1) * 4 + K * m * 4 + K * n * 4;
+    if (b3) *b3 = (n - 1) * 72 + N * 16 + K * n * 8;
+    if (launches) {
+        const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
+        const bool vals = lsn && !h->o.gradonly;
+        int L = 1 /*reparam*/ + (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*mid*/ + (h->n_row_tiles > 0) +
+                (h->n_segs > 0) + (h->n_multi > 0) + (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*update*/;
+        if (vals) L += 2;
+        *launches = L;
+    }
+    return POLEE_OK;
+}
+
+extern "C" int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, float *ms_avg) {
+    CHECK_H(h);
+    int rc = ready_for_steps(h);
+    if (rc) return rc;
+    if (reps < 1 || !ms_avg) return h->fail(POLEE_EINVAL, "time_kernel: bad arguments");
+    const int KP = h->KP, K = h->K;
+    const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const float *noise = h->o.noise_mode == POLEE_NOISE_INJECTED ? h->noise : nullptr;
+    CK(cudaEventRecord(e0, h->stream));
+    for (int r = 0; r < reps && !rc; ++r) {
+        if (which == 1) {
+            rc = launch_k1(h, h->x, h->w, false, h->lp_partial, KP);
+        } else if (which == 2) {
+            rc = launch_k2(h, h->w, h->g, KP);
+        } else if (which == 3) {
+            rc = launch_reparam_fwd(h, KP, K, noise, std::max<int64_t>(h->noise_steps, 1), 0);
+            if (!rc) rc = launch_tree_fwd(h, KP, 1, 1, 0);
+            if (!rc) rc = launch_mid(h, KP, 0);
+            if (!rc) rc = launch_tree_bwd(h, KP, lsn, true, nullptr);
+            if (!rc) rc = launch_update(h, KP, K, false, nullptr);
+        } else {
+            rc = h->fail(POLEE_EINVAL, "time_kernel: which must be 1, 2 or 3");
+        }
+    }
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    *ms_avg = ms / reps;
+    return rc;
+}
+
+// ------------------------------------------------------------------ multi-GPU
+extern "C" int polee_partition_rows(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval, int32_t nparts,
+                                    int64_t *row_bounds) {
+    if (!colptr || !rowval || !row_bounds || nparts < 1 || m < 1 || n < 1) return POLEE_EINVAL;
+    const int64_t nnz = (int64_t)colptr[n] - 1;
+    std::vector<int64_t> cnt(m + 1, 0);
+    for (int64_t e = 0; e < nnz; ++e) cnt[rowval[e]]++;  // 1-based row -> slot
+    for (int64_t i = 0; i < m; ++i) cnt[i + 1] += cnt[i];
+    row_bounds[0] = 0;
+    for (int p = 1; p < nparts; ++p) {
+        const int64_t target = nnz * p / nparts;
+        int64_t r = std::lower_bound(cnt.begin(), cnt.end(), target) - cnt.begin();
+        row_bounds[p] = std::min<int64_t>(std::max<int64_t>(r, row_bounds[p - 1]), m);
+    }
+    row_bounds[nparts] = m;
+    return POLEE_OK;
+}
+
+extern "C" int polee_comm_unique_id(char id[128]) {
+#ifdef POLEE_WITH_NCCL
+    static_assert(sizeof(ncclUniqueId) <= 128, "ncclUniqueId does not fit");
+    ncclUniqueId u;
+    if (ncclGetUniqueId(&u) != ncclSuccess) return POLEE_ENCCL;
+    std::memset(id, 0, 128);
+    std::memcpy(id, &u, sizeof(u));
+    return POLEE_OK;
+#else
+    (void)id;
+    return POLEE_ENCCL;
+#endif
+}
+
+extern "C" int polee_comm_init(polee_handle *h, int32_t nranks, int32_t rank, const char id[128]) {
+    CHECK_H(h);
+#ifdef POLEE_WITH_NCCL
+    if (nranks < 1 || rank < 0 || rank >= nranks) return h->fail(POLEE_EINVAL, "comm_init: bad rank / nranks");
+    drop_graph(h);
+    if (h->comm) { ncclCommDestroy(h->comm); h->comm = nullptr; }
+    h->nranks = nranks;
+    h->rank = rank;
+    if (nranks == 1) return POLEE_OK;
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof(u));
+    ncclResult_t r = ncclCommInitRank(&h->comm, nranks, u, rank);
+    if (r != ncclSuccess) return h->fail(POLEE_ENCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    return POLEE_OK;
+#else
+    (void)nranks; (void)rank; (void)id;
+    return h->fail(POLEE_ENCCL, "library built without NCCL");
+#endif
+}

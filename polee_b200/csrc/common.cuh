@@ -1,0 +1,220 @@
+// common.cuh -- internal declarations shared by the translation units of libpolee_b200.so.
+// Nothing here is part of the ABI (that is include/polee_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/polee_b200.h"
+
+#ifdef POLEE_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace polee {
+
+// ------------------------------------------------------------------ error plumbing
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define POLEE_CUDA_CHECK(h, expr)                                                          \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            return (h)->fail(POLEE_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+        }                                                                                  \
+    } while (0)
+
+// ------------------------------------------------------------------ device layouts
+// K1: one tile = up to ROW_TILE rows of one row-length class of the SELL slabs.
+constexpr int ROW_TILE = 256;
+struct RowTile {
+    uint64_t slab_off;  // element offset of (t = 0, first row of the tile) in sell_idx / sell_val
+    uint32_t stride;    // rows (padded) in the class = distance between successive t
+    uint32_t len;       // entries per row in this class
+    uint32_t row0;      // first permuted row id of the tile
+    uint32_t nrows;     // valid rows in the tile (<= ROW_TILE)
+};
+
+// K2: one warp = one segment of <= COL_SEG consecutive entries of one column (rows permuted, sorted).
+constexpr int COL_SEG = 256;
+struct ColSeg {
+    uint32_t start;  // entry offset in csc_row / csc_val
+    uint32_t len;
+    uint32_t col;
+    int32_t slot;    // >= 0: partial slot (column spans several segments); -1: writes g directly
+};
+struct MultiCol {
+    uint32_t col;
+    uint32_t first_slot;
+    uint32_t nslots;
+    uint32_t pad;
+};
+
+// step counters living in device memory so that one captured CUDA graph can be replayed for every step
+struct StepCtl {
+    int step_fwd;  // 1-based step the forward kernels of the current step use
+    int step_upd;  // same, as seen by the update kernel (set by k3_mid)
+};
+
+// Tree node, 0-based; leaf < 0 <=> internal node (then k = index among internal nodes in node order).
+struct TreeNode {
+    int32_t left, right, k, leaf;
+};
+
+// Level-ordered schedule of a set of "bins" (one CTA each).  Bin b owns levels
+// lvl_off[bin_lvl_ptr[b] .. bin_lvl_ptr[b+1]] (one more offset than levels) into sch_node.
+struct TreeSchedHost {
+    std::vector<int32_t> bin_lvl_ptr;  // nbins + 1
+    std::vector<int32_t> lvl_off;      // sum(levels_b + 1)
+    std::vector<int32_t> sch_node;     // node ids in (bin, level) order
+    int nbins() const { return (int)bin_lvl_ptr.size() - 1; }
+};
+
+struct TreeSchedDev {
+    int32_t *bin_lvl_ptr = nullptr, *lvl_off = nullptr, *sch_node = nullptr;
+    int nbins = 0;
+    int max_levels = 0;
+};
+
+struct TreeHost {
+    int64_t n = 0, N = 0;
+    std::vector<TreeNode> nodes;
+    std::vector<int32_t> parent, depth, size;
+    TreeSchedHost top, bottom;
+    int top_nodes = 0;
+    int max_depth = 0;
+    // returns "" or an error text
+    std::string build_from_lrf(int64_t n, const int32_t *left, const int32_t *right, const int32_t *leaf,
+                               int bin_nodes);
+    std::string build_from_parents(int64_t n, const int32_t *parent_idxs, const int32_t *js, int bin_nodes);
+    // inverse_transform!(t, fill(1f0/n, n), ys) -> mu = Float32(logit(ys))  (likelihood-approximation.jl:451-453)
+    void initial_mu(std::vector<float> &mu) const;
+};
+
+struct TreeDev {
+    int64_t n = 0, N = 0;
+    TreeNode *nodes = nullptr;
+    TreeSchedDev top, bottom;
+    void release();
+};
+
+std::string upload_tree(const TreeHost &th, TreeDev &td);
+
+}  // namespace polee
+
+// ------------------------------------------------------------------ the handle
+struct polee_handle {
+    polee_opts o;
+    std::string err;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    int K = 0, KP = 0;  // draws, padded draws (power of two)
+
+    // ---- matrix
+    int64_t m = 0, n = 0, nnz = 0;
+    int64_t m_pad = 0;          // rows in permuted order incl. class padding
+    uint32_t *sell_idx = nullptr;
+    float *sell_val = nullptr;
+    int64_t sell_elems = 0;
+    polee::RowTile *row_tiles = nullptr;
+    int n_row_tiles = 0;
+    uint32_t *row_perm = nullptr;  // original row -> permuted row
+    float *row_weight = nullptr;   // ks per permuted row (nullable)
+    uint32_t *csc_row = nullptr;
+    float *csc_val = nullptr;
+    polee::ColSeg *segs = nullptr;
+    int n_segs = 0;
+    polee::MultiCol *multi = nullptr;
+    int n_multi = 0;
+    int n_slots = 0;
+    bool have_matrix = false;
+
+    // ---- per-sample vectors
+    float *efflen = nullptr;      // [n]
+    float *efflen_adj = nullptr;  // Float32(n * (1/efflen))  likelihood.jl:105
+    bool have_efflen = false;
+
+    // ---- tree
+    polee::TreeHost th;
+    polee::TreeDev td;
+    bool have_tree = false;
+    std::vector<float> mu0;
+
+    // ---- parameters / ADAM state: [n-1] each
+    float *mu = nullptr, *omega = nullptr, *alpha = nullptr;
+    float *m_mu = nullptr, *m_omega = nullptr, *m_alpha = nullptr;
+    float *v_mu = nullptr, *v_omega = nullptr, *v_alpha = nullptr;
+    polee::StepCtl *d_step = nullptr;  // device step counters
+    int *d_bad_step = nullptr;         // first step with a non-finite gradient, 0 = none
+    int steps_enqueued = 0;
+
+    // ---- per-step work buffers (layouts [item][KP])
+    float *zs0 = nullptr, *zs = nullptr;  // [n-1][KP]
+    double *ys = nullptr;                 // [n-1][KP]
+    double *ygrad = nullptr;              // [n-1][KP]
+    double *us = nullptr;                 // [N][KP]
+    float2 *G = nullptr;                  // [N][KP]
+    float *x = nullptr;                   // [n][KP]
+    float *w = nullptr;                   // [m_pad][KP]
+    double *g = nullptr;                  // [n][KP]  (all-reduced across ranks)
+    double *seg_partial = nullptr;        // [n_slots][KP]
+    double *S_partial = nullptr;          // [n_tree_ctas][KP]
+    double *S = nullptr;                  // [KP] sum_j x_j / efflen_j      (then lp[KP] follows in g_tail)
+    double *lp_partial = nullptr;         // [n_row_tiles][KP]
+    double *ladj_partial = nullptr;       // [3][n_tree_ctas + n_elem_ctas][KP]
+    double *lp = nullptr;                 // [KP]
+    double *elbo = nullptr;               // [num_steps]
+    float *noise = nullptr;               // injected noise [steps][K][n-1]
+    int64_t noise_steps = 0;
+    float *grad_out = nullptr;            // [3][n-1] averaged grads (polee_lsn_draws)
+    int work_KP = 0;                      // KP the work buffers were sized for
+    int n_tree_ctas = 0;
+
+    // ---- graph
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+
+#ifdef POLEE_WITH_NCCL
+    ncclComm_t comm = nullptr;
+#endif
+    int nranks = 1, rank = 0;
+
+    int fail(int code, const std::string &msg) {
+        err = msg;
+        return code;
+    }
+};
+
+namespace polee {
+
+int pad_k(int K);
+
+// matrix_setup.cu
+int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const uint32_t *d_colptr,
+                                 const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
+                                 const uint32_t *h_colptr_or_null);
+void release_matrix(polee_handle *h);
+
+// sparse_kernels.cu
+int launch_k1(polee_handle *h, const float *x, float *w, bool want_lp, double *lp_partial, int KP);
+int launch_k2(polee_handle *h, const float *w, double *g, int KP);
+int launch_reduce_lp(polee_handle *h, const double *lp_partial, double *lp, int KP);
+
+// tree_kernels.cu
+int ensure_work_buffers(polee_handle *h, int KP);
+void release_work_buffers(polee_handle *h);
+int launch_reparam_fwd(polee_handle *h, int KP, int K, const float *noise, int64_t noise_steps, int want_ladj);
+int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_ladj);
+int launch_mid(polee_handle *h, int KP, int advance);
+int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, double *xgrad_out);
+int launch_update(polee_handle *h, int KP, int K, bool do_adam, float *grad_out);
+int launch_elbo(polee_handle *h, int KP, int K, bool have_lp);
+
+}  // namespace polee

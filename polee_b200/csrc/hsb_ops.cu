@@ -1,0 +1,389 @@
+// hsb_ops.cu -- K4: the three hierarchical-stick-breaking ops of the reference's TensorFlow plugin
+// (src/tensorflow_ext/hsb_ops.cpp), batched over B rows, on the same level-synchronous tree engine
+// as the fit (tree_host.cu).  The reference shards the batch over TF CPU threads and walks each
+// tree serially (hsb_ops.cpp:87-115, 206-245, 338-398); here every (schedule bin, row) is one CTA.
+//
+// Index tensors are [idx_batch][2n-1] with idx_batch == B (a tree per row, as the reference op
+// requires -- src/estimate.jl:357-360) or 1 (shared tree).  A "plan" holds the
+// validated, scheduled tree(s) on the device so that callers with constant index tensors (every
+// training step of a TF model) pay for the preparation once.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+using namespace polee;
+
+struct polee_hsb_plan {
+    int device = 0;
+    int64_t n = 0, N = 0, ntrees = 0;
+    TreeNode *nodes = nullptr;  // [ntrees][N]
+    // phase 0 = top bins, 1 = bottom bins (concatenated over trees)
+    int32_t *bin_lvl_ptr[2] = {nullptr, nullptr}, *lvl_off[2] = {nullptr, nullptr}, *sch_node[2] = {nullptr, nullptr};
+    int32_t *bin_tree[2] = {nullptr, nullptr};
+    int nbins[2] = {0, 0};
+    int32_t *desc_order = nullptr;  // [ntrees][n-1] internal node ids in descending node order (ladj emulation)
+    std::string err;
+};
+
+namespace {
+
+std::string g_hsb_error;
+std::mutex g_hsb_mu;
+
+int hsb_fail(int code, const std::string &msg) {
+    std::lock_guard<std::mutex> lk(g_hsb_mu);
+    g_hsb_error = msg;
+    return code;
+}
+
+constexpr int HSB_THREADS = 128;
+constexpr int HSB_BIN_NODES = 4096;
+
+struct Sched {
+    const int32_t *bin_lvl_ptr, *lvl_off, *sch_node, *bin_tree;
+};
+
+__device__ __forceinline__ void bin_row(const Sched &s, int shared_tree, int &tree, int64_t &row) {
+    tree = s.bin_tree[blockIdx.x];
+    row = shared_tree ? (int64_t)blockIdx.y : (int64_t)tree;
+}
+
+// HSBOp::Compute  hsb_ops.cpp:87-109
+__global__ void __launch_bounds__(HSB_THREADS)
+    k4_hsb_fwd(Sched s, int shared_tree, const TreeNode *__restrict__ nodes_all, int64_t n, int64_t N,
+               const float *__restrict__ y_logit, double *__restrict__ us, float *__restrict__ x) {
+    int tree;
+    int64_t row;
+    bin_row(s, shared_tree, tree, row);
+    const TreeNode *nodes = nodes_all + (size_t)tree * N;
+    double *u = us + (size_t)row * N;
+    const int l0 = s.bin_lvl_ptr[blockIdx.x], l1 = s.bin_lvl_ptr[blockIdx.x + 1] - 1;
+    for (int l = l0; l < l1; ++l) {
+        for (int q = s.lvl_off[l] + threadIdx.x; q < s.lvl_off[l + 1]; q += HSB_THREADS) {
+            const int node = s.sch_node[q];
+            const TreeNode nd = nodes[node];
+            const double ui = node == 0 ? 1.0 : u[node];
+            if (nd.leaf >= 0) {
+                x[(size_t)row * n + nd.leaf] = (float)ui;
+            } else {
+                // `1.0 / (1.0 + (double) exp(-y_logit_i[k]))`: exp() resolves to the double overload
+                const double y = __ddiv_rn(1.0, __dadd_rn(1.0, exp((double)(-y_logit[(size_t)row * (n - 1) + nd.k]))));
+                u[nd.left] = __dmul_rn(y, ui);
+                u[nd.right] = __dmul_rn(__dsub_rn(1.0, y), ui);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// InvHSBOp::Compute  hsb_ops.cpp:206-239 (bottom-up): y and log(u_j) per internal node
+__global__ void __launch_bounds__(HSB_THREADS)
+    k4_inv_hsb(Sched s, int shared_tree, const TreeNode *__restrict__ nodes_all, int64_t n, int64_t N,
+               const float *__restrict__ x, double *__restrict__ us, double *__restrict__ y, double *__restrict__ logu) {
+    int tree;
+    int64_t row;
+    bin_row(s, shared_tree, tree, row);
+    const TreeNode *nodes = nodes_all + (size_t)tree * N;
+    double *u = us + (size_t)row * N;
+    const int l0 = s.bin_lvl_ptr[blockIdx.x], l1 = s.bin_lvl_ptr[blockIdx.x + 1] - 1;
+    for (int l = l1 - 1; l >= l0; --l) {
+        for (int q = s.lvl_off[l] + threadIdx.x; q < s.lvl_off[l + 1]; q += HSB_THREADS) {
+            const int node = s.sch_node[q];
+            const TreeNode nd = nodes[node];
+            if (nd.leaf >= 0) {
+                u[node] = (double)x[(size_t)row * n + nd.leaf];
+            } else {
+                const double ul = u[nd.left], ur = u[nd.right];
+                const double uj = __dadd_rn(ul, ur);
+                u[node] = uj;
+                y[(size_t)row * (n - 1) + nd.k] = __ddiv_rn(ul, uj);
+                logu[(size_t)row * (n - 1) + nd.k] = log(uj);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// `ladj_i[0] -= log(u_data[j])` for j = 2n-2 .. 0 with a FLOAT accumulator (hsb_ops.cpp:211,234):
+// the rounding sequence is order dependent, so it is replayed serially, one thread per row.
+__global__ void k4_ladj_serial(int64_t B, int64_t nm1, const double *__restrict__ logu, float *__restrict__ ladj) {
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= B) return;
+    float acc = 0.0f;
+    const double *lu = logu + (size_t)row * nm1;
+    for (int64_t k = nm1 - 1; k >= 0; --k) acc = (float)__dsub_rn((double)acc, lu[k]);
+    ladj[row] = acc;
+}
+
+// InvHSBGradOp::Compute  hsb_ops.cpp:338-392 (top-down)
+__global__ void __launch_bounds__(HSB_THREADS)
+    k4_inv_hsb_grad(Sched s, int shared_tree, const TreeNode *__restrict__ nodes_all, int64_t n, int64_t N,
+                    const double *__restrict__ y_grad, const float *__restrict__ ladj_grad,
+                    const double *__restrict__ yv, double *__restrict__ us, double *__restrict__ vs,
+                    float *__restrict__ backprops) {
+    int tree;
+    int64_t row;
+    bin_row(s, shared_tree, tree, row);
+    const TreeNode *nodes = nodes_all + (size_t)tree * N;
+    double *u = us + (size_t)row * N, *v = vs + (size_t)row * N;
+    const double lg = (double)ladj_grad[row];
+    const int l0 = s.bin_lvl_ptr[blockIdx.x], l1 = s.bin_lvl_ptr[blockIdx.x + 1] - 1;
+    for (int l = l0; l < l1; ++l) {
+        for (int q = s.lvl_off[l] + threadIdx.x; q < s.lvl_off[l + 1]; q += HSB_THREADS) {
+            const int node = s.sch_node[q];
+            const TreeNode nd = nodes[node];
+            const double uj = node == 0 ? 1.0 : u[node];
+            const double vj = node == 0 ? 0.0 : v[node];
+            if (nd.leaf >= 0) {
+                backprops[(size_t)row * n + nd.leaf] = (float)vj;
+            } else {
+                const double y = yv[(size_t)row * (n - 1) + nd.k];
+                const double yg = y_grad[(size_t)row * (n - 1) + nd.k];
+                const double u_left = __dmul_rn(uj, y), u_right = __dmul_rn(uj, __dsub_rn(1.0, y));
+                const double dladj_du = __ddiv_rn(-1.0, uj), u_j2 = __dmul_rn(uj, uj);
+                const double base = __dadd_rn(__dmul_rn(dladj_du, lg), vj);
+                v[nd.left] = __dadd_rn(base, __dmul_rn(__ddiv_rn(u_right, u_j2), yg));
+                v[nd.right] = __dsub_rn(base, __dmul_rn(__ddiv_rn(u_left, u_j2), yg));
+                u[nd.left] = u_left;
+                u[nd.right] = u_right;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+cudaError_t up_vec(const std::vector<T> &v, T **d) {
+    *d = nullptr;
+    cudaError_t e = cudaMalloc((void **)d, std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (e == cudaSuccess && !v.empty()) e = cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+struct DevBuf {
+    std::vector<void *> ptrs;
+    ~DevBuf() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t alloc(T **p, size_t count) {
+        cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+    template <typename T>
+    cudaError_t upload(T **p, const T *host, size_t count) {
+        cudaError_t e = alloc(p, count);
+        if (e == cudaSuccess && count) e = cudaMemcpy(*p, host, count * sizeof(T), cudaMemcpyHostToDevice);
+        return e;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+typedef struct polee_hsb_plan polee_hsb_plan;
+
+const char *polee_hsb_last_error(void) {
+    std::lock_guard<std::mutex> lk(g_hsb_mu);
+    return g_hsb_error.c_str();
+}
+
+int polee_hsb_plan_destroy(polee_hsb_plan *p) {
+    if (!p) return POLEE_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->nodes);
+    cudaFree(p->desc_order);
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(p->bin_lvl_ptr[s]); cudaFree(p->lvl_off[s]); cudaFree(p->sch_node[s]); cudaFree(p->bin_tree[s]);
+    }
+    delete p;
+    return POLEE_OK;
+}
+
+int polee_hsb_plan_create(polee_hsb_plan **out, int32_t device, int64_t n, int64_t idx_batch, const int32_t *left,
+                          const int32_t *right, const int32_t *leaf) {
+    if (!out || !left || !right || !leaf || n < 1 || idx_batch < 1) return hsb_fail(POLEE_EINVAL, "hsb plan: bad arguments");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return hsb_fail(POLEE_ECUDA, "no CUDA device (libpolee_b200 has no CPU fallback)");
+    if (device < 0 || device >= count || cudaSetDevice(device) != cudaSuccess) return hsb_fail(POLEE_ECUDA, "cudaSetDevice failed");
+    const int64_t N = 2 * n - 1;
+    std::vector<TreeNode> nodes((size_t)idx_batch * N);
+    std::vector<int32_t> blp[2] = {{0}, {0}}, lo[2], sn[2], bt[2];
+    for (int64_t t = 0; t < idx_batch; ++t) {
+        TreeHost th;
+        std::string e = th.build_from_lrf(n, left + t * N, right + t * N, leaf + t * N, HSB_BIN_NODES);
+        if (!e.empty()) return hsb_fail(POLEE_EBADTREE, "tree " + std::to_string(t) + ": " + e);
+        std::copy(th.nodes.begin(), th.nodes.end(), nodes.begin() + (size_t)t * N);
+        const TreeSchedHost *hs[2] = {&th.top, &th.bottom};
+        for (int s = 0; s < 2; ++s) {
+            const int32_t node_base = (int32_t)sn[s].size(), lvl_base = (int32_t)lo[s].size();
+            sn[s].insert(sn[s].end(), hs[s]->sch_node.begin(), hs[s]->sch_node.end());
+            for (int32_t v : hs[s]->lvl_off) lo[s].push_back(v + node_base);
+            for (int b = 0; b < hs[s]->nbins(); ++b) {
+                blp[s].push_back(hs[s]->bin_lvl_ptr[b + 1] + lvl_base);
+                bt[s].push_back((int32_t)t);
+            }
+        }
+    }
+    polee_hsb_plan *p = new polee_hsb_plan();
+    p->device = device; p->n = n; p->N = N; p->ntrees = idx_batch;
+    cudaError_t e = up_vec(nodes, &p->nodes);
+    for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
+        p->nbins[s] = (int)bt[s].size();
+        e = up_vec(blp[s], &p->bin_lvl_ptr[s]);
+        if (e == cudaSuccess) e = up_vec(lo[s], &p->lvl_off[s]);
+        if (e == cudaSuccess) e = up_vec(sn[s], &p->sch_node[s]);
+        if (e == cudaSuccess) e = up_vec(bt[s], &p->bin_tree[s]);
+    }
+    if (e != cudaSuccess) {
+        polee_hsb_plan_destroy(p);
+        return hsb_fail(POLEE_ECUDA, std::string("hsb plan upload: ") + cudaGetErrorString(e));
+    }
+    *out = p;
+    return POLEE_OK;
+}
+
+#define HCK(expr)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) return hsb_fail(POLEE_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+static int check_plan(const polee_hsb_plan *p, int64_t B) {
+    if (!p || B < 1) return hsb_fail(POLEE_EINVAL, "hsb: bad plan / batch");
+    if (p->ntrees != 1 && p->ntrees != B) return hsb_fail(POLEE_EINVAL, "hsb: idx_batch must be 1 or B");
+    if (cudaSetDevice(p->device) != cudaSuccess) return hsb_fail(POLEE_ECUDA, "cudaSetDevice failed");
+    return POLEE_OK;
+}
+
+static Sched sched_of(const polee_hsb_plan *p, int s) {
+    return Sched{p->bin_lvl_ptr[s], p->lvl_off[s], p->sch_node[s], p->bin_tree[s]};
+}
+
+int polee_hsb_with_plan(const polee_hsb_plan *p, int64_t B, const float *y_logit, float *x) {
+    int rc = check_plan(p, B);
+    if (rc) return rc;
+    const int shared = p->ntrees == 1;
+    DevBuf db;
+    float *d_yl, *d_x;
+    double *d_us;
+    HCK(db.upload(&d_yl, y_logit, (size_t)B * (p->n - 1)));
+    HCK(db.alloc(&d_x, (size_t)B * p->n));
+    HCK(db.alloc(&d_us, (size_t)B * p->N));
+    for (int s = 0; s < 2; ++s)
+        if (p->nbins[s] > 0) {
+            dim3 grid(p->nbins[s], shared ? (unsigned)B : 1u);
+            k4_hsb_fwd<<<grid, HSB_THREADS>>>(sched_of(p, s), shared, p->nodes, p->n, p->N, d_yl, d_us, d_x);
+        }
+    HCK(cudaGetLastError());
+    HCK(cudaMemcpy(x, d_x, sizeof(float) * (size_t)B * p->n, cudaMemcpyDeviceToHost));
+    return POLEE_OK;
+}
+
+int polee_inv_hsb_with_plan(const polee_hsb_plan *p, int64_t B, const float *x, double *y, float *ladj) {
+    int rc = check_plan(p, B);
+    if (rc) return rc;
+    const int shared = p->ntrees == 1;
+    const int64_t nm1 = p->n - 1;
+    DevBuf db;
+    float *d_x, *d_ladj;
+    double *d_us, *d_y, *d_logu;
+    HCK(db.upload(&d_x, x, (size_t)B * p->n));
+    HCK(db.alloc(&d_us, (size_t)B * p->N));
+    HCK(db.alloc(&d_y, (size_t)B * nm1));
+    HCK(db.alloc(&d_logu, (size_t)B * nm1));
+    HCK(db.alloc(&d_ladj, (size_t)B));
+    for (int s = 1; s >= 0; --s)  // bottom bins first, then the top
+        if (p->nbins[s] > 0) {
+            dim3 grid(p->nbins[s], shared ? (unsigned)B : 1u);
+            k4_inv_hsb<<<grid, HSB_THREADS>>>(sched_of(p, s), shared, p->nodes, p->n, p->N, d_x, d_us, d_y, d_logu);
+        }
+    k4_ladj_serial<<<(unsigned)((B + 63) / 64), 64>>>(B, nm1, d_logu, d_ladj);
+    HCK(cudaGetLastError());
+    if (nm1 > 0) HCK(cudaMemcpy(y, d_y, sizeof(double) * (size_t)B * nm1, cudaMemcpyDeviceToHost));
+    HCK(cudaMemcpy(ladj, d_ladj, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost));
+    return POLEE_OK;
+}
+
+int polee_inv_hsb_grad_with_plan(const polee_hsb_plan *p, int64_t B, const double *y_grad, const float *ladj_grad,
+                                 const double *y, float *backprops) {
+    int rc = check_plan(p, B);
+    if (rc) return rc;
+    const int shared = p->ntrees == 1;
+    const int64_t nm1 = p->n - 1;
+    DevBuf db;
+    double *d_yg, *d_y, *d_us, *d_vs;
+    float *d_lg, *d_bp;
+    HCK(db.upload(&d_yg, y_grad, (size_t)B * nm1));
+    HCK(db.upload(&d_y, y, (size_t)B * nm1));
+    HCK(db.upload(&d_lg, ladj_grad, (size_t)B));
+    HCK(db.alloc(&d_us, (size_t)B * p->N));
+    HCK(db.alloc(&d_vs, (size_t)B * p->N));
+    HCK(db.alloc(&d_bp, (size_t)B * p->n));
+    for (int s = 0; s < 2; ++s)
+        if (p->nbins[s] > 0) {
+            dim3 grid(p->nbins[s], shared ? (unsigned)B : 1u);
+            k4_inv_hsb_grad<<<grid, HSB_THREADS>>>(sched_of(p, s), shared, p->nodes, p->n, p->N, d_yg, d_lg, d_y, d_us,
+                                                   d_vs, d_bp);
+        }
+    HCK(cudaGetLastError());
+    HCK(cudaMemcpy(backprops, d_bp, sizeof(float) * (size_t)B * p->n, cudaMemcpyDeviceToHost));
+    return POLEE_OK;
+}
+
+// ---- plan-less forms declared in include/polee_b200.h
+int polee_hsb(int32_t device, int64_t B, int64_t n, const float *y_logit, const int32_t *left, const int32_t *right,
+              const int32_t *leaf, int64_t idx_batch, float *x) {
+    if (idx_batch != 1 && idx_batch != B) return hsb_fail(POLEE_EINVAL, "hsb: idx_batch must be 1 or B");
+    polee_hsb_plan *p = nullptr;
+    int rc = polee_hsb_plan_create(&p, device, n, idx_batch, left, right, leaf);
+    if (!rc) rc = polee_hsb_with_plan(p, B, y_logit, x);
+    polee_hsb_plan_destroy(p);
+    return rc;
+}
+
+int polee_inv_hsb(int32_t device, int64_t B, int64_t n, const float *x, const int32_t *left, const int32_t *right,
+                  const int32_t *leaf, int64_t idx_batch, double *y, float *ladj) {
+    if (idx_batch != 1 && idx_batch != B) return hsb_fail(POLEE_EINVAL, "inv_hsb: idx_batch must be 1 or B");
+    polee_hsb_plan *p = nullptr;
+    int rc = polee_hsb_plan_create(&p, device, n, idx_batch, left, right, leaf);
+    if (!rc) rc = polee_inv_hsb_with_plan(p, B, x, y, ladj);
+    polee_hsb_plan_destroy(p);
+    return rc;
+}
+
+int polee_inv_hsb_grad(int32_t device, int64_t B, int64_t n, const double *y_grad, const float *ladj_grad,
+                       const double *y, const int32_t *left, const int32_t *right, const int32_t *leaf,
+                       int64_t idx_batch, float *backprops) {
+    if (idx_batch != 1 && idx_batch != B) return hsb_fail(POLEE_EINVAL, "inv_hsb_grad: idx_batch must be 1 or B");
+    polee_hsb_plan *p = nullptr;
+    int rc = polee_hsb_plan_create(&p, device, n, idx_batch, left, right, leaf);
+    if (!rc) rc = polee_inv_hsb_grad_with_plan(p, B, y_grad, ladj_grad, y, backprops);
+    polee_hsb_plan_destroy(p);
+    return rc;
+}
+
+// make_inverse_ptt_params  src/ptt.jl:293-309 (pure integer host helper)
+int polee_make_inverse_ptt_params(int64_t num_nodes, const int32_t *node_parent_idxs, const int32_t *node_js,
+                                  int32_t *left_index, int32_t *right_index, int32_t *leaf_index) {
+    if (!node_parent_idxs || !node_js || !left_index || !right_index || !leaf_index || num_nodes < 1) return POLEE_EINVAL;
+    for (int64_t i = 0; i < num_nodes; ++i) left_index[i] = right_index[i] = -1;
+    for (int64_t i = 1; i < num_nodes; ++i) {
+        const int32_t p = node_parent_idxs[i];
+        if (p < 1 || p > num_nodes) return POLEE_EBADTREE;
+        if (right_index[p - 1] == -1)
+            right_index[p - 1] = (int32_t)i;
+        else
+            left_index[p - 1] = (int32_t)i;
+    }
+    for (int64_t i = 0; i < num_nodes; ++i) leaf_index[i] = node_js[i] - 1;
+    return POLEE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+// matrix_setup.cu -- one-time (per fit) conversion of RNASeqSample.X, handed over exactly as Julia
+// stores it (SparseMatrixCSC{Float32,UInt32}: 1-based colptr/rowval, src/rnaseq_sample.jl:11,499), into
+// the two HBM layouts the per-step kernels stream.  Replaces `Xt = SparseMatrixCSC(transpose(X))`
+// (src/likelihood-approximation.jl:407), which the reference does on the host.
+//
+//  K1 layout ("SELL slabs"): rows (fragments) are stably sorted by their entry count, longest class
+//  first, and renumbered; class L is stored as a dense L x stride slab, t-major, so that lane r of a
+//  warp reads entry t of row r with a perfectly coalesced access and all 32 rows of a warp have the
+//  same trip count.  Inside a row the entries keep ascending transcript order -- the order in which
+//  the reference accumulates (src/sparse.jl:14-18).  No row pointer array is streamed at all.
+//
+//  K2 layout: the CSC arrays with row ids replaced by the permuted ids and each column re-sorted by
+//  permuted row id, so that consecutive lanes of a warp gather neighbouring rows of w.  Columns are cut
+//  into segments of <= COL_SEG entries (one warp each).
+//
+// The sorts use CUB's device radix sort (a library call, but setup only -- not on the per-step path).
+#include <algorithm>
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace polee {
+
+namespace {
+
+__global__ void k_count_rows(const uint32_t *__restrict__ rowval, int64_t nnz, uint32_t *row_len, int64_t m,
+                             int *bad) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t r = rowval[e] - 1u;
+        if (r >= (uint64_t)m)
+            *bad = 1;
+        else
+            atomicAdd(&row_len[r], 1u);
+    }
+}
+
+__global__ void k_make_len_keys(const uint32_t *__restrict__ row_len, int64_t m, uint32_t lmax, uint32_t *keys,
+                                uint32_t *vals) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        keys[i] = lmax - row_len[i];
+        vals[i] = (uint32_t)i;
+    }
+}
+
+// position in the length-sorted order -> permuted (class-padded) row id
+__global__ void k_assign_perm(const uint32_t *__restrict__ sorted_rows, const uint32_t *__restrict__ row_len,
+                              int64_t m, const uint32_t *__restrict__ cls_row_off_pad,
+                              const uint32_t *__restrict__ cls_row_off_unpad, uint32_t *row_perm, uint32_t *len_perm) {
+    for (int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pos < m;
+         pos += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t i = sorted_rows[pos];
+        uint32_t L = row_len[i];
+        uint32_t rp = cls_row_off_pad[L] + (uint32_t)(pos - cls_row_off_unpad[L]);
+        row_perm[i] = rp;
+        len_perm[rp] = L;
+    }
+}
+
+__global__ void k_entry_keys(const uint32_t *__restrict__ colptr, int64_t n, const uint32_t *__restrict__ rowval,
+                             int64_t nnz, const uint32_t *__restrict__ row_perm, uint32_t *col_of, uint32_t *key_r,
+                             uint32_t *val_e) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        // largest j with colptr[j] - 1 <= e
+        int64_t lo = 0, hi = n;  // invariant: colptr[lo]-1 <= e < colptr[hi]-1
+        while (hi - lo > 1) {
+            int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)colptr[mid] - 1 <= e)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        col_of[e] = (uint32_t)lo;
+        key_r[e] = row_perm[rowval[e] - 1u];
+        val_e[e] = (uint32_t)e;
+    }
+}
+
+__global__ void k_row_starts(const uint32_t *__restrict__ sorted_r, int64_t nnz, uint32_t *row_start) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
+        if (q == 0 || sorted_r[q] != sorted_r[q - 1]) row_start[sorted_r[q]] = (uint32_t)q;
+    }
+}
+
+__global__ void k_fill_sell(const uint32_t *__restrict__ sorted_r, const uint32_t *__restrict__ sorted_e, int64_t nnz,
+                            const uint32_t *__restrict__ row_start, const uint32_t *__restrict__ len_perm,
+                            const uint32_t *__restrict__ cls_row_off_pad, const uint64_t *__restrict__ cls_slab_off,
+                            const uint32_t *__restrict__ cls_stride, const uint32_t *__restrict__ col_of,
+                            const float *__restrict__ nzval, uint32_t *sell_idx, float *sell_val, uint32_t *key_c,
+                            uint32_t *val_q) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t rp = sorted_r[q], e = sorted_e[q];
+        uint32_t L = len_perm[rp];
+        uint32_t t = (uint32_t)q - row_start[rp];
+        uint64_t pos = cls_slab_off[L] + (uint64_t)t * cls_stride[L] + (rp - cls_row_off_pad[L]);
+        uint32_t c = col_of[e];
+        sell_idx[pos] = c;
+        sell_val[pos] = nzval[e];
+        key_c[q] = c;
+        val_q[q] = (uint32_t)q;
+    }
+}
+
+__global__ void k_fill_csc(const uint32_t *__restrict__ order_q, int64_t nnz, const uint32_t *__restrict__ sorted_r,
+                           const uint32_t *__restrict__ sorted_e, const float *__restrict__ nzval, uint32_t *csc_row,
+                           float *csc_val) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t q = order_q[p];
+        csc_row[p] = sorted_r[q];
+        csc_val[p] = nzval[sorted_e[q]];
+    }
+}
+
+__global__ void k_row_weights(const int64_t *__restrict__ ks, int64_t m, const uint32_t *__restrict__ row_perm,
+                              float *row_weight) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+        row_weight[row_perm[i]] = (float)ks[i];
+}
+
+int bits_for(uint64_t maxval) {
+    int b = 1;
+    while (b < 32 && (maxval >> b) != 0) ++b;
+    return b;
+}
+
+struct Scratch {
+    std::vector<void *> ptrs;
+    ~Scratch() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t alloc(T **p, size_t count) {
+        cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+
+}  // namespace
+
+void release_matrix(polee_handle *h) {
+    cudaFree(h->sell_idx); cudaFree(h->sell_val); cudaFree(h->row_tiles); cudaFree(h->row_perm);
+    cudaFree(h->row_weight); cudaFree(h->csc_row); cudaFree(h->csc_val); cudaFree(h->segs); cudaFree(h->multi);
+    h->sell_idx = nullptr; h->sell_val = nullptr; h->row_tiles = nullptr; h->row_perm = nullptr;
+    h->row_weight = nullptr; h->csc_row = nullptr; h->csc_val = nullptr; h->segs = nullptr; h->multi = nullptr;
+    h->have_matrix = false;
+}
+
+#define CK(expr) POLEE_CUDA_CHECK(h, expr)
+
+int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const uint32_t *d_colptr,
+                                 const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
+                                 const uint32_t *h_colptr_or_null) {
+    release_matrix(h);
+    if (m < 1 || n < 1) return h->fail(POLEE_EINVAL, "set_matrix: m and n must be >= 1");
+    if (m >= (int64_t)0xFFFFFF00u) return h->fail(POLEE_EINVAL, "set_matrix: m exceeds UInt32 row ids");
+    cudaStream_t st = h->stream;
+    std::vector<uint32_t> colptr(n + 1);
+    if (h_colptr_or_null)
+        std::copy(h_colptr_or_null, h_colptr_or_null + n + 1, colptr.begin());
+    else
+        CK(cudaMemcpy(colptr.data(), d_colptr, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost));
+    if (colptr[0] != 1) return h->fail(POLEE_EINVAL, "set_matrix: colptr must be 1-based (colptr[1] == 1)");
+    for (int64_t j = 0; j < n; ++j)
+        if (colptr[j + 1] < colptr[j]) return h->fail(POLEE_EINVAL, "set_matrix: colptr is not non-decreasing");
+    const int64_t nnz = (int64_t)colptr[n] - 1;
+    h->m = m; h->n = n; h->nnz = nnz;
+
+    const int TPB = 256;
+    auto grid_for = [&](int64_t work) { return (int)std::min<int64_t>((work + TPB - 1) / TPB, (int64_t)h->num_sms * 32); };
+
+    Scratch sc;
+    uint32_t *row_len, *keys_a, *keys_b, *vals_a, *vals_b;
+    int *d_bad;
+    CK(sc.alloc(&row_len, m));
+    CK(sc.alloc(&d_bad, 1));
+    CK(cudaMemsetAsync(row_len, 0, sizeof(uint32_t) * m, st));
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    if (nnz > 0) k_count_rows<<<grid_for(nnz), TPB, 0, st>>>(d_rowval, nnz, row_len, m, d_bad);
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+
+    // ---- row length classes
+    uint32_t *d_lmax;
+    CK(sc.alloc(&d_lmax, 1));
+    size_t tmp_bytes = 0;
+    void *d_tmp = nullptr;
+    CK(cub::DeviceReduce::Max(nullptr, tmp_bytes, row_len, d_lmax, (int)m, st));
+    CK(sc.alloc((char **)&d_tmp, tmp_bytes));
+    CK(cub::DeviceReduce::Max(d_tmp, tmp_bytes, row_len, d_lmax, (int)m, st));
+    uint32_t lmax = 0;
+    CK(cudaMemcpyAsync(&lmax, d_lmax, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (bad) return h->fail(POLEE_EINVAL, "set_matrix: rowval out of range 1..m");
+
+    int *d_hist;
+    CK(sc.alloc(&d_hist, (size_t)lmax + 1));
+    {
+        size_t hb = 0;
+        void *ht = nullptr;
+        CK(cub::DeviceHistogram::HistogramEven(nullptr, hb, row_len, d_hist, (int)lmax + 2, 0u, lmax + 1u, (int)m, st));
+        CK(sc.alloc((char **)&ht, hb));
+        CK(cub::DeviceHistogram::HistogramEven(ht, hb, row_len, d_hist, (int)lmax + 2, 0u, lmax + 1u, (int)m, st));
+    }
+    std::vector<int> hist(lmax + 1);
+    CK(cudaMemcpyAsync(hist.data(), d_hist, sizeof(int) * (lmax + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+
+    // classes in descending length; each padded to a multiple of 32 rows (one warp = one class)
+    std::vector<uint32_t> cls_row_off_pad(lmax + 1, 0), cls_row_off_unpad(lmax + 1, 0), cls_stride(lmax + 1, 0);
+    std::vector<uint64_t> cls_slab_off(lmax + 1, 0);
+    std::vector<RowTile> tiles;
+    uint64_t rows_pad = 0, rows_unpad = 0, slab = 0;
+    for (int64_t L = lmax; L >= 0; --L) {
+        uint32_t cnt = (uint32_t)hist[L];
+        uint32_t stride = L > 0 ? (cnt + 31u) & ~31u : cnt;
+        cls_row_off_pad[L] = (uint32_t)rows_pad;
+        cls_row_off_unpad[L] = (uint32_t)rows_unpad;
+        cls_stride[L] = stride;
+        cls_slab_off[L] = slab;
+        if (L > 0)
+            for (uint32_t r0 = 0; r0 < cnt; r0 += ROW_TILE) {
+                RowTile t;
+                t.slab_off = slab + r0;
+                t.stride = stride;
+                t.len = (uint32_t)L;
+                t.row0 = (uint32_t)rows_pad + r0;
+                t.nrows = std::min<uint32_t>(ROW_TILE, cnt - r0);
+                tiles.push_back(t);
+            }
+        rows_pad += stride;
+        rows_unpad += cnt;
+        slab += (uint64_t)L * stride;
+    }
+    if (rows_pad >= 0xFFFFFFFFull) return h->fail(POLEE_EINVAL, "set_matrix: too many rows");
+    h->m_pad = (int64_t)rows_pad;
+    h->sell_elems = (int64_t)slab;
+
+    uint32_t *d_cls_pad, *d_cls_unpad, *d_cls_stride;
+    uint64_t *d_cls_slab;
+    CK(sc.alloc(&d_cls_pad, lmax + 1)); CK(sc.alloc(&d_cls_unpad, lmax + 1));
+    CK(sc.alloc(&d_cls_stride, lmax + 1)); CK(sc.alloc(&d_cls_slab, lmax + 1));
+    CK(cudaMemcpyAsync(d_cls_pad, cls_row_off_pad.data(), 4 * (lmax + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cls_unpad, cls_row_off_unpad.data(), 4 * (lmax + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cls_stride, cls_stride.data(), 4 * (lmax + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cls_slab, cls_slab_off.data(), 8 * (lmax + 1), cudaMemcpyHostToDevice, st));
+
+    // ---- stable sort of rows by descending length -> permutation
+    const int64_t big = std::max<int64_t>(m, nnz);
+    CK(sc.alloc(&keys_a, big)); CK(sc.alloc(&keys_b, big)); CK(sc.alloc(&vals_a, big)); CK(sc.alloc(&vals_b, big));
+    k_make_len_keys<<<grid_for(m), TPB, 0, st>>>(row_len, m, lmax, keys_a, vals_a);
+    size_t sort_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_a, keys_b, vals_a, vals_b, (int)big, 0, 32, st));
+    void *d_sort = nullptr;
+    CK(sc.alloc((char **)&d_sort, sort_bytes));
+    CK(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, keys_a, keys_b, vals_a, vals_b, (int)m, 0, bits_for(lmax), st));
+
+    CK(cudaMalloc((void **)&h->row_perm, sizeof(uint32_t) * m));
+    uint32_t *len_perm, *row_start;
+    CK(sc.alloc(&len_perm, rows_pad)); CK(sc.alloc(&row_start, rows_pad));
+    CK(cudaMemsetAsync(len_perm, 0, sizeof(uint32_t) * std::max<uint64_t>(rows_pad, 1), st));
+    k_assign_perm<<<grid_for(m), TPB, 0, st>>>(vals_b, row_len, m, d_cls_pad, d_cls_unpad, h->row_perm, len_perm);
+
+    // ---- entries: sort by permuted row (stable from CSC order => ascending column inside a row)
+    uint32_t *col_of;
+    CK(sc.alloc(&col_of, nnz));
+    uint32_t *d_colptr_own = nullptr;
+    if (!d_colptr) {
+        CK(sc.alloc(&d_colptr_own, n + 1));
+        CK(cudaMemcpyAsync(d_colptr_own, colptr.data(), 4 * (n + 1), cudaMemcpyHostToDevice, st));
+        d_colptr = d_colptr_own;
+    }
+    CK(cudaMalloc((void **)&h->sell_idx, sizeof(uint32_t) * std::max<uint64_t>(slab, 1)));
+    CK(cudaMalloc((void **)&h->sell_val, sizeof(float) * std::max<uint64_t>(slab, 1)));
+    CK(cudaMemsetAsync(h->sell_idx, 0, sizeof(uint32_t) * std::max<uint64_t>(slab, 1), st));
+    CK(cudaMemsetAsync(h->sell_val, 0, sizeof(float) * std::max<uint64_t>(slab, 1), st));
+    CK(cudaMalloc((void **)&h->csc_row, sizeof(uint32_t) * std::max<int64_t>(nnz, 1)));
+    CK(cudaMalloc((void **)&h->csc_val, sizeof(float) * std::max<int64_t>(nnz, 1)));
+    if (nnz > 0) {
+        k_entry_keys<<<grid_for(nnz), TPB, 0, st>>>(d_colptr, n, d_rowval, nnz, h->row_perm, col_of, keys_a, vals_a);
+        CK(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, keys_a, keys_b, vals_a, vals_b, (int)nnz, 0,
+                                           bits_for(rows_pad), st));
+        // keys_b = sorted permuted rows, vals_b = entry ids
+        k_row_starts<<<grid_for(nnz), TPB, 0, st>>>(keys_b, nnz, row_start);
+        // reuse keys_a / vals_a for the column sort
+        k_fill_sell<<<grid_for(nnz), TPB, 0, st>>>(keys_b, vals_b, nnz, row_start, len_perm, d_cls_pad, d_cls_slab,
+                                                    d_cls_stride, col_of, d_nzval, h->sell_idx, h->sell_val, keys_a,
+                                                    vals_a);
+        // stable sort by column of the (row', col)-ordered list -> (col, row') order
+        uint32_t *keys_c, *vals_c;
+        CK(sc.alloc(&keys_c, nnz)); CK(sc.alloc(&vals_c, nnz));
+        CK(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, keys_a, keys_c, vals_a, vals_c, (int)nnz, 0,
+                                           bits_for((uint64_t)n), st));
+        k_fill_csc<<<grid_for(nnz), TPB, 0, st>>>(vals_c, nnz, keys_b, vals_b, d_nzval, h->csc_row, h->csc_val);
+    }
+    if (d_ks) {
+        CK(cudaMalloc((void **)&h->row_weight, sizeof(float) * std::max<uint64_t>(rows_pad, 1)));
+        CK(cudaMemsetAsync(h->row_weight, 0, sizeof(float) * std::max<uint64_t>(rows_pad, 1), st));
+        k_row_weights<<<grid_for(m), TPB, 0, st>>>(d_ks, m, h->row_perm, h->row_weight);
+    }
+
+    // ---- K1 tiles, K2 segments
+    h->n_row_tiles = (int)tiles.size();
+    CK(cudaMalloc((void **)&h->row_tiles, sizeof(RowTile) * std::max<size_t>(tiles.size(), 1)));
+    if (!tiles.empty())
+        CK(cudaMemcpyAsync(h->row_tiles, tiles.data(), sizeof(RowTile) * tiles.size(), cudaMemcpyHostToDevice, st));
+
+    std::vector<ColSeg> segs;
+    std::vector<MultiCol> multi;
+    segs.reserve((size_t)(nnz / COL_SEG + n));
+    uint32_t slots = 0;
+    for (int64_t j = 0; j < n; ++j) {
+        uint32_t s = colptr[j] - 1, len = colptr[j + 1] - colptr[j];
+        uint32_t ns = len == 0 ? 1 : (len + COL_SEG - 1) / COL_SEG;
+        if (ns > 1) multi.push_back(MultiCol{(uint32_t)j, slots, ns, 0});
+        for (uint32_t q = 0; q < ns; ++q) {
+            ColSeg sg;
+            sg.start = s + q * COL_SEG;
+            sg.len = std::min<uint32_t>(COL_SEG, len - q * COL_SEG);
+            sg.col = (uint32_t)j;
+            sg.slot = ns > 1 ? (int32_t)(slots + q) : -1;
+            segs.push_back(sg);
+        }
+        if (ns > 1) slots += ns;
+    }
+    h->n_segs = (int)segs.size();
+    h->n_multi = (int)multi.size();
+    h->n_slots = (int)slots;
+    CK(cudaMalloc((void **)&h->segs, sizeof(ColSeg) * std::max<size_t>(segs.size(), 1)));
+    CK(cudaMemcpyAsync(h->segs, segs.data(), sizeof(ColSeg) * segs.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMalloc((void **)&h->multi, sizeof(MultiCol) * std::max<size_t>(multi.size(), 1)));
+    if (!multi.empty())
+        CK(cudaMemcpyAsync(h->multi, multi.data(), sizeof(MultiCol) * multi.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    h->have_matrix = true;
+    return POLEE_OK;
+}
+
+}  // namespace polee

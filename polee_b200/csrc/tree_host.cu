@@ -1,0 +1,218 @@
+// tree_host.cu -- host-side preparation of a Polya tree for the level-synchronous device kernels.
+//
+// The tree itself is built by the reference's Julia code (hclust -> order_nodes, src/hclust.jl:193-389;
+// stays on the host by north_star) and arrives as (node_parent_idxs, node_js)
+// (src/likelihood-approximation.jl:618-621) or as the 0-based left/right/leaf arrays of
+// make_inverse_ptt_params (src/ptt.jl:293-309).  Here it is validated, converted to 0-based child
+// pointers with the reference's rule (first child seen = RIGHT child, src/ptt.jl:104-110) and cut
+// into a level-ordered schedule:
+//   * "bottom" bins: forests of whole subtrees with <= bin_nodes nodes in total, one CTA each;
+//   * "top": the nodes whose subtree is larger than bin_nodes, one CTA.
+// Every node's arithmetic depends only on its parent (forward) or its two children (backward), so a
+// level-synchronous sweep computes bit-identical values to the reference's serial index-order sweep.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace polee {
+
+int pad_k(int K) {
+    int p = 1;
+    while (p < K) p <<= 1;
+    return p;
+}
+
+static void make_sched(const std::vector<std::vector<int32_t>> &bins_nodes, const std::vector<int32_t> &level_of,
+                       TreeSchedHost &out, int &max_levels) {
+    out.bin_lvl_ptr.assign(1, 0);
+    out.lvl_off.clear();
+    out.sch_node.clear();
+    max_levels = 0;
+    for (const auto &bn : bins_nodes) {
+        int nl = 0;
+        for (int32_t v : bn) nl = std::max(nl, level_of[v] + 1);
+        std::vector<int32_t> cnt(nl + 1, 0);
+        for (int32_t v : bn) cnt[level_of[v] + 1]++;
+        for (int l = 0; l < nl; ++l) cnt[l + 1] += cnt[l];
+        int32_t base = (int32_t)out.sch_node.size();
+        out.sch_node.resize(base + bn.size());
+        std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1);
+        for (int32_t v : bn) out.sch_node[base + cur[level_of[v]]++] = v;
+        for (int l = 0; l <= nl; ++l) out.lvl_off.push_back(base + cnt[l]);
+        out.bin_lvl_ptr.push_back((int32_t)out.lvl_off.size());
+        max_levels = std::max(max_levels, nl);
+    }
+}
+
+std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int32_t *right, const int32_t *leaf,
+                                     int bin_nodes) {
+    n = n_;
+    N = 2 * n - 1;
+    if (n < 1) return "tree: n must be >= 1";
+    nodes.assign(N, TreeNode{-1, -1, -1, -1});
+    parent.assign(N, -1);
+    depth.assign(N, 0);
+    size.assign(N, 1);
+    std::vector<char> seen_leaf(n, 0);
+    int32_t k = 0;
+    int64_t nleaves = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        if (leaf[i] >= 0) {
+            if (leaf[i] >= n || seen_leaf[leaf[i]]) return "tree: leaf ids are not a permutation of 1..n";
+            seen_leaf[leaf[i]] = 1;
+            nodes[i].leaf = leaf[i];
+            ++nleaves;
+            if (left[i] >= 0 || right[i] >= 0) return "tree: leaf node has children";
+        } else {
+            int32_t l = left[i], r = right[i];
+            if (l < 0 || r < 0 || l >= N || r >= N || l == r) return "tree: internal node without two children";
+            if (l <= i || r <= i) return "tree: child index must be greater than its parent's (DFS order)";
+            if (parent[l] != -1 || parent[r] != -1) return "tree: node has two parents";
+            parent[l] = parent[r] = (int32_t)i;
+            nodes[i].left = l;
+            nodes[i].right = r;
+            nodes[i].k = k++;
+        }
+    }
+    if (nleaves != n || k != n - 1) return "tree: expected n leaves and n-1 internal nodes";
+    for (int64_t i = 1; i < N; ++i)
+        if (parent[i] < 0) return "tree: more than one root";
+    max_depth = 0;
+    for (int64_t i = 1; i < N; ++i) {
+        depth[i] = depth[parent[i]] + 1;
+        max_depth = std::max(max_depth, (int)depth[i]);
+    }
+    for (int64_t i = N - 1; i >= 1; --i) size[parent[i]] += size[i];
+
+    // ---- cut: top = nodes whose subtree exceeds bin_nodes
+    std::vector<char> is_top(N, 0);
+    std::vector<int32_t> top_list;
+    for (int64_t i = 0; i < N; ++i)
+        if (size[i] > bin_nodes) {
+            is_top[i] = 1;
+            top_list.push_back((int32_t)i);
+        }
+    top_nodes = (int)top_list.size();
+
+    std::vector<int32_t> level_of(N, 0);
+    std::vector<std::vector<int32_t>> bins;
+    int64_t cur_fill = 0;
+    std::vector<int32_t> stack;
+    for (int64_t r = 0; r < N; ++r) {
+        if (is_top[r] || (parent[r] >= 0 && !is_top[parent[r]])) continue;  // r is a bottom root
+        if (bins.empty() || cur_fill + size[r] > bin_nodes) {
+            bins.emplace_back();
+            cur_fill = 0;
+        }
+        cur_fill += size[r];
+        stack.assign(1, (int32_t)r);
+        while (!stack.empty()) {
+            int32_t v = stack.back();
+            stack.pop_back();
+            level_of[v] = depth[v] - depth[r];
+            bins.back().push_back(v);
+            if (nodes[v].leaf < 0) {
+                stack.push_back(nodes[v].left);
+                stack.push_back(nodes[v].right);
+            }
+        }
+    }
+    int ml = 0;
+    make_sched(bins, level_of, bottom, ml);
+    std::vector<std::vector<int32_t>> tb;
+    if (!top_list.empty()) {
+        tb.push_back(top_list);
+        for (int32_t v : top_list) level_of[v] = depth[v];
+    }
+    make_sched(tb, level_of, top, ml);
+    return "";
+}
+
+std::string TreeHost::build_from_parents(int64_t n_, const int32_t *parent_idxs, const int32_t *js, int bin_nodes) {
+    int64_t NN = 2 * n_ - 1;
+    if (n_ < 1) return "tree: n must be >= 1";
+    std::vector<int32_t> l(NN, -1), r(NN, -1), f(NN, -1);
+    // src/ptt.jl:89-116 (== make_inverse_ptt_params, src/ptt.jl:293-309): first child seen is the right one
+    if (parent_idxs[0] != 0) return "tree: node 1 must be the root (parent index 0)";
+    for (int64_t i = 0; i < NN; ++i) {
+        int32_t p = parent_idxs[i];
+        if (i > 0) {
+            if (p < 1 || p > NN) return "tree: parent index out of range";
+            if (p - 1 >= i) return "tree: parent index must be smaller than the node's own index";
+            if (r[p - 1] == -1)
+                r[p - 1] = (int32_t)i;
+            else if (l[p - 1] == -1)
+                l[p - 1] = (int32_t)i;
+            else
+                return "tree: node with more than two children";
+        }
+        if (js[i] < 0 || js[i] > n_) return "tree: node_js out of range";
+        f[i] = js[i] - 1;
+    }
+    return build_from_lrf(n_, l.data(), r.data(), f.data(), bin_nodes);
+}
+
+// inverse_transform!(t, fill(1.0f0/n, n), ys); map!(logit, mu, ys)   likelihood-approximation.jl:451-453
+// (us = Float64 sums of Float64(1f0/n) in the reference's bottom-up order, ptt.jl:257-285)
+void TreeHost::initial_mu(std::vector<float> &mu) const {
+    std::vector<double> us(N);
+    mu.assign(n > 1 ? n - 1 : 0, 0.0f);
+    const double leafv = (double)(1.0f / (float)n);
+    for (int64_t i = N - 1; i >= 0; --i) {
+        const TreeNode &nd = nodes[i];
+        if (nd.leaf >= 0) {
+            us[i] = leafv;
+        } else {
+            us[i] = us[nd.left] + us[nd.right];
+            double y = us[nd.left] / us[i];
+            mu[nd.k] = (float)std::log(y / (1.0 - y));
+        }
+    }
+}
+
+void TreeDev::release() {
+    cudaFree(nodes);
+    for (TreeSchedDev *s : {&top, &bottom}) {
+        cudaFree(s->bin_lvl_ptr);
+        cudaFree(s->lvl_off);
+        cudaFree(s->sch_node);
+        *s = TreeSchedDev();
+    }
+    nodes = nullptr;
+    n = N = 0;
+}
+
+static cudaError_t up(const std::vector<int32_t> &v, int32_t **d) {
+    *d = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(int32_t);
+    cudaError_t e = cudaMalloc((void **)d, bytes);
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpy(*d, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    return e;
+}
+
+std::string upload_tree(const TreeHost &th, TreeDev &td) {
+    td.release();
+    td.n = th.n;
+    td.N = th.N;
+    cudaError_t e = cudaMalloc((void **)&td.nodes, sizeof(TreeNode) * th.N);
+    if (e == cudaSuccess) e = cudaMemcpy(td.nodes, th.nodes.data(), sizeof(TreeNode) * th.N, cudaMemcpyHostToDevice);
+    const TreeSchedHost *hs[2] = {&th.top, &th.bottom};
+    TreeSchedDev *ds[2] = {&td.top, &td.bottom};
+    for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
+        e = up(hs[s]->bin_lvl_ptr, &ds[s]->bin_lvl_ptr);
+        if (e == cudaSuccess) e = up(hs[s]->lvl_off, &ds[s]->lvl_off);
+        if (e == cudaSuccess) e = up(hs[s]->sch_node, &ds[s]->sch_node);
+        ds[s]->nbins = hs[s]->nbins();
+        int ml = 0;
+        for (int b = 0; b < hs[s]->nbins(); ++b)
+            ml = std::max(ml, hs[s]->bin_lvl_ptr[b + 1] - hs[s]->bin_lvl_ptr[b] - 1);
+        ds[s]->max_levels = ml;
+    }
+    if (e != cudaSuccess) return std::string("upload_tree: ") + cudaGetErrorString(e);
+    return "";
+}
+
+}  // namespace polee

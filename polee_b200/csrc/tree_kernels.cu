@@ -1,0 +1,472 @@
+// tree_kernels.cu -- K3: reparameterisation, Polya-tree (hierarchical stick breaking) transform,
+// its backward pass with the log-Jacobian term, and the ADAM update, for KP draws at once.
+//
+//   k3_reparam_fwd   zs0 -> zs -> ys          sinh_asinh_transform! + logit_normal_transform! + clamp!
+//                                             (src/sinh_arcsinh.jl:10-23, src/logitnormal.jl:8-20,
+//                                              src/likelihood-approximation.jl:517-523)
+//   k3_tree_fwd      ys -> us -> xs           transform! + clamp!   (src/ptt.jl:125-160, l-a.jl:525-526)
+//   k3_mid           S_k = sum_j x_jk/efflen_j, step bookkeeping    (src/likelihood.jl:96-100)
+//   k3_tree_bwd      x_grad -> y_grad         effective_length_jacobian_adjustment! (likelihood.jl:104-106)
+//                                             + transform_gradients! (src/ptt.jl:167-209 / :217-251)
+//   k3_update        y_grad -> mu/omega/alpha grads (logitnormal.jl:38-55, sinh_arcsinh.jl:29-38,
+//                    l-a.jl:547-558) + adam_update_mv!/adam_update_params! (l-a.jl:116-146)
+//
+// The tree passes are level-synchronous inside one CTA per schedule bin (tree_host.cu): a node's
+// value depends only on its parent (forward) or its two children (backward), so the results are
+// bit-identical to the reference's serial sweeps -- the same IEEE operations in the same association,
+// with explicit _rn intrinsics so that nothing is contracted into an FMA the reference does not have.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace polee {
+
+namespace {
+
+constexpr int TREE_THREADS = 256;
+constexpr int TOP_THREADS = 1024;
+
+// ---------------------------------------------------------------- noise ("polee-philox-v1")
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+// one standard normal for (node i, draw d, step s): counter (i, d, s, 0), key = seed, Box-Muller cos branch
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t i, uint32_t d, uint32_t s) {
+    uint32_t c[4] = {i, d, s, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float r = sqrtf(-2.0f * logf(u1));
+    return r * cosf(6.28318530717958647692f * u2);
+}
+
+// deterministic block reduction of one double per thread laid out [slot][KP] (k fastest)
+template <int KP, int THREADS>
+__device__ __forceinline__ void block_reduce_k(double v, double *sm, double *out /* [KP] */) {
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int span = THREADS / KP / 2; span >= 1; span >>= 1) {
+        if ((int)threadIdx.x < span * KP) sm[threadIdx.x] += sm[threadIdx.x + span * KP];
+        __syncthreads();
+    }
+    if (threadIdx.x < KP) out[threadIdx.x] = sm[threadIdx.x];
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- reparameterisation forward
+// mode 0: logit skew normal (mu, omega, alpha + noise); mode 1: OptimizePTTApprox (ys = logistic(zs), no clamp)
+template <int KP>
+__global__ void __launch_bounds__(256)
+    k3_reparam_fwd(int64_t nm1, int K, int mode, const float *__restrict__ mu, const float *__restrict__ omega,
+                   const float *__restrict__ alpha, const float *__restrict__ noise, int64_t noise_steps,
+                   const StepCtl *__restrict__ ctl, uint64_t seed, float *__restrict__ zs0_out,
+                   float *__restrict__ zs_out, double *__restrict__ ys_out, int want_ladj,
+                   double *__restrict__ ladj_partial /* [2][gridDim.x][KP] or null */) {
+    __shared__ double sm[256];
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i = idx / KP;
+    const int k = (int)(idx % KP);
+    double l_skew = 0.0, l_ln = 0.0;
+    if (i < nm1) {
+        if (mode == 1) {
+            float e = expf(-mu[i]);
+            float y32 = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+            ys_out[idx] = (double)y32;
+            zs0_out[idx] = 0.0f;
+            zs_out[idx] = 0.0f;
+        } else {
+            const int step0 = ctl->step_fwd - 1;
+            float z0 = 0.0f;
+            if (k < K) {
+                if (noise)
+                    z0 = noise[((size_t)(step0 % noise_steps) * K + k) * (size_t)nm1 + i];
+                else
+                    z0 = philox_normal(seed, (uint32_t)i, (uint32_t)k, (uint32_t)step0);
+            }
+            const float sigma = expf(omega[i]);
+            const float c = __fadd_rn(alpha[i], asinhf(z0));
+            const float z = sinhf(c);
+            const float xx = __fadd_rn(mu[i], __fmul_rn(z, sigma));
+            const float e = expf(-xx);
+            const float y32 = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+            double y = (double)y32;
+            if (want_ladj && k < K) {
+                l_skew = (double)logf(coshf(c)) - 0.5 * (double)log1pf(__fmul_rn(z0, z0));
+                l_ln = log(__dmul_rn(__dmul_rn((double)sigma, y), __dsub_rn(1.0, y)));
+            }
+            y = fmin(fmax(y, 1e-10), 1.0 - 1e-10);
+            zs0_out[idx] = z0;
+            zs_out[idx] = z;
+            ys_out[idx] = y;
+        }
+    }
+    if (want_ladj) {
+        block_reduce_k<KP, 256>(l_skew, sm, ladj_partial + (size_t)blockIdx.x * KP);
+        block_reduce_k<KP, 256>(l_ln, sm, ladj_partial + ((size_t)gridDim.x + blockIdx.x) * KP);
+    }
+}
+
+// ---------------------------------------------------------------- tree forward
+template <int KP, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    k3_tree_fwd(const int32_t *__restrict__ bin_lvl_ptr, const int32_t *__restrict__ lvl_off,
+                const int32_t *__restrict__ sch_node, const TreeNode *__restrict__ nodes,
+                const double *__restrict__ ys, double *__restrict__ us, float *__restrict__ x, int clamp_x,
+                const float *__restrict__ efflen, double *__restrict__ S_partial, int part_base, int want_ladj,
+                double *__restrict__ ladj_partial) {
+    __shared__ double sm[THREADS];
+    const int k = threadIdx.x % KP, slot = threadIdx.x / KP;
+    constexpr int NPP = THREADS / KP;
+    const int l0 = bin_lvl_ptr[blockIdx.x], l1 = bin_lvl_ptr[blockIdx.x + 1] - 1;  // levels l0..l1-1
+    double sacc = 0.0, lacc = 0.0;
+    for (int l = l0; l < l1; ++l) {
+        const int lo = lvl_off[l], hi = lvl_off[l + 1];
+        for (int q = lo + slot; q < hi; q += NPP) {
+            const int node = sch_node[q];
+            const TreeNode nd = nodes[node];
+            const double ui = node == 0 ? 1.0 : us[(size_t)node * KP + k];
+            if (nd.leaf >= 0) {
+                float xv = (float)ui;
+                double d = (double)xv;
+                xv = (float)(d > 1e-16 ? d : 1e-16);  // ptt.jl:136-137
+                if (clamp_x) {                         // clamp!(xs, 1e-10, 1 - 1e-10) on a Float32 vector
+                    d = (double)xv;
+                    d = fmin(fmax(d, 1e-10), 1.0 - 1e-10);
+                    xv = (float)d;
+                }
+                x[(size_t)nd.leaf * KP + k] = xv;
+                if (efflen) sacc = __dadd_rn(sacc, (double)__fdiv_rn(xv, efflen[nd.leaf]));
+            } else {
+                const double y = ys[(size_t)nd.k * KP + k];
+                if (node == 0) us[k] = 1.0;
+                us[(size_t)nd.left * KP + k] = __dmul_rn(y, ui);
+                us[(size_t)nd.right * KP + k] = __dmul_rn(__dsub_rn(1.0, y), ui);
+                if (want_ladj) lacc += log(ui);
+            }
+        }
+        __syncthreads();
+    }
+    if (S_partial) block_reduce_k<KP, THREADS>(sacc, sm, S_partial + (size_t)(part_base + blockIdx.x) * KP);
+    if (want_ladj) block_reduce_k<KP, THREADS>(lacc, sm, ladj_partial + (size_t)(part_base + blockIdx.x) * KP);
+}
+
+// ---------------------------------------------------------------- mid-step: S reduction + step bookkeeping
+__global__ void __launch_bounds__(1024)
+    k3_mid(const double *__restrict__ S_partial, int count, int KP, double *__restrict__ S, StepCtl *ctl, int advance) {
+    __shared__ double sm[1024];
+    const int k = threadIdx.x % KP, lane_t = threadIdx.x / KP, per = 1024 / KP;
+    double s = 0.0;
+    for (int t = lane_t; t < count; t += per) s += S_partial[(size_t)t * KP + k];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int span = per / 2; span >= 1; span >>= 1) {
+        if (lane_t < span) sm[threadIdx.x] += sm[threadIdx.x + span * KP];
+        __syncthreads();
+    }
+    if (threadIdx.x < KP) S[threadIdx.x] = sm[threadIdx.x];
+    if (advance && threadIdx.x == 0) {
+        ctl->step_upd = ctl->step_fwd;
+        ctl->step_fwd = ctl->step_fwd + 1;
+    }
+}
+
+// ---------------------------------------------------------------- tree backward
+// WITH_LADJ: transform_gradients! (y_grad rounded to Float32 as in the reference's Float32 vector);
+// otherwise transform_gradients_no_ladj! with a Float64 y_grad (OptimizePTTApprox).
+template <int KP, int THREADS, bool WITH_LADJ>
+__global__ void __launch_bounds__(THREADS)
+    k3_tree_bwd(const int32_t *__restrict__ bin_lvl_ptr, const int32_t *__restrict__ lvl_off,
+                const int32_t *__restrict__ sch_node, const TreeNode *__restrict__ nodes,
+                const double *__restrict__ ys, const double *__restrict__ us, const double *__restrict__ g,
+                const float *__restrict__ efflen_adj, const double *__restrict__ S, float2 *__restrict__ G,
+                double *__restrict__ ygrad, double *__restrict__ xgrad_out) {
+    const int k = threadIdx.x % KP, slot = threadIdx.x / KP;
+    constexpr int NPP = THREADS / KP;
+    const int l0 = bin_lvl_ptr[blockIdx.x], l1 = bin_lvl_ptr[blockIdx.x + 1] - 1;
+    for (int l = l1 - 1; l >= l0; --l) {
+        const int lo = lvl_off[l], hi = lvl_off[l + 1];
+        for (int q = lo + slot; q < hi; q += NPP) {
+            const int node = sch_node[q];
+            const TreeNode nd = nodes[node];
+            if (nd.leaf >= 0) {
+                double gv = g[(size_t)nd.leaf * KP + k];
+                if (efflen_adj) gv = __dsub_rn(gv, __ddiv_rn((double)efflen_adj[nd.leaf], S[k]));  // likelihood.jl:105
+                if (xgrad_out) xgrad_out[(size_t)nd.leaf * KP + k] = gv;
+                G[(size_t)node * KP + k] = make_float2((float)gv, 0.0f);
+            } else {
+                const float2 gl = G[(size_t)nd.left * KP + k], gr = G[(size_t)nd.right * KP + k];
+                const double y = ys[(size_t)nd.k * KP + k];
+                const double ui = node == 0 ? 1.0 : us[(size_t)node * KP + k];
+                const double omy = __dsub_rn(1.0, y);
+                float2 out;
+                out.x = (float)__dadd_rn(__dmul_rn(y, (double)gl.x), __dmul_rn(omy, (double)gr.x));
+                if (WITH_LADJ) {
+                    const float d = __fsub_rn(__fadd_rn(gl.x, gl.y), __fadd_rn(gr.x, gr.y));
+                    ygrad[(size_t)nd.k * KP + k] = (double)(float)__dmul_rn(ui, (double)d);
+                    out.y = (float)__dadd_rn(__dadd_rn(__ddiv_rn(1.0, ui), __dmul_rn(y, (double)gl.y)),
+                                             __dmul_rn(omy, (double)gr.y));
+                } else {
+                    const float d = __fsub_rn(gl.x, gr.x);
+                    ygrad[(size_t)nd.k * KP + k] = __dmul_rn(ui, (double)d);
+                    out.y = 0.0f;
+                }
+                G[(size_t)node * KP + k] = out;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- reparameterisation backward + ADAM
+struct AdamCfg {
+    double max_step_mu, max_step_omega, max_step_alpha, max_step_z;
+};
+
+__device__ __forceinline__ void adam_one(float &param, float &m, float &v, double grad, float grad_sq_f32,
+                                         bool grad_is_f32, int step, double lr, double m_denom, double v_denom,
+                                         double max_step) {
+    // adam_update_mv!  l-a.jl:116-130
+    if (step == 1) {
+        m = (float)grad;
+        v = grad_is_f32 ? grad_sq_f32 : (float)__dmul_rn(grad, grad);
+    } else {
+        const double g2 = grad_is_f32 ? (double)grad_sq_f32 : __dmul_rn(grad, grad);
+        m = (float)__dadd_rn(__dmul_rn(0.7, (double)m), __dmul_rn(1.0 - 0.7, grad));
+        v = (float)__dadd_rn(__dmul_rn(0.9, (double)v), __dmul_rn(1.0 - 0.9, g2));
+    }
+    // adam_update_params!  l-a.jl:136-146  (ascent)
+    const double pm = __ddiv_rn((double)m, m_denom);
+    const double pv = __ddiv_rn((double)v, v_denom);
+    double delta = __ddiv_rn(__dmul_rn(lr, pm), __dadd_rn(sqrt(pv), 1e-8));
+    delta = fmin(fmax(delta, -max_step), max_step);
+    param = (float)__dadd_rn((double)param, delta);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(256)
+    k3_update(int64_t nm1, int K, int mode, float *__restrict__ mu, float *__restrict__ omega,
+              float *__restrict__ alpha, float *__restrict__ m_mu, float *__restrict__ m_omega,
+              float *__restrict__ m_alpha, float *__restrict__ v_mu, float *__restrict__ v_omega,
+              float *__restrict__ v_alpha, const float *__restrict__ zs0, const float *__restrict__ zs,
+              const double *__restrict__ ys, const double *__restrict__ ygrad, const StepCtl *__restrict__ ctl,
+              AdamCfg cfg, int do_adam, int *__restrict__ bad_step, float *__restrict__ grad_out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nm1) return;
+    const int step = ctl->step_upd;
+    // adam_learning_rate(step_num - 1)  l-a.jl:107-110, 497
+    const double lr = fmax(1e-3, 1.0 * exp(-2e-2 * (double)(step - 1)));
+    const double m_denom = 1.0 - pow(0.7, (double)step), v_denom = 1.0 - pow(0.9, (double)step);
+
+    if (mode == 1) {  // OptimizePTTApprox: z_grad = y (1 - y) y_grad, Float64 (l-a.jl:211-213)
+        const double y = ys[(size_t)i * KP];
+        const double zg = __dmul_rn(__dmul_rn(y, __dsub_rn(1.0, y)), ygrad[(size_t)i * KP]);
+        if (grad_out) grad_out[i] = (float)zg;
+        if (!isfinite(zg)) atomicCAS(bad_step, 0, step);
+        if (do_adam) adam_one(mu[i], m_mu[i], v_mu[i], zg, 0.0f, false, step, lr, m_denom, v_denom, cfg.max_step_z);
+        return;
+    }
+
+    const float sigma = expf(omega[i]);
+    const float al = alpha[i];
+    float mu_g = 0.0f, om_g = 0.0f, al_g = 0.0f;
+    for (int k = 0; k < K; ++k) {
+        const double y = ys[(size_t)i * KP + k];
+        const double yg = ygrad[(size_t)i * KP + k];  // already rounded to Float32
+        const double z = (double)zs[(size_t)i * KP + k];
+        const float z0 = zs0[(size_t)i * KP + k];
+        const double d = __dmul_rn(y, __dsub_rn(1.0, y));
+        const double omy2 = __dsub_rn(1.0, __dmul_rn(2.0, y));
+        // logit_normal_transform_gradients! (8-arg)  logitnormal.jl:38-55; sigma_grad / z_grad restart at 0 per draw
+        mu_g = (float)__dadd_rn((double)mu_g, __dmul_rn(d, yg));
+        float sg = (float)__dmul_rn(__dmul_rn(d, z), yg);
+        float zg = (float)__dmul_rn(__dmul_rn(d, (double)sigma), yg);
+        mu_g = (float)__dadd_rn((double)mu_g, omy2);
+        sg = (float)__dadd_rn((double)sg, __dadd_rn((double)__fdiv_rn(1.0f, sigma), __dmul_rn(z, omy2)));
+        zg = (float)__dadd_rn((double)zg, __dmul_rn((double)sigma, omy2));
+        // sinh_asinh_transform_gradients!  sinh_arcsinh.jl:29-38 (Float32)
+        const float c = __fadd_rn(al, asinhf(z0));
+        al_g = __fadd_rn(al_g, __fmul_rn(coshf(c), zg));
+        al_g = __fadd_rn(al_g, tanhf(c));
+        // omega chain rule  l-a.jl:547-549
+        om_g = __fadd_rn(om_g, __fmul_rn(sigma, sg));
+    }
+    const float Kf = (float)K;
+    mu_g = __fdiv_rn(mu_g, Kf);  // l-a.jl:552-556
+    om_g = __fdiv_rn(om_g, Kf);
+    al_g = __fdiv_rn(al_g, Kf);
+    if (!(isfinite(mu_g) && isfinite(om_g) && isfinite(al_g))) atomicCAS(bad_step, 0, step);
+    if (grad_out) {
+        grad_out[i] = mu_g;
+        grad_out[nm1 + i] = om_g;
+        grad_out[2 * nm1 + i] = al_g;
+    }
+    if (do_adam) {
+        adam_one(mu[i], m_mu[i], v_mu[i], (double)mu_g, __fmul_rn(mu_g, mu_g), true, step, lr, m_denom, v_denom,
+                 cfg.max_step_mu);
+        adam_one(omega[i], m_omega[i], v_omega[i], (double)om_g, __fmul_rn(om_g, om_g), true, step, lr, m_denom,
+                 v_denom, cfg.max_step_omega);
+        adam_one(alpha[i], m_alpha[i], v_alpha[i], (double)al_g, __fmul_rn(al_g, al_g), true, step, lr, m_denom,
+                 v_denom, cfg.max_step_alpha);
+    }
+}
+
+// ELBO of the step being updated: mean over the K draws of lp + the three log-Jacobians
+// (the reference ASSIGNS per draw and divides by K, l-a.jl:540,561 -- a quirk; this is the mean).
+__global__ void k3_elbo(int K, int KP, const double *__restrict__ lp, const double *__restrict__ ladj_partial,
+                        int n_elem_ctas, int n_tree_parts, const StepCtl *__restrict__ ctl, double *__restrict__ elbo,
+                        int max_steps) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double tot = 0.0;
+    for (int k = 0; k < K; ++k) {
+        double s = lp ? lp[k] : 0.0;
+        for (int t = 0; t < 2 * n_elem_ctas; ++t) s += ladj_partial[(size_t)t * KP + k];
+        const double *tp = ladj_partial + (size_t)2 * n_elem_ctas * KP;
+        for (int t = 0; t < n_tree_parts; ++t) s += tp[(size_t)t * KP + k];
+        tot += s;
+    }
+    const int step = ctl->step_upd;
+    if (step >= 1 && step <= max_steps) elbo[step - 1] = tot / (double)K;
+}
+
+}  // namespace
+
+// ================================================================== host side
+#define CK(expr) POLEE_CUDA_CHECK(h, expr)
+
+void release_work_buffers(polee_handle *h) {
+    void *ptrs[] = {h->zs0, h->zs, h->ys, h->ygrad, h->us, h->G, h->x, h->w, h->g, h->seg_partial, h->S_partial,
+                    h->S, h->lp_partial, h->ladj_partial, h->grad_out};
+    for (void *p : ptrs) cudaFree(p);
+    h->zs0 = h->zs = nullptr; h->ys = h->ygrad = h->us = nullptr; h->G = nullptr; h->x = h->w = nullptr;
+    h->g = h->seg_partial = h->S_partial = h->S = h->lp_partial = h->ladj_partial = nullptr;
+    h->grad_out = nullptr;
+    h->work_KP = 0;
+}
+
+static int elem_ctas(polee_handle *h, int KP) {
+    int64_t work = (h->n - 1) * (int64_t)KP;
+    return (int)std::max<int64_t>(1, (work + 255) / 256);
+}
+
+int ensure_work_buffers(polee_handle *h, int KP) {
+    if (h->work_KP == KP) return POLEE_OK;
+    release_work_buffers(h);
+    const int64_t n = h->n, nm1 = std::max<int64_t>(n - 1, 1), N = 2 * n - 1;
+    h->n_tree_ctas = 1 + h->td.bottom.nbins;
+    CK(cudaMalloc((void **)&h->zs0, sizeof(float) * nm1 * KP));
+    CK(cudaMalloc((void **)&h->zs, sizeof(float) * nm1 * KP));
+    CK(cudaMalloc((void **)&h->ys, sizeof(double) * nm1 * KP));
+    CK(cudaMalloc((void **)&h->ygrad, sizeof(double) * nm1 * KP));
+    CK(cudaMalloc((void **)&h->us, sizeof(double) * N * KP));
+    CK(cudaMalloc((void **)&h->G, sizeof(float2) * N * KP));
+    CK(cudaMalloc((void **)&h->x, sizeof(float) * n * KP));
+    CK(cudaMalloc((void **)&h->g, sizeof(double) * (n + 1) * KP));
+    CK(cudaMalloc((void **)&h->S_partial, sizeof(double) * h->n_tree_ctas * KP));
+    CK(cudaMalloc((void **)&h->S, sizeof(double) * KP));
+    CK(cudaMalloc((void **)&h->ladj_partial, sizeof(double) * (2 * (size_t)elem_ctas(h, KP) + h->n_tree_ctas) * KP));
+    CK(cudaMalloc((void **)&h->grad_out, sizeof(float) * 3 * nm1));
+    CK(cudaMemset(h->S_partial, 0, sizeof(double) * h->n_tree_ctas * KP));
+    CK(cudaMemset(h->ladj_partial, 0, sizeof(double) * (2 * (size_t)elem_ctas(h, KP) + h->n_tree_ctas) * KP));
+    CK(cudaMemset(h->g, 0, sizeof(double) * (n + 1) * KP));
+    if (h->have_matrix) {
+        CK(cudaMalloc((void **)&h->w, sizeof(float) * std::max<int64_t>(h->m_pad, 1) * KP));
+        CK(cudaMemset(h->w, 0, sizeof(float) * std::max<int64_t>(h->m_pad, 1) * KP));
+        CK(cudaMalloc((void **)&h->seg_partial, sizeof(double) * std::max(h->n_slots, 1) * KP));
+        CK(cudaMalloc((void **)&h->lp_partial, sizeof(double) * std::max(h->n_row_tiles, 1) * KP));
+    }
+    h->work_KP = KP;
+    return POLEE_OK;
+}
+
+#define DISPATCH_KP(KP, CALL)                                                   \
+    switch (KP) {                                                               \
+        case 1: { constexpr int KPC = 1; CALL; } break;                         \
+        case 2: { constexpr int KPC = 2; CALL; } break;                         \
+        case 4: { constexpr int KPC = 4; CALL; } break;                         \
+        case 8: { constexpr int KPC = 8; CALL; } break;                         \
+        case 16: { constexpr int KPC = 16; CALL; } break;                       \
+        default: return h->fail(POLEE_EINVAL, "unsupported number of MC draws (1..16)"); \
+    }
+
+int launch_reparam_fwd(polee_handle *h, int KP, int K, const float *noise, int64_t noise_steps, int want_ladj) {
+    const int64_t nm1 = h->n - 1;
+    if (nm1 <= 0) return POLEE_OK;
+    const int ctas = elem_ctas(h, KP);
+    const int mode = h->o.approx == POLEE_APPROX_OPTIMIZE_PTT ? 1 : 0;
+    DISPATCH_KP(KP, (k3_reparam_fwd<KPC><<<ctas, 256, 0, h->stream>>>(
+                        nm1, K, mode, h->mu, h->omega, h->alpha, noise, noise_steps, h->d_step,
+                        h->o.seed, h->zs0, h->zs, h->ys, want_ladj, h->ladj_partial)));
+    return POLEE_OK;
+}
+
+int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_ladj) {
+    const TreeDev &td = h->td;
+    double *ladj_tree = h->ladj_partial + (size_t)2 * elem_ctas(h, KP) * KP;
+    const float *eff = want_S ? h->efflen : nullptr;
+    double *Sp = want_S ? h->S_partial : nullptr;
+    if (td.top.nbins > 0) {
+        DISPATCH_KP(KP, (k3_tree_fwd<KPC, TOP_THREADS><<<td.top.nbins, TOP_THREADS, 0, h->stream>>>(
+                            td.top.bin_lvl_ptr, td.top.lvl_off, td.top.sch_node, td.nodes, h->ys, h->us, h->x, clamp_x,
+                            eff, Sp, 0, want_ladj, ladj_tree)));
+    }
+    if (td.bottom.nbins > 0) {
+        DISPATCH_KP(KP, (k3_tree_fwd<KPC, TREE_THREADS><<<td.bottom.nbins, TREE_THREADS, 0, h->stream>>>(
+                            td.bottom.bin_lvl_ptr, td.bottom.lvl_off, td.bottom.sch_node, td.nodes, h->ys, h->us, h->x,
+                            clamp_x, eff, Sp, 1, want_ladj, ladj_tree)));
+    }
+    return POLEE_OK;
+}
+
+int launch_mid(polee_handle *h, int KP, int advance) {
+    k3_mid<<<1, 1024, 0, h->stream>>>(h->S_partial, h->n_tree_ctas, KP, h->S, h->d_step, advance);
+    return POLEE_OK;
+}
+
+int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, double *xgrad_out) {
+    const TreeDev &td = h->td;
+    const float *adj = apply_efflen ? h->efflen_adj : nullptr;
+#define BWD(SCHED, THREADS)                                                                                          \
+    if (with_ladj) {                                                                                                 \
+        DISPATCH_KP(KP, (k3_tree_bwd<KPC, THREADS, true><<<SCHED.nbins, THREADS, 0, h->stream>>>(                    \
+                            SCHED.bin_lvl_ptr, SCHED.lvl_off, SCHED.sch_node, td.nodes, h->ys, h->us, h->g, adj, h->S, \
+                            h->G, h->ygrad, xgrad_out)));                                                            \
+    } else {                                                                                                         \
+        DISPATCH_KP(KP, (k3_tree_bwd<KPC, THREADS, false><<<SCHED.nbins, THREADS, 0, h->stream>>>(                   \
+                            SCHED.bin_lvl_ptr, SCHED.lvl_off, SCHED.sch_node, td.nodes, h->ys, h->us, h->g, adj, h->S, \
+                            h->G, h->ygrad, xgrad_out)));                                                            \
+    }
+    if (td.bottom.nbins > 0) { BWD(td.bottom, TREE_THREADS) }
+    if (td.top.nbins > 0) { BWD(td.top, TOP_THREADS) }
+#undef BWD
+    return POLEE_OK;
+}
+
+int launch_update(polee_handle *h, int KP, int K, bool do_adam, float *grad_out) {
+    const int64_t nm1 = h->n - 1;
+    if (nm1 <= 0) return POLEE_OK;
+    const int mode = h->o.approx == POLEE_APPROX_OPTIMIZE_PTT ? 1 : 0;
+    AdamCfg cfg{h->o.max_step_mu, h->o.max_step_omega, h->o.max_step_alpha, h->o.max_step_z};
+    const int ctas = (int)((nm1 + 255) / 256);
+    DISPATCH_KP(KP, (k3_update<KPC><<<ctas, 256, 0, h->stream>>>(
+                        nm1, K, mode, h->mu, h->omega, h->alpha, h->m_mu, h->m_omega, h->m_alpha, h->v_mu, h->v_omega,
+                        h->v_alpha, h->zs0, h->zs, h->ys, h->ygrad, h->d_step, cfg, do_adam ? 1 : 0,
+                        h->d_bad_step, grad_out)));
+    return POLEE_OK;
+}
+
+int launch_elbo(polee_handle *h, int KP, int K, bool have_lp) {
+    k3_elbo<<<1, 32, 0, h->stream>>>(K, KP, have_lp ? h->g + (size_t)h->n * KP : nullptr, h->ladj_partial,
+                                     elem_ctas(h, KP), h->n_tree_ctas, h->d_step, h->elbo,
+                                     h->o.num_steps);
+    return POLEE_OK;
+}
+
+}  // namespace polee
