@@ -331,9 +331,9 @@ void orc_list_nodes(int64_t n, int32_t *parent_idxs, int32_t *js) {
 
 /* sinh_arcsinh.jl:10-23 (all Float32).  The reference's threaded `ladj +=` is racy
  * (SURVEY App. C3); the serial sum is restated. */
-float orc_sinh_asinh_transform(int64_t nm1, const float *alpha, const float *zs0, float *zs,
-                               int compute_ladj) {
-    float ladj = 0.0f;
+double orc_sinh_asinh_transform(int64_t nm1, const float *alpha, const float *zs0, float *zs,
+                                int compute_ladj) {
+    double ladj = 0.0; /* `ladj = 0.0f0; ladj += <Float64>` is type-unstable: it is a Float64 after the first add */
 #pragma omp parallel for schedule(static) if (!compute_ladj)
     for (int64_t i = 0; i < nm1; ++i) {
         float c = alpha[i] + asinhf(zs0[i]);
@@ -341,16 +341,16 @@ float orc_sinh_asinh_transform(int64_t nm1, const float *alpha, const float *zs0
         if (compute_ladj) {
             /* log(cosh(c)) Float32 - 0.5 * log1p(z0^2): 0.5 is Float64 -> Float64, `ladj +=` */
             double term = (double)logf(coshf(c)) - 0.5 * (double)log1pf(zs0[i] * zs0[i]);
-            ladj = (float)((double)ladj + term);
+            ladj += term;
         }
     }
     return ladj;
 }
 
 /* logitnormal.jl:2-20: logistic(x) = inv(1 + exp(-x)) in Float32, stored into Float64 ys. */
-float orc_logit_normal_transform(int64_t nm1, const float *mu, const float *sigma, const float *zs,
-                                 double *ys, int compute_ladj) {
-    float ladj = 0.0f;
+double orc_logit_normal_transform(int64_t nm1, const float *mu, const float *sigma, const float *zs,
+                                  double *ys, int compute_ladj) {
+    double ladj = 0.0;
     for (int64_t i = 0; i < nm1; ++i) {
         float prod = zs[i] * sigma[i];
         float x = mu[i] + prod;
@@ -360,7 +360,7 @@ float orc_logit_normal_transform(int64_t nm1, const float *mu, const float *sigm
         if (compute_ladj) {
             /* log(sigma[i] * ys[i] * (1 - ys[i])): ys is Float64 here */
             double v = ((double)sigma[i] * ys[i]) * (1.0 - ys[i]);
-            ladj = (float)((double)ladj + log(v));
+            ladj += log(v);
         }
     }
     return ladj;
@@ -459,21 +459,16 @@ static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
     }
 }
 
-/* "polee-philox-v1": counter = (i>>2, draw, step, 0), key = seed; two Box-Muller pairs per block. */
+/* "polee-philox-v1": one Philox4x32-10 call per element, counter = (i, draw, step, 0), key = seed;
+ * z = sqrt(-2 ln u1) cos(2 pi u2) from the first two output words (Float32 arithmetic). */
 void orc_noise_fill(uint64_t seed, int64_t step, int64_t draw, int64_t nm1, float *zs0) {
-    for (int64_t b = 0; b * 4 < nm1; ++b) {
-        uint32_t c[4] = {(uint32_t)b, (uint32_t)draw, (uint32_t)step, 0u};
+    for (int64_t i = 0; i < nm1; ++i) {
+        uint32_t c[4] = {(uint32_t)i, (uint32_t)draw, (uint32_t)step, 0u};
         philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        float z[4];
-        for (int p = 0; p < 2; ++p) {
-            float u1 = ((float)(c[2 * p] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            float u2 = ((float)(c[2 * p + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            float r = sqrtf(-2.0f * logf(u1));
-            float th = 6.28318530717958647692f * u2;
-            z[2 * p] = r * cosf(th);
-            z[2 * p + 1] = r * sinf(th);
-        }
-        for (int q = 0; q < 4 && b * 4 + q < nm1; ++q) zs0[b * 4 + q] = z[q];
+        float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float r = sqrtf(-2.0f * logf(u1));
+        zs0[i] = r * cosf(6.28318530717958647692f * u2);
     }
 }
 
@@ -590,62 +585,105 @@ static double lsn_draw_body(orc_model *M, orc_ptt *t, const int64_t *ks, const f
     return elbo;
 }
 
-int orc_fit_lsn_ptt(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,
-                    const float *nzval, const int64_t *ks, const float *efflens,
-                    const int32_t *node_parent_idxs, const int32_t *node_js, const orc_fit_opts *o,
-                    float *mu, float *omega, float *alpha, double *elbo_traj) {
-    int64_t nm1 = n - 1;
+struct orc_fit_state {
     orc_model M;
-    model_init(&M, m, n, colptr, rowval, nzval);
-    orc_ptt *t = orc_ptt_new(node_parent_idxs, node_js, 2 * n - 1);
+    orc_ptt *t;
     draw_ws w;
-    ws_init(&w, n);
-    float *buf = (float *)calloc((size_t)nm1 * 10, sizeof(float));
+    const int64_t *ks;
+    const float *efflens;
+    orc_fit_opts o;
+    int64_t n;
+    int step; /* steps completed */
+    float *buf, *mu, *omega, *alpha;
+    double last_elbo;
+};
+
+orc_fit_state *orc_fit_begin(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,
+                             const float *nzval, const int64_t *ks, const float *efflens,
+                             const int32_t *node_parent_idxs, const int32_t *node_js, const orc_fit_opts *o) {
+    orc_fit_state *s = (orc_fit_state *)calloc(1, sizeof(orc_fit_state));
+    int64_t nm1 = n - 1;
+    model_init(&s->M, m, n, colptr, rowval, nzval);
+    s->t = orc_ptt_new(node_parent_idxs, node_js, 2 * n - 1);
+    ws_init(&s->w, n);
+    s->ks = ks; s->efflens = efflens; s->o = *o; s->n = n; s->step = 0;
+    s->buf = (float *)calloc((size_t)nm1 * 13, sizeof(float));
+    s->mu = s->buf + 10 * nm1; s->omega = s->buf + 11 * nm1; s->alpha = s->buf + 12 * nm1;
+    lsn_init(s->t, n, s->mu, s->omega, s->alpha);
+    return s;
+}
+
+/* one iteration of the loop at likelihood-approximation.jl:496-575; returns 0 or the failing step */
+int orc_fit_step(orc_fit_state *s) {
+    int64_t nm1 = s->n - 1;
+    float *buf = s->buf;
     float *m_mu = buf, *m_omega = buf + nm1, *m_alpha = buf + 2 * nm1;
     float *v_mu = buf + 3 * nm1, *v_omega = buf + 4 * nm1, *v_alpha = buf + 5 * nm1;
     float *mu_grad = buf + 6 * nm1, *omega_grad = buf + 7 * nm1, *alpha_grad = buf + 8 * nm1;
     float *zs0 = buf + 9 * nm1;
     const double ss_mu = 2e-1, ss_omega = 2e-1, ss_alpha = 2e-2; /* :421-423 */
-    int K = o->num_mc_samples, status = 0;
-
-    lsn_init(t, n, mu, omega, alpha);
-
-    for (int step = 1; step <= o->num_steps; ++step) {                       /* :496 */
-        double lr = orc_adam_learning_rate(step - 1);                        /* :497 */
-        double elbo = 0.0;
-        memset(mu_grad, 0, sizeof(float) * (size_t)nm1 * 3);                 /* :501-503 */
-        for (int64_t i = 0; i < nm1; ++i) w.sigma[i] = expf(omega[i]);       /* :505-507 */
-        for (int d = 0; d < K; ++d) {                                        /* :511 */
-            if (o->noise)
-                memcpy(zs0, o->noise + ((size_t)(step - 1) * K + d) * (size_t)nm1,
-                       sizeof(float) * (size_t)nm1);
-            else
-                orc_noise_fill(o->seed, step - 1, d, nm1, zs0);              /* :517-519 */
-            double e = lsn_draw_body(&M, t, ks, efflens, o->gradonly, o->use_efflen_jacobian, mu,
-                                     alpha, zs0, &w, mu_grad, omega_grad, alpha_grad);
-            if (o->elbo_fix) elbo += e; else elbo = e;                       /* :540 (quirk) */
-        }
-        int all_finite = 1;
-        for (int64_t i = 0; i < nm1; ++i) {                                  /* :552-558 */
-            mu_grad[i] /= (float)K;
-            omega_grad[i] /= (float)K;
-            alpha_grad[i] /= (float)K;
-            all_finite &= isfinite(mu_grad[i]) && isfinite(omega_grad[i]) && isfinite(alpha_grad[i]);
-        }
-        if (!all_finite) { status = step; break; }                           /* :559 @assert */
-        elbo /= (double)K;                                                   /* :561 */
-        if (elbo_traj) elbo_traj[step - 1] = elbo;
-        orc_adam_update_mv(nm1, m_mu, v_mu, mu_grad, step);                  /* :566-568 */
-        orc_adam_update_mv(nm1, m_omega, v_omega, omega_grad, step);
-        orc_adam_update_mv(nm1, m_alpha, v_alpha, alpha_grad, step);
-        orc_adam_update_params(nm1, mu, m_mu, v_mu, lr, step, ss_mu);        /* :570-572 */
-        orc_adam_update_params(nm1, omega, m_omega, v_omega, lr, step, ss_omega);
-        orc_adam_update_params(nm1, alpha, m_alpha, v_alpha, lr, step, ss_alpha);
+    const orc_fit_opts *o = &s->o;
+    int K = o->num_mc_samples;
+    int step = s->step + 1;                                                  /* :496 */
+    double lr = orc_adam_learning_rate(step - 1);                            /* :497 */
+    double elbo = 0.0;
+    memset(mu_grad, 0, sizeof(float) * (size_t)nm1 * 3);                     /* :501-503 */
+    for (int64_t i = 0; i < nm1; ++i) s->w.sigma[i] = expf(s->omega[i]);     /* :505-507 */
+    for (int d = 0; d < K; ++d) {                                            /* :511 */
+        if (o->noise)
+            memcpy(zs0, o->noise + ((size_t)(step - 1) * K + d) * (size_t)nm1, sizeof(float) * (size_t)nm1);
+        else
+            orc_noise_fill(o->seed, step - 1, d, nm1, zs0);                  /* :517-519 */
+        double e = lsn_draw_body(&s->M, s->t, s->ks, s->efflens, o->gradonly, o->use_efflen_jacobian, s->mu,
+                                 s->alpha, zs0, &s->w, mu_grad, omega_grad, alpha_grad);
+        if (o->elbo_fix) elbo += e; else elbo = e;                           /* :540 (quirk) */
     }
-    free(buf);
-    ws_free(&w);
-    orc_ptt_free(t);
-    model_free(&M);
+    int all_finite = 1;
+    for (int64_t i = 0; i < nm1; ++i) {                                      /* :552-558 */
+        mu_grad[i] /= (float)K;
+        omega_grad[i] /= (float)K;
+        alpha_grad[i] /= (float)K;
+        all_finite &= isfinite(mu_grad[i]) && isfinite(omega_grad[i]) && isfinite(alpha_grad[i]);
+    }
+    if (!all_finite) return step;                                            /* :559 @assert */
+    elbo /= (double)K;                                                       /* :561 */
+    s->last_elbo = elbo;
+    orc_adam_update_mv(nm1, m_mu, v_mu, mu_grad, step);                      /* :566-568 */
+    orc_adam_update_mv(nm1, m_omega, v_omega, omega_grad, step);
+    orc_adam_update_mv(nm1, m_alpha, v_alpha, alpha_grad, step);
+    orc_adam_update_params(nm1, s->mu, m_mu, v_mu, lr, step, ss_mu);         /* :570-572 */
+    orc_adam_update_params(nm1, s->omega, m_omega, v_omega, lr, step, ss_omega);
+    orc_adam_update_params(nm1, s->alpha, m_alpha, v_alpha, lr, step, ss_alpha);
+    s->step = step;
+    return 0;
+}
+
+void orc_fit_params(const orc_fit_state *s, float *mu, float *omega, float *alpha) {
+    size_t b = sizeof(float) * (size_t)(s->n - 1);
+    memcpy(mu, s->mu, b); memcpy(omega, s->omega, b); memcpy(alpha, s->alpha, b);
+}
+
+void orc_fit_end(orc_fit_state *s) {
+    if (!s) return;
+    free(s->buf);
+    ws_free(&s->w);
+    orc_ptt_free(s->t);
+    model_free(&s->M);
+    free(s);
+}
+
+int orc_fit_lsn_ptt(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,
+                    const float *nzval, const int64_t *ks, const float *efflens,
+                    const int32_t *node_parent_idxs, const int32_t *node_js, const orc_fit_opts *o,
+                    float *mu, float *omega, float *alpha, double *elbo_traj) {
+    orc_fit_state *s = orc_fit_begin(m, n, colptr, rowval, nzval, ks, efflens, node_parent_idxs, node_js, o);
+    int status = 0;
+    for (int step = 1; step <= o->num_steps && !status; ++step) {
+        status = orc_fit_step(s);
+        if (!status && elbo_traj) elbo_traj[step - 1] = s->last_elbo;
+    }
+    orc_fit_params(s, mu, omega, alpha);
+    orc_fit_end(s);
     return status;
 }
 

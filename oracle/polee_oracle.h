@@ -97,10 +97,10 @@ void orc_make_inverse_ptt_params(const int32_t *node_parent_idxs, const int32_t 
 void orc_list_nodes(int64_t n, int32_t *parent_idxs, int32_t *js);
 
 /* ---- logitnormal.jl / sinh_arcsinh.jl ---- */
-float orc_sinh_asinh_transform(int64_t nm1, const float *alpha, const float *zs0, float *zs,
-                               int compute_ladj);
-float orc_logit_normal_transform(int64_t nm1, const float *mu, const float *sigma, const float *zs,
-                                 double *ys, int compute_ladj);
+double orc_sinh_asinh_transform(int64_t nm1, const float *alpha, const float *zs0, float *zs,
+                                int compute_ladj);
+double orc_logit_normal_transform(int64_t nm1, const float *mu, const float *sigma, const float *zs,
+                                  double *ys, int compute_ladj);
 void orc_logit_normal_transform_gradients(int64_t nm1, const float *zs, const double *ys,
                                           const float *mu, const float *sigma, const float *y_grad,
                                           float *z_grad, float *mu_grad, float *sigma_grad);
@@ -135,6 +135,15 @@ int orc_fit_lsn_ptt(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t
                     const float *nzval, const int64_t *ks, const float *efflens,
                     const int32_t *node_parent_idxs, const int32_t *node_js, const orc_fit_opts *opts,
                     float *mu, float *omega, float *alpha, double *elbo_traj);
+
+/* the same fit, one ADAM step at a time (bench.py's CPU baseline times orc_fit_step) */
+typedef struct orc_fit_state orc_fit_state;
+orc_fit_state *orc_fit_begin(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,
+                             const float *nzval, const int64_t *ks, const float *efflens,
+                             const int32_t *node_parent_idxs, const int32_t *node_js, const orc_fit_opts *opts);
+int orc_fit_step(orc_fit_state *s);
+void orc_fit_params(const orc_fit_state *s, float *mu, float *omega, float *alpha);
+void orc_fit_end(orc_fit_state *s);
 
 /* one MC draw of the loop body (:512-549) at fixed parameters and injected noise: outputs the
  * per-draw gradient contributions and intermediates for piecewise parity tests. */

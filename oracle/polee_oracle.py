@@ -47,8 +47,9 @@ def lib():
         _lib.orc_ptt_index.restype = P
         _lib.orc_ptt_transform.restype = c_dbl
         _lib.orc_ptt_inverse_transform.restype = c_dbl
-        _lib.orc_sinh_asinh_transform.restype = C.c_float
-        _lib.orc_logit_normal_transform.restype = C.c_float
+        _lib.orc_sinh_asinh_transform.restype = c_dbl
+        _lib.orc_logit_normal_transform.restype = c_dbl
+        _lib.orc_fit_begin.restype = P
         _lib.orc_adam_learning_rate.restype = c_dbl
         _lib.orc_lsn_draw.restype = c_dbl
     return _lib
@@ -189,6 +190,34 @@ def fit_lsn_ptt(m, n, colptr, rowval, nzval, efflens, parent_idxs, js, ks=None, 
     if st != 0:
         raise FloatingPointError("non-finite gradient at step %d" % st)
     return {"mu": mu, "omega": omega, "alpha": alpha, "elbo": elbo}
+
+
+class FitStepper:
+    """orc_fit_begin / orc_fit_step: the reference loop one ADAM step at a time (CPU baseline timing)."""
+
+    def __init__(self, m, n, colptr, rowval, nzval, efflens, parent_idxs, js, ks=None, num_mc_samples=6,
+                 gradonly=True, use_efflen_jacobian=True, seed=0):
+        self.keep = [_c(colptr, np.uint32), _c(rowval, np.uint32), _c(nzval, np.float32), _c(efflens, np.float32),
+                     _c(parent_idxs, np.int32), _c(js, np.int32), None if ks is None else _c(ks, np.int64)]
+        self.n = n
+        o = OrcFitOpts(0, num_mc_samples, int(gradonly), int(use_efflen_jacobian), seed, None, 0)
+        k = self.keep
+        self.s = lib().orc_fit_begin(c_i64(m), c_i64(n), _p(k[0]), _p(k[1]), _p(k[2]), _p(k[6]), _p(k[3]), _p(k[4]),
+                                     _p(k[5]), C.byref(o))
+
+    def step(self):
+        st = lib().orc_fit_step(P(self.s))
+        if st != 0:
+            raise FloatingPointError("non-finite gradient at step %d" % st)
+
+    def params(self):
+        mu = np.zeros(self.n - 1, np.float32); om = np.zeros_like(mu); al = np.zeros_like(mu)
+        lib().orc_fit_params(P(self.s), _p(mu), _p(om), _p(al))
+        return mu, om, al
+
+    def close(self):
+        if self.s:
+            lib().orc_fit_end(P(self.s)); self.s = None
 
 
 def lsn_draw(m, n, colptr, rowval, nzval, efflens, parent_idxs, js, mu, omega, alpha, zs0, ks=None, gradonly=True,

@@ -1,0 +1,77 @@
+"""GPU tests at BASELINE.json sizes through size-independent properties (the oracle is too slow there):
+identity sum_j x_j g_j = m, determinism, agreement between K-batched and one-at-a-time evaluation."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_sample(m, n, seed, **kw):
+    import torch
+    from polee_b200 import synth
+    s = synth.make_sample(m, n, seed=seed, device="cuda", **kw)
+    colptr = s["colptr"].to(torch.int32)
+    rowval = s["rowval"].to(torch.int32)
+    return s, colptr, rowval
+
+
+def test_config2_shape_vs_oracle(oracle):
+    """C2: m = 1 048 576, n = 20 000, K = 1 -- the oracle still finishes in seconds here."""
+    import torch
+    import polee_b200 as pb
+    from polee_b200 import synth
+    s, colptr, rowval = _device_sample(1 << 20, 20000, 20260002)
+    ns = synth.to_numpy_sample(s)
+    tree = synth.balanced_tree(20000, s["gene_sizes"].cpu().numpy())
+    h = pb.Handle(num_mc_samples=1, num_steps=4, noise_mode=1)
+    h.set_matrix_device(s["m"], s["n"], colptr.data_ptr(), rowval.data_ptr(), s["nzval"].data_ptr())
+    h.set_efflens(ns["efflens"])
+    h.set_tree(*tree)
+    xs = np.random.default_rng(0).dirichlet(np.ones(20000)).astype(np.float32).clip(1e-10)
+    lp, g = h.loglik_grad(xs, gradonly=False)
+    lp_o, g_o = oracle.Model(ns["m"], ns["n"], ns["colptr"], ns["rowval"], ns["nzval"]).log_likelihood(xs, gradonly=False)
+    assert abs(lp[0] - lp_o) <= 1e-9 * abs(lp_o)
+    nz = g_o != 0
+    assert np.max(np.abs(g[0][nz] - g_o[nz]) / g_o[nz]) <= 1e-5
+    noise = np.random.default_rng(1).normal(size=(4, 1, 19999)).astype(np.float32)
+    dev = h.fit(noise=noise)
+    ora = oracle.fit_lsn_ptt(ns["m"], ns["n"], ns["colptr"], ns["rowval"], ns["nzval"], ns["efflens"], *tree,
+                             num_steps=4, num_mc_samples=1, noise=noise)
+    for key in ("mu", "omega", "alpha"):
+        assert np.abs(dev[key] - ora[key]).max() <= 2e-4, key
+    h.close()
+    del s, colptr, rowval
+    torch.cuda.empty_cache()
+
+
+def test_config3_shape_properties():
+    """C3: m = 30 M, n = 200 k, K = 8 on one B200: gradient identity, determinism, batched == single."""
+    import torch
+    import polee_b200 as pb
+    from polee_b200 import synth
+    m, n, K = 30_000_000, 200_000, 8
+    s, colptr, rowval = _device_sample(m, n, 20260003)
+    efflens = s["efflens"].cpu().numpy()
+    tree = synth.balanced_tree(n, s["gene_sizes"].cpu().numpy())
+    h = pb.Handle(num_mc_samples=K, num_steps=3)
+    h.set_matrix_device(m, n, colptr.data_ptr(), rowval.data_ptr(), s["nzval"].data_ptr())
+    nnz = s["nnz"]
+    del s, colptr, rowval
+    torch.cuda.empty_cache()
+    h.set_efflens(efflens)
+    h.set_tree(*tree)
+    rng = np.random.default_rng(0)
+    xs = rng.dirichlet(np.ones(n), K).astype(np.float32).clip(1e-10)
+    lp, g = h.loglik_grad(xs, gradonly=False)
+    assert np.all(np.isfinite(lp)) and np.all(np.isfinite(g))
+    ident = (xs.astype(np.float64) * g).sum(1)
+    assert np.max(np.abs(ident - m)) <= 1e-5 * m                   # sum_j x_j g_j = m for every draw
+    lp2, g2 = h.loglik_grad(xs, gradonly=False)
+    assert np.array_equal(g, g2) and np.array_equal(lp, lp2)        # deterministic: no atomics
+    lp1, g1 = h.loglik_grad(xs[3], gradonly=False)                  # K = 1 kernels on the same data
+    assert abs(lp1[0] - lp[3]) <= 1e-12 * abs(lp[3])
+    assert np.max(np.abs(g1[0] - g[3]) / np.maximum(g[3], 1e-300)) <= 1e-9
+    out = h.fit()
+    assert all(np.all(np.isfinite(out[k])) for k in ("mu", "omega", "alpha"))
+    assert nnz > 100_000_000
+    h.close()

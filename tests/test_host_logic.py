@@ -1,0 +1,123 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/polee_b200.h declares, fails
+loudly without a GPU (no fallback), and the pure-host helpers (tree arrays, partitioning, generator) are exact."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from polee_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build_library()
+    return _lib.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from polee_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "polee_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(polee_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 35
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_no_cpu_fallback_create_fails_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from polee_b200 import _lib
+    import polee_b200 as pb
+    h = C.c_void_p()
+    o = _lib.PoleeOpts()
+    assert lib.polee_opts_default(C.byref(o)) == 0
+    assert (o.num_steps, o.num_mc_samples, o.gradonly, o.use_efflen_jacobian) == (500, 6, 1, 1)
+    rc = lib.polee_create(C.byref(h), C.byref(o))
+    assert rc == _lib.POLEE_ECUDA and not h.value
+    assert b"no CPU fallback" in lib.polee_last_error(None)
+    with pytest.raises(pb.PoleeError):
+        pb.Handle()
+    with pytest.raises(pb.PoleeError):   # the hsb ops have no fallback either
+        pb.hsb(np.zeros((1, 2), np.float32), [1, -1, -1, -1, -1], [2, -1, -1, -1, -1], [-1, 0, 1, -1, -1][:5])
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "polee_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "polee_oracle" not in src and "oracle/" not in src, os.path.join(dirpath, fn)
+
+
+def test_make_inverse_ptt_params_exact(lib, fx, oracle):
+    import polee_b200 as pb
+    l, r, f = pb.make_inverse_ptt_params(fx.parent_idxs, fx.js)
+    lo, ro, fo = oracle.make_inverse_ptt_params(fx.parent_idxs, fx.js)
+    assert np.array_equal(l, lo) and np.array_equal(r, ro) and np.array_equal(f, fo)
+    assert l[0] > r[0] == 1 and f[0] == -1
+
+
+def test_sequential_tree_matches_list_nodes(oracle):
+    from polee_b200.api import sequential_tree
+    for n in (2, 3, 17, 313):
+        pi, js = sequential_tree(n)
+        po, jo = oracle.list_nodes(n)
+        assert np.array_equal(pi, po) and np.array_equal(js, jo)
+
+
+def test_partition_rows_equal_nnz(lib, fx):
+    import polee_b200 as pb
+    sample = pb.RNASeqSample(fx.m, fx.n, fx.colptr, fx.rowval, fx.nzval, fx.efflens)
+    rows = np.bincount(fx.rowval - 1, minlength=fx.m)
+    for parts in (1, 2, 4, 8):
+        b = pb.partition_rows(sample, parts)
+        assert b[0] == 0 and b[-1] == fx.m and np.all(np.diff(b) > 0)
+        per = np.add.reduceat(rows, b[:-1])
+        assert per.sum() == len(fx.rowval) and per.max() - per.min() <= 2 * rows.max()
+        blocks = [pb.api.row_block(sample, int(b[i]), int(b[i + 1])) for i in range(parts)]
+        assert sum(len(s.rowval) for s in blocks) == len(fx.rowval)
+        assert all(s.rowval.min() == 1 and s.rowval.max() == s.m for s in blocks)
+
+
+def test_synthetic_generator_invariants(small_synth, oracle):
+    s = small_synth
+    m, n = s["m"], s["n"]
+    colptr, rowval, nzval = s["colptr"], s["rowval"], s["nzval"]
+    assert colptr[0] == 1 and colptr[-1] == len(rowval) + 1 and np.all(np.diff(colptr.astype(np.int64)) >= 0)
+    col_of = np.repeat(np.arange(n), np.diff(colptr.astype(np.int64)))
+    key = col_of.astype(np.int64) * (m + 1) + rowval
+    assert np.all(np.diff(key) > 0)                                   # sorted, no duplicate (row, col)
+    rows = np.bincount(rowval - 1, minlength=m)
+    assert rows.min() >= 1 and 3.0 < rows.mean() < 5.5                # every row non-empty, mean length ~ 4
+    assert nzval.min() > 1e-12 and nzval.dtype == np.float32          # MIN_FRAG_PROB floor (constants.jl:45)
+    assert s["efflens"].min() >= 1.0
+    pi, js = s["tree"]
+    t = oracle.PTT(pi, js)                                            # valid DFS tree: transform sums to one
+    x, _ = t.transform(np.full(n - 1, 0.37))
+    assert abs(x.astype(np.float64).sum() - 1.0) < 1e-5
+    assert sorted(js[js > 0].tolist()) == list(range(1, n + 1))
+
+
+def test_tree_builders_follow_the_dfs_contract(oracle):
+    """node 1 is the root, parent < child, right child = idx + 1, subtrees contiguous."""
+    from polee_b200 import synth
+    for pi, js in (synth.random_tree(200, 1), synth.balanced_tree(77), synth.balanced_tree(10, [3, 1, 6])):
+        N = len(js)
+        assert pi[0] == 0 and np.all(pi[1:] < np.arange(2, N + 1))
+        idx = oracle.PTT(pi, js).index()
+        internal = np.nonzero(idx[0] == 0)[0]
+        assert np.all(idx[2, internal] == internal + 2)
+
+
+def test_julia_glue_binds_only_exported_symbols():
+    from polee_b200 import _lib
+    src = open(os.path.join(ROOT, "julia", "PoleeB200.jl")).read()
+    used = set(re.findall(r":(polee_[a-z0-9_]+)", src))
+    assert used and used <= set(_lib.EXPORTS), used - set(_lib.EXPORTS)
