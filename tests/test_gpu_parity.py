@@ -248,6 +248,9 @@ def test_long_rows_and_empty_columns(pb, oracle):
     """Config-4-shaped rows (up to 512 entries), columns spanning many K2 segments, empty columns."""
     from polee_b200 import synth
     s = synth.to_numpy_sample(synth.make_sample(6000, 3000, seed=5, long_rows=True))
+    s["n"] += 7                                                   # trailing empty columns (fixture: 29 of 313 empty)
+    s["colptr"] = np.concatenate([s["colptr"], np.full(7, s["colptr"][-1], np.uint32)])
+    s["efflens"] = np.concatenate([s["efflens"], np.full(7, 1000, np.float32)])
     rows = np.bincount(s["rowval"] - 1, minlength=s["m"])
     cols = np.diff(s["colptr"].astype(np.int64))
     assert rows.max() > 256 and cols.max() > 256 and (cols == 0).any()
