@@ -56,7 +56,7 @@ typedef struct polee_opts {
     int32_t gradonly;            /* Val(gradonly) = true: skip log-likelihood / ELBO values */
     int32_t use_efflen_jacobian; /* true */
     int32_t noise_mode;          /* POLEE_NOISE_* */
-    int32_t reserved0;
+    int32_t exact_accumulation;  /* 0 (default): fast mixed f32/f64 sparse kernels; 1: reference-order all-f64 sums */
     uint64_t seed;               /* Random.seed! default 123456789, main.jl:123-127 */
     double max_step_mu;          /* ss_max_mu_step    = 2e-1, likelihood-approximation.jl:421 */
     double max_step_omega;       /* ss_max_omega_step = 2e-1 */

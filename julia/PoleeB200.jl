@@ -32,7 +32,7 @@ mutable struct PoleeOpts
     gradonly::Int32
     use_efflen_jacobian::Int32
     noise_mode::Int32
-    reserved0::Int32
+    exact_accumulation::Int32
     seed::UInt64
     max_step_mu::Float64
     max_step_omega::Float64

@@ -22,7 +22,7 @@ class PoleeError(RuntimeError):
 class PoleeOpts(C.Structure):
     _fields_ = [("device", C.c_int32), ("approx", C.c_int32), ("num_steps", C.c_int32),
                 ("num_mc_samples", C.c_int32), ("gradonly", C.c_int32), ("use_efflen_jacobian", C.c_int32),
-                ("noise_mode", C.c_int32), ("reserved0", C.c_int32), ("seed", C.c_uint64),
+                ("noise_mode", C.c_int32), ("exact_accumulation", C.c_int32), ("seed", C.c_uint64),
                 ("max_step_mu", C.c_double), ("max_step_omega", C.c_double), ("max_step_alpha", C.c_double),
                 ("max_step_z", C.c_double), ("use_cuda_graph", C.c_int32), ("reserved1", C.c_int32)]
 

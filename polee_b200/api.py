@@ -71,13 +71,14 @@ class Handle:
 
     def __init__(self, device=0, approx=L.APPROX_LSN_PTT, num_steps=LIKAP_NUM_STEPS,
                  num_mc_samples=LIKAP_NUM_MC_SAMPLES, gradonly=True, use_efflen_jacobian=True, seed=123456789,
-                 noise_mode=L.NOISE_PHILOX, use_cuda_graph=True):
+                 noise_mode=L.NOISE_PHILOX, use_cuda_graph=True, exact_accumulation=False):
         self.lib = L.load_library()
         o = L.PoleeOpts()
         self.lib.polee_opts_default(C.byref(o))
         o.device, o.approx, o.num_steps, o.num_mc_samples = device, approx, num_steps, num_mc_samples
         o.gradonly, o.use_efflen_jacobian, o.seed = int(gradonly), int(use_efflen_jacobian), seed
         o.noise_mode, o.use_cuda_graph = noise_mode, int(use_cuda_graph)
+        o.exact_accumulation = int(exact_accumulation)
         self.opts = o
         self.h = _P()
         rc = self.lib.polee_create(C.byref(self.h), C.byref(o))
@@ -335,10 +336,10 @@ def make_inverse_ptt_params(node_parent_idxs, node_js):
     return l, r, f
 
 
-def log_likelihood(sample, xs, gradonly=True, ks=None, tree=None, device=0):
+def log_likelihood(sample, xs, gradonly=True, ks=None, tree=None, device=0, exact_accumulation=False):
     """log_likelihood(frag_probs, log_frag_probs, X, Xt, xs, x_grad, Val(gradonly)) -> (lp, x_grad)
     (src/likelihood.jl:36-56; factored_log_likelihood :59-85 when ks is given)."""
-    h = Handle(device=device, num_mc_samples=1)
+    h = Handle(device=device, num_mc_samples=1, exact_accumulation=exact_accumulation)
     try:
         h.set_sample(sample, ks)
         pi, js = tree if tree is not None else sequential_tree(sample.n)
@@ -351,7 +352,8 @@ def log_likelihood(sample, xs, gradonly=True, ks=None, tree=None, device=0):
 
 def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, use_efflen_jacobian=True,
                            gene_noninformative=False, ks=None, num_steps=LIKAP_NUM_STEPS,
-                           num_mc_samples=LIKAP_NUM_MC_SAMPLES, seed=123456789, noise=None, device=0, want_elbo=False):
+                           num_mc_samples=LIKAP_NUM_MC_SAMPLES, seed=123456789, noise=None, device=0, want_elbo=False,
+                           exact_accumulation=False):
     """approximate_likelihood(approx, sample, Val(gradonly); tree_topology_input_filename, use_efflen_jacobian,
     gene_noninformative) -> Dict  (src/likelihood-approximation.jl:395-624; :248-392 with ks; :149-242 for
     OptimizePTTApprox).
@@ -379,7 +381,8 @@ def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, us
         tree_topology = sequential_tree(sample.n)
     h = Handle(device=device, num_steps=num_steps, num_mc_samples=num_mc_samples, gradonly=gradonly,
                use_efflen_jacobian=use_efflen_jacobian, seed=seed,
-               noise_mode=L.NOISE_INJECTED if noise is not None else L.NOISE_PHILOX)
+               noise_mode=L.NOISE_INJECTED if noise is not None else L.NOISE_PHILOX,
+               exact_accumulation=exact_accumulation)
     try:
         h.set_sample(sample, ks)
         h.set_tree(*tree_topology)

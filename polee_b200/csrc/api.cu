@@ -342,7 +342,7 @@ static int launch_step_sequence(polee_handle *h, bool do_adam, float *grad_out, 
     if ((rc = launch_reparam_fwd(h, KP, K, noise, noise_steps, want_vals))) return rc;
     if ((rc = launch_tree_fwd(h, KP, 1, apply_eff, want_vals))) return rc;
     if ((rc = launch_mid(h, KP, do_adam ? 1 : 0))) return rc;
-    if ((rc = launch_k1(h, h->x, h->w, want_vals, h->lp_partial, KP))) return rc;
+    if ((rc = launch_k1(h, h->x, h->xd, h->w, want_vals, h->lp_partial, KP))) return rc;
     if ((rc = launch_k2(h, h->w, h->g, KP))) return rc;
     if (want_vals && (rc = launch_reduce_lp(h, h->lp_partial, h->g + (size_t)h->n * KP, KP))) return rc;
 #ifdef POLEE_WITH_NCCL
@@ -478,7 +478,8 @@ extern "C" int polee_loglik_grad(polee_handle *h, const float *xs, int32_t K, in
     int KP, rc;
     if ((rc = use_kp(h, K, &KP))) return rc;
     if ((rc = upload_kmajor<float>(h, xs, K, KP, h->n, h->x, 1.0f))) return rc;
-    if ((rc = launch_k1(h, h->x, h->w, !gradonly, h->lp_partial, KP))) return rc;
+    if ((rc = launch_widen_x(h, h->x, h->xd, KP))) return rc;
+    if ((rc = launch_k1(h, h->x, h->xd, h->w, !gradonly, h->lp_partial, KP))) return rc;
     if ((rc = launch_k2(h, h->w, h->g, KP))) return rc;
     if (!gradonly && (rc = launch_reduce_lp(h, h->lp_partial, h->g + (size_t)h->n * KP, KP))) return rc;
     CK(cudaGetLastError());
@@ -503,7 +504,8 @@ extern "C" int polee_frag_prob_recip(polee_handle *h, const float *xs, float *w)
     int KP, rc;
     if ((rc = use_kp(h, 1, &KP))) return rc;
     if ((rc = upload_kmajor<float>(h, xs, 1, KP, h->n, h->x, 1.0f))) return rc;
-    if ((rc = launch_k1(h, h->x, h->w, false, h->lp_partial, KP))) return rc;
+    if ((rc = launch_widen_x(h, h->x, h->xd, KP))) return rc;
+    if ((rc = launch_k1(h, h->x, h->xd, h->w, false, h->lp_partial, KP))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     std::vector<float> wp(h->m_pad);
     std::vector<uint32_t> perm(h->m);
@@ -658,7 +660,7 @@ extern "C" int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, f
     CK(cudaEventRecord(e0, h->stream));
     for (int r = 0; r < reps && !rc; ++r) {
         if (which == 1) {
-            rc = launch_k1(h, h->x, h->w, false, h->lp_partial, KP);
+            rc = launch_k1(h, h->x, h->xd, h->w, false, h->lp_partial, KP);
         } else if (which == 2) {
             rc = launch_k2(h, h->w, h->g, KP);
         } else if (which == 3) {

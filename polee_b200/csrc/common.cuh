@@ -45,9 +45,10 @@ struct RowTile {
 constexpr int COL_SEG = 256;
 struct ColSeg {
     uint32_t start;  // entry offset in csc_row / csc_val
-    uint32_t len;
+    uint32_t len;    // low 16 bits: entries; high 16 bits: r > 0 if this segment heads a run of r segments of
+                     // the same column inside one CTA item (K2_WARPS consecutive segments)
     uint32_t col;
-    int32_t slot;    // >= 0: partial slot (column spans several segments); -1: writes g directly
+    int32_t slot;    // of a run head: >= 0 partial slot (column spans several runs); -1: the run writes g directly
 };
 struct MultiCol {
     uint32_t col;
@@ -162,6 +163,7 @@ struct polee_handle {
     double *us = nullptr;                 // [N][KP]
     float2 *G = nullptr;                  // [N][KP]
     float *x = nullptr;                   // [n][KP]
+    double *xd = nullptr;                 // [n][KP] Float64(x): K1's gather table
     float *w = nullptr;                   // [m_pad][KP]
     double *g = nullptr;                  // [n][KP]  (all-reduced across ranks)
     double *seg_partial = nullptr;        // [n_slots][KP]
@@ -203,7 +205,8 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
 void release_matrix(polee_handle *h);
 
 // sparse_kernels.cu
-int launch_k1(polee_handle *h, const float *x, float *w, bool want_lp, double *lp_partial, int KP);
+int launch_k1(polee_handle *h, const float *x, const double *xd, float *w, bool want_lp, double *lp_partial, int KP);
+int launch_widen_x(polee_handle *h, const float *x, double *xd, int KP);
 int launch_k2(polee_handle *h, const float *w, double *g, int KP);
 int launch_reduce_lp(polee_handle *h, const double *lp_partial, double *lp, int KP);
 

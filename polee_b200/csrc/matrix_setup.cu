@@ -273,8 +273,11 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
     CK(cudaMalloc((void **)&h->sell_val, sizeof(float) * std::max<uint64_t>(slab, 1)));
     CK(cudaMemsetAsync(h->sell_idx, 0, sizeof(uint32_t) * std::max<uint64_t>(slab, 1), st));
     CK(cudaMemsetAsync(h->sell_val, 0, sizeof(float) * std::max<uint64_t>(slab, 1), st));
-    CK(cudaMalloc((void **)&h->csc_row, sizeof(uint32_t) * std::max<int64_t>(nnz, 1)));
-    CK(cudaMalloc((void **)&h->csc_val, sizeof(float) * std::max<int64_t>(nnz, 1)));
+    // +16 elements: K2's bulk copies round their byte count up to 16
+    CK(cudaMalloc((void **)&h->csc_row, sizeof(uint32_t) * (nnz + 16)));
+    CK(cudaMalloc((void **)&h->csc_val, sizeof(float) * (nnz + 16)));
+    CK(cudaMemsetAsync(h->csc_row, 0, sizeof(uint32_t) * (nnz + 16), st));
+    CK(cudaMemsetAsync(h->csc_val, 0, sizeof(float) * (nnz + 16), st));
     if (nnz > 0) {
         k_entry_keys<<<grid_for(nnz), TPB, 0, st>>>(d_colptr, n, d_rowval, nnz, h->row_perm, col_of, keys_a, vals_a);
         CK(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, keys_a, keys_b, vals_a, vals_b, (int)nnz, 0,
@@ -307,20 +310,42 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
     std::vector<ColSeg> segs;
     std::vector<MultiCol> multi;
     segs.reserve((size_t)(nnz / COL_SEG + n));
-    uint32_t slots = 0;
     for (int64_t j = 0; j < n; ++j) {
         uint32_t s = colptr[j] - 1, len = colptr[j + 1] - colptr[j];
         uint32_t ns = len == 0 ? 1 : (len + COL_SEG - 1) / COL_SEG;
-        if (ns > 1) multi.push_back(MultiCol{(uint32_t)j, slots, ns, 0});
         for (uint32_t q = 0; q < ns; ++q) {
             ColSeg sg;
             sg.start = s + q * COL_SEG;
             sg.len = std::min<uint32_t>(COL_SEG, len - q * COL_SEG);
             sg.col = (uint32_t)j;
-            sg.slot = ns > 1 ? (int32_t)(slots + q) : -1;
+            sg.slot = -1;
             segs.push_back(sg);
         }
-        if (ns > 1) slots += ns;
+    }
+    // runs: consecutive segments of one column inside one CTA item (8 consecutive segments)
+    constexpr size_t ITEM = 8;
+    uint32_t slots = 0;
+    for (size_t i = 0; i < segs.size();) {
+        const uint32_t col = segs[i].col;
+        size_t j = i;
+        while (j < segs.size() && segs[j].col == col) ++j;      // [i, j) = all segments of this column
+        size_t nruns = 0;
+        const uint32_t first_slot = slots;
+        for (size_t a = i; a < j;) {
+            size_t b = std::min(j, (a / ITEM + 1) * ITEM);         // run = [a, b) inside one item
+            segs[a].len |= (uint32_t)(b - a) << 16;
+            ++nruns;
+            a = b;
+        }
+        if (nruns > 1) {
+            for (size_t a = i; a < j;) {
+                size_t b = std::min(j, (a / ITEM + 1) * ITEM);
+                segs[a].slot = (int32_t)slots++;
+                a = b;
+            }
+            multi.push_back(MultiCol{col, first_slot, (uint32_t)nruns, 0});
+        }
+        i = j;
     }
     h->n_segs = (int)segs.size();
     h->n_multi = (int)multi.size();

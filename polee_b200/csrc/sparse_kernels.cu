@@ -7,10 +7,19 @@
 //  K2  transposed gradient   g[j][k] = sum_i X[i][j] * w[i][k]       pAt_mulinv_B!(x_grad, X, frag_probs)
 //      deterministic: no atomics, fixed reduction trees              src/sparse.jl:25-40
 //
-// Arithmetic contract: each product x*v is rounded to Float32 and summed in
-// Float64 in ascending-transcript order, exactly as the reference does -> p is bit-identical to the
-// reference's frag_probs.  w is stored as Float32 (one rounding, <= 2^-24 relative); g accumulates
-// Float64(v) * Float64(w) in Float64.  Tensor cores are not used: nothing here is a dense contraction.
+// Arithmetic contract, two modes selected by opts.exact_accumulation:
+//   exact (1): each product x*v is rounded to Float32 and summed in Float64 in ascending-transcript order,
+//              exactly as the reference does -> p is bit-identical to the reference's frag_probs; g is a
+//              Float64 FMA per entry.  (v1 K1 kernel: direct global loads.)
+//   fast  (0, default): K1 accumulates Float64(v) * Float64(x) with one DFMA per (entry, draw) -- exact
+//              products, Float64 sums, |dp/p| <= 2^-24 * row entries from not rounding the products;
+//              K2 accumulates a lane's <= 8 products of a segment in Float32 and everything above that in
+//              Float64.  Both stay ~1e-7 relative, 50x inside the 1e-5 gate; the f32->f64 conversions that
+//              kept the XU pipe 40 % busy in v1 (profiles/r01_v1_*) are gone.
+// w is stored as Float32 (one rounding, <= 2^-24 relative).  Deterministic either way: no atomics, fixed
+// reduction trees.  Tensor cores are not used: nothing here is a dense contraction.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace polee {
@@ -197,72 +206,6 @@ __device__ __forceinline__ bool lane_writes(int lane) {
 
 constexpr int K2_WARPS = 8;
 
-// One warp = one column segment (<= COL_SEG consecutive entries of one column, rows ascending):
-// lane l takes entries l, l+32, ... so a warp-wide gather touches neighbouring rows of w.
-template <int KP>
-__global__ void __launch_bounds__(K2_WARPS * 32)
-    k2_csc_grad(const ColSeg *__restrict__ segs, int n_segs, const uint32_t *__restrict__ csc_row,
-                const float *__restrict__ csc_val, const float *__restrict__ w, double *__restrict__ g,
-                double *__restrict__ seg_partial) {
-    const int lane = threadIdx.x & 31;
-    const int sidx = blockIdx.x * K2_WARPS + (threadIdx.x >> 5);
-    if (sidx >= n_segs) return;
-    const ColSeg sg = segs[sidx];
-    double acc[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) acc[k] = 0.0;
-    const uint32_t *rp = csc_row + sg.start;
-    const float *vp = csc_val + sg.start;
-    constexpr int U = (KP >= 16) ? 2 : 4;
-    uint32_t off = lane;
-    for (; off + 32 * (U - 1) < sg.len; off += 32 * U) {
-        uint32_t r[U];
-        float v[U];
-        float wv[U][KP];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            r[u] = ld_stream_u32(rp + off + 32 * u);
-            v[u] = ld_stream_f32(vp + off + 32 * u);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) Vec<KP>::ld(w + (size_t)r[u] * KP, wv[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const double dv = (double)v[u];
-#pragma unroll
-            for (int k = 0; k < KP; ++k) acc[k] = fma(dv, (double)wv[u][k], acc[k]);
-        }
-    }
-    for (; off < sg.len; off += 32) {
-        uint32_t r = ld_stream_u32(rp + off);
-        const double dv = (double)ld_stream_f32(vp + off);
-        float wv[KP];
-        Vec<KP>::ld(w + (size_t)r * KP, wv);
-#pragma unroll
-        for (int k = 0; k < KP; ++k) acc[k] = fma(dv, (double)wv[k], acc[k]);
-    }
-    warp_reduce_scatter<KP>(acc, lane);
-    if (lane_writes<KP>(lane)) {
-        const int k = draw_of_lane<KP>(lane);
-        if (sg.slot < 0)
-            g[(size_t)sg.col * KP + k] = acc[0];
-        else
-            seg_partial[(size_t)sg.slot * KP + k] = acc[0];
-    }
-}
-
-// columns that span several segments: add their partials in segment order
-__global__ void k2_combine(const MultiCol *__restrict__ multi, int n_multi, int KP,
-                           const double *__restrict__ seg_partial, double *__restrict__ g) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_multi * KP) return;
-    const MultiCol mc = multi[t / KP];
-    const int k = t % KP;
-    double s = 0.0;
-    for (uint32_t q = 0; q < mc.nslots; ++q) s += seg_partial[(size_t)(mc.first_slot + q) * KP + k];
-    g[(size_t)mc.col * KP + k] = s;
-}
-
 // single CTA, fixed order: out[k] = sum_t partial[t][k]
 __global__ void __launch_bounds__(1024) k_reduce_partials(const double *__restrict__ partial, int count, int KP,
                                                           double *__restrict__ out) {
@@ -279,33 +222,409 @@ __global__ void __launch_bounds__(1024) k_reduce_partials(const double *__restri
     if (threadIdx.x < KP) out[threadIdx.x] = sm[threadIdx.x];
 }
 
+
+// =====================================================================================================
+// v2 kernels: warp-specialised, TMA-fed.  One producer warp streams the matrix tiles into a shared-memory
+// ring with 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on mbarriers; eight consumer
+// warps do the gathers and the arithmetic.  The stream never touches registers or L1, tens of KB per SM
+// are in flight without any occupancy cost, and the only latency left on a consumer's critical path is
+// the gather itself.
+// =====================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <int KP>
-int launch_k1_t(polee_handle *h, const float *x, float *w, bool want_lp, double *lp_partial) {
+struct VecD {  // KP doubles; 256-bit requests (sm_100) where KP allows
+    static __device__ __forceinline__ void ld(const double *p, double *v) {
+        if constexpr (KP >= 4) {
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q)
+                asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                             : "=d"(v[4 * q]), "=d"(v[4 * q + 1]), "=d"(v[4 * q + 2]), "=d"(v[4 * q + 3])
+                             : "l"(p + 4 * q));
+        } else if constexpr (KP == 2) {
+            double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+            v[0] = t.x;
+            v[1] = t.y;
+        } else {
+            v[0] = __ldg(p);
+        }
+    }
+};
+
+constexpr int V2_CONSUMER_WARPS = 8;
+constexpr int V2_THREADS = (V2_CONSUMER_WARPS + 1) * 32;
+constexpr int K1_TC = 8;      // entries of a row per ring stage
+constexpr int K1_STAGES = 4;
+
+struct K1Smem {
+    uint32_t idx[K1_STAGES][K1_TC][ROW_TILE];
+    float val[K1_STAGES][K1_TC][ROW_TILE];
+    double lpsm[V2_CONSUMER_WARPS][16];
+    uint64_t full[K1_STAGES], empty[K1_STAGES];
+};
+
+// K1 v2.  x is read from a Float64 copy of the Float32 x table (xd[j][k] = Float64(x[j][k])), so the
+// row sum is one DFMA per (entry, draw): p = sum_j Float64(v) * Float64(x) accumulated in Float64.
+// (EXACT builds keep the v1 kernel, whose products are rounded to Float32 first as in the reference.)
+template <int KP, bool LP, bool WEIGHTED>
+__global__ void __launch_bounds__(V2_THREADS, 3)
+    k1_sell_fwd_tma(const RowTile *__restrict__ tiles, int n_tiles, const uint32_t *__restrict__ idx,
+                    const float *__restrict__ val, const double *__restrict__ xd, float *__restrict__ w,
+                    const float *__restrict__ row_weight, double *__restrict__ lp_partial) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    K1Smem &sm = *reinterpret_cast<K1Smem *>(smraw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K1_STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], V2_CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == V2_CONSUMER_WARPS) {
+        // ------------------------------ producer warp (one lane)
+        if (lane == 0) {
+            int item = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const RowTile t = tiles[tile];
+                const uint32_t bytes_row = ((t.nrows + 31u) & ~31u) * 4u;
+                for (uint32_t t0 = 0; t0 < t.len; t0 += K1_TC, ++item) {
+                    const int stage = item % K1_STAGES;
+                    mbar_wait(&sm.empty[stage], ((item / K1_STAGES) & 1) ^ 1);
+                    const uint32_t tc = min((uint32_t)K1_TC, t.len - t0);
+                    mbar_expect_tx(&sm.full[stage], tc * 2u * bytes_row);
+                    for (uint32_t tt = 0; tt < tc; ++tt) {
+                        const size_t off = t.slab_off + (size_t)(t0 + tt) * t.stride;
+                        bulk_g2s(&sm.idx[stage][tt][0], idx + off, bytes_row, &sm.full[stage]);
+                        bulk_g2s(&sm.val[stage][tt][0], val + off, bytes_row, &sm.full[stage]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ------------------------------ consumer warps: thread = one row of the tile
+    const uint32_t r = threadIdx.x;  // 0..255
+    int item = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const RowTile t = tiles[tile];
+        const bool active = r < t.nrows;
+        double acc[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+        for (uint32_t t0 = 0; t0 < t.len; t0 += K1_TC, ++item) {
+            const int stage = item % K1_STAGES;
+            mbar_wait(&sm.full[stage], (item / K1_STAGES) & 1);
+            const uint32_t tc = min((uint32_t)K1_TC, t.len - t0);
+            if (active) {
+                constexpr int U = (KP >= 8) ? 2 : 4;
+                uint32_t tt = 0;
+                for (; tt + U <= tc; tt += U) {
+                    double xv[U][KP];
+                    double dv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t c = sm.idx[stage][tt + u][r];
+                        dv[u] = (double)sm.val[stage][tt + u][r];
+                        VecD<KP>::ld(xd + (size_t)c * KP, xv[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) acc[k] = fma(dv[u], xv[u][k], acc[k]);
+                }
+                for (; tt < tc; ++tt) {
+                    const uint32_t c = sm.idx[stage][tt][r];
+                    const double dv = (double)sm.val[stage][tt][r];
+                    double xv[KP];
+                    VecD<KP>::ld(xd + (size_t)c * KP, xv);
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) acc[k] = fma(dv, xv[k], acc[k]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        }
+        double lpv[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) lpv[k] = 0.0;
+        if (active) {
+            float wt = 1.0f;
+            if (WEIGHTED) wt = row_weight[t.row0 + r];
+            float wv[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                float rc = __frcp_rn((float)acc[k]);
+                wv[k] = WEIGHTED ? rc * wt : rc;
+            }
+            Vec<KP>::st(w + (size_t)(t.row0 + r) * KP, wv);
+            if (LP) {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) lpv[k] = WEIGHTED ? log(acc[k]) * (double)wt : log(acc[k]);
+            }
+        }
+        if (LP) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                double v = lpv[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) sm.lpsm[warp][k] = v;
+            }
+            consumer_bar_sync();
+            if (threadIdx.x < KP) {
+                double s = 0.0;
+                for (int wi = 0; wi < V2_CONSUMER_WARPS; ++wi) s += sm.lpsm[wi][threadIdx.x];
+                lp_partial[(size_t)tile * KP + threadIdx.x] = s;
+            }
+            consumer_bar_sync();
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K2 v2
+constexpr int K2_STAGES = 4;
+constexpr int K2_ITEM_ENTRIES = K2_WARPS * COL_SEG;  // 2048
+
+struct K2Smem {
+    uint32_t row[K2_STAGES][K2_ITEM_ENTRIES + 8];
+    float val[K2_STAGES][K2_ITEM_ENTRIES + 8];
+    double part[2][K2_WARPS][16];
+    uint64_t full[K2_STAGES], empty[K2_STAGES];
+};
+
+// One item = K2_WARPS consecutive segments = one contiguous range of CSC entries.  Consumer warp wi owns
+// segment wi of the item.  FAST: the lane's <= COL_SEG/32 products are accumulated in Float32, then widened
+// and reduced in Float64 (lane -> warp butterfly -> segments of a column inside the CTA -> k2_combine);
+// EXACT: every product is a Float64 FMA.  Fixed order everywhere: deterministic, no atomics.
+template <int KP, bool EXACT>
+__global__ void __launch_bounds__(V2_THREADS, 3)
+    k2_csc_grad_tma(const ColSeg *__restrict__ segs, int n_segs, const uint32_t *__restrict__ csc_row,
+                    const float *__restrict__ csc_val, const float *__restrict__ w, double *__restrict__ g,
+                    double *__restrict__ seg_partial) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    K2Smem &sm = *reinterpret_cast<K2Smem *>(smraw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K2_STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], K2_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int n_items = (n_segs + K2_WARPS - 1) / K2_WARPS;
+
+    if (warp == K2_WARPS) {
+        if (lane == 0) {
+            int j = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+                const int stage = j % K2_STAGES;
+                const ColSeg first = segs[it * K2_WARPS];
+                const ColSeg last = segs[min(it * K2_WARPS + K2_WARPS - 1, n_segs - 1)];
+                const uint32_t a0 = first.start & ~3u;
+                const uint32_t bytes = ((last.start + (last.len & 0xffffu) - a0) * 4u + 15u) & ~15u;
+                mbar_wait(&sm.empty[stage], ((j / K2_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&sm.full[stage], 2u * bytes);
+                if (bytes) {
+                    bulk_g2s(&sm.row[stage][0], csc_row + a0, bytes, &sm.full[stage]);
+                    bulk_g2s(&sm.val[stage][0], csc_val + a0, bytes, &sm.full[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    int j = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+        const int stage = j % K2_STAGES;
+        const int sidx = it * K2_WARPS + warp;
+        const bool have = sidx < n_segs;
+        ColSeg sg;
+        sg.start = 0; sg.len = 0; sg.col = 0; sg.slot = -1;
+        if (have) sg = segs[sidx];
+        const uint32_t a0 = segs[it * K2_WARPS].start & ~3u;
+        const uint32_t len = sg.len & 0xffffu, run = sg.len >> 16;  // run > 0: head of a run of `run` segments
+        mbar_wait(&sm.full[stage], (j / K2_STAGES) & 1);
+        double acc[KP];
+        {
+            const uint32_t *rp = &sm.row[stage][sg.start - a0];
+            const float *vp = &sm.val[stage][sg.start - a0];
+            float facc[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) { acc[k] = 0.0; facc[k] = 0.0f; }
+            constexpr int U = (KP >= 16) ? 2 : 4;
+            uint32_t off = lane;
+            for (; off + 32 * (U - 1) < len; off += 32 * U) {
+                float wv[U][KP];
+                float v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t r = rp[off + 32 * u];
+                    v[u] = vp[off + 32 * u];
+                    Vec<KP>::ld(w + (size_t)r * KP, wv[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        if (EXACT) acc[k] = fma((double)v[u], (double)wv[u][k], acc[k]);
+                        else facc[k] = fmaf(v[u], wv[u][k], facc[k]);
+                    }
+                }
+            }
+            for (; off < len; off += 32) {
+                const uint32_t r = rp[off];
+                const float v = vp[off];
+                float wv[KP];
+                Vec<KP>::ld(w + (size_t)r * KP, wv);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    if (EXACT) acc[k] = fma((double)v, (double)wv[k], acc[k]);
+                    else facc[k] = fmaf(v, wv[k], facc[k]);
+                }
+            }
+            if (!EXACT) {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) acc[k] = (double)facc[k];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        warp_reduce_scatter<KP>(acc, lane);
+        const int buf = j & 1;
+        if (lane_writes<KP>(lane)) sm.part[buf][warp][draw_of_lane<KP>(lane)] = acc[0];
+        consumer_bar_sync();
+        if (have && run > 0 && lane < KP) {
+            double s = 0.0;
+            for (uint32_t q = 0; q < run; ++q) s += sm.part[buf][warp + q][lane];
+            if (sg.slot < 0)
+                g[(size_t)sg.col * KP + lane] = s;
+            else
+                seg_partial[(size_t)sg.slot * KP + lane] = s;
+        }
+    }
+}
+
+// columns that span several CTA items: one warp per column adds the partials in slot order
+template <int KP>
+__global__ void __launch_bounds__(256) k2_combine_warp(const MultiCol *__restrict__ multi, int n_multi,
+                                                       const double *__restrict__ seg_partial, double *__restrict__ g) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= n_multi) return;
+    const MultiCol mc = multi[wid];
+    constexpr int SUB = 32 / KP;  // slots per warp iteration
+    const int k = lane % KP, sub = lane / KP;
+    double s = 0.0;
+    for (uint32_t q = sub; q < mc.nslots; q += SUB) s += seg_partial[(size_t)(mc.first_slot + q) * KP + k];
+#pragma unroll
+    for (int o = 16; o >= KP; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (sub == 0) g[(size_t)mc.col * KP + k] = s;
+}
+
+__global__ void k_widen_f32(const float *__restrict__ in, double *__restrict__ out, size_t count) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (double)in[i];
+}
+
+template <int KP>
+int launch_k1_t(polee_handle *h, const float *x, const double *xd, float *w, bool want_lp, double *lp_partial) {
     if (h->n_row_tiles == 0) return POLEE_OK;
-    dim3 grid(h->n_row_tiles), block(ROW_TILE);
     const bool wt = h->row_weight != nullptr;
+    if (h->o.exact_accumulation) {
+        dim3 grid(h->n_row_tiles), block(ROW_TILE);
 #define K1_LAUNCH(LPF, WF)                                                                                      \
     k1_sell_fwd<KP, LPF, WF><<<grid, block, 0, h->stream>>>(h->row_tiles, h->sell_idx, h->sell_val, x, w,       \
                                                             h->row_weight, lp_partial)
-    if (want_lp) {
-        if (wt) K1_LAUNCH(true, true); else K1_LAUNCH(true, false);
-    } else {
-        if (wt) K1_LAUNCH(false, true); else K1_LAUNCH(false, false);
-    }
+        if (want_lp) {
+            if (wt) K1_LAUNCH(true, true); else K1_LAUNCH(true, false);
+        } else {
+            if (wt) K1_LAUNCH(false, true); else K1_LAUNCH(false, false);
+        }
 #undef K1_LAUNCH
+        return POLEE_OK;
+    }
+    const int grid = std::min(h->n_row_tiles, h->num_sms * 3);
+    const size_t smem = sizeof(K1Smem);
+#define K1_LAUNCH2(LPF, WF)                                                                                        \
+    do {                                                                                                           \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            cudaFuncSetAttribute(k1_sell_fwd_tma<KP, LPF, WF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            attr_done = true;                                                                                      \
+        }                                                                                                          \
+        k1_sell_fwd_tma<KP, LPF, WF><<<grid, V2_THREADS, smem, h->stream>>>(h->row_tiles, h->n_row_tiles, h->sell_idx, \
+                                                                            h->sell_val, xd, w, h->row_weight, lp_partial); \
+    } while (0)
+    if (want_lp) {
+        if (wt) K1_LAUNCH2(true, true); else K1_LAUNCH2(true, false);
+    } else {
+        if (wt) K1_LAUNCH2(false, true); else K1_LAUNCH2(false, false);
+    }
+#undef K1_LAUNCH2
     return POLEE_OK;
 }
 
 template <int KP>
 int launch_k2_t(polee_handle *h, const float *w, double *g) {
     if (h->n_segs > 0) {
-        dim3 grid((h->n_segs + K2_WARPS - 1) / K2_WARPS), block(K2_WARPS * 32);
-        k2_csc_grad<KP><<<grid, block, 0, h->stream>>>(h->segs, h->n_segs, h->csc_row, h->csc_val, w, g,
-                                                       h->seg_partial);
+        const int n_items = (h->n_segs + K2_WARPS - 1) / K2_WARPS;
+        const int grid = std::min(n_items, h->num_sms * 3);
+        const size_t smem = sizeof(K2Smem);
+        if (h->o.exact_accumulation) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(k2_csc_grad_tma<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_done = true;
+            }
+            k2_csc_grad_tma<KP, true><<<grid, V2_THREADS, smem, h->stream>>>(h->segs, h->n_segs, h->csc_row, h->csc_val, w,
+                                                                              g, h->seg_partial);
+        } else {
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(k2_csc_grad_tma<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_done = true;
+            }
+            k2_csc_grad_tma<KP, false><<<grid, V2_THREADS, smem, h->stream>>>(h->segs, h->n_segs, h->csc_row, h->csc_val,
+                                                                               w, g, h->seg_partial);
+        }
     }
     if (h->n_multi > 0) {
-        int work = h->n_multi * KP;
-        k2_combine<<<(work + 255) / 256, 256, 0, h->stream>>>(h->multi, h->n_multi, KP, h->seg_partial, g);
+        const int warps_per_block = 8;
+        k2_combine_warp<KP><<<(h->n_multi + warps_per_block - 1) / warps_per_block, 256, 0, h->stream>>>(
+            h->multi, h->n_multi, h->seg_partial, g);
     }
     return POLEE_OK;
 }
@@ -322,9 +641,9 @@ int launch_k2_t(polee_handle *h, const float *w, double *g) {
         default: return h->fail(POLEE_EINVAL, "unsupported number of MC draws (1..16)"); \
     }
 
-int launch_k1(polee_handle *h, const float *x, float *w, bool want_lp, double *lp_partial, int KP) {
+int launch_k1(polee_handle *h, const float *x, const double *xd, float *w, bool want_lp, double *lp_partial, int KP) {
     int rc = POLEE_OK;
-    DISPATCH_KP(KP, rc = launch_k1_t<KPC>(h, x, w, want_lp, lp_partial));
+    DISPATCH_KP(KP, rc = launch_k1_t<KPC>(h, x, xd, w, want_lp, lp_partial));
     return rc;
 }
 
@@ -332,6 +651,12 @@ int launch_k2(polee_handle *h, const float *w, double *g, int KP) {
     int rc = POLEE_OK;
     DISPATCH_KP(KP, rc = launch_k2_t<KPC>(h, w, g));
     return rc;
+}
+
+int launch_widen_x(polee_handle *h, const float *x, double *xd, int KP) {
+    const size_t count = (size_t)h->n * KP;
+    k_widen_f32<<<(unsigned)std::min<size_t>((count + 255) / 256, 4096), 256, 0, h->stream>>>(x, xd, count);
+    return POLEE_OK;
 }
 
 int launch_reduce_lp(polee_handle *h, const double *lp_partial, double *lp, int KP) {

@@ -119,7 +119,8 @@ template <int KP, int THREADS>
 __global__ void __launch_bounds__(THREADS)
     k3_tree_fwd(const int32_t *__restrict__ bin_lvl_ptr, const int32_t *__restrict__ lvl_off,
                 const int32_t *__restrict__ sch_node, const TreeNode *__restrict__ nodes,
-                const double *__restrict__ ys, double *__restrict__ us, float *__restrict__ x, int clamp_x,
+                const double *__restrict__ ys, double *__restrict__ us, float *__restrict__ x, double *__restrict__ xd,
+                int clamp_x,
                 const float *__restrict__ efflen, double *__restrict__ S_partial, int part_base, int want_ladj,
                 double *__restrict__ ladj_partial) {
     __shared__ double sm[THREADS];
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(THREADS)
                     xv = (float)d;
                 }
                 x[(size_t)nd.leaf * KP + k] = xv;
+                xd[(size_t)nd.leaf * KP + k] = (double)xv;
                 if (efflen) sacc = __dadd_rn(sacc, (double)__fdiv_rn(xv, efflen[nd.leaf]));
             } else {
                 const double y = ys[(size_t)nd.k * KP + k];
@@ -342,10 +344,10 @@ __global__ void k3_elbo(int K, int KP, const double *__restrict__ lp, const doub
 #define CK(expr) POLEE_CUDA_CHECK(h, expr)
 
 void release_work_buffers(polee_handle *h) {
-    void *ptrs[] = {h->zs0, h->zs, h->ys, h->ygrad, h->us, h->G, h->x, h->w, h->g, h->seg_partial, h->S_partial,
+    void *ptrs[] = {h->zs0, h->zs, h->ys, h->ygrad, h->us, h->G, h->x, h->xd, h->w, h->g, h->seg_partial, h->S_partial,
                     h->S, h->lp_partial, h->ladj_partial, h->grad_out};
     for (void *p : ptrs) cudaFree(p);
-    h->zs0 = h->zs = nullptr; h->ys = h->ygrad = h->us = nullptr; h->G = nullptr; h->x = h->w = nullptr;
+    h->zs0 = h->zs = nullptr; h->ys = h->ygrad = h->us = nullptr; h->G = nullptr; h->x = h->w = nullptr; h->xd = nullptr;
     h->g = h->seg_partial = h->S_partial = h->S = h->lp_partial = h->ladj_partial = nullptr;
     h->grad_out = nullptr;
     h->work_KP = 0;
@@ -368,6 +370,7 @@ int ensure_work_buffers(polee_handle *h, int KP) {
     CK(cudaMalloc((void **)&h->us, sizeof(double) * N * KP));
     CK(cudaMalloc((void **)&h->G, sizeof(float2) * N * KP));
     CK(cudaMalloc((void **)&h->x, sizeof(float) * n * KP));
+    CK(cudaMalloc((void **)&h->xd, sizeof(double) * n * KP));
     CK(cudaMalloc((void **)&h->g, sizeof(double) * (n + 1) * KP));
     CK(cudaMalloc((void **)&h->S_partial, sizeof(double) * h->n_tree_ctas * KP));
     CK(cudaMalloc((void **)&h->S, sizeof(double) * KP));
@@ -414,13 +417,13 @@ int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_l
     double *Sp = want_S ? h->S_partial : nullptr;
     if (td.top.nbins > 0) {
         DISPATCH_KP(KP, (k3_tree_fwd<KPC, TOP_THREADS><<<td.top.nbins, TOP_THREADS, 0, h->stream>>>(
-                            td.top.bin_lvl_ptr, td.top.lvl_off, td.top.sch_node, td.nodes, h->ys, h->us, h->x, clamp_x,
+                            td.top.bin_lvl_ptr, td.top.lvl_off, td.top.sch_node, td.nodes, h->ys, h->us, h->x, h->xd, clamp_x,
                             eff, Sp, 0, want_ladj, ladj_tree)));
     }
     if (td.bottom.nbins > 0) {
         DISPATCH_KP(KP, (k3_tree_fwd<KPC, TREE_THREADS><<<td.bottom.nbins, TREE_THREADS, 0, h->stream>>>(
                             td.bottom.bin_lvl_ptr, td.bottom.lvl_off, td.bottom.sch_node, td.nodes, h->ys, h->us, h->x,
-                            clamp_x, eff, Sp, 1, want_ladj, ladj_tree)));
+                            h->xd, clamp_x, eff, Sp, 1, want_ladj, ladj_tree)));
     }
     return POLEE_OK;
 }

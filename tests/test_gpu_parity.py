@@ -25,13 +25,15 @@ def _synth_sample(pb, s):
     return pb.RNASeqSample(s["m"], s["n"], s["colptr"], s["rowval"], s["nzval"], s["efflens"])
 
 
+@pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("K", [1, 2, 6, 8, 16])
-def test_loglik_and_gradient_fixture(pb, fx, oracle, K):
-    """K1 + K2 vs sparse.jl restated: lp and x_grad <= 1e-5 relative, identity sum_j x_j g_j = m."""
+def test_loglik_and_gradient_fixture(pb, fx, oracle, K, exact):
+    """K1 + K2 vs sparse.jl restated: lp and x_grad <= 1e-5 relative, identity sum_j x_j g_j = m.
+    exact=True: reference-order all-Float64 sums (p bit-identical); exact=False: the default fast kernels."""
     rng = np.random.default_rng(K)
     xs = rng.dirichlet(np.ones(fx.n), K).astype(np.float32).clip(1e-10)
     xs[0] = np.float32(1) / np.float32(fx.n)
-    h = pb.Handle(num_mc_samples=K)
+    h = pb.Handle(num_mc_samples=K, exact_accumulation=exact)
     h.set_sample(_sample(pb, fx))
     h.set_tree(fx.parent_idxs, fx.js)
     lp, g = h.loglik_grad(xs, gradonly=False)
@@ -39,7 +41,7 @@ def test_loglik_and_gradient_fixture(pb, fx, oracle, K):
     for k in range(K):
         lp_o, g_o = M.log_likelihood(xs[k], gradonly=False)
         assert abs(lp[k] - lp_o) <= 1e-5 * abs(lp_o)
-        assert abs(lp[k] - lp_o) <= 1e-12 * abs(lp_o)            # in fact p is bit-identical, only the sum order differs
+        assert abs(lp[k] - lp_o) <= (1e-12 if exact else 1e-9) * abs(lp_o)   # exact: p is bit-identical, only the sum order differs
         assert relerr(g[k], g_o) <= 1e-5
         assert abs(xs[k].astype(np.float64) @ g[k] - fx.m) <= 1e-5 * fx.m
     assert abs(lp[0] - (-364724.375767)) < 1e-4                  # SURVEY 8c known answer
@@ -51,7 +53,7 @@ def test_loglik_and_gradient_fixture(pb, fx, oracle, K):
 def test_frag_probs_bitwise(pb, fx, oracle):
     """1/frag_probs: frag_probs is accumulated exactly as pAt_mul_B! does, then rounded once to Float32."""
     xs = np.random.default_rng(0).dirichlet(np.ones(fx.n)).astype(np.float32).clip(1e-10)
-    h = pb.Handle(num_mc_samples=1)
+    h = pb.Handle(num_mc_samples=1, exact_accumulation=True)
     h.set_sample(_sample(pb, fx))
     h.set_tree(fx.parent_idxs, fx.js)
     w = h.frag_prob_recip(xs)
@@ -60,6 +62,11 @@ def test_frag_probs_bitwise(pb, fx, oracle):
     expect = (np.float32(1) / M.frag_probs.astype(np.float32)).astype(np.float32)
     assert np.array_equal(w, expect)
     h.close()
+    h = pb.Handle(num_mc_samples=1)                                 # default fast kernels: same to ~1 ulp of Float32
+    h.set_sample(_sample(pb, fx))
+    h.set_tree(fx.parent_idxs, fx.js)
+    assert relerr(h.frag_prob_recip(xs), expect) <= 3e-7
+    h.close()
 
 
 def test_factored_likelihood(pb, fx, oracle):
@@ -67,7 +74,7 @@ def test_factored_likelihood(pb, fx, oracle):
     xs = np.random.default_rng(3).dirichlet(np.ones(fx.n)).astype(np.float32).clip(1e-10)
     lp, g = pb.log_likelihood(_sample(pb, fx), xs, gradonly=False, ks=ks, tree=(fx.parent_idxs, fx.js))
     lp_o, g_o = oracle.Model(fx.m, fx.n, fx.colptr, fx.rowval, fx.nzval).log_likelihood(xs, gradonly=False, ks=ks)
-    assert abs(lp - lp_o) <= 1e-9 * abs(lp_o) and relerr(g, g_o) <= 1e-5
+    assert abs(lp - lp_o) <= 1e-8 * abs(lp_o) and relerr(g, g_o) <= 1e-5
 
 
 def _trees(fx):
@@ -202,11 +209,14 @@ def test_sequential_treemethod_and_output_topology(pb, fx):
         pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox("cluster"), _sample(pb, fx))
 
 
-def test_optimize_ptt(pb, fx, oracle):
-    """approximate_likelihood(::OptimizePTTApprox): point estimate on the :sequential tree."""
+@pytest.mark.parametrize("exact", [True, False])
+def test_optimize_ptt(pb, fx, oracle, exact):
+    """approximate_likelihood(::OptimizePTTApprox): point estimate on the :sequential tree.  A depth-312 chain
+    amplifies last-bit differences of the gradient over the ADAM steps, so the comparison is on the objective
+    reached and, loosely, on the abundant transcripts."""
     steps = 60
     xo = oracle.fit_optimize_ptt(fx.m, fx.n, fx.colptr, fx.rowval, fx.nzval, fx.efflens, steps)
-    h = pb.Handle(approx=1, num_steps=steps)
+    h = pb.Handle(approx=1, num_steps=steps, exact_accumulation=exact)
     h.set_sample(_sample(pb, fx))
     xd = h.fit_optimize_ptt()
     h.close()
@@ -216,7 +226,7 @@ def test_optimize_ptt(pb, fx, oracle):
     lp_o, _ = M.log_likelihood(xo, gradonly=False)
     assert abs(lp_d - lp_o) <= 1e-4 * abs(lp_o)
     big = xo > 1e-4
-    assert np.median(np.abs(xd[big] - xo[big]) / xo[big]) < 1e-3
+    assert np.median(np.abs(xd[big] - xo[big]) / xo[big]) < (1e-3 if exact else 1e-2)
 
 
 def test_synthetic_sample_all_paths(pb, small_synth, oracle):
@@ -233,7 +243,7 @@ def test_synthetic_sample_all_paths(pb, small_synth, oracle):
     M = oracle.Model(s["m"], s["n"], s["colptr"], s["rowval"], s["nzval"])
     for k in (0, K - 1):
         lp_o, g_o = M.log_likelihood(xs[k], gradonly=False)
-        assert abs(lp[k] - lp_o) <= 1e-9 * abs(lp_o) and relerr(g[k], g_o) <= 1e-5
+        assert abs(lp[k] - lp_o) <= 1e-8 * abs(lp_o) and relerr(g[k], g_o) <= 1e-5
     noise = rng.normal(size=(25, K, s["n"] - 1)).astype(np.float32)
     dev = h.fit(noise=noise, want_elbo=True)
     ora = oracle.fit_lsn_ptt(s["m"], s["n"], s["colptr"], s["rowval"], s["nzval"], s["efflens"], pi, js, num_steps=25,
@@ -260,7 +270,7 @@ def test_long_rows_and_empty_columns(pb, oracle):
     M = oracle.Model(s["m"], s["n"], s["colptr"], s["rowval"], s["nzval"])
     for k in range(2):
         lp_o, g_o = M.log_likelihood(xs[k], gradonly=False)
-        assert abs(lp[k] - lp_o) <= 1e-9 * abs(lp_o)
+        assert abs(lp[k] - lp_o) <= 1e-8 * abs(lp_o)
         assert np.array_equal(g[k] == 0, g_o == 0)               # empty columns give exactly 0
         nz = g_o != 0
         assert relerr(g[k][nz], g_o[nz]) <= 1e-5
