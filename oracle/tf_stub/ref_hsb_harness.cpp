@@ -1,5 +1,6 @@
-// ref_hsb_harness.cpp -- drives the reference's (unmodified) HSB / InvHSB / InvHSBGrad OpKernels
-// through the stub TF API with raw pointers.  TEST INFRASTRUCTURE ONLY.  Linked together with
+// ref_hsb_harness.cpp -- drives the HSB / InvHSB / InvHSBGrad OpKernels registered in the stub TF registry
+// with raw pointers: the reference's (unmodified) ones, or -- with -DHARNESS_PREFIX_SHIM -- this project's
+// replacement shim (polee_b200/tf/hsb_ops_b200.cpp), exported as shim_*.  TEST INFRASTRUCTURE ONLY.  Linked together with
 // /root/reference/src/tensorflow_ext/hsb_ops.cpp into oracle/_ref/libref_hsb_ops.so.
 #include <cstring>
 #include <memory>
@@ -24,6 +25,12 @@ static int run_op(const char* name, std::vector<const Tensor*> inputs, std::vect
   for (size_t i = 0; i < out_ptrs.size(); ++i) std::memcpy(out_ptrs[i], ctx.outputs[i]->raw(), out_bytes[i]);
   return 0;
 }
+
+#ifdef HARNESS_PREFIX_SHIM
+#define ref_hsb shim_hsb
+#define ref_inv_hsb shim_inv_hsb
+#define ref_inv_hsb_grad shim_inv_hsb_grad
+#endif
 
 extern "C" {
 

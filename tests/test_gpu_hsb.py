@@ -50,3 +50,36 @@ def test_hsb_bad_tree():
     import polee_b200 as pb
     with pytest.raises(pb.PoleeError):
         pb.hsb(np.zeros((1, 2), np.float32), [1, 3, -1, -1, -1], [2, 4, -1, -1, -1], [-1, -1, 0, 0, 1])
+
+
+def test_tf_shim_through_stub_tensorflow():
+    """The rebuilt TF plugin (polee_b200/tf/hsb_ops_b200.cpp: same REGISTER_OP signatures, Compute() forwards to the
+    C ABI) driven through the stub TF API -- the same harness that runs the reference's own op file."""
+    import ctypes as C
+    from conftest import ROOT
+    path = os.path.join(ROOT, "polee_b200", "tf", "libshim_hsb_ops_stubtf.so")
+    if not os.path.exists(path):
+        import subprocess
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(path), "check"])
+    import polee_b200  # noqa: F401  (loads libpolee_b200.so first)
+    shim = C.CDLL(path)
+    v = np.load(os.path.join(GOLDEN, "hsb_reference_vectors.npz"))
+    P = C.c_void_p
+    p = lambda a: a.ctypes.data_as(P)  # noqa: E731
+    for case in ("fixture_shared", "per_row"):
+        g = lambda k: np.ascontiguousarray(v["%s__%s" % (case, k)])  # noqa: E731
+        L, R, F, yl = g("left"), g("right"), g("leaf"), g("y_logit")
+        B, n = yl.shape[0], yl.shape[1] + 1
+        x = np.zeros((B, n), np.float32)
+        assert shim.shim_hsb(C.c_int64(B), C.c_int64(n), p(yl), p(L), p(R), p(F), p(x), C.c_int(1)) == 0
+        assert relerr(x, g("x")) <= 1e-6
+        y = np.zeros((B, n - 1), np.float64)
+        ladj = np.zeros((B, 1), np.float32)
+        xin = g("x")
+        assert shim.shim_inv_hsb(C.c_int64(B), C.c_int64(n), p(xin), p(L), p(R), p(F), p(y), p(ladj), C.c_int(1)) == 0
+        assert np.array_equal(y, g("y")) and relerr(ladj, g("ladj")) <= 1e-6
+        bp = np.zeros((B, n), np.float32)
+        yg, lg, yy, la = g("y_grad"), g("ladj_grad"), g("y"), g("ladj")
+        assert shim.shim_inv_hsb_grad(C.c_int64(B), C.c_int64(n), p(yg), p(lg), p(yy), p(la), p(L), p(R), p(F), p(bp),
+                                      C.c_int(1)) == 0
+        assert np.array_equal(bp, g("backprops"))

@@ -121,3 +121,19 @@ def test_julia_glue_binds_only_exported_symbols():
     src = open(os.path.join(ROOT, "julia", "PoleeB200.jl")).read()
     used = set(re.findall(r":(polee_[a-z0-9_]+)", src))
     assert used and used <= set(_lib.EXPORTS), used - set(_lib.EXPORTS)
+
+
+def test_opts_struct_layout_matches_header_in_python_and_julia():
+    header = open(os.path.join(ROOT, "include", "polee_b200.h")).read()
+    body = re.search(r"typedef struct polee_opts \{(.*?)\} polee_opts;", header, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"(int32_t|uint64_t|double)\s+(\w+);", body)
+    from polee_b200 import _lib
+    py = [(n, t) for n, t in _lib.PoleeOpts._fields_]
+    cmap = {"int32_t": C.c_int32, "uint64_t": C.c_uint64, "double": C.c_double}
+    assert [(n, cmap[t]) for t, n in fields] == py
+    jl = open(os.path.join(ROOT, "julia", "PoleeB200.jl")).read()
+    jbody = re.search(r"mutable struct PoleeOpts(.*?)PoleeOpts\(\) = new\(\)", jl, flags=re.S).group(1)
+    jfields = re.findall(r"(\w+)::(Int32|UInt64|Float64)", jbody)
+    jmap = {"int32_t": "Int32", "uint64_t": "UInt64", "double": "Float64"}
+    assert [(n, jmap[t]) for t, n in fields] == jfields
