@@ -6,8 +6,8 @@
 // Build (mirrors src/tensorflow_ext/mkfile and PoleeModel.jl:53-64):
 //   g++ -std=c++14 -shared -fPIC -O2 hsb_ops_b200.cpp -o hsb_ops.so $TF_CFLAGS $TF_LFLAGS
 //       -I<repo>/include -L<repo>/polee_b200 -lpolee_b200 -Wl,-rpath,<repo>/polee_b200
-// TensorFlow is not installed in the build image; `make check` compiles this file against the stub TF API in
-// oracle/tf_stub (the same stub that builds the reference's own op file) and the GPU tests drive it that way.
+// TensorFlow is not installed in the build image; `make -C tests/tf_shim check` compiles this file against a stub
+// of the TF op API (the same stub that builds the reference's own op file) and the GPU tests drive it that way.
 //
 // The kernels are registered for DEVICE_CPU on purpose: the tensors TF hands over are host tensors (as for the
 // reference op) and the library does its own device transfers; registering a DEVICE_GPU kernel that consumes

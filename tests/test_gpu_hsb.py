@@ -57,7 +57,7 @@ def test_tf_shim_through_stub_tensorflow():
     C ABI) driven through the stub TF API -- the same harness that runs the reference's own op file."""
     import ctypes as C
     from conftest import ROOT
-    path = os.path.join(ROOT, "polee_b200", "tf", "libshim_hsb_ops_stubtf.so")
+    path = os.path.join(ROOT, "tests", "tf_shim", "libshim_hsb_ops_stubtf.so")
     if not os.path.exists(path):
         import subprocess
         subprocess.check_call(["make", "-s", "-C", os.path.dirname(path), "check"])
