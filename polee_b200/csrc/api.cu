@@ -18,7 +18,7 @@ static std::mutex g_err_mu;
     (h)->err.clear();                 \
     if (cudaSetDevice((h)->device) != cudaSuccess) return (h)->fail(POLEE_ECUDA, "cudaSetDevice failed")
 
-constexpr int TREE_BIN_NODES = 1024;
+constexpr int TREE_BIN_NODES = 512;
 
 static void drop_graph(polee_handle *h) {
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);

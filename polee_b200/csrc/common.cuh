@@ -77,6 +77,25 @@ struct TreeSchedHost {
     int nbins() const { return (int)bin_lvl_ptr.size() - 1; }
 };
 
+// Schedule-order records for the shared-memory tree kernels: bin b owns records bin_off[b]..bin_off[b+1],
+// level-ordered; children are LOCAL positions inside the bin.
+struct SNode {
+    int32_t k_or_leaf;  // >= 0: internal node, index k; < 0: leaf, transcript = -1 - v; INT32_MIN: exchange leaf
+    int32_t left, right;  // local positions of the children (internal nodes only)
+    int32_t slot;  // level-0 nodes of bottom bins / exchange leaves of the top bin: exchange slot; -1: global root; else -2
+};
+struct SSchedHost {
+    std::vector<int32_t> bin_off, bin_lvl_ptr, lvl_off;
+    std::vector<SNode> recs;
+    int max_bin_nodes = 0, max_bin_levels = 0;
+    int nbins() const { return (int)bin_off.size() - 1; }
+};
+struct SSchedDev {
+    int32_t *bin_off = nullptr, *bin_lvl_ptr = nullptr, *lvl_off = nullptr;
+    SNode *recs = nullptr;
+    int nbins = 0, max_bin_nodes = 0, max_bin_levels = 0;
+};
+
 struct TreeSchedDev {
     int32_t *bin_lvl_ptr = nullptr, *lvl_off = nullptr, *sch_node = nullptr;
     int nbins = 0;
@@ -88,6 +107,8 @@ struct TreeHost {
     std::vector<TreeNode> nodes;
     std::vector<int32_t> parent, depth, size;
     TreeSchedHost top, bottom;
+    SSchedHost s_top, s_bottom;  // same cut, schedule-order records (shared-memory kernels)
+    int n_slots = 0;             // exchange slots = bottom subtree roots
     int top_nodes = 0;
     int max_depth = 0;
     // returns "" or an error text
@@ -102,6 +123,9 @@ struct TreeDev {
     int64_t n = 0, N = 0;
     TreeNode *nodes = nullptr;
     TreeSchedDev top, bottom;
+    SSchedDev s_top, s_bottom;
+    int n_slots = 0;
+    bool smem_path = false;  // shared-memory kernels usable (top part fits one CTA per draw)
     void release();
 };
 
@@ -162,6 +186,8 @@ struct polee_handle {
     double *ygrad = nullptr;              // [n-1][KP]
     double *us = nullptr;                 // [N][KP]
     float2 *G = nullptr;                  // [N][KP]
+    double *root_us = nullptr;            // [n_slots][KP] top -> bottom exchange (shared-memory tree kernels)
+    float2 *root_G = nullptr;             // [n_slots][KP] bottom -> top exchange
     float *x = nullptr;                   // [n][KP]
     double *xd = nullptr;                 // [n][KP] Float64(x): K1's gather table
     float *w = nullptr;                   // [m_pad][KP]

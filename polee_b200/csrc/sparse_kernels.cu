@@ -19,6 +19,8 @@
 // w is stored as Float32 (one rounding, <= 2^-24 relative).  Deterministic either way: no atomics, fixed
 // reduction trees.  Tensor cores are not used: nothing here is a dense contraction.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -295,10 +297,11 @@ struct K1Smem {
 // K1 v2.  x is read from a Float64 copy of the Float32 x table (xd[j][k] = Float64(x[j][k])), so the
 // row sum is one DFMA per (entry, draw): p = sum_j Float64(v) * Float64(x) accumulated in Float64.
 // (EXACT builds keep the v1 kernel, whose products are rounded to Float32 first as in the reference.)
-template <int KP, bool LP, bool WEIGHTED>
+template <int KP, bool LP, bool WEIGHTED, bool XF32>
 __global__ void __launch_bounds__(V2_THREADS, 3)
     k1_sell_fwd_tma(const RowTile *__restrict__ tiles, int n_tiles, const uint32_t *__restrict__ idx,
-                    const float *__restrict__ val, const double *__restrict__ xd, float *__restrict__ w,
+                    const float *__restrict__ val, const double *__restrict__ xd, const float *__restrict__ xf,
+                    float *__restrict__ w,
                     const float *__restrict__ row_weight, double *__restrict__ lp_partial) {
     extern __shared__ __align__(128) unsigned char smraw[];
     K1Smem &sm = *reinterpret_cast<K1Smem *>(smraw);
@@ -349,29 +352,55 @@ __global__ void __launch_bounds__(V2_THREADS, 3)
             mbar_wait(&sm.full[stage], (item / K1_STAGES) & 1);
             const uint32_t tc = min((uint32_t)K1_TC, t.len - t0);
             if (active) {
-                constexpr int U = (KP >= 8) ? 2 : 4;
-                uint32_t tt = 0;
-                for (; tt + U <= tc; tt += U) {
-                    double xv[U][KP];
-                    double dv[U];
+                if constexpr (XF32) {
+                    // Float32 x table: a batch of <= 4 products is summed in Float32 (one FFMA each), then
+                    // widened once and added to the Float64 row sum
+                    constexpr int U = 4;
+                    for (uint32_t tt = 0; tt < tc; tt += U) {
+                        float xv[U][KP];
+                        float v[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const uint32_t c = sm.idx[stage][tt + u][r];
-                        dv[u] = (double)sm.val[stage][tt + u][r];
-                        VecD<KP>::ld(xd + (size_t)c * KP, xv[u]);
+                        for (int u = 0; u < U; ++u) {
+                            const bool ok = tt + u < tc;
+                            const uint32_t c = ok ? sm.idx[stage][tt + u][r] : 0u;
+                            v[u] = ok ? sm.val[stage][tt + u][r] : 0.0f;
+                            Vec<KP>::ld(xf + (size_t)c * KP, xv[u]);
+                        }
+                        float facc[KP];
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) facc[k] = v[0] * xv[0][k];
+#pragma unroll
+                        for (int u = 1; u < U; ++u)
+#pragma unroll
+                            for (int k = 0; k < KP; ++k) facc[k] = fmaf(v[u], xv[u][k], facc[k]);
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) acc[k] += (double)facc[k];
                     }
+                } else {
+                    constexpr int U = (KP >= 8) ? 2 : 4;
+                    uint32_t tt = 0;
+                    for (; tt + U <= tc; tt += U) {
+                        double xv[U][KP];
+                        double dv[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
+                        for (int u = 0; u < U; ++u) {
+                            const uint32_t c = sm.idx[stage][tt + u][r];
+                            dv[u] = (double)sm.val[stage][tt + u][r];
+                            VecD<KP>::ld(xd + (size_t)c * KP, xv[u]);
+                        }
 #pragma unroll
-                        for (int k = 0; k < KP; ++k) acc[k] = fma(dv[u], xv[u][k], acc[k]);
-                }
-                for (; tt < tc; ++tt) {
-                    const uint32_t c = sm.idx[stage][tt][r];
-                    const double dv = (double)sm.val[stage][tt][r];
-                    double xv[KP];
-                    VecD<KP>::ld(xd + (size_t)c * KP, xv);
+                        for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int k = 0; k < KP; ++k) acc[k] = fma(dv, xv[k], acc[k]);
+                            for (int k = 0; k < KP; ++k) acc[k] = fma(dv[u], xv[u][k], acc[k]);
+                    }
+                    for (; tt < tc; ++tt) {
+                        const uint32_t c = sm.idx[stage][tt][r];
+                        const double dv = (double)sm.val[stage][tt][r];
+                        double xv[KP];
+                        VecD<KP>::ld(xd + (size_t)c * KP, xv);
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) acc[k] = fma(dv, xv[k], acc[k]);
+                    }
                 }
             }
             __syncwarp();
@@ -418,11 +447,13 @@ __global__ void __launch_bounds__(V2_THREADS, 3)
 constexpr int K2_STAGES = 4;
 constexpr int K2_ITEM_ENTRIES = K2_WARPS * COL_SEG;  // 2048
 
+constexpr int K2_PART_BUFS = 2 * K2_STAGES;  // consumers can run at most K2_STAGES items ahead of a combine
 struct K2Smem {
     uint32_t row[K2_STAGES][K2_ITEM_ENTRIES + 8];
     float val[K2_STAGES][K2_ITEM_ENTRIES + 8];
-    double part[2][K2_WARPS][16];
-    uint64_t full[K2_STAGES], empty[K2_STAGES];
+    ColSeg seg[K2_STAGES][K2_WARPS];  // the item's segment descriptors travel through the ring too
+    double part[K2_PART_BUFS][K2_WARPS][16];
+    uint64_t full[K2_STAGES], empty[K2_STAGES], part_full[K2_PART_BUFS];
 };
 
 // One item = K2_WARPS consecutive segments = one contiguous range of CSC entries.  Consumer warp wi owns
@@ -442,6 +473,7 @@ __global__ void __launch_bounds__(V2_THREADS, 3)
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], K2_WARPS);
         }
+        for (int s = 0; s < K2_PART_BUFS; ++s) mbar_init(&sm.part_full[s], K2_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -456,8 +488,10 @@ __global__ void __launch_bounds__(V2_THREADS, 3)
                 const ColSeg last = segs[min(it * K2_WARPS + K2_WARPS - 1, n_segs - 1)];
                 const uint32_t a0 = first.start & ~3u;
                 const uint32_t bytes = ((last.start + (last.len & 0xffffu) - a0) * 4u + 15u) & ~15u;
+                const uint32_t nseg = (uint32_t)min(K2_WARPS, n_segs - it * K2_WARPS);
                 mbar_wait(&sm.empty[stage], ((j / K2_STAGES) & 1) ^ 1);
-                mbar_expect_tx(&sm.full[stage], 2u * bytes);
+                mbar_expect_tx(&sm.full[stage], 2u * bytes + nseg * (uint32_t)sizeof(ColSeg));
+                bulk_g2s(&sm.seg[stage][0], segs + (size_t)it * K2_WARPS, nseg * (uint32_t)sizeof(ColSeg), &sm.full[stage]);
                 if (bytes) {
                     bulk_g2s(&sm.row[stage][0], csc_row + a0, bytes, &sm.full[stage]);
                     bulk_g2s(&sm.val[stage][0], csc_val + a0, bytes, &sm.full[stage]);
@@ -472,12 +506,12 @@ __global__ void __launch_bounds__(V2_THREADS, 3)
         const int stage = j % K2_STAGES;
         const int sidx = it * K2_WARPS + warp;
         const bool have = sidx < n_segs;
-        ColSeg sg;
-        sg.start = 0; sg.len = 0; sg.col = 0; sg.slot = -1;
-        if (have) sg = segs[sidx];
-        const uint32_t a0 = segs[it * K2_WARPS].start & ~3u;
-        const uint32_t len = sg.len & 0xffffu, run = sg.len >> 16;  // run > 0: head of a run of `run` segments
         mbar_wait(&sm.full[stage], (j / K2_STAGES) & 1);
+        ColSeg sg;
+        sg.start = sm.seg[stage][0].start; sg.len = 0; sg.col = 0; sg.slot = -1;
+        if (have) sg = sm.seg[stage][warp];
+        const uint32_t a0 = sm.seg[stage][0].start & ~3u;
+        const uint32_t len = sg.len & 0xffffu, run = sg.len >> 16;  // run > 0: head of a run of `run` segments
         double acc[KP];
         {
             const uint32_t *rp = &sm.row[stage][sg.start - a0];
@@ -524,9 +558,13 @@ __global__ void __launch_bounds__(V2_THREADS, 3)
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[stage]);
         warp_reduce_scatter<KP>(acc, lane);
-        const int buf = j & 1;
+        // in-CTA combine without a block-wide stall: every warp publishes its partial and arrives on an mbarrier;
+        // only the warps that head a run wait for it, everyone else moves on to the next item
+        const int buf = j % K2_PART_BUFS;
         if (lane_writes<KP>(lane)) sm.part[buf][warp][draw_of_lane<KP>(lane)] = acc[0];
-        consumer_bar_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.part_full[buf]);
+        if (have && run > 0) mbar_wait(&sm.part_full[buf], (j / K2_PART_BUFS) & 1);
         if (have && run > 0 && lane < KP) {
             double s = 0.0;
             for (uint32_t q = 0; q < run; ++q) s += sm.part[buf][warp + q][lane];
@@ -578,15 +616,17 @@ int launch_k1_t(polee_handle *h, const float *x, const double *xd, float *w, boo
     }
     const int grid = std::min(h->n_row_tiles, h->num_sms * 3);
     const size_t smem = sizeof(K1Smem);
-#define K1_LAUNCH2(LPF, WF)                                                                                        \
+    static const bool x_f64 = getenv("POLEE_K1_X") && !strcmp(getenv("POLEE_K1_X"), "f64");
+#define K1_LAUNCH3(LPF, WF, XF)                                                                                    \
     do {                                                                                                           \
-        static bool attr_done = false;                                                                             \
-        if (!attr_done) {                                                                                          \
-            cudaFuncSetAttribute(k1_sell_fwd_tma<KP, LPF, WF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            attr_done = true;                                                                                      \
-        }                                                                                                          \
-        k1_sell_fwd_tma<KP, LPF, WF><<<grid, V2_THREADS, smem, h->stream>>>(h->row_tiles, h->n_row_tiles, h->sell_idx, \
-                                                                            h->sell_val, xd, w, h->row_weight, lp_partial); \
+        cudaFuncSetAttribute(k1_sell_fwd_tma<KP, LPF, WF, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        k1_sell_fwd_tma<KP, LPF, WF, XF><<<grid, V2_THREADS, smem, h->stream>>>(                                   \
+            h->row_tiles, h->n_row_tiles, h->sell_idx, h->sell_val, xd, x, w, h->row_weight, lp_partial);          \
+    } while (0)
+#define K1_LAUNCH2(LPF, WF)                                \
+    do {                                                   \
+        if (x_f64) K1_LAUNCH3(LPF, WF, false);             \
+        else K1_LAUNCH3(LPF, WF, true);                    \
     } while (0)
     if (want_lp) {
         if (wt) K1_LAUNCH2(true, true); else K1_LAUNCH2(true, false);
@@ -594,6 +634,7 @@ int launch_k1_t(polee_handle *h, const float *x, const double *xd, float *w, boo
         if (wt) K1_LAUNCH2(false, true); else K1_LAUNCH2(false, false);
     }
 #undef K1_LAUNCH2
+#undef K1_LAUNCH3
     return POLEE_OK;
 }
 

@@ -12,6 +12,8 @@
 // level-synchronous sweep computes bit-identical values to the reference's serial index-order sweep.
 #include <algorithm>
 #include <cmath>
+#include <climits>
+#include <cstdint>
 #include <cstring>
 
 #include "common.cuh"
@@ -127,6 +129,70 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
         for (int32_t v : top_list) level_of[v] = depth[v];
     }
     make_sched(tb, level_of, top, ml);
+
+    // ---- schedule-order records for the shared-memory kernels
+    std::vector<int32_t> slot_of(N, -2);
+    n_slots = 0;
+    for (const auto &bn : bins)
+        for (int32_t v : bn)
+            if (parent[v] < 0 || is_top[parent[v]]) slot_of[v] = parent[v] < 0 ? -1 : n_slots++;
+    auto make_ssched = [&](const std::vector<std::vector<int32_t>> &bins_nodes, bool is_top_sched, SSchedHost &out) {
+        out.bin_off.assign(1, 0);
+        out.bin_lvl_ptr.assign(1, 0);
+        out.lvl_off.clear();
+        out.recs.clear();
+        out.max_bin_nodes = 0;
+        out.max_bin_levels = 0;
+        std::vector<int32_t> local(N, -1);
+        for (const auto &bn0 : bins_nodes) {
+            // members: the bin's nodes (+ for the top bin: the bottom roots hanging off it, as exchange leaves)
+            std::vector<int32_t> bn(bn0);
+            std::vector<int32_t> lvl_local(bn.size());
+            if (is_top_sched)
+                for (int32_t v : bn0)
+                    if (nodes[v].leaf < 0)
+                        for (int32_t c : {nodes[v].left, nodes[v].right})
+                            if (!is_top[c]) bn.push_back(c);
+            auto lvl = [&](int32_t v) { return is_top_sched ? depth[v] : level_of[v]; };
+            int nl = 0;
+            for (int32_t v : bn) nl = std::max(nl, lvl(v) + 1);
+            std::vector<int32_t> cnt(nl + 1, 0);
+            for (int32_t v : bn) cnt[lvl(v) + 1]++;
+            for (int l = 0; l < nl; ++l) cnt[l + 1] += cnt[l];
+            std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1), order(bn.size());
+            for (int32_t v : bn) {
+                local[v] = cur[lvl(v)]++;
+                order[local[v]] = v;
+            }
+            const int32_t base = (int32_t)out.recs.size();
+            for (int32_t v : order) {
+                SNode r;
+                const bool exch = is_top_sched && !is_top[v];
+                if (exch) {
+                    r.k_or_leaf = INT32_MIN;
+                    r.left = r.right = -1;
+                    r.slot = slot_of[v];
+                } else if (nodes[v].leaf >= 0) {
+                    r.k_or_leaf = -1 - nodes[v].leaf;
+                    r.left = r.right = -1;
+                    r.slot = is_top_sched ? -2 : slot_of[v];
+                } else {
+                    r.k_or_leaf = nodes[v].k;
+                    r.left = local[nodes[v].left];
+                    r.right = local[nodes[v].right];
+                    r.slot = is_top_sched ? (parent[v] < 0 ? -1 : -2) : slot_of[v];
+                }
+                out.recs.push_back(r);
+            }
+            for (int l = 0; l <= nl; ++l) out.lvl_off.push_back(base + cnt[l]);
+            out.bin_lvl_ptr.push_back((int32_t)out.lvl_off.size());
+            out.bin_off.push_back((int32_t)out.recs.size());
+            out.max_bin_nodes = std::max(out.max_bin_nodes, (int)bn.size());
+            out.max_bin_levels = std::max(out.max_bin_levels, nl);
+        }
+    };
+    make_ssched(bins, false, s_bottom);
+    make_ssched(tb, true, s_top);
     return "";
 }
 
@@ -180,8 +246,17 @@ void TreeDev::release() {
         cudaFree(s->sch_node);
         *s = TreeSchedDev();
     }
+    for (SSchedDev *s : {&s_top, &s_bottom}) {
+        cudaFree(s->bin_off);
+        cudaFree(s->bin_lvl_ptr);
+        cudaFree(s->lvl_off);
+        cudaFree(s->recs);
+        *s = SSchedDev();
+    }
     nodes = nullptr;
     n = N = 0;
+    n_slots = 0;
+    smem_path = false;
 }
 
 static cudaError_t up(const std::vector<int32_t> &v, int32_t **d) {
@@ -211,6 +286,23 @@ std::string upload_tree(const TreeHost &th, TreeDev &td) {
             ml = std::max(ml, hs[s]->bin_lvl_ptr[b + 1] - hs[s]->bin_lvl_ptr[b] - 1);
         ds[s]->max_levels = ml;
     }
+    const SSchedHost *hss[2] = {&th.s_top, &th.s_bottom};
+    SSchedDev *dss[2] = {&td.s_top, &td.s_bottom};
+    for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
+        e = up(hss[s]->bin_off, &dss[s]->bin_off);
+        if (e == cudaSuccess) e = up(hss[s]->bin_lvl_ptr, &dss[s]->bin_lvl_ptr);
+        if (e == cudaSuccess) e = up(hss[s]->lvl_off, &dss[s]->lvl_off);
+        if (e == cudaSuccess) {
+            size_t bytes = std::max<size_t>(hss[s]->recs.size(), 1) * sizeof(SNode);
+            e = cudaMalloc((void **)&dss[s]->recs, bytes);
+            if (e == cudaSuccess && !hss[s]->recs.empty())
+                e = cudaMemcpy(dss[s]->recs, hss[s]->recs.data(), hss[s]->recs.size() * sizeof(SNode), cudaMemcpyHostToDevice);
+        }
+        dss[s]->nbins = hss[s]->nbins();
+        dss[s]->max_bin_nodes = hss[s]->max_bin_nodes;
+        dss[s]->max_bin_levels = hss[s]->max_bin_levels;
+    }
+    td.n_slots = th.n_slots;
     if (e != cudaSuccess) return std::string("upload_tree: ") + cudaGetErrorString(e);
     return "";
 }

@@ -17,6 +17,10 @@
 // with explicit _rn intrinsics so that nothing is contracted into an FMA the reference does not have.
 #include <math_constants.h>
 
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace polee {
@@ -227,6 +231,219 @@ __global__ void __launch_bounds__(THREADS)
     }
 }
 
+// ================================================================ shared-memory tree kernels
+// Same arithmetic as k3_tree_fwd / k3_tree_bwd above, but a CTA first pulls everything its bin needs into shared
+// memory with coalesced loads (schedule-order records, ys, the u of its subtree roots / the G of its leaves), runs
+// the level loops entirely out of shared memory (one __syncthreads per level, no global load on the critical path)
+// and writes its results back at the end.  grid = (bins, KP / KPC): KPC draws per CTA (8 for the bottom forests,
+// 1 for the top part so that a few thousand nodes fit).  Bottom subtree roots exchange u (top -> bottom) and G
+// (bottom -> top) through [slot][KP] arrays.  The backward kernel recomputes u from ys instead of reading it back.
+template <int KPC, int THREADS>
+__device__ __forceinline__ void block_reduce_kc(double v, double *red, double *out /* [KPC] */) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int span = THREADS / KPC / 2; span >= 1; span >>= 1) {
+        if ((int)threadIdx.x < span * KPC) red[threadIdx.x] += red[threadIdx.x + span * KPC];
+        __syncthreads();
+    }
+    if (threadIdx.x < KPC) out[threadIdx.x] = red[threadIdx.x];
+    __syncthreads();
+}
+
+template <int KP, int KPC, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    k3s_tree_fwd(const int32_t *__restrict__ bin_off, const int32_t *__restrict__ bin_lvl_ptr,
+                 const int32_t *__restrict__ lvl_off, const SNode *__restrict__ recs, const double *__restrict__ ys,
+                 double *__restrict__ root_us, float *__restrict__ x, double *__restrict__ xd, int clamp_x,
+                 const float *__restrict__ efflen, double *__restrict__ S_partial, int part_base, int want_ladj,
+                 double *__restrict__ ladj_partial) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ double red[THREADS];
+    const int q0 = bin_off[blockIdx.x], nb = bin_off[blockIdx.x + 1] - q0;
+    SNode *rec_s = reinterpret_cast<SNode *>(smraw);
+    double *us_s = reinterpret_cast<double *>(smraw + (size_t)nb * sizeof(SNode));
+    double *ys_s = us_s + (size_t)nb * KPC;
+    int *lvl_s = reinterpret_cast<int *>(ys_s + (size_t)nb * KPC);
+    const int kk = threadIdx.x % KPC, slot_t = threadIdx.x / KPC, k = blockIdx.y * KPC + kk;
+    constexpr int NPP = THREADS / KPC;
+    const int l0 = bin_lvl_ptr[blockIdx.x], nlev = bin_lvl_ptr[blockIdx.x + 1] - 1 - l0;
+
+    for (int p = threadIdx.x; p < nb; p += THREADS) rec_s[p] = recs[q0 + p];
+    for (int l = threadIdx.x; l <= nlev; l += THREADS) lvl_s[l] = lvl_off[l0 + l] - q0;
+    __syncthreads();
+    // gather phase, 4 positions per thread in flight (the loads are independent: batch them for MLP)
+    for (int base = slot_t; base < nb; base += 4 * NPP) {
+        SNode r[4];
+        double yv[4], uv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * NPP;
+            r[u] = p < nb ? rec_s[p] : SNode{-1, -1, -1, -2};
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            yv[u] = 0.0;
+            uv[u] = 1.0;
+            if (r[u].k_or_leaf >= 0) yv[u] = ys[(size_t)r[u].k_or_leaf * KP + k];
+            if (r[u].slot >= 0 && r[u].k_or_leaf != INT32_MIN) uv[u] = root_us[(size_t)r[u].slot * KP + k];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * NPP;
+            if (p < nb) {
+                if (r[u].k_or_leaf >= 0) ys_s[p * KPC + kk] = yv[u];
+                if (r[u].slot >= -1 && r[u].k_or_leaf != INT32_MIN) us_s[p * KPC + kk] = uv[u];
+            }
+        }
+    }
+    __syncthreads();
+
+    double sacc = 0.0, lacc = 0.0;
+    for (int l = 0; l < nlev; ++l) {
+        const int lo = lvl_s[l], hi = lvl_s[l + 1];
+        for (int p = lo + slot_t; p < hi; p += NPP) {
+            const SNode r = rec_s[p];
+            const double ui = us_s[p * KPC + kk];
+            if (r.k_or_leaf >= 0) {
+                const double y = ys_s[p * KPC + kk];
+                us_s[r.left * KPC + kk] = __dmul_rn(y, ui);
+                us_s[r.right * KPC + kk] = __dmul_rn(__dsub_rn(1.0, y), ui);
+                if (want_ladj) lacc += log(ui);
+            } else if (r.k_or_leaf == INT32_MIN) {
+                root_us[(size_t)r.slot * KP + k] = ui;  // a bottom subtree root: hand u over
+            } else {
+                const int leaf = -1 - r.k_or_leaf;
+                float xv = (float)ui;
+                double d = (double)xv;
+                xv = (float)(d > 1e-16 ? d : 1e-16);  // ptt.jl:136-137
+                if (clamp_x) {                         // clamp!(xs, 1e-10, 1 - 1e-10) on a Float32 vector
+                    d = (double)xv;
+                    d = fmin(fmax(d, 1e-10), 1.0 - 1e-10);
+                    xv = (float)d;
+                }
+                x[(size_t)leaf * KP + k] = xv;
+                xd[(size_t)leaf * KP + k] = (double)xv;
+                if (efflen) sacc = __dadd_rn(sacc, (double)__fdiv_rn(xv, efflen[leaf]));
+            }
+        }
+        __syncthreads();
+    }
+    if (S_partial)
+        block_reduce_kc<KPC, THREADS>(sacc, red, S_partial + (size_t)(part_base + blockIdx.x) * KP + blockIdx.y * KPC);
+    if (want_ladj)
+        block_reduce_kc<KPC, THREADS>(lacc, red, ladj_partial + (size_t)(part_base + blockIdx.x) * KP + blockIdx.y * KPC);
+}
+
+template <int KP, int KPC, int THREADS, int MINB, bool WITH_LADJ>
+__global__ void __launch_bounds__(THREADS, MINB)
+    k3s_tree_bwd(const int32_t *__restrict__ bin_off, const int32_t *__restrict__ bin_lvl_ptr,
+                 const int32_t *__restrict__ lvl_off, const SNode *__restrict__ recs, const double *__restrict__ ys,
+                 const double *__restrict__ root_us, float2 *__restrict__ root_G, const double *__restrict__ g,
+                 const float *__restrict__ efflen_adj, const double *__restrict__ S, double *__restrict__ ygrad,
+                 double *__restrict__ xgrad_out) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int q0 = bin_off[blockIdx.x], nb = bin_off[blockIdx.x + 1] - q0;
+    SNode *rec_s = reinterpret_cast<SNode *>(smraw);
+    double *us_s = reinterpret_cast<double *>(smraw + (size_t)nb * sizeof(SNode));
+    double *ys_s = us_s + (size_t)nb * KPC;
+    float2 *G_s = reinterpret_cast<float2 *>(ys_s + (size_t)nb * KPC);
+    int *lvl_s = reinterpret_cast<int *>(G_s + (size_t)nb * KPC);
+    const int kk = threadIdx.x % KPC, slot_t = threadIdx.x / KPC, k = blockIdx.y * KPC + kk;
+    constexpr int NPP = THREADS / KPC;
+    const int l0 = bin_lvl_ptr[blockIdx.x], nlev = bin_lvl_ptr[blockIdx.x + 1] - 1 - l0;
+
+    for (int p = threadIdx.x; p < nb; p += THREADS) rec_s[p] = recs[q0 + p];
+    for (int l = threadIdx.x; l <= nlev; l += THREADS) lvl_s[l] = lvl_off[l0 + l] - q0;
+    __syncthreads();
+    const double Sk = efflen_adj ? S[k] : 1.0;
+    for (int base = slot_t; base < nb; base += 4 * NPP) {
+        SNode r[4];
+        double v0[4], uv[4];
+        float adj[4];
+        float2 gx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * NPP;
+            r[u] = p < nb ? rec_s[p] : SNode{-1, -1, -1, -2};
+            if (p >= nb) r[u].k_or_leaf = INT32_MIN + 1;  // nothing to load
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v0[u] = 0.0; uv[u] = 1.0; adj[u] = 0.0f; gx[u] = make_float2(0.f, 0.f);
+            if (r[u].k_or_leaf >= 0) {
+                v0[u] = ys[(size_t)r[u].k_or_leaf * KP + k];
+            } else if (r[u].k_or_leaf == INT32_MIN) {
+                gx[u] = root_G[(size_t)r[u].slot * KP + k];
+            } else if (r[u].k_or_leaf != INT32_MIN + 1) {
+                const int leaf = -1 - r[u].k_or_leaf;
+                v0[u] = g[(size_t)leaf * KP + k];
+                if (efflen_adj) adj[u] = efflen_adj[leaf];
+            }
+            if (r[u].slot >= 0 && r[u].k_or_leaf != INT32_MIN) uv[u] = root_us[(size_t)r[u].slot * KP + k];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * NPP;
+            if (p >= nb) continue;
+            if (r[u].k_or_leaf >= 0) {
+                ys_s[p * KPC + kk] = v0[u];
+            } else if (r[u].k_or_leaf == INT32_MIN) {
+                G_s[p * KPC + kk] = gx[u];
+            } else {
+                const int leaf = -1 - r[u].k_or_leaf;
+                double gv = v0[u];
+                if (efflen_adj) gv = __dsub_rn(gv, __ddiv_rn((double)adj[u], Sk));  // likelihood.jl:105
+                if (xgrad_out) xgrad_out[(size_t)leaf * KP + k] = gv;
+                G_s[p * KPC + kk] = make_float2((float)gv, 0.0f);
+            }
+            if (r[u].slot >= -1 && r[u].k_or_leaf != INT32_MIN) us_s[p * KPC + kk] = uv[u];
+        }
+    }
+    __syncthreads();
+
+    // forward recompute of u (same operations as k3s_tree_fwd -> same bits)
+    for (int l = 0; l < nlev; ++l) {
+        const int lo = lvl_s[l], hi = lvl_s[l + 1];
+        for (int p = lo + slot_t; p < hi; p += NPP) {
+            const SNode r = rec_s[p];
+            if (r.k_or_leaf >= 0) {
+                const double ui = us_s[p * KPC + kk], y = ys_s[p * KPC + kk];
+                us_s[r.left * KPC + kk] = __dmul_rn(y, ui);
+                us_s[r.right * KPC + kk] = __dmul_rn(__dsub_rn(1.0, y), ui);
+            }
+        }
+        __syncthreads();
+    }
+    // backward sweep
+    for (int l = nlev - 1; l >= 0; --l) {
+        const int lo = lvl_s[l], hi = lvl_s[l + 1];
+        for (int p = lo + slot_t; p < hi; p += NPP) {
+            const SNode r = rec_s[p];
+            if (r.k_or_leaf >= 0) {
+                const float2 gl = G_s[r.left * KPC + kk], gr = G_s[r.right * KPC + kk];
+                const double y = ys_s[p * KPC + kk], ui = us_s[p * KPC + kk];
+                const double omy = __dsub_rn(1.0, y);
+                float2 out;
+                out.x = (float)__dadd_rn(__dmul_rn(y, (double)gl.x), __dmul_rn(omy, (double)gr.x));
+                if (WITH_LADJ) {
+                    const float d = __fsub_rn(__fadd_rn(gl.x, gl.y), __fadd_rn(gr.x, gr.y));
+                    ygrad[(size_t)r.k_or_leaf * KP + k] = (double)(float)__dmul_rn(ui, (double)d);
+                    out.y = (float)__dadd_rn(__dadd_rn(__ddiv_rn(1.0, ui), __dmul_rn(y, (double)gl.y)),
+                                             __dmul_rn(omy, (double)gr.y));
+                } else {
+                    const float d = __fsub_rn(gl.x, gr.x);
+                    ygrad[(size_t)r.k_or_leaf * KP + k] = __dmul_rn(ui, (double)d);
+                    out.y = 0.0f;
+                }
+                G_s[p * KPC + kk] = out;
+            }
+            if (r.slot >= 0 && r.k_or_leaf != INT32_MIN && l == 0)
+                root_G[(size_t)r.slot * KP + k] = G_s[p * KPC + kk];  // bottom subtree root: hand G to the top part
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- reparameterisation backward + ADAM
 struct AdamCfg {
     double max_step_mu, max_step_omega, max_step_alpha, max_step_z;
@@ -344,10 +561,10 @@ __global__ void k3_elbo(int K, int KP, const double *__restrict__ lp, const doub
 #define CK(expr) POLEE_CUDA_CHECK(h, expr)
 
 void release_work_buffers(polee_handle *h) {
-    void *ptrs[] = {h->zs0, h->zs, h->ys, h->ygrad, h->us, h->G, h->x, h->xd, h->w, h->g, h->seg_partial, h->S_partial,
+    void *ptrs[] = {h->zs0, h->zs, h->ys, h->ygrad, h->us, h->G, h->root_us, h->root_G, h->x, h->xd, h->w, h->g, h->seg_partial, h->S_partial,
                     h->S, h->lp_partial, h->ladj_partial, h->grad_out};
     for (void *p : ptrs) cudaFree(p);
-    h->zs0 = h->zs = nullptr; h->ys = h->ygrad = h->us = nullptr; h->G = nullptr; h->x = h->w = nullptr; h->xd = nullptr;
+    h->zs0 = h->zs = nullptr; h->ys = h->ygrad = h->us = nullptr; h->G = nullptr; h->x = h->w = nullptr; h->xd = nullptr; h->root_us = nullptr; h->root_G = nullptr;
     h->g = h->seg_partial = h->S_partial = h->S = h->lp_partial = h->ladj_partial = nullptr;
     h->grad_out = nullptr;
     h->work_KP = 0;
@@ -369,6 +586,8 @@ int ensure_work_buffers(polee_handle *h, int KP) {
     CK(cudaMalloc((void **)&h->ygrad, sizeof(double) * nm1 * KP));
     CK(cudaMalloc((void **)&h->us, sizeof(double) * N * KP));
     CK(cudaMalloc((void **)&h->G, sizeof(float2) * N * KP));
+    CK(cudaMalloc((void **)&h->root_us, sizeof(double) * std::max(h->td.n_slots, 1) * KP));
+    CK(cudaMalloc((void **)&h->root_G, sizeof(float2) * std::max(h->td.n_slots, 1) * KP));
     CK(cudaMalloc((void **)&h->x, sizeof(float) * n * KP));
     CK(cudaMalloc((void **)&h->xd, sizeof(double) * n * KP));
     CK(cudaMalloc((void **)&h->g, sizeof(double) * (n + 1) * KP));
@@ -410,11 +629,123 @@ int launch_reparam_fwd(polee_handle *h, int KP, int K, const float *noise, int64
     return POLEE_OK;
 }
 
+constexpr int S_BOT_THREADS = 512;
+constexpr int S_TOP_THREADS = 1024;
+
+template <typename F>
+static void set_smem_attr(F func, size_t bytes) {
+    cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// bottom-forest launch variants (draws per CTA, threads, min CTAs/SM); POLEE_TREE_VARIANT picks one at run time
+static int tree_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("POLEE_TREE_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+static int variant_kpc(int KP) {
+    const int v = tree_variant();
+    const int want = v == 1 ? 4 : (v == 2 ? 2 : 8);
+    return KP < want ? KP : want;
+}
+
+template <int KP, int KPC, int THREADS, int MINB>
+static void launch_fwd_bottom_v(polee_handle *h, int clamp_x, const float *eff, double *Sp, int want_ladj, double *ladj_tree) {
+    const TreeDev &td = h->td;
+    const size_t smem = (size_t)td.s_bottom.max_bin_nodes * (sizeof(SNode) + 16 * KPC) + 4 * (td.s_bottom.max_bin_levels + 2);
+    auto fn = k3s_tree_fwd<KP, KPC, THREADS, MINB>;
+    set_smem_attr(fn, smem);
+    fn<<<dim3(td.s_bottom.nbins, KP / KPC), THREADS, smem, h->stream>>>(
+        td.s_bottom.bin_off, td.s_bottom.bin_lvl_ptr, td.s_bottom.lvl_off, td.s_bottom.recs, h->ys, h->root_us, h->x, h->xd,
+        clamp_x, eff, Sp, 1, want_ladj, ladj_tree);
+}
+template <int KP, int KPC, int THREADS, int MINB, bool WITH_LADJ>
+static void launch_bwd_bottom_v(polee_handle *h, const float *adj, double *xgrad_out) {
+    const TreeDev &td = h->td;
+    const size_t smem = (size_t)td.s_bottom.max_bin_nodes * (sizeof(SNode) + 24 * KPC) + 4 * (td.s_bottom.max_bin_levels + 2);
+    auto fn = k3s_tree_bwd<KP, KPC, THREADS, MINB, WITH_LADJ>;
+    set_smem_attr(fn, smem);
+    fn<<<dim3(td.s_bottom.nbins, KP / KPC), THREADS, smem, h->stream>>>(
+        td.s_bottom.bin_off, td.s_bottom.bin_lvl_ptr, td.s_bottom.lvl_off, td.s_bottom.recs, h->ys, h->root_us, h->root_G, h->g,
+        adj, h->S, h->ygrad, xgrad_out);
+}
+
+template <int KP>
+static int launch_tree_fwd_smem(polee_handle *h, int clamp_x, const float *eff, double *Sp, int want_ladj, double *ladj_tree) {
+    const TreeDev &td = h->td;
+    if (td.s_top.nbins > 0) {
+        const size_t smem = (size_t)td.s_top.max_bin_nodes * (sizeof(SNode) + 16) + 4 * (td.s_top.max_bin_levels + 2);
+        auto fn = k3s_tree_fwd<KP, 1, S_TOP_THREADS, 1>;
+        set_smem_attr(fn, smem);
+        fn<<<dim3(td.s_top.nbins, KP), S_TOP_THREADS, smem, h->stream>>>(
+            td.s_top.bin_off, td.s_top.bin_lvl_ptr, td.s_top.lvl_off, td.s_top.recs, h->ys, h->root_us, h->x, h->xd, clamp_x,
+            eff, Sp, 0, want_ladj, ladj_tree);
+    }
+    if (td.s_bottom.nbins > 0) {
+        if constexpr (KP == 8) {
+            const int v = tree_variant();
+            if (v == 1) launch_fwd_bottom_v<8, 8, 512, 1>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
+            else if (v == 2) launch_fwd_bottom_v<8, 2, 256, 6>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
+            else if (v == 3) launch_fwd_bottom_v<8, 8, 256, 2>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
+            else launch_fwd_bottom_v<8, 4, 256, 3>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
+        } else {
+            launch_fwd_bottom_v<KP, (KP < 8 ? KP : 8), 256, 2>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
+        }
+    }
+    return POLEE_OK;
+}
+
+template <int KP, bool WITH_LADJ>
+static int launch_tree_bwd_smem(polee_handle *h, const float *adj, double *xgrad_out) {
+    const TreeDev &td = h->td;
+    if (td.s_bottom.nbins > 0) {
+        if constexpr (KP == 8) {
+            const int v = tree_variant();
+            if (v == 1) launch_bwd_bottom_v<8, 8, 512, 1, WITH_LADJ>(h, adj, xgrad_out);
+            else if (v == 2) launch_bwd_bottom_v<8, 2, 256, 6, WITH_LADJ>(h, adj, xgrad_out);
+            else if (v == 3) launch_bwd_bottom_v<8, 8, 256, 2, WITH_LADJ>(h, adj, xgrad_out);
+            else launch_bwd_bottom_v<8, 4, 256, 3, WITH_LADJ>(h, adj, xgrad_out);
+        } else {
+            launch_bwd_bottom_v<KP, (KP < 8 ? KP : 8), 256, 2, WITH_LADJ>(h, adj, xgrad_out);
+        }
+    }
+    if (td.s_top.nbins > 0) {
+        const size_t smem = (size_t)td.s_top.max_bin_nodes * (sizeof(SNode) + 24) + 4 * (td.s_top.max_bin_levels + 2);
+        auto fn = k3s_tree_bwd<KP, 1, S_TOP_THREADS, 1, WITH_LADJ>;
+        set_smem_attr(fn, smem);
+        fn<<<dim3(td.s_top.nbins, KP), S_TOP_THREADS, smem, h->stream>>>(
+            td.s_top.bin_off, td.s_top.bin_lvl_ptr, td.s_top.lvl_off, td.s_top.recs, h->ys, h->root_us, h->root_G, h->g, adj,
+            h->S, h->ygrad, xgrad_out);
+    }
+    return POLEE_OK;
+}
+
+// the shared-memory kernels need the largest bin (bottom: <= bin_nodes; top: top nodes + subtree roots, one draw
+// per CTA) to fit in one CTA's shared memory; otherwise (very deep trees, e.g. :sequential) the global-memory
+// kernels above are used
+static bool smem_path_ok(const polee_handle *h, int KP) {
+    const TreeDev &td = h->td;
+    const int KPC = KP < 8 ? KP : 8;
+    const size_t limit = 200 * 1024;
+    const char *env = getenv("POLEE_TREE_PATH");
+    if (env && !strcmp(env, "global")) return false;
+    return (size_t)td.s_bottom.max_bin_nodes * (sizeof(SNode) + 24 * KPC) + 4 * (td.s_bottom.max_bin_levels + 2) <= limit &&
+           (size_t)td.s_top.max_bin_nodes * (sizeof(SNode) + 24) + 4 * (td.s_top.max_bin_levels + 2) <= limit;
+}
+
 int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_ladj) {
     const TreeDev &td = h->td;
     double *ladj_tree = h->ladj_partial + (size_t)2 * elem_ctas(h, KP) * KP;
     const float *eff = want_S ? h->efflen : nullptr;
     double *Sp = want_S ? h->S_partial : nullptr;
+    if (smem_path_ok(h, KP)) {
+        int rc = POLEE_OK;
+        DISPATCH_KP(KP, rc = launch_tree_fwd_smem<KPC>(h, clamp_x, eff, Sp, want_ladj, ladj_tree));
+        return rc;
+    }
     if (td.top.nbins > 0) {
         DISPATCH_KP(KP, (k3_tree_fwd<KPC, TOP_THREADS><<<td.top.nbins, TOP_THREADS, 0, h->stream>>>(
                             td.top.bin_lvl_ptr, td.top.lvl_off, td.top.sch_node, td.nodes, h->ys, h->us, h->x, h->xd, clamp_x,
@@ -436,6 +767,15 @@ int launch_mid(polee_handle *h, int KP, int advance) {
 int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, double *xgrad_out) {
     const TreeDev &td = h->td;
     const float *adj = apply_efflen ? h->efflen_adj : nullptr;
+    if (smem_path_ok(h, KP)) {
+        int rc = POLEE_OK;
+        if (with_ladj) {
+            DISPATCH_KP(KP, (rc = launch_tree_bwd_smem<KPC, true>(h, adj, xgrad_out)));
+        } else {
+            DISPATCH_KP(KP, (rc = launch_tree_bwd_smem<KPC, false>(h, adj, xgrad_out)));
+        }
+        return rc;
+    }
 #define BWD(SCHED, THREADS)                                                                                          \
     if (with_ladj) {                                                                                                 \
         DISPATCH_KP(KP, (k3_tree_bwd<KPC, THREADS, true><<<SCHED.nbins, THREADS, 0, h->stream>>>(                    \
