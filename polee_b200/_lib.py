@@ -66,7 +66,7 @@ def load_library():
     if not os.path.exists(LIB_PATH):
         raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(or `make -C polee_b200/csrc`). There is no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(LIB_PATH)
     lib.polee_last_error.restype = C.c_char_p
     lib.polee_last_error.argtypes = [C.c_void_p]
     lib.polee_hsb_last_error.restype = C.c_char_p

@@ -5,9 +5,44 @@
 #include <cstring>
 #include <mutex>
 
+#include <dlfcn.h>
+
 #include "common.cuh"
 
 using namespace polee;
+
+#ifdef POLEE_WITH_NCCL
+// NCCL is bound lazily with dlopen: single-GPU users need no NCCL at all, and a host process that already
+// carries its own libnccl.so.2 (e.g. PyTorch's bundled one) keeps using exactly that copy.
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (lib) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(lib, "ncclAllReduce");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(lib, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+        }
+    }
+    return api;
+}
+}  // namespace
+#endif
 
 static std::string g_create_error;
 static std::mutex g_err_mu;
@@ -106,7 +141,7 @@ extern "C" int polee_destroy(polee_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_graph(h);
 #ifdef POLEE_WITH_NCCL
-    if (h->comm) ncclCommDestroy(h->comm);
+    if (h->comm) nccl_api().CommDestroy(h->comm);
 #endif
     release_work_buffers(h);
     release_matrix(h);
@@ -348,8 +383,8 @@ static int launch_step_sequence(polee_handle *h, bool do_adam, float *grad_out, 
 #ifdef POLEE_WITH_NCCL
     if (h->nranks > 1) {
         size_t count = (size_t)(h->n + (want_vals ? 1 : 0)) * KP;
-        ncclResult_t r = ncclAllReduce(h->g, h->g, count, ncclDouble, ncclSum, h->comm, h->stream);
-        if (r != ncclSuccess) return h->fail(POLEE_ENCCL, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+        ncclResult_t r = nccl_api().AllReduce(h->g, h->g, count, ncclDouble, ncclSum, h->comm, h->stream);
+        if (r != ncclSuccess) return h->fail(POLEE_ENCCL, std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r));
     }
 #endif
     if ((rc = launch_tree_bwd(h, KP, lsn, apply_eff, xgrad_out))) return rc;
@@ -706,7 +741,7 @@ extern "C" int polee_comm_unique_id(char id[128]) {
 #ifdef POLEE_WITH_NCCL
     static_assert(sizeof(ncclUniqueId) <= 128, "ncclUniqueId does not fit");
     ncclUniqueId u;
-    if (ncclGetUniqueId(&u) != ncclSuccess) return POLEE_ENCCL;
+    if (!nccl_api().ok || nccl_api().GetUniqueId(&u) != ncclSuccess) return POLEE_ENCCL;
     std::memset(id, 0, 128);
     std::memcpy(id, &u, sizeof(u));
     return POLEE_OK;
@@ -720,15 +755,16 @@ extern "C" int polee_comm_init(polee_handle *h, int32_t nranks, int32_t rank, co
     CHECK_H(h);
 #ifdef POLEE_WITH_NCCL
     if (nranks < 1 || rank < 0 || rank >= nranks) return h->fail(POLEE_EINVAL, "comm_init: bad rank / nranks");
+    if (!nccl_api().ok) return h->fail(POLEE_ENCCL, "libnccl.so.2 could not be loaded");
     drop_graph(h);
-    if (h->comm) { ncclCommDestroy(h->comm); h->comm = nullptr; }
+    if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     h->nranks = nranks;
     h->rank = rank;
     if (nranks == 1) return POLEE_OK;
     ncclUniqueId u;
     std::memcpy(&u, id, sizeof(u));
-    ncclResult_t r = ncclCommInitRank(&h->comm, nranks, u, rank);
-    if (r != ncclSuccess) return h->fail(POLEE_ENCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    ncclResult_t r = nccl_api().CommInitRank(&h->comm, nranks, u, rank);
+    if (r != ncclSuccess) return h->fail(POLEE_ENCCL, std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(r));
     return POLEE_OK;
 #else
     (void)nranks; (void)rank; (void)id;

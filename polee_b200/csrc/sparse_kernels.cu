@@ -263,6 +263,42 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// one short row (L <= 4 entries, the common case): everything in Float32 -- L gathers in flight, L FFMAs per draw,
+// one MUFU reciprocal per draw; no Float64 and no conversions at all
+template <int KP, int L, bool WEIGHTED>
+__device__ __forceinline__ void k1_short_row(const uint32_t (*sidx)[ROW_TILE], const float (*sval)[ROW_TILE], uint32_t r,
+                                             const float *__restrict__ xf, float *__restrict__ wout, float wt,
+                                             float *pout) {
+    float xv[L][KP], v[L];
+    const char *xb = reinterpret_cast<const char *>(xf);
+#pragma unroll
+    for (int u = 0; u < L; ++u) {
+        const uint32_t c = sidx[u][r];
+        v[u] = sval[u][r];
+        Vec<KP>::ld(reinterpret_cast<const float *>(xb + (size_t)c * (KP * 4)), xv[u]);
+    }
+    float facc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) facc[k] = v[0] * xv[0][k];
+#pragma unroll
+    for (int u = 1; u < L; ++u)
+#pragma unroll
+        for (int k = 0; k < KP; ++k) facc[k] = fmaf(v[u], xv[u][k], facc[k]);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        if (pout) pout[k] = facc[k];
+        const float rc = rcp_approx(facc[k]);
+        facc[k] = WEIGHTED ? rc * wt : rc;
+    }
+    Vec<KP>::st(wout, facc);
+}
+
 template <int KP>
 struct VecD {  // KP doubles; 256-bit requests (sm_100) where KP allows
     static __device__ __forceinline__ void ld(const double *p, double *v) {
@@ -344,6 +380,47 @@ __global__ void __launch_bounds__(V2_THREADS, 3)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const RowTile t = tiles[tile];
         const bool active = r < t.nrows;
+        if constexpr (XF32) {
+            if (t.len <= 4) {  // warp-uniform: the whole tile is one ring item
+                const int stage = item % K1_STAGES;
+                mbar_wait(&sm.full[stage], (item / K1_STAGES) & 1);
+                float pv[KP];
+#pragma unroll
+                for (int k = 0; k < KP; ++k) pv[k] = 1.0f;
+                float wt = 1.0f;
+                if (active) {
+                    if (WEIGHTED) wt = row_weight[t.row0 + r];
+                    float *wout = w + (size_t)(t.row0 + r) * KP;
+                    float *pp = LP ? pv : nullptr;
+                    switch (t.len) {
+                        case 1: k1_short_row<KP, 1, WEIGHTED>(sm.idx[stage], sm.val[stage], r, xf, wout, wt, pp); break;
+                        case 2: k1_short_row<KP, 2, WEIGHTED>(sm.idx[stage], sm.val[stage], r, xf, wout, wt, pp); break;
+                        case 3: k1_short_row<KP, 3, WEIGHTED>(sm.idx[stage], sm.val[stage], r, xf, wout, wt, pp); break;
+                        default: k1_short_row<KP, 4, WEIGHTED>(sm.idx[stage], sm.val[stage], r, xf, wout, wt, pp); break;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[stage]);
+                ++item;
+                if constexpr (LP) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        double v = active ? (WEIGHTED ? log((double)pv[k]) * (double)wt : log((double)pv[k])) : 0.0;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        if (lane == 0) sm.lpsm[warp][k] = v;
+                    }
+                    consumer_bar_sync();
+                    if (threadIdx.x < KP) {
+                        double sacc = 0.0;
+                        for (int wi = 0; wi < V2_CONSUMER_WARPS; ++wi) sacc += sm.lpsm[wi][threadIdx.x];
+                        lp_partial[(size_t)tile * KP + threadIdx.x] = sacc;
+                    }
+                    consumer_bar_sync();
+                }
+                continue;
+            }
+        }
         double acc[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) acc[k] = 0.0;
@@ -460,7 +537,7 @@ struct K2Smem {
 // segment wi of the item.  FAST: the lane's <= COL_SEG/32 products are accumulated in Float32, then widened
 // and reduced in Float64 (lane -> warp butterfly -> segments of a column inside the CTA -> k2_combine);
 // EXACT: every product is a Float64 FMA.  Fixed order everywhere: deterministic, no atomics.
-template <int KP, bool EXACT>
+template <int KP, bool EXACT, bool PREFETCH>
 __global__ void __launch_bounds__(V2_THREADS, 3)
     k2_csc_grad_tma(const ColSeg *__restrict__ segs, int n_segs, const uint32_t *__restrict__ csc_row,
                     const float *__restrict__ csc_val, const float *__restrict__ w, double *__restrict__ g,
@@ -480,15 +557,20 @@ __global__ void __launch_bounds__(V2_THREADS, 3)
     const int n_items = (n_segs + K2_WARPS - 1) / K2_WARPS;
 
     if (warp == K2_WARPS) {
-        if (lane == 0) {
-            int j = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
-                const int stage = j % K2_STAGES;
-                const ColSeg first = segs[it * K2_WARPS];
-                const ColSeg last = segs[min(it * K2_WARPS + K2_WARPS - 1, n_segs - 1)];
-                const uint32_t a0 = first.start & ~3u;
-                const uint32_t bytes = ((last.start + (last.len & 0xffffu) - a0) * 4u + 15u) & ~15u;
-                const uint32_t nseg = (uint32_t)min(K2_WARPS, n_segs - it * K2_WARPS);
+        // producer warp.  Lane 0 keeps the ring full; then the whole warp walks the row ids of the item that
+        // landed one iteration earlier and issues L2 prefetches for the w rows the consumers are about to gather:
+        // prefetches hold no registers, so they add memory-level parallelism the register file cannot.
+        int j = 0;
+        uint32_t prev_a0 = 0, prev_cnt = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+            const int stage = j % K2_STAGES;
+            const ColSeg first = segs[it * K2_WARPS];
+            const ColSeg last = segs[min(it * K2_WARPS + K2_WARPS - 1, n_segs - 1)];
+            const uint32_t a0 = first.start & ~3u;
+            const uint32_t cnt = last.start + (last.len & 0xffffu) - a0;
+            const uint32_t bytes = (cnt * 4u + 15u) & ~15u;
+            const uint32_t nseg = (uint32_t)min(K2_WARPS, n_segs - it * K2_WARPS);
+            if (lane == 0) {
                 mbar_wait(&sm.empty[stage], ((j / K2_STAGES) & 1) ^ 1);
                 mbar_expect_tx(&sm.full[stage], 2u * bytes + nseg * (uint32_t)sizeof(ColSeg));
                 bulk_g2s(&sm.seg[stage][0], segs + (size_t)it * K2_WARPS, nseg * (uint32_t)sizeof(ColSeg), &sm.full[stage]);
@@ -497,7 +579,19 @@ __global__ void __launch_bounds__(V2_THREADS, 3)
                     bulk_g2s(&sm.val[stage][0], csc_val + a0, bytes, &sm.full[stage]);
                 }
             }
+            __syncwarp();
+            if (PREFETCH && j > 0) {
+                const int ps = (j - 1) % K2_STAGES;
+                mbar_wait(&sm.full[ps], ((j - 1) / K2_STAGES) & 1);
+                for (uint32_t e = lane; e < prev_cnt; e += 32) {
+                    const uint32_t r = sm.row[ps][e];
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(w + (size_t)r * KP));
+                }
+            }
+            prev_a0 = a0;
+            prev_cnt = cnt;
         }
+        (void)prev_a0;
         return;
     }
 
@@ -644,23 +738,20 @@ int launch_k2_t(polee_handle *h, const float *w, double *g) {
         const int n_items = (h->n_segs + K2_WARPS - 1) / K2_WARPS;
         const int grid = std::min(n_items, h->num_sms * 3);
         const size_t smem = sizeof(K2Smem);
+        // the producer-warp L2 prefetch of w rows measured SLOWER on B200 (0.508 vs 0.483 ms at C3): opt-in only
+        static const bool no_pf = !(getenv("POLEE_K2_PREFETCH") && !strcmp(getenv("POLEE_K2_PREFETCH"), "1"));
+#define K2_LAUNCH(EX, PF)                                                                                           \
+    do {                                                                                                            \
+        cudaFuncSetAttribute(k2_csc_grad_tma<KP, EX, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        k2_csc_grad_tma<KP, EX, PF><<<grid, V2_THREADS, smem, h->stream>>>(h->segs, h->n_segs, h->csc_row, h->csc_val, \
+                                                                           w, g, h->seg_partial);                  \
+    } while (0)
         if (h->o.exact_accumulation) {
-            static bool attr_done = false;
-            if (!attr_done) {
-                cudaFuncSetAttribute(k2_csc_grad_tma<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_done = true;
-            }
-            k2_csc_grad_tma<KP, true><<<grid, V2_THREADS, smem, h->stream>>>(h->segs, h->n_segs, h->csc_row, h->csc_val, w,
-                                                                              g, h->seg_partial);
+            if (no_pf) K2_LAUNCH(true, false); else K2_LAUNCH(true, true);
         } else {
-            static bool attr_done = false;
-            if (!attr_done) {
-                cudaFuncSetAttribute(k2_csc_grad_tma<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_done = true;
-            }
-            k2_csc_grad_tma<KP, false><<<grid, V2_THREADS, smem, h->stream>>>(h->segs, h->n_segs, h->csc_row, h->csc_val,
-                                                                               w, g, h->seg_partial);
+            if (no_pf) K2_LAUNCH(false, false); else K2_LAUNCH(false, true);
         }
+#undef K2_LAUNCH
     }
     if (h->n_multi > 0) {
         const int warps_per_block = 8;
