@@ -302,6 +302,7 @@ extern "C" int polee_init_params(polee_handle *h) {
     CK(cudaMemcpy(h->d_step, &c, sizeof(c), cudaMemcpyHostToDevice));
     CK(cudaMemset(h->d_bad_step, 0, sizeof(int)));
     h->steps_enqueued = 0;
+    h->reparam_ready = false;
     return POLEE_OK;
 }
 
@@ -328,6 +329,7 @@ extern "C" int polee_set_params(polee_handle *h, const float *mu, const float *o
         if (omega) CK(cudaMemcpy(h->omega, omega, sizeof(float) * nm1, cudaMemcpyHostToDevice));
         if (alpha) CK(cudaMemcpy(h->alpha, alpha, sizeof(float) * nm1, cudaMemcpyHostToDevice));
     }
+    h->reparam_ready = false;
     return POLEE_OK;
 }
 
@@ -335,6 +337,7 @@ extern "C" int polee_set_noise(polee_handle *h, const float *noise, int64_t num_
     CHECK_H(h);
     if (!h->have_tree) return h->fail(POLEE_EINVAL, "set_noise: set the tree first");
     drop_graph(h);
+    h->reparam_ready = false;
     cudaFree(h->noise);
     h->noise = nullptr;
     h->noise_steps = 0;
@@ -366,15 +369,17 @@ static int ready_for_steps(polee_handle *h) {
     return POLEE_OK;
 }
 
-// the launch sequence of one step (SURVEY 3a inner loop, batched over the K draws)
-static int launch_step_sequence(polee_handle *h, bool do_adam, float *grad_out, double *xgrad_out, const float *noise,
-                                int64_t noise_steps) {
+// The launch sequence of one step (SURVEY 3a inner loop, batched over the K draws).  ys / zs0 of the step are
+// produced by the previous step's fused update+reparam kernel (or by ensure_reparam for the first step):
+//   tree fwd (top, bottom) -> mid -> K1 -> K2 (+combine) -> [lp reduce] -> [all-reduce] -> tree bwd (bottom, top)
+//   -> [elbo] -> update(step s) + reparam(step s+1)
+static int launch_step_sequence(polee_handle *h, bool do_adam, bool next_reparam, float *grad_out, double *xgrad_out,
+                                const float *noise, int64_t noise_steps) {
     const int KP = h->KP, K = h->K;
     const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
     const bool want_vals = lsn && !h->o.gradonly;
     const bool apply_eff = lsn ? (h->o.use_efflen_jacobian != 0) : true;
     int rc;
-    if ((rc = launch_reparam_fwd(h, KP, K, noise, noise_steps, want_vals))) return rc;
     if ((rc = launch_tree_fwd(h, KP, 1, apply_eff, want_vals))) return rc;
     if ((rc = launch_mid(h, KP, do_adam ? 1 : 0))) return rc;
     if ((rc = launch_k1(h, h->x, h->xd, h->w, want_vals, h->lp_partial, KP))) return rc;
@@ -389,21 +394,36 @@ static int launch_step_sequence(polee_handle *h, bool do_adam, float *grad_out, 
 #endif
     if ((rc = launch_tree_bwd(h, KP, lsn, apply_eff, xgrad_out))) return rc;
     if (want_vals && (rc = launch_elbo(h, KP, K, true))) return rc;
-    if ((rc = launch_update(h, KP, K, do_adam, grad_out))) return rc;
+    if ((rc = launch_elem(h, KP, K, true, do_adam, next_reparam, noise, noise_steps, next_reparam && want_vals, grad_out)))
+        return rc;
+    return POLEE_OK;
+}
+
+// first step after (re)initialisation: produce ys / zs0 for the step the counters point at
+static int ensure_reparam(polee_handle *h) {
+    if (h->reparam_ready) return POLEE_OK;
+    const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
+    const float *noise = h->o.noise_mode == POLEE_NOISE_INJECTED ? h->noise : nullptr;
+    int rc = launch_elem(h, h->KP, h->K, false, false, true, noise, std::max<int64_t>(h->noise_steps, 1),
+                         lsn && !h->o.gradonly, nullptr);
+    if (rc) return rc;
+    h->reparam_ready = true;
     return POLEE_OK;
 }
 
 static int enqueue_step(polee_handle *h) {
     const float *noise = h->o.noise_mode == POLEE_NOISE_INJECTED ? h->noise : nullptr;
+    int rc = ensure_reparam(h);
+    if (rc) return rc;
     if (!h->o.use_cuda_graph) {
-        int rc = launch_step_sequence(h, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
+        rc = launch_step_sequence(h, true, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
         if (rc) return rc;
         CK(cudaGetLastError());
         return POLEE_OK;
     }
     if (!h->graph_exec) {
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = launch_step_sequence(h, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
+        rc = launch_step_sequence(h, true, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
         cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
         if (rc) return rc;
         if (e != cudaSuccess) return h->fail(POLEE_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
@@ -501,6 +521,7 @@ extern "C" int polee_fit_optimize_ptt(polee_handle *h, float *xs) {
     if ((rc = polee_sync(h))) return rc;
     // final transform of the optimised zs  (l-a.jl:237-241)
     if ((rc = launch_reparam_fwd(h, h->KP, h->K, nullptr, 1, 0))) return rc;
+    h->reparam_ready = false;
     if ((rc = launch_tree_fwd(h, h->KP, 1, 0, 0))) return rc;
     return download_kmajor<float, float>(h, h->x, 1, h->KP, h->n, xs);
 }
@@ -561,7 +582,7 @@ extern "C" int polee_ptt_transform(polee_handle *h, const double *ys, int32_t K,
     CK(cudaGetLastError());
     if ((rc = download_kmajor<float, float>(h, h->x, K, KP, h->n, xs))) return rc;
     if (ladj) {
-        const int ne = (int)std::max<int64_t>(1, ((h->n - 1) * (int64_t)KP + 255) / 256);
+        const int ne = elem_ctas(h, KP);
         std::vector<double> part((size_t)h->n_tree_ctas * KP);
         CK(cudaMemcpy(part.data(), h->ladj_partial + (size_t)2 * ne * KP, sizeof(double) * part.size(), cudaMemcpyDeviceToHost));
         for (int k = 0; k < K; ++k) {
@@ -638,7 +659,9 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(&saved, h->d_step, sizeof(saved), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(h->d_step, &one, sizeof(one), cudaMemcpyHostToDevice));
-    rc = launch_step_sequence(h, false, h->grad_out, d_xg, d_noise, 1);
+    rc = launch_elem(h, KP, K, false, false, true, d_noise, 1, !h->o.gradonly, nullptr);
+    if (!rc) rc = launch_step_sequence(h, false, false, h->grad_out, d_xg, d_noise, 1);
+    h->reparam_ready = false;
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (!rc && e != cudaSuccess) rc = h->fail(POLEE_ECUDA, std::string("lsn_draws: ") + cudaGetErrorString(e));
     if (!rc && xs) rc = download_kmajor<float, float>(h, h->x, K, KP, n, xs);
@@ -673,8 +696,8 @@ extern "C" int polee_step_stats(polee_handle *h, double *b1, double *b2, double 
     if (launches) {
         const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
         const bool vals = lsn && !h->o.gradonly;
-        int L = 1 /*reparam*/ + (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*mid*/ + (h->n_row_tiles > 0) +
-                (h->n_segs > 0) + (h->n_multi > 0) + (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*update*/;
+        int L = (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*mid*/ + (h->n_row_tiles > 0) +
+                (h->n_segs > 0) + (h->n_multi > 0) + (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*update + reparam*/;
         if (vals) L += 2;
         *launches = L;
     }
@@ -686,6 +709,7 @@ extern "C" int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, f
     int rc = ready_for_steps(h);
     if (rc) return rc;
     if (reps < 1 || !ms_avg) return h->fail(POLEE_EINVAL, "time_kernel: bad arguments");
+    if ((rc = ensure_reparam(h))) return rc;
     const int KP = h->KP, K = h->K;
     const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
     cudaEvent_t e0, e1;
@@ -699,11 +723,10 @@ extern "C" int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, f
         } else if (which == 2) {
             rc = launch_k2(h, h->w, h->g, KP);
         } else if (which == 3) {
-            rc = launch_reparam_fwd(h, KP, K, noise, std::max<int64_t>(h->noise_steps, 1), 0);
-            if (!rc) rc = launch_tree_fwd(h, KP, 1, 1, 0);
+            rc = launch_tree_fwd(h, KP, 1, 1, 0);
             if (!rc) rc = launch_mid(h, KP, 0);
             if (!rc) rc = launch_tree_bwd(h, KP, lsn, true, nullptr);
-            if (!rc) rc = launch_update(h, KP, K, false, nullptr);
+            if (!rc) rc = launch_elem(h, KP, K, true, false, true, noise, std::max<int64_t>(h->noise_steps, 1), 0, nullptr);
         } else {
             rc = h->fail(POLEE_EINVAL, "time_kernel: which must be 1, 2 or 3");
         }

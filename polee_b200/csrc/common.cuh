@@ -179,6 +179,7 @@ struct polee_handle {
     polee::StepCtl *d_step = nullptr;  // device step counters
     int *d_bad_step = nullptr;         // first step with a non-finite gradient, 0 = none
     int steps_enqueued = 0;
+    bool reparam_ready = false;  // ys / zs0 of the next step have been produced (fused update + reparam kernel)
 
     // ---- per-step work buffers (layouts [item][KP])
     float *zs0 = nullptr, *zs = nullptr;  // [n-1][KP]
@@ -244,6 +245,9 @@ int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_l
 int launch_mid(polee_handle *h, int KP, int advance);
 int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, double *xgrad_out);
 int launch_update(polee_handle *h, int KP, int K, bool do_adam, float *grad_out);
+int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bool do_reparam, const float *noise,
+                int64_t noise_steps, int want_ladj, float *grad_out);
+int elem_ctas(polee_handle *h, int KP);
 int launch_elbo(polee_handle *h, int KP, int K, bool have_lp);
 
 }  // namespace polee

@@ -43,11 +43,13 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
     }
 }
 // one standard normal for (node i, draw d, step s): counter (i, d, s, 0), key = seed, Box-Muller cos branch
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t i, uint32_t d, uint32_t s) {
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t i, uint32_t d, uint32_t s, int fast) {
     uint32_t c[4] = {i, d, s, 0u};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
     float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    if (fast)  // hardware log2 / cos: ~1e-6 absolute on a noise sample, no parity contract (tests inject noise)
+        return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530717958647692f * u2);
     float r = sqrtf(-2.0f * logf(u1));
     return r * cosf(6.28318530717958647692f * u2);
 }
@@ -63,59 +65,6 @@ __device__ __forceinline__ void block_reduce_k(double v, double *sm, double *out
     }
     if (threadIdx.x < KP) out[threadIdx.x] = sm[threadIdx.x];
     __syncthreads();
-}
-
-// ---------------------------------------------------------------- reparameterisation forward
-// mode 0: logit skew normal (mu, omega, alpha + noise); mode 1: OptimizePTTApprox (ys = logistic(zs), no clamp)
-template <int KP>
-__global__ void __launch_bounds__(256)
-    k3_reparam_fwd(int64_t nm1, int K, int mode, const float *__restrict__ mu, const float *__restrict__ omega,
-                   const float *__restrict__ alpha, const float *__restrict__ noise, int64_t noise_steps,
-                   const StepCtl *__restrict__ ctl, uint64_t seed, float *__restrict__ zs0_out,
-                   float *__restrict__ zs_out, double *__restrict__ ys_out, int want_ladj,
-                   double *__restrict__ ladj_partial /* [2][gridDim.x][KP] or null */) {
-    __shared__ double sm[256];
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t i = idx / KP;
-    const int k = (int)(idx % KP);
-    double l_skew = 0.0, l_ln = 0.0;
-    if (i < nm1) {
-        if (mode == 1) {
-            float e = expf(-mu[i]);
-            float y32 = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
-            ys_out[idx] = (double)y32;
-            zs0_out[idx] = 0.0f;
-            zs_out[idx] = 0.0f;
-        } else {
-            const int step0 = ctl->step_fwd - 1;
-            float z0 = 0.0f;
-            if (k < K) {
-                if (noise)
-                    z0 = noise[((size_t)(step0 % noise_steps) * K + k) * (size_t)nm1 + i];
-                else
-                    z0 = philox_normal(seed, (uint32_t)i, (uint32_t)k, (uint32_t)step0);
-            }
-            const float sigma = expf(omega[i]);
-            const float c = __fadd_rn(alpha[i], asinhf(z0));
-            const float z = sinhf(c);
-            const float xx = __fadd_rn(mu[i], __fmul_rn(z, sigma));
-            const float e = expf(-xx);
-            const float y32 = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
-            double y = (double)y32;
-            if (want_ladj && k < K) {
-                l_skew = (double)logf(coshf(c)) - 0.5 * (double)log1pf(__fmul_rn(z0, z0));
-                l_ln = log(__dmul_rn(__dmul_rn((double)sigma, y), __dsub_rn(1.0, y)));
-            }
-            y = fmin(fmax(y, 1e-10), 1.0 - 1e-10);
-            zs0_out[idx] = z0;
-            zs_out[idx] = z;
-            ys_out[idx] = y;
-        }
-    }
-    if (want_ladj) {
-        block_reduce_k<KP, 256>(l_skew, sm, ladj_partial + (size_t)blockIdx.x * KP);
-        block_reduce_k<KP, 256>(l_ln, sm, ladj_partial + ((size_t)gridDim.x + blockIdx.x) * KP);
-    }
 }
 
 // ---------------------------------------------------------------- tree forward
@@ -469,71 +418,155 @@ __device__ __forceinline__ void adam_one(float &param, float &m, float &v, doubl
     param = (float)__dadd_rn((double)param, delta);
 }
 
+// One thread per internal node; both halves of the step boundary in one pass over the parameters:
+//   UPDATE  (step s):   logit-normal + sinh-arcsinh backward accumulated over the K draws in draw order, /K, finite
+//                       check, ADAM ascent with step clamp
+//   REPARAM (step s+1): noise -> zs -> ys for the next step's tree forward
+// sinh(alpha + asinh z0) is evaluated as z0 cosh(alpha) + sqrt(1 + z0^2) sinh(alpha) (and cosh(c), tanh(c)
+// likewise from cosh/sinh(alpha)): the same real function as the reference's Float32 expression with two
+// transcendentals per NODE instead of four per DRAW; the difference is a few Float32 ulp.
 template <int KP>
 __global__ void __launch_bounds__(256)
-    k3_update(int64_t nm1, int K, int mode, float *__restrict__ mu, float *__restrict__ omega,
-              float *__restrict__ alpha, float *__restrict__ m_mu, float *__restrict__ m_omega,
-              float *__restrict__ m_alpha, float *__restrict__ v_mu, float *__restrict__ v_omega,
-              float *__restrict__ v_alpha, const float *__restrict__ zs0, const float *__restrict__ zs,
-              const double *__restrict__ ys, const double *__restrict__ ygrad, const StepCtl *__restrict__ ctl,
-              AdamCfg cfg, int do_adam, int *__restrict__ bad_step, float *__restrict__ grad_out) {
+    k3_elem(int64_t nm1, int K, int mode, int do_update, int do_adam, int do_reparam, float *__restrict__ mu,
+            float *__restrict__ omega, float *__restrict__ alpha, float *__restrict__ m_mu, float *__restrict__ m_omega,
+            float *__restrict__ m_alpha, float *__restrict__ v_mu, float *__restrict__ v_omega, float *__restrict__ v_alpha,
+            float *__restrict__ zs0, double *__restrict__ ys, const double *__restrict__ ygrad,
+            const StepCtl *__restrict__ ctl, AdamCfg cfg, int *__restrict__ bad_step, float *__restrict__ grad_out,
+            const float *__restrict__ noise, int64_t noise_steps, uint64_t seed, int fast_noise, int want_ladj,
+            double *__restrict__ ladj_partial /* [2][gridDim.x][KP] */) {
+    __shared__ double sm[256];
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= nm1) return;
-    const int step = ctl->step_upd;
-    // adam_learning_rate(step_num - 1)  l-a.jl:107-110, 497
-    const double lr = fmax(1e-3, 1.0 * exp(-2e-2 * (double)(step - 1)));
-    const double m_denom = 1.0 - pow(0.7, (double)step), v_denom = 1.0 - pow(0.9, (double)step);
-
-    if (mode == 1) {  // OptimizePTTApprox: z_grad = y (1 - y) y_grad, Float64 (l-a.jl:211-213)
-        const double y = ys[(size_t)i * KP];
-        const double zg = __dmul_rn(__dmul_rn(y, __dsub_rn(1.0, y)), ygrad[(size_t)i * KP]);
-        if (grad_out) grad_out[i] = (float)zg;
-        if (!isfinite(zg)) atomicCAS(bad_step, 0, step);
-        if (do_adam) adam_one(mu[i], m_mu[i], v_mu[i], zg, 0.0f, false, step, lr, m_denom, v_denom, cfg.max_step_z);
-        return;
+    const bool live = i < nm1;
+    float p_mu = 0.f, p_om = 0.f, p_al = 0.f;
+    if (live) {
+        p_mu = mu[i];
+        if (mode == 0) { p_om = omega[i]; p_al = alpha[i]; }
     }
 
-    const float sigma = expf(omega[i]);
-    const float al = alpha[i];
-    float mu_g = 0.0f, om_g = 0.0f, al_g = 0.0f;
-    for (int k = 0; k < K; ++k) {
-        const double y = ys[(size_t)i * KP + k];
-        const double yg = ygrad[(size_t)i * KP + k];  // already rounded to Float32
-        const double z = (double)zs[(size_t)i * KP + k];
-        const float z0 = zs0[(size_t)i * KP + k];
-        const double d = __dmul_rn(y, __dsub_rn(1.0, y));
-        const double omy2 = __dsub_rn(1.0, __dmul_rn(2.0, y));
-        // logit_normal_transform_gradients! (8-arg)  logitnormal.jl:38-55; sigma_grad / z_grad restart at 0 per draw
-        mu_g = (float)__dadd_rn((double)mu_g, __dmul_rn(d, yg));
-        float sg = (float)__dmul_rn(__dmul_rn(d, z), yg);
-        float zg = (float)__dmul_rn(__dmul_rn(d, (double)sigma), yg);
-        mu_g = (float)__dadd_rn((double)mu_g, omy2);
-        sg = (float)__dadd_rn((double)sg, __dadd_rn((double)__fdiv_rn(1.0f, sigma), __dmul_rn(z, omy2)));
-        zg = (float)__dadd_rn((double)zg, __dmul_rn((double)sigma, omy2));
-        // sinh_asinh_transform_gradients!  sinh_arcsinh.jl:29-38 (Float32)
-        const float c = __fadd_rn(al, asinhf(z0));
-        al_g = __fadd_rn(al_g, __fmul_rn(coshf(c), zg));
-        al_g = __fadd_rn(al_g, tanhf(c));
-        // omega chain rule  l-a.jl:547-549
-        om_g = __fadd_rn(om_g, __fmul_rn(sigma, sg));
+    if (do_update && live) {
+        const int step = ctl->step_upd;
+        // adam_learning_rate(step_num - 1)  l-a.jl:107-110, 497
+        const double lr = fmax(1e-3, 1.0 * exp(-2e-2 * (double)(step - 1)));
+        const double m_denom = 1.0 - pow(0.7, (double)step), v_denom = 1.0 - pow(0.9, (double)step);
+        if (mode == 1) {  // OptimizePTTApprox: z_grad = y (1 - y) y_grad, Float64 (l-a.jl:211-213)
+            const double y = ys[(size_t)i * KP];
+            const double zg = __dmul_rn(__dmul_rn(y, __dsub_rn(1.0, y)), ygrad[(size_t)i * KP]);
+            if (grad_out) grad_out[i] = (float)zg;
+            if (!isfinite(zg)) atomicCAS(bad_step, 0, step);
+            if (do_adam) {
+                float mm = m_mu[i], vv = v_mu[i];
+                adam_one(p_mu, mm, vv, zg, 0.0f, false, step, lr, m_denom, v_denom, cfg.max_step_z);
+                m_mu[i] = mm; v_mu[i] = vv; mu[i] = p_mu;
+            }
+        } else {
+            const float sigma = expf(p_om);
+            const float sa = sinhf(p_al), ca = coshf(p_al);
+            const float inv_sigma = __fdiv_rn(1.0f, sigma);
+            float mu_g = 0.0f, om_g = 0.0f, al_g = 0.0f;
+            for (int k = 0; k < K; ++k) {
+                const double y = ys[(size_t)i * KP + k];
+                const double yg = ygrad[(size_t)i * KP + k];  // already rounded to Float32
+                const float z0 = zs0[(size_t)i * KP + k];
+                const float r = sqrtf(fmaf(z0, z0, 1.0f));     // cosh(asinh z0)
+                const float zf = fmaf(z0, ca, r * sa);         // sinh(alpha + asinh z0)
+                const float ch = fmaf(ca, r, sa * z0);         // cosh(alpha + asinh z0)
+                const double z = (double)zf;
+                const double d = __dmul_rn(y, __dsub_rn(1.0, y));
+                const double omy2 = __dsub_rn(1.0, __dmul_rn(2.0, y));
+                // logit_normal_transform_gradients! (8-arg)  logitnormal.jl:38-55; sigma_grad / z_grad restart per draw
+                mu_g = (float)__dadd_rn((double)mu_g, __dmul_rn(d, yg));
+                float sg = (float)__dmul_rn(__dmul_rn(d, z), yg);
+                float zg = (float)__dmul_rn(__dmul_rn(d, (double)sigma), yg);
+                mu_g = (float)__dadd_rn((double)mu_g, omy2);
+                sg = (float)__dadd_rn((double)sg, __dadd_rn((double)inv_sigma, __dmul_rn(z, omy2)));
+                zg = (float)__dadd_rn((double)zg, __dmul_rn((double)sigma, omy2));
+                // sinh_asinh_transform_gradients!  sinh_arcsinh.jl:29-38: cosh(c) z_grad + tanh(c)
+                al_g = __fadd_rn(al_g, __fmul_rn(ch, zg));
+                al_g = __fadd_rn(al_g, __fdiv_rn(zf, ch));
+                // omega chain rule  l-a.jl:547-549
+                om_g = __fadd_rn(om_g, __fmul_rn(sigma, sg));
+            }
+            const float Kf = (float)K;
+            mu_g = __fdiv_rn(mu_g, Kf);  // l-a.jl:552-556
+            om_g = __fdiv_rn(om_g, Kf);
+            al_g = __fdiv_rn(al_g, Kf);
+            if (!(isfinite(mu_g) && isfinite(om_g) && isfinite(al_g))) atomicCAS(bad_step, 0, step);
+            if (grad_out) {
+                grad_out[i] = mu_g;
+                grad_out[nm1 + i] = om_g;
+                grad_out[2 * nm1 + i] = al_g;
+            }
+            if (do_adam) {
+                float mm = m_mu[i], vv = v_mu[i];
+                adam_one(p_mu, mm, vv, (double)mu_g, __fmul_rn(mu_g, mu_g), true, step, lr, m_denom, v_denom, cfg.max_step_mu);
+                m_mu[i] = mm; v_mu[i] = vv; mu[i] = p_mu;
+                mm = m_omega[i]; vv = v_omega[i];
+                adam_one(p_om, mm, vv, (double)om_g, __fmul_rn(om_g, om_g), true, step, lr, m_denom, v_denom, cfg.max_step_omega);
+                m_omega[i] = mm; v_omega[i] = vv; omega[i] = p_om;
+                mm = m_alpha[i]; vv = v_alpha[i];
+                adam_one(p_al, mm, vv, (double)al_g, __fmul_rn(al_g, al_g), true, step, lr, m_denom, v_denom, cfg.max_step_alpha);
+                m_alpha[i] = mm; v_alpha[i] = vv; alpha[i] = p_al;
+            }
+        }
     }
-    const float Kf = (float)K;
-    mu_g = __fdiv_rn(mu_g, Kf);  // l-a.jl:552-556
-    om_g = __fdiv_rn(om_g, Kf);
-    al_g = __fdiv_rn(al_g, Kf);
-    if (!(isfinite(mu_g) && isfinite(om_g) && isfinite(al_g))) atomicCAS(bad_step, 0, step);
-    if (grad_out) {
-        grad_out[i] = mu_g;
-        grad_out[nm1 + i] = om_g;
-        grad_out[2 * nm1 + i] = al_g;
+
+    if (!do_reparam) return;
+    double l_skew[KP], l_ln[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) { l_skew[k] = 0.0; l_ln[k] = 0.0; }
+    if (live) {
+        if (mode == 1) {
+            const float e = expf(-p_mu);
+            ys[(size_t)i * KP] = (double)__fdiv_rn(1.0f, __fadd_rn(1.0f, e));  // ys = logistic(zs), no clamp (l-a.jl:196)
+            zs0[(size_t)i * KP] = 0.0f;
+        } else {
+            const int step0 = ctl->step_fwd - 1;  // 0-based index of the step these draws belong to
+            const float sigma = expf(p_om);
+            const float sa = sinhf(p_al), ca = coshf(p_al);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                float z0 = 0.0f;
+                if (k < K) {
+                    if (noise) z0 = noise[((size_t)(step0 % noise_steps) * K + k) * (size_t)nm1 + i];
+                    else z0 = philox_normal(seed, (uint32_t)i, (uint32_t)k, (uint32_t)step0, fast_noise);
+                }
+                const float r = sqrtf(fmaf(z0, z0, 1.0f));
+                const float zf = fmaf(z0, ca, r * sa);
+                const float xx = __fadd_rn(p_mu, __fmul_rn(zf, sigma));
+                const float e = expf(-xx);
+                const float y32 = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+                double y = (double)y32;
+                if (want_ladj && k < K) {
+                    const float ch = fmaf(ca, r, sa * z0);
+                    l_skew[k] = (double)logf(ch) - (double)logf(r);  // log cosh(c) - 0.5 log1p(z0^2)
+                    l_ln[k] = log(__dmul_rn(__dmul_rn((double)sigma, y), __dsub_rn(1.0, y)));
+                }
+                y = fmin(fmax(y, 1e-10), 1.0 - 1e-10);
+                zs0[(size_t)i * KP + k] = z0;
+                ys[(size_t)i * KP + k] = y;
+            }
+        }
     }
-    if (do_adam) {
-        adam_one(mu[i], m_mu[i], v_mu[i], (double)mu_g, __fmul_rn(mu_g, mu_g), true, step, lr, m_denom, v_denom,
-                 cfg.max_step_mu);
-        adam_one(omega[i], m_omega[i], v_omega[i], (double)om_g, __fmul_rn(om_g, om_g), true, step, lr, m_denom,
-                 v_denom, cfg.max_step_omega);
-        adam_one(alpha[i], m_alpha[i], v_alpha[i], (double)al_g, __fmul_rn(al_g, al_g), true, step, lr, m_denom,
-                 v_denom, cfg.max_step_alpha);
+    if (want_ladj) {
+        // per-draw block sums, fixed order
+        for (int k = 0; k < KP; ++k) {
+            sm[threadIdx.x] = l_skew[k];
+            __syncthreads();
+            for (int span = 128; span >= 1; span >>= 1) {
+                if ((int)threadIdx.x < span) sm[threadIdx.x] += sm[threadIdx.x + span];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) ladj_partial[(size_t)blockIdx.x * KP + k] = sm[0];
+            __syncthreads();
+            sm[threadIdx.x] = l_ln[k];
+            __syncthreads();
+            for (int span = 128; span >= 1; span >>= 1) {
+                if ((int)threadIdx.x < span) sm[threadIdx.x] += sm[threadIdx.x + span];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) ladj_partial[((size_t)gridDim.x + blockIdx.x) * KP + k] = sm[0];
+            __syncthreads();
+        }
     }
 }
 
@@ -570,9 +603,9 @@ void release_work_buffers(polee_handle *h) {
     h->work_KP = 0;
 }
 
-static int elem_ctas(polee_handle *h, int KP) {
-    int64_t work = (h->n - 1) * (int64_t)KP;
-    return (int)std::max<int64_t>(1, (work + 255) / 256);
+int elem_ctas(polee_handle *h, int KP) {
+    (void)KP;
+    return (int)std::max<int64_t>(1, (h->n - 1 + 255) / 256);
 }
 
 int ensure_work_buffers(polee_handle *h, int KP) {
@@ -618,15 +651,23 @@ int ensure_work_buffers(polee_handle *h, int KP) {
         default: return h->fail(POLEE_EINVAL, "unsupported number of MC draws (1..16)"); \
     }
 
-int launch_reparam_fwd(polee_handle *h, int KP, int K, const float *noise, int64_t noise_steps, int want_ladj) {
+int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bool do_reparam, const float *noise,
+                int64_t noise_steps, int want_ladj, float *grad_out) {
     const int64_t nm1 = h->n - 1;
     if (nm1 <= 0) return POLEE_OK;
-    const int ctas = elem_ctas(h, KP);
     const int mode = h->o.approx == POLEE_APPROX_OPTIMIZE_PTT ? 1 : 0;
-    DISPATCH_KP(KP, (k3_reparam_fwd<KPC><<<ctas, 256, 0, h->stream>>>(
-                        nm1, K, mode, h->mu, h->omega, h->alpha, noise, noise_steps, h->d_step,
-                        h->o.seed, h->zs0, h->zs, h->ys, want_ladj, h->ladj_partial)));
+    AdamCfg cfg{h->o.max_step_mu, h->o.max_step_omega, h->o.max_step_alpha, h->o.max_step_z};
+    const int ctas = elem_ctas(h, KP);
+    DISPATCH_KP(KP, (k3_elem<KPC><<<ctas, 256, 0, h->stream>>>(
+                        nm1, K, mode, do_update ? 1 : 0, do_adam ? 1 : 0, do_reparam ? 1 : 0, h->mu, h->omega, h->alpha, h->m_mu,
+                        h->m_omega, h->m_alpha, h->v_mu, h->v_omega, h->v_alpha, h->zs0, h->ys, h->ygrad, h->d_step, cfg,
+                        h->d_bad_step, grad_out, noise, std::max<int64_t>(noise_steps, 1), h->o.seed, 1, want_ladj,
+                        h->ladj_partial)));
     return POLEE_OK;
+}
+
+int launch_reparam_fwd(polee_handle *h, int KP, int K, const float *noise, int64_t noise_steps, int want_ladj) {
+    return launch_elem(h, KP, K, false, false, true, noise, noise_steps, want_ladj, nullptr);
 }
 
 constexpr int S_BOT_THREADS = 512;
@@ -793,16 +834,7 @@ int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, 
 }
 
 int launch_update(polee_handle *h, int KP, int K, bool do_adam, float *grad_out) {
-    const int64_t nm1 = h->n - 1;
-    if (nm1 <= 0) return POLEE_OK;
-    const int mode = h->o.approx == POLEE_APPROX_OPTIMIZE_PTT ? 1 : 0;
-    AdamCfg cfg{h->o.max_step_mu, h->o.max_step_omega, h->o.max_step_alpha, h->o.max_step_z};
-    const int ctas = (int)((nm1 + 255) / 256);
-    DISPATCH_KP(KP, (k3_update<KPC><<<ctas, 256, 0, h->stream>>>(
-                        nm1, K, mode, h->mu, h->omega, h->alpha, h->m_mu, h->m_omega, h->m_alpha, h->v_mu, h->v_omega,
-                        h->v_alpha, h->zs0, h->zs, h->ys, h->ygrad, h->d_step, cfg, do_adam ? 1 : 0,
-                        h->d_bad_step, grad_out)));
-    return POLEE_OK;
+    return launch_elem(h, KP, K, true, do_adam, false, nullptr, 1, 0, grad_out);
 }
 
 int launch_elbo(polee_handle *h, int KP, int K, bool have_lp) {
