@@ -182,46 +182,20 @@ __global__ void __launch_bounds__(THREADS)
 
 // ================================================================ shared-memory tree kernels
 // Same arithmetic as k3_tree_fwd / k3_tree_bwd above, but a CTA first pulls everything its bin needs into shared
-// memory (schedule-order records, ys, the u of its subtree roots / the G of its leaves), runs the level loops
-// entirely out of shared memory (one __syncthreads per level, no global load on the critical path) and writes its
-// results back at the end.  THREAD = NODE: a thread carries its node through all KPC draws of the CTA, so the
-// record decode, the branch and the address arithmetic are paid once per node instead of once per (node, draw);
-// shared arrays are draw-major ([kk][node]) so that neighbouring threads hit neighbouring banks.
-// grid = (bins, KP / KPC): KPC = all draws for the bottom forests, 1 for the top part (a few thousand nodes must
-// fit one CTA).  Bottom subtree roots exchange u (top -> bottom) and G (bottom -> top) through [slot][KP] arrays.
-// The backward kernel recomputes u from ys instead of reading it back.
-template <int KPC>
-__device__ __forceinline__ void ld_draws(const double *p, double *v) {
-    if constexpr (KPC % 2 == 0) {
-#pragma unroll
-        for (int q = 0; q < KPC / 2; ++q) {
-            const double2 t = *reinterpret_cast<const double2 *>(p + 2 * q);
-            v[2 * q] = t.x;
-            v[2 * q + 1] = t.y;
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < KPC; ++q) v[q] = p[q];
-    }
-}
-
-// deterministic per-draw block sum of v[KPC] (warp shuffle tree, then the warps in order) into out[KPC]
+// memory with coalesced loads (schedule-order records, ys, the u of its subtree roots / the G of its leaves), runs
+// the level loops entirely out of shared memory (one __syncthreads per level, no global load on the critical path)
+// and writes its results back at the end.  grid = (bins, KP / KPC): KPC draws per CTA (8 for the bottom forests,
+// 1 for the top part so that a few thousand nodes fit).  Bottom subtree roots exchange u (top -> bottom) and G
+// (bottom -> top) through [slot][KP] arrays.  The backward kernel recomputes u from ys instead of reading it back.
 template <int KPC, int THREADS>
-__device__ __forceinline__ void block_sum_draws(const double (&v)[KPC], double *red /* [THREADS/32][KPC] */, double *out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int kk = 0; kk < KPC; ++kk) {
-        double t = v[kk];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) red[warp * KPC + kk] = t;
-    }
+__device__ __forceinline__ void block_reduce_kc(double v, double *red, double *out /* [KPC] */) {
+    red[threadIdx.x] = v;
     __syncthreads();
-    if (threadIdx.x < KPC) {
-        double t = 0.0;
-        for (int wv = 0; wv < THREADS / 32; ++wv) t += red[wv * KPC + threadIdx.x];
-        out[threadIdx.x] = t;
+    for (int span = THREADS / KPC / 2; span >= 1; span >>= 1) {
+        if ((int)threadIdx.x < span * KPC) red[threadIdx.x] += red[threadIdx.x + span * KPC];
+        __syncthreads();
     }
+    if (threadIdx.x < KPC) out[threadIdx.x] = red[threadIdx.x];
     __syncthreads();
 }
 
@@ -233,86 +207,80 @@ __global__ void __launch_bounds__(THREADS, MINB)
                  const float *__restrict__ efflen, double *__restrict__ S_partial, int part_base, int want_ladj,
                  double *__restrict__ ladj_partial) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ double red[(THREADS / 32) * KPC];
+    __shared__ double red[THREADS];
     const int q0 = bin_off[blockIdx.x], nb = bin_off[blockIdx.x + 1] - q0;
     SNode *rec_s = reinterpret_cast<SNode *>(smraw);
-    double *us_s = reinterpret_cast<double *>(smraw + (size_t)nb * sizeof(SNode));  // [KPC][nb]
-    double *ys_s = us_s + (size_t)nb * KPC;                                           // [KPC][nb]
+    double *us_s = reinterpret_cast<double *>(smraw + (size_t)nb * sizeof(SNode));
+    double *ys_s = us_s + (size_t)nb * KPC;
     int *lvl_s = reinterpret_cast<int *>(ys_s + (size_t)nb * KPC);
-    const int k0 = blockIdx.y * KPC;
+    const int kk = threadIdx.x % KPC, slot_t = threadIdx.x / KPC, k = blockIdx.y * KPC + kk;
+    constexpr int NPP = THREADS / KPC;
     const int l0 = bin_lvl_ptr[blockIdx.x], nlev = bin_lvl_ptr[blockIdx.x + 1] - 1 - l0;
 
-    // gather phase: thread = node; one record, KPC draws of ys / root u per node
+    for (int p = threadIdx.x; p < nb; p += THREADS) rec_s[p] = recs[q0 + p];
     for (int l = threadIdx.x; l <= nlev; l += THREADS) lvl_s[l] = lvl_off[l0 + l] - q0;
-    for (int p = threadIdx.x; p < nb; p += THREADS) {
-        const SNode r = recs[q0 + p];
-        rec_s[p] = r;
-        if (r.k_or_leaf >= 0) {
-            double v[KPC];
-            ld_draws<KPC>(ys + (size_t)r.k_or_leaf * KP + k0, v);
+    __syncthreads();
+    // gather phase, 4 positions per thread in flight (the loads are independent: batch them for MLP)
+    for (int base = slot_t; base < nb; base += 4 * NPP) {
+        SNode r[4];
+        double yv[4], uv[4];
 #pragma unroll
-            for (int kk = 0; kk < KPC; ++kk) ys_s[kk * nb + p] = v[kk];
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * NPP;
+            r[u] = p < nb ? rec_s[p] : SNode{-1, -1, -1, -2};
         }
-        if (r.slot == -1) {
 #pragma unroll
-            for (int kk = 0; kk < KPC; ++kk) us_s[kk * nb + p] = 1.0;
-        } else if (r.slot >= 0 && r.k_or_leaf != INT32_MIN) {
-            double v[KPC];
-            ld_draws<KPC>(root_us + (size_t)r.slot * KP + k0, v);
+        for (int u = 0; u < 4; ++u) {
+            yv[u] = 0.0;
+            uv[u] = 1.0;
+            if (r[u].k_or_leaf >= 0) yv[u] = ys[(size_t)r[u].k_or_leaf * KP + k];
+            if (r[u].slot >= 0 && r[u].k_or_leaf != INT32_MIN) uv[u] = root_us[(size_t)r[u].slot * KP + k];
+        }
 #pragma unroll
-            for (int kk = 0; kk < KPC; ++kk) us_s[kk * nb + p] = v[kk];
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * NPP;
+            if (p < nb) {
+                if (r[u].k_or_leaf >= 0) ys_s[p * KPC + kk] = yv[u];
+                if (r[u].slot >= -1 && r[u].k_or_leaf != INT32_MIN) us_s[p * KPC + kk] = uv[u];
+            }
         }
     }
     __syncthreads();
 
-    double sacc[KPC], lacc[KPC];
-#pragma unroll
-    for (int kk = 0; kk < KPC; ++kk) { sacc[kk] = 0.0; lacc[kk] = 0.0; }
+    double sacc = 0.0, lacc = 0.0;
     for (int l = 0; l < nlev; ++l) {
         const int lo = lvl_s[l], hi = lvl_s[l + 1];
-        for (int p = lo + threadIdx.x; p < hi; p += THREADS) {
+        for (int p = lo + slot_t; p < hi; p += NPP) {
             const SNode r = rec_s[p];
+            const double ui = us_s[p * KPC + kk];
             if (r.k_or_leaf >= 0) {
-#pragma unroll
-                for (int kk = 0; kk < KPC; ++kk) {
-                    const double ui = us_s[kk * nb + p], y = ys_s[kk * nb + p];
-                    us_s[kk * nb + r.left] = __dmul_rn(y, ui);
-                    us_s[kk * nb + r.right] = __dmul_rn(__dsub_rn(1.0, y), ui);
-                    if (want_ladj) lacc[kk] += log(ui);
-                }
+                const double y = ys_s[p * KPC + kk];
+                us_s[r.left * KPC + kk] = __dmul_rn(y, ui);
+                us_s[r.right * KPC + kk] = __dmul_rn(__dsub_rn(1.0, y), ui);
+                if (want_ladj) lacc += log(ui);
             } else if (r.k_or_leaf == INT32_MIN) {
-#pragma unroll
-                for (int kk = 0; kk < KPC; ++kk) root_us[(size_t)r.slot * KP + k0 + kk] = us_s[kk * nb + p];  // hand u over
+                root_us[(size_t)r.slot * KP + k] = ui;  // a bottom subtree root: hand u over
             } else {
                 const int leaf = -1 - r.k_or_leaf;
-                const float el = efflen ? efflen[leaf] : 1.0f;
-                float xo[KPC];
-                double xdo[KPC];
-#pragma unroll
-                for (int kk = 0; kk < KPC; ++kk) {
-                    float xv = (float)us_s[kk * nb + p];
-                    double d = (double)xv;
-                    xv = (float)(d > 1e-16 ? d : 1e-16);  // ptt.jl:136-137
-                    if (clamp_x) {                         // clamp!(xs, 1e-10, 1 - 1e-10) on a Float32 vector
-                        d = (double)xv;
-                        d = fmin(fmax(d, 1e-10), 1.0 - 1e-10);
-                        xv = (float)d;
-                    }
-                    xo[kk] = xv;
-                    xdo[kk] = (double)xv;
-                    if (efflen) sacc[kk] = __dadd_rn(sacc[kk], (double)__fdiv_rn(xv, el));
+                float xv = (float)ui;
+                double d = (double)xv;
+                xv = (float)(d > 1e-16 ? d : 1e-16);  // ptt.jl:136-137
+                if (clamp_x) {                         // clamp!(xs, 1e-10, 1 - 1e-10) on a Float32 vector
+                    d = (double)xv;
+                    d = fmin(fmax(d, 1e-10), 1.0 - 1e-10);
+                    xv = (float)d;
                 }
-#pragma unroll
-                for (int kk = 0; kk < KPC; ++kk) {
-                    x[(size_t)leaf * KP + k0 + kk] = xo[kk];
-                    xd[(size_t)leaf * KP + k0 + kk] = xdo[kk];
-                }
+                x[(size_t)leaf * KP + k] = xv;
+                xd[(size_t)leaf * KP + k] = (double)xv;
+                if (efflen) sacc = __dadd_rn(sacc, (double)__fdiv_rn(xv, efflen[leaf]));
             }
         }
         __syncthreads();
     }
-    if (S_partial) block_sum_draws<KPC, THREADS>(sacc, red, S_partial + (size_t)(part_base + blockIdx.x) * KP + k0);
-    if (want_ladj) block_sum_draws<KPC, THREADS>(lacc, red, ladj_partial + (size_t)(part_base + blockIdx.x) * KP + k0);
+    if (S_partial)
+        block_reduce_kc<KPC, THREADS>(sacc, red, S_partial + (size_t)(part_base + blockIdx.x) * KP + blockIdx.y * KPC);
+    if (want_ladj)
+        block_reduce_kc<KPC, THREADS>(lacc, red, ladj_partial + (size_t)(part_base + blockIdx.x) * KP + blockIdx.y * KPC);
 }
 
 template <int KP, int KPC, int THREADS, int MINB, bool WITH_LADJ>
@@ -325,49 +293,59 @@ __global__ void __launch_bounds__(THREADS, MINB)
     extern __shared__ __align__(16) unsigned char smraw[];
     const int q0 = bin_off[blockIdx.x], nb = bin_off[blockIdx.x + 1] - q0;
     SNode *rec_s = reinterpret_cast<SNode *>(smraw);
-    double *us_s = reinterpret_cast<double *>(smraw + (size_t)nb * sizeof(SNode));  // [KPC][nb]
+    double *us_s = reinterpret_cast<double *>(smraw + (size_t)nb * sizeof(SNode));
     double *ys_s = us_s + (size_t)nb * KPC;
     float2 *G_s = reinterpret_cast<float2 *>(ys_s + (size_t)nb * KPC);
     int *lvl_s = reinterpret_cast<int *>(G_s + (size_t)nb * KPC);
-    const int k0 = blockIdx.y * KPC;
+    const int kk = threadIdx.x % KPC, slot_t = threadIdx.x / KPC, k = blockIdx.y * KPC + kk;
+    constexpr int NPP = THREADS / KPC;
     const int l0 = bin_lvl_ptr[blockIdx.x], nlev = bin_lvl_ptr[blockIdx.x + 1] - 1 - l0;
 
-    double Sk[KPC];
-#pragma unroll
-    for (int kk = 0; kk < KPC; ++kk) Sk[kk] = efflen_adj ? S[k0 + kk] : 1.0;
+    for (int p = threadIdx.x; p < nb; p += THREADS) rec_s[p] = recs[q0 + p];
     for (int l = threadIdx.x; l <= nlev; l += THREADS) lvl_s[l] = lvl_off[l0 + l] - q0;
-    for (int p = threadIdx.x; p < nb; p += THREADS) {
-        const SNode r = recs[q0 + p];
-        rec_s[p] = r;
-        if (r.k_or_leaf >= 0) {
-            double v[KPC];
-            ld_draws<KPC>(ys + (size_t)r.k_or_leaf * KP + k0, v);
+    __syncthreads();
+    const double Sk = efflen_adj ? S[k] : 1.0;
+    for (int base = slot_t; base < nb; base += 4 * NPP) {
+        SNode r[4];
+        double v0[4], uv[4];
+        float adj[4];
+        float2 gx[4];
 #pragma unroll
-            for (int kk = 0; kk < KPC; ++kk) ys_s[kk * nb + p] = v[kk];
-        } else if (r.k_or_leaf == INT32_MIN) {
-#pragma unroll
-            for (int kk = 0; kk < KPC; ++kk) G_s[kk * nb + p] = root_G[(size_t)r.slot * KP + k0 + kk];
-        } else {
-            const int leaf = -1 - r.k_or_leaf;
-            double v[KPC];
-            ld_draws<KPC>(g + (size_t)leaf * KP + k0, v);
-            const double adj = efflen_adj ? (double)efflen_adj[leaf] : 0.0;
-#pragma unroll
-            for (int kk = 0; kk < KPC; ++kk) {
-                double gv = v[kk];
-                if (efflen_adj) gv = __dsub_rn(gv, __ddiv_rn(adj, Sk[kk]));  // likelihood.jl:105
-                if (xgrad_out) xgrad_out[(size_t)leaf * KP + k0 + kk] = gv;
-                G_s[kk * nb + p] = make_float2((float)gv, 0.0f);
-            }
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * NPP;
+            r[u] = p < nb ? rec_s[p] : SNode{-1, -1, -1, -2};
+            if (p >= nb) r[u].k_or_leaf = INT32_MIN + 1;  // nothing to load
         }
-        if (r.slot == -1) {
 #pragma unroll
-            for (int kk = 0; kk < KPC; ++kk) us_s[kk * nb + p] = 1.0;
-        } else if (r.slot >= 0 && r.k_or_leaf != INT32_MIN) {
-            double v[KPC];
-            ld_draws<KPC>(root_us + (size_t)r.slot * KP + k0, v);
+        for (int u = 0; u < 4; ++u) {
+            v0[u] = 0.0; uv[u] = 1.0; adj[u] = 0.0f; gx[u] = make_float2(0.f, 0.f);
+            if (r[u].k_or_leaf >= 0) {
+                v0[u] = ys[(size_t)r[u].k_or_leaf * KP + k];
+            } else if (r[u].k_or_leaf == INT32_MIN) {
+                gx[u] = root_G[(size_t)r[u].slot * KP + k];
+            } else if (r[u].k_or_leaf != INT32_MIN + 1) {
+                const int leaf = -1 - r[u].k_or_leaf;
+                v0[u] = g[(size_t)leaf * KP + k];
+                if (efflen_adj) adj[u] = efflen_adj[leaf];
+            }
+            if (r[u].slot >= 0 && r[u].k_or_leaf != INT32_MIN) uv[u] = root_us[(size_t)r[u].slot * KP + k];
+        }
 #pragma unroll
-            for (int kk = 0; kk < KPC; ++kk) us_s[kk * nb + p] = v[kk];
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * NPP;
+            if (p >= nb) continue;
+            if (r[u].k_or_leaf >= 0) {
+                ys_s[p * KPC + kk] = v0[u];
+            } else if (r[u].k_or_leaf == INT32_MIN) {
+                G_s[p * KPC + kk] = gx[u];
+            } else {
+                const int leaf = -1 - r[u].k_or_leaf;
+                double gv = v0[u];
+                if (efflen_adj) gv = __dsub_rn(gv, __ddiv_rn((double)adj[u], Sk));  // likelihood.jl:105
+                if (xgrad_out) xgrad_out[(size_t)leaf * KP + k] = gv;
+                G_s[p * KPC + kk] = make_float2((float)gv, 0.0f);
+            }
+            if (r[u].slot >= -1 && r[u].k_or_leaf != INT32_MIN) us_s[p * KPC + kk] = uv[u];
         }
     }
     __syncthreads();
@@ -375,15 +353,12 @@ __global__ void __launch_bounds__(THREADS, MINB)
     // forward recompute of u (same operations as k3s_tree_fwd -> same bits)
     for (int l = 0; l < nlev; ++l) {
         const int lo = lvl_s[l], hi = lvl_s[l + 1];
-        for (int p = lo + threadIdx.x; p < hi; p += THREADS) {
+        for (int p = lo + slot_t; p < hi; p += NPP) {
             const SNode r = rec_s[p];
             if (r.k_or_leaf >= 0) {
-#pragma unroll
-                for (int kk = 0; kk < KPC; ++kk) {
-                    const double ui = us_s[kk * nb + p], y = ys_s[kk * nb + p];
-                    us_s[kk * nb + r.left] = __dmul_rn(y, ui);
-                    us_s[kk * nb + r.right] = __dmul_rn(__dsub_rn(1.0, y), ui);
-                }
+                const double ui = us_s[p * KPC + kk], y = ys_s[p * KPC + kk];
+                us_s[r.left * KPC + kk] = __dmul_rn(y, ui);
+                us_s[r.right * KPC + kk] = __dmul_rn(__dsub_rn(1.0, y), ui);
             }
         }
         __syncthreads();
@@ -391,36 +366,28 @@ __global__ void __launch_bounds__(THREADS, MINB)
     // backward sweep
     for (int l = nlev - 1; l >= 0; --l) {
         const int lo = lvl_s[l], hi = lvl_s[l + 1];
-        for (int p = lo + threadIdx.x; p < hi; p += THREADS) {
+        for (int p = lo + slot_t; p < hi; p += NPP) {
             const SNode r = rec_s[p];
             if (r.k_or_leaf >= 0) {
-                double yg[KPC];
-#pragma unroll
-                for (int kk = 0; kk < KPC; ++kk) {
-                    const float2 gl = G_s[kk * nb + r.left], gr = G_s[kk * nb + r.right];
-                    const double y = ys_s[kk * nb + p], ui = us_s[kk * nb + p];
-                    const double omy = __dsub_rn(1.0, y);
-                    float2 out;
-                    out.x = (float)__dadd_rn(__dmul_rn(y, (double)gl.x), __dmul_rn(omy, (double)gr.x));
-                    if (WITH_LADJ) {
-                        const float d = __fsub_rn(__fadd_rn(gl.x, gl.y), __fadd_rn(gr.x, gr.y));
-                        yg[kk] = (double)(float)__dmul_rn(ui, (double)d);
-                        out.y = (float)__dadd_rn(__dadd_rn(__ddiv_rn(1.0, ui), __dmul_rn(y, (double)gl.y)),
-                                                 __dmul_rn(omy, (double)gr.y));
-                    } else {
-                        const float d = __fsub_rn(gl.x, gr.x);
-                        yg[kk] = __dmul_rn(ui, (double)d);
-                        out.y = 0.0f;
-                    }
-                    G_s[kk * nb + p] = out;
+                const float2 gl = G_s[r.left * KPC + kk], gr = G_s[r.right * KPC + kk];
+                const double y = ys_s[p * KPC + kk], ui = us_s[p * KPC + kk];
+                const double omy = __dsub_rn(1.0, y);
+                float2 out;
+                out.x = (float)__dadd_rn(__dmul_rn(y, (double)gl.x), __dmul_rn(omy, (double)gr.x));
+                if (WITH_LADJ) {
+                    const float d = __fsub_rn(__fadd_rn(gl.x, gl.y), __fadd_rn(gr.x, gr.y));
+                    ygrad[(size_t)r.k_or_leaf * KP + k] = (double)(float)__dmul_rn(ui, (double)d);
+                    out.y = (float)__dadd_rn(__dadd_rn(__ddiv_rn(1.0, ui), __dmul_rn(y, (double)gl.y)),
+                                             __dmul_rn(omy, (double)gr.y));
+                } else {
+                    const float d = __fsub_rn(gl.x, gr.x);
+                    ygrad[(size_t)r.k_or_leaf * KP + k] = __dmul_rn(ui, (double)d);
+                    out.y = 0.0f;
                 }
-#pragma unroll
-                for (int kk = 0; kk < KPC; ++kk) ygrad[(size_t)r.k_or_leaf * KP + k0 + kk] = yg[kk];
+                G_s[p * KPC + kk] = out;
             }
-            if (r.slot >= 0 && r.k_or_leaf != INT32_MIN && l == 0) {
-#pragma unroll
-                for (int kk = 0; kk < KPC; ++kk) root_G[(size_t)r.slot * KP + k0 + kk] = G_s[kk * nb + p];  // to the top part
-            }
+            if (r.slot >= 0 && r.k_or_leaf != INT32_MIN && l == 0)
+                root_G[(size_t)r.slot * KP + k] = G_s[p * KPC + kk];  // bottom subtree root: hand G to the top part
         }
         __syncthreads();
     }
@@ -763,8 +730,8 @@ static int launch_tree_fwd_smem(polee_handle *h, int clamp_x, const float *eff, 
             const int v = tree_variant();
             if (v == 1) launch_fwd_bottom_v<8, 8, 512, 1>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
             else if (v == 2) launch_fwd_bottom_v<8, 2, 256, 6>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
-            else if (v == 3) launch_fwd_bottom_v<8, 4, 256, 3>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
-            else launch_fwd_bottom_v<8, 8, 256, 2>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
+            else if (v == 3) launch_fwd_bottom_v<8, 8, 256, 2>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
+            else launch_fwd_bottom_v<8, 4, 256, 3>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
         } else {
             launch_fwd_bottom_v<KP, (KP < 8 ? KP : 8), 256, 2>(h, clamp_x, eff, Sp, want_ladj, ladj_tree);
         }
@@ -780,8 +747,8 @@ static int launch_tree_bwd_smem(polee_handle *h, const float *adj, double *xgrad
             const int v = tree_variant();
             if (v == 1) launch_bwd_bottom_v<8, 8, 512, 1, WITH_LADJ>(h, adj, xgrad_out);
             else if (v == 2) launch_bwd_bottom_v<8, 2, 256, 6, WITH_LADJ>(h, adj, xgrad_out);
-            else if (v == 3) launch_bwd_bottom_v<8, 4, 256, 3, WITH_LADJ>(h, adj, xgrad_out);
-            else launch_bwd_bottom_v<8, 8, 256, 2, WITH_LADJ>(h, adj, xgrad_out);
+            else if (v == 3) launch_bwd_bottom_v<8, 8, 256, 2, WITH_LADJ>(h, adj, xgrad_out);
+            else launch_bwd_bottom_v<8, 4, 256, 3, WITH_LADJ>(h, adj, xgrad_out);
         } else {
             launch_bwd_bottom_v<KP, (KP < 8 ? KP : 8), 256, 2, WITH_LADJ>(h, adj, xgrad_out);
         }
