@@ -121,6 +121,12 @@ int polee_step_stats(polee_handle *h, double *bytes_k1, double *bytes_k2, double
  * which = 1 (K1 forward SpMM), 2 (K2 transposed gradient), 3 (K3 tree+reparam+ADAM) */
 int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, float *ms_avg);
 
+/* Random.rand!(als::ApproxLikelihoodSampler, xs)  src/approx-sampler.jl:37-44 (used by `polee sample`,
+ * src/main.jl:845-855, and load_samples_hdf5's x0 init, src/estimate.jl:436-455): num_samples draws from the
+ * approximation held by the handle (polee_set_tree + polee_set_params with omega = log(sigma)); xs[num_samples][n].
+ * Device Philox noise keyed (seed; node, draw, batch). */
+int polee_sample(polee_handle *h, int32_t num_samples, uint64_t seed, float *xs);
+
 /* ------------------------------------------------------------------ piecewise (parity tests)
  * log_likelihood(frag_probs, log_frag_probs, X, Xt, xs, x_grad, Val(gradonly))  likelihood.jl:36-56
  * for K stacked xs vectors: xs[K][n] Float32 -> lp[K] (0 when gradonly), x_grad[K][n] Float64.

@@ -11,6 +11,7 @@ from ._lib import LIB_PATH, PoleeError, build_library, load_library  # noqa: F40
 from .api import (  # noqa: F401
     LIKAP_NUM_MC_SAMPLES,
     LIKAP_NUM_STEPS,
+    ApproxLikelihoodSampler,
     Handle,
     LogitSkewNormalPTTApprox,
     OptimizePTTApprox,

@@ -236,6 +236,11 @@ class Handle:
         out["elbo"] = elbo.value
         return out
 
+    def sample(self, num_samples, seed=0):
+        xs = np.zeros((num_samples, self.n), np.float32)
+        self.check(self.lib.polee_sample(self.h, C.c_int32(num_samples), C.c_uint64(seed), _p(xs)))
+        return xs
+
     # ---- multi-GPU
     def comm_init(self, nranks, rank, unique_id):
         self.check(self.lib.polee_comm_init(self.h, C.c_int32(nranks), C.c_int32(rank), C.c_char_p(unique_id)))
@@ -306,6 +311,25 @@ class PolyaTreeTransform:
         ys, ladj = self.handle.ptt_inverse_transform(xs)
         one = np.ndim(xs) == 1
         return (ys[0] if one else ys), (ladj[0] if one else ladj)
+
+
+class ApproxLikelihoodSampler:
+    """ApproxLikelihoodSampler (src/approx-sampler.jl:1-44): set_transform!(als, t, mu, sigma, alpha); rand!(als, xs)."""
+
+    def __init__(self, device=0, draws_per_launch=16):
+        self.handle = Handle(device=device, num_mc_samples=draws_per_launch)
+        self.calls = 0
+
+    def set_transform(self, t, mu, sigma, alpha):
+        """t: PolyaTreeTransform or (node_parent_idxs, node_js); sigma = exp(omega) as in src/main.jl:833."""
+        pi, js = (t.node_parent_idxs, t.node_js) if isinstance(t, PolyaTreeTransform) else t
+        self.handle.set_tree(pi, js)
+        self.handle.set_params(mu, np.log(_c(sigma, np.float32)), alpha)
+
+    def rand(self, num_samples=1, seed=None):
+        """rand!(als, xs) for num_samples draws at once -> xs[num_samples][n]"""
+        self.calls += 1
+        return self.handle.sample(num_samples, self.calls if seed is None else seed)
 
 
 def sequential_tree(n):

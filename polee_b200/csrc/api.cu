@@ -684,6 +684,29 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
     return rc;
 }
 
+// ------------------------------------------------------------------ approx-likelihood sampler
+// Random.rand!(als::ApproxLikelihoodSampler, xs)  src/approx-sampler.jl:37-44: zs = randn; sinh_asinh_transform!;
+// logit_normal_transform! (no clamp); transform!(t, ys, xs).  KP draws per launch at the handle's parameters.
+extern "C" int polee_sample(polee_handle *h, int32_t num_samples, uint64_t seed, float *xs) {
+    CHECK_H(h);
+    if (!h->have_tree) return h->fail(POLEE_EINVAL, "no tree: call polee_set_tree first");
+    if (h->o.approx != POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT) return h->fail(POLEE_EINVAL, "polee_sample needs a LogitSkewNormalPTTApprox handle");
+    if (num_samples < 0 || (!xs && num_samples > 0)) return h->fail(POLEE_EINVAL, "polee_sample: bad arguments");
+    h->n = h->td.n;
+    int rc = ensure_work_buffers(h, h->KP);
+    if (rc) return rc;
+    const int KP = h->KP;
+    h->reparam_ready = false;
+    for (int done = 0, batch = 0; done < num_samples; done += KP, ++batch) {
+        const int take = std::min(KP, num_samples - done);
+        if ((rc = launch_elem(h, KP, KP, false, false, true, nullptr, 1, 0, nullptr, batch, seed, 0))) return rc;
+        if ((rc = launch_tree_fwd(h, KP, 0, 0, 0))) return rc;
+        CK(cudaGetLastError());
+        if ((rc = download_kmajor<float, float>(h, h->x, take, KP, h->n, xs + (size_t)done * h->n))) return rc;
+    }
+    return POLEE_OK;
+}
+
 // ------------------------------------------------------------------ measurement helpers
 extern "C" int polee_step_stats(polee_handle *h, double *b1, double *b2, double *b3, int32_t *launches) {
     CHECK_H(h);

@@ -109,6 +109,8 @@ struct TreeHost {
     TreeSchedHost top, bottom;
     SSchedHost s_top, s_bottom;  // same cut, schedule-order records (shared-memory kernels)
     int n_slots = 0;             // exchange slots = bottom subtree roots
+    bool caterpillar = false;    // list tree: internal node k at index 2k, right child = leaf at 2k+1, left = 2k+2
+    std::vector<int32_t> chain_leaf;  // [n]: leaf id hanging off spine node k (k < n-1), [n-1] = the last leaf
     int top_nodes = 0;
     int max_depth = 0;
     // returns "" or an error text
@@ -125,6 +127,8 @@ struct TreeDev {
     TreeSchedDev top, bottom;
     SSchedDev s_top, s_bottom;
     int n_slots = 0;
+    bool caterpillar = false;
+    int32_t *chain_leaf = nullptr;
     bool smem_path = false;  // shared-memory kernels usable (top part fits one CTA per draw)
     void release();
 };
@@ -246,8 +250,13 @@ int launch_mid(polee_handle *h, int KP, int advance);
 int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, double *xgrad_out);
 int launch_update(polee_handle *h, int KP, int K, bool do_adam, float *grad_out);
 int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bool do_reparam, const float *noise,
-                int64_t noise_steps, int want_ladj, float *grad_out);
+                int64_t noise_steps, int want_ladj, float *grad_out, int step0_fixed = -1, uint64_t seed_override = 0,
+                int clamp_y = 1);
 int elem_ctas(polee_handle *h, int KP);
 int launch_elbo(polee_handle *h, int KP, int K, bool have_lp);
+
+// tree_chain.cu (caterpillar trees)
+int launch_chain_fwd(polee_handle *h, int KP, int clamp_x, const float *eff, double *Sp, int want_ladj, double *ladj_tree);
+int launch_chain_bwd(polee_handle *h, int KP, bool with_ladj, const float *adj, double *xgrad_out);
 
 }  // namespace polee

@@ -88,6 +88,20 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
     }
     for (int64_t i = N - 1; i >= 1; --i) size[parent[i]] += size[i];
 
+    // ---- caterpillar ("list") tree?
+    caterpillar = n >= 2;
+    for (int64_t i = 0; i < N && caterpillar; ++i) {
+        if (nodes[i].leaf >= 0) continue;
+        caterpillar = (i % 2 == 0) && nodes[i].right == i + 1 && nodes[i].left == i + 2 && nodes[i + 1].leaf >= 0;
+    }
+    chain_leaf.clear();
+    if (caterpillar) {
+        chain_leaf.resize(n);
+        for (int64_t kk = 0; kk < n - 1; ++kk) chain_leaf[kk] = nodes[2 * kk + 1].leaf;
+        chain_leaf[n - 1] = nodes[N - 1].leaf;
+        caterpillar = nodes[N - 1].leaf >= 0;
+    }
+
     // ---- cut: top = nodes whose subtree exceeds bin_nodes
     std::vector<char> is_top(N, 0);
     std::vector<int32_t> top_list;
@@ -246,6 +260,9 @@ void TreeDev::release() {
         cudaFree(s->sch_node);
         *s = TreeSchedDev();
     }
+    cudaFree(chain_leaf);
+    chain_leaf = nullptr;
+    caterpillar = false;
     for (SSchedDev *s : {&s_top, &s_bottom}) {
         cudaFree(s->bin_off);
         cudaFree(s->bin_lvl_ptr);
@@ -303,6 +320,8 @@ std::string upload_tree(const TreeHost &th, TreeDev &td) {
         dss[s]->max_bin_levels = hss[s]->max_bin_levels;
     }
     td.n_slots = th.n_slots;
+    td.caterpillar = th.caterpillar;
+    if (e == cudaSuccess && th.caterpillar) e = up(th.chain_leaf, &td.chain_leaf);
     if (e != cudaSuccess) return std::string("upload_tree: ") + cudaGetErrorString(e);
     return "";
 }

@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(256)
             float *__restrict__ zs0, double *__restrict__ ys, const double *__restrict__ ygrad,
             const StepCtl *__restrict__ ctl, AdamCfg cfg, int *__restrict__ bad_step, float *__restrict__ grad_out,
             const float *__restrict__ noise, int64_t noise_steps, uint64_t seed, int fast_noise, int want_ladj,
-            double *__restrict__ ladj_partial /* [2][gridDim.x][KP] */) {
+            double *__restrict__ ladj_partial /* [2][gridDim.x][KP] */, int step0_fixed, int clamp_y) {
     __shared__ double sm[256];
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool live = i < nm1;
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(256)
             ys[(size_t)i * KP] = (double)__fdiv_rn(1.0f, __fadd_rn(1.0f, e));  // ys = logistic(zs), no clamp (l-a.jl:196)
             zs0[(size_t)i * KP] = 0.0f;
         } else {
-            const int step0 = ctl->step_fwd - 1;  // 0-based index of the step these draws belong to
+            const int step0 = step0_fixed >= 0 ? step0_fixed : ctl->step_fwd - 1;  // 0-based index of the step of these draws
             const float sigma = expf(p_om);
             const float sa = sinhf(p_al), ca = coshf(p_al);
 #pragma unroll
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(256)
                     l_skew[k] = (double)logf(ch) - (double)logf(r);  // log cosh(c) - 0.5 log1p(z0^2)
                     l_ln[k] = log(__dmul_rn(__dmul_rn((double)sigma, y), __dsub_rn(1.0, y)));
                 }
-                y = fmin(fmax(y, 1e-10), 1.0 - 1e-10);
+                if (clamp_y) y = fmin(fmax(y, 1e-10), 1.0 - 1e-10);
                 zs0[(size_t)i * KP + k] = z0;
                 ys[(size_t)i * KP + k] = y;
             }
@@ -652,7 +652,7 @@ int ensure_work_buffers(polee_handle *h, int KP) {
     }
 
 int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bool do_reparam, const float *noise,
-                int64_t noise_steps, int want_ladj, float *grad_out) {
+                int64_t noise_steps, int want_ladj, float *grad_out, int step0_fixed, uint64_t seed_override, int clamp_y) {
     const int64_t nm1 = h->n - 1;
     if (nm1 <= 0) return POLEE_OK;
     const int mode = h->o.approx == POLEE_APPROX_OPTIMIZE_PTT ? 1 : 0;
@@ -661,13 +661,13 @@ int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bo
     DISPATCH_KP(KP, (k3_elem<KPC><<<ctas, 256, 0, h->stream>>>(
                         nm1, K, mode, do_update ? 1 : 0, do_adam ? 1 : 0, do_reparam ? 1 : 0, h->mu, h->omega, h->alpha, h->m_mu,
                         h->m_omega, h->m_alpha, h->v_mu, h->v_omega, h->v_alpha, h->zs0, h->ys, h->ygrad, h->d_step, cfg,
-                        h->d_bad_step, grad_out, noise, std::max<int64_t>(noise_steps, 1), h->o.seed, 1, want_ladj,
-                        h->ladj_partial)));
+                        h->d_bad_step, grad_out, noise, std::max<int64_t>(noise_steps, 1),
+                        step0_fixed >= 0 ? seed_override : h->o.seed, 1, want_ladj, h->ladj_partial, step0_fixed, clamp_y)));
     return POLEE_OK;
 }
 
 int launch_reparam_fwd(polee_handle *h, int KP, int K, const float *noise, int64_t noise_steps, int want_ladj) {
-    return launch_elem(h, KP, K, false, false, true, noise, noise_steps, want_ladj, nullptr);
+    return launch_elem(h, KP, K, false, false, true, noise, noise_steps, want_ladj, nullptr, -1, 0, 1);
 }
 
 constexpr int S_BOT_THREADS = 512;
@@ -777,11 +777,19 @@ static bool smem_path_ok(const polee_handle *h, int KP) {
            (size_t)td.s_top.max_bin_nodes * (sizeof(SNode) + 24) + 4 * (td.s_top.max_bin_levels + 2) <= limit;
 }
 
+// large caterpillar trees take the scan kernels of tree_chain.cu (POLEE_CHAIN_MIN_NODES overrides the threshold)
+static bool chain_path(const polee_handle *h) {
+    const char *e = getenv("POLEE_CHAIN_MIN_NODES");
+    const int64_t min_nodes = e ? atoll(e) : 4096;
+    return h->td.caterpillar && h->td.N >= min_nodes;
+}
+
 int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_ladj) {
     const TreeDev &td = h->td;
     double *ladj_tree = h->ladj_partial + (size_t)2 * elem_ctas(h, KP) * KP;
     const float *eff = want_S ? h->efflen : nullptr;
     double *Sp = want_S ? h->S_partial : nullptr;
+    if (chain_path(h)) return launch_chain_fwd(h, KP, clamp_x, eff, Sp, want_ladj, ladj_tree);
     if (smem_path_ok(h, KP)) {
         int rc = POLEE_OK;
         DISPATCH_KP(KP, rc = launch_tree_fwd_smem<KPC>(h, clamp_x, eff, Sp, want_ladj, ladj_tree));
@@ -808,6 +816,7 @@ int launch_mid(polee_handle *h, int KP, int advance) {
 int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, double *xgrad_out) {
     const TreeDev &td = h->td;
     const float *adj = apply_efflen ? h->efflen_adj : nullptr;
+    if (chain_path(h)) return launch_chain_bwd(h, KP, with_ladj, adj, xgrad_out);
     if (smem_path_ok(h, KP)) {
         int rc = POLEE_OK;
         if (with_ladj) {
@@ -834,7 +843,7 @@ int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, 
 }
 
 int launch_update(polee_handle *h, int KP, int K, bool do_adam, float *grad_out) {
-    return launch_elem(h, KP, K, true, do_adam, false, nullptr, 1, 0, grad_out);
+    return launch_elem(h, KP, K, true, do_adam, false, nullptr, 1, 0, grad_out, -1, 0, 1);
 }
 
 int launch_elbo(polee_handle *h, int KP, int K, bool have_lp) {

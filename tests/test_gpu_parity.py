@@ -288,3 +288,75 @@ def test_non_finite_gradient_is_reported(pb, fx):
         h.fit()
     assert e.value.code == L.POLEE_ENONFINITE and "step 1" in str(e.value)
     h.close()
+
+
+def test_approx_likelihood_sampler(pb, fx, oracle):
+    """Random.rand!(::ApproxLikelihoodSampler, xs) (src/approx-sampler.jl:37-44) on the device: draws from the
+    reference's own fitted approximation (prep.h5) reproduce the survey's probe statistics (mean log-likelihood of
+    draws -327172 +- 30) and every draw is a point of the simplex."""
+    als = pb.ApproxLikelihoodSampler(draws_per_launch=16)
+    als.set_transform((fx.parent_idxs, fx.js), fx.mu, np.exp(fx.omega), fx.alpha)
+    xs = als.rand(400, seed=1)
+    assert xs.shape == (400, fx.n) and np.all(xs > 0)
+    np.testing.assert_allclose(xs.astype(np.float64).sum(1), 1.0, atol=2e-5)
+    M = oracle.Model(fx.m, fx.n, fx.colptr, fx.rowval, fx.nzval)
+    lps = [M.log_likelihood(np.maximum(x, np.float32(1e-10)), gradonly=False)[0] for x in xs[:300]]
+    assert abs(np.mean(lps) - (-327172.0)) < 30.0
+    xs2 = als.rand(400, seed=1)
+    assert np.array_equal(xs, xs2)                       # counter-based noise: same seed, same draws
+    assert not np.array_equal(xs[:16], xs[16:32])         # batches use different Philox counters
+    # moments agree with the CPU restatement of rand! (conftest.sample_loglik) on the abundant transcripts
+    from conftest import sample_loglik
+    _, xm = sample_loglik(oracle, fx, fx.mu, fx.omega, fx.alpha, ndraws=400, seed=3)
+    big = xm > 1e-3
+    assert np.median(np.abs(xs.mean(0)[big] - xm[big]) / xm[big]) < 0.05
+
+
+def test_large_sequential_tree_scan_path(pb, oracle):
+    """Caterpillar trees with >= 4096 nodes take the blocked-scan kernels (tree_chain.cu).  They re-associate the
+    Float64 products and carry the backward recurrences in Float64, so the comparison with the serial reference
+    sweep is to rounding error: x <= 1e-12 relative, y_grad <= 2e-5 of its scale (the reference itself rounds G to
+    Float32 at every one of the n-1 spine nodes)."""
+    from polee_b200.api import sequential_tree
+    n, K = 6000, 3
+    pi, js = sequential_tree(n)
+    rng = np.random.default_rng(2)
+    # ys of a near-uniform composition (what the fit starts from): u_k stays O(1/n), no underflow
+    x0 = rng.dirichlet(np.ones(n) * 5.0, K).astype(np.float32)
+    to = oracle.PTT(pi, js)
+    ys = np.stack([to.inverse_transform(x0[k])[0] for k in range(K)])
+    t = pb.PolyaTreeTransform(pi, js)
+    xs, ladj = t.transform(ys, compute_ladj=True)
+    x_grad = rng.normal(size=(K, n)) * 100
+    yg = t.transform_gradients(ys, x_grad)
+    yg0 = t.transform_gradients_no_ladj(ys, x_grad)
+    for k in range(K):
+        xo, ladj_o = to.transform(ys[k], True)
+        assert relerr(xs[k], xo) <= 2e-7                  # Float32 output of a Float64 product differing by ~1e-16
+        assert abs(ladj[k] - ladj_o) <= 1e-10 * abs(ladj_o)
+        ygo = to.transform_gradients(ys[k], x_grad[k])
+        assert np.abs(yg[k] - ygo).max() <= 2e-5 * np.abs(ygo).max()
+        ygo0 = to.transform_gradients_no_ladj(ys[k], x_grad[k])
+        assert np.abs(yg0[k] - ygo0).max() <= 2e-5 * np.abs(ygo0).max()
+
+
+def test_optimize_ptt_large_sequential(pb, small_synth, oracle):
+    """optimize_likelihood on n = 1500 takes the level-synchronous path, on a padded n >= 2048 the scan path; both
+    must reach the oracle's objective."""
+    s = small_synth
+    sample = _synth_sample(pb, s)
+    steps = 40
+    xo = oracle.fit_optimize_ptt(s["m"], s["n"], s["colptr"], s["rowval"], s["nzval"], s["efflens"], steps)
+    M = oracle.Model(s["m"], s["n"], s["colptr"], s["rowval"], s["nzval"])
+    lp_o, _ = M.log_likelihood(xo, gradonly=False)
+    for env in ("1000000000", "1"):                      # force level-synchronous / force scan kernels
+        import os
+        os.environ["POLEE_CHAIN_MIN_NODES"] = env
+        h = pb.Handle(approx=1, num_steps=steps)
+        h.set_sample(sample)
+        xd = h.fit_optimize_ptt()
+        h.close()
+        lp_d, _ = M.log_likelihood(xd, gradonly=False)
+        assert abs(lp_d - lp_o) <= 2e-4 * abs(lp_o), env
+        assert abs(xd.astype(np.float64).sum() - 1.0) < 1e-4
+    os.environ.pop("POLEE_CHAIN_MIN_NODES")
