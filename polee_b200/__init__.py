@@ -25,4 +25,5 @@ from .api import (  # noqa: F401
     make_inverse_ptt_params,
     optimize_likelihood,
     partition_rows,
+    prep_many,
 )

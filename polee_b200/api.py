@@ -419,6 +419,40 @@ def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, us
     return params
 
 
+def prep_many(samples, tree_topologies, devices=(0,), **fit_kwargs):
+    """The sample loop of `polee prep` (src/main.jl:590-631) with whole samples sharded over GPUs: "replicas only"
+    (BASELINE config 5) -- one worker per device pulls the next sample from a queue; no collective.
+    Returns the parameter dicts in input order.  Handles are independent, ctypes releases the GIL during calls."""
+    import queue
+    import threading
+
+    todo = queue.Queue()
+    for i, (smp, tree) in enumerate(zip(samples, tree_topologies)):
+        todo.put((i, smp, tree))
+    out = [None] * len(samples)
+    errors = []
+
+    def worker(dev):
+        while True:
+            try:
+                i, smp, tree = todo.get_nowait()
+            except queue.Empty:
+                return
+            try:
+                out[i] = approximate_likelihood(LogitSkewNormalPTTApprox(), smp, tree_topology=tree, device=dev, **fit_kwargs)
+            except Exception as e:  # surface after joining
+                errors.append((i, e))
+
+    threads = [threading.Thread(target=worker, args=(d,)) for d in devices]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0][1]
+    return out
+
+
 def optimize_likelihood(sample, device=0):
     """optimize_likelihood(sample) (src/likelihood-approximation.jl:23-25)"""
     return approximate_likelihood(OptimizePTTApprox(), sample, device=device)["x"]

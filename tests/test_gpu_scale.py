@@ -75,3 +75,49 @@ def test_config3_shape_properties():
     assert all(np.all(np.isfinite(out[k])) for k in ("mu", "omega", "alpha"))
     assert nnz > 100_000_000
     h.close()
+
+
+def test_config5_many_samples_replicas():
+    """C5 shape in miniature: whole samples handed to per-device workers (no collective); concurrent handles on
+    one GPU give exactly the sequential results."""
+    import polee_b200 as pb
+    from polee_b200 import synth
+    samples, trees = [], []
+    for i in range(5):
+        s = synth.make_sample(40000 + 7000 * i, 2500, seed=300 + i)
+        ns = synth.to_numpy_sample(s)
+        samples.append(pb.RNASeqSample(ns["m"], ns["n"], ns["colptr"], ns["rowval"], ns["nzval"], ns["efflens"]))
+        trees.append(synth.balanced_tree(2500, s["gene_sizes"].numpy()))
+    seq = [pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), s, tree_topology=t, num_steps=30, num_mc_samples=8)
+           for s, t in zip(samples, trees)]
+    par = pb.prep_many(samples, trees, devices=(0, 0, 0), num_steps=30, num_mc_samples=8)
+    for a, b in zip(seq, par):
+        assert all(np.array_equal(a[k], b[k]) for k in ("mu", "omega", "alpha"))
+
+
+def test_config4_shape_long_rows_properties():
+    """C4 shape (heavy multi-mapping: 10 % of the rows span 64-512 transcripts), scaled to one GPU's test budget:
+    m = 4 M, n = 250 k, nnz ~ 120 M; gradient identity, determinism and a finite fit."""
+    import torch
+    import polee_b200 as pb
+    from polee_b200 import synth
+    m, n, K = 4_000_000, 250_000, 8
+    s, colptr, rowval = _device_sample(m, n, 20260004, long_rows=True)
+    assert s["nnz"] > 100_000_000
+    efflens = s["efflens"].cpu().numpy()
+    tree = synth.balanced_tree(n, s["gene_sizes"].cpu().numpy())
+    h = pb.Handle(num_mc_samples=K, num_steps=3)
+    h.set_matrix_device(m, n, colptr.data_ptr(), rowval.data_ptr(), s["nzval"].data_ptr())
+    del s, colptr, rowval
+    torch.cuda.empty_cache()
+    h.set_efflens(efflens)
+    h.set_tree(*tree)
+    xs = np.random.default_rng(0).dirichlet(np.ones(n), K).astype(np.float32).clip(1e-10)
+    lp, g = h.loglik_grad(xs, gradonly=False)
+    ident = (xs.astype(np.float64) * g).sum(1)
+    assert np.max(np.abs(ident - m)) <= 1e-5 * m
+    lp2, g2 = h.loglik_grad(xs, gradonly=False)
+    assert np.array_equal(g, g2) and np.array_equal(lp, lp2)
+    out = h.fit()
+    assert all(np.all(np.isfinite(out[k])) for k in ("mu", "omega", "alpha"))
+    h.close()
