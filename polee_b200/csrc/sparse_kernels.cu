@@ -321,7 +321,7 @@ struct VecD {  // KP doubles; 256-bit requests (sm_100) where KP allows
 constexpr int V2_CONSUMER_WARPS = 8;
 constexpr int V2_THREADS = (V2_CONSUMER_WARPS + 1) * 32;
 constexpr int K1_TC = 8;      // entries of a row per ring stage
-constexpr int K1_STAGES = 4;
+constexpr int K1_STAGES = 3;
 
 struct K1Smem {
     uint32_t idx[K1_STAGES][K1_TC][ROW_TILE];
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(V2_THREADS, 3)
 }
 
 // ---------------------------------------------------------------- K2 v2
-constexpr int K2_STAGES = 4;
+constexpr int K2_STAGES = 2;
 constexpr int K2_ITEM_ENTRIES = K2_WARPS * COL_SEG;  // 2048
 
 constexpr int K2_PART_BUFS = 2 * K2_STAGES;  // consumers can run at most K2_STAGES items ahead of a combine
@@ -736,7 +736,8 @@ template <int KP>
 int launch_k2_t(polee_handle *h, const float *w, double *g) {
     if (h->n_segs > 0) {
         const int n_items = (h->n_segs + K2_WARPS - 1) / K2_WARPS;
-        const int grid = std::min(n_items, h->num_sms * 3);
+        static const int k2_ctas = getenv("POLEE_K2_CTAS") ? atoi(getenv("POLEE_K2_CTAS")) : 3;
+        const int grid = std::min(n_items, h->num_sms * k2_ctas);
         const size_t smem = sizeof(K2Smem);
         // the producer-warp L2 prefetch of w rows measured SLOWER on B200 (0.508 vs 0.483 ms at C3): opt-in only
         static const bool no_pf = !(getenv("POLEE_K2_PREFETCH") && !strcmp(getenv("POLEE_K2_PREFETCH"), "1"));
