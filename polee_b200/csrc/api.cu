@@ -230,7 +230,7 @@ extern "C" int polee_set_efflens(polee_handle *h, const float *efflens) {
     CK(cudaMemcpy(h->efflen, efflens, sizeof(float) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->efflen_adj, adj.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
     h->have_efflen = true;
-    return POLEE_OK;
+    return patch_leaf_records(h);
 }
 
 static int alloc_params(polee_handle *h) {
@@ -252,6 +252,7 @@ static int finish_tree(polee_handle *h, const std::string &err) {
     h->have_tree = true;
     int rc = alloc_params(h);
     if (rc) return rc;
+    if ((rc = patch_leaf_records(h))) return rc;
     return polee_init_params(h);
 }
 

@@ -93,6 +93,7 @@ struct SSchedHost {
 struct SSchedDev {
     int32_t *bin_off = nullptr, *bin_lvl_ptr = nullptr, *lvl_off = nullptr;
     SNode *recs = nullptr;
+    int32_t *bin_desc = nullptr;  // [nbins][4] = {q0, nb, l0, nlev} (persistent kernels)
     int nbins = 0, max_bin_nodes = 0, max_bin_levels = 0;
 };
 
@@ -209,6 +210,7 @@ struct polee_handle {
     float *grad_out = nullptr;            // [3][n-1] averaged grads (polee_lsn_draws)
     int work_KP = 0;                      // KP the work buffers were sized for
     int n_tree_ctas = 0;
+    int tree_grid = 0;  // persistent bottom-tree grid
 
     // ---- graph
     cudaGraph_t graph = nullptr;
@@ -253,6 +255,7 @@ int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bo
                 int64_t noise_steps, int want_ladj, float *grad_out, int step0_fixed = -1, uint64_t seed_override = 0,
                 int clamp_y = 1);
 int elem_ctas(polee_handle *h, int KP);
+int patch_leaf_records(polee_handle *h);
 int launch_elbo(polee_handle *h, int KP, int K, bool have_lp);
 
 // tree_chain.cu (caterpillar trees)

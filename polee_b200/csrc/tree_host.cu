@@ -268,6 +268,7 @@ void TreeDev::release() {
         cudaFree(s->bin_lvl_ptr);
         cudaFree(s->lvl_off);
         cudaFree(s->recs);
+        cudaFree(s->bin_desc);
         *s = SSchedDev();
     }
     nodes = nullptr;
@@ -314,6 +315,16 @@ std::string upload_tree(const TreeHost &th, TreeDev &td) {
             e = cudaMalloc((void **)&dss[s]->recs, bytes);
             if (e == cudaSuccess && !hss[s]->recs.empty())
                 e = cudaMemcpy(dss[s]->recs, hss[s]->recs.data(), hss[s]->recs.size() * sizeof(SNode), cudaMemcpyHostToDevice);
+        }
+        if (e == cudaSuccess) {
+            std::vector<int32_t> desc;
+            for (int b = 0; b < hss[s]->nbins(); ++b) {
+                desc.push_back(hss[s]->bin_off[b]);
+                desc.push_back(hss[s]->bin_off[b + 1] - hss[s]->bin_off[b]);
+                desc.push_back(hss[s]->bin_lvl_ptr[b]);
+                desc.push_back(hss[s]->bin_lvl_ptr[b + 1] - 1 - hss[s]->bin_lvl_ptr[b]);
+            }
+            e = up(desc, &dss[s]->bin_desc);
         }
         dss[s]->nbins = hss[s]->nbins();
         dss[s]->max_bin_nodes = hss[s]->max_bin_nodes;

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 }
                 x[(size_t)leaf * KP + k] = xv;
                 xd[(size_t)leaf * KP + k] = (double)xv;
-                if (efflen) sacc = __dadd_rn(sacc, (double)__fdiv_rn(xv, efflen[leaf]));
+                if (efflen) sacc = __dadd_rn(sacc, (double)__fdiv_rn(xv, __int_as_float(r.left)));
             }
         }
         __syncthreads();
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
             } else if (r[u].k_or_leaf != INT32_MIN + 1) {
                 const int leaf = -1 - r[u].k_or_leaf;
                 v0[u] = g[(size_t)leaf * KP + k];
-                if (efflen_adj) adj[u] = efflen_adj[leaf];
+                if (efflen_adj) adj[u] = __int_as_float(r[u].right);
             }
             if (r[u].slot >= 0 && r[u].k_or_leaf != INT32_MIN) uv[u] = root_us[(size_t)r[u].slot * KP + k];
         }
@@ -390,6 +390,20 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 root_G[(size_t)r.slot * KP + k] = G_s[p * KPC + kk];  // bottom subtree root: hand G to the top part
         }
         __syncthreads();
+    }
+}
+
+// Leaf records carry the leaf's effective length (left) and Float32(n / efflen) (right) as raw Float32 bits, so the
+// level loops never touch global memory for them.
+__global__ void k_patch_leaf_recs(SNode *recs, int count, const float *__restrict__ efflen, const float *__restrict__ adj) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    SNode r = recs[q];
+    if (r.k_or_leaf < 0 && r.k_or_leaf != INT32_MIN) {
+        const int leaf = -1 - r.k_or_leaf;
+        r.left = __float_as_int(efflen[leaf]);
+        r.right = __float_as_int(adj[leaf]);
+        recs[q] = r;
     }
 }
 
@@ -612,7 +626,8 @@ int ensure_work_buffers(polee_handle *h, int KP) {
     if (h->work_KP == KP) return POLEE_OK;
     release_work_buffers(h);
     const int64_t n = h->n, nm1 = std::max<int64_t>(n - 1, 1), N = 2 * n - 1;
-    h->n_tree_ctas = 1 + h->td.bottom.nbins;
+    h->tree_grid = std::max(1, std::min(h->td.s_bottom.nbins * std::max(1, KP / std::min(KP, 4)), 2 * h->num_sms));
+    h->n_tree_ctas = 1 + std::max(h->td.bottom.nbins, h->tree_grid);
     CK(cudaMalloc((void **)&h->zs0, sizeof(float) * nm1 * KP));
     CK(cudaMalloc((void **)&h->zs, sizeof(float) * nm1 * KP));
     CK(cudaMalloc((void **)&h->ys, sizeof(double) * nm1 * KP));
@@ -650,6 +665,17 @@ int ensure_work_buffers(polee_handle *h, int KP) {
         case 16: { constexpr int KPC = 16; CALL; } break;                       \
         default: return h->fail(POLEE_EINVAL, "unsupported number of MC draws (1..16)"); \
     }
+
+int patch_leaf_records(polee_handle *h) {
+    if (!h->have_efflen || !h->have_tree) return POLEE_OK;
+    for (SSchedDev *sd : {&h->td.s_top, &h->td.s_bottom}) {
+        const int count = (int)(sd == &h->td.s_top ? h->th.s_top.recs.size() : h->th.s_bottom.recs.size());
+        if (count > 0)
+            k_patch_leaf_recs<<<(count + 255) / 256, 256, 0, h->stream>>>(sd->recs, count, h->efflen, h->efflen_adj);
+    }
+    CK(cudaGetLastError());
+    return POLEE_OK;
+}
 
 int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bool do_reparam, const float *noise,
                 int64_t noise_steps, int want_ladj, float *grad_out, int step0_fixed, uint64_t seed_override, int clamp_y) {
