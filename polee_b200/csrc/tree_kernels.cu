@@ -28,6 +28,7 @@ namespace polee {
 namespace {
 
 constexpr int TREE_THREADS = 256;
+constexpr int ELEM_THREADS = 128;  // k3_elem: one thread per internal node; small CTAs keep the tail wave short
 constexpr int TOP_THREADS = 1024;
 
 // ---------------------------------------------------------------- noise ("polee-philox-v1")
@@ -440,7 +441,7 @@ __device__ __forceinline__ void adam_one(float &param, float &m, float &v, doubl
 // likewise from cosh/sinh(alpha)): the same real function as the reference's Float32 expression with two
 // transcendentals per NODE instead of four per DRAW; the difference is a few Float32 ulp.
 template <int KP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ELEM_THREADS)
     k3_elem(int64_t nm1, int K, int mode, int do_update, int do_adam, int do_reparam, float *__restrict__ mu,
             float *__restrict__ omega, float *__restrict__ alpha, float *__restrict__ m_mu, float *__restrict__ m_omega,
             float *__restrict__ m_alpha, float *__restrict__ v_mu, float *__restrict__ v_omega, float *__restrict__ v_alpha,
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(256)
             const StepCtl *__restrict__ ctl, AdamCfg cfg, int *__restrict__ bad_step, float *__restrict__ grad_out,
             const float *__restrict__ noise, int64_t noise_steps, uint64_t seed, int fast_noise, int want_ladj,
             double *__restrict__ ladj_partial /* [2][gridDim.x][KP] */, int step0_fixed, int clamp_y) {
-    __shared__ double sm[256];
+    __shared__ double sm[ELEM_THREADS];
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool live = i < nm1;
     float p_mu = 0.f, p_om = 0.f, p_al = 0.f;
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(256)
         for (int k = 0; k < KP; ++k) {
             sm[threadIdx.x] = l_skew[k];
             __syncthreads();
-            for (int span = 128; span >= 1; span >>= 1) {
+            for (int span = ELEM_THREADS / 2; span >= 1; span >>= 1) {
                 if ((int)threadIdx.x < span) sm[threadIdx.x] += sm[threadIdx.x + span];
                 __syncthreads();
             }
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(256)
             __syncthreads();
             sm[threadIdx.x] = l_ln[k];
             __syncthreads();
-            for (int span = 128; span >= 1; span >>= 1) {
+            for (int span = ELEM_THREADS / 2; span >= 1; span >>= 1) {
                 if ((int)threadIdx.x < span) sm[threadIdx.x] += sm[threadIdx.x + span];
                 __syncthreads();
             }
@@ -619,7 +620,7 @@ void release_work_buffers(polee_handle *h) {
 
 int elem_ctas(polee_handle *h, int KP) {
     (void)KP;
-    return (int)std::max<int64_t>(1, (h->n - 1 + 255) / 256);
+    return (int)std::max<int64_t>(1, (h->n - 1 + ELEM_THREADS - 1) / ELEM_THREADS);
 }
 
 int ensure_work_buffers(polee_handle *h, int KP) {
@@ -684,7 +685,7 @@ int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bo
     const int mode = h->o.approx == POLEE_APPROX_OPTIMIZE_PTT ? 1 : 0;
     AdamCfg cfg{h->o.max_step_mu, h->o.max_step_omega, h->o.max_step_alpha, h->o.max_step_z};
     const int ctas = elem_ctas(h, KP);
-    DISPATCH_KP(KP, (k3_elem<KPC><<<ctas, 256, 0, h->stream>>>(
+    DISPATCH_KP(KP, (k3_elem<KPC><<<ctas, ELEM_THREADS, 0, h->stream>>>(
                         nm1, K, mode, do_update ? 1 : 0, do_adam ? 1 : 0, do_reparam ? 1 : 0, h->mu, h->omega, h->alpha, h->m_mu,
                         h->m_omega, h->m_alpha, h->v_mu, h->v_omega, h->v_alpha, h->zs0, h->ys, h->ygrad, h->d_step, cfg,
                         h->d_bad_step, grad_out, noise, std::max<int64_t>(noise_steps, 1),
