@@ -50,28 +50,65 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region, sampled through NVML every few ms (the nvidia-smi
+    query of B200_PROFILING.md takes longer than a whole timed region here); falls back to nvidia-smi."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.004):
         self.gpu = gpu_index
-        self.rows = []
+        self.period = period_s
+        self.sm, self.reasons = [], set()
+        self.sm_max = None
         self.stop = threading.Event()
         self.t = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: map the CUDA ordinal to the NVML device through the PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+            self.h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        self.h = hh
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def _run(self):
+        n = self.nvml
+        bits = {}
+        if n is not None:
+            for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+                v = getattr(n, attr, None) or getattr(n, attr.replace("ClocksEventReason", "ClocksThrottleReason"), None)
+                if v is not None:
+                    bits[name] = v
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
+                if n is not None:
+                    self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                    get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+                    r = get(self.h)
+                    for name, b in bits.items():
+                        if r & b:
+                            self.reasons.add(name)
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    a, b = out.strip().split(",")
+                    self.sm.append(float(a)); self.sm_max = float(b)
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(self.period)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -83,19 +120,10 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active") and not v.lower().startswith("not"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def generate(cfg, device):
@@ -161,12 +189,17 @@ def run_ours(args):
     m_loc, colptr_d, rowval_d, nzval_d = row_block_device(s, bounds[rank], bounds[rank + 1])
     nnz_loc = int(rowval_d.numel())
 
-    # host copy of the full matrix for the e2e arm and the CPU baseline (rank 0 only)
+    # pinned host copies for the e2e arm: the whole matrix at N = 1 (also feeds the CPU baseline), each rank's own
+    # row block at N > 1
     host = None
-    if rank == 0 and not args.no_e2e:
-        pin = lambda t, dt: torch.empty(t.shape, dtype=dt, pin_memory=True).copy_(t.to(dt)).numpy()  # noqa: E731
-        host = {"colptr": pin(s["colptr"], torch.int32).view(np.uint32), "rowval": pin(s["rowval"], torch.int32).view(np.uint32),
-                "nzval": pin(s["nzval"], torch.float32)}
+    pin = lambda t, dt: torch.empty(t.shape, dtype=dt, pin_memory=True).copy_(t.to(dt)).numpy()  # noqa: E731
+    if not args.no_e2e:
+        if world == 1:
+            host = {"colptr": pin(s["colptr"], torch.int32).view(np.uint32), "rowval": pin(s["rowval"], torch.int32).view(np.uint32),
+                    "nzval": pin(s["nzval"], torch.float32)}
+        else:
+            host = {"colptr": pin(colptr_d, torch.int32).view(np.uint32), "rowval": pin(rowval_d, torch.int32).view(np.uint32),
+                    "nzval": pin(nzval_d, torch.float32)}
     del s
     torch.cuda.empty_cache()
 
@@ -235,13 +268,13 @@ def run_ours(args):
             roofline["traffic"] = json.load(open(tr)).get(dom[0])
         except Exception:
             pass
-    h.close()
-    torch.cuda.empty_cache()
 
-    # ---- e2e: one whole fit through the public API from host buffers (rank 0 at N = 1 only)
+    # ---- e2e: one whole fit through the public API from HOST buffers
     e2e = None
     cpu = None
-    if rank == 0 and host is not None and world == 1:
+    if host is not None and world == 1:
+        h.close()
+        torch.cuda.empty_cache()
         sample = pb.RNASeqSample(m, n, host["colptr"], host["rowval"], host["nzval"], efflens)
         for rep in range(2):   # first call warms the CUDA context / allocator; the second is reported
             torch.cuda.synchronize()
@@ -257,6 +290,35 @@ def run_ours(args):
                        "%d ADAM steps x %d draws + parameter download" % (FIT_STEPS, K)}
         if not args.no_cpu:
             cpu = cpu_baseline(m, n, K, host, efflens, tree, budget_s=args.cpu_budget)
+    elif host is not None:
+        # N > 1: every rank re-feeds its own row block from host memory into its (comm-initialised) handle and runs
+        # the whole 500-step fit; wall time, max over ranks
+        block = pb.RNASeqSample(m_loc, n, host["colptr"], host["rowval"], host["nzval"], efflens)
+        h.opts.num_steps = FIT_STEPS
+        t_fit = None
+        for rep in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            h.set_sample(block)
+            h.set_tree(*tree)
+            h.init_params()
+            h.run_steps(FIT_STEPS)
+            h.sync()
+            out = h.get_params()
+            tt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_fit = float(tt.item())
+        h2d = host["colptr"].nbytes + host["rowval"].nbytes + host["nzval"].nbytes + efflens.nbytes + 2 * 4 * (2 * n - 1)
+        hb = torch.tensor([h2d], device=dev, dtype=torch.float64)
+        dist.all_reduce(hb)
+        e2e = {"value": round(K * FIT_STEPS / t_fit, 1), "unit": "evals/s", "h2d_bytes_per_step": int(hb.item()),
+               "d2h_bytes_per_step": int(3 * 4 * (n - 1)), "fit_time_s": round(t_fit, 4), "adam_steps_per_fit": FIT_STEPS,
+               "step": "every rank: its row block's CSC upload from pinned host memory + layout build + %d ADAM steps x %d "
+                       "draws (one all-reduce each) + parameter download; wall time, max over ranks" % (FIT_STEPS, K)}
+        h.close()
+    else:
+        h.close()
+    torch.cuda.empty_cache()
 
     if rank == 0:
         line = {"metric": "elbo_grad_evals_per_sec", "value": round(evals_per_s, 1), "unit": "evals/s", "n_gpus": world,
