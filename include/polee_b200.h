@@ -88,6 +88,13 @@ int polee_set_matrix_csc_device(polee_handle *h, int64_t m, int64_t n, const uin
                                 const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks);
 /* sample.effective_lengths (Float32[n]) */
 int polee_set_efflens(polee_handle *h, const float *efflens);
+/* Optional: the gene -> transcripts map of `--gene-noninformative` (the `gene_transcripts` Dict built at
+ * likelihood-approximation.jl:476-493), flattened: gene g owns transcripts[gene_ptr[g] .. gene_ptr[g+1]).  When set,
+ * every draw adds gene_noninformative_prior! (likelihood.jl:114-159) to x_grad after the effective-length adjustment
+ * (likelihood-approximation.jl:535-538).  Needs opts.use_efflen_jacobian (the reference's prior reads the `xls` that
+ * adjustment fills) and the unweighted LogitSkewNormalPTTApprox fit.  num_genes == 0 clears the map (the default). */
+int polee_set_gene_groups(polee_handle *h, int64_t num_genes, const int64_t *gene_ptr /* num_genes+1, 0-based offsets */,
+                          const int32_t *transcripts /* 1-based transcript ids */);
 /* PolyaTreeTransform(parent_idxs, output_idxs)  src/ptt.jl:89-116; 2n-1 entries each, as written to
  * .prep.h5 (node_parent_idxs, node_js).  Also computes the initial parameters
  * (likelihood-approximation.jl:451-456). */

@@ -78,6 +78,14 @@ end
 set_efflens!(h, efflens::Vector{Float32}) =
     check(h, ccall((:polee_set_efflens, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}), h, efflens))
 
+function set_gene_groups!(h, gene_transcripts::Dict{String,Vector{Int}})
+    groups = collect(values(gene_transcripts))
+    gene_ptr = Int64[0; cumsum(length.(groups))]
+    transcripts = Int32[i for g in groups for i in g]      # 1-based, as stored in the Dict
+    check(h, ccall((:polee_set_gene_groups, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int32}),
+                   h, length(groups), gene_ptr, transcripts))
+end
+
 function set_tree!(h, t::Polee.PolyaTreeTransform)
     parent_idxs = Vector{Int32}(t.index[4, :])   # what the reference serialises (l-a.jl:618-621)
     js = Vector{Int32}(t.index[1, :])
@@ -100,10 +108,24 @@ function approximate_likelihood_b200(approx::Polee.LogitSkewNormalPTTApprox, sam
                                      tree_topology_output_filename=nothing,
                                      gene_noninformative::Bool=false,
                                      use_efflen_jacobian::Bool=true) where {gradonly}
-    if gene_noninformative || tree_topology_output_filename !== nothing
-        # rarely used diagnostics (likelihood.jl:114-159, l-a.jl:578-613) are not on the GPU path; enable!()
-        # has overwritten the CPU method, so run those invocations without PoleeB200 loaded.
-        error("PoleeB200: --gene-noninformative / --write-tree-topology are only available on the CPU path")
+    if tree_topology_output_filename !== nothing
+        # the YAML tree dump (l-a.jl:578-613) walks the host-side HClustNode objects; enable!() has overwritten
+        # the CPU method, so run that diagnostic without PoleeB200 loaded.
+        error("PoleeB200: --write-tree-topology is only available on the CPU path")
+    end
+    # gene_id -> transcript indexes, exactly as l-a.jl:476-493
+    gene_transcripts = Dict{String,Vector{Int}}()
+    if gene_noninformative
+        for (i, tr) in enumerate(sample.ts)
+            tid = tr.metadata.name
+            if haskey(sample.transcript_metadata.gene_id, tid)
+                push!(get!(gene_transcripts, sample.transcript_metadata.gene_id[tid], Int[]), i)
+            end
+        end
+        if isempty(gene_transcripts)
+            @warn "'--gene-noninformative' used, but no gene information available"
+            gene_noninformative = false
+        end
     end
     X = sample.X
     m, n = size(X)
@@ -129,6 +151,7 @@ function approximate_likelihood_b200(approx::Polee.LogitSkewNormalPTTApprox, sam
         set_matrix!(h, X)
         set_efflens!(h, sample.effective_lengths)
         pj = set_tree!(h, t)
+        gene_noninformative && set_gene_groups!(h, gene_transcripts)
         check(h, ccall((:polee_fit, LIB), Cint,
                        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Ptr{Float32}),
                        h, mu, omega, alpha, C_NULL, C_NULL))

@@ -159,6 +159,34 @@ double orc_effective_length_jacobian_adjustment(int64_t n, const float *efflens,
     return 0.0;
 }
 
+/* likelihood.jl:114-159.  `values(gene_transcripts)` iterates a Julia Dict (order unpinned); it only decides the
+ * order of the Float64 sum `offdiag_contrib`, which here runs over transcripts 1..n as the reference's loop :144 does. */
+double orc_gene_noninformative_prior(int64_t n, const float *efflens, const float *xls, double *xl_grad,
+                                     const float *xs, double *x_grad, const orc_genes *genes) {
+    for (int64_t i = 0; i < n; ++i) xl_grad[i] = 0.0;                                   /* :118 */
+    for (int64_t g = 0; g < genes->num_genes; ++g) {                                     /* :120-133 */
+        int64_t b = genes->gene_ptr[g], e = genes->gene_ptr[g + 1], k = e - b;
+        if (k > 1) {
+            double c = 0.0;
+            for (int64_t q = b; q < e; ++q) c += (double)xls[genes->transcripts[q] - 1];
+            for (int64_t q = b; q < e; ++q) xl_grad[genes->transcripts[q] - 1] = -(double)(k - 1) / c;
+        }
+    }
+    double x_scaled_sum = 0.0;                                                           /* :137-141 */
+    for (int64_t i = 0; i < n; ++i) x_scaled_sum += (double)(xs[i] / efflens[i]);
+    double x_scaled_sum_sq = x_scaled_sum * x_scaled_sum;
+    double offdiag_contrib = 0.0;                                                        /* :143-147 */
+    for (int64_t i = 0; i < n; ++i) offdiag_contrib += -xl_grad[i] * (double)xls[i];
+    offdiag_contrib /= x_scaled_sum_sq;
+    for (int64_t i = 0; i < n; ++i) {                                                    /* :149-154 */
+        float inv = 1.0f / efflens[i];
+        double grad_a = xl_grad[i] * ((double)inv / x_scaled_sum);
+        double grad_b = (double)inv * offdiag_contrib;
+        x_grad[i] += grad_a + grad_b;
+    }
+    return 0.0;
+}
+
 /* =============================== ptt.jl =============================== */
 
 #define IDX(t, r, i) ((t)->index[4 * (size_t)((i)-1) + ((r)-1)]) /* 1-based (row, node) */
@@ -517,7 +545,7 @@ static void lsn_init(orc_ptt *t, int64_t n, float *mu, float *omega, float *alph
 /* scratch for one draw */
 typedef struct {
     float *zs, *xs, *xls, *y_grad, *z_grad, *sigma_grad, *sigma;
-    double *ys, *x_grad;
+    double *ys, *x_grad, *xl_grad;
 } draw_ws;
 
 static void ws_init(draw_ws *w, int64_t n) {
@@ -527,16 +555,17 @@ static void ws_init(draw_ws *w, int64_t n) {
     w->z_grad = (float *)calloc(nm1, 4); w->sigma_grad = (float *)calloc(nm1, 4);
     w->sigma = (float *)calloc(nm1, 4);
     w->ys = (double *)calloc(nm1, 8); w->x_grad = (double *)calloc((size_t)n, 8);
+    w->xl_grad = (double *)calloc((size_t)n, 8);
 }
 static void ws_free(draw_ws *w) {
     free(w->zs); free(w->xs); free(w->xls); free(w->y_grad); free(w->z_grad);
-    free(w->sigma_grad); free(w->sigma); free(w->ys); free(w->x_grad);
+    free(w->sigma_grad); free(w->sigma); free(w->ys); free(w->x_grad); free(w->xl_grad);
 }
 
 /* body of the MC loop, likelihood-approximation.jl:512-549 (and :322-355 when ks != NULL).
  * Accumulates into mu_grad / omega_grad / alpha_grad, returns this draw's "elbo". */
 static double lsn_draw_body(orc_model *M, orc_ptt *t, const int64_t *ks, const float *efflens,
-                            int gradonly, int use_efflen_jacobian, const float *mu,
+                            int gradonly, int use_efflen_jacobian, const orc_genes *genes, const float *mu,
                             const float *alpha, const float *zs0, draw_ws *w, float *mu_grad,
                             float *omega_grad, float *alpha_grad) {
     int64_t n = M->n, nm1 = n - 1;
@@ -572,6 +601,8 @@ static double lsn_draw_body(orc_model *M, orc_ptt *t, const int64_t *ks, const f
                                 lik_gradonly);                                         /* :528 */
     if (use_efflen_jacobian)
         lp += orc_effective_length_jacobian_adjustment(n, efflens, w->xs, w->xls, w->x_grad); /* :531 */
+    if (genes && !ks)                                                                  /* :535-538 */
+        lp += orc_gene_noninformative_prior(n, efflens, w->xls, w->xl_grad, w->xs, w->x_grad, genes);
     double elbo = lp + skew_ladj + ln_ladj + hsb_ladj;                                 /* :540 */
 
     orc_ptt_transform_gradients(t, w->ys, w->y_grad, w->x_grad);                       /* :542 */
@@ -634,7 +665,7 @@ int orc_fit_step(orc_fit_state *s) {
             memcpy(zs0, o->noise + ((size_t)(step - 1) * K + d) * (size_t)nm1, sizeof(float) * (size_t)nm1);
         else
             orc_noise_fill(o->seed, step - 1, d, nm1, zs0);                  /* :517-519 */
-        double e = lsn_draw_body(&s->M, s->t, s->ks, s->efflens, o->gradonly, o->use_efflen_jacobian, s->mu,
+        double e = lsn_draw_body(&s->M, s->t, s->ks, s->efflens, o->gradonly, o->use_efflen_jacobian, o->genes, s->mu,
                                  s->alpha, zs0, &s->w, mu_grad, omega_grad, alpha_grad);
         if (o->elbo_fix) elbo += e; else elbo = e;                           /* :540 (quirk) */
     }
@@ -693,6 +724,17 @@ double orc_lsn_draw(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t
                     int use_efflen_jacobian, const float *mu, const float *omega, const float *alpha,
                     const float *zs0, float *xs, double *ys, double *x_grad, float *y_grad,
                     float *mu_grad, float *omega_grad, float *alpha_grad) {
+    return orc_lsn_draw_genes(m, n, colptr, rowval, nzval, ks, efflens, node_parent_idxs, node_js, gradonly,
+                              use_efflen_jacobian, NULL, mu, omega, alpha, zs0, xs, ys, x_grad, y_grad, mu_grad,
+                              omega_grad, alpha_grad);
+}
+
+double orc_lsn_draw_genes(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,
+                          const float *nzval, const int64_t *ks, const float *efflens,
+                          const int32_t *node_parent_idxs, const int32_t *node_js, int gradonly,
+                          int use_efflen_jacobian, const orc_genes *genes, const float *mu, const float *omega,
+                          const float *alpha, const float *zs0, float *xs, double *ys, double *x_grad,
+                          float *y_grad, float *mu_grad, float *omega_grad, float *alpha_grad) {
     int64_t nm1 = n - 1;
     orc_model M;
     model_init(&M, m, n, colptr, rowval, nzval);
@@ -703,7 +745,7 @@ double orc_lsn_draw(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t
     memset(mu_grad, 0, sizeof(float) * (size_t)nm1);
     memset(omega_grad, 0, sizeof(float) * (size_t)nm1);
     memset(alpha_grad, 0, sizeof(float) * (size_t)nm1);
-    double e = lsn_draw_body(&M, t, ks, efflens, gradonly, use_efflen_jacobian, mu, alpha, zs0, &w,
+    double e = lsn_draw_body(&M, t, ks, efflens, gradonly, use_efflen_jacobian, genes, mu, alpha, zs0, &w,
                              mu_grad, omega_grad, alpha_grad);
     memcpy(xs, w.xs, sizeof(float) * (size_t)n);
     memcpy(ys, w.ys, sizeof(double) * (size_t)nm1);

@@ -117,6 +117,17 @@ void orc_adam_update_params(int64_t len, float *params, const float *ms, const f
  *      reference uses Julia's global MersenneTwister randn(Float32), which cannot be reproduced) ---- */
 void orc_noise_fill(uint64_t seed, int64_t step, int64_t draw, int64_t nm1, float *zs0);
 
+/* gene -> transcripts map of gene_noninformative_prior! (likelihood-approximation.jl:476-493), flattened */
+typedef struct {
+    int64_t num_genes;
+    const int64_t *gene_ptr;     /* num_genes + 1 offsets into transcripts */
+    const int32_t *transcripts;  /* 1-based transcript ids */
+} orc_genes;
+
+/* likelihood.jl:114-159 (xls as left by orc_effective_length_jacobian_adjustment) */
+double orc_gene_noninformative_prior(int64_t n, const float *efflens, const float *xls, double *xl_grad,
+                                     const float *xs, double *x_grad, const orc_genes *genes);
+
 /* ---- the fits ---- */
 typedef struct {
     int num_steps;            /* LIKAP_NUM_STEPS */
@@ -126,6 +137,7 @@ typedef struct {
     uint64_t seed;
     const float *noise;       /* nullable: [num_steps][num_mc_samples][n-1] injected zs0 */
     int elbo_fix;             /* 0: reference quirk (elbo assigned per draw); 1: mean over draws */
+    const orc_genes *genes;   /* nullable: gene_noninformative=true (likelihood-approximation.jl:535-538) */
 } orc_fit_opts;
 
 /* approximate_likelihood(::LogitSkewNormalPTTApprox, sample)  likelihood-approximation.jl:395-624
@@ -153,6 +165,14 @@ double orc_lsn_draw(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t
                     int use_efflen_jacobian, const float *mu, const float *omega, const float *alpha,
                     const float *zs0, float *xs /*n*/, double *ys /*n-1*/, double *x_grad /*n*/,
                     float *y_grad /*n-1*/, float *mu_grad, float *omega_grad, float *alpha_grad);
+
+/* the same with the gene prior switched on (genes nullable) */
+double orc_lsn_draw_genes(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,
+                          const float *nzval, const int64_t *ks, const float *efflens,
+                          const int32_t *node_parent_idxs, const int32_t *node_js, int gradonly,
+                          int use_efflen_jacobian, const orc_genes *genes, const float *mu, const float *omega,
+                          const float *alpha, const float *zs0, float *xs, double *ys, double *x_grad,
+                          float *y_grad, float *mu_grad, float *omega_grad, float *alpha_grad);
 
 /* approximate_likelihood(::OptimizePTTApprox, sample)  likelihood-approximation.jl:149-242 */
 int orc_fit_optimize_ptt(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,

@@ -28,7 +28,22 @@ def build(force=False):
 
 class OrcFitOpts(C.Structure):
     _fields_ = [("num_steps", c_int), ("num_mc_samples", c_int), ("gradonly", c_int),
-                ("use_efflen_jacobian", c_int), ("seed", c_u64), ("noise", P), ("elbo_fix", c_int)]
+                ("use_efflen_jacobian", c_int), ("seed", c_u64), ("noise", P), ("elbo_fix", c_int), ("genes", P)]
+
+
+class OrcGenes(C.Structure):
+    _fields_ = [("num_genes", c_i64), ("gene_ptr", P), ("transcripts", P)]
+
+
+def make_genes(gene_transcripts):
+    """{gene: [1-based transcript ids]} (or a list of id lists) -> (OrcGenes, keep-alive arrays); None -> (None, ())"""
+    if not gene_transcripts:
+        return None, ()
+    groups = list(gene_transcripts.values()) if hasattr(gene_transcripts, "values") else list(gene_transcripts)
+    ptr = np.zeros(len(groups) + 1, np.int64)
+    ptr[1:] = np.cumsum([len(g) for g in groups])
+    tx = np.ascontiguousarray(np.concatenate([np.asarray(g, np.int32) for g in groups]), np.int32)
+    return OrcGenes(len(groups), _p(ptr), _p(tx)), (ptr, tx)
 
 
 _lib = None
@@ -52,6 +67,7 @@ def lib():
         _lib.orc_fit_begin.restype = P
         _lib.orc_adam_learning_rate.restype = c_dbl
         _lib.orc_lsn_draw.restype = c_dbl
+        _lib.orc_lsn_draw_genes.restype = c_dbl
     return _lib
 
 
@@ -111,6 +127,16 @@ def effective_length_jacobian_adjustment(efflens, xs, x_grad):
     xls = np.empty_like(xs)
     lib().orc_effective_length_jacobian_adjustment(c_i64(len(xs)), _p(efflens), _p(xs), _p(xls), _p(x_grad))
     return xls
+
+
+def gene_noninformative_prior(efflens, xls, xs, x_grad, gene_transcripts):
+    """likelihood.jl:114-159; adds to x_grad in place, returns xl_grad"""
+    efflens = _c(efflens, np.float32); xs = _c(xs, np.float32); xls = _c(xls, np.float32)
+    genes, _keep = make_genes(gene_transcripts)
+    xl_grad = np.zeros(len(xs), np.float64)
+    lib().orc_gene_noninformative_prior(c_i64(len(xs)), _p(efflens), _p(xls), _p(xl_grad), _p(xs), _p(x_grad),
+                                        C.byref(genes))
+    return xl_grad
 
 
 # ------------------------------------------------------------------ ptt
@@ -174,7 +200,8 @@ def noise_fill(seed, step, draw, nm1):
 
 
 def fit_lsn_ptt(m, n, colptr, rowval, nzval, efflens, parent_idxs, js, ks=None, num_steps=500, num_mc_samples=6,
-                gradonly=True, use_efflen_jacobian=True, seed=0, noise=None, elbo_fix=False):
+                gradonly=True, use_efflen_jacobian=True, seed=0, noise=None, elbo_fix=False, gene_transcripts=None):
+    genes, _keep = make_genes(gene_transcripts)
     colptr = _c(colptr, np.uint32); rowval = _c(rowval, np.uint32); nzval = _c(nzval, np.float32)
     efflens = _c(efflens, np.float32); parent_idxs = _c(parent_idxs, np.int32); js = _c(js, np.int32)
     if ks is not None:
@@ -182,7 +209,8 @@ def fit_lsn_ptt(m, n, colptr, rowval, nzval, efflens, parent_idxs, js, ks=None, 
     if noise is not None:
         noise = _c(noise, np.float32)
         assert noise.size == num_steps * num_mc_samples * (n - 1)
-    o = OrcFitOpts(num_steps, num_mc_samples, int(gradonly), int(use_efflen_jacobian), seed, _p(noise), int(elbo_fix))
+    o = OrcFitOpts(num_steps, num_mc_samples, int(gradonly), int(use_efflen_jacobian), seed, _p(noise), int(elbo_fix),
+                   C.cast(C.pointer(genes), P) if genes is not None else None)
     mu = np.zeros(n - 1, np.float32); omega = np.zeros(n - 1, np.float32); alpha = np.zeros(n - 1, np.float32)
     elbo = np.zeros(num_steps, np.float64)
     st = lib().orc_fit_lsn_ptt(c_i64(m), c_i64(n), _p(colptr), _p(rowval), _p(nzval), _p(ks), _p(efflens),
@@ -200,7 +228,7 @@ class FitStepper:
         self.keep = [_c(colptr, np.uint32), _c(rowval, np.uint32), _c(nzval, np.float32), _c(efflens, np.float32),
                      _c(parent_idxs, np.int32), _c(js, np.int32), None if ks is None else _c(ks, np.int64)]
         self.n = n
-        o = OrcFitOpts(0, num_mc_samples, int(gradonly), int(use_efflen_jacobian), seed, None, 0)
+        o = OrcFitOpts(0, num_mc_samples, int(gradonly), int(use_efflen_jacobian), seed, None, 0, None)
         k = self.keep
         self.s = lib().orc_fit_begin(c_i64(m), c_i64(n), _p(k[0]), _p(k[1]), _p(k[2]), _p(k[6]), _p(k[3]), _p(k[4]),
                                      _p(k[5]), C.byref(o))
@@ -221,7 +249,8 @@ class FitStepper:
 
 
 def lsn_draw(m, n, colptr, rowval, nzval, efflens, parent_idxs, js, mu, omega, alpha, zs0, ks=None, gradonly=True,
-             use_efflen_jacobian=True):
+             use_efflen_jacobian=True, gene_transcripts=None):
+    genes, _keep = make_genes(gene_transcripts)
     colptr = _c(colptr, np.uint32); rowval = _c(rowval, np.uint32); nzval = _c(nzval, np.float32)
     efflens = _c(efflens, np.float32); parent_idxs = _c(parent_idxs, np.int32); js = _c(js, np.int32)
     mu = _c(mu, np.float32); omega = _c(omega, np.float32); alpha = _c(alpha, np.float32); zs0 = _c(zs0, np.float32)
@@ -230,9 +259,10 @@ def lsn_draw(m, n, colptr, rowval, nzval, efflens, parent_idxs, js, mu, omega, a
     out = {"xs": np.zeros(n, np.float32), "ys": np.zeros(n - 1, np.float64), "x_grad": np.zeros(n, np.float64),
            "y_grad": np.zeros(n - 1, np.float32), "mu_grad": np.zeros(n - 1, np.float32),
            "omega_grad": np.zeros(n - 1, np.float32), "alpha_grad": np.zeros(n - 1, np.float32)}
-    out["elbo"] = lib().orc_lsn_draw(
+    out["elbo"] = lib().orc_lsn_draw_genes(
         c_i64(m), c_i64(n), _p(colptr), _p(rowval), _p(nzval), _p(ks), _p(efflens), _p(parent_idxs), _p(js),
-        c_int(int(gradonly)), c_int(int(use_efflen_jacobian)), _p(mu), _p(omega), _p(alpha), _p(zs0),
+        c_int(int(gradonly)), c_int(int(use_efflen_jacobian)), C.byref(genes) if genes is not None else None,
+        _p(mu), _p(omega), _p(alpha), _p(zs0),
         _p(out["xs"]), _p(out["ys"]), _p(out["x_grad"]), _p(out["y_grad"]), _p(out["mu_grad"]),
         _p(out["omega_grad"]), _p(out["alpha_grad"]))
     return out

@@ -30,7 +30,8 @@ class PoleeOpts(C.Structure):
 # every symbol include/polee_b200.h declares (tests check that the built library exports them all)
 EXPORTS = [
     "polee_opts_default", "polee_create", "polee_destroy", "polee_last_error", "polee_device_info",
-    "polee_set_matrix_csc", "polee_set_matrix_csc_device", "polee_set_efflens", "polee_set_tree",
+    "polee_set_matrix_csc", "polee_set_matrix_csc_device", "polee_set_efflens", "polee_set_gene_groups",
+    "polee_set_tree",
     "polee_set_tree_sequential", "polee_fit", "polee_fit_optimize_ptt", "polee_init_params", "polee_run_steps",
     "polee_sync", "polee_get_params", "polee_set_params", "polee_set_noise", "polee_get_elbo", "polee_stream",
     "polee_step_stats", "polee_time_kernel", "polee_sample", "polee_loglik_grad", "polee_frag_prob_recip", "polee_ptt_transform",

@@ -115,6 +115,15 @@ class Handle:
     def set_efflens(self, efflens):
         self.check(self.lib.polee_set_efflens(self.h, _p(_c(efflens, np.float32))))
 
+    def set_gene_groups(self, gene_transcripts):
+        """gene_transcripts: {gene_id: [1-based transcript indices]} as built at likelihood-approximation.jl:476-487
+        (or any iterable of index lists).  Empty / None clears the map."""
+        groups = list(gene_transcripts.values()) if hasattr(gene_transcripts, "values") else list(gene_transcripts or [])
+        ptr = np.zeros(len(groups) + 1, np.int64)
+        ptr[1:] = np.cumsum([len(g) for g in groups])
+        tx = _c(np.concatenate([np.asarray(g, np.int32) for g in groups]) if groups else np.zeros(0, np.int32), np.int32)
+        self.check(self.lib.polee_set_gene_groups(self.h, C.c_int64(len(groups)), _p(ptr), _p(tx)))
+
     def set_tree(self, node_parent_idxs, node_js):
         pi, js = _c(node_parent_idxs, np.int32), _c(node_js, np.int32)
         assert pi.shape == js.shape and len(js) % 2 == 1
@@ -377,7 +386,7 @@ def log_likelihood(sample, xs, gradonly=True, ks=None, tree=None, device=0, exac
 def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, use_efflen_jacobian=True,
                            gene_noninformative=False, ks=None, num_steps=LIKAP_NUM_STEPS,
                            num_mc_samples=LIKAP_NUM_MC_SAMPLES, seed=123456789, noise=None, device=0, want_elbo=False,
-                           exact_accumulation=False):
+                           exact_accumulation=False, gene_transcripts=None):
     """approximate_likelihood(approx, sample, Val(gradonly); tree_topology_input_filename, use_efflen_jacobian,
     gene_noninformative) -> Dict  (src/likelihood-approximation.jl:395-624; :248-392 with ks; :149-242 for
     OptimizePTTApprox).
@@ -385,9 +394,13 @@ def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, us
     tree_topology = (node_parent_idxs, node_js), what the reference reads from tree_topology_input_filename
     (:428-433).  The reference otherwise builds the tree on the host with hclust (stays Julia, north_star); this
     mirror accepts treemethod "sequential" without a topology and requires one for "cluster"/"random".
+    gene_transcripts = {gene_id: [1-based transcript indices]} is the map the reference derives from the transcript
+    metadata when gene_noninformative is set (:476-487); without it the flag is dropped with a warning (:489-492).
     """
-    if gene_noninformative:
-        raise NotImplementedError("gene_noninformative prior (likelihood.jl:114-159) is off by default and out of scope")
+    if gene_noninformative and not gene_transcripts:
+        import warnings
+        warnings.warn("'--gene-noninformative' used, but no gene information available")
+        gene_noninformative = False
     if isinstance(approx, OptimizePTTApprox):
         h = Handle(device=device, approx=L.APPROX_OPTIMIZE_PTT, num_steps=num_steps)
         try:
@@ -410,6 +423,8 @@ def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, us
     try:
         h.set_sample(sample, ks)
         h.set_tree(*tree_topology)
+        if gene_noninformative:
+            h.set_gene_groups(gene_transcripts)
         params = h.fit(noise=noise, want_elbo=want_elbo)
     finally:
         h.close()

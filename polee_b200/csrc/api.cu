@@ -149,6 +149,8 @@ extern "C" int polee_destroy(polee_handle *h) {
     h->td.release();
     cudaFree(h->efflen); cudaFree(h->efflen_adj); cudaFree(h->elbo); cudaFree(h->noise);
     cudaFree(h->d_step); cudaFree(h->d_bad_step);
+    release_gene_buffers(h);
+    cudaFree(h->gene_ptr); cudaFree(h->gene_tx);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return POLEE_OK;
@@ -231,6 +233,45 @@ extern "C" int polee_set_efflens(polee_handle *h, const float *efflens) {
     CK(cudaMemcpy(h->efflen_adj, adj.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
     h->have_efflen = true;
     return patch_leaf_records(h);
+}
+
+// Gene groups of gene_noninformative_prior! (likelihood.jl:114-159): the flattened `gene_transcripts` Dict the reference
+// builds at likelihood-approximation.jl:476-493.  Only genes with more than one transcript contribute (:123).
+extern "C" int polee_set_gene_groups(polee_handle *h, int64_t num_genes, const int64_t *gene_ptr, const int32_t *transcripts) {
+    CHECK_H(h);
+    drop_graph(h);
+    release_gene_buffers(h);
+    cudaFree(h->gene_ptr); cudaFree(h->gene_tx);
+    h->gene_ptr = nullptr; h->gene_tx = nullptr; h->n_genes = 0; h->gene_n = 0;
+    if (num_genes == 0) return POLEE_OK;
+    if (num_genes < 0 || !gene_ptr || !transcripts) return h->fail(POLEE_EINVAL, "set_gene_groups: null pointer");
+    const int64_t n = h->have_matrix ? h->n : (h->have_tree ? h->td.n : 0);
+    if (n < 1) return h->fail(POLEE_EINVAL, "set_gene_groups: set the matrix or the tree first (n unknown)");
+    if (gene_ptr[0] != 0) return h->fail(POLEE_EINVAL, "set_gene_groups: gene_ptr[0] must be 0");
+    std::vector<int64_t> ptr{0};
+    std::vector<int32_t> tx;
+    std::vector<uint8_t> seen((size_t)n, 0);
+    for (int64_t gidx = 0; gidx < num_genes; ++gidx) {
+        const int64_t b = gene_ptr[gidx], e = gene_ptr[gidx + 1];
+        if (e < b) return h->fail(POLEE_EINVAL, "set_gene_groups: gene_ptr must be non-decreasing");
+        for (int64_t q = b; q < e; ++q) {
+            const int64_t i = (int64_t)transcripts[q] - 1;  // 1-based ids, as the Dict values
+            if (i < 0 || i >= n) return h->fail(POLEE_EINVAL, "set_gene_groups: transcript id out of range 1..n");
+            if (seen[i]) return h->fail(POLEE_EINVAL, "set_gene_groups: a transcript belongs to more than one gene");
+            seen[i] = 1;
+        }
+        if (e - b < 2) continue;
+        for (int64_t q = b; q < e; ++q) tx.push_back(transcripts[q] - 1);
+        ptr.push_back((int64_t)tx.size());
+    }
+    h->gene_n = n;
+    h->n_genes = (int64_t)ptr.size() - 1;
+    if (h->n_genes == 0) return POLEE_OK;  // nothing but single-transcript genes: the prior is identically zero
+    CK(cudaMalloc((void **)&h->gene_ptr, sizeof(int64_t) * ptr.size()));
+    CK(cudaMalloc((void **)&h->gene_tx, sizeof(int32_t) * tx.size()));
+    CK(cudaMemcpy(h->gene_ptr, ptr.data(), sizeof(int64_t) * ptr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->gene_tx, tx.data(), sizeof(int32_t) * tx.size(), cudaMemcpyHostToDevice));
+    return POLEE_OK;
 }
 
 static int alloc_params(polee_handle *h) {
@@ -359,10 +400,20 @@ static int ready_for_steps(polee_handle *h) {
     if (h->n != h->td.n) return h->fail(POLEE_EINVAL, "matrix and tree disagree on n");
     const bool need_eff = h->o.use_efflen_jacobian || h->o.approx == POLEE_APPROX_OPTIMIZE_PTT;
     if (need_eff && !h->have_efflen) return h->fail(POLEE_EINVAL, "no effective lengths: call polee_set_efflens first");
+    if (h->n_genes > 0) {
+        // the reference reads xls, which only effective_length_jacobian_adjustment! fills (likelihood.jl:98-101), and
+        // the factored / OptimizePTT entries have no gene prior (likelihood-approximation.jl:248-251, :149-151)
+        if (h->gene_n != h->n) return h->fail(POLEE_EINVAL, "gene groups were set for a different n");
+        if (h->o.approx != POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT || h->row_weight)
+            return h->fail(POLEE_EINVAL, "gene groups: the prior exists only in the unweighted LogitSkewNormalPTTApprox fit");
+        if (!h->o.use_efflen_jacobian)
+            return h->fail(POLEE_EINVAL, "gene groups need use_efflen_jacobian (the prior reads the scaled abundances it computes)");
+    }
     if (h->o.noise_mode == POLEE_NOISE_INJECTED && h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT && !h->noise)
         return h->fail(POLEE_EINVAL, "noise_mode is INJECTED but no noise was supplied");
     int rc = ensure_work_buffers(h, h->KP);
     if (rc) return rc;
+    if ((rc = ensure_gene_buffers(h, h->KP))) return rc;
     if (!h->elbo) {
         CK(cudaMalloc((void **)&h->elbo, sizeof(double) * std::max(h->o.num_steps, 1)));
         CK(cudaMemset(h->elbo, 0, sizeof(double) * std::max(h->o.num_steps, 1)));
@@ -393,6 +444,7 @@ static int launch_step_sequence(polee_handle *h, bool do_adam, bool next_reparam
         if (r != ncclSuccess) return h->fail(POLEE_ENCCL, std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r));
     }
 #endif
+    if (h->n_genes > 0 && (rc = launch_gene_prior(h, KP))) return rc;
     if ((rc = launch_tree_bwd(h, KP, lsn, apply_eff, xgrad_out))) return rc;
     if (want_vals && (rc = launch_elbo(h, KP, K, true))) return rc;
     if ((rc = launch_elem(h, KP, K, true, do_adam, next_reparam, noise, noise_steps, next_reparam && want_vals, grad_out)))
@@ -643,6 +695,7 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
     if (rc == POLEE_EINVAL && !h->noise && h->o.noise_mode == POLEE_NOISE_INJECTED && h->have_matrix && h->have_tree) {
         h->err.clear();
         rc = ensure_work_buffers(h, h->KP);
+        if (!rc) rc = ensure_gene_buffers(h, h->KP);
         if (!rc && !h->elbo) {
             CK(cudaMalloc((void **)&h->elbo, sizeof(double) * std::max(h->o.num_steps, 1)));
             CK(cudaMemset(h->elbo, 0, sizeof(double) * std::max(h->o.num_steps, 1)));

@@ -171,6 +171,16 @@ struct polee_handle {
     float *efflen_adj = nullptr;  // Float32(n * (1/efflen))  likelihood.jl:105
     bool have_efflen = false;
 
+    // ---- optional gene groups for gene_noninformative_prior! (likelihood.jl:114-159); only genes with >= 2 transcripts
+    int64_t n_genes = 0;
+    int64_t gene_n = 0;                 // n the groups were validated against
+    int64_t *gene_ptr = nullptr;        // [n_genes + 1] offsets into gene_tx
+    int32_t *gene_tx = nullptr;         // 0-based transcript ids
+    double *gene_xl_grad = nullptr;     // [n][KP]
+    double *gene_off_partial = nullptr; // [blocks][KP]
+    double *gene_off = nullptr;         // [KP]
+    int gene_KP = 0;
+
     // ---- tree
     polee::TreeHost th;
     polee::TreeDev td;
@@ -257,6 +267,11 @@ int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bo
 int elem_ctas(polee_handle *h, int KP);
 int patch_leaf_records(polee_handle *h);
 int launch_elbo(polee_handle *h, int KP, int K, bool have_lp);
+
+// gene_prior.cu
+int ensure_gene_buffers(polee_handle *h, int KP);
+void release_gene_buffers(polee_handle *h);
+int launch_gene_prior(polee_handle *h, int KP);
 
 // tree_chain.cu (caterpillar trees)
 int launch_chain_fwd(polee_handle *h, int KP, int clamp_x, const float *eff, double *Sp, int want_ladj, double *ladj_tree);

@@ -360,3 +360,81 @@ def test_optimize_ptt_large_sequential(pb, small_synth, oracle):
         assert abs(lp_d - lp_o) <= 2e-4 * abs(lp_o), env
         assert abs(xd.astype(np.float64).sum() - 1.0) < 1e-4
     os.environ.pop("POLEE_CHAIN_MIN_NODES")
+
+
+def _gene_groups(n, seed=3):
+    """synthetic gene -> transcripts map: contiguous genes of 1..6 transcripts, a few transcripts in no gene"""
+    rng = np.random.default_rng(seed)
+    groups, i = {}, 1
+    while i <= n:
+        k = int(rng.integers(1, 7))
+        ids = list(range(i, min(i + k, n + 1)))
+        if rng.random() > 0.1:                       # ~10 % of the transcripts have no gene_id (l-a.jl:480)
+            groups["gene%d" % len(groups)] = ids
+        i += k
+    return groups
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [6, 8])
+def test_gene_noninformative_prior(pb, fx, oracle, K):
+    """gene_noninformative_prior! (likelihood.jl:114-159) inside one step of draws and inside a fit."""
+    genes = _gene_groups(fx.n)
+    rng = np.random.default_rng(20 + K)
+    h = pb.Handle(num_mc_samples=K, noise_mode=1, num_steps=2)
+    h.set_sample(_sample(pb, fx))
+    h.set_tree(fx.parent_idxs, fx.js)
+    mu, om, al = h.get_params()
+    al = (rng.normal(size=fx.n - 1) * 0.1).astype(np.float32)
+    h.set_params(mu, om, al)
+    zs0 = rng.normal(size=(K, fx.n - 1)).astype(np.float32)
+    base = h.lsn_draws(zs0)
+    h.set_gene_groups(genes)
+    d = h.lsn_draws(zs0)
+    acc = {k: np.zeros(fx.n - 1, np.float32) for k in ("mu_grad", "omega_grad", "alpha_grad")}
+    for k in range(K):
+        o = oracle.lsn_draw(fx.m, fx.n, fx.colptr, fx.rowval, fx.nzval, fx.efflens, fx.parent_idxs, fx.js, mu, om, al,
+                            zs0[k], gene_transcripts=genes)
+        o0 = oracle.lsn_draw(fx.m, fx.n, fx.colptr, fx.rowval, fx.nzval, fx.efflens, fx.parent_idxs, fx.js, mu, om, al,
+                             zs0[k])
+        prior = o["x_grad"] - o0["x_grad"]                     # the prior's own contribution
+        assert np.abs(prior).max() > 0
+        got = d["x_grad"][k] - base["x_grad"][k]
+        assert np.abs(got - prior).max() <= 1e-5 * np.abs(prior).max() + 1e-9 * np.abs(o["x_grad"]).max()
+        assert np.abs(d["x_grad"][k] - o["x_grad"]).max() <= 1e-5 * np.abs(o["x_grad"]).max()
+        for key in acc:
+            acc[key] += o[key]
+    for key in acc:
+        ref = acc[key] / np.float32(K)
+        assert np.abs(d[key] - ref).max() <= 1e-5 * np.abs(ref).max(), key
+    h.set_gene_groups(None)                                    # cleared -> back to the plain gradient, bit for bit
+    again = h.lsn_draws(zs0)
+    assert np.array_equal(again["x_grad"], base["x_grad"])
+    # error behaviour: the prior needs the effective-length adjustment; a transcript may sit in one gene only
+    with pytest.raises(pb.PoleeError):
+        h.set_gene_groups([[1, 2], [2, 3]])
+    with pytest.raises(pb.PoleeError):
+        h.set_gene_groups([[0, 1]])
+    h.close()
+    h2 = pb.Handle(num_mc_samples=K, use_efflen_jacobian=False, num_steps=2)
+    h2.set_sample(_sample(pb, fx))
+    h2.set_tree(fx.parent_idxs, fx.js)
+    h2.set_gene_groups(genes)
+    with pytest.raises(pb.PoleeError):
+        h2.run_steps(1)
+    h2.close()
+    # the fit: same noise, prior on -> tracks the oracle, and differs from the fit without the prior
+    steps = 40
+    noise = np.random.default_rng(K).normal(size=(steps, K, fx.n - 1)).astype(np.float32)
+    ora = oracle.fit_lsn_ptt(fx.m, fx.n, fx.colptr, fx.rowval, fx.nzval, fx.efflens, fx.parent_idxs, fx.js,
+                             num_steps=steps, num_mc_samples=K, noise=noise, gene_transcripts=genes)
+    kw = dict(tree_topology=(fx.parent_idxs, fx.js), num_steps=steps, num_mc_samples=K, noise=noise)
+    dev = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), _sample(pb, fx), gene_noninformative=True,
+                                    gene_transcripts=genes, **kw)
+    plain = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), _sample(pb, fx), **kw)
+    for key in ("mu", "omega", "alpha"):
+        assert np.abs(dev[key] - ora[key]).max() <= 2e-4, key
+    assert np.abs(dev["mu"] - plain["mu"]).max() > 1e-3
+    with pytest.warns(UserWarning):                            # l-a.jl:489-492: flag dropped without gene information
+        same = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), _sample(pb, fx), gene_noninformative=True, **kw)
+    assert np.array_equal(same["mu"], plain["mu"])
