@@ -70,6 +70,11 @@ typedef struct polee_opts {
 int polee_opts_default(polee_opts *opts);
 int polee_create(polee_handle **h, const polee_opts *opts);
 int polee_destroy(polee_handle *h);
+/* Device memory a destroyed handle used is kept in a per-process cache and handed to the next handle: `polee prep`
+ * (src/main.jl:590-631) fits one sample after another, and cudaMalloc/cudaFree of the GB-sized layouts would cost
+ * as much as ~100 ADAM steps per sample.  polee_trim_memory returns the cached blocks of `device` (-1: every device)
+ * to the driver; POLEE_NO_CACHE=1 in the environment disables the cache. */
+int polee_trim_memory(int32_t device);
 /* text of the last error on this handle (or, with h == NULL, the last error of a failed create) */
 const char *polee_last_error(const polee_handle *h);
 /* library / device probe: returns POLEE_OK and fills what it can; sm = 100 on B200 */

@@ -26,4 +26,5 @@ from .api import (  # noqa: F401
     optimize_likelihood,
     partition_rows,
     prep_many,
+    trim_memory,
 )

@@ -29,7 +29,7 @@ class PoleeOpts(C.Structure):
 
 # every symbol include/polee_b200.h declares (tests check that the built library exports them all)
 EXPORTS = [
-    "polee_opts_default", "polee_create", "polee_destroy", "polee_last_error", "polee_device_info",
+    "polee_opts_default", "polee_create", "polee_destroy", "polee_trim_memory", "polee_last_error", "polee_device_info",
     "polee_set_matrix_csc", "polee_set_matrix_csc_device", "polee_set_efflens", "polee_set_gene_groups",
     "polee_set_tree",
     "polee_set_tree_sequential", "polee_fit", "polee_fit_optimize_ptt", "polee_init_params", "polee_run_steps",

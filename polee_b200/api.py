@@ -255,6 +255,11 @@ class Handle:
         self.check(self.lib.polee_comm_init(self.h, C.c_int32(nranks), C.c_int32(rank), C.c_char_p(unique_id)))
 
 
+def trim_memory(device=-1):
+    """Return the device memory cached from destroyed handles to the driver (polee_trim_memory)."""
+    L.load_library().polee_trim_memory(C.c_int32(device))
+
+
 def comm_unique_id():
     buf = C.create_string_buffer(128)
     rc = L.load_library().polee_comm_unique_id(buf)

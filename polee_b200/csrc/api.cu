@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include "common.cuh"
+#include <chrono>
 
 using namespace polee;
 
@@ -120,8 +121,8 @@ extern "C" int polee_create(polee_handle **out, const polee_opts *opts) {
     h->K = o.num_mc_samples;
     h->KP = pad_k(h->K);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void **)&h->d_step, sizeof(StepCtl)) != cudaSuccess ||
-        cudaMalloc((void **)&h->d_bad_step, sizeof(int)) != cudaSuccess) {
+        polee::dmalloc((void **)&h->d_step, sizeof(StepCtl)) != cudaSuccess ||
+        polee::dmalloc((void **)&h->d_bad_step, sizeof(int)) != cudaSuccess) {
         delete h;
         return fail(POLEE_ECUDA, "stream / control block allocation failed");
     }
@@ -131,7 +132,7 @@ extern "C" int polee_create(polee_handle **out, const polee_opts *opts) {
 
 static void release_params(polee_handle *h) {
     float *ptrs[] = {h->mu, h->omega, h->alpha, h->m_mu, h->m_omega, h->m_alpha, h->v_mu, h->v_omega, h->v_alpha};
-    for (float *p : ptrs) cudaFree(p);
+    for (float *p : ptrs) polee::dfree(p);
     h->mu = h->omega = h->alpha = h->m_mu = h->m_omega = h->m_alpha = h->v_mu = h->v_omega = h->v_alpha = nullptr;
 }
 
@@ -147,12 +148,19 @@ extern "C" int polee_destroy(polee_handle *h) {
     release_matrix(h);
     release_params(h);
     h->td.release();
-    cudaFree(h->efflen); cudaFree(h->efflen_adj); cudaFree(h->elbo); cudaFree(h->noise);
-    cudaFree(h->d_step); cudaFree(h->d_bad_step);
+    polee::dfree(h->efflen); polee::dfree(h->efflen_adj); polee::dfree(h->elbo); polee::dfree(h->noise);
+    polee::dfree(h->d_step); polee::dfree(h->d_bad_step);
     release_gene_buffers(h);
-    cudaFree(h->gene_ptr); cudaFree(h->gene_tx);
+    polee::dfree(h->gene_ptr); polee::dfree(h->gene_tx);
+    if (h->copy_done) cudaEventDestroy(h->copy_done);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+    return POLEE_OK;
+}
+
+extern "C" int polee_trim_memory(int32_t device) {
+    polee::dtrim(device);
     return POLEE_OK;
 }
 
@@ -176,7 +184,7 @@ extern "C" int polee_set_matrix_csc_device(polee_handle *h, int64_t m, int64_t n
     if (h->have_tree && h->td.n != n) return h->fail(POLEE_EINVAL, "n differs from the tree already set");
     drop_graph(h);
     release_work_buffers(h);
-    return setup_matrix_from_device_csc(h, m, n, d_colptr, d_rowval, d_nzval, d_ks, nullptr);
+    return setup_matrix_from_device_csc(h, m, n, d_colptr, d_rowval, d_nzval, d_ks, nullptr, nullptr);
 }
 
 extern "C" int polee_set_matrix_csc(polee_handle *h, int64_t m, int64_t n, const uint32_t *colptr,
@@ -193,7 +201,7 @@ extern "C" int polee_set_matrix_csc(polee_handle *h, int64_t m, int64_t n, const
     float *d_nzval = nullptr;
     int64_t *d_ks = nullptr;
     int rc = POLEE_OK;
-    auto cleanup = [&]() { cudaFree(d_colptr); cudaFree(d_rowval); cudaFree(d_nzval); cudaFree(d_ks); };
+    auto cleanup = [&]() { polee::dfree(d_colptr); polee::dfree(d_rowval); polee::dfree(d_nzval); polee::dfree(d_ks); };
 #define CKC(expr)                                                                                     \
     do {                                                                                              \
         cudaError_t _e = (expr);                                                                      \
@@ -202,18 +210,24 @@ extern "C" int polee_set_matrix_csc(polee_handle *h, int64_t m, int64_t n, const
             return h->fail(POLEE_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
         }                                                                                             \
     } while (0)
-    CKC(cudaMalloc((void **)&d_colptr, sizeof(uint32_t) * (n + 1)));
-    CKC(cudaMalloc((void **)&d_rowval, sizeof(uint32_t) * std::max<int64_t>(nnz, 1)));
-    CKC(cudaMalloc((void **)&d_nzval, sizeof(float) * std::max<int64_t>(nnz, 1)));
+    CKC(polee::dmalloc((void **)&d_colptr, sizeof(uint32_t) * (n + 1)));
+    CKC(polee::dmalloc((void **)&d_rowval, sizeof(uint32_t) * std::max<int64_t>(nnz, 1)));
+    CKC(polee::dmalloc((void **)&d_nzval, sizeof(float) * std::max<int64_t>(nnz, 1)));
+    // the row ids go first on the compute stream (the row-length pass and both sorts need nothing else); the values
+    // and counts follow on a side stream so that their transfer overlaps the first half of the layout build
+    if (!h->copy_stream) CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->copy_done) CKC(cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming));
     CKC(cudaMemcpyAsync(d_colptr, colptr, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, h->stream));
     CKC(cudaMemcpyAsync(d_rowval, rowval, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice, h->stream));
-    CKC(cudaMemcpyAsync(d_nzval, nzval, sizeof(float) * nnz, cudaMemcpyHostToDevice, h->stream));
+    CKC(cudaMemcpyAsync(d_nzval, nzval, sizeof(float) * nnz, cudaMemcpyHostToDevice, h->copy_stream));
     if (ks) {
-        CKC(cudaMalloc((void **)&d_ks, sizeof(int64_t) * m));
-        CKC(cudaMemcpyAsync(d_ks, ks, sizeof(int64_t) * m, cudaMemcpyHostToDevice, h->stream));
+        CKC(polee::dmalloc((void **)&d_ks, sizeof(int64_t) * m));
+        CKC(cudaMemcpyAsync(d_ks, ks, sizeof(int64_t) * m, cudaMemcpyHostToDevice, h->copy_stream));
     }
+    CKC(cudaEventRecord(h->copy_done, h->copy_stream));
 #undef CKC
-    rc = setup_matrix_from_device_csc(h, m, n, d_colptr, d_rowval, d_nzval, d_ks, colptr);
+    rc = setup_matrix_from_device_csc(h, m, n, d_colptr, d_rowval, d_nzval, d_ks, colptr, h->copy_done);
+    cudaStreamSynchronize(h->copy_stream);
     cleanup();
     return rc;
 }
@@ -223,12 +237,12 @@ extern "C" int polee_set_efflens(polee_handle *h, const float *efflens) {
     if (!efflens) return h->fail(POLEE_EINVAL, "set_efflens: null pointer");
     int64_t n = h->have_matrix ? h->n : (h->have_tree ? h->td.n : 0);
     if (n < 1) return h->fail(POLEE_EINVAL, "set_efflens: set the matrix or the tree first (n unknown)");
-    cudaFree(h->efflen); cudaFree(h->efflen_adj);
+    polee::dfree(h->efflen); polee::dfree(h->efflen_adj);
     h->efflen = h->efflen_adj = nullptr;
     std::vector<float> adj(n);
     for (int64_t j = 0; j < n; ++j) adj[j] = (float)n * (1.0f / efflens[j]);  // likelihood.jl:105, Float32
-    CK(cudaMalloc((void **)&h->efflen, sizeof(float) * n));
-    CK(cudaMalloc((void **)&h->efflen_adj, sizeof(float) * n));
+    CK(polee::dmalloc((void **)&h->efflen, sizeof(float) * n));
+    CK(polee::dmalloc((void **)&h->efflen_adj, sizeof(float) * n));
     CK(cudaMemcpy(h->efflen, efflens, sizeof(float) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->efflen_adj, adj.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
     h->have_efflen = true;
@@ -241,7 +255,7 @@ extern "C" int polee_set_gene_groups(polee_handle *h, int64_t num_genes, const i
     CHECK_H(h);
     drop_graph(h);
     release_gene_buffers(h);
-    cudaFree(h->gene_ptr); cudaFree(h->gene_tx);
+    polee::dfree(h->gene_ptr); polee::dfree(h->gene_tx);
     h->gene_ptr = nullptr; h->gene_tx = nullptr; h->n_genes = 0; h->gene_n = 0;
     if (num_genes == 0) return POLEE_OK;
     if (num_genes < 0 || !gene_ptr || !transcripts) return h->fail(POLEE_EINVAL, "set_gene_groups: null pointer");
@@ -267,8 +281,8 @@ extern "C" int polee_set_gene_groups(polee_handle *h, int64_t num_genes, const i
     h->gene_n = n;
     h->n_genes = (int64_t)ptr.size() - 1;
     if (h->n_genes == 0) return POLEE_OK;  // nothing but single-transcript genes: the prior is identically zero
-    CK(cudaMalloc((void **)&h->gene_ptr, sizeof(int64_t) * ptr.size()));
-    CK(cudaMalloc((void **)&h->gene_tx, sizeof(int32_t) * tx.size()));
+    CK(polee::dmalloc((void **)&h->gene_ptr, sizeof(int64_t) * ptr.size()));
+    CK(polee::dmalloc((void **)&h->gene_tx, sizeof(int32_t) * tx.size()));
     CK(cudaMemcpy(h->gene_ptr, ptr.data(), sizeof(int64_t) * ptr.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->gene_tx, tx.data(), sizeof(int32_t) * tx.size(), cudaMemcpyHostToDevice));
     return POLEE_OK;
@@ -279,22 +293,39 @@ static int alloc_params(polee_handle *h) {
     const int64_t nm1 = std::max<int64_t>(h->td.n - 1, 1);
     float **ptrs[] = {&h->mu, &h->omega, &h->alpha, &h->m_mu, &h->m_omega, &h->m_alpha, &h->v_mu, &h->v_omega, &h->v_alpha};
     for (float **p : ptrs) {
-        CK(cudaMalloc((void **)p, sizeof(float) * nm1));
+        CK(polee::dmalloc((void **)p, sizeof(float) * nm1));
         CK(cudaMemset(*p, 0, sizeof(float) * nm1));
     }
     return POLEE_OK;
 }
 
-static int finish_tree(polee_handle *h, const std::string &err) {
+// POLEE_SETUP_TIMING=1: where polee_set_tree spends its time
+struct HostPhaseTimer {
+    bool on = getenv("POLEE_SETUP_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[polee tree ] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+static int finish_tree(polee_handle *h, const std::string &err, HostPhaseTimer &pt) {
     if (!err.empty()) return h->fail(POLEE_EBADTREE, err);
+    pt.mark("validate + schedule (host)");
     std::string e2 = upload_tree(h->th, h->td);
     if (!e2.empty()) return h->fail(POLEE_ECUDA, e2);
+    pt.mark("upload");
     h->th.initial_mu(h->mu0);
+    pt.mark("initial mu (host)");
     h->have_tree = true;
     int rc = alloc_params(h);
     if (rc) return rc;
     if ((rc = patch_leaf_records(h))) return rc;
-    return polee_init_params(h);
+    rc = polee_init_params(h);
+    pt.mark("params alloc + init");
+    return rc;
 }
 
 extern "C" int polee_set_tree(polee_handle *h, int64_t n, const int32_t *node_parent_idxs, const int32_t *node_js) {
@@ -304,7 +335,8 @@ extern "C" int polee_set_tree(polee_handle *h, int64_t n, const int32_t *node_pa
     drop_graph(h);
     release_work_buffers(h);
     h->have_tree = false;
-    return finish_tree(h, h->th.build_from_parents(n, node_parent_idxs, node_js, TREE_BIN_NODES));
+    HostPhaseTimer pt;
+    return finish_tree(h, h->th.build_from_parents(n, node_parent_idxs, node_js, TREE_BIN_NODES), pt);
 }
 
 extern "C" int polee_set_tree_sequential(polee_handle *h, int64_t n) {
@@ -380,12 +412,12 @@ extern "C" int polee_set_noise(polee_handle *h, const float *noise, int64_t num_
     if (!h->have_tree) return h->fail(POLEE_EINVAL, "set_noise: set the tree first");
     drop_graph(h);
     h->reparam_ready = false;
-    cudaFree(h->noise);
+    polee::dfree(h->noise);
     h->noise = nullptr;
     h->noise_steps = 0;
     if (!noise || num_steps <= 0) return POLEE_OK;
     const size_t count = (size_t)num_steps * h->K * (size_t)std::max<int64_t>(h->td.n - 1, 1);
-    CK(cudaMalloc((void **)&h->noise, sizeof(float) * count));
+    CK(polee::dmalloc((void **)&h->noise, sizeof(float) * count));
     CK(cudaMemcpy(h->noise, noise, sizeof(float) * count, cudaMemcpyHostToDevice));
     h->noise_steps = num_steps;
     return POLEE_OK;
@@ -415,7 +447,7 @@ static int ready_for_steps(polee_handle *h) {
     if (rc) return rc;
     if ((rc = ensure_gene_buffers(h, h->KP))) return rc;
     if (!h->elbo) {
-        CK(cudaMalloc((void **)&h->elbo, sizeof(double) * std::max(h->o.num_steps, 1)));
+        CK(polee::dmalloc((void **)&h->elbo, sizeof(double) * std::max(h->o.num_steps, 1)));
         CK(cudaMemset(h->elbo, 0, sizeof(double) * std::max(h->o.num_steps, 1)));
     }
     return POLEE_OK;
@@ -697,7 +729,7 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
         rc = ensure_work_buffers(h, h->KP);
         if (!rc) rc = ensure_gene_buffers(h, h->KP);
         if (!rc && !h->elbo) {
-            CK(cudaMalloc((void **)&h->elbo, sizeof(double) * std::max(h->o.num_steps, 1)));
+            CK(polee::dmalloc((void **)&h->elbo, sizeof(double) * std::max(h->o.num_steps, 1)));
             CK(cudaMemset(h->elbo, 0, sizeof(double) * std::max(h->o.num_steps, 1)));
         }
     }
@@ -706,8 +738,8 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
     const int64_t n = h->n, nm1 = n - 1;
     float *d_noise = nullptr;
     double *d_xg = nullptr;
-    CK(cudaMalloc((void **)&d_noise, sizeof(float) * (size_t)K * std::max<int64_t>(nm1, 1)));
-    CK(cudaMalloc((void **)&d_xg, sizeof(double) * (size_t)n * KP));
+    CK(polee::dmalloc((void **)&d_noise, sizeof(float) * (size_t)K * std::max<int64_t>(nm1, 1)));
+    CK(polee::dmalloc((void **)&d_xg, sizeof(double) * (size_t)n * KP));
     CK(cudaMemcpy(d_noise, zs0, sizeof(float) * (size_t)K * nm1, cudaMemcpyHostToDevice));
     StepCtl saved, one{1, 1};
     CK(cudaStreamSynchronize(h->stream));
@@ -733,8 +765,8 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
     }
     cudaMemcpy(h->d_step, &saved, sizeof(saved), cudaMemcpyHostToDevice);
     cudaMemset(h->d_bad_step, 0, sizeof(int));
-    cudaFree(d_noise);
-    cudaFree(d_xg);
+    polee::dfree(d_noise);
+    polee::dfree(d_xg);
     return rc;
 }
 

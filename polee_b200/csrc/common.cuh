@@ -145,6 +145,8 @@ struct polee_handle {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of nzval / ks overlapping the layout build
+    cudaEvent_t copy_done = nullptr;
     int K = 0, KP = 0;  // draws, padded draws (power of two)
 
     // ---- matrix
@@ -241,10 +243,16 @@ namespace polee {
 
 int pad_k(int K);
 
+// mem_cache.cu: caching device allocator (cudaMalloc / cudaFree semantics, freed blocks are kept for the next sample)
+cudaError_t dmalloc(void **p, size_t bytes);
+cudaError_t dfree(void *p);
+void dtrim(int device);  // -1 = every device
+size_t dcached_bytes(int device);
+
 // matrix_setup.cu
 int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const uint32_t *d_colptr,
                                  const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
-                                 const uint32_t *h_colptr_or_null);
+                                 const uint32_t *h_colptr_or_null, cudaEvent_t vals_ready_or_null);
 void release_matrix(polee_handle *h);
 
 // sparse_kernels.cu

@@ -89,9 +89,9 @@ __global__ void __launch_bounds__(GP_THREADS)
 #define CK(expr) POLEE_CUDA_CHECK(h, expr)
 
 void release_gene_buffers(polee_handle *h) {
-    cudaFree(h->gene_xl_grad);
-    cudaFree(h->gene_off_partial);
-    cudaFree(h->gene_off);
+    polee::dfree(h->gene_xl_grad);
+    polee::dfree(h->gene_off_partial);
+    polee::dfree(h->gene_off);
     h->gene_xl_grad = h->gene_off_partial = h->gene_off = nullptr;
     h->gene_KP = 0;
 }
@@ -100,10 +100,10 @@ int ensure_gene_buffers(polee_handle *h, int KP) {
     if (h->n_genes == 0 || h->gene_KP == KP) return POLEE_OK;
     release_gene_buffers(h);
     const int blocks = (int)((h->n_genes * KP + GP_THREADS - 1) / GP_THREADS);
-    CK(cudaMalloc((void **)&h->gene_xl_grad, sizeof(double) * (size_t)h->n * KP));
+    CK(polee::dmalloc((void **)&h->gene_xl_grad, sizeof(double) * (size_t)h->n * KP));
     CK(cudaMemset(h->gene_xl_grad, 0, sizeof(double) * (size_t)h->n * KP));  // transcripts outside multi-transcript genes: 0 (:118)
-    CK(cudaMalloc((void **)&h->gene_off_partial, sizeof(double) * (size_t)blocks * KP));
-    CK(cudaMalloc((void **)&h->gene_off, sizeof(double) * KP));
+    CK(polee::dmalloc((void **)&h->gene_off_partial, sizeof(double) * (size_t)blocks * KP));
+    CK(polee::dmalloc((void **)&h->gene_off, sizeof(double) * KP));
     h->gene_KP = KP;
     return POLEE_OK;
 }

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(HSB_THREADS)
 template <typename T>
 cudaError_t up_vec(const std::vector<T> &v, T **d) {
     *d = nullptr;
-    cudaError_t e = cudaMalloc((void **)d, std::max<size_t>(v.size(), 1) * sizeof(T));
+    cudaError_t e = polee::dmalloc((void **)d, std::max<size_t>(v.size(), 1) * sizeof(T));
     if (e == cudaSuccess && !v.empty()) e = cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
     return e;
 }
@@ -165,11 +165,11 @@ cudaError_t up_vec(const std::vector<T> &v, T **d) {
 struct DevBuf {
     std::vector<void *> ptrs;
     ~DevBuf() {
-        for (void *p : ptrs) cudaFree(p);
+        for (void *p : ptrs) polee::dfree(p);
     }
     template <typename T>
     cudaError_t alloc(T **p, size_t count) {
-        cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+        cudaError_t e = polee::dmalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
@@ -195,10 +195,10 @@ const char *polee_hsb_last_error(void) {
 int polee_hsb_plan_destroy(polee_hsb_plan *p) {
     if (!p) return POLEE_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->nodes);
-    cudaFree(p->desc_order);
+    polee::dfree(p->nodes);
+    polee::dfree(p->desc_order);
     for (int s = 0; s < 2; ++s) {
-        cudaFree(p->bin_lvl_ptr[s]); cudaFree(p->lvl_off[s]); cudaFree(p->sch_node[s]); cudaFree(p->bin_tree[s]);
+        polee::dfree(p->bin_lvl_ptr[s]); polee::dfree(p->lvl_off[s]); polee::dfree(p->sch_node[s]); polee::dfree(p->bin_tree[s]);
     }
     delete p;
     return POLEE_OK;

@@ -18,6 +18,9 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace polee {
 
@@ -125,11 +128,11 @@ int bits_for(uint64_t maxval) {
 struct Scratch {
     std::vector<void *> ptrs;
     ~Scratch() {
-        for (void *p : ptrs) cudaFree(p);
+        for (void *p : ptrs) polee::dfree(p);
     }
     template <typename T>
     cudaError_t alloc(T **p, size_t count) {
-        cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+        cudaError_t e = polee::dmalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
@@ -138,8 +141,8 @@ struct Scratch {
 }  // namespace
 
 void release_matrix(polee_handle *h) {
-    cudaFree(h->sell_idx); cudaFree(h->sell_val); cudaFree(h->row_tiles); cudaFree(h->row_perm);
-    cudaFree(h->row_weight); cudaFree(h->csc_row); cudaFree(h->csc_val); cudaFree(h->segs); cudaFree(h->multi);
+    polee::dfree(h->sell_idx); polee::dfree(h->sell_val); polee::dfree(h->row_tiles); polee::dfree(h->row_perm);
+    polee::dfree(h->row_weight); polee::dfree(h->csc_row); polee::dfree(h->csc_val); polee::dfree(h->segs); polee::dfree(h->multi);
     h->sell_idx = nullptr; h->sell_val = nullptr; h->row_tiles = nullptr; h->row_perm = nullptr;
     h->row_weight = nullptr; h->csc_row = nullptr; h->csc_val = nullptr; h->segs = nullptr; h->multi = nullptr;
     h->have_matrix = false;
@@ -147,13 +150,30 @@ void release_matrix(polee_handle *h) {
 
 #define CK(expr) POLEE_CUDA_CHECK(h, expr)
 
+// POLEE_SETUP_TIMING=1 prints where the layout build spends its time (synchronises at every mark)
+struct PhaseTimer {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer(cudaStream_t s) : on(getenv("POLEE_SETUP_TIMING") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[polee setup] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const uint32_t *d_colptr,
                                  const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
-                                 const uint32_t *h_colptr_or_null) {
+                                 const uint32_t *h_colptr_or_null, cudaEvent_t vals_ready_or_null) {
     release_matrix(h);
     if (m < 1 || n < 1) return h->fail(POLEE_EINVAL, "set_matrix: m and n must be >= 1");
     if (m >= (int64_t)0xFFFFFF00u) return h->fail(POLEE_EINVAL, "set_matrix: m exceeds UInt32 row ids");
     cudaStream_t st = h->stream;
+    PhaseTimer pt(st);
+    pt.mark("inputs resident (H2D)");
     std::vector<uint32_t> colptr(n + 1);
     if (h_colptr_or_null)
         std::copy(h_colptr_or_null, h_colptr_or_null + n + 1, colptr.begin());
@@ -191,6 +211,7 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
     CK(cudaMemcpyAsync(&lmax, d_lmax, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (bad) return h->fail(POLEE_EINVAL, "set_matrix: rowval out of range 1..m");
+    pt.mark("row lengths + max");
 
     int *d_hist;
     CK(sc.alloc(&d_hist, (size_t)lmax + 1));
@@ -244,6 +265,7 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
     CK(cudaMemcpyAsync(d_cls_stride, cls_stride.data(), 4 * (lmax + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_cls_slab, cls_slab_off.data(), 8 * (lmax + 1), cudaMemcpyHostToDevice, st));
 
+    pt.mark("length classes (host)");
     // ---- stable sort of rows by descending length -> permutation
     const int64_t big = std::max<int64_t>(m, nnz);
     CK(sc.alloc(&keys_a, big)); CK(sc.alloc(&keys_b, big)); CK(sc.alloc(&vals_a, big)); CK(sc.alloc(&vals_b, big));
@@ -254,12 +276,13 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
     CK(sc.alloc((char **)&d_sort, sort_bytes));
     CK(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, keys_a, keys_b, vals_a, vals_b, (int)m, 0, bits_for(lmax), st));
 
-    CK(cudaMalloc((void **)&h->row_perm, sizeof(uint32_t) * m));
+    CK(polee::dmalloc((void **)&h->row_perm, sizeof(uint32_t) * m));
     uint32_t *len_perm, *row_start;
     CK(sc.alloc(&len_perm, rows_pad)); CK(sc.alloc(&row_start, rows_pad));
     CK(cudaMemsetAsync(len_perm, 0, sizeof(uint32_t) * std::max<uint64_t>(rows_pad, 1), st));
     k_assign_perm<<<grid_for(m), TPB, 0, st>>>(vals_b, row_len, m, d_cls_pad, d_cls_unpad, h->row_perm, len_perm);
 
+    pt.mark("row sort + permutation");
     // ---- entries: sort by permuted row (stable from CSC order => ascending column inside a row)
     uint32_t *col_of;
     CK(sc.alloc(&col_of, nnz));
@@ -269,41 +292,48 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
         CK(cudaMemcpyAsync(d_colptr_own, colptr.data(), 4 * (n + 1), cudaMemcpyHostToDevice, st));
         d_colptr = d_colptr_own;
     }
-    CK(cudaMalloc((void **)&h->sell_idx, sizeof(uint32_t) * std::max<uint64_t>(slab, 1)));
-    CK(cudaMalloc((void **)&h->sell_val, sizeof(float) * std::max<uint64_t>(slab, 1)));
+    CK(polee::dmalloc((void **)&h->sell_idx, sizeof(uint32_t) * std::max<uint64_t>(slab, 1)));
+    CK(polee::dmalloc((void **)&h->sell_val, sizeof(float) * std::max<uint64_t>(slab, 1)));
     CK(cudaMemsetAsync(h->sell_idx, 0, sizeof(uint32_t) * std::max<uint64_t>(slab, 1), st));
     CK(cudaMemsetAsync(h->sell_val, 0, sizeof(float) * std::max<uint64_t>(slab, 1), st));
     // +16 elements: K2's bulk copies round their byte count up to 16
-    CK(cudaMalloc((void **)&h->csc_row, sizeof(uint32_t) * (nnz + 16)));
-    CK(cudaMalloc((void **)&h->csc_val, sizeof(float) * (nnz + 16)));
+    CK(polee::dmalloc((void **)&h->csc_row, sizeof(uint32_t) * (nnz + 16)));
+    CK(polee::dmalloc((void **)&h->csc_val, sizeof(float) * (nnz + 16)));
     CK(cudaMemsetAsync(h->csc_row, 0, sizeof(uint32_t) * (nnz + 16), st));
     CK(cudaMemsetAsync(h->csc_val, 0, sizeof(float) * (nnz + 16), st));
+    pt.mark("layout alloc + clear");
     if (nnz > 0) {
         k_entry_keys<<<grid_for(nnz), TPB, 0, st>>>(d_colptr, n, d_rowval, nnz, h->row_perm, col_of, keys_a, vals_a);
         CK(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, keys_a, keys_b, vals_a, vals_b, (int)nnz, 0,
                                            bits_for(rows_pad), st));
-        // keys_b = sorted permuted rows, vals_b = entry ids
+        pt.mark("entry sort by row");
+        // keys_b = sorted permuted rows, vals_b = entry ids; from here on nzval (and ks) are read
+        if (vals_ready_or_null) CK(cudaStreamWaitEvent(st, vals_ready_or_null, 0));
         k_row_starts<<<grid_for(nnz), TPB, 0, st>>>(keys_b, nnz, row_start);
         // reuse keys_a / vals_a for the column sort
         k_fill_sell<<<grid_for(nnz), TPB, 0, st>>>(keys_b, vals_b, nnz, row_start, len_perm, d_cls_pad, d_cls_slab,
                                                     d_cls_stride, col_of, d_nzval, h->sell_idx, h->sell_val, keys_a,
                                                     vals_a);
+        pt.mark("SELL fill");
         // stable sort by column of the (row', col)-ordered list -> (col, row') order
         uint32_t *keys_c, *vals_c;
         CK(sc.alloc(&keys_c, nnz)); CK(sc.alloc(&vals_c, nnz));
         CK(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, keys_a, keys_c, vals_a, vals_c, (int)nnz, 0,
                                            bits_for((uint64_t)n), st));
+        pt.mark("entry sort by column");
         k_fill_csc<<<grid_for(nnz), TPB, 0, st>>>(vals_c, nnz, keys_b, vals_b, d_nzval, h->csc_row, h->csc_val);
+        pt.mark("CSC fill");
     }
     if (d_ks) {
-        CK(cudaMalloc((void **)&h->row_weight, sizeof(float) * std::max<uint64_t>(rows_pad, 1)));
+        if (vals_ready_or_null) CK(cudaStreamWaitEvent(st, vals_ready_or_null, 0));
+        CK(polee::dmalloc((void **)&h->row_weight, sizeof(float) * std::max<uint64_t>(rows_pad, 1)));
         CK(cudaMemsetAsync(h->row_weight, 0, sizeof(float) * std::max<uint64_t>(rows_pad, 1), st));
         k_row_weights<<<grid_for(m), TPB, 0, st>>>(d_ks, m, h->row_perm, h->row_weight);
     }
 
     // ---- K1 tiles, K2 segments
     h->n_row_tiles = (int)tiles.size();
-    CK(cudaMalloc((void **)&h->row_tiles, sizeof(RowTile) * std::max<size_t>(tiles.size(), 1)));
+    CK(polee::dmalloc((void **)&h->row_tiles, sizeof(RowTile) * std::max<size_t>(tiles.size(), 1)));
     if (!tiles.empty())
         CK(cudaMemcpyAsync(h->row_tiles, tiles.data(), sizeof(RowTile) * tiles.size(), cudaMemcpyHostToDevice, st));
 
@@ -347,16 +377,18 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
         }
         i = j;
     }
+    pt.mark("segments (host)");
     h->n_segs = (int)segs.size();
     h->n_multi = (int)multi.size();
     h->n_slots = (int)slots;
-    CK(cudaMalloc((void **)&h->segs, sizeof(ColSeg) * std::max<size_t>(segs.size(), 1)));
+    CK(polee::dmalloc((void **)&h->segs, sizeof(ColSeg) * std::max<size_t>(segs.size(), 1)));
     CK(cudaMemcpyAsync(h->segs, segs.data(), sizeof(ColSeg) * segs.size(), cudaMemcpyHostToDevice, st));
-    CK(cudaMalloc((void **)&h->multi, sizeof(MultiCol) * std::max<size_t>(multi.size(), 1)));
+    CK(polee::dmalloc((void **)&h->multi, sizeof(MultiCol) * std::max<size_t>(multi.size(), 1)));
     if (!multi.empty())
         CK(cudaMemcpyAsync(h->multi, multi.data(), sizeof(MultiCol) * multi.size(), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    pt.mark("descriptor upload");
     h->have_matrix = true;
     return POLEE_OK;
 }

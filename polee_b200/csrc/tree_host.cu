@@ -253,22 +253,22 @@ void TreeHost::initial_mu(std::vector<float> &mu) const {
 }
 
 void TreeDev::release() {
-    cudaFree(nodes);
+    polee::dfree(nodes);
     for (TreeSchedDev *s : {&top, &bottom}) {
-        cudaFree(s->bin_lvl_ptr);
-        cudaFree(s->lvl_off);
-        cudaFree(s->sch_node);
+        polee::dfree(s->bin_lvl_ptr);
+        polee::dfree(s->lvl_off);
+        polee::dfree(s->sch_node);
         *s = TreeSchedDev();
     }
-    cudaFree(chain_leaf);
+    polee::dfree(chain_leaf);
     chain_leaf = nullptr;
     caterpillar = false;
     for (SSchedDev *s : {&s_top, &s_bottom}) {
-        cudaFree(s->bin_off);
-        cudaFree(s->bin_lvl_ptr);
-        cudaFree(s->lvl_off);
-        cudaFree(s->recs);
-        cudaFree(s->bin_desc);
+        polee::dfree(s->bin_off);
+        polee::dfree(s->bin_lvl_ptr);
+        polee::dfree(s->lvl_off);
+        polee::dfree(s->recs);
+        polee::dfree(s->bin_desc);
         *s = SSchedDev();
     }
     nodes = nullptr;
@@ -280,7 +280,7 @@ void TreeDev::release() {
 static cudaError_t up(const std::vector<int32_t> &v, int32_t **d) {
     *d = nullptr;
     size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(int32_t);
-    cudaError_t e = cudaMalloc((void **)d, bytes);
+    cudaError_t e = polee::dmalloc((void **)d, bytes);
     if (e != cudaSuccess) return e;
     if (!v.empty()) e = cudaMemcpy(*d, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
     return e;
@@ -290,7 +290,7 @@ std::string upload_tree(const TreeHost &th, TreeDev &td) {
     td.release();
     td.n = th.n;
     td.N = th.N;
-    cudaError_t e = cudaMalloc((void **)&td.nodes, sizeof(TreeNode) * th.N);
+    cudaError_t e = polee::dmalloc((void **)&td.nodes, sizeof(TreeNode) * th.N);
     if (e == cudaSuccess) e = cudaMemcpy(td.nodes, th.nodes.data(), sizeof(TreeNode) * th.N, cudaMemcpyHostToDevice);
     const TreeSchedHost *hs[2] = {&th.top, &th.bottom};
     TreeSchedDev *ds[2] = {&td.top, &td.bottom};
@@ -312,7 +312,7 @@ std::string upload_tree(const TreeHost &th, TreeDev &td) {
         if (e == cudaSuccess) e = up(hss[s]->lvl_off, &dss[s]->lvl_off);
         if (e == cudaSuccess) {
             size_t bytes = std::max<size_t>(hss[s]->recs.size(), 1) * sizeof(SNode);
-            e = cudaMalloc((void **)&dss[s]->recs, bytes);
+            e = polee::dmalloc((void **)&dss[s]->recs, bytes);
             if (e == cudaSuccess && !hss[s]->recs.empty())
                 e = cudaMemcpy(dss[s]->recs, hss[s]->recs.data(), hss[s]->recs.size() * sizeof(SNode), cudaMemcpyHostToDevice);
         }

@@ -611,7 +611,7 @@ __global__ void k3_elbo(int K, int KP, const double *__restrict__ lp, const doub
 void release_work_buffers(polee_handle *h) {
     void *ptrs[] = {h->zs0, h->zs, h->ys, h->ygrad, h->us, h->G, h->root_us, h->root_G, h->x, h->xd, h->w, h->g, h->seg_partial, h->S_partial,
                     h->S, h->lp_partial, h->ladj_partial, h->grad_out};
-    for (void *p : ptrs) cudaFree(p);
+    for (void *p : ptrs) polee::dfree(p);
     h->zs0 = h->zs = nullptr; h->ys = h->ygrad = h->us = nullptr; h->G = nullptr; h->x = h->w = nullptr; h->xd = nullptr; h->root_us = nullptr; h->root_G = nullptr;
     h->g = h->seg_partial = h->S_partial = h->S = h->lp_partial = h->ladj_partial = nullptr;
     h->grad_out = nullptr;
@@ -629,29 +629,29 @@ int ensure_work_buffers(polee_handle *h, int KP) {
     const int64_t n = h->n, nm1 = std::max<int64_t>(n - 1, 1), N = 2 * n - 1;
     h->tree_grid = std::max(1, std::min(h->td.s_bottom.nbins * std::max(1, KP / std::min(KP, 4)), 2 * h->num_sms));
     h->n_tree_ctas = 1 + std::max(h->td.bottom.nbins, h->tree_grid);
-    CK(cudaMalloc((void **)&h->zs0, sizeof(float) * nm1 * KP));
-    CK(cudaMalloc((void **)&h->zs, sizeof(float) * nm1 * KP));
-    CK(cudaMalloc((void **)&h->ys, sizeof(double) * nm1 * KP));
-    CK(cudaMalloc((void **)&h->ygrad, sizeof(double) * nm1 * KP));
-    CK(cudaMalloc((void **)&h->us, sizeof(double) * N * KP));
-    CK(cudaMalloc((void **)&h->G, sizeof(float2) * N * KP));
-    CK(cudaMalloc((void **)&h->root_us, sizeof(double) * std::max(h->td.n_slots, 1) * KP));
-    CK(cudaMalloc((void **)&h->root_G, sizeof(float2) * std::max(h->td.n_slots, 1) * KP));
-    CK(cudaMalloc((void **)&h->x, sizeof(float) * n * KP));
-    CK(cudaMalloc((void **)&h->xd, sizeof(double) * n * KP));
-    CK(cudaMalloc((void **)&h->g, sizeof(double) * (n + 1) * KP));
-    CK(cudaMalloc((void **)&h->S_partial, sizeof(double) * h->n_tree_ctas * KP));
-    CK(cudaMalloc((void **)&h->S, sizeof(double) * KP));
-    CK(cudaMalloc((void **)&h->ladj_partial, sizeof(double) * (2 * (size_t)elem_ctas(h, KP) + h->n_tree_ctas) * KP));
-    CK(cudaMalloc((void **)&h->grad_out, sizeof(float) * 3 * nm1));
+    CK(polee::dmalloc((void **)&h->zs0, sizeof(float) * nm1 * KP));
+    CK(polee::dmalloc((void **)&h->zs, sizeof(float) * nm1 * KP));
+    CK(polee::dmalloc((void **)&h->ys, sizeof(double) * nm1 * KP));
+    CK(polee::dmalloc((void **)&h->ygrad, sizeof(double) * nm1 * KP));
+    CK(polee::dmalloc((void **)&h->us, sizeof(double) * N * KP));
+    CK(polee::dmalloc((void **)&h->G, sizeof(float2) * N * KP));
+    CK(polee::dmalloc((void **)&h->root_us, sizeof(double) * std::max(h->td.n_slots, 1) * KP));
+    CK(polee::dmalloc((void **)&h->root_G, sizeof(float2) * std::max(h->td.n_slots, 1) * KP));
+    CK(polee::dmalloc((void **)&h->x, sizeof(float) * n * KP));
+    CK(polee::dmalloc((void **)&h->xd, sizeof(double) * n * KP));
+    CK(polee::dmalloc((void **)&h->g, sizeof(double) * (n + 1) * KP));
+    CK(polee::dmalloc((void **)&h->S_partial, sizeof(double) * h->n_tree_ctas * KP));
+    CK(polee::dmalloc((void **)&h->S, sizeof(double) * KP));
+    CK(polee::dmalloc((void **)&h->ladj_partial, sizeof(double) * (2 * (size_t)elem_ctas(h, KP) + h->n_tree_ctas) * KP));
+    CK(polee::dmalloc((void **)&h->grad_out, sizeof(float) * 3 * nm1));
     CK(cudaMemset(h->S_partial, 0, sizeof(double) * h->n_tree_ctas * KP));
     CK(cudaMemset(h->ladj_partial, 0, sizeof(double) * (2 * (size_t)elem_ctas(h, KP) + h->n_tree_ctas) * KP));
     CK(cudaMemset(h->g, 0, sizeof(double) * (n + 1) * KP));
     if (h->have_matrix) {
-        CK(cudaMalloc((void **)&h->w, sizeof(float) * std::max<int64_t>(h->m_pad, 1) * KP));
+        CK(polee::dmalloc((void **)&h->w, sizeof(float) * std::max<int64_t>(h->m_pad, 1) * KP));
         CK(cudaMemset(h->w, 0, sizeof(float) * std::max<int64_t>(h->m_pad, 1) * KP));
-        CK(cudaMalloc((void **)&h->seg_partial, sizeof(double) * std::max(h->n_slots, 1) * KP));
-        CK(cudaMalloc((void **)&h->lp_partial, sizeof(double) * std::max(h->n_row_tiles, 1) * KP));
+        CK(polee::dmalloc((void **)&h->seg_partial, sizeof(double) * std::max(h->n_slots, 1) * KP));
+        CK(polee::dmalloc((void **)&h->lp_partial, sizeof(double) * std::max(h->n_row_tiles, 1) * KP));
     }
     h->work_KP = KP;
     return POLEE_OK;
