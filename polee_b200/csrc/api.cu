@@ -453,6 +453,19 @@ static int ready_for_steps(polee_handle *h) {
     return POLEE_OK;
 }
 
+// log-likelihood gradient of the KP draws in h->x: the fused single pass, or K1 + K2 on the split layout
+static int launch_likelihood(polee_handle *h, int KP, bool want_lp) {
+    int rc;
+    if (h->fused) {
+        if ((rc = launch_fused(h, h->x, h->g, want_lp, h->lp_partial, nullptr, KP))) return rc;
+    } else {
+        if ((rc = launch_k1(h, h->x, h->xd, h->w, want_lp, h->lp_partial, KP))) return rc;
+        if ((rc = launch_k2(h, h->w, h->g, KP))) return rc;
+    }
+    if (want_lp && (rc = launch_reduce_lp(h, h->lp_partial, h->g + (size_t)h->n * KP, KP))) return rc;
+    return POLEE_OK;
+}
+
 // The launch sequence of one step (SURVEY 3a inner loop, batched over the K draws).  ys / zs0 of the step are
 // produced by the previous step's fused update+reparam kernel (or by ensure_reparam for the first step):
 //   tree fwd (top, bottom) -> mid -> K1 -> K2 (+combine) -> [lp reduce] -> [all-reduce] -> tree bwd (bottom, top)
@@ -466,9 +479,7 @@ static int launch_step_sequence(polee_handle *h, bool do_adam, bool next_reparam
     int rc;
     if ((rc = launch_tree_fwd(h, KP, 1, apply_eff, want_vals))) return rc;
     if ((rc = launch_mid(h, KP, do_adam ? 1 : 0))) return rc;
-    if ((rc = launch_k1(h, h->x, h->xd, h->w, want_vals, h->lp_partial, KP))) return rc;
-    if ((rc = launch_k2(h, h->w, h->g, KP))) return rc;
-    if (want_vals && (rc = launch_reduce_lp(h, h->lp_partial, h->g + (size_t)h->n * KP, KP))) return rc;
+    if ((rc = launch_likelihood(h, KP, want_vals))) return rc;
 #ifdef POLEE_WITH_NCCL
     if (h->nranks > 1) {
         size_t count = (size_t)(h->n + (want_vals ? 1 : 0)) * KP;
@@ -620,9 +631,7 @@ extern "C" int polee_loglik_grad(polee_handle *h, const float *xs, int32_t K, in
     if ((rc = use_kp(h, K, &KP))) return rc;
     if ((rc = upload_kmajor<float>(h, xs, K, KP, h->n, h->x, 1.0f))) return rc;
     if ((rc = launch_widen_x(h, h->x, h->xd, KP))) return rc;
-    if ((rc = launch_k1(h, h->x, h->xd, h->w, !gradonly, h->lp_partial, KP))) return rc;
-    if ((rc = launch_k2(h, h->w, h->g, KP))) return rc;
-    if (!gradonly && (rc = launch_reduce_lp(h, h->lp_partial, h->g + (size_t)h->n * KP, KP))) return rc;
+    if ((rc = launch_likelihood(h, KP, !gradonly))) return rc;
     CK(cudaGetLastError());
     if (x_grad && (rc = download_kmajor<double, double>(h, h->g, K, KP, h->n, x_grad))) return rc;
     if (lp) {
@@ -645,6 +654,21 @@ extern "C" int polee_frag_prob_recip(polee_handle *h, const float *xs, float *w)
     int KP, rc;
     if ((rc = use_kp(h, 1, &KP))) return rc;
     if ((rc = upload_kmajor<float>(h, xs, 1, KP, h->n, h->x, 1.0f))) return rc;
+    if (h->fused) {  // rows keep their original order in the fused layout
+        float *d_w = nullptr;
+        CK(polee::dmalloc((void **)&d_w, sizeof(float) * (size_t)h->m * KP));
+        rc = launch_fused(h, h->x, h->g, false, h->lp_partial, d_w, KP);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (!rc && e != cudaSuccess) rc = h->fail(POLEE_ECUDA, std::string("frag_prob_recip: ") + cudaGetErrorString(e));
+        if (!rc) {
+            std::vector<float> wp((size_t)h->m * KP);
+            e = cudaMemcpy(wp.data(), d_w, sizeof(float) * wp.size(), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = h->fail(POLEE_ECUDA, std::string("frag_prob_recip: ") + cudaGetErrorString(e));
+            for (int64_t i = 0; i < h->m; ++i) w[i] = wp[(size_t)i * KP];
+        }
+        polee::dfree(d_w);
+        return rc;
+    }
     if ((rc = launch_widen_x(h, h->x, h->xd, KP))) return rc;
     if ((rc = launch_k1(h, h->x, h->xd, h->w, false, h->lp_partial, KP))) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -799,14 +823,23 @@ extern "C" int polee_step_stats(polee_handle *h, double *b1, double *b2, double 
     if (!h->have_matrix || !h->have_tree) return h->fail(POLEE_EINVAL, "step_stats: set the matrix and the tree first");
     // SURVEY 8(d) / BASELINE.md section 2 formulas with the padded draw count actually streamed
     const double nnz = (double)h->nnz, m = (double)h->m, n = (double)h->n, K = (double)h->KP, N = 2 * n - 1;
-    if (b1) *b1 = nnz * 8 + (m + 1) * 4 + K * n * 4 + K * m * 4;
-    if (b2) *b2 = nnz * 8 + (n + 1) * 4 + K * m * 4 + K * n * 4;
+    if (h->fused) {
+        // one pass: the matrix once (val + col + the 16-bit column-major permutation), row offsets, x, and the
+        // (tile, column) partials written and read back; b2 = 0 tells the caller there is no second sparse kernel
+        if (b1) *b1 = nnz * 10 + (m + 1) * 2 + K * n * 4 + (double)h->ft_parts * K * 4 * 2 + K * n * 8;
+        if (b2) *b2 = 0;
+    } else {
+        if (b1) *b1 = nnz * 8 + (m + 1) * 4 + K * n * 4 + K * m * 4;
+        if (b2) *b2 = nnz * 8 + (n + 1) * 4 + K * m * 4 + K * n * 4;
+    }
     if (b3) *b3 = (n - 1) * 72 + N * 16 + K * n * 8;
     if (launches) {
         const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
         const bool vals = lsn && !h->o.gradonly;
-        int L = (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*mid*/ + (h->n_row_tiles > 0) +
-                (h->n_segs > 0) + (h->n_multi > 0) + (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*update + reparam*/;
+        const int sparse_launches = h->fused ? 1 + (h->ft_nunits > 0) + (h->ft_nmulti > 0)
+                                             : (h->n_row_tiles > 0) + (h->n_segs > 0) + (h->n_multi > 0);
+        int L = (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*mid*/ + sparse_launches +
+                (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*update + reparam*/;
         if (vals) L += 2;
         *launches = L;
     }
@@ -828,9 +861,10 @@ extern "C" int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, f
     CK(cudaEventRecord(e0, h->stream));
     for (int r = 0; r < reps && !rc; ++r) {
         if (which == 1) {
-            rc = launch_k1(h, h->x, h->xd, h->w, false, h->lp_partial, KP);
+            rc = h->fused ? launch_fused(h, h->x, h->g, false, h->lp_partial, nullptr, KP)
+                          : launch_k1(h, h->x, h->xd, h->w, false, h->lp_partial, KP);
         } else if (which == 2) {
-            rc = launch_k2(h, h->w, h->g, KP);
+            if (!h->fused) rc = launch_k2(h, h->w, h->g, KP);  // fused layout: there is no second sparse kernel
         } else if (which == 3) {
             rc = launch_tree_fwd(h, KP, 1, 1, 0);
             if (!rc) rc = launch_mid(h, KP, 0);

@@ -41,6 +41,53 @@ struct RowTile {
     uint32_t nrows;     // valid rows in the tile (<= ROW_TILE)
 };
 
+// ---- fused likelihood layout ("row tiles"): K1 and K2 in one pass over the matrix.
+// A tile is a run of consecutive rows (<= FT_ROWS rows, about FT_ENTRIES entries).  Its entries are stored once, in
+// row-major order (val, col), together with a 16-bit permutation that enumerates them column-major, so one CTA can
+// compute p = X x for the tile's rows and then the tile's contribution to X^T (1/p) without w ever leaving the SM.
+// Everything a tile needs travels as one 16-byte aligned blob (one bulk copy):
+//   header | rowoff u16[rows+1] | val f32[E] | col u32[E] | perm u16[E] | slot0 u16[chunks] | cslot u16[C+1]
+// perm[q] = (row-major index of the q-th column-major entry) | flag << 15, flag = "last entry of its column inside its
+// chunk of FT_CHUNK column-major entries"; slot0[c] = index of the first partial sum chunk c emits; cslot[j] = first
+// partial sum of the tile's j-th distinct column.
+constexpr int FT_ROWS = 256;
+constexpr int FT_CHUNK = 16;
+constexpr int FT_MAX_E = 32767;  // perm is 15 bits
+struct FusedHdr {
+    uint32_t rows, E, C, nslots;  // rows, entries, distinct columns, partial sums (slots) of the tile
+    uint32_t row0, part0;         // first row; index of the tile's first (tile, column) partial
+    uint32_t chunks, pad;
+};
+struct FusedTileDesc {
+    uint64_t off;    // byte offset of the blob
+    uint32_t bytes;  // blob size (multiple of 16)
+    uint32_t pad;
+};
+struct BlobLayout {
+    uint32_t rowoff, val, col, perm, slot0, cslot, bytes;
+};
+__host__ __device__ inline BlobLayout blob_layout(uint32_t rows, uint32_t E, uint32_t C, uint32_t chunks) {
+    BlobLayout L;
+    L.rowoff = (uint32_t)sizeof(FusedHdr);
+    L.val = L.rowoff + (((rows + 1u) * 2u + 15u) & ~15u);
+    L.col = L.val + ((E * 4u + 15u) & ~15u);
+    L.perm = L.col + ((E * 4u + 15u) & ~15u);
+    L.slot0 = L.perm + ((E * 2u + 15u) & ~15u);
+    L.cslot = L.slot0 + ((chunks * 2u + 15u) & ~15u);
+    L.bytes = L.cslot + (((C + 1u) * 2u + 15u) & ~15u);
+    return L;
+}
+// second stage: g[col] = sum of the (tile, column) partials of the column, in tile order.  A unit is <= FT_UNIT
+// partials of one column (one warp); columns with more than one unit are finished by a second small launch.
+constexpr int FT_UNIT = 64;
+struct FusedUnit {
+    uint32_t col, begin, end;  // [begin, end) into the column-sorted partial list
+    int32_t out;               // -1: writes g[col]; >= 0: writes the level-2 slot
+};
+struct FusedMulti {
+    uint32_t col, first, count, pad;  // level-2 slots [first, first + count)
+};
+
 // K2: one warp = one segment of <= COL_SEG consecutive entries of one column (rows permuted, sorted).
 constexpr int COL_SEG = 256;
 struct ColSeg {
@@ -167,6 +214,24 @@ struct polee_handle {
     int n_multi = 0;
     int n_slots = 0;
     bool have_matrix = false;
+    // fused layout (used instead of the SELL / CSC pair when `fused`)
+    bool fused = false;
+    unsigned char *ft_blob = nullptr;
+    polee::FusedTileDesc *ft_desc = nullptr;
+    int ft_tiles = 0;
+    uint32_t ft_max_blob = 0, ft_max_E = 0, ft_max_slots = 0, ft_max_rows = 0;
+    uint64_t ft_blob_bytes = 0;
+    int64_t ft_parts = 0;            // (tile, column) partials
+    uint32_t *ft_plist = nullptr;    // partial ids sorted by column
+    polee::FusedUnit *ft_units = nullptr;
+    int ft_nunits = 0;
+    polee::FusedMulti *ft_multi = nullptr;
+    int ft_nmulti = 0, ft_nlvl2 = 0;
+    float *ft_row_weight = nullptr;  // ks per row, original order (nullable)
+    float *ft_partial = nullptr;     // [ft_parts][KP]           (work buffer)
+    double *ft_lvl2 = nullptr;       // [ft_nlvl2][KP]           (work buffer)
+    float *ft_gslots = nullptr;      // [grid][ft_max_slots][KP] (work buffer, only when a tile's slots exceed shared memory)
+    int ft_grid = 0;
 
     // ---- per-sample vectors
     float *efflen = nullptr;      // [n]
@@ -254,6 +319,14 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
                                  const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
                                  const uint32_t *h_colptr_or_null, cudaEvent_t vals_ready_or_null);
 void release_matrix(polee_handle *h);
+// returns POLEE_OK with h->fused set, or POLEE_OK with h->fused == false when the row order has too little locality
+int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t nnz, const uint32_t *d_colptr,
+                                const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
+                                const std::vector<uint32_t> &colptr, cudaEvent_t vals_ready_or_null);
+
+// fused_kernels.cu
+int fused_grid(polee_handle *h, int KP);
+int launch_fused(polee_handle *h, const float *x, double *g, bool want_lp, double *lp_partial, float *w_out, int KP);
 
 // sparse_kernels.cu
 int launch_k1(polee_handle *h, const float *x, const double *xd, float *w, bool want_lp, double *lp_partial, int KP);

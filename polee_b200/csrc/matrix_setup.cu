@@ -119,6 +119,184 @@ __global__ void k_row_weights(const int64_t *__restrict__ ks, int64_t m, const u
         row_weight[row_perm[i]] = (float)ks[i];
 }
 
+
+// ------------------------------------------------------------------ fused row-tile layout (see common.cuh)
+constexpr uint32_t FT_WINDOW = 2048;  // a tile = the rows whose key  row_ptr[i] + FT_ROW_COST * i  falls in one window
+constexpr uint32_t FT_ROW_COST = 7;   // => rows <= FT_WINDOW / 8 = FT_ROWS (non-empty rows), entries < FT_WINDOW + longest row
+
+__device__ __forceinline__ uint64_t tile_key(const uint32_t *row_ptr, int64_t i) {
+    return ((uint64_t)row_ptr[i] + (uint64_t)FT_ROW_COST * (uint64_t)i) / FT_WINDOW;
+}
+
+__global__ void k_tile_flags(const uint32_t *__restrict__ row_ptr, int64_t m, uint32_t *flag) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+        flag[i] = (i == 0 || tile_key(row_ptr, i) != tile_key(row_ptr, i - 1)) ? 1u : 0u;
+}
+
+// tile_incl[i] = 1 + tile of row i (inclusive scan of the flags)
+__global__ void k_tile_row0(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ tile_incl, int64_t m,
+                            uint32_t n_tiles, uint32_t *tile_row0) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        if (flag[i]) tile_row0[tile_incl[i] - 1u] = (uint32_t)i;
+        if (i == m - 1) tile_row0[n_tiles] = (uint32_t)m;
+    }
+}
+
+__global__ void k_csc_expand(const uint32_t *__restrict__ colptr, int64_t n, const uint32_t *__restrict__ rowval,
+                             int64_t nnz, const uint32_t *__restrict__ tile_incl, uint32_t *col_of, uint32_t *key_row,
+                             uint32_t *key_tile, uint32_t *val_e) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = n;  // largest j with colptr[j] - 1 <= e
+        while (hi - lo > 1) {
+            int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)colptr[mid] - 1 <= e)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const uint32_t r = rowval[e] - 1u;
+        col_of[e] = (uint32_t)lo;
+        key_row[e] = r;
+        key_tile[e] = tile_incl[r] - 1u;
+        val_e[e] = (uint32_t)e;
+    }
+}
+
+__global__ void k_inverse_perm(const uint32_t *__restrict__ a_csc, int64_t nnz, uint32_t *apos_of_csc) {
+    for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nnz; a += (int64_t)gridDim.x * blockDim.x)
+        apos_of_csc[a_csc[a]] = (uint32_t)a;
+}
+
+// column-major (within tile) order: column and row-major position of every entry
+__global__ void k_b_gather(const uint32_t *__restrict__ b_csc, int64_t nnz, const uint32_t *__restrict__ col_of,
+                           const uint32_t *__restrict__ apos_of_csc, uint32_t *colB, uint32_t *aposB) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t e = b_csc[q];
+        colB[q] = col_of[e];
+        aposB[q] = apos_of_csc[e];
+    }
+}
+
+__global__ void k_b_flags(const uint32_t *__restrict__ tileB, const uint32_t *__restrict__ colB, int64_t nnz,
+                          const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ tile_row0, uint32_t *flagB,
+                          uint32_t *colstart) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q <= nnz; q += (int64_t)gridDim.x * blockDim.x) {
+        if (q == nnz) {  // sentinel for the exclusive scans
+            flagB[q] = 0;
+            colstart[q] = 0;
+            continue;
+        }
+        const uint32_t t = tileB[q];
+        const uint32_t a0 = row_ptr[tile_row0[t]], a1 = row_ptr[tile_row0[t + 1]];
+        const uint32_t qq = (uint32_t)q - a0, c = colB[q];
+        const bool last = (uint32_t)q == a1 - 1u;
+        flagB[q] = (qq % FT_CHUNK == FT_CHUNK - 1 || last || colB[q + 1] != c) ? 1u : 0u;
+        colstart[q] = (qq == 0 || colB[q - 1] != c) ? 1u : 0u;
+    }
+}
+
+__global__ void k_tile_meta(uint32_t n_tiles, const uint32_t *__restrict__ tile_row0, const uint32_t *__restrict__ row_ptr,
+                            const uint32_t *__restrict__ runs_before, const uint32_t *__restrict__ cols_before,
+                            FusedHdr *hdrs, uint64_t *blob_bytes, uint32_t *maxima /* E, slots, rows, bytes */) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+        const uint32_t row0 = tile_row0[t], row1 = tile_row0[t + 1];
+        const uint32_t a0 = row_ptr[row0], a1 = row_ptr[row1];
+        FusedHdr hd;
+        hd.rows = row1 - row0;
+        hd.E = a1 - a0;
+        hd.C = cols_before[a1] - cols_before[a0];
+        hd.nslots = runs_before[a1] - runs_before[a0];
+        hd.row0 = row0;
+        hd.part0 = cols_before[a0];
+        hd.chunks = (hd.E + FT_CHUNK - 1) / FT_CHUNK;
+        hd.pad = 0;
+        hdrs[t] = hd;
+        const uint32_t bytes = blob_layout(hd.rows, hd.E, hd.C, hd.chunks).bytes;
+        blob_bytes[t] = bytes;
+        atomicMax(&maxima[0], hd.E);
+        atomicMax(&maxima[1], hd.nslots);
+        atomicMax(&maxima[2], hd.rows);
+        atomicMax(&maxima[3], bytes);
+    }
+}
+
+__global__ void k_tile_desc(uint32_t n_tiles, const FusedHdr *__restrict__ hdrs, const uint64_t *__restrict__ blob_off,
+                            const uint64_t *__restrict__ blob_bytes, FusedTileDesc *desc, unsigned char *blob) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+        desc[t] = FusedTileDesc{blob_off[t], (uint32_t)blob_bytes[t], 0u};
+        *reinterpret_cast<FusedHdr *>(blob + blob_off[t]) = hdrs[t];
+    }
+}
+
+__global__ void k_pack_rows(int64_t m, const uint32_t *__restrict__ tile_incl, const uint32_t *__restrict__ row_ptr,
+                            const FusedHdr *__restrict__ hdrs, const uint64_t *__restrict__ blob_off, unsigned char *blob) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t t = tile_incl[i] - 1u;
+        const FusedHdr hd = hdrs[t];
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.chunks);
+        uint16_t *rowoff = reinterpret_cast<uint16_t *>(blob + blob_off[t] + L.rowoff);
+        const uint32_t a0 = row_ptr[hd.row0];
+        rowoff[i - hd.row0] = (uint16_t)(row_ptr[i] - a0);
+        if (i == (int64_t)hd.row0 + hd.rows - 1) rowoff[hd.rows] = (uint16_t)hd.E;
+    }
+}
+
+__global__ void k_pack_a(int64_t nnz, const uint32_t *__restrict__ rowA, const uint32_t *__restrict__ a_csc,
+                         const uint32_t *__restrict__ tile_incl, const uint32_t *__restrict__ row_ptr,
+                         const FusedHdr *__restrict__ hdrs, const uint64_t *__restrict__ blob_off,
+                         const uint32_t *__restrict__ col_of, const float *__restrict__ nzval, unsigned char *blob) {
+    for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nnz; a += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t t = tile_incl[rowA[a]] - 1u;
+        const FusedHdr hd = hdrs[t];
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.chunks);
+        unsigned char *b = blob + blob_off[t];
+        const uint32_t e = (uint32_t)a - row_ptr[hd.row0];
+        const uint32_t src = a_csc[a];
+        reinterpret_cast<float *>(b + L.val)[e] = nzval[src];
+        reinterpret_cast<uint32_t *>(b + L.col)[e] = col_of[src];
+    }
+}
+
+__global__ void k_pack_b(int64_t nnz, const uint32_t *__restrict__ tileB, const uint32_t *__restrict__ colB,
+                         const uint32_t *__restrict__ aposB, const uint32_t *__restrict__ flagB,
+                         const uint32_t *__restrict__ colstart, const uint32_t *__restrict__ runs_before,
+                         const uint32_t *__restrict__ cols_before, const uint32_t *__restrict__ row_ptr,
+                         const FusedHdr *__restrict__ hdrs, const uint64_t *__restrict__ blob_off, unsigned char *blob,
+                         uint32_t *part_col) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t t = tileB[q];
+        const FusedHdr hd = hdrs[t];
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.chunks);
+        unsigned char *b = blob + blob_off[t];
+        const uint32_t a0 = row_ptr[hd.row0];
+        const uint32_t qq = (uint32_t)q - a0;
+        const uint32_t run = runs_before[q] - runs_before[a0];
+        reinterpret_cast<uint16_t *>(b + L.perm)[qq] = (uint16_t)((aposB[q] - a0) | (flagB[q] << 15));
+        if (qq % FT_CHUNK == 0) reinterpret_cast<uint16_t *>(b + L.slot0)[qq / FT_CHUNK] = (uint16_t)run;
+        if (colstart[q]) {
+            const uint32_t pid = cols_before[q];
+            reinterpret_cast<uint16_t *>(b + L.cslot)[pid - hd.part0] = (uint16_t)run;
+            part_col[pid] = colB[q];
+        }
+        if (qq == hd.E - 1u) reinterpret_cast<uint16_t *>(b + L.cslot)[hd.C] = (uint16_t)hd.nslots;
+    }
+}
+
+__global__ void k_iota_u32(uint32_t *v, int64_t count) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        v[i] = (uint32_t)i;
+}
+
+__global__ void k_count_keys(const uint32_t *__restrict__ keys, int64_t count, uint32_t *cnt) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&cnt[keys[i]], 1u);
+}
+
+__global__ void k_ks_to_f32(const int64_t *__restrict__ ks, int64_t m, float *out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (float)ks[i];
+}
+
 int bits_for(uint64_t maxval) {
     int b = 1;
     while (b < 32 && (maxval >> b) != 0) ++b;
@@ -140,11 +318,15 @@ struct Scratch {
 
 }  // namespace
 
+void release_fused(polee_handle *h);
+
 void release_matrix(polee_handle *h) {
     polee::dfree(h->sell_idx); polee::dfree(h->sell_val); polee::dfree(h->row_tiles); polee::dfree(h->row_perm);
     polee::dfree(h->row_weight); polee::dfree(h->csc_row); polee::dfree(h->csc_val); polee::dfree(h->segs); polee::dfree(h->multi);
     h->sell_idx = nullptr; h->sell_val = nullptr; h->row_tiles = nullptr; h->row_perm = nullptr;
     h->row_weight = nullptr; h->csc_row = nullptr; h->csc_val = nullptr; h->segs = nullptr; h->multi = nullptr;
+    h->n_row_tiles = 0; h->n_segs = 0; h->n_multi = 0; h->n_slots = 0; h->m_pad = 0;
+    release_fused(h);
     h->have_matrix = false;
 }
 
@@ -165,6 +347,194 @@ struct PhaseTimer {
     }
 };
 
+void release_fused(polee_handle *h) {
+    polee::dfree(h->ft_blob); polee::dfree(h->ft_desc); polee::dfree(h->ft_plist); polee::dfree(h->ft_units);
+    polee::dfree(h->ft_multi); polee::dfree(h->ft_row_weight);
+    h->ft_blob = nullptr; h->ft_desc = nullptr; h->ft_plist = nullptr; h->ft_units = nullptr; h->ft_multi = nullptr;
+    h->ft_row_weight = nullptr;
+    h->fused = false;
+    h->ft_tiles = 0; h->ft_parts = 0; h->ft_nunits = h->ft_nmulti = h->ft_nlvl2 = 0;
+}
+
+// Build the fused layout.  All passes are device passes (CUB sorts / scans + small kernels); the host only sees the
+// per-column partial counts (n numbers) to cut the second-stage work list.
+int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t nnz, const uint32_t *d_colptr,
+                                const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
+                                const std::vector<uint32_t> &colptr_host, cudaEvent_t vals_ready_or_null) {
+    release_fused(h);
+    cudaStream_t st = h->stream;
+    PhaseTimer pt(st);
+    const int TPB = 256;
+    auto grid_for = [&](int64_t work) { return (int)std::max<int64_t>(1, std::min<int64_t>((work + TPB - 1) / TPB, (int64_t)h->num_sms * 32)); };
+    Scratch sc;
+    size_t tmp_bytes = 0, need = 0;
+    void *d_tmp = nullptr;
+    auto ensure_tmp = [&](size_t bytes) -> cudaError_t {
+        if (bytes <= tmp_bytes) return cudaSuccess;
+        tmp_bytes = bytes + bytes / 8;
+        return sc.alloc((char **)&d_tmp, tmp_bytes);
+    };
+
+    // ---- row lengths, row pointers, tiles
+    uint32_t *row_len, *row_ptr, *flag, *tile_incl, *d_lmax;
+    int *d_bad;
+    CK(sc.alloc(&row_len, m + 1)); CK(sc.alloc(&row_ptr, m + 1)); CK(sc.alloc(&flag, m)); CK(sc.alloc(&tile_incl, m));
+    CK(sc.alloc(&d_lmax, 1)); CK(sc.alloc(&d_bad, 1));
+    CK(cudaMemsetAsync(row_len, 0, sizeof(uint32_t) * (m + 1), st));
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    if (nnz > 0) k_count_rows<<<grid_for(nnz), TPB, 0, st>>>(d_rowval, nnz, row_len, m, d_bad);
+    CK(cub::DeviceReduce::Max(nullptr, need, row_len, d_lmax, (int)m, st));
+    CK(ensure_tmp(need));
+    CK(cub::DeviceReduce::Max(d_tmp, need, row_len, d_lmax, (int)m, st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, row_len, row_ptr, (int)(m + 1), st));
+    CK(ensure_tmp(need));
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, row_len, row_ptr, (int)(m + 1), st));
+    k_tile_flags<<<grid_for(m), TPB, 0, st>>>(row_ptr, m, flag);
+    CK(cub::DeviceScan::InclusiveSum(nullptr, need, flag, tile_incl, (int)m, st));
+    CK(ensure_tmp(need));
+    CK(cub::DeviceScan::InclusiveSum(d_tmp, need, flag, tile_incl, (int)m, st));
+    int bad = 0;
+    uint32_t lmax = 0, n_tiles = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&lmax, d_lmax, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&n_tiles, tile_incl + (m - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (bad) return h->fail(POLEE_EINVAL, "set_matrix: rowval out of range 1..m");
+    if ((uint64_t)lmax + FT_WINDOW > (uint64_t)FT_MAX_E) return POLEE_OK;  // a row too long for 15-bit tile offsets
+    pt.mark("fused: rows + tiles");
+    uint32_t *tile_row0;
+    CK(sc.alloc(&tile_row0, (size_t)n_tiles + 1));
+    k_tile_row0<<<grid_for(m), TPB, 0, st>>>(flag, tile_incl, m, n_tiles, tile_row0);
+
+    // ---- the two entry orders: row-major (A) and column-major inside a tile (B)
+    uint32_t *col_of, *keyR, *keyT, *valE, *rowA, *a_csc, *tileB, *b_csc, *apos_of_csc;
+    CK(sc.alloc(&col_of, nnz)); CK(sc.alloc(&keyR, nnz)); CK(sc.alloc(&keyT, nnz)); CK(sc.alloc(&valE, nnz));
+    CK(sc.alloc(&rowA, nnz)); CK(sc.alloc(&a_csc, nnz)); CK(sc.alloc(&tileB, nnz)); CK(sc.alloc(&b_csc, nnz));
+    CK(sc.alloc(&apos_of_csc, nnz));
+    uint32_t *d_colptr_own = nullptr;
+    if (!d_colptr) {
+        CK(sc.alloc(&d_colptr_own, n + 1));
+        CK(cudaMemcpyAsync(d_colptr_own, colptr_host.data(), 4 * (n + 1), cudaMemcpyHostToDevice, st));
+        d_colptr = d_colptr_own;
+    }
+    if (nnz > 0) {
+        k_csc_expand<<<grid_for(nnz), TPB, 0, st>>>(d_colptr, n, d_rowval, nnz, tile_incl, col_of, keyR, keyT, valE);
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, keyR, rowA, valE, a_csc, (int)nnz, 0, 32, st));
+        CK(ensure_tmp(need));
+        CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, keyR, rowA, valE, a_csc, (int)nnz, 0, bits_for((uint64_t)m), st));
+        CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, keyT, tileB, valE, b_csc, (int)nnz, 0, bits_for((uint64_t)n_tiles), st));
+        k_inverse_perm<<<grid_for(nnz), TPB, 0, st>>>(a_csc, nnz, apos_of_csc);
+    }
+    pt.mark("fused: two entry sorts");
+    uint32_t *colB = keyR, *aposB = keyT;  // the sort inputs are free again
+    uint32_t *flagB, *colstart, *runs_before, *cols_before;
+    CK(sc.alloc(&flagB, nnz + 1)); CK(sc.alloc(&colstart, nnz + 1)); CK(sc.alloc(&runs_before, nnz + 1));
+    CK(sc.alloc(&cols_before, nnz + 1));
+    if (nnz > 0) k_b_gather<<<grid_for(nnz), TPB, 0, st>>>(b_csc, nnz, col_of, apos_of_csc, colB, aposB);
+    k_b_flags<<<grid_for(nnz + 1), TPB, 0, st>>>(tileB, colB, nnz, row_ptr, tile_row0, flagB, colstart);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, flagB, runs_before, (int)(nnz + 1), st));
+    CK(ensure_tmp(need));
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, flagB, runs_before, (int)(nnz + 1), st));
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, colstart, cols_before, (int)(nnz + 1), st));
+
+    // ---- per-tile headers, blob offsets
+    FusedHdr *hdrs;
+    uint64_t *blob_bytes, *blob_off;
+    uint32_t *d_max;
+    CK(sc.alloc(&hdrs, n_tiles)); CK(sc.alloc(&blob_bytes, (size_t)n_tiles + 1)); CK(sc.alloc(&blob_off, (size_t)n_tiles + 1));
+    CK(sc.alloc(&d_max, 4));
+    CK(cudaMemsetAsync(d_max, 0, 16, st));
+    CK(cudaMemsetAsync(blob_bytes, 0, sizeof(uint64_t) * ((size_t)n_tiles + 1), st));
+    k_tile_meta<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, tile_row0, row_ptr, runs_before, cols_before, hdrs, blob_bytes, d_max);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, blob_bytes, blob_off, (int)(n_tiles + 1), st));
+    CK(ensure_tmp(need));
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, blob_bytes, blob_off, (int)(n_tiles + 1), st));
+    uint32_t maxima[4];
+    uint64_t total_bytes = 0;
+    uint32_t n_parts = 0;
+    CK(cudaMemcpyAsync(maxima, d_max, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&total_bytes, blob_off + n_tiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&n_parts, cols_before + nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    pt.mark("fused: runs + tile headers");
+    // locality gate: the (tile, column) partials are written and read back once per step (32 B each at K = 8);
+    // with rows in random order they would outweigh the matrix itself
+    const char *force = getenv("POLEE_LAYOUT");
+    const bool forced = force && std::string(force) == "fused";
+    if (!forced && (double)n_parts * 64.0 > 0.35 * (double)total_bytes) return POLEE_OK;
+    if (maxima[3] > 64u * 1024u) return POLEE_OK;  // a tile must fit a shared-memory stage
+
+    CK(polee::dmalloc((void **)&h->ft_blob, std::max<uint64_t>(total_bytes, 16)));
+    CK(polee::dmalloc((void **)&h->ft_desc, sizeof(FusedTileDesc) * std::max<uint32_t>(n_tiles, 1)));
+    CK(cudaMemsetAsync(h->ft_blob, 0, std::max<uint64_t>(total_bytes, 16), st));
+    uint32_t *part_col, *part_col_sorted, *pid_iota, *col_cnt;
+    CK(sc.alloc(&part_col, n_parts)); CK(sc.alloc(&part_col_sorted, n_parts)); CK(sc.alloc(&pid_iota, n_parts));
+    CK(sc.alloc(&col_cnt, n));
+    CK(polee::dmalloc((void **)&h->ft_plist, sizeof(uint32_t) * std::max<uint32_t>(n_parts, 1)));
+    k_tile_desc<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, hdrs, blob_off, blob_bytes, h->ft_desc, h->ft_blob);
+    k_pack_rows<<<grid_for(m), TPB, 0, st>>>(m, tile_incl, row_ptr, hdrs, blob_off, h->ft_blob);
+    if (vals_ready_or_null) CK(cudaStreamWaitEvent(st, vals_ready_or_null, 0));
+    if (nnz > 0) {
+        k_pack_a<<<grid_for(nnz), TPB, 0, st>>>(nnz, rowA, a_csc, tile_incl, row_ptr, hdrs, blob_off, col_of, d_nzval, h->ft_blob);
+        k_pack_b<<<grid_for(nnz), TPB, 0, st>>>(nnz, tileB, colB, aposB, flagB, colstart, runs_before, cols_before, row_ptr,
+                                                 hdrs, blob_off, h->ft_blob, part_col);
+    }
+    pt.mark("fused: pack blobs");
+    // ---- second stage work list: partial ids by column
+    CK(cudaMemsetAsync(col_cnt, 0, sizeof(uint32_t) * n, st));
+    if (n_parts > 0) {
+        k_iota_u32<<<grid_for(n_parts), TPB, 0, st>>>(pid_iota, n_parts);
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, part_col, part_col_sorted, pid_iota, h->ft_plist, (int)n_parts, 0, 32, st));
+        CK(ensure_tmp(need));
+        CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, part_col, part_col_sorted, pid_iota, h->ft_plist, (int)n_parts, 0,
+                                           bits_for((uint64_t)n), st));
+        k_count_keys<<<grid_for(n_parts), TPB, 0, st>>>(part_col, n_parts, col_cnt);
+    }
+    std::vector<uint32_t> cnt(n);
+    CK(cudaMemcpyAsync(cnt.data(), col_cnt, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<FusedUnit> units;
+    std::vector<FusedMulti> multi;
+    units.reserve((size_t)n + n_parts / FT_UNIT);
+    uint32_t pos = 0, lvl2 = 0;
+    for (int64_t j = 0; j < n; ++j) {
+        const uint32_t c = cnt[j], nu = c == 0 ? 1u : (c + FT_UNIT - 1) / FT_UNIT;
+        if (nu == 1) {
+            units.push_back(FusedUnit{(uint32_t)j, pos, pos + c, -1});
+        } else {
+            multi.push_back(FusedMulti{(uint32_t)j, lvl2, nu, 0u});
+            for (uint32_t u = 0; u < nu; ++u)
+                units.push_back(FusedUnit{(uint32_t)j, pos + u * FT_UNIT, pos + std::min<uint32_t>(c, (u + 1) * FT_UNIT), (int32_t)lvl2++});
+        }
+        pos += c;
+    }
+    CK(polee::dmalloc((void **)&h->ft_units, sizeof(FusedUnit) * std::max<size_t>(units.size(), 1)));
+    CK(polee::dmalloc((void **)&h->ft_multi, sizeof(FusedMulti) * std::max<size_t>(multi.size(), 1)));
+    CK(cudaMemcpyAsync(h->ft_units, units.data(), sizeof(FusedUnit) * units.size(), cudaMemcpyHostToDevice, st));
+    if (!multi.empty())
+        CK(cudaMemcpyAsync(h->ft_multi, multi.data(), sizeof(FusedMulti) * multi.size(), cudaMemcpyHostToDevice, st));
+    if (d_ks) {
+        CK(polee::dmalloc((void **)&h->ft_row_weight, sizeof(float) * m));
+        k_ks_to_f32<<<grid_for(m), TPB, 0, st>>>(d_ks, m, h->ft_row_weight);
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    pt.mark("fused: second-stage list");
+    h->ft_tiles = (int)n_tiles;
+    h->ft_max_E = maxima[0]; h->ft_max_slots = maxima[1]; h->ft_max_rows = maxima[2]; h->ft_max_blob = maxima[3];
+    h->ft_blob_bytes = total_bytes;
+    h->ft_parts = n_parts;
+    h->ft_nunits = (int)units.size();
+    h->ft_nmulti = (int)multi.size();
+    h->ft_nlvl2 = (int)lvl2;
+    h->fused = true;
+    if (getenv("POLEE_SETUP_TIMING"))
+        fprintf(stderr, "[polee setup] fused: %u tiles, %.1f MB blobs (%.2f B/entry), %u partials, %zu units, %zu multi, max E %u slots %u rows %u blob %u\n",
+                n_tiles, total_bytes / 1e6, nnz ? (double)total_bytes / nnz : 0.0, n_parts, units.size(), multi.size(),
+                maxima[0], maxima[1], maxima[2], maxima[3]);
+    return POLEE_OK;
+}
+
 int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const uint32_t *d_colptr,
                                  const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
                                  const uint32_t *h_colptr_or_null, cudaEvent_t vals_ready_or_null) {
@@ -184,6 +554,21 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
         if (colptr[j + 1] < colptr[j]) return h->fail(POLEE_EINVAL, "set_matrix: colptr is not non-decreasing");
     const int64_t nnz = (int64_t)colptr[n] - 1;
     h->m = m; h->n = n; h->nnz = nnz;
+
+    // fused row-tile layout (one pass per step) unless the reference-order Float64 path was asked for, the caller
+    // pins the split layout (POLEE_LAYOUT=split), or the row order has too little locality for it
+    {
+        const char *lay = getenv("POLEE_LAYOUT");
+        const bool want_fused = !h->o.exact_accumulation && !(lay && std::string(lay) == "split");
+        if (want_fused) {
+            int rc = setup_fused_from_device_csc(h, m, n, nnz, d_colptr, d_rowval, d_nzval, d_ks, colptr, vals_ready_or_null);
+            if (rc) return rc;
+            if (h->fused) {
+                h->have_matrix = true;
+                return POLEE_OK;
+            }
+        }
+    }
 
     const int TPB = 256;
     auto grid_for = [&](int64_t work) { return (int)std::min<int64_t>((work + TPB - 1) / TPB, (int64_t)h->num_sms * 32); };
