@@ -42,21 +42,26 @@ struct RowTile {
 };
 
 // ---- fused likelihood layout ("row tiles"): K1 and K2 in one pass over the matrix.
-// A tile is a run of consecutive rows (<= FT_ROWS rows, about FT_ENTRIES entries).  Its entries are stored once, in
-// row-major order (val, col), together with a 16-bit permutation that enumerates them column-major, so one CTA can
-// compute p = X x for the tile's rows and then the tile's contribution to X^T (1/p) without w ever leaving the SM.
-// Everything a tile needs travels as one 16-byte aligned blob (one bulk copy):
-//   header | rowoff u16[rows+1] | val f32[E] | col u32[E] | perm u16[E] | slot0 u16[chunks] | cslot u16[C+1]
-// perm[q] = (row-major index of the q-th column-major entry) | flag << 15, flag = "last entry of its column inside its
-// chunk of FT_CHUNK column-major entries"; slot0[c] = index of the first partial sum chunk c emits; cslot[j] = first
-// partial sum of the tile's j-th distinct column.
-constexpr int FT_ROWS = 256;
-constexpr int FT_CHUNK = 16;
-constexpr int FT_MAX_E = 32767;  // perm is 15 bits
+// A tile is a run of <= FT_ROWS consecutive rows (and < FT_ENTRY_WINDOW + longest-row entries), processed by ONE warp;
+// inside a tile the rows are re-ordered longest first (lanes of a warp then run the same trip counts).  The entries
+// are stored once, row-major, with a 16-bit permutation that enumerates them column-major, so the warp can compute
+// p = X x for its rows and then the tile's contribution to X^T (1/p) without w ever leaving the SM.  Everything a
+// tile needs travels as one 16-byte aligned blob (one bulk copy):
+//   header | cols u32[C] | rowoff u16[rows+1] | val f32[E] | perm u16[E] | slot0 u16[32] | cslot u16[C+1] | lcol u8[E]
+// cols = the tile's C distinct columns (a local dictionary, C <= 255: x of these columns is staged in shared memory
+// once per tile); lcol[e] = local column of row-major entry e; perm[q] = (row-major index of the q-th column-major
+// entry) | flag << 15.  Column sums: lane l walks the column-major entries [l * chunk, (l + 1) * chunk) sequentially
+// and emits a partial sum ("slot") wherever flag is set (= the column changes or its chunk ends); slot0[l] = index of
+// lane l's first slot, cslot[j] = first slot of local column j.  7 bytes per entry instead of the 16 the split
+// layouts stream (8 in K1 + 8 in K2).
+constexpr int FT_ROWS = 64;
+constexpr uint32_t FT_ENTRY_WINDOW = 512;
+constexpr uint32_t FT_MAX_C = 255;
+constexpr int FT_MAX_E = 32767;
 struct FusedHdr {
-    uint32_t rows, E, C, nslots;  // rows, entries, distinct columns, partial sums (slots) of the tile
-    uint32_t row0, part0;         // first row; index of the tile's first (tile, column) partial
-    uint32_t chunks, pad;
+    uint32_t rows, E, C, nslots;  // rows, entries, distinct columns, partial sums ("slots") of the tile
+    uint32_t row0, part0;         // first row position; index of the tile's first (tile, column) partial
+    uint32_t chunk, pad;          // column-major entries per lane = ceil(E / 32)
 };
 struct FusedTileDesc {
     uint64_t off;    // byte offset of the blob
@@ -64,22 +69,23 @@ struct FusedTileDesc {
     uint32_t pad;
 };
 struct BlobLayout {
-    uint32_t rowoff, val, col, perm, slot0, cslot, bytes;
+    uint32_t cols, rowoff, val, perm, slot0, cslot, lcol, bytes;
 };
-__host__ __device__ inline BlobLayout blob_layout(uint32_t rows, uint32_t E, uint32_t C, uint32_t chunks) {
+__host__ __device__ inline BlobLayout blob_layout(uint32_t rows, uint32_t E, uint32_t C) {
     BlobLayout L;
-    L.rowoff = (uint32_t)sizeof(FusedHdr);
+    L.cols = (uint32_t)sizeof(FusedHdr);
+    L.rowoff = L.cols + ((C * 4u + 15u) & ~15u);
     L.val = L.rowoff + (((rows + 1u) * 2u + 15u) & ~15u);
-    L.col = L.val + ((E * 4u + 15u) & ~15u);
-    L.perm = L.col + ((E * 4u + 15u) & ~15u);
+    L.perm = L.val + ((E * 4u + 15u) & ~15u);
     L.slot0 = L.perm + ((E * 2u + 15u) & ~15u);
-    L.cslot = L.slot0 + ((chunks * 2u + 15u) & ~15u);
-    L.bytes = L.cslot + (((C + 1u) * 2u + 15u) & ~15u);
+    L.cslot = L.slot0 + 64u;
+    L.lcol = L.cslot + (((C + 1u) * 2u + 15u) & ~15u);
+    L.bytes = L.lcol + ((E + 15u) & ~15u);
     return L;
 }
 // second stage: g[col] = sum of the (tile, column) partials of the column, in tile order.  A unit is <= FT_UNIT
 // partials of one column (one warp); columns with more than one unit are finished by a second small launch.
-constexpr int FT_UNIT = 64;
+constexpr int FT_UNIT = 256;
 struct FusedUnit {
     uint32_t col, begin, end;  // [begin, end) into the column-sorted partial list
     int32_t out;               // -1: writes g[col]; >= 0: writes the level-2 slot
@@ -219,7 +225,8 @@ struct polee_handle {
     unsigned char *ft_blob = nullptr;
     polee::FusedTileDesc *ft_desc = nullptr;
     int ft_tiles = 0;
-    uint32_t ft_max_blob = 0, ft_max_E = 0, ft_max_slots = 0, ft_max_rows = 0;
+    uint32_t ft_max_blob = 0, ft_max_E = 0, ft_max_rows = 0, ft_max_C = 0, ft_max_slots = 0;
+    uint32_t *ft_row_of_pos = nullptr;  // original row of every (tile-sorted) row position
     uint64_t ft_blob_bytes = 0;
     int64_t ft_parts = 0;            // (tile, column) partials
     uint32_t *ft_plist = nullptr;    // partial ids sorted by column
@@ -230,7 +237,6 @@ struct polee_handle {
     float *ft_row_weight = nullptr;  // ks per row, original order (nullable)
     float *ft_partial = nullptr;     // [ft_parts][KP]           (work buffer)
     double *ft_lvl2 = nullptr;       // [ft_nlvl2][KP]           (work buffer)
-    float *ft_gslots = nullptr;      // [grid][ft_max_slots][KP] (work buffer, only when a tile's slots exceed shared memory)
     int ft_grid = 0;
 
     // ---- per-sample vectors

@@ -23,46 +23,26 @@ namespace polee {
 
 namespace {
 
-constexpr int FK_CONSUMER_WARPS = 8;
-constexpr int FK_CONSUMERS = FK_CONSUMER_WARPS * 32;  // 256
-constexpr int FK_THREADS = FK_CONSUMERS + 32;         // + producer warp
-constexpr int FK_STAGES = 2;
-constexpr int FK_SLOT_CAP = 512;                      // partial sums of a tile kept in shared memory
-
-struct FkSmemHead {
-    uint64_t full[FK_STAGES], empty[FK_STAGES];
-    double lpsm[FK_CONSUMER_WARPS][16];
-};
+constexpr int FW_WARPS = 4;  // warps per CTA; every warp streams its own tiles (no CTA-wide barrier anywhere)
 
 __host__ __device__ inline uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
 
-struct FkCarve {
-    uint32_t stage0, blob_cap, w_tile, lrow, slots, total;
+struct FwCarve {
+    uint32_t head, w_tile, xs, lrow, per_warp, total;  // per-warp offsets (the ring sits at 0)
 };
-__host__ __device__ inline FkCarve fk_carve(uint32_t max_blob, uint32_t max_rows, uint32_t max_E, int KP) {
-    FkCarve c;
-    c.stage0 = al128((uint32_t)sizeof(FkSmemHead));
-    c.blob_cap = al128(max_blob);
-    c.w_tile = c.stage0 + FK_STAGES * c.blob_cap;
-    c.lrow = c.w_tile + al128(max_rows * KP * 4u);
-    c.slots = c.lrow + al128(max_E * 2u);
-    c.total = c.slots + FK_SLOT_CAP * KP * 4u;
+// xs = x of the tile's columns during pass A, then the partial-sum slots of pass B (never live together)
+__host__ __device__ inline FwCarve fw_carve(uint32_t ring_bytes, uint32_t max_rows, uint32_t max_E, uint32_t max_C,
+                                            uint32_t max_slots, int KP) {
+    FwCarve c;
+    c.head = 128;  // FW_WARPS x 2 mbarriers
+    c.w_tile = al128(ring_bytes);
+    c.xs = c.w_tile + al128(max_rows * KP * 4u);
+    c.lrow = c.xs + al128((max_C > max_slots ? max_C : max_slots) * KP * 4u);
+    c.per_warp = c.lrow + al128(max_E);
+    c.total = c.head + FW_WARPS * c.per_warp;
     return c;
 }
 
-template <int KP>
-__device__ __forceinline__ void lds_vec(const float *p, float *v) {
-    if constexpr (KP >= 4) {
-#pragma unroll
-        for (int q = 0; q < KP / 4; ++q) {
-            float4 t = reinterpret_cast<const float4 *>(p)[q];
-            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < KP; ++k) v[k] = p[k];
-    }
-}
 template <int KP>
 __device__ __forceinline__ void sts_vec(float *p, const float *v) {
     if constexpr (KP >= 4) {
@@ -75,111 +55,179 @@ __device__ __forceinline__ void sts_vec(float *p, const float *v) {
     }
 }
 
+// KP floats as packed pairs: Blackwell issues two Float32 FMAs per FFMA2 (fma.rn.f32x2), each exactly fmaf
+template <int KP>
+struct Acc {
+    static constexpr int NP = (KP + 1) / 2;
+    float2 v[NP];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) v[i] = make_float2(0.0f, 0.0f);
+    }
+    __device__ __forceinline__ void lds(const float *p) {
+        if constexpr (KP >= 4) {
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q) {
+                const float4 t = reinterpret_cast<const float4 *>(p)[q];
+                v[2 * q] = make_float2(t.x, t.y);
+                v[2 * q + 1] = make_float2(t.z, t.w);
+            }
+        } else if constexpr (KP == 2) {
+            v[0] = *reinterpret_cast<const float2 *>(p);
+        } else {
+            v[0] = make_float2(p[0], 0.0f);
+        }
+    }
+    __device__ __forceinline__ void sts(float *p) const {
+        if constexpr (KP >= 4) {
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q)
+                reinterpret_cast<float4 *>(p)[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+        } else if constexpr (KP == 2) {
+            *reinterpret_cast<float2 *>(p) = v[0];
+        } else {
+            p[0] = v[0].x;
+        }
+    }
+    __device__ __forceinline__ float get(int k) const { return (k & 1) ? v[k >> 1].y : v[k >> 1].x; }
+    // this += s * o   (per element fmaf(s, o, this))
+    __device__ __forceinline__ void fma(float s, const Acc &o) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%0, %1};\n\t"
+                "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+                : "+f"(v[i].x), "+f"(v[i].y)
+                : "f"(s), "f"(o.v[i].x), "f"(o.v[i].y));
+        }
+    }
+};
+
 template <int KP, bool LP, bool WEIGHTED, bool WRITE_W>
-__global__ void __launch_bounds__(FK_THREADS, 2)
+__global__ void __launch_bounds__(FW_WARPS * 32, 4)
     k12_fused(const FusedTileDesc *__restrict__ desc, int n_tiles, const unsigned char *__restrict__ blob,
               const float *__restrict__ xf, float *__restrict__ partial, const float *__restrict__ row_weight,
-              double *__restrict__ lp_partial, float *__restrict__ w_out, float *__restrict__ gslots, uint32_t max_slots,
-              uint32_t max_blob, uint32_t max_rows, uint32_t max_E) {
+              const uint32_t *__restrict__ row_of_pos, double *__restrict__ lp_partial, float *__restrict__ w_out,
+              uint32_t ring_bytes, uint32_t max_rows, uint32_t max_E, uint32_t max_C, uint32_t max_slots) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    FkSmemHead &hd0 = *reinterpret_cast<FkSmemHead *>(smraw);
-    const FkCarve cv = fk_carve(max_blob, max_rows, max_E, KP);
+    const FwCarve cv = fw_carve(ring_bytes, max_rows, max_E, max_C, max_slots, KP);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < FK_STAGES; ++s) {
-            mbar_init(&hd0.full[s], 1);
-            mbar_init(&hd0.empty[s], FK_CONSUMER_WARPS);
-        }
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smraw) + 2 * warp;
+    unsigned char *base = smraw + cv.head + (size_t)warp * cv.per_warp;
+    unsigned char *ring = base;
+    float *w_tile = reinterpret_cast<float *>(base + cv.w_tile);
+    float *xs = reinterpret_cast<float *>(base + cv.xs);
+    uint8_t *lrow = base + cv.lrow;
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();
+    const int nw = gridDim.x * FW_WARPS;
+    int tile = blockIdx.x * FW_WARPS + warp;
+    if (tile >= n_tiles) return;
 
-    if (warp == FK_CONSUMER_WARPS) {
-        // ------------------------------ producer: one bulk copy per tile
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const FusedTileDesc d = desc[tile];
-                const int stage = it % FK_STAGES;
-                mbar_wait(&hd0.empty[stage], ((it / FK_STAGES) & 1) ^ 1);
-                mbar_expect_tx(&hd0.full[stage], d.bytes);
-                bulk_g2s(smraw + cv.stage0 + stage * cv.blob_cap, blob + d.off, d.bytes, &hd0.full[stage]);
-            }
-        }
-        return;
+    // ring state (warp-uniform): the current tile lives at [cur_off, cur_off + cur_bytes)
+    uint32_t cur_off = 0, cur_bytes = 0, phase = 0;  // phase bit b = parity to wait for on bar[b]
+    int cur_bar = 0;
+    FusedTileDesc dn{0, 0, 0};  // descriptor of the next tile, fetched one tile ahead (lane 0)
+    if (lane == 0) {
+        const FusedTileDesc d = desc[tile];
+        mbar_expect_tx(&bar[0], d.bytes);
+        bulk_g2s(ring, blob + d.off, d.bytes, &bar[0]);
+        cur_bytes = d.bytes;
+        if (tile + nw < n_tiles) dn = desc[tile + nw];
     }
+    cur_bytes = __shfl_sync(0xffffffffu, cur_bytes, 0);
 
-    float *w_tile = reinterpret_cast<float *>(smraw + cv.w_tile);
-    uint16_t *lrow_s = reinterpret_cast<uint16_t *>(smraw + cv.lrow);
-    float *sm_slots = reinterpret_cast<float *>(smraw + cv.slots);
-    const uint32_t tid = threadIdx.x;  // 0..255
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int stage = it % FK_STAGES;
-        mbar_wait(&hd0.full[stage], (it / FK_STAGES) & 1);
-        const unsigned char *b = smraw + cv.stage0 + stage * cv.blob_cap;
+    for (;;) {
+        const int next = tile + nw;
+        uint32_t pre = 0, noff = 0, nbytes = 0;
+        if (next < n_tiles) {
+            if (lane == 0) {
+                nbytes = dn.bytes;
+                const uint32_t cand = cur_off + cur_bytes;
+                if (cand + nbytes <= ring_bytes) {
+                    noff = cand;
+                    pre = 1;
+                } else if (nbytes <= cur_off) {
+                    noff = 0;
+                    pre = 1;
+                }
+                if (pre) {
+                    mbar_expect_tx(&bar[cur_bar ^ 1], nbytes);
+                    bulk_g2s(ring + noff, blob + dn.off, nbytes, &bar[cur_bar ^ 1]);
+                }
+            }
+            pre = __shfl_sync(0xffffffffu, pre, 0);
+            noff = __shfl_sync(0xffffffffu, noff, 0);
+            nbytes = __shfl_sync(0xffffffffu, nbytes, 0);
+        }
+        const uint64_t dn_off = dn.off;  // lane 0 only
+        if (lane == 0 && next + nw < n_tiles) dn = desc[next + nw];
+
+        mbar_wait(&bar[cur_bar], (phase >> cur_bar) & 1u);
+        phase ^= 1u << cur_bar;
+        const unsigned char *b = ring + cur_off;
         const FusedHdr hd = *reinterpret_cast<const FusedHdr *>(b);
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.chunks);
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C);
+        const uint32_t *cols = reinterpret_cast<const uint32_t *>(b + L.cols);
         const uint16_t *rowoff = reinterpret_cast<const uint16_t *>(b + L.rowoff);
         const float *val = reinterpret_cast<const float *>(b + L.val);
-        const uint32_t *col = reinterpret_cast<const uint32_t *>(b + L.col);
         const uint16_t *perm = reinterpret_cast<const uint16_t *>(b + L.perm);
         const uint16_t *slot0 = reinterpret_cast<const uint16_t *>(b + L.slot0);
         const uint16_t *cslot = reinterpret_cast<const uint16_t *>(b + L.cslot);
-        float *slots = hd.nslots <= FK_SLOT_CAP ? sm_slots : gslots + (size_t)blockIdx.x * max_slots * KP;
+        const uint8_t *lcol = b + L.lcol;
 
-        // ------------------------------ pass A: p and w of the tile's rows (thread = row)
+        // ------------------------------ x of the tile's columns -> shared memory (the only gather of the tile)
+        for (uint32_t j = lane; j < hd.C; j += 32) {
+            float xv[KP];
+            Vec<KP>::ld(xf + (size_t)cols[j] * KP, xv);
+            sts_vec<KP>(xs + (size_t)j * KP, xv);
+        }
+        __syncwarp();
+
+        // ------------------------------ pass A: p and w of the tile's rows (lane = row; rows sorted longest first)
         double lpv[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) lpv[k] = 0.0;
-        for (uint32_t r = tid; r < hd.rows; r += FK_CONSUMERS) {
-            const uint32_t e0 = rowoff[r], e1 = rowoff[r + 1], len = e1 - e0;
+        for (uint32_t r = lane; r < hd.rows; r += 32) {
+            const uint32_t e0 = rowoff[r], len = rowoff[r + 1] - e0;
+            Acc<KP> facc;
+            facc.zero();
             double acc[KP];
-            float facc[KP];
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                acc[k] = 0.0;
-                facc[k] = 0.0f;
-            }
-            for (uint32_t t0 = 0; t0 < len; t0 += 4) {
-                float xv[4][KP], v[4];
+            for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+            for (uint32_t t = 0; t < len; ++t) {
+                if ((t & 3u) == 0u && t != 0u) {  // every four products the Float32 batch is added to the Float64 row sum
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const bool ok = t0 + u < len;
-                    v[u] = ok ? val[e0 + t0 + u] : 0.0f;
-                    if (ok) {
-                        Vec<KP>::ld(xf + (size_t)col[e0 + t0 + u] * KP, xv[u]);
-                        lrow_s[e0 + t0 + u] = (uint16_t)r;
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < KP; ++k) xv[u][k] = 0.0f;
-                    }
+                    for (int k = 0; k < KP; ++k) acc[k] += (double)facc.get(k);
+                    facc.zero();
                 }
-#pragma unroll
-                for (int k = 0; k < KP; ++k) facc[k] = v[0] * xv[0][k];
-#pragma unroll
-                for (int u = 1; u < 4; ++u)
-#pragma unroll
-                    for (int k = 0; k < KP; ++k) facc[k] = fmaf(v[u], xv[u][k], facc[k]);
-                if (len > 4) {
-#pragma unroll
-                    for (int k = 0; k < KP; ++k) acc[k] += (double)facc[k];
-                }
+                const float v = val[e0 + t];
+                Acc<KP> xv;
+                xv.lds(xs + (size_t)lcol[e0 + t] * KP);
+                lrow[e0 + t] = (uint8_t)r;
+                facc.fma(v, xv);
             }
             float wt = 1.0f;
             if (WEIGHTED) wt = row_weight[hd.row0 + r];
             float wv[KP];
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
-                const float rc = len > 4 ? __frcp_rn((float)acc[k]) : rcp_approx(facc[k]);
-                wv[k] = WEIGHTED ? rc * wt : rc;
-                if (LP) {
-                    const double lg = len > 4 ? log(acc[k]) : log((double)facc[k]);
-                    lpv[k] += WEIGHTED ? lg * (double)wt : lg;
+                float rc;
+                if (len > 4) {
+                    acc[k] += (double)facc.get(k);
+                    rc = __frcp_rn((float)acc[k]);
+                    if (LP) lpv[k] += WEIGHTED ? log(acc[k]) * (double)wt : log(acc[k]);
+                } else {
+                    rc = rcp_approx(facc.get(k));
+                    if (LP) lpv[k] += WEIGHTED ? log((double)facc.get(k)) * (double)wt : log((double)facc.get(k));
                 }
+                wv[k] = WEIGHTED ? rc * wt : rc;
             }
             sts_vec<KP>(w_tile + (size_t)r * KP, wv);
-            if (WRITE_W) Vec<KP>::st(w_out + (size_t)(hd.row0 + r) * KP, wv);
+            if (WRITE_W) Vec<KP>::st(w_out + (size_t)row_of_pos[hd.row0 + r] * KP, wv);
         }
         if (LP) {
 #pragma unroll
@@ -187,55 +235,57 @@ __global__ void __launch_bounds__(FK_THREADS, 2)
                 double v = lpv[k];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) hd0.lpsm[warp][k] = v;
+                if (lane == k) lp_partial[(size_t)tile * KP + k] = v;
             }
         }
-        consumer_bar_sync();
-        if (LP && tid < KP) {
-            double s = 0.0;
-            for (int wi = 0; wi < FK_CONSUMER_WARPS; ++wi) s += hd0.lpsm[wi][tid];
-            lp_partial[(size_t)tile * KP + tid] = s;
-        }
+        __syncwarp();
 
-        // ------------------------------ pass B: column-major walk, one partial sum per (chunk, column) run
-        for (uint32_t c = tid; c < hd.chunks; c += FK_CONSUMERS) {
-            uint32_t slot = slot0[c];
-            const uint32_t q0 = c * FT_CHUNK, q1 = min(hd.E, q0 + FT_CHUNK);
-            float acc[KP];
-#pragma unroll
-            for (int k = 0; k < KP; ++k) acc[k] = 0.0f;
+        // ------------------------------ pass B: lane walks its chunk of the column-major order, one slot per run
+        {
+            const uint32_t q0 = lane * hd.chunk, q1 = min(hd.E, q0 + hd.chunk);
+            uint32_t slot = q0 < hd.E ? slot0[lane] : 0u;
+            Acc<KP> acc;
+            acc.zero();
             for (uint32_t q = q0; q < q1; ++q) {
                 const uint32_t pe = perm[q], e = pe & 0x7fffu;
                 const float v = val[e];
-                float wv[KP];
-                lds_vec<KP>(w_tile + (size_t)lrow_s[e] * KP, wv);
-#pragma unroll
-                for (int k = 0; k < KP; ++k) acc[k] = fmaf(v, wv[k], acc[k]);
+                Acc<KP> wv;
+                wv.lds(w_tile + (size_t)lrow[e] * KP);
+                acc.fma(v, wv);
                 if (pe & 0x8000u) {
-                    if (hd.nslots <= FK_SLOT_CAP) {
-                        sts_vec<KP>(slots + (size_t)slot * KP, acc);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < KP; ++k) slots[(size_t)slot * KP + k] = acc[k];
-                    }
+                    acc.sts(xs + (size_t)slot * KP);
                     ++slot;
-#pragma unroll
-                    for (int k = 0; k < KP; ++k) acc[k] = 0.0f;
+                    acc.zero();
                 }
             }
         }
-        consumer_bar_sync();
+        __syncwarp();
 
-        // ------------------------------ pass C: one (tile, column) partial per distinct column
-        for (uint32_t j = tid / KP; j < hd.C; j += FK_CONSUMERS / KP) {
-            const int k = tid % KP;
-            const uint32_t s0 = cslot[j], s1 = cslot[j + 1];
-            double a = 0.0;
-            for (uint32_t s = s0; s < s1; ++s) a += (double)slots[(size_t)s * KP + k];
-            partial[(size_t)(hd.part0 + j) * KP + k] = (float)a;
+        // ------------------------------ pass C: (tile, column) partial = sum of the column's slots
+        {
+            float *pout = partial + (size_t)hd.part0 * KP;
+            for (uint32_t idx = lane; idx < hd.C * KP; idx += 32) {
+                const uint32_t j = idx / KP, k = idx % KP;
+                const uint32_t s0 = cslot[j], s1 = cslot[j + 1];
+                float a = 0.0f;
+                for (uint32_t sidx = s0; sidx < s1; ++sidx) a += xs[(size_t)sidx * KP + k];
+                pout[idx] = a;
+            }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&hd0.empty[stage]);
+
+        if (next >= n_tiles) break;
+        if (!pre) {  // the next tile did not fit beside this one: load it now
+            if (lane == 0) {
+                mbar_expect_tx(&bar[cur_bar ^ 1], nbytes);
+                bulk_g2s(ring, blob + dn_off, nbytes, &bar[cur_bar ^ 1]);
+            }
+            noff = 0;
+        }
+        cur_off = noff;
+        cur_bytes = nbytes;
+        cur_bar ^= 1;
+        tile = next;
     }
 }
 
@@ -251,6 +301,7 @@ __global__ void __launch_bounds__(256)
     const int grp = lane / KP, k = lane % KP;
     const FusedUnit u = units[unit];
     double a = 0.0;
+#pragma unroll 4
     for (uint32_t i = u.begin + grp; i < u.end; i += G) a += (double)partial[(size_t)plist[i] * KP + k];
 #pragma unroll
     for (int o = 16; o >= KP; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
@@ -278,18 +329,26 @@ __global__ void __launch_bounds__(256)
     if (grp == 0) g[(size_t)mc.col * KP + k] = a;
 }
 
+static uint32_t fused_ring_bytes(const polee_handle *h) {
+    uint32_t ring = std::max<uint32_t>(5120u, al128(h->ft_max_blob));
+    if (const char *e = getenv("POLEE_FUSED_RING")) ring = std::max<uint32_t>(al128((uint32_t)atoi(e)), al128(h->ft_max_blob));
+    return ring;
+}
+
 template <int KP>
 int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, double *lp_partial, float *w_out) {
-    const FkCarve cv = fk_carve(h->ft_max_blob, h->ft_max_rows, h->ft_max_E, KP);
+    const uint32_t ring = fused_ring_bytes(h);
+    const FwCarve cv = fw_carve(ring, h->ft_max_rows, h->ft_max_E, h->ft_max_C, h->ft_max_slots, KP);
     const bool weighted = h->ft_row_weight != nullptr;
-#define FK_LAUNCH(LPF, WF, WW)                                                                                               \
-    do {                                                                                                                     \
-        auto kern = k12_fused<KP, LPF, WF, WW>;                                                                              \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total);              \
-        if (e != cudaSuccess) return h->fail(POLEE_ECUDA, std::string("fused kernel smem: ") + cudaGetErrorString(e));       \
-        kern<<<h->ft_grid, FK_THREADS, cv.total, h->stream>>>(h->ft_desc, h->ft_tiles, h->ft_blob, x, h->ft_partial,         \
-                                                              h->ft_row_weight, lp_partial, w_out, h->ft_gslots,             \
-                                                              h->ft_max_slots, h->ft_max_blob, h->ft_max_rows, h->ft_max_E); \
+#define FK_LAUNCH(LPF, WF, WW)                                                                                              \
+    do {                                                                                                                    \
+        auto kern = k12_fused<KP, LPF, WF, WW>;                                                                             \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total);             \
+        if (e != cudaSuccess) return h->fail(POLEE_ECUDA, std::string("fused kernel smem: ") + cudaGetErrorString(e));      \
+        kern<<<h->ft_grid, FW_WARPS * 32, cv.total, h->stream>>>(h->ft_desc, h->ft_tiles, h->ft_blob, x, h->ft_partial,     \
+                                                                 h->ft_row_weight, h->ft_row_of_pos, lp_partial, w_out,     \
+                                                                 ring, h->ft_max_rows, h->ft_max_E, h->ft_max_C,            \
+                                                                 h->ft_max_slots);                                          \
     } while (0)
     if (w_out) {
         if (weighted) FK_LAUNCH(false, true, true); else FK_LAUNCH(false, false, true);
@@ -312,14 +371,13 @@ int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, dou
 
 }  // namespace
 
-// CTAs for the persistent fused kernel; negative when some tile's partial sums do not fit in shared memory and the
-// per-CTA global spill area is needed
+// CTAs (of FW_WARPS warps) for the persistent fused kernel: as many as shared memory lets an SM hold
 int fused_grid(polee_handle *h, int KP) {
-    const FkCarve cv = fk_carve(h->ft_max_blob, h->ft_max_rows, h->ft_max_E, KP);
-    int per_sm = (int)std::max<uint32_t>(1, std::min<uint32_t>(2, (227u * 1024u) / (cv.total + 1024u)));
+    const FwCarve cv = fw_carve(fused_ring_bytes(h), h->ft_max_rows, h->ft_max_E, h->ft_max_C, h->ft_max_slots, KP);
+    int per_sm = (int)std::max<uint32_t>(1, std::min<uint32_t>(5, (227u * 1024u) / (cv.total + 1024u)));
     if (const char *e = getenv("POLEE_FUSED_CTAS")) per_sm = std::max(1, atoi(e));
-    const int grid = std::max(1, std::min(h->ft_tiles, h->num_sms * per_sm));
-    return h->ft_max_slots > (uint32_t)FK_SLOT_CAP ? -grid : grid;
+    const int ctas_needed = (h->ft_tiles + FW_WARPS - 1) / FW_WARPS;
+    return std::max(1, std::min(ctas_needed, h->num_sms * per_sm));
 }
 
 int launch_fused(polee_handle *h, const float *x, double *g, bool want_lp, double *lp_partial, float *w_out, int KP) {

@@ -121,16 +121,9 @@ __global__ void k_row_weights(const int64_t *__restrict__ ks, int64_t m, const u
 
 
 // ------------------------------------------------------------------ fused row-tile layout (see common.cuh)
-constexpr uint32_t FT_WINDOW = 2048;  // a tile = the rows whose key  row_ptr[i] + FT_ROW_COST * i  falls in one window
-constexpr uint32_t FT_ROW_COST = 7;   // => rows <= FT_WINDOW / 8 = FT_ROWS (non-empty rows), entries < FT_WINDOW + longest row
-
-__device__ __forceinline__ uint64_t tile_key(const uint32_t *row_ptr, int64_t i) {
-    return ((uint64_t)row_ptr[i] + (uint64_t)FT_ROW_COST * (uint64_t)i) / FT_WINDOW;
-}
-
 __global__ void k_tile_flags(const uint32_t *__restrict__ row_ptr, int64_t m, uint32_t *flag) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
-        flag[i] = (i == 0 || tile_key(row_ptr, i) != tile_key(row_ptr, i - 1)) ? 1u : 0u;
+        flag[i] = (i % FT_ROWS == 0 || row_ptr[i] / FT_ENTRY_WINDOW != row_ptr[i - 1] / FT_ENTRY_WINDOW) ? 1u : 0u;
 }
 
 // tile_incl[i] = 1 + tile of row i (inclusive scan of the flags)
@@ -142,9 +135,31 @@ __global__ void k_tile_row0(const uint32_t *__restrict__ flag, const uint32_t *_
     }
 }
 
+// rows of a tile longest first: key = tile << 16 | (0xFFFF - len)
+__global__ void k_row_sort_keys(const uint32_t *__restrict__ tile_incl, const uint32_t *__restrict__ row_len, int64_t m,
+                                uint64_t *keys, uint32_t *vals) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        keys[i] = ((uint64_t)(tile_incl[i] - 1u) << 16) | (uint64_t)(0xFFFFu - min(row_len[i], 0xFFFFu));
+        vals[i] = (uint32_t)i;
+    }
+}
+
+__global__ void k_row_positions(const uint32_t *__restrict__ row_of_pos, const uint32_t *__restrict__ row_len, int64_t m,
+                                uint32_t *rpos, uint32_t *len_sorted) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p <= m; p += (int64_t)gridDim.x * blockDim.x) {
+        if (p == m) {
+            len_sorted[p] = 0;
+            continue;
+        }
+        const uint32_t i = row_of_pos[p];
+        rpos[i] = (uint32_t)p;
+        len_sorted[p] = row_len[i];
+    }
+}
+
 __global__ void k_csc_expand(const uint32_t *__restrict__ colptr, int64_t n, const uint32_t *__restrict__ rowval,
-                             int64_t nnz, const uint32_t *__restrict__ tile_incl, uint32_t *col_of, uint32_t *key_row,
-                             uint32_t *key_tile, uint32_t *val_e) {
+                             int64_t nnz, const uint32_t *__restrict__ tile_incl, const uint32_t *__restrict__ rpos,
+                             uint32_t *col_of, uint32_t *key_row, uint32_t *key_tile, uint32_t *val_e) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
         int64_t lo = 0, hi = n;  // largest j with colptr[j] - 1 <= e
         while (hi - lo > 1) {
@@ -156,7 +171,7 @@ __global__ void k_csc_expand(const uint32_t *__restrict__ colptr, int64_t n, con
         }
         const uint32_t r = rowval[e] - 1u;
         col_of[e] = (uint32_t)lo;
-        key_row[e] = r;
+        key_row[e] = rpos[r];
         key_tile[e] = tile_incl[r] - 1u;
         val_e[e] = (uint32_t)e;
     }
@@ -167,37 +182,28 @@ __global__ void k_inverse_perm(const uint32_t *__restrict__ a_csc, int64_t nnz, 
         apos_of_csc[a_csc[a]] = (uint32_t)a;
 }
 
-// column-major (within tile) order: column and row-major position of every entry
-__global__ void k_b_gather(const uint32_t *__restrict__ b_csc, int64_t nnz, const uint32_t *__restrict__ col_of,
-                           const uint32_t *__restrict__ apos_of_csc, uint32_t *colB, uint32_t *aposB) {
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t e = b_csc[q];
-        colB[q] = col_of[e];
-        aposB[q] = apos_of_csc[e];
-    }
-}
-
-__global__ void k_b_flags(const uint32_t *__restrict__ tileB, const uint32_t *__restrict__ colB, int64_t nnz,
-                          const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ tile_row0, uint32_t *flagB,
-                          uint32_t *colstart) {
+// column-major (within tile) order: slot flags and column starts (+ zero sentinels at nnz for the exclusive scans)
+__global__ void k_b_flags(const uint32_t *__restrict__ tileB, const uint32_t *__restrict__ b_csc, int64_t nnz,
+                          const uint32_t *__restrict__ col_of, const uint32_t *__restrict__ row_ptr,
+                          const uint32_t *__restrict__ tile_row0, uint32_t *flagB, uint32_t *colstart) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q <= nnz; q += (int64_t)gridDim.x * blockDim.x) {
-        if (q == nnz) {  // sentinel for the exclusive scans
+        if (q == nnz) {
             flagB[q] = 0;
             colstart[q] = 0;
             continue;
         }
         const uint32_t t = tileB[q];
         const uint32_t a0 = row_ptr[tile_row0[t]], a1 = row_ptr[tile_row0[t + 1]];
-        const uint32_t qq = (uint32_t)q - a0, c = colB[q];
+        const uint32_t qq = (uint32_t)q - a0, chunk = (a1 - a0 + 31u) / 32u, c = col_of[b_csc[q]];
         const bool last = (uint32_t)q == a1 - 1u;
-        flagB[q] = (qq % FT_CHUNK == FT_CHUNK - 1 || last || colB[q + 1] != c) ? 1u : 0u;
-        colstart[q] = (qq == 0 || colB[q - 1] != c) ? 1u : 0u;
+        flagB[q] = ((qq + 1u) % chunk == 0u || last || col_of[b_csc[q + 1]] != c) ? 1u : 0u;
+        colstart[q] = (qq == 0u || col_of[b_csc[q - 1]] != c) ? 1u : 0u;
     }
 }
 
 __global__ void k_tile_meta(uint32_t n_tiles, const uint32_t *__restrict__ tile_row0, const uint32_t *__restrict__ row_ptr,
                             const uint32_t *__restrict__ runs_before, const uint32_t *__restrict__ cols_before,
-                            FusedHdr *hdrs, uint64_t *blob_bytes, uint32_t *maxima /* E, slots, rows, bytes */) {
+                            FusedHdr *hdrs, uint64_t *blob_bytes, uint32_t *maxima /* E, C, rows, bytes, slots */) {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
         const uint32_t row0 = tile_row0[t], row1 = tile_row0[t + 1];
         const uint32_t a0 = row_ptr[row0], a1 = row_ptr[row1];
@@ -208,15 +214,16 @@ __global__ void k_tile_meta(uint32_t n_tiles, const uint32_t *__restrict__ tile_
         hd.nslots = runs_before[a1] - runs_before[a0];
         hd.row0 = row0;
         hd.part0 = cols_before[a0];
-        hd.chunks = (hd.E + FT_CHUNK - 1) / FT_CHUNK;
+        hd.chunk = (hd.E + 31u) / 32u;
         hd.pad = 0;
         hdrs[t] = hd;
-        const uint32_t bytes = blob_layout(hd.rows, hd.E, hd.C, hd.chunks).bytes;
+        const uint32_t bytes = blob_layout(hd.rows, hd.E, hd.C).bytes;
         blob_bytes[t] = bytes;
         atomicMax(&maxima[0], hd.E);
-        atomicMax(&maxima[1], hd.nslots);
+        atomicMax(&maxima[1], hd.C);
         atomicMax(&maxima[2], hd.rows);
         atomicMax(&maxima[3], bytes);
+        atomicMax(&maxima[4], hd.nslots);
     }
 }
 
@@ -228,55 +235,59 @@ __global__ void k_tile_desc(uint32_t n_tiles, const FusedHdr *__restrict__ hdrs,
     }
 }
 
-__global__ void k_pack_rows(int64_t m, const uint32_t *__restrict__ tile_incl, const uint32_t *__restrict__ row_ptr,
-                            const FusedHdr *__restrict__ hdrs, const uint64_t *__restrict__ blob_off, unsigned char *blob) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t t = tile_incl[i] - 1u;
+// p = row position (rows of a tile sorted longest first)
+__global__ void k_pack_rows(int64_t m, const uint32_t *__restrict__ row_of_pos, const uint32_t *__restrict__ tile_incl,
+                            const uint32_t *__restrict__ row_ptr, const FusedHdr *__restrict__ hdrs,
+                            const uint64_t *__restrict__ blob_off, unsigned char *blob) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t t = tile_incl[row_of_pos[p]] - 1u;
         const FusedHdr hd = hdrs[t];
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.chunks);
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C);
         uint16_t *rowoff = reinterpret_cast<uint16_t *>(blob + blob_off[t] + L.rowoff);
         const uint32_t a0 = row_ptr[hd.row0];
-        rowoff[i - hd.row0] = (uint16_t)(row_ptr[i] - a0);
-        if (i == (int64_t)hd.row0 + hd.rows - 1) rowoff[hd.rows] = (uint16_t)hd.E;
+        rowoff[p - hd.row0] = (uint16_t)(row_ptr[p] - a0);
+        if (p == (int64_t)hd.row0 + hd.rows - 1) rowoff[hd.rows] = (uint16_t)hd.E;
     }
 }
 
-__global__ void k_pack_a(int64_t nnz, const uint32_t *__restrict__ rowA, const uint32_t *__restrict__ a_csc,
-                         const uint32_t *__restrict__ tile_incl, const uint32_t *__restrict__ row_ptr,
-                         const FusedHdr *__restrict__ hdrs, const uint64_t *__restrict__ blob_off,
-                         const uint32_t *__restrict__ col_of, const float *__restrict__ nzval, unsigned char *blob) {
+__global__ void k_pack_a(int64_t nnz, const uint32_t *__restrict__ posA, const uint32_t *__restrict__ a_csc,
+                         const uint32_t *__restrict__ row_of_pos, const uint32_t *__restrict__ tile_incl,
+                         const uint32_t *__restrict__ row_ptr, const FusedHdr *__restrict__ hdrs,
+                         const uint64_t *__restrict__ blob_off, const float *__restrict__ nzval, unsigned char *blob) {
     for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nnz; a += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t t = tile_incl[rowA[a]] - 1u;
+        const uint32_t t = tile_incl[row_of_pos[posA[a]]] - 1u;
         const FusedHdr hd = hdrs[t];
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.chunks);
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C);
         unsigned char *b = blob + blob_off[t];
         const uint32_t e = (uint32_t)a - row_ptr[hd.row0];
-        const uint32_t src = a_csc[a];
-        reinterpret_cast<float *>(b + L.val)[e] = nzval[src];
-        reinterpret_cast<uint32_t *>(b + L.col)[e] = col_of[src];
+        reinterpret_cast<float *>(b + L.val)[e] = nzval[a_csc[a]];
     }
 }
 
-__global__ void k_pack_b(int64_t nnz, const uint32_t *__restrict__ tileB, const uint32_t *__restrict__ colB,
-                         const uint32_t *__restrict__ aposB, const uint32_t *__restrict__ flagB,
-                         const uint32_t *__restrict__ colstart, const uint32_t *__restrict__ runs_before,
-                         const uint32_t *__restrict__ cols_before, const uint32_t *__restrict__ row_ptr,
-                         const FusedHdr *__restrict__ hdrs, const uint64_t *__restrict__ blob_off, unsigned char *blob,
-                         uint32_t *part_col) {
+__global__ void k_pack_b(int64_t nnz, const uint32_t *__restrict__ tileB, const uint32_t *__restrict__ b_csc,
+                         const uint32_t *__restrict__ apos_of_csc, const uint32_t *__restrict__ col_of,
+                         const uint32_t *__restrict__ flagB, const uint32_t *__restrict__ colstart,
+                         const uint32_t *__restrict__ runs_before, const uint32_t *__restrict__ cols_before,
+                         const uint32_t *__restrict__ row_ptr, const FusedHdr *__restrict__ hdrs,
+                         const uint64_t *__restrict__ blob_off, unsigned char *blob, uint32_t *part_col) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t t = tileB[q];
         const FusedHdr hd = hdrs[t];
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.chunks);
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C);
         unsigned char *b = blob + blob_off[t];
         const uint32_t a0 = row_ptr[hd.row0];
         const uint32_t qq = (uint32_t)q - a0;
-        const uint32_t run = runs_before[q] - runs_before[a0];
-        reinterpret_cast<uint16_t *>(b + L.perm)[qq] = (uint16_t)((aposB[q] - a0) | (flagB[q] << 15));
-        if (qq % FT_CHUNK == 0) reinterpret_cast<uint16_t *>(b + L.slot0)[qq / FT_CHUNK] = (uint16_t)run;
+        const uint32_t src = b_csc[q];
+        const uint32_t e = apos_of_csc[src] - a0;
+        const uint32_t pid = cols_before[q] + colstart[q] - 1u;  // (tile, column) run containing q
+        const uint32_t run = runs_before[q] - runs_before[a0];   // slots emitted before q in this tile
+        reinterpret_cast<uint16_t *>(b + L.perm)[qq] = (uint16_t)(e | (flagB[q] << 15));
+        (b + L.lcol)[e] = (unsigned char)(pid - hd.part0);
+        if (qq % hd.chunk == 0u) reinterpret_cast<uint16_t *>(b + L.slot0)[qq / hd.chunk] = (uint16_t)run;
         if (colstart[q]) {
-            const uint32_t pid = cols_before[q];
             reinterpret_cast<uint16_t *>(b + L.cslot)[pid - hd.part0] = (uint16_t)run;
-            part_col[pid] = colB[q];
+            reinterpret_cast<uint32_t *>(b + L.cols)[pid - hd.part0] = col_of[src];
+            part_col[pid] = col_of[src];
         }
         if (qq == hd.E - 1u) reinterpret_cast<uint16_t *>(b + L.cslot)[hd.C] = (uint16_t)hd.nslots;
     }
@@ -292,9 +303,9 @@ __global__ void k_count_keys(const uint32_t *__restrict__ keys, int64_t count, u
         atomicAdd(&cnt[keys[i]], 1u);
 }
 
-__global__ void k_ks_to_f32(const int64_t *__restrict__ ks, int64_t m, float *out) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = (float)ks[i];
+__global__ void k_ks_to_f32(const int64_t *__restrict__ ks, const uint32_t *__restrict__ row_of_pos, int64_t m, float *out) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m; p += (int64_t)gridDim.x * blockDim.x)
+        out[p] = (float)ks[row_of_pos[p]];
 }
 
 int bits_for(uint64_t maxval) {
@@ -349,7 +360,8 @@ struct PhaseTimer {
 
 void release_fused(polee_handle *h) {
     polee::dfree(h->ft_blob); polee::dfree(h->ft_desc); polee::dfree(h->ft_plist); polee::dfree(h->ft_units);
-    polee::dfree(h->ft_multi); polee::dfree(h->ft_row_weight);
+    polee::dfree(h->ft_multi); polee::dfree(h->ft_row_weight); polee::dfree(h->ft_row_of_pos);
+    h->ft_row_of_pos = nullptr;
     h->ft_blob = nullptr; h->ft_desc = nullptr; h->ft_plist = nullptr; h->ft_units = nullptr; h->ft_multi = nullptr;
     h->ft_row_weight = nullptr;
     h->fused = false;
@@ -400,16 +412,32 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     CK(cudaMemcpyAsync(&n_tiles, tile_incl + (m - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (bad) return h->fail(POLEE_EINVAL, "set_matrix: rowval out of range 1..m");
-    if ((uint64_t)lmax + FT_WINDOW > (uint64_t)FT_MAX_E) return POLEE_OK;  // a row too long for 15-bit tile offsets
+    if ((uint64_t)lmax + FT_ENTRY_WINDOW > (uint64_t)FT_MAX_E) return POLEE_OK;  // a row too long for 15-bit tile offsets
+    auto unsuitable = [&]() { release_fused(h); return (int)POLEE_OK; };
     pt.mark("fused: rows + tiles");
     uint32_t *tile_row0;
     CK(sc.alloc(&tile_row0, (size_t)n_tiles + 1));
     k_tile_row0<<<grid_for(m), TPB, 0, st>>>(flag, tile_incl, m, n_tiles, tile_row0);
 
+    // ---- rows of every tile longest first; row pointers in that order
+    uint64_t *rkey, *rkey_s;
+    uint32_t *rval, *rpos, *len_sorted;
+    CK(sc.alloc(&rkey, m)); CK(sc.alloc(&rkey_s, m)); CK(sc.alloc(&rval, m)); CK(sc.alloc(&rpos, m)); CK(sc.alloc(&len_sorted, m + 1));
+    CK(polee::dmalloc((void **)&h->ft_row_of_pos, sizeof(uint32_t) * m));
+    k_row_sort_keys<<<grid_for(m), TPB, 0, st>>>(tile_incl, row_len, m, rkey, rval);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, rkey, rkey_s, rval, h->ft_row_of_pos, (int)m, 0, 64, st));
+    CK(ensure_tmp(need));
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, rkey, rkey_s, rval, h->ft_row_of_pos, (int)m, 0,
+                                       16 + bits_for((uint64_t)n_tiles), st));
+    k_row_positions<<<grid_for(m + 1), TPB, 0, st>>>(h->ft_row_of_pos, row_len, m, rpos, len_sorted);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, len_sorted, row_ptr, (int)(m + 1), st));
+    CK(ensure_tmp(need));
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, len_sorted, row_ptr, (int)(m + 1), st));
+
     // ---- the two entry orders: row-major (A) and column-major inside a tile (B)
-    uint32_t *col_of, *keyR, *keyT, *valE, *rowA, *a_csc, *tileB, *b_csc, *apos_of_csc;
-    CK(sc.alloc(&col_of, nnz)); CK(sc.alloc(&keyR, nnz)); CK(sc.alloc(&keyT, nnz)); CK(sc.alloc(&valE, nnz));
-    CK(sc.alloc(&rowA, nnz)); CK(sc.alloc(&a_csc, nnz)); CK(sc.alloc(&tileB, nnz)); CK(sc.alloc(&b_csc, nnz));
+    uint32_t *col_of, *keyR, *keyT, *valE, *posA, *a_csc, *tileB, *b_csc, *apos_of_csc;
+    CK(sc.alloc(&col_of, nnz + 1)); CK(sc.alloc(&keyR, nnz)); CK(sc.alloc(&keyT, nnz)); CK(sc.alloc(&valE, nnz));
+    CK(sc.alloc(&posA, nnz)); CK(sc.alloc(&a_csc, nnz)); CK(sc.alloc(&tileB, nnz)); CK(sc.alloc(&b_csc, nnz + 1));
     CK(sc.alloc(&apos_of_csc, nnz));
     uint32_t *d_colptr_own = nullptr;
     if (!d_colptr) {
@@ -418,20 +446,18 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
         d_colptr = d_colptr_own;
     }
     if (nnz > 0) {
-        k_csc_expand<<<grid_for(nnz), TPB, 0, st>>>(d_colptr, n, d_rowval, nnz, tile_incl, col_of, keyR, keyT, valE);
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, keyR, rowA, valE, a_csc, (int)nnz, 0, 32, st));
+        k_csc_expand<<<grid_for(nnz), TPB, 0, st>>>(d_colptr, n, d_rowval, nnz, tile_incl, rpos, col_of, keyR, keyT, valE);
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, keyR, posA, valE, a_csc, (int)nnz, 0, 32, st));
         CK(ensure_tmp(need));
-        CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, keyR, rowA, valE, a_csc, (int)nnz, 0, bits_for((uint64_t)m), st));
+        CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, keyR, posA, valE, a_csc, (int)nnz, 0, bits_for((uint64_t)m), st));
         CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, keyT, tileB, valE, b_csc, (int)nnz, 0, bits_for((uint64_t)n_tiles), st));
         k_inverse_perm<<<grid_for(nnz), TPB, 0, st>>>(a_csc, nnz, apos_of_csc);
     }
-    pt.mark("fused: two entry sorts");
-    uint32_t *colB = keyR, *aposB = keyT;  // the sort inputs are free again
+    pt.mark("fused: row sort + two entry sorts");
     uint32_t *flagB, *colstart, *runs_before, *cols_before;
     CK(sc.alloc(&flagB, nnz + 1)); CK(sc.alloc(&colstart, nnz + 1)); CK(sc.alloc(&runs_before, nnz + 1));
     CK(sc.alloc(&cols_before, nnz + 1));
-    if (nnz > 0) k_b_gather<<<grid_for(nnz), TPB, 0, st>>>(b_csc, nnz, col_of, apos_of_csc, colB, aposB);
-    k_b_flags<<<grid_for(nnz + 1), TPB, 0, st>>>(tileB, colB, nnz, row_ptr, tile_row0, flagB, colstart);
+    k_b_flags<<<grid_for(nnz + 1), TPB, 0, st>>>(tileB, b_csc, nnz, col_of, row_ptr, tile_row0, flagB, colstart);
     CK(cub::DeviceScan::ExclusiveSum(nullptr, need, flagB, runs_before, (int)(nnz + 1), st));
     CK(ensure_tmp(need));
     CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, flagB, runs_before, (int)(nnz + 1), st));
@@ -442,17 +468,17 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     uint64_t *blob_bytes, *blob_off;
     uint32_t *d_max;
     CK(sc.alloc(&hdrs, n_tiles)); CK(sc.alloc(&blob_bytes, (size_t)n_tiles + 1)); CK(sc.alloc(&blob_off, (size_t)n_tiles + 1));
-    CK(sc.alloc(&d_max, 4));
-    CK(cudaMemsetAsync(d_max, 0, 16, st));
+    CK(sc.alloc(&d_max, 8));
+    CK(cudaMemsetAsync(d_max, 0, 32, st));
     CK(cudaMemsetAsync(blob_bytes, 0, sizeof(uint64_t) * ((size_t)n_tiles + 1), st));
     k_tile_meta<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, tile_row0, row_ptr, runs_before, cols_before, hdrs, blob_bytes, d_max);
     CK(cub::DeviceScan::ExclusiveSum(nullptr, need, blob_bytes, blob_off, (int)(n_tiles + 1), st));
     CK(ensure_tmp(need));
     CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, blob_bytes, blob_off, (int)(n_tiles + 1), st));
-    uint32_t maxima[4];
+    uint32_t maxima[8];
     uint64_t total_bytes = 0;
     uint32_t n_parts = 0;
-    CK(cudaMemcpyAsync(maxima, d_max, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(maxima, d_max, 32, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&total_bytes, blob_off + n_tiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&n_parts, cols_before + nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -461,8 +487,9 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     // with rows in random order they would outweigh the matrix itself
     const char *force = getenv("POLEE_LAYOUT");
     const bool forced = force && std::string(force) == "fused";
-    if (!forced && (double)n_parts * 64.0 > 0.35 * (double)total_bytes) return POLEE_OK;
-    if (maxima[3] > 64u * 1024u) return POLEE_OK;  // a tile must fit a shared-memory stage
+    if (!forced && (double)n_parts * 64.0 > 0.35 * (double)total_bytes) return unsuitable();
+    if (maxima[3] > 40u * 1024u) return unsuitable();  // a tile must fit a warp's shared-memory ring
+    if (maxima[1] > FT_MAX_C) return unsuitable();     // local column ids are 8 bits
 
     CK(polee::dmalloc((void **)&h->ft_blob, std::max<uint64_t>(total_bytes, 16)));
     CK(polee::dmalloc((void **)&h->ft_desc, sizeof(FusedTileDesc) * std::max<uint32_t>(n_tiles, 1)));
@@ -472,12 +499,12 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     CK(sc.alloc(&col_cnt, n));
     CK(polee::dmalloc((void **)&h->ft_plist, sizeof(uint32_t) * std::max<uint32_t>(n_parts, 1)));
     k_tile_desc<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, hdrs, blob_off, blob_bytes, h->ft_desc, h->ft_blob);
-    k_pack_rows<<<grid_for(m), TPB, 0, st>>>(m, tile_incl, row_ptr, hdrs, blob_off, h->ft_blob);
+    k_pack_rows<<<grid_for(m), TPB, 0, st>>>(m, h->ft_row_of_pos, tile_incl, row_ptr, hdrs, blob_off, h->ft_blob);
     if (vals_ready_or_null) CK(cudaStreamWaitEvent(st, vals_ready_or_null, 0));
     if (nnz > 0) {
-        k_pack_a<<<grid_for(nnz), TPB, 0, st>>>(nnz, rowA, a_csc, tile_incl, row_ptr, hdrs, blob_off, col_of, d_nzval, h->ft_blob);
-        k_pack_b<<<grid_for(nnz), TPB, 0, st>>>(nnz, tileB, colB, aposB, flagB, colstart, runs_before, cols_before, row_ptr,
-                                                 hdrs, blob_off, h->ft_blob, part_col);
+        k_pack_a<<<grid_for(nnz), TPB, 0, st>>>(nnz, posA, a_csc, h->ft_row_of_pos, tile_incl, row_ptr, hdrs, blob_off, d_nzval, h->ft_blob);
+        k_pack_b<<<grid_for(nnz), TPB, 0, st>>>(nnz, tileB, b_csc, apos_of_csc, col_of, flagB, colstart, runs_before, cols_before,
+                                                 row_ptr, hdrs, blob_off, h->ft_blob, part_col);
     }
     pt.mark("fused: pack blobs");
     // ---- second stage work list: partial ids by column
@@ -515,13 +542,13 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
         CK(cudaMemcpyAsync(h->ft_multi, multi.data(), sizeof(FusedMulti) * multi.size(), cudaMemcpyHostToDevice, st));
     if (d_ks) {
         CK(polee::dmalloc((void **)&h->ft_row_weight, sizeof(float) * m));
-        k_ks_to_f32<<<grid_for(m), TPB, 0, st>>>(d_ks, m, h->ft_row_weight);
+        k_ks_to_f32<<<grid_for(m), TPB, 0, st>>>(d_ks, h->ft_row_of_pos, m, h->ft_row_weight);
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     pt.mark("fused: second-stage list");
     h->ft_tiles = (int)n_tiles;
-    h->ft_max_E = maxima[0]; h->ft_max_slots = maxima[1]; h->ft_max_rows = maxima[2]; h->ft_max_blob = maxima[3];
+    h->ft_max_E = maxima[0]; h->ft_max_C = maxima[1]; h->ft_max_rows = maxima[2]; h->ft_max_blob = maxima[3]; h->ft_max_slots = maxima[4];
     h->ft_blob_bytes = total_bytes;
     h->ft_parts = n_parts;
     h->ft_nunits = (int)units.size();
@@ -529,9 +556,9 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     h->ft_nlvl2 = (int)lvl2;
     h->fused = true;
     if (getenv("POLEE_SETUP_TIMING"))
-        fprintf(stderr, "[polee setup] fused: %u tiles, %.1f MB blobs (%.2f B/entry), %u partials, %zu units, %zu multi, max E %u slots %u rows %u blob %u\n",
+        fprintf(stderr, "[polee setup] fused: %u tiles, %.1f MB blobs (%.2f B/entry), %u partials, %zu units, %zu multi, max E %u C %u rows %u blob %u slots %u\n",
                 n_tiles, total_bytes / 1e6, nnz ? (double)total_bytes / nnz : 0.0, n_parts, units.size(), multi.size(),
-                maxima[0], maxima[1], maxima[2], maxima[3]);
+                maxima[0], maxima[1], maxima[2], maxima[3], maxima[4]);
     return POLEE_OK;
 }
 

@@ -610,9 +610,9 @@ __global__ void k3_elbo(int K, int KP, const double *__restrict__ lp, const doub
 
 void release_work_buffers(polee_handle *h) {
     void *ptrs[] = {h->zs0, h->zs, h->ys, h->ygrad, h->us, h->G, h->root_us, h->root_G, h->x, h->xd, h->w, h->g, h->seg_partial, h->S_partial,
-                    h->S, h->lp_partial, h->ladj_partial, h->grad_out, h->ft_partial, h->ft_lvl2, h->ft_gslots};
+                    h->S, h->lp_partial, h->ladj_partial, h->grad_out, h->ft_partial, h->ft_lvl2};
     for (void *p : ptrs) polee::dfree(p);
-    h->ft_partial = nullptr; h->ft_lvl2 = nullptr; h->ft_gslots = nullptr;
+    h->ft_partial = nullptr; h->ft_lvl2 = nullptr;
     h->zs0 = h->zs = nullptr; h->ys = h->ygrad = h->us = nullptr; h->G = nullptr; h->x = h->w = nullptr; h->xd = nullptr; h->root_us = nullptr; h->root_G = nullptr;
     h->g = h->seg_partial = h->S_partial = h->S = h->lp_partial = h->ladj_partial = nullptr;
     h->grad_out = nullptr;
@@ -657,10 +657,6 @@ int ensure_work_buffers(polee_handle *h, int KP) {
             CK(polee::dmalloc((void **)&h->ft_partial, sizeof(float) * std::max<int64_t>(h->ft_parts, 1) * KP));
             CK(polee::dmalloc((void **)&h->ft_lvl2, sizeof(double) * std::max(h->ft_nlvl2, 1) * KP));
             h->ft_grid = fused_grid(h, KP);
-            if (h->ft_grid < 0) {  // tiles with more partial sums than fit in shared memory spill them to a per-CTA global area
-                h->ft_grid = -h->ft_grid;
-                CK(polee::dmalloc((void **)&h->ft_gslots, sizeof(float) * (size_t)h->ft_grid * h->ft_max_slots * KP));
-            }
         }
     }
     h->work_KP = KP;
