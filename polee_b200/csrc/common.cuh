@@ -42,26 +42,26 @@ struct RowTile {
 };
 
 // ---- fused likelihood layout ("row tiles"): K1 and K2 in one pass over the matrix.
-// A tile is a run of <= FT_ROWS consecutive rows (and < FT_ENTRY_WINDOW + longest-row entries), processed by ONE warp;
-// inside a tile the rows are re-ordered longest first (lanes of a warp then run the same trip counts).  The entries
-// are stored once, row-major, with a 16-bit permutation that enumerates them column-major, so the warp can compute
-// p = X x for its rows and then the tile's contribution to X^T (1/p) without w ever leaving the SM.  Everything a
-// tile needs travels as one 16-byte aligned blob (one bulk copy):
-//   header | cols u32[C] | rowoff u16[rows+1] | val f32[E] | perm u16[E] | slot0 u16[32] | cslot u16[C+1] | lcol u8[E]
+// A tile is a run of <= FT_ROWS consecutive rows (and < FT_ENTRY_WINDOW + longest-row entries), processed by one CTA;
+// inside a tile the rows are re-ordered longest first (the lanes of a warp then run the same trip counts).  The
+// entries are stored once, row-major, with a 16-bit permutation that enumerates them column-major, so the CTA can
+// compute p = X x for its rows and then the tile's contribution to X^T (1/p) without w ever leaving the SM.
+// Everything a tile needs travels as one 16-byte aligned blob (one bulk copy):
+//   header | cols u32[C] | rowoff u16[rows+1] | val f32[E] | perm u16[E] | segptr u16[S+1] | lcol u8[E]
 // cols = the tile's C distinct columns (a local dictionary, C <= 255: x of these columns is staged in shared memory
-// once per tile); lcol[e] = local column of row-major entry e; perm[q] = (row-major index of the q-th column-major
-// entry) | flag << 15.  Column sums: lane l walks the column-major entries [l * chunk, (l + 1) * chunk) sequentially
-// and emits a partial sum ("slot") wherever flag is set (= the column changes or its chunk ends); slot0[l] = index of
-// lane l's first slot, cslot[j] = first slot of local column j.  7 bytes per entry instead of the 16 the split
-// layouts stream (8 in K1 + 8 in K2).
-constexpr int FT_ROWS = 64;
-constexpr uint32_t FT_ENTRY_WINDOW = 512;
+// once per tile); lcol[e] = local column of row-major entry e; perm[q] = row-major index of the q-th column-major
+// entry.  The column-major list is cut into S segments of <= FT_SEG entries of one column (segptr); one warp sums one
+// segment and writes one partial, the second stage adds the partials of a column over all tiles.  7 bytes per entry
+// instead of the 16 the split layouts stream (8 in K1 + 8 in K2).
+constexpr int FT_ROWS = 512;
+constexpr uint32_t FT_ENTRY_WINDOW = 4096;
+constexpr uint32_t FT_SEG = 128;
 constexpr uint32_t FT_MAX_C = 255;
 constexpr int FT_MAX_E = 32767;
 struct FusedHdr {
-    uint32_t rows, E, C, nslots;  // rows, entries, distinct columns, partial sums ("slots") of the tile
-    uint32_t row0, part0;         // first row position; index of the tile's first (tile, column) partial
-    uint32_t chunk, pad;          // column-major entries per lane = ceil(E / 32)
+    uint32_t rows, E, C, S;  // rows, entries, distinct columns, column segments of the tile
+    uint32_t row0, part0;    // first row position; index of the tile's first partial (= first segment)
+    uint32_t pad0, pad1;
 };
 struct FusedTileDesc {
     uint64_t off;    // byte offset of the blob
@@ -69,17 +69,16 @@ struct FusedTileDesc {
     uint32_t pad;
 };
 struct BlobLayout {
-    uint32_t cols, rowoff, val, perm, slot0, cslot, lcol, bytes;
+    uint32_t cols, rowoff, val, perm, segptr, lcol, bytes;
 };
-__host__ __device__ inline BlobLayout blob_layout(uint32_t rows, uint32_t E, uint32_t C) {
+__host__ __device__ inline BlobLayout blob_layout(uint32_t rows, uint32_t E, uint32_t C, uint32_t S) {
     BlobLayout L;
     L.cols = (uint32_t)sizeof(FusedHdr);
     L.rowoff = L.cols + ((C * 4u + 15u) & ~15u);
     L.val = L.rowoff + (((rows + 1u) * 2u + 15u) & ~15u);
     L.perm = L.val + ((E * 4u + 15u) & ~15u);
-    L.slot0 = L.perm + ((E * 2u + 15u) & ~15u);
-    L.cslot = L.slot0 + 64u;
-    L.lcol = L.cslot + (((C + 1u) * 2u + 15u) & ~15u);
+    L.segptr = L.perm + ((E * 2u + 15u) & ~15u);
+    L.lcol = L.segptr + (((S + 1u) * 2u + 15u) & ~15u);
     L.bytes = L.lcol + ((E + 15u) & ~15u);
     return L;
 }

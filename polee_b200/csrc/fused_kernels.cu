@@ -23,25 +23,27 @@ namespace polee {
 
 namespace {
 
-constexpr int FW_WARPS = 4;  // warps per CTA; every warp streams its own tiles (no CTA-wide barrier anywhere)
+constexpr int FC_WARPS = 8;
+constexpr int FC_THREADS = FC_WARPS * 32;
 
 __host__ __device__ inline uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
 
-struct FwCarve {
-    uint32_t head, w_tile, xs, lrow, per_warp, total;  // per-warp offsets (the ring sits at 0)
+struct FcCarve {
+    uint32_t ring, w_tile, x_loc, lrow, total;  // byte offsets; [0, ring) = control block
 };
-// xs = x of the tile's columns during pass A, then the partial-sum slots of pass B (never live together)
-__host__ __device__ inline FwCarve fw_carve(uint32_t ring_bytes, uint32_t max_rows, uint32_t max_E, uint32_t max_C,
-                                            uint32_t max_slots, int KP) {
-    FwCarve c;
-    c.head = 128;  // FW_WARPS x 2 mbarriers
-    c.w_tile = al128(ring_bytes);
-    c.xs = c.w_tile + al128(max_rows * KP * 4u);
-    c.lrow = c.xs + al128((max_C > max_slots ? max_C : max_slots) * KP * 4u);
-    c.per_warp = c.lrow + al128(max_E);
-    c.total = c.head + FW_WARPS * c.per_warp;
+__host__ __device__ inline FcCarve fc_carve(uint32_t ring_bytes, uint32_t max_rows, uint32_t max_E, uint32_t max_C, int KP) {
+    FcCarve c;
+    c.ring = 128;
+    c.w_tile = c.ring + al128(ring_bytes);
+    c.x_loc = c.w_tile + al128(max_rows * KP * 4u);
+    c.lrow = c.x_loc + al128(max_C * KP * 4u);
+    c.total = c.lrow + al128(max_E * 2u);
     return c;
 }
+
+struct FcCtl {  // shared control block
+    uint64_t bar[2];
+};
 
 template <int KP>
 __device__ __forceinline__ void sts_vec(float *p, const float *v) {
@@ -78,17 +80,6 @@ struct Acc {
             v[0] = make_float2(p[0], 0.0f);
         }
     }
-    __device__ __forceinline__ void sts(float *p) const {
-        if constexpr (KP >= 4) {
-#pragma unroll
-            for (int q = 0; q < KP / 4; ++q)
-                reinterpret_cast<float4 *>(p)[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
-        } else if constexpr (KP == 2) {
-            *reinterpret_cast<float2 *>(p) = v[0];
-        } else {
-            p[0] = v[0].x;
-        }
-    }
     __device__ __forceinline__ float get(int k) const { return (k & 1) ? v[k >> 1].y : v[k >> 1].x; }
     // this += s * o   (per element fmaf(s, o, this))
     __device__ __forceinline__ void fma(float s, const Acc &o) {
@@ -100,131 +91,188 @@ struct Acc {
                 : "f"(s), "f"(o.v[i].x), "f"(o.v[i].y));
         }
     }
+    __device__ __forceinline__ void add(const Acc &o) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            v[i].x += o.v[i].x;
+            v[i].y += o.v[i].y;
+        }
+    }
 };
 
+// Sum acc[0..KP) over the 32 lanes and store the KP totals to out[0..KP).  KP == 8: reduce-scatter (9 shuffles
+// instead of 40); other KP: plain butterflies, lane 0 stores.  Fixed order => deterministic.
+template <int KP>
+__device__ __forceinline__ void warp_reduce_store(float (&acc)[KP], int lane, float *__restrict__ out) {
+    if constexpr (KP == 8) {
+        float a4[4], a2[2], a1;
+        const bool h16 = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = h16 ? acc[i] : acc[i + 4];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+            a4[i] = (h16 ? acc[i + 4] : acc[i]) + recv;
+        }
+        const bool h8 = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = h8 ? a4[i] : a4[i + 2];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+            a2[i] = (h8 ? a4[i + 2] : a4[i]) + recv;
+        }
+        const bool h4 = lane & 4;
+        {
+            const float send = h4 ? a2[0] : a2[1];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+            a1 = (h4 ? a2[1] : a2[0]) + recv;
+        }
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+        const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        if ((lane & 3) == 0) out[k] = a1;
+    } else {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            float v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[k] = v;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) out[k] = acc[k];
+        }
+    }
+}
+
+__device__ __forceinline__ void consumer_sync() { __syncthreads(); }
+
 template <int KP, bool LP, bool WEIGHTED, bool WRITE_W>
-__global__ void __launch_bounds__(FW_WARPS * 32, 4)
+__global__ void __launch_bounds__(FC_THREADS, 3)
     k12_fused(const FusedTileDesc *__restrict__ desc, int n_tiles, const unsigned char *__restrict__ blob,
               const float *__restrict__ xf, float *__restrict__ partial, const float *__restrict__ row_weight,
               const uint32_t *__restrict__ row_of_pos, double *__restrict__ lp_partial, float *__restrict__ w_out,
-              uint32_t ring_bytes, uint32_t max_rows, uint32_t max_E, uint32_t max_C, uint32_t max_slots) {
+              uint32_t ring_bytes, uint32_t max_rows, uint32_t max_E, uint32_t max_C) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const FwCarve cv = fw_carve(ring_bytes, max_rows, max_E, max_C, max_slots, KP);
+    const FcCarve cv = fc_carve(ring_bytes, max_rows, max_E, max_C, KP);
+    FcCtl &ctl = *reinterpret_cast<FcCtl *>(smraw);
+    unsigned char *ring = smraw + cv.ring;
+    float *w_tile = reinterpret_cast<float *>(smraw + cv.w_tile);
+    float *x_loc = reinterpret_cast<float *>(smraw + cv.x_loc);
+    uint16_t *lrow = reinterpret_cast<uint16_t *>(smraw + cv.lrow);
+    __shared__ double lpsm[FC_WARPS][16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smraw) + 2 * warp;
-    unsigned char *base = smraw + cv.head + (size_t)warp * cv.per_warp;
-    unsigned char *ring = base;
-    float *w_tile = reinterpret_cast<float *>(base + cv.w_tile);
-    float *xs = reinterpret_cast<float *>(base + cv.xs);
-    uint8_t *lrow = base + cv.lrow;
-    if (lane == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+    const uint32_t tid = threadIdx.x;
+    int tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    if (tid == 0) {
+        mbar_init(&ctl.bar[0], 1);
+        mbar_init(&ctl.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
-    const int nw = gridDim.x * FW_WARPS;
-    int tile = blockIdx.x * FW_WARPS + warp;
-    if (tile >= n_tiles) return;
-
-    // ring state (warp-uniform): the current tile lives at [cur_off, cur_off + cur_bytes)
-    uint32_t cur_off = 0, cur_bytes = 0, phase = 0;  // phase bit b = parity to wait for on bar[b]
+    // ring state, computed redundantly (and identically) by every thread; thread 0 issues the copies.
+    // The current tile lives at [cur_off, cur_off + cur_bytes).
+    const int stride = (int)gridDim.x;
+    FusedTileDesc dcur = desc[tile];
+    FusedTileDesc dn = tile + stride < n_tiles ? desc[tile + stride] : FusedTileDesc{0, 0, 0};
+    uint32_t cur_off = 0, cur_bytes = dcur.bytes, phase = 0;
+    uint64_t cur_goff = dcur.off;
+    bool cur_issued = false;
     int cur_bar = 0;
-    FusedTileDesc dn{0, 0, 0};  // descriptor of the next tile, fetched one tile ahead (lane 0)
-    if (lane == 0) {
-        const FusedTileDesc d = desc[tile];
-        mbar_expect_tx(&bar[0], d.bytes);
-        bulk_g2s(ring, blob + d.off, d.bytes, &bar[0]);
-        cur_bytes = d.bytes;
-        if (tile + nw < n_tiles) dn = desc[tile + nw];
-    }
-    cur_bytes = __shfl_sync(0xffffffffu, cur_bytes, 0);
 
     for (;;) {
-        const int next = tile + nw;
-        uint32_t pre = 0, noff = 0, nbytes = 0;
-        if (next < n_tiles) {
-            if (lane == 0) {
-                nbytes = dn.bytes;
-                const uint32_t cand = cur_off + cur_bytes;
-                if (cand + nbytes <= ring_bytes) {
-                    noff = cand;
-                    pre = 1;
-                } else if (nbytes <= cur_off) {
-                    noff = 0;
-                    pre = 1;
-                }
-                if (pre) {
-                    mbar_expect_tx(&bar[cur_bar ^ 1], nbytes);
-                    bulk_g2s(ring + noff, blob + dn.off, nbytes, &bar[cur_bar ^ 1]);
-                }
+        __syncthreads();  // everyone is done with the previous tile (its ring space may be reused from here on)
+        if (!cur_issued) {
+            cur_off = 0;
+            if (tid == 0) {
+                mbar_expect_tx(&ctl.bar[cur_bar], cur_bytes);
+                bulk_g2s(ring, blob + cur_goff, cur_bytes, &ctl.bar[cur_bar]);
             }
-            pre = __shfl_sync(0xffffffffu, pre, 0);
-            noff = __shfl_sync(0xffffffffu, noff, 0);
-            nbytes = __shfl_sync(0xffffffffu, nbytes, 0);
         }
-        const uint64_t dn_off = dn.off;  // lane 0 only
-        if (lane == 0 && next + nw < n_tiles) dn = desc[next + nw];
-
-        mbar_wait(&bar[cur_bar], (phase >> cur_bar) & 1u);
+        const int next = tile + stride;
+        bool pre = false;
+        uint32_t noff = 0;
+        const uint32_t nbytes = dn.bytes;
+        const uint64_t ngoff = dn.off;
+        if (next < n_tiles) {  // prefetch the next tile beside the current one when it fits
+            const uint32_t cand = cur_off + cur_bytes;
+            if (cand + nbytes <= ring_bytes) {
+                noff = cand;
+                pre = true;
+            } else if (nbytes <= cur_off) {
+                noff = 0;
+                pre = true;
+            }
+            if (pre && tid == 0) {
+                mbar_expect_tx(&ctl.bar[cur_bar ^ 1], nbytes);
+                bulk_g2s(ring + noff, blob + ngoff, nbytes, &ctl.bar[cur_bar ^ 1]);
+            }
+            if (next + stride < n_tiles) dn = desc[next + stride];
+        }
+        mbar_wait(&ctl.bar[cur_bar], (phase >> cur_bar) & 1u);
         phase ^= 1u << cur_bar;
-        const unsigned char *b = ring + cur_off;
+        const uint32_t my_off = cur_off;
+        const unsigned char *b = ring + my_off;
         const FusedHdr hd = *reinterpret_cast<const FusedHdr *>(b);
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C);
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.S);
         const uint32_t *cols = reinterpret_cast<const uint32_t *>(b + L.cols);
         const uint16_t *rowoff = reinterpret_cast<const uint16_t *>(b + L.rowoff);
         const float *val = reinterpret_cast<const float *>(b + L.val);
         const uint16_t *perm = reinterpret_cast<const uint16_t *>(b + L.perm);
-        const uint16_t *slot0 = reinterpret_cast<const uint16_t *>(b + L.slot0);
-        const uint16_t *cslot = reinterpret_cast<const uint16_t *>(b + L.cslot);
+        const uint16_t *segptr = reinterpret_cast<const uint16_t *>(b + L.segptr);
         const uint8_t *lcol = b + L.lcol;
 
         // ------------------------------ x of the tile's columns -> shared memory (the only gather of the tile)
-        for (uint32_t j = lane; j < hd.C; j += 32) {
+        for (uint32_t j = tid; j < hd.C; j += FC_THREADS) {
             float xv[KP];
             Vec<KP>::ld(xf + (size_t)cols[j] * KP, xv);
-            sts_vec<KP>(xs + (size_t)j * KP, xv);
+            sts_vec<KP>(x_loc + (size_t)j * KP, xv);
         }
-        __syncwarp();
+        __syncthreads();
 
-        // ------------------------------ pass A: p and w of the tile's rows (lane = row; rows sorted longest first)
+        // ------------------------------ pass A: p and w of the tile's rows (thread = row; rows sorted longest first)
         double lpv[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) lpv[k] = 0.0;
-        for (uint32_t r = lane; r < hd.rows; r += 32) {
+        for (uint32_t r = tid; r < hd.rows; r += FC_THREADS) {
             const uint32_t e0 = rowoff[r], len = rowoff[r + 1] - e0;
-            Acc<KP> facc;
-            facc.zero();
-            double acc[KP];
+            Acc<KP> fsum;  // Float32 batches of four products, batch sums added in Float32
+            fsum.zero();
+            uint32_t t = 0;
+            for (; t + 4 <= len; t += 4) {
+                Acc<KP> bat;
+                bat.zero();
 #pragma unroll
-            for (int k = 0; k < KP; ++k) acc[k] = 0.0;
-            for (uint32_t t = 0; t < len; ++t) {
-                if ((t & 3u) == 0u && t != 0u) {  // every four products the Float32 batch is added to the Float64 row sum
-#pragma unroll
-                    for (int k = 0; k < KP; ++k) acc[k] += (double)facc.get(k);
-                    facc.zero();
+                for (int u = 0; u < 4; ++u) {
+                    const float v = val[e0 + t + u];
+                    Acc<KP> xv;
+                    xv.lds(x_loc + (size_t)lcol[e0 + t + u] * KP);
+                    lrow[e0 + t + u] = (uint16_t)r;
+                    bat.fma(v, xv);
                 }
-                const float v = val[e0 + t];
-                Acc<KP> xv;
-                xv.lds(xs + (size_t)lcol[e0 + t] * KP);
-                lrow[e0 + t] = (uint8_t)r;
-                facc.fma(v, xv);
+                fsum.add(bat);
+            }
+            if (t < len) {
+                Acc<KP> bat;
+                bat.zero();
+                for (; t < len; ++t) {
+                    const float v = val[e0 + t];
+                    Acc<KP> xv;
+                    xv.lds(x_loc + (size_t)lcol[e0 + t] * KP);
+                    lrow[e0 + t] = (uint16_t)r;
+                    bat.fma(v, xv);
+                }
+                fsum.add(bat);
             }
             float wt = 1.0f;
             if (WEIGHTED) wt = row_weight[hd.row0 + r];
             float wv[KP];
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
-                float rc;
-                if (len > 4) {
-                    acc[k] += (double)facc.get(k);
-                    rc = __frcp_rn((float)acc[k]);
-                    if (LP) lpv[k] += WEIGHTED ? log(acc[k]) * (double)wt : log(acc[k]);
-                } else {
-                    rc = rcp_approx(facc.get(k));
-                    if (LP) lpv[k] += WEIGHTED ? log((double)facc.get(k)) * (double)wt : log((double)facc.get(k));
-                }
+                const float p = fsum.get(k);
+                const float rc = rcp_approx(p);
                 wv[k] = WEIGHTED ? rc * wt : rc;
+                if (LP) lpv[k] += WEIGHTED ? log((double)p) * (double)wt : log((double)p);
             }
             sts_vec<KP>(w_tile + (size_t)r * KP, wv);
             if (WRITE_W) Vec<KP>::st(w_out + (size_t)row_of_pos[hd.row0 + r] * KP, wv);
@@ -235,57 +283,41 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 4)
                 double v = lpv[k];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == k) lp_partial[(size_t)tile * KP + k] = v;
+                if (lane == 0) lpsm[warp][k] = v;
             }
         }
-        __syncwarp();
+        __syncthreads();
+        if (LP && tid < KP) {
+            double sacc = 0.0;
+            for (int wi = 0; wi < FC_WARPS; ++wi) sacc += lpsm[wi][tid];
+            lp_partial[(size_t)tile * KP + tid] = sacc;
+        }
 
-        // ------------------------------ pass B: lane walks its chunk of the column-major order, one slot per run
-        {
-            const uint32_t q0 = lane * hd.chunk, q1 = min(hd.E, q0 + hd.chunk);
-            uint32_t slot = q0 < hd.E ? slot0[lane] : 0u;
+        // ------------------------------ pass B: one warp sums one column segment (<= FT_SEG entries) -> one partial
+        for (uint32_t sg = warp; sg < hd.S; sg += FC_WARPS) {
+            const uint32_t q0 = segptr[sg], q1 = segptr[sg + 1];
             Acc<KP> acc;
             acc.zero();
-            for (uint32_t q = q0; q < q1; ++q) {
-                const uint32_t pe = perm[q], e = pe & 0x7fffu;
+            for (uint32_t q = q0 + lane; q < q1; q += 32) {
+                const uint32_t e = perm[q];
                 const float v = val[e];
                 Acc<KP> wv;
                 wv.lds(w_tile + (size_t)lrow[e] * KP);
                 acc.fma(v, wv);
-                if (pe & 0x8000u) {
-                    acc.sts(xs + (size_t)slot * KP);
-                    ++slot;
-                    acc.zero();
-                }
             }
+            float a[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) a[k] = acc.get(k);
+            warp_reduce_store<KP>(a, lane, partial + (size_t)(hd.part0 + sg) * KP);
         }
-        __syncwarp();
-
-        // ------------------------------ pass C: (tile, column) partial = sum of the column's slots
-        {
-            float *pout = partial + (size_t)hd.part0 * KP;
-            for (uint32_t idx = lane; idx < hd.C * KP; idx += 32) {
-                const uint32_t j = idx / KP, k = idx % KP;
-                const uint32_t s0 = cslot[j], s1 = cslot[j + 1];
-                float a = 0.0f;
-                for (uint32_t sidx = s0; sidx < s1; ++sidx) a += xs[(size_t)sidx * KP + k];
-                pout[idx] = a;
-            }
-        }
-        __syncwarp();
 
         if (next >= n_tiles) break;
-        if (!pre) {  // the next tile did not fit beside this one: load it now
-            if (lane == 0) {
-                mbar_expect_tx(&bar[cur_bar ^ 1], nbytes);
-                bulk_g2s(ring, blob + dn_off, nbytes, &bar[cur_bar ^ 1]);
-            }
-            noff = 0;
-        }
+        tile = next;
         cur_off = noff;
         cur_bytes = nbytes;
+        cur_goff = ngoff;
+        cur_issued = pre;
         cur_bar ^= 1;
-        tile = next;
     }
 }
 
@@ -330,25 +362,25 @@ __global__ void __launch_bounds__(256)
 }
 
 static uint32_t fused_ring_bytes(const polee_handle *h) {
-    uint32_t ring = std::max<uint32_t>(5120u, al128(h->ft_max_blob));
-    if (const char *e = getenv("POLEE_FUSED_RING")) ring = std::max<uint32_t>(al128((uint32_t)atoi(e)), al128(h->ft_max_blob));
+    const uint32_t mb = al128(h->ft_max_blob);
+    uint32_t ring = std::max<uint32_t>(mb, std::min<uint32_t>(2 * mb, 40u * 1024u));
+    if (const char *e = getenv("POLEE_FUSED_RING")) ring = std::max<uint32_t>(al128((uint32_t)atoi(e)), mb);
     return ring;
 }
 
 template <int KP>
 int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, double *lp_partial, float *w_out) {
     const uint32_t ring = fused_ring_bytes(h);
-    const FwCarve cv = fw_carve(ring, h->ft_max_rows, h->ft_max_E, h->ft_max_C, h->ft_max_slots, KP);
+    const FcCarve cv = fc_carve(ring, h->ft_max_rows, h->ft_max_E, h->ft_max_C, KP);
     const bool weighted = h->ft_row_weight != nullptr;
-#define FK_LAUNCH(LPF, WF, WW)                                                                                              \
-    do {                                                                                                                    \
-        auto kern = k12_fused<KP, LPF, WF, WW>;                                                                             \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total);             \
-        if (e != cudaSuccess) return h->fail(POLEE_ECUDA, std::string("fused kernel smem: ") + cudaGetErrorString(e));      \
-        kern<<<h->ft_grid, FW_WARPS * 32, cv.total, h->stream>>>(h->ft_desc, h->ft_tiles, h->ft_blob, x, h->ft_partial,     \
-                                                                 h->ft_row_weight, h->ft_row_of_pos, lp_partial, w_out,     \
-                                                                 ring, h->ft_max_rows, h->ft_max_E, h->ft_max_C,            \
-                                                                 h->ft_max_slots);                                          \
+#define FK_LAUNCH(LPF, WF, WW)                                                                                           \
+    do {                                                                                                                 \
+        auto kern = k12_fused<KP, LPF, WF, WW>;                                                                          \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total);          \
+        if (e != cudaSuccess) return h->fail(POLEE_ECUDA, std::string("fused kernel smem: ") + cudaGetErrorString(e));   \
+        kern<<<h->ft_grid, FC_THREADS, cv.total, h->stream>>>(h->ft_desc, h->ft_tiles, h->ft_blob, x, h->ft_partial,     \
+                                                              h->ft_row_weight, h->ft_row_of_pos, lp_partial, w_out,     \
+                                                              ring, h->ft_max_rows, h->ft_max_E, h->ft_max_C);           \
     } while (0)
     if (w_out) {
         if (weighted) FK_LAUNCH(false, true, true); else FK_LAUNCH(false, false, true);
@@ -371,13 +403,12 @@ int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, dou
 
 }  // namespace
 
-// CTAs (of FW_WARPS warps) for the persistent fused kernel: as many as shared memory lets an SM hold
+// CTAs for the persistent fused kernel: as many as shared memory lets an SM hold (at most 3: register budget)
 int fused_grid(polee_handle *h, int KP) {
-    const FwCarve cv = fw_carve(fused_ring_bytes(h), h->ft_max_rows, h->ft_max_E, h->ft_max_C, h->ft_max_slots, KP);
-    int per_sm = (int)std::max<uint32_t>(1, std::min<uint32_t>(5, (227u * 1024u) / (cv.total + 1024u)));
+    const FcCarve cv = fc_carve(fused_ring_bytes(h), h->ft_max_rows, h->ft_max_E, h->ft_max_C, KP);
+    int per_sm = (int)std::max<uint32_t>(1, std::min<uint32_t>(3, (227u * 1024u) / (cv.total + 2048u)));
     if (const char *e = getenv("POLEE_FUSED_CTAS")) per_sm = std::max(1, atoi(e));
-    const int ctas_needed = (h->ft_tiles + FW_WARPS - 1) / FW_WARPS;
-    return std::max(1, std::min(ctas_needed, h->num_sms * per_sm));
+    return std::max(1, std::min(h->ft_tiles, h->num_sms * per_sm));
 }
 
 int launch_fused(polee_handle *h, const float *x, double *g, bool want_lp, double *lp_partial, float *w_out, int KP) {

@@ -182,28 +182,41 @@ __global__ void k_inverse_perm(const uint32_t *__restrict__ a_csc, int64_t nnz, 
         apos_of_csc[a_csc[a]] = (uint32_t)a;
 }
 
-// column-major (within tile) order: slot flags and column starts (+ zero sentinels at nnz for the exclusive scans)
-__global__ void k_b_flags(const uint32_t *__restrict__ tileB, const uint32_t *__restrict__ b_csc, int64_t nnz,
-                          const uint32_t *__restrict__ col_of, const uint32_t *__restrict__ row_ptr,
-                          const uint32_t *__restrict__ tile_row0, uint32_t *flagB, uint32_t *colstart) {
+// column-major (within tile) order: (tile, column) run starts (+ a zero sentinel at nnz for the exclusive scan)
+__global__ void k_col_starts(const uint32_t *__restrict__ tileB, const uint32_t *__restrict__ b_csc, int64_t nnz,
+                             const uint32_t *__restrict__ col_of, uint32_t *colstart) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q <= nnz; q += (int64_t)gridDim.x * blockDim.x) {
         if (q == nnz) {
-            flagB[q] = 0;
             colstart[q] = 0;
             continue;
         }
-        const uint32_t t = tileB[q];
-        const uint32_t a0 = row_ptr[tile_row0[t]], a1 = row_ptr[tile_row0[t + 1]];
-        const uint32_t qq = (uint32_t)q - a0, chunk = (a1 - a0 + 31u) / 32u, c = col_of[b_csc[q]];
-        const bool last = (uint32_t)q == a1 - 1u;
-        flagB[q] = ((qq + 1u) % chunk == 0u || last || col_of[b_csc[q + 1]] != c) ? 1u : 0u;
-        colstart[q] = (qq == 0u || col_of[b_csc[q - 1]] != c) ? 1u : 0u;
+        colstart[q] = (q == 0 || tileB[q] != tileB[q - 1] || col_of[b_csc[q]] != col_of[b_csc[q - 1]]) ? 1u : 0u;
+    }
+}
+
+// run_pos[pid] = first position of (tile, column) run pid
+__global__ void k_run_pos(const uint32_t *__restrict__ colstart, const uint32_t *__restrict__ cols_before, int64_t nnz,
+                          uint32_t *run_pos) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x)
+        if (colstart[q]) run_pos[cols_before[q]] = (uint32_t)q;
+}
+
+// segment starts: every FT_SEG entries of a run
+__global__ void k_seg_starts(const uint32_t *__restrict__ colstart, const uint32_t *__restrict__ cols_before,
+                             const uint32_t *__restrict__ run_pos, int64_t nnz, uint32_t *segstart) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q <= nnz; q += (int64_t)gridDim.x * blockDim.x) {
+        if (q == nnz) {
+            segstart[q] = 0;
+            continue;
+        }
+        const uint32_t pid = cols_before[q] + colstart[q] - 1u;
+        segstart[q] = (((uint32_t)q - run_pos[pid]) % FT_SEG == 0u) ? 1u : 0u;
     }
 }
 
 __global__ void k_tile_meta(uint32_t n_tiles, const uint32_t *__restrict__ tile_row0, const uint32_t *__restrict__ row_ptr,
-                            const uint32_t *__restrict__ runs_before, const uint32_t *__restrict__ cols_before,
-                            FusedHdr *hdrs, uint64_t *blob_bytes, uint32_t *maxima /* E, C, rows, bytes, slots */) {
+                            const uint32_t *__restrict__ segs_before, const uint32_t *__restrict__ cols_before,
+                            FusedHdr *hdrs, uint64_t *blob_bytes, uint32_t *maxima /* E, C, rows, bytes, S */) {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
         const uint32_t row0 = tile_row0[t], row1 = tile_row0[t + 1];
         const uint32_t a0 = row_ptr[row0], a1 = row_ptr[row1];
@@ -211,19 +224,19 @@ __global__ void k_tile_meta(uint32_t n_tiles, const uint32_t *__restrict__ tile_
         hd.rows = row1 - row0;
         hd.E = a1 - a0;
         hd.C = cols_before[a1] - cols_before[a0];
-        hd.nslots = runs_before[a1] - runs_before[a0];
+        hd.S = segs_before[a1] - segs_before[a0];
         hd.row0 = row0;
-        hd.part0 = cols_before[a0];
-        hd.chunk = (hd.E + 31u) / 32u;
-        hd.pad = 0;
+        hd.part0 = segs_before[a0];
+        hd.pad0 = cols_before[a0];  // first (tile, column) run of the tile (setup only)
+        hd.pad1 = 0;
         hdrs[t] = hd;
-        const uint32_t bytes = blob_layout(hd.rows, hd.E, hd.C).bytes;
+        const uint32_t bytes = blob_layout(hd.rows, hd.E, hd.C, hd.S).bytes;
         blob_bytes[t] = bytes;
         atomicMax(&maxima[0], hd.E);
         atomicMax(&maxima[1], hd.C);
         atomicMax(&maxima[2], hd.rows);
         atomicMax(&maxima[3], bytes);
-        atomicMax(&maxima[4], hd.nslots);
+        atomicMax(&maxima[4], hd.S);
     }
 }
 
@@ -242,7 +255,7 @@ __global__ void k_pack_rows(int64_t m, const uint32_t *__restrict__ row_of_pos, 
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m; p += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t t = tile_incl[row_of_pos[p]] - 1u;
         const FusedHdr hd = hdrs[t];
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C);
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.S);
         uint16_t *rowoff = reinterpret_cast<uint16_t *>(blob + blob_off[t] + L.rowoff);
         const uint32_t a0 = row_ptr[hd.row0];
         rowoff[p - hd.row0] = (uint16_t)(row_ptr[p] - a0);
@@ -257,7 +270,7 @@ __global__ void k_pack_a(int64_t nnz, const uint32_t *__restrict__ posA, const u
     for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nnz; a += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t t = tile_incl[row_of_pos[posA[a]]] - 1u;
         const FusedHdr hd = hdrs[t];
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C);
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.S);
         unsigned char *b = blob + blob_off[t];
         const uint32_t e = (uint32_t)a - row_ptr[hd.row0];
         reinterpret_cast<float *>(b + L.val)[e] = nzval[a_csc[a]];
@@ -266,30 +279,29 @@ __global__ void k_pack_a(int64_t nnz, const uint32_t *__restrict__ posA, const u
 
 __global__ void k_pack_b(int64_t nnz, const uint32_t *__restrict__ tileB, const uint32_t *__restrict__ b_csc,
                          const uint32_t *__restrict__ apos_of_csc, const uint32_t *__restrict__ col_of,
-                         const uint32_t *__restrict__ flagB, const uint32_t *__restrict__ colstart,
-                         const uint32_t *__restrict__ runs_before, const uint32_t *__restrict__ cols_before,
+                         const uint32_t *__restrict__ segstart, const uint32_t *__restrict__ colstart,
+                         const uint32_t *__restrict__ segs_before, const uint32_t *__restrict__ cols_before,
                          const uint32_t *__restrict__ row_ptr, const FusedHdr *__restrict__ hdrs,
                          const uint64_t *__restrict__ blob_off, unsigned char *blob, uint32_t *part_col) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t t = tileB[q];
         const FusedHdr hd = hdrs[t];
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C);
+        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.S);
         unsigned char *b = blob + blob_off[t];
         const uint32_t a0 = row_ptr[hd.row0];
         const uint32_t qq = (uint32_t)q - a0;
         const uint32_t src = b_csc[q];
         const uint32_t e = apos_of_csc[src] - a0;
         const uint32_t pid = cols_before[q] + colstart[q] - 1u;  // (tile, column) run containing q
-        const uint32_t run = runs_before[q] - runs_before[a0];   // slots emitted before q in this tile
-        reinterpret_cast<uint16_t *>(b + L.perm)[qq] = (uint16_t)(e | (flagB[q] << 15));
-        (b + L.lcol)[e] = (unsigned char)(pid - hd.part0);
-        if (qq % hd.chunk == 0u) reinterpret_cast<uint16_t *>(b + L.slot0)[qq / hd.chunk] = (uint16_t)run;
-        if (colstart[q]) {
-            reinterpret_cast<uint16_t *>(b + L.cslot)[pid - hd.part0] = (uint16_t)run;
-            reinterpret_cast<uint32_t *>(b + L.cols)[pid - hd.part0] = col_of[src];
-            part_col[pid] = col_of[src];
+        reinterpret_cast<uint16_t *>(b + L.perm)[qq] = (uint16_t)e;
+        (b + L.lcol)[e] = (unsigned char)(pid - hd.pad0);
+        if (segstart[q]) {
+            const uint32_t sid = segs_before[q];
+            reinterpret_cast<uint16_t *>(b + L.segptr)[sid - hd.part0] = (uint16_t)qq;
+            part_col[sid] = col_of[src];
         }
-        if (qq == hd.E - 1u) reinterpret_cast<uint16_t *>(b + L.cslot)[hd.C] = (uint16_t)hd.nslots;
+        if (colstart[q]) reinterpret_cast<uint32_t *>(b + L.cols)[pid - hd.pad0] = col_of[src];
+        if (qq == hd.E - 1u) reinterpret_cast<uint16_t *>(b + L.segptr)[hd.S] = (uint16_t)hd.E;
     }
 }
 
@@ -454,14 +466,16 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
         k_inverse_perm<<<grid_for(nnz), TPB, 0, st>>>(a_csc, nnz, apos_of_csc);
     }
     pt.mark("fused: row sort + two entry sorts");
-    uint32_t *flagB, *colstart, *runs_before, *cols_before;
-    CK(sc.alloc(&flagB, nnz + 1)); CK(sc.alloc(&colstart, nnz + 1)); CK(sc.alloc(&runs_before, nnz + 1));
-    CK(sc.alloc(&cols_before, nnz + 1));
-    k_b_flags<<<grid_for(nnz + 1), TPB, 0, st>>>(tileB, b_csc, nnz, col_of, row_ptr, tile_row0, flagB, colstart);
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, flagB, runs_before, (int)(nnz + 1), st));
+    uint32_t *segstart, *colstart, *segs_before, *cols_before, *run_pos;
+    CK(sc.alloc(&segstart, nnz + 1)); CK(sc.alloc(&colstart, nnz + 1)); CK(sc.alloc(&segs_before, nnz + 1));
+    CK(sc.alloc(&cols_before, nnz + 1)); CK(sc.alloc(&run_pos, nnz + 1));
+    k_col_starts<<<grid_for(nnz + 1), TPB, 0, st>>>(tileB, b_csc, nnz, col_of, colstart);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, colstart, cols_before, (int)(nnz + 1), st));
     CK(ensure_tmp(need));
-    CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, flagB, runs_before, (int)(nnz + 1), st));
     CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, colstart, cols_before, (int)(nnz + 1), st));
+    if (nnz > 0) k_run_pos<<<grid_for(nnz), TPB, 0, st>>>(colstart, cols_before, nnz, run_pos);
+    k_seg_starts<<<grid_for(nnz + 1), TPB, 0, st>>>(colstart, cols_before, run_pos, nnz, segstart);
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, segstart, segs_before, (int)(nnz + 1), st));
 
     // ---- per-tile headers, blob offsets
     FusedHdr *hdrs;
@@ -471,7 +485,7 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     CK(sc.alloc(&d_max, 8));
     CK(cudaMemsetAsync(d_max, 0, 32, st));
     CK(cudaMemsetAsync(blob_bytes, 0, sizeof(uint64_t) * ((size_t)n_tiles + 1), st));
-    k_tile_meta<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, tile_row0, row_ptr, runs_before, cols_before, hdrs, blob_bytes, d_max);
+    k_tile_meta<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, tile_row0, row_ptr, segs_before, cols_before, hdrs, blob_bytes, d_max);
     CK(cub::DeviceScan::ExclusiveSum(nullptr, need, blob_bytes, blob_off, (int)(n_tiles + 1), st));
     CK(ensure_tmp(need));
     CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, blob_bytes, blob_off, (int)(n_tiles + 1), st));
@@ -480,7 +494,7 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     uint32_t n_parts = 0;
     CK(cudaMemcpyAsync(maxima, d_max, 32, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&total_bytes, blob_off + n_tiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&n_parts, cols_before + nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&n_parts, segs_before + nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     pt.mark("fused: runs + tile headers");
     // locality gate: the (tile, column) partials are written and read back once per step (32 B each at K = 8);
@@ -488,7 +502,7 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     const char *force = getenv("POLEE_LAYOUT");
     const bool forced = force && std::string(force) == "fused";
     if (!forced && (double)n_parts * 64.0 > 0.35 * (double)total_bytes) return unsuitable();
-    if (maxima[3] > 40u * 1024u) return unsuitable();  // a tile must fit a warp's shared-memory ring
+    if (maxima[3] > 64u * 1024u) return unsuitable();  // a tile must fit a shared-memory stage
     if (maxima[1] > FT_MAX_C) return unsuitable();     // local column ids are 8 bits
 
     CK(polee::dmalloc((void **)&h->ft_blob, std::max<uint64_t>(total_bytes, 16)));
@@ -503,7 +517,7 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     if (vals_ready_or_null) CK(cudaStreamWaitEvent(st, vals_ready_or_null, 0));
     if (nnz > 0) {
         k_pack_a<<<grid_for(nnz), TPB, 0, st>>>(nnz, posA, a_csc, h->ft_row_of_pos, tile_incl, row_ptr, hdrs, blob_off, d_nzval, h->ft_blob);
-        k_pack_b<<<grid_for(nnz), TPB, 0, st>>>(nnz, tileB, b_csc, apos_of_csc, col_of, flagB, colstart, runs_before, cols_before,
+        k_pack_b<<<grid_for(nnz), TPB, 0, st>>>(nnz, tileB, b_csc, apos_of_csc, col_of, segstart, colstart, segs_before, cols_before,
                                                  row_ptr, hdrs, blob_off, h->ft_blob, part_col);
     }
     pt.mark("fused: pack blobs");
@@ -556,7 +570,7 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     h->ft_nlvl2 = (int)lvl2;
     h->fused = true;
     if (getenv("POLEE_SETUP_TIMING"))
-        fprintf(stderr, "[polee setup] fused: %u tiles, %.1f MB blobs (%.2f B/entry), %u partials, %zu units, %zu multi, max E %u C %u rows %u blob %u slots %u\n",
+        fprintf(stderr, "[polee setup] fused: %u tiles, %.1f MB blobs (%.2f B/entry), %u partials, %zu units, %zu multi, max E %u C %u rows %u blob %u segs %u\n",
                 n_tiles, total_bytes / 1e6, nnz ? (double)total_bytes / nnz : 0.0, n_parts, units.size(), multi.size(),
                 maxima[0], maxima[1], maxima[2], maxima[3], maxima[4]);
     return POLEE_OK;
