@@ -826,7 +826,7 @@ extern "C" int polee_step_stats(polee_handle *h, double *b1, double *b2, double 
     if (h->fused) {
         // one pass: the matrix once (val + col + the 16-bit column-major permutation), row offsets, x, and the
         // (tile, column) partials written and read back; b2 = 0 tells the caller there is no second sparse kernel
-        if (b1) *b1 = nnz * 7 + (m + 1) * 2 + (double)h->ft_parts * (4 + 2 + K * 4 * 2 + 4) + K * n * 8;
+        if (b1) *b1 = (double)h->ft_blob_bytes + (double)h->ft_parts * (K * 4 * 2 + 4) + K * n * 8;
         if (b2) *b2 = 0;
     } else {
         if (b1) *b1 = nnz * 8 + (m + 1) * 4 + K * n * 4 + K * m * 4;

@@ -43,25 +43,26 @@ struct RowTile {
 
 // ---- fused likelihood layout ("row tiles"): K1 and K2 in one pass over the matrix.
 // A tile is a run of <= FT_ROWS consecutive rows (and < FT_ENTRY_WINDOW + longest-row entries), processed by one CTA;
-// inside a tile the rows are re-ordered longest first (the lanes of a warp then run the same trip counts).  The
-// entries are stored once, row-major, with a 16-bit permutation that enumerates them column-major, so the CTA can
-// compute p = X x for its rows and then the tile's contribution to X^T (1/p) without w ever leaving the SM.
-// Everything a tile needs travels as one 16-byte aligned blob (one bulk copy):
-//   header | cols u32[C] | rowoff u16[rows+1] | val f32[E] | perm u16[E] | segptr u16[S+1] | lcol u8[E]
-// cols = the tile's C distinct columns (a local dictionary, C <= 255: x of these columns is staged in shared memory
-// once per tile); lcol[e] = local column of row-major entry e; perm[q] = row-major index of the q-th column-major
-// entry.  The column-major list is cut into S segments of <= FT_SEG entries of one column (segptr); one warp sums one
-// segment and writes one partial, the second stage adds the partials of a column over all tiles.  7 bytes per entry
-// instead of the 16 the split layouts stream (8 in K1 + 8 in K2).
+// inside a tile the rows are re-ordered longest first and cut into groups of 32 (one warp, one lane per row).  A tile
+// carries its entries twice, once per access pattern, and everything travels as one 16-byte aligned blob (one bulk
+// copy):
+//   header | cols u32[C] | ginfo u32[G] | valA f32[EA] | valB f32[E] | lrowB u16[E] | segptr u16[S+1] | lcolA u8[EA]
+//  * row side (p = X x): group g is a dense glen x 32 slab, entry t of lane l at gbase + t * 32 + l (val 0 padding),
+//    so a warp reads it conflict-free with one trip count; lcolA = index into cols, the tile's C <= 255 distinct
+//    columns (a local dictionary: x of these columns is staged in shared memory once per tile); ginfo = gbase | glen << 16.
+//  * column side (g += X^T w): the entries column-major with their row position, cut into S segments of <= FT_SEG
+//    entries of one column (segptr); one warp sums one segment and writes one partial; the second stage adds the
+//    partials of a column over all tiles.  w never leaves shared memory.
+// ~11 bytes per entry instead of the 16 the split layouts stream (8 in K1 + 8 in K2) plus 2 x K x 4 bytes per row of w.
 constexpr int FT_ROWS = 512;
 constexpr uint32_t FT_ENTRY_WINDOW = 4096;
 constexpr uint32_t FT_SEG = 128;
 constexpr uint32_t FT_MAX_C = 255;
-constexpr int FT_MAX_E = 32767;
+constexpr uint32_t FT_MAX_EA = 32767;
 struct FusedHdr {
     uint32_t rows, E, C, S;  // rows, entries, distinct columns, column segments of the tile
     uint32_t row0, part0;    // first row position; index of the tile's first partial (= first segment)
-    uint32_t pad0, pad1;
+    uint32_t EA, G;          // padded row-side entries, row groups
 };
 struct FusedTileDesc {
     uint64_t off;    // byte offset of the blob
@@ -69,17 +70,18 @@ struct FusedTileDesc {
     uint32_t pad;
 };
 struct BlobLayout {
-    uint32_t cols, rowoff, val, perm, segptr, lcol, bytes;
+    uint32_t cols, ginfo, valA, valB, lrowB, segptr, lcolA, bytes;
 };
-__host__ __device__ inline BlobLayout blob_layout(uint32_t rows, uint32_t E, uint32_t C, uint32_t S) {
+__host__ __device__ inline BlobLayout blob_layout(const FusedHdr &hd) {
     BlobLayout L;
     L.cols = (uint32_t)sizeof(FusedHdr);
-    L.rowoff = L.cols + ((C * 4u + 15u) & ~15u);
-    L.val = L.rowoff + (((rows + 1u) * 2u + 15u) & ~15u);
-    L.perm = L.val + ((E * 4u + 15u) & ~15u);
-    L.segptr = L.perm + ((E * 2u + 15u) & ~15u);
-    L.lcol = L.segptr + (((S + 1u) * 2u + 15u) & ~15u);
-    L.bytes = L.lcol + ((E + 15u) & ~15u);
+    L.ginfo = L.cols + ((hd.C * 4u + 15u) & ~15u);
+    L.valA = L.ginfo + ((hd.G * 4u + 15u) & ~15u);
+    L.valB = L.valA + ((hd.EA * 4u + 15u) & ~15u);
+    L.lrowB = L.valB + ((hd.E * 4u + 15u) & ~15u);
+    L.segptr = L.lrowB + ((hd.E * 2u + 15u) & ~15u);
+    L.lcolA = L.segptr + (((hd.S + 1u) * 2u + 15u) & ~15u);
+    L.bytes = L.lcolA + ((hd.EA + 15u) & ~15u);
     return L;
 }
 // second stage: g[col] = sum of the (tile, column) partials of the column, in tile order.  A unit is <= FT_UNIT

@@ -29,15 +29,14 @@ constexpr int FC_THREADS = FC_WARPS * 32;
 __host__ __device__ inline uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
 
 struct FcCarve {
-    uint32_t ring, w_tile, x_loc, lrow, total;  // byte offsets; [0, ring) = control block
+    uint32_t ring, w_tile, x_loc, total;  // byte offsets; [0, ring) = control block
 };
-__host__ __device__ inline FcCarve fc_carve(uint32_t ring_bytes, uint32_t max_rows, uint32_t max_E, uint32_t max_C, int KP) {
+__host__ __device__ inline FcCarve fc_carve(uint32_t ring_bytes, uint32_t max_rows, uint32_t max_C, int KP) {
     FcCarve c;
     c.ring = 128;
     c.w_tile = c.ring + al128(ring_bytes);
-    c.x_loc = c.w_tile + al128(max_rows * KP * 4u);
-    c.lrow = c.x_loc + al128(max_C * KP * 4u);
-    c.total = c.lrow + al128(max_E * 2u);
+    c.x_loc = c.w_tile + al128(((max_rows + 31u) & ~31u) * KP * 4u);
+    c.total = c.x_loc + al128(((max_C + 7u) & ~7u) * KP * 4u);
     return c;
 }
 
@@ -45,15 +44,19 @@ struct FcCtl {  // shared control block
     uint64_t bar[2];
 };
 
+// x of the tile's columns and w of its rows live in shared memory as planes of four draws: item i, draws 4p..4p+3 at
+// base + p * stride + i * 4.  A 16-byte access per lane then conflicts only when two lanes of a quarter warp hit items
+// that are equal modulo 8 (with 32-byte items it was modulo 4, and both halves).
 template <int KP>
-__device__ __forceinline__ void sts_vec(float *p, const float *v) {
+__device__ __forceinline__ void sts_planes(float *base, uint32_t stride, uint32_t i, const float *v) {
     if constexpr (KP >= 4) {
 #pragma unroll
         for (int q = 0; q < KP / 4; ++q)
-            reinterpret_cast<float4 *>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            *reinterpret_cast<float4 *>(base + (size_t)q * stride + (size_t)i * 4) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     } else {
 #pragma unroll
-        for (int k = 0; k < KP; ++k) p[k] = v[k];
+        for (int k = 0; k < KP; ++k) base[(size_t)i * KP + k] = v[k];
     }
 }
 
@@ -66,18 +69,18 @@ struct Acc {
 #pragma unroll
         for (int i = 0; i < NP; ++i) v[i] = make_float2(0.0f, 0.0f);
     }
-    __device__ __forceinline__ void lds(const float *p) {
+    __device__ __forceinline__ void lds(const float *base, uint32_t stride, uint32_t i) {  // plane layout, see sts_planes
         if constexpr (KP >= 4) {
 #pragma unroll
             for (int q = 0; q < KP / 4; ++q) {
-                const float4 t = reinterpret_cast<const float4 *>(p)[q];
+                const float4 t = *reinterpret_cast<const float4 *>(base + (size_t)q * stride + (size_t)i * 4);
                 v[2 * q] = make_float2(t.x, t.y);
                 v[2 * q + 1] = make_float2(t.z, t.w);
             }
         } else if constexpr (KP == 2) {
-            v[0] = *reinterpret_cast<const float2 *>(p);
+            v[0] = *reinterpret_cast<const float2 *>(base + (size_t)i * 2);
         } else {
-            v[0] = make_float2(p[0], 0.0f);
+            v[0] = make_float2(base[i], 0.0f);
         }
     }
     __device__ __forceinline__ float get(int k) const { return (k & 1) ? v[k >> 1].y : v[k >> 1].x; }
@@ -152,14 +155,14 @@ __global__ void __launch_bounds__(FC_THREADS, 3)
     k12_fused(const FusedTileDesc *__restrict__ desc, int n_tiles, const unsigned char *__restrict__ blob,
               const float *__restrict__ xf, float *__restrict__ partial, const float *__restrict__ row_weight,
               const uint32_t *__restrict__ row_of_pos, double *__restrict__ lp_partial, float *__restrict__ w_out,
-              uint32_t ring_bytes, uint32_t max_rows, uint32_t max_E, uint32_t max_C) {
+              uint32_t ring_bytes, uint32_t max_rows, uint32_t max_C) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const FcCarve cv = fc_carve(ring_bytes, max_rows, max_E, max_C, KP);
+    const FcCarve cv = fc_carve(ring_bytes, max_rows, max_C, KP);
     FcCtl &ctl = *reinterpret_cast<FcCtl *>(smraw);
     unsigned char *ring = smraw + cv.ring;
     float *w_tile = reinterpret_cast<float *>(smraw + cv.w_tile);
     float *x_loc = reinterpret_cast<float *>(smraw + cv.x_loc);
-    uint16_t *lrow = reinterpret_cast<uint16_t *>(smraw + cv.lrow);
+    const uint32_t wstride = ((max_rows + 31u) & ~31u) * 4u, xstride = ((max_C + 7u) & ~7u) * 4u;  // floats per plane
     __shared__ double lpsm[FC_WARPS][16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tid = threadIdx.x;
@@ -214,68 +217,72 @@ __global__ void __launch_bounds__(FC_THREADS, 3)
         const uint32_t my_off = cur_off;
         const unsigned char *b = ring + my_off;
         const FusedHdr hd = *reinterpret_cast<const FusedHdr *>(b);
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.S);
+        const BlobLayout L = blob_layout(hd);
         const uint32_t *cols = reinterpret_cast<const uint32_t *>(b + L.cols);
-        const uint16_t *rowoff = reinterpret_cast<const uint16_t *>(b + L.rowoff);
-        const float *val = reinterpret_cast<const float *>(b + L.val);
-        const uint16_t *perm = reinterpret_cast<const uint16_t *>(b + L.perm);
+        const uint32_t *ginfo = reinterpret_cast<const uint32_t *>(b + L.ginfo);
+        const float *valA = reinterpret_cast<const float *>(b + L.valA);
+        const float *valB = reinterpret_cast<const float *>(b + L.valB);
+        const uint16_t *lrowB = reinterpret_cast<const uint16_t *>(b + L.lrowB);
         const uint16_t *segptr = reinterpret_cast<const uint16_t *>(b + L.segptr);
-        const uint8_t *lcol = b + L.lcol;
+        const uint8_t *lcolA = b + L.lcolA;
 
         // ------------------------------ x of the tile's columns -> shared memory (the only gather of the tile)
         for (uint32_t j = tid; j < hd.C; j += FC_THREADS) {
             float xv[KP];
             Vec<KP>::ld(xf + (size_t)cols[j] * KP, xv);
-            sts_vec<KP>(x_loc + (size_t)j * KP, xv);
+            sts_planes<KP>(x_loc, xstride, j, xv);
         }
         __syncthreads();
 
-        // ------------------------------ pass A: p and w of the tile's rows (thread = row; rows sorted longest first)
+        // ------------------------------ pass A: p and w of the tile's rows.  One warp = one group of 32 rows (a dense
+        // glen x 32 slab, lane = row); groups are dealt to the warps boustrophedon so that long and short groups mix.
         double lpv[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) lpv[k] = 0.0;
-        for (uint32_t r = tid; r < hd.rows; r += FC_THREADS) {
-            const uint32_t e0 = rowoff[r], len = rowoff[r + 1] - e0;
+        for (uint32_t round = 0; round * FC_WARPS < hd.G; ++round) {
+            const uint32_t g = round * FC_WARPS + ((round & 1u) ? (uint32_t)(FC_WARPS - 1 - warp) : (uint32_t)warp);
+            if (g >= hd.G) continue;
+            const uint32_t gi = ginfo[g], base = (gi & 0xffffu) + lane, glen = gi >> 16;
+            const uint32_t r = g * 32u + lane;
             Acc<KP> fsum;  // Float32 batches of four products, batch sums added in Float32
             fsum.zero();
             uint32_t t = 0;
-            for (; t + 4 <= len; t += 4) {
+            for (; t + 4 <= glen; t += 4) {
                 Acc<KP> bat;
                 bat.zero();
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const float v = val[e0 + t + u];
+                    const float v = valA[base + (t + u) * 32u];
                     Acc<KP> xv;
-                    xv.lds(x_loc + (size_t)lcol[e0 + t + u] * KP);
-                    lrow[e0 + t + u] = (uint16_t)r;
+                    xv.lds(x_loc, xstride, lcolA[base + (t + u) * 32u]);
                     bat.fma(v, xv);
                 }
                 fsum.add(bat);
             }
-            if (t < len) {
+            if (t < glen) {
                 Acc<KP> bat;
                 bat.zero();
-                for (; t < len; ++t) {
-                    const float v = val[e0 + t];
+                for (; t < glen; ++t) {
+                    const float v = valA[base + t * 32u];
                     Acc<KP> xv;
-                    xv.lds(x_loc + (size_t)lcol[e0 + t] * KP);
-                    lrow[e0 + t] = (uint16_t)r;
+                    xv.lds(x_loc, xstride, lcolA[base + t * 32u]);
                     bat.fma(v, xv);
                 }
                 fsum.add(bat);
             }
+            const bool rowok = r < hd.rows;
             float wt = 1.0f;
-            if (WEIGHTED) wt = row_weight[hd.row0 + r];
+            if (WEIGHTED && rowok) wt = row_weight[hd.row0 + r];
             float wv[KP];
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
                 const float p = fsum.get(k);
                 const float rc = rcp_approx(p);
                 wv[k] = WEIGHTED ? rc * wt : rc;
-                if (LP) lpv[k] += WEIGHTED ? log((double)p) * (double)wt : log((double)p);
+                if (LP && rowok) lpv[k] += WEIGHTED ? log((double)p) * (double)wt : log((double)p);
             }
-            sts_vec<KP>(w_tile + (size_t)r * KP, wv);
-            if (WRITE_W) Vec<KP>::st(w_out + (size_t)row_of_pos[hd.row0 + r] * KP, wv);
+            sts_planes<KP>(w_tile, wstride, r, wv);
+            if (WRITE_W && rowok) Vec<KP>::st(w_out + (size_t)row_of_pos[hd.row0 + r] * KP, wv);
         }
         if (LP) {
 #pragma unroll
@@ -298,12 +305,15 @@ __global__ void __launch_bounds__(FC_THREADS, 3)
             const uint32_t q0 = segptr[sg], q1 = segptr[sg + 1];
             Acc<KP> acc;
             acc.zero();
-            for (uint32_t q = q0 + lane; q < q1; q += 32) {
-                const uint32_t e = perm[q];
-                const float v = val[e];
-                Acc<KP> wv;
-                wv.lds(w_tile + (size_t)lrow[e] * KP);
-                acc.fma(v, wv);
+#pragma unroll
+            for (uint32_t it = 0; it < FT_SEG / 32; ++it) {
+                const uint32_t q = q0 + lane + it * 32u;
+                if (q < q1) {
+                    const float v = valB[q];
+                    Acc<KP> wv;
+                    wv.lds(w_tile, wstride, lrowB[q]);
+                    acc.fma(v, wv);
+                }
             }
             float a[KP];
 #pragma unroll
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(256)
 
 static uint32_t fused_ring_bytes(const polee_handle *h) {
     const uint32_t mb = al128(h->ft_max_blob);
-    uint32_t ring = std::max<uint32_t>(mb, std::min<uint32_t>(2 * mb, 40u * 1024u));
+    uint32_t ring = std::max<uint32_t>(mb, std::min<uint32_t>(2 * mb, 48u * 1024u));
     if (const char *e = getenv("POLEE_FUSED_RING")) ring = std::max<uint32_t>(al128((uint32_t)atoi(e)), mb);
     return ring;
 }
@@ -371,7 +381,7 @@ static uint32_t fused_ring_bytes(const polee_handle *h) {
 template <int KP>
 int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, double *lp_partial, float *w_out) {
     const uint32_t ring = fused_ring_bytes(h);
-    const FcCarve cv = fc_carve(ring, h->ft_max_rows, h->ft_max_E, h->ft_max_C, KP);
+    const FcCarve cv = fc_carve(ring, h->ft_max_rows, h->ft_max_C, KP);
     const bool weighted = h->ft_row_weight != nullptr;
 #define FK_LAUNCH(LPF, WF, WW)                                                                                           \
     do {                                                                                                                 \
@@ -380,7 +390,7 @@ int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, dou
         if (e != cudaSuccess) return h->fail(POLEE_ECUDA, std::string("fused kernel smem: ") + cudaGetErrorString(e));   \
         kern<<<h->ft_grid, FC_THREADS, cv.total, h->stream>>>(h->ft_desc, h->ft_tiles, h->ft_blob, x, h->ft_partial,     \
                                                               h->ft_row_weight, h->ft_row_of_pos, lp_partial, w_out,     \
-                                                              ring, h->ft_max_rows, h->ft_max_E, h->ft_max_C);           \
+                                                              ring, h->ft_max_rows, h->ft_max_C);                        \
     } while (0)
     if (w_out) {
         if (weighted) FK_LAUNCH(false, true, true); else FK_LAUNCH(false, false, true);
@@ -405,7 +415,7 @@ int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, dou
 
 // CTAs for the persistent fused kernel: as many as shared memory lets an SM hold (at most 3: register budget)
 int fused_grid(polee_handle *h, int KP) {
-    const FcCarve cv = fc_carve(fused_ring_bytes(h), h->ft_max_rows, h->ft_max_E, h->ft_max_C, KP);
+    const FcCarve cv = fc_carve(fused_ring_bytes(h), h->ft_max_rows, h->ft_max_C, KP);
     int per_sm = (int)std::max<uint32_t>(1, std::min<uint32_t>(3, (227u * 1024u) / (cv.total + 2048u)));
     if (const char *e = getenv("POLEE_FUSED_CTAS")) per_sm = std::max(1, atoi(e));
     return std::max(1, std::min(h->ft_tiles, h->num_sms * per_sm));

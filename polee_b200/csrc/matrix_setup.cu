@@ -215,8 +215,9 @@ __global__ void k_seg_starts(const uint32_t *__restrict__ colstart, const uint32
 }
 
 __global__ void k_tile_meta(uint32_t n_tiles, const uint32_t *__restrict__ tile_row0, const uint32_t *__restrict__ row_ptr,
-                            const uint32_t *__restrict__ segs_before, const uint32_t *__restrict__ cols_before,
-                            FusedHdr *hdrs, uint64_t *blob_bytes, uint32_t *maxima /* E, C, rows, bytes, S */) {
+                            const uint32_t *__restrict__ len_sorted, const uint32_t *__restrict__ segs_before,
+                            const uint32_t *__restrict__ cols_before, FusedHdr *hdrs, uint32_t *col0, uint64_t *blob_bytes,
+                            uint32_t *maxima /* E, C, rows, bytes, S, EA */) {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
         const uint32_t row0 = tile_row0[t], row1 = tile_row0[t + 1];
         const uint32_t a0 = row_ptr[row0], a1 = row_ptr[row1];
@@ -227,80 +228,93 @@ __global__ void k_tile_meta(uint32_t n_tiles, const uint32_t *__restrict__ tile_
         hd.S = segs_before[a1] - segs_before[a0];
         hd.row0 = row0;
         hd.part0 = segs_before[a0];
-        hd.pad0 = cols_before[a0];  // first (tile, column) run of the tile (setup only)
-        hd.pad1 = 0;
+        hd.G = (hd.rows + 31u) / 32u;
+        uint32_t ea = 0;
+        for (uint32_t g = 0; g < hd.G; ++g) ea += 32u * len_sorted[row0 + 32u * g];  // rows are sorted longest first
+        hd.EA = ea;
         hdrs[t] = hd;
-        const uint32_t bytes = blob_layout(hd.rows, hd.E, hd.C, hd.S).bytes;
+        col0[t] = cols_before[a0];
+        const uint32_t bytes = blob_layout(hd).bytes;
         blob_bytes[t] = bytes;
         atomicMax(&maxima[0], hd.E);
         atomicMax(&maxima[1], hd.C);
         atomicMax(&maxima[2], hd.rows);
         atomicMax(&maxima[3], bytes);
         atomicMax(&maxima[4], hd.S);
+        atomicMax(&maxima[5], hd.EA);
     }
 }
 
+// header + group table of every blob
 __global__ void k_tile_desc(uint32_t n_tiles, const FusedHdr *__restrict__ hdrs, const uint64_t *__restrict__ blob_off,
-                            const uint64_t *__restrict__ blob_bytes, FusedTileDesc *desc, unsigned char *blob) {
+                            const uint64_t *__restrict__ blob_bytes, const uint32_t *__restrict__ len_sorted,
+                            FusedTileDesc *desc, unsigned char *blob) {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
-        desc[t] = FusedTileDesc{blob_off[t], (uint32_t)blob_bytes[t], 0u};
-        *reinterpret_cast<FusedHdr *>(blob + blob_off[t]) = hdrs[t];
-    }
-}
-
-// p = row position (rows of a tile sorted longest first)
-__global__ void k_pack_rows(int64_t m, const uint32_t *__restrict__ row_of_pos, const uint32_t *__restrict__ tile_incl,
-                            const uint32_t *__restrict__ row_ptr, const FusedHdr *__restrict__ hdrs,
-                            const uint64_t *__restrict__ blob_off, unsigned char *blob) {
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < m; p += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t t = tile_incl[row_of_pos[p]] - 1u;
         const FusedHdr hd = hdrs[t];
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.S);
-        uint16_t *rowoff = reinterpret_cast<uint16_t *>(blob + blob_off[t] + L.rowoff);
-        const uint32_t a0 = row_ptr[hd.row0];
-        rowoff[p - hd.row0] = (uint16_t)(row_ptr[p] - a0);
-        if (p == (int64_t)hd.row0 + hd.rows - 1) rowoff[hd.rows] = (uint16_t)hd.E;
+        desc[t] = FusedTileDesc{blob_off[t], (uint32_t)blob_bytes[t], 0u};
+        unsigned char *b = blob + blob_off[t];
+        *reinterpret_cast<FusedHdr *>(b) = hd;
+        uint32_t *ginfo = reinterpret_cast<uint32_t *>(b + blob_layout(hd).ginfo);
+        uint32_t base = 0;
+        for (uint32_t g = 0; g < hd.G; ++g) {
+            const uint32_t L = len_sorted[hd.row0 + 32u * g];
+            ginfo[g] = base | (L << 16);
+            base += 32u * L;
+        }
     }
 }
 
+// row-side slab position of the t-th entry of the row at tile-local position rr
+__device__ __forceinline__ uint32_t slab_index(const unsigned char *b, const BlobLayout &L, uint32_t rr, uint32_t t) {
+    const uint32_t gi = reinterpret_cast<const uint32_t *>(b + L.ginfo)[rr >> 5];
+    return (gi & 0xffffu) + t * 32u + (rr & 31u);
+}
+
+// a = position in the (row position, column) order
 __global__ void k_pack_a(int64_t nnz, const uint32_t *__restrict__ posA, const uint32_t *__restrict__ a_csc,
                          const uint32_t *__restrict__ row_of_pos, const uint32_t *__restrict__ tile_incl,
                          const uint32_t *__restrict__ row_ptr, const FusedHdr *__restrict__ hdrs,
                          const uint64_t *__restrict__ blob_off, const float *__restrict__ nzval, unsigned char *blob) {
     for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nnz; a += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t t = tile_incl[row_of_pos[posA[a]]] - 1u;
+        const uint32_t p = posA[a];
+        const uint32_t t = tile_incl[row_of_pos[p]] - 1u;
         const FusedHdr hd = hdrs[t];
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.S);
+        const BlobLayout L = blob_layout(hd);
         unsigned char *b = blob + blob_off[t];
-        const uint32_t e = (uint32_t)a - row_ptr[hd.row0];
-        reinterpret_cast<float *>(b + L.val)[e] = nzval[a_csc[a]];
+        const uint32_t idx = slab_index(b, L, p - hd.row0, (uint32_t)a - row_ptr[p]);
+        reinterpret_cast<float *>(b + L.valA)[idx] = nzval[a_csc[a]];
     }
 }
 
+// q = position in the (tile, column, row) order
 __global__ void k_pack_b(int64_t nnz, const uint32_t *__restrict__ tileB, const uint32_t *__restrict__ b_csc,
-                         const uint32_t *__restrict__ apos_of_csc, const uint32_t *__restrict__ col_of,
-                         const uint32_t *__restrict__ segstart, const uint32_t *__restrict__ colstart,
-                         const uint32_t *__restrict__ segs_before, const uint32_t *__restrict__ cols_before,
-                         const uint32_t *__restrict__ row_ptr, const FusedHdr *__restrict__ hdrs,
-                         const uint64_t *__restrict__ blob_off, unsigned char *blob, uint32_t *part_col) {
+                         const uint32_t *__restrict__ apos_of_csc, const uint32_t *__restrict__ posA,
+                         const uint32_t *__restrict__ col_of, const uint32_t *__restrict__ segstart,
+                         const uint32_t *__restrict__ colstart, const uint32_t *__restrict__ segs_before,
+                         const uint32_t *__restrict__ cols_before, const uint32_t *__restrict__ row_ptr,
+                         const FusedHdr *__restrict__ hdrs, const uint32_t *__restrict__ col0,
+                         const uint64_t *__restrict__ blob_off, const float *__restrict__ nzval, unsigned char *blob,
+                         uint32_t *part_col) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t t = tileB[q];
         const FusedHdr hd = hdrs[t];
-        const BlobLayout L = blob_layout(hd.rows, hd.E, hd.C, hd.S);
+        const BlobLayout L = blob_layout(hd);
         unsigned char *b = blob + blob_off[t];
         const uint32_t a0 = row_ptr[hd.row0];
         const uint32_t qq = (uint32_t)q - a0;
         const uint32_t src = b_csc[q];
-        const uint32_t e = apos_of_csc[src] - a0;
+        const uint32_t apos = apos_of_csc[src];
+        const uint32_t p = posA[apos];
         const uint32_t pid = cols_before[q] + colstart[q] - 1u;  // (tile, column) run containing q
-        reinterpret_cast<uint16_t *>(b + L.perm)[qq] = (uint16_t)e;
-        (b + L.lcol)[e] = (unsigned char)(pid - hd.pad0);
+        reinterpret_cast<float *>(b + L.valB)[qq] = nzval[src];
+        reinterpret_cast<uint16_t *>(b + L.lrowB)[qq] = (uint16_t)(p - hd.row0);
+        (b + L.lcolA)[slab_index(b, L, p - hd.row0, apos - row_ptr[p])] = (unsigned char)(pid - col0[t]);
         if (segstart[q]) {
             const uint32_t sid = segs_before[q];
             reinterpret_cast<uint16_t *>(b + L.segptr)[sid - hd.part0] = (uint16_t)qq;
             part_col[sid] = col_of[src];
         }
-        if (colstart[q]) reinterpret_cast<uint32_t *>(b + L.cols)[pid - hd.pad0] = col_of[src];
+        if (colstart[q]) reinterpret_cast<uint32_t *>(b + L.cols)[pid - col0[t]] = col_of[src];
         if (qq == hd.E - 1u) reinterpret_cast<uint16_t *>(b + L.segptr)[hd.S] = (uint16_t)hd.E;
     }
 }
@@ -424,7 +438,7 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     CK(cudaMemcpyAsync(&n_tiles, tile_incl + (m - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (bad) return h->fail(POLEE_EINVAL, "set_matrix: rowval out of range 1..m");
-    if ((uint64_t)lmax + FT_ENTRY_WINDOW > (uint64_t)FT_MAX_E) return POLEE_OK;  // a row too long for 15-bit tile offsets
+    if ((uint64_t)lmax + FT_ENTRY_WINDOW > 32767ull) return POLEE_OK;  // a row too long for 16-bit tile offsets
     auto unsuitable = [&]() { release_fused(h); return (int)POLEE_OK; };
     pt.mark("fused: rows + tiles");
     uint32_t *tile_row0;
@@ -481,11 +495,13 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     FusedHdr *hdrs;
     uint64_t *blob_bytes, *blob_off;
     uint32_t *d_max;
+    uint32_t *col0;
     CK(sc.alloc(&hdrs, n_tiles)); CK(sc.alloc(&blob_bytes, (size_t)n_tiles + 1)); CK(sc.alloc(&blob_off, (size_t)n_tiles + 1));
+    CK(sc.alloc(&col0, n_tiles));
     CK(sc.alloc(&d_max, 8));
     CK(cudaMemsetAsync(d_max, 0, 32, st));
     CK(cudaMemsetAsync(blob_bytes, 0, sizeof(uint64_t) * ((size_t)n_tiles + 1), st));
-    k_tile_meta<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, tile_row0, row_ptr, segs_before, cols_before, hdrs, blob_bytes, d_max);
+    k_tile_meta<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, tile_row0, row_ptr, len_sorted, segs_before, cols_before, hdrs, col0, blob_bytes, d_max);
     CK(cub::DeviceScan::ExclusiveSum(nullptr, need, blob_bytes, blob_off, (int)(n_tiles + 1), st));
     CK(ensure_tmp(need));
     CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, blob_bytes, blob_off, (int)(n_tiles + 1), st));
@@ -504,6 +520,7 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     if (!forced && (double)n_parts * 64.0 > 0.35 * (double)total_bytes) return unsuitable();
     if (maxima[3] > 64u * 1024u) return unsuitable();  // a tile must fit a shared-memory stage
     if (maxima[1] > FT_MAX_C) return unsuitable();     // local column ids are 8 bits
+    if (maxima[5] > FT_MAX_EA) return unsuitable();    // 16-bit slab offsets
 
     CK(polee::dmalloc((void **)&h->ft_blob, std::max<uint64_t>(total_bytes, 16)));
     CK(polee::dmalloc((void **)&h->ft_desc, sizeof(FusedTileDesc) * std::max<uint32_t>(n_tiles, 1)));
@@ -512,13 +529,12 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     CK(sc.alloc(&part_col, n_parts)); CK(sc.alloc(&part_col_sorted, n_parts)); CK(sc.alloc(&pid_iota, n_parts));
     CK(sc.alloc(&col_cnt, n));
     CK(polee::dmalloc((void **)&h->ft_plist, sizeof(uint32_t) * std::max<uint32_t>(n_parts, 1)));
-    k_tile_desc<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, hdrs, blob_off, blob_bytes, h->ft_desc, h->ft_blob);
-    k_pack_rows<<<grid_for(m), TPB, 0, st>>>(m, h->ft_row_of_pos, tile_incl, row_ptr, hdrs, blob_off, h->ft_blob);
+    k_tile_desc<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, hdrs, blob_off, blob_bytes, len_sorted, h->ft_desc, h->ft_blob);
     if (vals_ready_or_null) CK(cudaStreamWaitEvent(st, vals_ready_or_null, 0));
     if (nnz > 0) {
         k_pack_a<<<grid_for(nnz), TPB, 0, st>>>(nnz, posA, a_csc, h->ft_row_of_pos, tile_incl, row_ptr, hdrs, blob_off, d_nzval, h->ft_blob);
-        k_pack_b<<<grid_for(nnz), TPB, 0, st>>>(nnz, tileB, b_csc, apos_of_csc, col_of, segstart, colstart, segs_before, cols_before,
-                                                 row_ptr, hdrs, blob_off, h->ft_blob, part_col);
+        k_pack_b<<<grid_for(nnz), TPB, 0, st>>>(nnz, tileB, b_csc, apos_of_csc, posA, col_of, segstart, colstart, segs_before,
+                                                 cols_before, row_ptr, hdrs, col0, blob_off, d_nzval, h->ft_blob, part_col);
     }
     pt.mark("fused: pack blobs");
     // ---- second stage work list: partial ids by column
@@ -562,7 +578,7 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     CK(cudaGetLastError());
     pt.mark("fused: second-stage list");
     h->ft_tiles = (int)n_tiles;
-    h->ft_max_E = maxima[0]; h->ft_max_C = maxima[1]; h->ft_max_rows = maxima[2]; h->ft_max_blob = maxima[3]; h->ft_max_slots = maxima[4];
+    h->ft_max_E = maxima[0]; h->ft_max_C = maxima[1]; h->ft_max_rows = maxima[2]; h->ft_max_blob = maxima[3];
     h->ft_blob_bytes = total_bytes;
     h->ft_parts = n_parts;
     h->ft_nunits = (int)units.size();
@@ -570,9 +586,9 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     h->ft_nlvl2 = (int)lvl2;
     h->fused = true;
     if (getenv("POLEE_SETUP_TIMING"))
-        fprintf(stderr, "[polee setup] fused: %u tiles, %.1f MB blobs (%.2f B/entry), %u partials, %zu units, %zu multi, max E %u C %u rows %u blob %u segs %u\n",
+        fprintf(stderr, "[polee setup] fused: %u tiles, %.1f MB blobs (%.2f B/entry), %u partials, %zu units, %zu multi, max E %u C %u rows %u blob %u segs %u EA %u\n",
                 n_tiles, total_bytes / 1e6, nnz ? (double)total_bytes / nnz : 0.0, n_parts, units.size(), multi.size(),
-                maxima[0], maxima[1], maxima[2], maxima[3], maxima[4]);
+                maxima[0], maxima[1], maxima[2], maxima[3], maxima[4], maxima[5]);
     return POLEE_OK;
 }
 
