@@ -61,6 +61,7 @@ static void drop_graph(polee_handle *h) {
     if (h->graph) cudaGraphDestroy(h->graph);
     h->graph_exec = nullptr;
     h->graph = nullptr;
+    h->graph_warm = false;
 }
 
 extern "C" int polee_opts_default(polee_opts *o) {
@@ -517,8 +518,19 @@ static int enqueue_step(polee_handle *h) {
         CK(cudaGetLastError());
         return POLEE_OK;
     }
+    if (!h->graph_warm) {
+        // the first step of a handle runs uncaptured: every kernel it needs is then loaded before a capture starts
+        // (lazy module loading allocates, which a capture does not tolerate)
+        rc = launch_step_sequence(h, true, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
+        if (rc) return rc;
+        CK(cudaGetLastError());
+        h->graph_warm = true;
+        return POLEE_OK;
+    }
     if (!h->graph_exec) {
-        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        // Relaxed: other host threads (one handle per thread in `polee prep`) may allocate, free or synchronise while
+        // this thread records; the handle's streams are non-blocking, so nothing they do can join this capture.
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
         rc = launch_step_sequence(h, true, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
         cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
         if (rc) return rc;

@@ -46,13 +46,13 @@ struct RowTile {
 // inside a tile the rows are re-ordered longest first and cut into groups of 32 (one warp, one lane per row).  A tile
 // carries its entries twice, once per access pattern, and everything travels as one 16-byte aligned blob (one bulk
 // copy):
-//   header | cols u32[C] | ginfo u32[G] | valA f32[EA] | valB f32[E] | lrowB u16[E] | segptr u16[S+1] | lcolA u8[EA]
+//   header | cols u32[C] | ginfo u32[G] | dest u32[S] | valA f32[EA] | valB f32[E] | lrowB u16[E] | segptr u16[S+1] | lcolA u8[EA]
 //  * row side (p = X x): group g is a dense glen x 32 slab, entry t of lane l at gbase + t * 32 + l (val 0 padding),
 //    so a warp reads it conflict-free with one trip count; lcolA = index into cols, the tile's C <= 255 distinct
 //    columns (a local dictionary: x of these columns is staged in shared memory once per tile); ginfo = gbase | glen << 16.
 //  * column side (g += X^T w): the entries column-major with their row position, cut into S segments of <= FT_SEG
-//    entries of one column (segptr); one warp sums one segment and writes one partial; the second stage adds the
-//    partials of a column over all tiles.  w never leaves shared memory.
+//    entries of one column (segptr); one warp sums one segment and writes one partial to slot dest[segment] of the
+//    partial array, which is ordered by column, so the second stage adds contiguous runs.  w never leaves shared memory.
 // ~11 bytes per entry instead of the 16 the split layouts stream (8 in K1 + 8 in K2) plus 2 x K x 4 bytes per row of w.
 constexpr int FT_ROWS = 512;
 constexpr uint32_t FT_ENTRY_WINDOW = 4096;
@@ -70,13 +70,14 @@ struct FusedTileDesc {
     uint32_t pad;
 };
 struct BlobLayout {
-    uint32_t cols, ginfo, valA, valB, lrowB, segptr, lcolA, bytes;
+    uint32_t cols, ginfo, dest, valA, valB, lrowB, segptr, lcolA, bytes;
 };
 __host__ __device__ inline BlobLayout blob_layout(const FusedHdr &hd) {
     BlobLayout L;
     L.cols = (uint32_t)sizeof(FusedHdr);
     L.ginfo = L.cols + ((hd.C * 4u + 15u) & ~15u);
-    L.valA = L.ginfo + ((hd.G * 4u + 15u) & ~15u);
+    L.dest = L.ginfo + ((hd.G * 4u + 15u) & ~15u);
+    L.valA = L.dest + ((hd.S * 4u + 15u) & ~15u);
     L.valB = L.valA + ((hd.EA * 4u + 15u) & ~15u);
     L.lrowB = L.valB + ((hd.E * 4u + 15u) & ~15u);
     L.segptr = L.lrowB + ((hd.E * 2u + 15u) & ~15u);
@@ -88,7 +89,7 @@ __host__ __device__ inline BlobLayout blob_layout(const FusedHdr &hd) {
 // partials of one column (one warp); columns with more than one unit are finished by a second small launch.
 constexpr int FT_UNIT = 256;
 struct FusedUnit {
-    uint32_t col, begin, end;  // [begin, end) into the column-sorted partial list
+    uint32_t col, begin, end;  // partials [begin, end) (the partial array is ordered by column)
     int32_t out;               // -1: writes g[col]; >= 0: writes the level-2 slot
 };
 struct FusedMulti {
@@ -230,7 +231,6 @@ struct polee_handle {
     uint32_t *ft_row_of_pos = nullptr;  // original row of every (tile-sorted) row position
     uint64_t ft_blob_bytes = 0;
     int64_t ft_parts = 0;            // (tile, column) partials
-    uint32_t *ft_plist = nullptr;    // partial ids sorted by column
     polee::FusedUnit *ft_units = nullptr;
     int ft_nunits = 0;
     polee::FusedMulti *ft_multi = nullptr;
@@ -299,6 +299,7 @@ struct polee_handle {
     // ---- graph
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
+    bool graph_warm = false;  // one uncaptured step has run with the current layouts
 
 #ifdef POLEE_WITH_NCCL
     ncclComm_t comm = nullptr;

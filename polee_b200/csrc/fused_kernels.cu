@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(FC_THREADS, 3)
         const BlobLayout L = blob_layout(hd);
         const uint32_t *cols = reinterpret_cast<const uint32_t *>(b + L.cols);
         const uint32_t *ginfo = reinterpret_cast<const uint32_t *>(b + L.ginfo);
+        const uint32_t *dest = reinterpret_cast<const uint32_t *>(b + L.dest);
         const float *valA = reinterpret_cast<const float *>(b + L.valA);
         const float *valB = reinterpret_cast<const float *>(b + L.valB);
         const uint16_t *lrowB = reinterpret_cast<const uint16_t *>(b + L.lrowB);
@@ -305,9 +306,8 @@ __global__ void __launch_bounds__(FC_THREADS, 3)
             const uint32_t q0 = segptr[sg], q1 = segptr[sg + 1];
             Acc<KP> acc;
             acc.zero();
-#pragma unroll
-            for (uint32_t it = 0; it < FT_SEG / 32; ++it) {
-                const uint32_t q = q0 + lane + it * 32u;
+            for (uint32_t qb = q0; qb < q1; qb += 32u) {  // <= FT_SEG / 32 trips, warp-uniform
+                const uint32_t q = qb + lane;
                 if (q < q1) {
                     const float v = valB[q];
                     Acc<KP> wv;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(FC_THREADS, 3)
             float a[KP];
 #pragma unroll
             for (int k = 0; k < KP; ++k) a[k] = acc.get(k);
-            warp_reduce_store<KP>(a, lane, partial + (size_t)(hd.part0 + sg) * KP);
+            warp_reduce_store<KP>(a, lane, partial + (size_t)dest[sg] * KP);
         }
 
         if (next >= n_tiles) break;
@@ -334,8 +334,8 @@ __global__ void __launch_bounds__(FC_THREADS, 3)
 // g[col] (or a level-2 slot) = sum of <= FT_UNIT (tile, column) partials, in tile order.  One warp per unit.
 template <int KP>
 __global__ void __launch_bounds__(256)
-    k_fused_combine1(const FusedUnit *__restrict__ units, int n_units, const uint32_t *__restrict__ plist,
-                     const float *__restrict__ partial, double *__restrict__ g, double *__restrict__ lvl2) {
+    k_fused_combine1(const FusedUnit *__restrict__ units, int n_units, const float *__restrict__ partial,
+                     double *__restrict__ g, double *__restrict__ lvl2) {
     const int unit = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     if (unit >= n_units) return;
     const int lane = threadIdx.x & 31;
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256)
     const FusedUnit u = units[unit];
     double a = 0.0;
 #pragma unroll 4
-    for (uint32_t i = u.begin + grp; i < u.end; i += G) a += (double)partial[(size_t)plist[i] * KP + k];
+    for (uint32_t i = u.begin + grp; i < u.end; i += G) a += (double)partial[(size_t)i * KP + k];
 #pragma unroll
     for (int o = 16; o >= KP; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
     if (grp == 0) {
@@ -402,7 +402,7 @@ int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, dou
 #undef FK_LAUNCH
     if (h->ft_nunits > 0) {
         const int blocks = (h->ft_nunits + 7) / 8;
-        k_fused_combine1<KP><<<blocks, 256, 0, h->stream>>>(h->ft_units, h->ft_nunits, h->ft_plist, h->ft_partial, g, h->ft_lvl2);
+        k_fused_combine1<KP><<<blocks, 256, 0, h->stream>>>(h->ft_units, h->ft_nunits, h->ft_partial, g, h->ft_lvl2);
     }
     if (h->ft_nmulti > 0) {
         const int blocks = (h->ft_nmulti + 7) / 8;
@@ -413,10 +413,22 @@ int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, dou
 
 }  // namespace
 
-// CTAs for the persistent fused kernel: as many as shared memory lets an SM hold (at most 3: register budget)
+// CTAs for the persistent fused kernel: what registers and shared memory let an SM hold
 int fused_grid(polee_handle *h, int KP) {
     const FcCarve cv = fc_carve(fused_ring_bytes(h), h->ft_max_rows, h->ft_max_C, KP);
-    int per_sm = (int)std::max<uint32_t>(1, std::min<uint32_t>(3, (227u * 1024u) / (cv.total + 2048u)));
+    int per_sm = 1;
+    auto probe = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, FC_THREADS, cv.total) == cudaSuccess && nb > 0) per_sm = nb;
+    };
+    switch (KP) {
+        case 1: probe(k12_fused<1, false, false, false>); break;
+        case 2: probe(k12_fused<2, false, false, false>); break;
+        case 4: probe(k12_fused<4, false, false, false>); break;
+        case 8: probe(k12_fused<8, false, false, false>); break;
+        default: probe(k12_fused<16, false, false, false>); break;
+    }
     if (const char *e = getenv("POLEE_FUSED_CTAS")) per_sm = std::max(1, atoi(e));
     return std::max(1, std::min(h->ft_tiles, h->num_sms * per_sm));
 }

@@ -121,9 +121,10 @@ __global__ void k_row_weights(const int64_t *__restrict__ ks, int64_t m, const u
 
 
 // ------------------------------------------------------------------ fused row-tile layout (see common.cuh)
-__global__ void k_tile_flags(const uint32_t *__restrict__ row_ptr, int64_t m, uint32_t *flag) {
+__global__ void k_tile_flags(const uint32_t *__restrict__ row_ptr, int64_t m, uint32_t tile_rows, uint32_t window,
+                             uint32_t *flag) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
-        flag[i] = (i % FT_ROWS == 0 || row_ptr[i] / FT_ENTRY_WINDOW != row_ptr[i - 1] / FT_ENTRY_WINDOW) ? 1u : 0u;
+        flag[i] = (i % tile_rows == 0 || row_ptr[i] / window != row_ptr[i - 1] / window) ? 1u : 0u;
 }
 
 // tile_incl[i] = 1 + tile of row i (inclusive scan of the flags)
@@ -294,7 +295,7 @@ __global__ void k_pack_b(int64_t nnz, const uint32_t *__restrict__ tileB, const 
                          const uint32_t *__restrict__ cols_before, const uint32_t *__restrict__ row_ptr,
                          const FusedHdr *__restrict__ hdrs, const uint32_t *__restrict__ col0,
                          const uint64_t *__restrict__ blob_off, const float *__restrict__ nzval, unsigned char *blob,
-                         uint32_t *part_col) {
+                         uint32_t *part_col, uint32_t *part_tile) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t t = tileB[q];
         const FusedHdr hd = hdrs[t];
@@ -313,9 +314,20 @@ __global__ void k_pack_b(int64_t nnz, const uint32_t *__restrict__ tileB, const 
             const uint32_t sid = segs_before[q];
             reinterpret_cast<uint16_t *>(b + L.segptr)[sid - hd.part0] = (uint16_t)qq;
             part_col[sid] = col_of[src];
+            part_tile[sid] = t;
         }
         if (colstart[q]) reinterpret_cast<uint32_t *>(b + L.cols)[pid - col0[t]] = col_of[src];
         if (qq == hd.E - 1u) reinterpret_cast<uint16_t *>(b + L.segptr)[hd.S] = (uint16_t)hd.E;
+    }
+}
+
+// the partial array is ordered by column: segment plist[i] writes slot i
+__global__ void k_pack_dest(uint32_t n_parts, const uint32_t *__restrict__ plist, const uint32_t *__restrict__ part_tile,
+                            const FusedHdr *__restrict__ hdrs, const uint64_t *__restrict__ blob_off, unsigned char *blob) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_parts; i += gridDim.x * blockDim.x) {
+        const uint32_t sid = plist[i], t = part_tile[sid];
+        const FusedHdr hd = hdrs[t];
+        reinterpret_cast<uint32_t *>(blob + blob_off[t] + blob_layout(hd).dest)[sid - hd.part0] = i;
     }
 }
 
@@ -385,10 +397,10 @@ struct PhaseTimer {
 };
 
 void release_fused(polee_handle *h) {
-    polee::dfree(h->ft_blob); polee::dfree(h->ft_desc); polee::dfree(h->ft_plist); polee::dfree(h->ft_units);
+    polee::dfree(h->ft_blob); polee::dfree(h->ft_desc); polee::dfree(h->ft_units);
     polee::dfree(h->ft_multi); polee::dfree(h->ft_row_weight); polee::dfree(h->ft_row_of_pos);
     h->ft_row_of_pos = nullptr;
-    h->ft_blob = nullptr; h->ft_desc = nullptr; h->ft_plist = nullptr; h->ft_units = nullptr; h->ft_multi = nullptr;
+    h->ft_blob = nullptr; h->ft_desc = nullptr; h->ft_units = nullptr; h->ft_multi = nullptr;
     h->ft_row_weight = nullptr;
     h->fused = false;
     h->ft_tiles = 0; h->ft_parts = 0; h->ft_nunits = h->ft_nmulti = h->ft_nlvl2 = 0;
@@ -427,7 +439,10 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     CK(cub::DeviceScan::ExclusiveSum(nullptr, need, row_len, row_ptr, (int)(m + 1), st));
     CK(ensure_tmp(need));
     CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, row_len, row_ptr, (int)(m + 1), st));
-    k_tile_flags<<<grid_for(m), TPB, 0, st>>>(row_ptr, m, flag);
+    uint32_t tile_rows = FT_ROWS, window = FT_ENTRY_WINDOW;
+    if (const char *e = getenv("POLEE_FT_ROWS")) tile_rows = std::max(32, atoi(e)) / 32 * 32;
+    if (const char *e = getenv("POLEE_FT_WINDOW")) window = (uint32_t)std::max(256, atoi(e));
+    k_tile_flags<<<grid_for(m), TPB, 0, st>>>(row_ptr, m, tile_rows, window, flag);
     CK(cub::DeviceScan::InclusiveSum(nullptr, need, flag, tile_incl, (int)m, st));
     CK(ensure_tmp(need));
     CK(cub::DeviceScan::InclusiveSum(d_tmp, need, flag, tile_incl, (int)m, st));
@@ -528,24 +543,26 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     uint32_t *part_col, *part_col_sorted, *pid_iota, *col_cnt;
     CK(sc.alloc(&part_col, n_parts)); CK(sc.alloc(&part_col_sorted, n_parts)); CK(sc.alloc(&pid_iota, n_parts));
     CK(sc.alloc(&col_cnt, n));
-    CK(polee::dmalloc((void **)&h->ft_plist, sizeof(uint32_t) * std::max<uint32_t>(n_parts, 1)));
+    uint32_t *plist, *part_tile;
+    CK(sc.alloc(&plist, n_parts)); CK(sc.alloc(&part_tile, n_parts));
     k_tile_desc<<<grid_for(n_tiles), TPB, 0, st>>>(n_tiles, hdrs, blob_off, blob_bytes, len_sorted, h->ft_desc, h->ft_blob);
     if (vals_ready_or_null) CK(cudaStreamWaitEvent(st, vals_ready_or_null, 0));
     if (nnz > 0) {
         k_pack_a<<<grid_for(nnz), TPB, 0, st>>>(nnz, posA, a_csc, h->ft_row_of_pos, tile_incl, row_ptr, hdrs, blob_off, d_nzval, h->ft_blob);
         k_pack_b<<<grid_for(nnz), TPB, 0, st>>>(nnz, tileB, b_csc, apos_of_csc, posA, col_of, segstart, colstart, segs_before,
-                                                 cols_before, row_ptr, hdrs, col0, blob_off, d_nzval, h->ft_blob, part_col);
+                                                 cols_before, row_ptr, hdrs, col0, blob_off, d_nzval, h->ft_blob, part_col, part_tile);
     }
     pt.mark("fused: pack blobs");
     // ---- second stage work list: partial ids by column
     CK(cudaMemsetAsync(col_cnt, 0, sizeof(uint32_t) * n, st));
     if (n_parts > 0) {
         k_iota_u32<<<grid_for(n_parts), TPB, 0, st>>>(pid_iota, n_parts);
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, part_col, part_col_sorted, pid_iota, h->ft_plist, (int)n_parts, 0, 32, st));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, part_col, part_col_sorted, pid_iota, plist, (int)n_parts, 0, 32, st));
         CK(ensure_tmp(need));
-        CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, part_col, part_col_sorted, pid_iota, h->ft_plist, (int)n_parts, 0,
+        CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, part_col, part_col_sorted, pid_iota, plist, (int)n_parts, 0,
                                            bits_for((uint64_t)n), st));
         k_count_keys<<<grid_for(n_parts), TPB, 0, st>>>(part_col, n_parts, col_cnt);
+        k_pack_dest<<<grid_for(n_parts), TPB, 0, st>>>(n_parts, plist, part_tile, hdrs, blob_off, h->ft_blob);
     }
     std::vector<uint32_t> cnt(n);
     CK(cudaMemcpyAsync(cnt.data(), col_cnt, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
