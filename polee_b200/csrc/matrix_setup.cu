@@ -629,11 +629,17 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
     const int64_t nnz = (int64_t)colptr[n] - 1;
     h->m = m; h->n = n; h->nnz = nnz;
 
-    // fused row-tile layout (one pass per step) unless the reference-order Float64 path was asked for, the caller
-    // pins the split layout (POLEE_LAYOUT=split), or the row order has too little locality for it
+    // Two layouts.  "split" (SELL slabs for K1 + re-sorted CSC for K2) streams the matrix twice and round-trips w
+    // through HBM; it is HBM-bound and the faster one when columns are long.  "fused" (row tiles, one pass, w stays in
+    // shared memory) moves ~40 % of the bytes but is bound by the shared-memory pipe; it wins when the columns of this
+    // rank's block are short (K2's <= 256-entry segments run underfilled), i.e. on small samples and on the row blocks
+    // of a >= 4-way partition of a large one (measured at C3: 0.80 vs 0.77 ms on 1 GPU, 0.135 vs 0.158 ms per 1/8
+    // block).  POLEE_LAYOUT=split|fused overrides; exact_accumulation always uses the reference-order split kernels.
     {
         const char *lay = getenv("POLEE_LAYOUT");
-        const bool want_fused = !h->o.exact_accumulation && !(lay && std::string(lay) == "split");
+        const bool forced = lay && std::string(lay) == "fused";
+        const bool short_columns = (double)nnz < 256.0 * (double)n;
+        const bool want_fused = !h->o.exact_accumulation && !(lay && std::string(lay) == "split") && (forced || short_columns);
         if (want_fused) {
             int rc = setup_fused_from_device_csc(h, m, n, nnz, d_colptr, d_rowval, d_nzval, d_ks, colptr, vals_ready_or_null);
             if (rc) return rc;

@@ -438,3 +438,48 @@ def test_gene_noninformative_prior(pb, fx, oracle, K):
     with pytest.warns(UserWarning):                            # l-a.jl:489-492: flag dropped without gene information
         same = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), _sample(pb, fx), gene_noninformative=True, **kw)
     assert np.array_equal(same["mu"], plain["mu"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [1, 6, 8])
+def test_split_and_fused_layouts_agree(pb, fx, small_synth, oracle, K, monkeypatch):
+    """The two device layouts of the matrix (SELL + CSC pair vs. fused row tiles, matrix_setup.cu) are two
+    implementations of the same pAt_mul_B! / pAt_mulinv_B! pair (sparse.jl:6-40): each within 1e-5 of the oracle,
+    within 1e-6 of each other, each run-to-run identical; also with row counts (likelihood.jl:59-85) and for the
+    row-wise 1/p output."""
+    rng = np.random.default_rng(40 + K)
+    for (m, n, colptr, rowval, nzval, eff, tree) in (
+            (fx.m, fx.n, fx.colptr, fx.rowval, fx.nzval, fx.efflens, (fx.parent_idxs, fx.js)),
+            (small_synth["m"], small_synth["n"], small_synth["colptr"], small_synth["rowval"], small_synth["nzval"],
+             small_synth["efflens"], small_synth["tree"])):
+        sample = pb.RNASeqSample(m, n, colptr, rowval, nzval, eff)
+        xs = rng.dirichlet(np.ones(n), K).astype(np.float32).clip(1e-10)
+        ks = rng.integers(1, 5, size=m).astype(np.int64)
+        M = oracle.Model(m, n, colptr, rowval, nzval)
+        out = {}
+        for layout in ("split", "fused"):
+            monkeypatch.setenv("POLEE_LAYOUT", layout)
+            h = pb.Handle(num_mc_samples=K, gradonly=False)
+            h.set_sample(sample)
+            h.set_tree(*tree)
+            lp, g = h.loglik_grad(xs, gradonly=False)
+            lp2, g2 = h.loglik_grad(xs, gradonly=False)
+            assert np.array_equal(g, g2) and np.array_equal(lp, lp2)          # deterministic
+            w = np.zeros(m, np.float32)
+            h.check(h.lib.polee_frag_prob_recip(h.h, xs[0].ctypes.data_as(pb.api._P), w.ctypes.data_as(pb.api._P)))
+            h.close()
+            hk = pb.Handle(num_mc_samples=K, gradonly=False)
+            hk.set_sample(sample, ks)
+            hk.set_tree(*tree)
+            lpk, gk = hk.loglik_grad(xs, gradonly=False)
+            hk.close()
+            out[layout] = (lp, g, w, lpk, gk)
+            for k in (0, K - 1):
+                lp_o, g_o = M.log_likelihood(xs[k], gradonly=False)
+                assert abs(lp[k] - lp_o) <= 1e-8 * abs(lp_o) and relerr(g[k], g_o) <= 1e-5, layout
+                lpk_o, gk_o = M.log_likelihood(xs[k], gradonly=False, ks=ks)
+                assert abs(lpk[k] - lpk_o) <= 1e-8 * abs(lpk_o) and relerr(gk[k], gk_o) <= 1e-5, layout
+        a, b = out["split"], out["fused"]
+        assert relerr(a[1], b[1]) <= 1e-6 and relerr(a[0], b[0]) <= 1e-9      # rows > 4 entries: Float32 vs Float64 row sums
+        assert relerr(a[2], b[2]) <= 5e-7                                       # 1/p per row, original row order
+        assert relerr(a[4], b[4]) <= 1e-6

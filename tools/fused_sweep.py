@@ -9,10 +9,18 @@ from bench import generate
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="c3")
+ap.add_argument("--ranks", type=int, default=1, help="time rank 0's row block of an R-way equal-nnz partition")
 ap.add_argument("geoms", nargs="*", default=["512:4096"])
 a = ap.parse_args()
 s, tree, K = generate(a.config, "cuda:0")
-cp, rv, nz = s["colptr"].to(torch.int32), s["rowval"].to(torch.int32), s["nzval"].contiguous()
+from bench import row_block_device, equal_nnz_bounds
+m_loc = s["m"]
+if a.ranks > 1:
+    bounds = equal_nnz_bounds(s, a.ranks)
+    m_loc, cp, rv, nz = row_block_device(s, bounds[0], bounds[1])
+    nz = nz.contiguous()
+else:
+    cp, rv, nz = s["colptr"].to(torch.int32), s["rowval"].to(torch.int32), s["nzval"].contiguous()
 eff = s["efflens"].cpu().numpy()
 for geom in a.geoms:
     parts = geom.split(":")
@@ -26,7 +34,7 @@ for geom in a.geoms:
         else:
             os.environ.pop("POLEE_FUSED_CTAS", None)
     h = pb.Handle(num_mc_samples=K, num_steps=10)
-    h.set_matrix_device(s["m"], s["n"], cp.data_ptr(), rv.data_ptr(), nz.data_ptr())
+    h.set_matrix_device(m_loc, s["n"], cp.data_ptr(), rv.data_ptr(), nz.data_ptr())
     h.set_efflens(eff)
     h.set_tree(*tree)
     h.init_params()
