@@ -190,6 +190,16 @@ const char *polee_hsb_last_error(void);
 int polee_make_inverse_ptt_params(int64_t num_nodes, const int32_t *node_parent_idxs, const int32_t *node_js,
                                   int32_t *left_index, int32_t *right_index, int32_t *leaf_index);
 
+/* Exact row de-duplication (tools/exact-factorization.jl:31-68): rows of X that agree in their transcript ids and
+ * Float32 values bit for bit are merged; counts[u] = multiplicity of unique row u.  The compressed matrix + counts go
+ * to polee_set_matrix_csc(..., ks = counts) (the factored likelihood, likelihood.jl:59-85) and give the same
+ * likelihood and gradient as the original.  Unique rows are numbered by first occurrence (the reference's order is a
+ * Julia Dict's iteration order, i.e. unspecified).  Host arrays in and out; rowval_out / nzval_out need room for nnz
+ * entries, counts_out for m.  Runs on `device` (sorts + scans), standalone: no handle needed. */
+int polee_exact_factorization(int32_t device, int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,
+                              const float *nzval, int64_t *m_unique, uint32_t *colptr_out /* n+1 */,
+                              uint32_t *rowval_out, float *nzval_out, int64_t *counts_out, int64_t *nnz_out);
+
 /* ------------------------------------------------------------------ multi-GPU (row-partitioned X)
  * Each rank holds a contiguous row block (equal nnz) and all n columns; one ncclAllReduce(sum) of the
  * transcript-length gradient g[n][K] (+K log-likelihoods) per ADAM step.  No reference counterpart

@@ -139,6 +139,38 @@ def gene_noninformative_prior(efflens, xls, xs, x_grad, gene_transcripts):
     return xl_grad
 
 
+def exact_factorization(m, n, colptr, rowval, nzval):
+    """tools/exact-factorization.jl:31-68: one copy of every distinct row (transcript ids + Float32 values, compared
+    bit for bit) and its multiplicity.  The reference numbers the unique rows in the iteration order of a Julia Dict
+    (unspecified); here, and in the device implementation, by first occurrence.  Returns (m_unique, colptr, rowval,
+    nzval, counts) with 1-based UInt32 CSC arrays like the input."""
+    colptr = np.asarray(colptr, np.int64); rowval = np.asarray(rowval, np.int64); nzval = _c(nzval, np.float32)
+    nnz = len(rowval)
+    col_of = np.repeat(np.arange(n, dtype=np.int64), np.diff(colptr))
+    order = np.argsort(rowval, kind="stable")                      # Xt = transpose(X): row-major, ascending transcript
+    rptr = np.zeros(m + 1, np.int64)
+    np.add.at(rptr, rowval, 1)
+    rptr = np.cumsum(rptr)
+    cols_r, vals_r = col_of[order], nzval[order]
+    seen, uidx, counts = {}, np.zeros(m, np.int64), []
+    for i in range(m):
+        a, b = rptr[i], rptr[i + 1]
+        key = (cols_r[a:b].tobytes(), vals_r[a:b].tobytes())       # :38-40
+        u = seen.get(key)
+        if u is None:
+            u = seen[key] = len(counts)
+            counts.append(0)
+            uidx[i] = u + 1
+        counts[u] += 1
+    keep = uidx[rowval - 1] > 0                                    # the first occurrences' entries, CSC order kept
+    new_rowval = uidx[rowval - 1][keep].astype(np.uint32)
+    new_nzval = nzval[keep]
+    cnt = np.zeros(n, np.int64)
+    np.add.at(cnt, col_of[keep], 1)
+    new_colptr = np.concatenate([[1], 1 + np.cumsum(cnt)]).astype(np.uint32)
+    return len(counts), new_colptr, new_rowval, new_nzval, np.asarray(counts, np.int64)
+
+
 # ------------------------------------------------------------------ ptt
 class PTT:
     def __init__(self, parent_idxs, js):

@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     PolyaTreeTransform,
     RNASeqSample,
     approximate_likelihood,
+    exact_factorization,
     hsb,
     inv_hsb,
     inv_hsb_grad,

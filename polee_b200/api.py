@@ -255,6 +255,26 @@ class Handle:
         self.check(self.lib.polee_comm_init(self.h, C.c_int32(nranks), C.c_int32(rank), C.c_char_p(unique_id)))
 
 
+def exact_factorization(sample, device=0):
+    """tools/exact-factorization.jl:31-68 on the device: (compressed RNASeqSample, counts).  Feed the pair to
+    approximate_likelihood(..., ks=counts) / Handle.set_sample(sample, ks): same likelihood, fewer rows to stream."""
+    lib = L.load_library()
+    nnz = len(sample.rowval)
+    colptr = np.zeros(sample.n + 1, np.uint32)
+    rowval = np.zeros(max(nnz, 1), np.uint32)
+    nzval = np.zeros(max(nnz, 1), np.float32)
+    counts = np.zeros(sample.m, np.int64)
+    mu, nu = C.c_int64(), C.c_int64()
+    rc = lib.polee_exact_factorization(C.c_int32(device), C.c_int64(sample.m), C.c_int64(sample.n), _p(sample.colptr),
+                                       _p(sample.rowval), _p(sample.nzval), C.byref(mu), _p(colptr), _p(rowval), _p(nzval),
+                                       _p(counts), C.byref(nu))
+    if rc != 0:
+        raise L.PoleeError(rc, "polee_exact_factorization failed")
+    out = RNASeqSample(mu.value, sample.n, colptr, rowval[:nu.value].copy(), nzval[:nu.value].copy(),
+                       sample.effective_lengths)
+    return out, counts[:mu.value].copy()
+
+
 def trim_memory(device=-1):
     """Return the device memory cached from destroyed handles to the driver (polee_trim_memory)."""
     L.load_library().polee_trim_memory(C.c_int32(device))

@@ -483,3 +483,43 @@ def test_split_and_fused_layouts_agree(pb, fx, small_synth, oracle, K, monkeypat
         assert relerr(a[1], b[1]) <= 1e-6 and relerr(a[0], b[0]) <= 1e-9      # rows > 4 entries: Float32 vs Float64 row sums
         assert relerr(a[2], b[2]) <= 5e-7                                       # 1/p per row, original row order
         assert relerr(a[4], b[4]) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_exact_factorization_on_device(pb, fx, small_synth, oracle):
+    """polee_exact_factorization vs the restated tools/exact-factorization.jl: identical unique rows, counts and CSC
+    arrays (bit for bit; rows numbered by first occurrence), and the factored likelihood of the compressed sample
+    equals the plain likelihood of the original."""
+    rng = np.random.default_rng(77)
+    # the fixture as is (2 % duplicates), and a synthetic sample with every row repeated 1-4 times
+    s = small_synth
+    X = []
+    import scipy.sparse as sp
+    A = sp.csc_matrix((s["nzval"], s["rowval"].astype(np.int64) - 1, s["colptr"].astype(np.int64) - 1),
+                      shape=(s["m"], s["n"])).tocsr()
+    reps = rng.integers(1, 5, size=2000)
+    rows = np.repeat(rng.integers(0, s["m"], size=2000), reps)
+    rng.shuffle(rows)
+    B = A[rows].tocsc()
+    B.sort_indices()
+    dup = (B.shape[0], B.shape[1], (B.indptr + 1).astype(np.uint32), (B.indices + 1).astype(np.uint32),
+           B.data.astype(np.float32), s["efflens"])
+    for (m, n, colptr, rowval, nzval, eff) in ((fx.m, fx.n, fx.colptr, fx.rowval, fx.nzval, fx.efflens), dup):
+        sample = pb.RNASeqSample(m, n, colptr, rowval, nzval, eff)
+        comp, counts = pb.exact_factorization(sample)
+        mu, cp, rv, nz, cnt = oracle.exact_factorization(m, n, colptr, rowval, nzval)
+        assert comp.m == mu and counts.sum() == m
+        assert np.array_equal(counts, cnt) and np.array_equal(comp.colptr, cp)
+        assert np.array_equal(comp.rowval, rv) and np.array_equal(comp.nzval.view(np.uint32), nz.view(np.uint32))
+        xs = rng.dirichlet(np.ones(n), 2).astype(np.float32).clip(1e-10)
+        tree = pb.sequential_tree(n) if hasattr(pb, "sequential_tree") else pb.api.sequential_tree(n)
+        h0 = pb.Handle(num_mc_samples=2, gradonly=False)
+        h0.set_sample(sample); h0.set_tree(*tree)
+        lp0, g0 = h0.loglik_grad(xs, gradonly=False)
+        h0.close()
+        h1 = pb.Handle(num_mc_samples=2, gradonly=False)
+        h1.set_sample(comp, counts); h1.set_tree(*tree)
+        lp1, g1 = h1.loglik_grad(xs, gradonly=False)
+        h1.close()
+        assert relerr(lp1, lp0) <= 1e-10 and relerr(g1, g0) <= 1e-6
+    assert dup[0] > 2 * comp.m * 0.9                                  # the synthetic case really was ~2.5x redundant
