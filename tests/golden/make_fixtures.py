@@ -10,9 +10,9 @@ Inputs (reference test data):
   test/dataset/mBr_M_6w_1.likelihood-matrix.h5   written by rnaseq_sample.jl:505-519
   test/dataset/mBr_M_6w_1.prep.h5                written by likelihood-approximation.jl:61-87
 
-No HDF5 library exists in this image, so this is a ~150-line reader of exactly the
-HDF5 features those two files use (superblock v0, v1 object headers, compact link
-messages or a single fractal-heap direct block, contiguous / chunked+deflate layouts).
+No HDF5 library exists in this image; polee_b200/h5min.py reads exactly the HDF5 features
+those two files use (superblock v0, v1 object headers, compact link messages or a single
+fractal-heap direct block, contiguous / chunked+deflate layouts).
 """
 import hashlib
 import json
@@ -27,139 +27,8 @@ REF = "/root/reference/test/dataset"
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
-def read_object_header(buf, addr):
-    """v1 object header -> list of (type, body); follows continuation messages."""
-    ver, _, nmsgs, _refc, hsize = struct.unpack_from("<BBHII", buf, addr)
-    assert ver == 1, ver
-    msgs, blocks = [], [(addr + 16, hsize)]
-    while blocks and len(msgs) < nmsgs:
-        off, size = blocks.pop(0)
-        end = off + size
-        while off + 8 <= end and len(msgs) < nmsgs:
-            t, s, _fl = struct.unpack_from("<HHB", buf, off)
-            body = buf[off + 8: off + 8 + s]
-            msgs.append((t, body))
-            if t == 0x10:
-                o, l = struct.unpack_from("<QQ", body, 0)
-                blocks.append((o, l))
-            off += 8 + s
-    return msgs
-
-
-def parse_link(body):
-    """link message v1 -> (name, object header address) for hard links."""
-    ver, flags = body[0], body[1]
-    assert ver == 1
-    p = 2
-    ltype = 0
-    if flags & 0x08:
-        ltype = body[p]; p += 1
-    if flags & 0x04:
-        p += 8
-    if flags & 0x10:
-        p += 1
-    w = 1 << (flags & 3)
-    nlen = int.from_bytes(body[p:p + w], "little"); p += w
-    name = body[p:p + nlen].decode(); p += nlen
-    assert ltype == 0
-    return name, struct.unpack_from("<Q", body, p)[0]
-
-
-def parse_dtype(body):
-    cls = body[0] & 0x0F
-    size = struct.unpack_from("<I", body, 4)[0]
-    if cls == 0:
-        signed = bool(body[1] & 0x08)
-        return np.dtype(("<i" if signed else "<u") + str(size))
-    if cls == 1:
-        return np.dtype("<f" + str(size))
-    raise ValueError("unsupported datatype class %d" % cls)
-
-
-def parse_dataspace(body):
-    ver, rank = body[0], body[1]
-    off = 8 if ver == 1 else 4
-    return [struct.unpack_from("<Q", body, off + 8 * i)[0] for i in range(rank)]
-
-
-def read_chunks(buf, addr, ndims, out):
-    """v1 B-tree (node type 1) over deflate-compressed chunks."""
-    assert buf[addr:addr + 4] == b"TREE", buf[addr:addr + 4]
-    ntype, level, nent = struct.unpack_from("<BBH", buf, addr + 4)
-    assert ntype == 1
-    p = addr + 24
-    keysz = 8 + 8 * ndims
-    for _ in range(nent):
-        nbytes, _mask = struct.unpack_from("<II", buf, p)
-        offs = struct.unpack_from("<%dQ" % ndims, buf, p + 8)
-        child = struct.unpack_from("<Q", buf, p + keysz)[0]
-        if level == 0:
-            out.append((offs[0], zlib.decompress(buf[child:child + nbytes])))
-        else:
-            read_chunks(buf, child, ndims, out)
-        p += keysz + 8
-
-
-def read_dataset(buf, addr):
-    msgs = read_object_header(buf, addr)
-    dims = dtype = layout = None
-    filtered = False
-    for t, b in msgs:
-        if t == 0x01:
-            dims = parse_dataspace(b)
-        elif t == 0x03:
-            dtype = parse_dtype(b)
-        elif t == 0x08:
-            layout = b
-        elif t == 0x0B:
-            filtered = True
-    count = int(np.prod(dims)) if dims else 1
-    assert layout[0] == 3
-    cls = layout[1]
-    if cls == 1:
-        a, _sz = struct.unpack_from("<QQ", layout, 2)
-        assert not filtered
-        return np.frombuffer(buf, dtype, count, a).copy()
-    if cls == 2:
-        nd = layout[2]
-        bt = struct.unpack_from("<Q", layout, 3)[0]
-        cdims = struct.unpack_from("<%dI" % nd, layout, 11)
-        chunks = []
-        read_chunks(buf, bt, nd, chunks)
-        arr = np.empty(count, dtype)
-        for off, raw in chunks:
-            a = np.frombuffer(raw if filtered else raw, dtype)
-            nn = min(len(a), count - off, cdims[0])
-            arr[off:off + nn] = a[:nn]
-        return arr
-    raise ValueError("layout class %d" % cls)
-
-
-def root_links(buf):
-    root = struct.unpack_from("<Q", buf, 56 + 8)[0]
-    links = {}
-    for t, b in read_object_header(buf, root):
-        if t == 0x06:
-            name, addr = parse_link(b)
-            links[name] = addr
-    if links:
-        return links
-    # dense link storage: scan the single fractal-heap direct block
-    p = buf.find(b"FHDB")
-    assert p >= 0
-    end = len(buf)
-    q = p
-    while True:
-        q = buf.find(b"\x01\x10\x01", q + 1)
-        if q < 0 or q > end:
-            break
-        nlen = buf[q + 3]
-        name = buf[q + 4:q + 4 + nlen]
-        if 0 < nlen < 64 and name.isascii() and name.replace(b"_", b"a").isalnum():
-            addr = struct.unpack_from("<Q", buf, q + 4 + nlen)[0]
-            if addr < len(buf):
-                links[name.decode()] = addr
-    return links
+sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+from polee_b200.h5min import read_dataset, root_links  # noqa: E402  (the reader lives in the package: SURVEY 8f-3)
 
 
 def sha(a):

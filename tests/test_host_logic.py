@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, Fixture
 
 
 @pytest.fixture(scope="module")
@@ -137,3 +137,42 @@ def test_opts_struct_layout_matches_header_in_python_and_julia():
     jfields = re.findall(r"(\w+)::(Int32|UInt64|Float64)", jbody)
     jmap = {"int32_t": "Int32", "uint64_t": "UInt64", "double": "Float64"}
     assert [(n, jmap[t]) for t, n in fields] == jfields
+
+
+def test_h5min_prep_roundtrip_and_reference_files(tmp_path):
+    """the harness-side reader/writer of Polee's two HDF5 formats.  write_prep -> read_prep round trip
+    (the file write_approximation produces, likelihood-approximation.jl:61-87), structural checks on the bytes, and
+    -- where the reference checkout is present (the build container) -- the reference's own files decode to the
+    committed golden arrays."""
+    import struct
+    from polee_b200 import h5min
+    rng = np.random.default_rng(1)
+    n, m = 313, 19743
+    params = {"mu": rng.normal(size=n - 1).astype(np.float32), "omega": rng.normal(size=n - 1).astype(np.float32),
+              "alpha": rng.normal(size=n - 1).astype(np.float32),
+              "node_parent_idxs": rng.integers(0, 2 * n - 1, 2 * n - 1).astype(np.int32),
+              "node_js": rng.integers(0, n, 2 * n - 1).astype(np.int32)}
+    eff = rng.uniform(1, 5000, n).astype(np.float32)
+    path = str(tmp_path / "x.prep.h5")
+    size = h5min.write_prep(path, params, n, m, eff, gfffilename="genes.gff3", gffhash="q83vEjRWeJA=", date="2026-10-17",
+                            args="prep-sample a b")
+    raw = open(path, "rb").read()
+    assert len(raw) == size and raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0 and raw[13] == 8 and raw[14] == 8
+    assert struct.unpack_from("<Q", raw, 40)[0] == size                        # end-of-file address
+    back = h5min.read_prep(path)
+    assert back["n"] == n and back["m"] == m and back["n"].dtype == np.int64
+    assert np.array_equal(back["effective_lengths"], eff)
+    for k, v in params.items():
+        assert back[k].dtype == v.dtype and np.array_equal(back[k], v)
+    md = back["metadata"]
+    assert md["version"] == 2 and md["approximation"] == "Polee.LogitSkewNormalPTTApprox"
+    assert md["gfffilename"] == "genes.gff3" and md["gffhash"] == "q83vEjRWeJA=" and md["args"] == "prep-sample a b"
+    ref = "/root/reference/test/dataset"
+    if not os.path.exists(ref):
+        pytest.skip("reference checkout not present (GPU box): the decode of its files is pinned by tests/golden")
+    fx = Fixture()
+    lm = h5min.read_likelihood_matrix(os.path.join(ref, "mBr_M_6w_1.likelihood-matrix.h5"))
+    assert (lm["m"], lm["n"]) == (fx.m, fx.n) and np.array_equal(lm["colptr"], fx.colptr)
+    assert np.array_equal(lm["rowval"], fx.rowval) and np.array_equal(lm["nzval"], fx.nzval)
+    pp = h5min.read_prep(os.path.join(ref, "mBr_M_6w_1.prep.h5"))
+    assert np.array_equal(pp["mu"], fx.mu) and np.array_equal(pp["node_js"], fx.js) and pp["n"] == fx.n
