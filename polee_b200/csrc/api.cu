@@ -172,12 +172,6 @@ extern "C" const char *polee_last_error(const polee_handle *h) {
 }
 
 // ------------------------------------------------------------------ inputs
-static int check_dims(polee_handle *h, int64_t n) {
-    if (h->have_matrix && h->n != n) return h->fail(POLEE_EINVAL, "n differs from the matrix already set");
-    if (h->have_tree && h->td.n != n) return h->fail(POLEE_EINVAL, "n differs from the tree already set");
-    return POLEE_OK;
-}
-
 extern "C" int polee_set_matrix_csc_device(polee_handle *h, int64_t m, int64_t n, const uint32_t *d_colptr,
                                            const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks) {
     CHECK_H(h);

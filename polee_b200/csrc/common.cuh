@@ -227,7 +227,7 @@ struct polee_handle {
     unsigned char *ft_blob = nullptr;
     polee::FusedTileDesc *ft_desc = nullptr;
     int ft_tiles = 0;
-    uint32_t ft_max_blob = 0, ft_max_E = 0, ft_max_rows = 0, ft_max_C = 0, ft_max_slots = 0;
+    uint32_t ft_max_blob = 0, ft_max_E = 0, ft_max_rows = 0, ft_max_C = 0;
     uint32_t *ft_row_of_pos = nullptr;  // original row of every (tile-sorted) row position
     uint64_t ft_blob_bytes = 0;
     int64_t ft_parts = 0;            // (tile, column) partials

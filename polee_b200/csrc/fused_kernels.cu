@@ -1,17 +1,20 @@
 // fused_kernels.cu -- K1 and K2 of one ADAM step in ONE pass over the matrix ("row tiles", layout in common.cuh).
 //
 // The split kernels (sparse_kernels.cu) stream the matrix twice per step and round-trip w = 1/p through HBM:
-// 2 x nnz x 8 B + 2 x K x m x 4 B = 4.0 GB at C3.  Here a CTA takes a tile of <= 256 consecutive rows (~1-2 k
-// entries, one bulk copy), computes p and w for the rows (pAt_mul_B!, src/sparse.jl:6-21), keeps w in shared memory,
-// and immediately forms the tile's contribution to g = X^T w (pAt_mulinv_B!, src/sparse.jl:25-40) by walking the same
-// entries column-major through a 16-bit permutation.  What leaves the SM is one partial sum per (tile, column) --
-// rows arrive sorted by genomic position (src/rnaseq_sample.jl:399-419), so a tile touches a handful of columns.
-// A second, small pass adds the partials of every column in tile order.  Bytes per step: nnz x 10 B + rows x 2 B
-// + partials, ~1.4 GB at C3 instead of 4.0 GB.
+// 2 x nnz x 8 B + 2 x K x m x 4 B = 4.0 GB at C3.  Here a CTA takes a tile of <= 512 consecutive rows (~1.5 k entries,
+// one bulk copy), stages x of the tile's <= 255 distinct columns in shared memory, computes p and w for the rows
+// (pAt_mul_B!, src/sparse.jl:6-21), keeps w in shared memory, and immediately forms the tile's contribution to
+// g = X^T w (pAt_mulinv_B!, src/sparse.jl:25-40) from a second, column-major copy of the entries.  What leaves the SM
+// is one partial sum per column segment -- rows arrive sorted by genomic position (src/rnaseq_sample.jl:399-419), so
+// a tile touches a handful of columns.  A second, small pass adds the partials of every column (contiguous in the
+// column-ordered partial array).  ~1.6 GB per step at C3 instead of 4.0 GB -- but the pass is bound by the
+// shared-memory pipe (a 32-byte read of x and one of w per entry), not by HBM, and only beats the split pair where
+// columns are short; matrix_setup.cu picks the layout ("K12").
 //
-// Arithmetic = the split fast path: rows of <= 4 entries are summed in Float32 (FFMA) and inverted with
-// rcp.approx, longer rows add Float32 batches of four into a Float64 sum (bit-identical p and w to k1_sell_fwd_tma);
-// column sums: Float32 over <= FT_CHUNK entries, Float64 above.  No atomics, fixed orders: run-to-run identical.
+// Arithmetic: p = Float32 batches of four products (FFMA2) summed in Float32, w = rcp.approx(p) (the split fast path
+// does the same for rows of <= 4 entries and keeps a Float64 row sum above that); column sums: Float32 over a segment
+// of <= FT_SEG entries (lane partials + shuffle reduce-scatter), Float64 across segments and tiles.  No atomics, fixed
+// orders: run-to-run identical.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -147,8 +150,6 @@ __device__ __forceinline__ void warp_reduce_store(float (&acc)[KP], int lane, fl
         }
     }
 }
-
-__device__ __forceinline__ void consumer_sync() { __syncthreads(); }
 
 template <int KP, bool LP, bool WEIGHTED, bool WRITE_W>
 __global__ void __launch_bounds__(FC_THREADS, 3)

@@ -703,7 +703,6 @@ int launch_reparam_fwd(polee_handle *h, int KP, int K, const float *noise, int64
     return launch_elem(h, KP, K, false, false, true, noise, noise_steps, want_ladj, nullptr, -1, 0, 1);
 }
 
-constexpr int S_BOT_THREADS = 512;
 constexpr int S_TOP_THREADS = 1024;
 
 template <typename F>
@@ -719,11 +718,6 @@ static int tree_variant() {
         v = e ? atoi(e) : 0;
     }
     return v;
-}
-static int variant_kpc(int KP) {
-    const int v = tree_variant();
-    const int want = v == 1 ? 4 : (v == 2 ? 2 : 8);
-    return KP < want ? KP : want;
 }
 
 template <int KP, int KPC, int THREADS, int MINB>
