@@ -238,8 +238,8 @@ extern "C" int polee_set_efflens(polee_handle *h, const float *efflens) {
     for (int64_t j = 0; j < n; ++j) adj[j] = (float)n * (1.0f / efflens[j]);  // likelihood.jl:105, Float32
     CK(polee::dmalloc((void **)&h->efflen, sizeof(float) * n));
     CK(polee::dmalloc((void **)&h->efflen_adj, sizeof(float) * n));
-    CK(cudaMemcpy(h->efflen, efflens, sizeof(float) * n, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->efflen_adj, adj.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+    CK(polee::copy_sync(h->stream, h->efflen, efflens, sizeof(float) * n, cudaMemcpyHostToDevice));
+    CK(polee::copy_sync(h->stream, h->efflen_adj, adj.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
     h->have_efflen = true;
     return patch_leaf_records(h);
 }
@@ -278,8 +278,8 @@ extern "C" int polee_set_gene_groups(polee_handle *h, int64_t num_genes, const i
     if (h->n_genes == 0) return POLEE_OK;  // nothing but single-transcript genes: the prior is identically zero
     CK(polee::dmalloc((void **)&h->gene_ptr, sizeof(int64_t) * ptr.size()));
     CK(polee::dmalloc((void **)&h->gene_tx, sizeof(int32_t) * tx.size()));
-    CK(cudaMemcpy(h->gene_ptr, ptr.data(), sizeof(int64_t) * ptr.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->gene_tx, tx.data(), sizeof(int32_t) * tx.size(), cudaMemcpyHostToDevice));
+    CK(polee::copy_sync(h->stream, h->gene_ptr, ptr.data(), sizeof(int64_t) * ptr.size(), cudaMemcpyHostToDevice));
+    CK(polee::copy_sync(h->stream, h->gene_tx, tx.data(), sizeof(int32_t) * tx.size(), cudaMemcpyHostToDevice));
     return POLEE_OK;
 }
 
@@ -289,7 +289,7 @@ static int alloc_params(polee_handle *h) {
     float **ptrs[] = {&h->mu, &h->omega, &h->alpha, &h->m_mu, &h->m_omega, &h->m_alpha, &h->v_mu, &h->v_omega, &h->v_alpha};
     for (float **p : ptrs) {
         CK(polee::dmalloc((void **)p, sizeof(float) * nm1));
-        CK(cudaMemset(*p, 0, sizeof(float) * nm1));
+        CK(cudaMemsetAsync(*p, 0, sizeof(float) * nm1, h->stream));
     }
     return POLEE_OK;
 }
@@ -361,15 +361,15 @@ extern "C" int polee_init_params(polee_handle *h) {
     const int64_t nm1 = h->td.n - 1;
     if (nm1 > 0) {
         std::vector<float> om(nm1, logf(0.1f)), al(nm1, 0.0f);  // likelihood-approximation.jl:455-456
-        CK(cudaMemcpy(h->mu, h->mu0.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->omega, om.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->alpha, al.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        CK(polee::copy_sync(h->stream, h->mu, h->mu0.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        CK(polee::copy_sync(h->stream, h->omega, om.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        CK(polee::copy_sync(h->stream, h->alpha, al.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
         float *st[] = {h->m_mu, h->m_omega, h->m_alpha, h->v_mu, h->v_omega, h->v_alpha};
-        for (float *p : st) CK(cudaMemset(p, 0, sizeof(float) * nm1));
+        for (float *p : st) CK(cudaMemsetAsync(p, 0, sizeof(float) * nm1, h->stream));
     }
     StepCtl c{1, 1};
-    CK(cudaMemcpy(h->d_step, &c, sizeof(c), cudaMemcpyHostToDevice));
-    CK(cudaMemset(h->d_bad_step, 0, sizeof(int)));
+    CK(polee::copy_sync(h->stream, h->d_step, &c, sizeof(c), cudaMemcpyHostToDevice));
+    CK(cudaMemsetAsync(h->d_bad_step, 0, sizeof(int), h->stream));
     h->steps_enqueued = 0;
     h->reparam_ready = false;
     return POLEE_OK;
@@ -381,9 +381,9 @@ extern "C" int polee_get_params(polee_handle *h, float *mu, float *omega, float 
     const int64_t nm1 = h->td.n - 1;
     CK(cudaStreamSynchronize(h->stream));
     if (nm1 > 0) {
-        if (mu) CK(cudaMemcpy(mu, h->mu, sizeof(float) * nm1, cudaMemcpyDeviceToHost));
-        if (omega) CK(cudaMemcpy(omega, h->omega, sizeof(float) * nm1, cudaMemcpyDeviceToHost));
-        if (alpha) CK(cudaMemcpy(alpha, h->alpha, sizeof(float) * nm1, cudaMemcpyDeviceToHost));
+        if (mu) CK(polee::copy_sync(h->stream, mu, h->mu, sizeof(float) * nm1, cudaMemcpyDeviceToHost));
+        if (omega) CK(polee::copy_sync(h->stream, omega, h->omega, sizeof(float) * nm1, cudaMemcpyDeviceToHost));
+        if (alpha) CK(polee::copy_sync(h->stream, alpha, h->alpha, sizeof(float) * nm1, cudaMemcpyDeviceToHost));
     }
     return POLEE_OK;
 }
@@ -394,9 +394,9 @@ extern "C" int polee_set_params(polee_handle *h, const float *mu, const float *o
     const int64_t nm1 = h->td.n - 1;
     CK(cudaStreamSynchronize(h->stream));
     if (nm1 > 0) {
-        if (mu) CK(cudaMemcpy(h->mu, mu, sizeof(float) * nm1, cudaMemcpyHostToDevice));
-        if (omega) CK(cudaMemcpy(h->omega, omega, sizeof(float) * nm1, cudaMemcpyHostToDevice));
-        if (alpha) CK(cudaMemcpy(h->alpha, alpha, sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        if (mu) CK(polee::copy_sync(h->stream, h->mu, mu, sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        if (omega) CK(polee::copy_sync(h->stream, h->omega, omega, sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        if (alpha) CK(polee::copy_sync(h->stream, h->alpha, alpha, sizeof(float) * nm1, cudaMemcpyHostToDevice));
     }
     h->reparam_ready = false;
     return POLEE_OK;
@@ -413,7 +413,7 @@ extern "C" int polee_set_noise(polee_handle *h, const float *noise, int64_t num_
     if (!noise || num_steps <= 0) return POLEE_OK;
     const size_t count = (size_t)num_steps * h->K * (size_t)std::max<int64_t>(h->td.n - 1, 1);
     CK(polee::dmalloc((void **)&h->noise, sizeof(float) * count));
-    CK(cudaMemcpy(h->noise, noise, sizeof(float) * count, cudaMemcpyHostToDevice));
+    CK(polee::copy_sync(h->stream, h->noise, noise, sizeof(float) * count, cudaMemcpyHostToDevice));
     h->noise_steps = num_steps;
     return POLEE_OK;
 }
@@ -443,7 +443,7 @@ static int ready_for_steps(polee_handle *h) {
     if ((rc = ensure_gene_buffers(h, h->KP))) return rc;
     if (!h->elbo) {
         CK(polee::dmalloc((void **)&h->elbo, sizeof(double) * std::max(h->o.num_steps, 1)));
-        CK(cudaMemset(h->elbo, 0, sizeof(double) * std::max(h->o.num_steps, 1)));
+        CK(cudaMemsetAsync(h->elbo, 0, sizeof(double) * std::max(h->o.num_steps, 1), h->stream));
     }
     return POLEE_OK;
 }
@@ -524,6 +524,7 @@ static int enqueue_step(polee_handle *h) {
     if (!h->graph_exec) {
         // Relaxed: other host threads (one handle per thread in `polee prep`) may allocate, free or synchronise while
         // this thread records; the handle's streams are non-blocking, so nothing they do can join this capture.
+        std::shared_lock<std::shared_mutex> cap(polee::capture_mutex());  // no device-wide sync anywhere meanwhile
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
         rc = launch_step_sequence(h, true, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
         cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
@@ -551,7 +552,7 @@ extern "C" int polee_sync(polee_handle *h) {
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     int bad = 0;
-    CK(cudaMemcpy(&bad, h->d_bad_step, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(polee::copy_sync(h->stream, &bad, h->d_bad_step, sizeof(int), cudaMemcpyDeviceToHost));
     if (bad) return h->fail(POLEE_ENONFINITE, "non-finite gradient at step " + std::to_string(bad));
     return POLEE_OK;
 }
@@ -560,7 +561,7 @@ extern "C" int polee_get_elbo(polee_handle *h, double *elbo, int32_t nsteps) {
     CHECK_H(h);
     if (!h->elbo || !elbo) return h->fail(POLEE_EINVAL, "get_elbo: nothing recorded");
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(elbo, h->elbo, sizeof(double) * std::min(nsteps, std::max(h->o.num_steps, 1)), cudaMemcpyDeviceToHost));
+    CK(polee::copy_sync(h->stream, elbo, h->elbo, sizeof(double) * std::min(nsteps, std::max(h->o.num_steps, 1)), cudaMemcpyDeviceToHost));
     return POLEE_OK;
 }
 
@@ -599,7 +600,7 @@ template <typename T, typename U>
 static int download_kmajor(polee_handle *h, const T *dev, int K, int KP, int64_t len, U *host) {
     std::vector<T> tmp((size_t)len * KP);
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(tmp.data(), dev, sizeof(T) * tmp.size(), cudaMemcpyDeviceToHost));
+    CK(polee::copy_sync(h->stream, tmp.data(), dev, sizeof(T) * tmp.size(), cudaMemcpyDeviceToHost));
     for (int k = 0; k < K; ++k)
         for (int64_t i = 0; i < len; ++i) host[(size_t)k * len + i] = (U)tmp[(size_t)i * KP + k];
     return POLEE_OK;
@@ -646,7 +647,7 @@ extern "C" int polee_loglik_grad(polee_handle *h, const float *xs, int32_t K, in
         } else {
             std::vector<double> t(KP);
             CK(cudaStreamSynchronize(h->stream));
-            CK(cudaMemcpy(t.data(), h->g + (size_t)h->n * KP, sizeof(double) * KP, cudaMemcpyDeviceToHost));
+            CK(polee::copy_sync(h->stream, t.data(), h->g + (size_t)h->n * KP, sizeof(double) * KP, cudaMemcpyDeviceToHost));
             std::copy(t.begin(), t.begin() + K, lp);
         }
     }
@@ -668,7 +669,7 @@ extern "C" int polee_frag_prob_recip(polee_handle *h, const float *xs, float *w)
         if (!rc && e != cudaSuccess) rc = h->fail(POLEE_ECUDA, std::string("frag_prob_recip: ") + cudaGetErrorString(e));
         if (!rc) {
             std::vector<float> wp((size_t)h->m * KP);
-            e = cudaMemcpy(wp.data(), d_w, sizeof(float) * wp.size(), cudaMemcpyDeviceToHost);
+            e = polee::copy_sync(h->stream, wp.data(), d_w, sizeof(float) * wp.size(), cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) rc = h->fail(POLEE_ECUDA, std::string("frag_prob_recip: ") + cudaGetErrorString(e));
             for (int64_t i = 0; i < h->m; ++i) w[i] = wp[(size_t)i * KP];
         }
@@ -680,8 +681,8 @@ extern "C" int polee_frag_prob_recip(polee_handle *h, const float *xs, float *w)
     CK(cudaStreamSynchronize(h->stream));
     std::vector<float> wp(h->m_pad);
     std::vector<uint32_t> perm(h->m);
-    CK(cudaMemcpy(wp.data(), h->w, sizeof(float) * h->m_pad, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(perm.data(), h->row_perm, sizeof(uint32_t) * h->m, cudaMemcpyDeviceToHost));
+    CK(polee::copy_sync(h->stream, wp.data(), h->w, sizeof(float) * h->m_pad, cudaMemcpyDeviceToHost));
+    CK(polee::copy_sync(h->stream, perm.data(), h->row_perm, sizeof(uint32_t) * h->m, cudaMemcpyDeviceToHost));
     for (int64_t i = 0; i < h->m; ++i) w[i] = wp[perm[i]];
     return POLEE_OK;
 }
@@ -699,7 +700,7 @@ extern "C" int polee_ptt_transform(polee_handle *h, const double *ys, int32_t K,
     if (ladj) {
         const int ne = elem_ctas(h, KP);
         std::vector<double> part((size_t)h->n_tree_ctas * KP);
-        CK(cudaMemcpy(part.data(), h->ladj_partial + (size_t)2 * ne * KP, sizeof(double) * part.size(), cudaMemcpyDeviceToHost));
+        CK(polee::copy_sync(h->stream, part.data(), h->ladj_partial + (size_t)2 * ne * KP, sizeof(double) * part.size(), cudaMemcpyDeviceToHost));
         for (int k = 0; k < K; ++k) {
             double s = 0.0;
             for (int t = 0; t < h->n_tree_ctas; ++t) s += part[(size_t)t * KP + k];
@@ -760,7 +761,7 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
         if (!rc) rc = ensure_gene_buffers(h, h->KP);
         if (!rc && !h->elbo) {
             CK(polee::dmalloc((void **)&h->elbo, sizeof(double) * std::max(h->o.num_steps, 1)));
-            CK(cudaMemset(h->elbo, 0, sizeof(double) * std::max(h->o.num_steps, 1)));
+            CK(cudaMemsetAsync(h->elbo, 0, sizeof(double) * std::max(h->o.num_steps, 1), h->stream));
         }
     }
     if (rc) return rc;
@@ -770,11 +771,11 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
     double *d_xg = nullptr;
     CK(polee::dmalloc((void **)&d_noise, sizeof(float) * (size_t)K * std::max<int64_t>(nm1, 1)));
     CK(polee::dmalloc((void **)&d_xg, sizeof(double) * (size_t)n * KP));
-    CK(cudaMemcpy(d_noise, zs0, sizeof(float) * (size_t)K * nm1, cudaMemcpyHostToDevice));
+    CK(polee::copy_sync(h->stream, d_noise, zs0, sizeof(float) * (size_t)K * nm1, cudaMemcpyHostToDevice));
     StepCtl saved, one{1, 1};
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(&saved, h->d_step, sizeof(saved), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(h->d_step, &one, sizeof(one), cudaMemcpyHostToDevice));
+    CK(polee::copy_sync(h->stream, &saved, h->d_step, sizeof(saved), cudaMemcpyDeviceToHost));
+    CK(polee::copy_sync(h->stream, h->d_step, &one, sizeof(one), cudaMemcpyHostToDevice));
     rc = launch_elem(h, KP, K, false, false, true, d_noise, 1, !h->o.gradonly, nullptr);
     if (!rc) rc = launch_step_sequence(h, false, false, h->grad_out, d_xg, d_noise, 1);
     h->reparam_ready = false;
@@ -785,16 +786,16 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
     if (!rc && x_grad) rc = download_kmajor<double, double>(h, d_xg, K, KP, n, x_grad);
     if (!rc && y_grad) rc = download_kmajor<double, float>(h, h->ygrad, K, KP, nm1, y_grad);
     if (!rc && nm1 > 0) {
-        if (mu_grad) cudaMemcpy(mu_grad, h->grad_out, sizeof(float) * nm1, cudaMemcpyDeviceToHost);
-        if (omega_grad) cudaMemcpy(omega_grad, h->grad_out + nm1, sizeof(float) * nm1, cudaMemcpyDeviceToHost);
-        if (alpha_grad) cudaMemcpy(alpha_grad, h->grad_out + 2 * nm1, sizeof(float) * nm1, cudaMemcpyDeviceToHost);
+        if (mu_grad) polee::copy_sync(h->stream, mu_grad, h->grad_out, sizeof(float) * nm1, cudaMemcpyDeviceToHost);
+        if (omega_grad) polee::copy_sync(h->stream, omega_grad, h->grad_out + nm1, sizeof(float) * nm1, cudaMemcpyDeviceToHost);
+        if (alpha_grad) polee::copy_sync(h->stream, alpha_grad, h->grad_out + 2 * nm1, sizeof(float) * nm1, cudaMemcpyDeviceToHost);
     }
     if (!rc && elbo) {
         *elbo = 0.0;
-        if (!h->o.gradonly) cudaMemcpy(elbo, h->elbo, sizeof(double), cudaMemcpyDeviceToHost);
+        if (!h->o.gradonly) polee::copy_sync(h->stream, elbo, h->elbo, sizeof(double), cudaMemcpyDeviceToHost);
     }
-    cudaMemcpy(h->d_step, &saved, sizeof(saved), cudaMemcpyHostToDevice);
-    cudaMemset(h->d_bad_step, 0, sizeof(int));
+    polee::copy_sync(h->stream, h->d_step, &saved, sizeof(saved), cudaMemcpyHostToDevice);
+    cudaMemsetAsync(h->d_bad_step, 0, sizeof(int), h->stream);
     polee::dfree(d_noise);
     polee::dfree(d_xg);
     return rc;

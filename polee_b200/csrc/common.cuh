@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -315,6 +316,28 @@ struct polee_handle {
 namespace polee {
 
 int pad_k(int K);
+
+// Dynamic shared memory opt-in.  The attribute is per FUNCTION and process-wide, and several handles (host threads)
+// with different tile / tree sizes launch the same kernels: always raise it to the device limit, never to "what this
+// launch needs", or one handle's smaller value makes another handle's launch fail.
+// Copies and clears go through the handle's own (non-blocking) stream.  The legacy default stream does not order
+// against it: a cudaMemset, or the DMA tail of a pageable cudaMemcpy, issued there can still be in flight when the next
+// kernel of the handle starts -- harmless on an idle GPU, a data race as soon as other handles keep the GPU busy.
+inline cudaError_t copy_sync(cudaStream_t st, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, st);
+    return e == cudaSuccess ? cudaStreamSynchronize(st) : e;
+}
+
+constexpr int MAX_DYN_SMEM = 227 * 1024;
+template <typename F>
+inline cudaError_t allow_max_smem(F func) {
+    return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+}
+
+// Device-wide synchronisation (explicit, or implied by cudaFree / cudaMalloc) is not permitted while ANY stream of the
+// device is being captured into a graph, and it invalidates that capture -- also when the capture runs in another host
+// thread on another handle.  Captures therefore hold this lock shared, device-wide operations hold it exclusively.
+std::shared_mutex &capture_mutex();
 
 // mem_cache.cu: caching device allocator (cudaMalloc / cudaFree semantics, freed blocks are kept for the next sample)
 cudaError_t dmalloc(void **p, size_t bytes);

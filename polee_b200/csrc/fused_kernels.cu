@@ -387,7 +387,7 @@ int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, dou
 #define FK_LAUNCH(LPF, WF, WW)                                                                                           \
     do {                                                                                                                 \
         auto kern = k12_fused<KP, LPF, WF, WW>;                                                                          \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total);          \
+        cudaError_t e = allow_max_smem(kern);                                                                            \
         if (e != cudaSuccess) return h->fail(POLEE_ECUDA, std::string("fused kernel smem: ") + cudaGetErrorString(e));   \
         kern<<<h->ft_grid, FC_THREADS, cv.total, h->stream>>>(h->ft_desc, h->ft_tiles, h->ft_blob, x, h->ft_partial,     \
                                                               h->ft_row_weight, h->ft_row_of_pos, lp_partial, w_out,     \
@@ -419,7 +419,7 @@ int fused_grid(polee_handle *h, int KP) {
     const FcCarve cv = fc_carve(fused_ring_bytes(h), h->ft_max_rows, h->ft_max_C, KP);
     int per_sm = 1;
     auto probe = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total);
+        allow_max_smem(kern);
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, FC_THREADS, cv.total) == cudaSuccess && nb > 0) per_sm = nb;
     };

@@ -101,7 +101,7 @@ int ensure_gene_buffers(polee_handle *h, int KP) {
     release_gene_buffers(h);
     const int blocks = (int)((h->n_genes * KP + GP_THREADS - 1) / GP_THREADS);
     CK(polee::dmalloc((void **)&h->gene_xl_grad, sizeof(double) * (size_t)h->n * KP));
-    CK(cudaMemset(h->gene_xl_grad, 0, sizeof(double) * (size_t)h->n * KP));  // transcripts outside multi-transcript genes: 0 (:118)
+    CK(cudaMemsetAsync(h->gene_xl_grad, 0, sizeof(double) * (size_t)h->n * KP, h->stream));  // transcripts outside multi-transcript genes: 0 (:118)
     CK(polee::dmalloc((void **)&h->gene_off_partial, sizeof(double) * (size_t)blocks * KP));
     CK(polee::dmalloc((void **)&h->gene_off, sizeof(double) * KP));
     h->gene_KP = KP;

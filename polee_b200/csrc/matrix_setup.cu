@@ -136,11 +136,34 @@ __global__ void k_tile_row0(const uint32_t *__restrict__ flag, const uint32_t *_
     }
 }
 
-// rows of a tile longest first: key = tile << 16 | (0xFFFF - len)
-__global__ void k_row_sort_keys(const uint32_t *__restrict__ tile_incl, const uint32_t *__restrict__ row_len, int64_t m,
-                                uint64_t *keys, uint32_t *vals) {
+// column of every CSC entry + an order-independent hash of every row's column set
+__global__ void k_col_of(const uint32_t *__restrict__ colptr, int64_t n, const uint32_t *__restrict__ rowval, int64_t nnz,
+                         uint32_t *col_of, uint32_t *row_pattern) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = n;  // largest j with colptr[j] - 1 <= e
+        while (hi - lo > 1) {
+            int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)colptr[mid] - 1 <= e)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        col_of[e] = (uint32_t)lo;
+        uint32_t hsh = (uint32_t)lo * 0x9E3779B1u;
+        hsh ^= hsh >> 15;
+        hsh *= 0x85EBCA77u;
+        atomicAdd(&row_pattern[rowval[e] - 1u], hsh ^ (hsh >> 13));
+    }
+}
+
+// rows of a tile longest first, rows with the same column set next to each other (the lanes of a warp then read the
+// same x from shared memory -- a broadcast -- and a column's entries hit consecutive rows of w):
+// key = tile << 44 | (0xFFFF - len) << 28 | pattern hash (28 bits)
+__global__ void k_row_sort_keys(const uint32_t *__restrict__ tile_incl, const uint32_t *__restrict__ row_len,
+                                const uint32_t *__restrict__ row_pattern, int64_t m, uint64_t *keys, uint32_t *vals) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
-        keys[i] = ((uint64_t)(tile_incl[i] - 1u) << 16) | (uint64_t)(0xFFFFu - min(row_len[i], 0xFFFFu));
+        keys[i] = ((uint64_t)(tile_incl[i] - 1u) << 44) | ((uint64_t)(0xFFFFu - min(row_len[i], 0xFFFFu)) << 28) |
+                  (uint64_t)(row_pattern[i] & 0x0FFFFFFFu);
         vals[i] = (uint32_t)i;
     }
 }
@@ -158,24 +181,25 @@ __global__ void k_row_positions(const uint32_t *__restrict__ row_of_pos, const u
     }
 }
 
-__global__ void k_csc_expand(const uint32_t *__restrict__ colptr, int64_t n, const uint32_t *__restrict__ rowval,
-                             int64_t nnz, const uint32_t *__restrict__ tile_incl, const uint32_t *__restrict__ rpos,
-                             uint32_t *col_of, uint32_t *key_row, uint32_t *key_tile, uint32_t *val_e) {
+__global__ void k_csc_expand(const uint32_t *__restrict__ rowval, int64_t nnz, const uint32_t *__restrict__ rpos,
+                             uint32_t *key_row, uint32_t *val_e) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t lo = 0, hi = n;  // largest j with colptr[j] - 1 <= e
-        while (hi - lo > 1) {
-            int64_t mid = (lo + hi) >> 1;
-            if ((int64_t)colptr[mid] - 1 <= e)
-                lo = mid;
-            else
-                hi = mid;
-        }
-        const uint32_t r = rowval[e] - 1u;
-        col_of[e] = (uint32_t)lo;
-        key_row[e] = rpos[r];
-        key_tile[e] = tile_incl[r] - 1u;
+        key_row[e] = rpos[rowval[e] - 1u];
         val_e[e] = (uint32_t)e;
     }
+}
+
+// second order: the row-major list re-sorted (stably) by (tile, column) -> (tile, column, row position)
+__global__ void k_b_keys(const uint32_t *__restrict__ posA, const uint32_t *__restrict__ a_csc, int64_t nnz,
+                         const uint32_t *__restrict__ row_of_pos, const uint32_t *__restrict__ tile_incl,
+                         const uint32_t *__restrict__ col_of, uint64_t *keys) {
+    for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nnz; a += (int64_t)gridDim.x * blockDim.x)
+        keys[a] = ((uint64_t)(tile_incl[row_of_pos[posA[a]]] - 1u) << 32) | (uint64_t)col_of[a_csc[a]];
+}
+
+__global__ void k_b_tiles(const uint64_t *__restrict__ keys_sorted, int64_t nnz, uint32_t *tileB) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x)
+        tileB[q] = (uint32_t)(keys_sorted[q] >> 32);
 }
 
 __global__ void k_inverse_perm(const uint32_t *__restrict__ a_csc, int64_t nnz, uint32_t *apos_of_csc) {
@@ -462,37 +486,46 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
 
     // ---- rows of every tile longest first; row pointers in that order
     uint64_t *rkey, *rkey_s;
-    uint32_t *rval, *rpos, *len_sorted;
+    uint32_t *rval, *rpos, *len_sorted, *row_pattern, *col_of;
     CK(sc.alloc(&rkey, m)); CK(sc.alloc(&rkey_s, m)); CK(sc.alloc(&rval, m)); CK(sc.alloc(&rpos, m)); CK(sc.alloc(&len_sorted, m + 1));
+    CK(sc.alloc(&row_pattern, m)); CK(sc.alloc(&col_of, nnz + 1));
     CK(polee::dmalloc((void **)&h->ft_row_of_pos, sizeof(uint32_t) * m));
-    k_row_sort_keys<<<grid_for(m), TPB, 0, st>>>(tile_incl, row_len, m, rkey, rval);
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, rkey, rkey_s, rval, h->ft_row_of_pos, (int)m, 0, 64, st));
-    CK(ensure_tmp(need));
-    CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, rkey, rkey_s, rval, h->ft_row_of_pos, (int)m, 0,
-                                       16 + bits_for((uint64_t)n_tiles), st));
-    k_row_positions<<<grid_for(m + 1), TPB, 0, st>>>(h->ft_row_of_pos, row_len, m, rpos, len_sorted);
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, len_sorted, row_ptr, (int)(m + 1), st));
-    CK(ensure_tmp(need));
-    CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, len_sorted, row_ptr, (int)(m + 1), st));
-
-    // ---- the two entry orders: row-major (A) and column-major inside a tile (B)
-    uint32_t *col_of, *keyR, *keyT, *valE, *posA, *a_csc, *tileB, *b_csc, *apos_of_csc;
-    CK(sc.alloc(&col_of, nnz + 1)); CK(sc.alloc(&keyR, nnz)); CK(sc.alloc(&keyT, nnz)); CK(sc.alloc(&valE, nnz));
-    CK(sc.alloc(&posA, nnz)); CK(sc.alloc(&a_csc, nnz)); CK(sc.alloc(&tileB, nnz)); CK(sc.alloc(&b_csc, nnz + 1));
-    CK(sc.alloc(&apos_of_csc, nnz));
     uint32_t *d_colptr_own = nullptr;
     if (!d_colptr) {
         CK(sc.alloc(&d_colptr_own, n + 1));
         CK(cudaMemcpyAsync(d_colptr_own, colptr_host.data(), 4 * (n + 1), cudaMemcpyHostToDevice, st));
         d_colptr = d_colptr_own;
     }
+    CK(cudaMemsetAsync(row_pattern, 0, sizeof(uint32_t) * m, st));
+    if (nnz > 0) k_col_of<<<grid_for(nnz), TPB, 0, st>>>(d_colptr, n, d_rowval, nnz, col_of, row_pattern);
+    k_row_sort_keys<<<grid_for(m), TPB, 0, st>>>(tile_incl, row_len, row_pattern, m, rkey, rval);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, rkey, rkey_s, rval, h->ft_row_of_pos, (int)m, 0, 64, st));
+    CK(ensure_tmp(need));
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, rkey, rkey_s, rval, h->ft_row_of_pos, (int)m, 0,
+                                       44 + bits_for((uint64_t)n_tiles), st));
+    k_row_positions<<<grid_for(m + 1), TPB, 0, st>>>(h->ft_row_of_pos, row_len, m, rpos, len_sorted);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, len_sorted, row_ptr, (int)(m + 1), st));
+    CK(ensure_tmp(need));
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, len_sorted, row_ptr, (int)(m + 1), st));
+
+    // ---- the two entry orders: row-major (A) and column-major inside a tile (B)
+    uint32_t *keyR, *valE, *posA, *a_csc, *tileB, *b_csc, *apos_of_csc;
+    uint64_t *keyB, *keyB_s;
+    CK(sc.alloc(&keyR, nnz)); CK(sc.alloc(&valE, nnz)); CK(sc.alloc(&posA, nnz)); CK(sc.alloc(&a_csc, nnz));
+    CK(sc.alloc(&tileB, nnz)); CK(sc.alloc(&b_csc, nnz + 1)); CK(sc.alloc(&apos_of_csc, nnz));
+    CK(sc.alloc(&keyB, nnz)); CK(sc.alloc(&keyB_s, nnz));
     if (nnz > 0) {
-        k_csc_expand<<<grid_for(nnz), TPB, 0, st>>>(d_colptr, n, d_rowval, nnz, tile_incl, rpos, col_of, keyR, keyT, valE);
+        k_csc_expand<<<grid_for(nnz), TPB, 0, st>>>(d_rowval, nnz, rpos, keyR, valE);
         CK(cub::DeviceRadixSort::SortPairs(nullptr, need, keyR, posA, valE, a_csc, (int)nnz, 0, 32, st));
         CK(ensure_tmp(need));
         CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, keyR, posA, valE, a_csc, (int)nnz, 0, bits_for((uint64_t)m), st));
-        CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, keyT, tileB, valE, b_csc, (int)nnz, 0, bits_for((uint64_t)n_tiles), st));
         k_inverse_perm<<<grid_for(nnz), TPB, 0, st>>>(a_csc, nnz, apos_of_csc);
+        k_b_keys<<<grid_for(nnz), TPB, 0, st>>>(posA, a_csc, nnz, h->ft_row_of_pos, tile_incl, col_of, keyB);
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, keyB, keyB_s, a_csc, b_csc, (int)nnz, 0, 64, st));
+        CK(ensure_tmp(need));
+        CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, keyB, keyB_s, a_csc, b_csc, (int)nnz, 0,
+                                           32 + bits_for((uint64_t)n_tiles), st));
+        k_b_tiles<<<grid_for(nnz), TPB, 0, st>>>(keyB_s, nnz, tileB);
     }
     pt.mark("fused: row sort + two entry sorts");
     uint32_t *segstart, *colstart, *segs_before, *cols_before, *run_pos;
@@ -622,7 +655,7 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
     if (h_colptr_or_null)
         std::copy(h_colptr_or_null, h_colptr_or_null + n + 1, colptr.begin());
     else
-        CK(cudaMemcpy(colptr.data(), d_colptr, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost));
+        CK(polee::copy_sync(h->stream, colptr.data(), d_colptr, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost));
     if (colptr[0] != 1) return h->fail(POLEE_EINVAL, "set_matrix: colptr must be 1-based (colptr[1] == 1)");
     for (int64_t j = 0; j < n; ++j)
         if (colptr[j + 1] < colptr[j]) return h->fail(POLEE_EINVAL, "set_matrix: colptr is not non-decreasing");

@@ -29,6 +29,15 @@ std::unordered_map<void *, Live> g_live;                 // blocks handed out
 std::map<int, std::multimap<size_t, void *>> g_free;     // device -> size -> cached block
 std::map<int, size_t> g_cached_bytes;
 
+}  // namespace
+
+std::shared_mutex &capture_mutex() {
+    static std::shared_mutex mu;
+    return mu;
+}
+
+namespace {
+
 bool cache_enabled() {
     static const bool on = getenv("POLEE_NO_CACHE") == nullptr;
     return on;
@@ -40,7 +49,10 @@ void trim_locked(int device) {
         int cur = 0;
         cudaGetDevice(&cur);
         cudaSetDevice(dev.first);
-        for (auto &blk : dev.second) cudaFree(blk.second);
+        {
+            std::unique_lock<std::shared_mutex> cap(capture_mutex());
+            for (auto &blk : dev.second) cudaFree(blk.second);
+        }
         dev.second.clear();
         g_cached_bytes[dev.first] = 0;
         cudaSetDevice(cur);
@@ -68,10 +80,14 @@ cudaError_t dmalloc(void **p, size_t bytes) {
             return cudaSuccess;
         }
     }
-    e = cudaMalloc(p, want);
+    {
+        std::unique_lock<std::shared_mutex> cap(capture_mutex());
+        e = cudaMalloc(p, want);
+    }
     if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();  // clear the sticky-free error, release the cache, retry once
         trim_locked(device);
+        std::unique_lock<std::shared_mutex> cap(capture_mutex());
         e = cudaMalloc(p, want);
     }
     if (e == cudaSuccess) g_live[*p] = Live{want, device};
@@ -84,6 +100,7 @@ cudaError_t dfree(void *p) {
     auto it = g_live.find(p);
     if (it == g_live.end() || !cache_enabled()) {
         if (it != g_live.end()) g_live.erase(it);
+        std::unique_lock<std::shared_mutex> cap(capture_mutex());
         return cudaFree(p);
     }
     const Live blk = it->second;
@@ -91,7 +108,11 @@ cudaError_t dfree(void *p) {
     int cur = 0;
     cudaGetDevice(&cur);
     if (cur != blk.device) cudaSetDevice(blk.device);
-    cudaError_t e = cudaDeviceSynchronize();  // nothing in flight may still touch the block once it is reusable
+    cudaError_t e;
+    {
+        std::unique_lock<std::shared_mutex> cap(capture_mutex());
+        e = cudaDeviceSynchronize();  // nothing in flight may still touch the block once it is reusable
+    }
     if (cur != blk.device) cudaSetDevice(cur);
     g_free[blk.device].emplace(blk.bytes, p);
     g_cached_bytes[blk.device] += blk.bytes;

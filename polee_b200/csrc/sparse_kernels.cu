@@ -614,7 +614,7 @@ int launch_k1_t(polee_handle *h, const float *x, const double *xd, float *w, boo
     static const bool x_f64 = getenv("POLEE_K1_X") && !strcmp(getenv("POLEE_K1_X"), "f64");
 #define K1_LAUNCH3(LPF, WF, XF)                                                                                    \
     do {                                                                                                           \
-        cudaFuncSetAttribute(k1_sell_fwd_tma<KP, LPF, WF, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        allow_max_smem(k1_sell_fwd_tma<KP, LPF, WF, XF>);                                                              \
         k1_sell_fwd_tma<KP, LPF, WF, XF><<<grid, V2_THREADS, smem, h->stream>>>(                                   \
             h->row_tiles, h->n_row_tiles, h->sell_idx, h->sell_val, xd, x, w, h->row_weight, lp_partial);          \
     } while (0)
@@ -644,7 +644,7 @@ int launch_k2_t(polee_handle *h, const float *w, double *g) {
         static const bool no_pf = !(getenv("POLEE_K2_PREFETCH") && !strcmp(getenv("POLEE_K2_PREFETCH"), "1"));
 #define K2_LAUNCH(EX, PF)                                                                                           \
     do {                                                                                                            \
-        cudaFuncSetAttribute(k2_csc_grad_tma<KP, EX, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        allow_max_smem(k2_csc_grad_tma<KP, EX, PF>);                                                               \
         k2_csc_grad_tma<KP, EX, PF><<<grid, V2_THREADS, smem, h->stream>>>(h->segs, h->n_segs, h->csc_row, h->csc_val, \
                                                                            w, g, h->seg_partial);                  \
     } while (0)

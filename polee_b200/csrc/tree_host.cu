@@ -17,6 +17,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include <mutex>
 
 namespace polee {
 
@@ -334,6 +335,12 @@ std::string upload_tree(const TreeHost &th, TreeDev &td) {
     td.caterpillar = th.caterpillar;
     if (e == cudaSuccess && th.caterpillar) e = up(th.chain_leaf, &td.chain_leaf);
     if (e != cudaSuccess) return std::string("upload_tree: ") + cudaGetErrorString(e);
+    // the pageable-memory copies above run on the legacy stream, which does not order against the handle's
+    // non-blocking stream: make sure their DMA tails have landed before any kernel can read the tree
+    {
+        std::unique_lock<std::shared_mutex> cap(capture_mutex());
+        if (cudaDeviceSynchronize() != cudaSuccess) return "upload_tree: device synchronisation failed";
+    }
     return "";
 }
 

@@ -645,12 +645,12 @@ int ensure_work_buffers(polee_handle *h, int KP) {
     CK(polee::dmalloc((void **)&h->S, sizeof(double) * KP));
     CK(polee::dmalloc((void **)&h->ladj_partial, sizeof(double) * (2 * (size_t)elem_ctas(h, KP) + h->n_tree_ctas) * KP));
     CK(polee::dmalloc((void **)&h->grad_out, sizeof(float) * 3 * nm1));
-    CK(cudaMemset(h->S_partial, 0, sizeof(double) * h->n_tree_ctas * KP));
-    CK(cudaMemset(h->ladj_partial, 0, sizeof(double) * (2 * (size_t)elem_ctas(h, KP) + h->n_tree_ctas) * KP));
-    CK(cudaMemset(h->g, 0, sizeof(double) * (n + 1) * KP));
+    CK(cudaMemsetAsync(h->S_partial, 0, sizeof(double) * h->n_tree_ctas * KP, h->stream));
+    CK(cudaMemsetAsync(h->ladj_partial, 0, sizeof(double) * (2 * (size_t)elem_ctas(h, KP) + h->n_tree_ctas) * KP, h->stream));
+    CK(cudaMemsetAsync(h->g, 0, sizeof(double) * (n + 1) * KP, h->stream));
     if (h->have_matrix) {
         CK(polee::dmalloc((void **)&h->w, sizeof(float) * std::max<int64_t>(h->m_pad, 1) * KP));
-        CK(cudaMemset(h->w, 0, sizeof(float) * std::max<int64_t>(h->m_pad, 1) * KP));
+        CK(cudaMemsetAsync(h->w, 0, sizeof(float) * std::max<int64_t>(h->m_pad, 1) * KP, h->stream));
         CK(polee::dmalloc((void **)&h->seg_partial, sizeof(double) * std::max(h->n_slots, 1) * KP));
         CK(polee::dmalloc((void **)&h->lp_partial, sizeof(double) * std::max(std::max(h->n_row_tiles, h->ft_tiles), 1) * KP));
         if (h->fused) {
@@ -707,7 +707,8 @@ constexpr int S_TOP_THREADS = 1024;
 
 template <typename F>
 static void set_smem_attr(F func, size_t bytes) {
-    cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    (void)bytes;
+    allow_max_smem(func);  // per-function, process-wide: see common.cuh
 }
 
 // bottom-forest launch variants (draws per CTA, threads, min CTAs/SM); POLEE_TREE_VARIANT picks one at run time

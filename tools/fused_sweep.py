@@ -27,7 +27,7 @@ for geom in a.geoms:
     if parts[0] == "split":
         os.environ["POLEE_LAYOUT"] = "split"
     else:
-        os.environ.pop("POLEE_LAYOUT", None)
+        os.environ["POLEE_LAYOUT"] = "fused"
         os.environ["POLEE_FT_ROWS"], os.environ["POLEE_FT_WINDOW"] = parts[0], parts[1]
         if len(parts) > 2:
             os.environ["POLEE_FUSED_CTAS"] = parts[2]
