@@ -190,6 +190,14 @@ const char *polee_hsb_last_error(void);
 int polee_make_inverse_ptt_params(int64_t num_nodes, const int32_t *node_parent_idxs, const int32_t *node_js,
                                   int32_t *left_index, int32_t *right_index, int32_t *leaf_index);
 
+/* PolyaTreeTransform(X, :cluster): the reference's tree heuristic, hclust + order_nodes (src/hclust.jl:193-319,
+ * 361-389), on the host.  Output = the (node_parent_idxs, node_js) pair polee_set_tree takes (2n-1 entries each,
+ * 1-based, DFS order with the right branch first).  Similarity ties are broken by an explicit rule (smaller node ids
+ * first); the reference leaves them to unspecified library internals, so its exact tree cannot be reproduced (SURVEY
+ * 8c) -- any valid tree gives a valid approximation.  No GPU needed. */
+int polee_hclust(int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval, int32_t *node_parent_idxs,
+                 int32_t *node_js);
+
 /* Exact row de-duplication (tools/exact-factorization.jl:31-68): rows of X that agree in their transcript ids and
  * Float32 values bit for bit are merged; counts[u] = multiplicity of unique row u.  The compressed matrix + counts go
  * to polee_set_matrix_csc(..., ks = counts) (the factored likelihood, likelihood.jl:59-85) and give the same

@@ -171,6 +171,88 @@ def exact_factorization(m, n, colptr, rowval, nzval):
     return len(counts), new_colptr, new_rowval, new_nzval, np.asarray(counts, np.int64)
 
 
+def hclust_tree(m, n, colptr, rowval):
+    """PolyaTreeTransform(X, :cluster): hclust + order_nodes (src/hclust.jl:193-319, 361-389) restated with heapq and
+    numpy set operations.  Tie policy (unpinned in the reference): equal Float32 similarities -> smaller
+    (j1, j2) first; equal sizes in the remainder queue -> smaller node id first; neighbour lists keep first
+    occurrences.  Returns (node_parent_idxs, node_js), 1-based, DFS order with the right branch first."""
+    import heapq
+    colptr = np.asarray(colptr, np.int64); rowval = np.asarray(rowval, np.uint32)
+    K = 25
+    med = np.zeros(n, np.uint32)
+    for j in range(n):
+        if colptr[j] != colptr[j + 1]:
+            med[j] = rowval[(colptr[j] + colptr[j + 1]) // 2 - 1]
+    idxs = np.argsort(med, kind="stable")
+    N = 2 * n - 1
+    sets = [None] * N
+    left = [-1] * N; right = [-1] * N; leaf_tx = [0] * N
+    dead = [False] * N; live = [False] * N
+    nbr = [[] for _ in range(N)]
+    for j in range(n):
+        t = idxs[j]
+        sets[j] = rowval[colptr[t] - 1:colptr[t + 1] - 1]
+        leaf_tx[j] = int(t) + 1
+        live[j] = True
+
+    def jaccard(a, b):
+        if len(a) == 0 and len(b) == 0:
+            return np.float32(0)
+        c = len(np.intersect1d(a, b, assume_unique=True))
+        return np.float32(c / (len(a) + len(b) - c))
+
+    def add_nbr(a, b):
+        if b not in nbr[a]:
+            nbr[a].append(b)
+
+    heap = []
+    for j1 in range(n):
+        for j2 in range(j1 + 1, min(j1 + K, n - 1) + 1):
+            s = jaccard(sets[j1], sets[j2])
+            if s > 0:
+                heapq.heappush(heap, (-float(s), j1, j2))
+            add_nbr(j1, j2); add_nbr(j2, j1)
+    nxt = n
+    while heap:
+        _, j1, j2 = heapq.heappop(heap)
+        if dead[j1] or dead[j2]:
+            continue
+        k = nxt; nxt += 1
+        sets[k] = np.union1d(sets[j1], sets[j2])
+        left[k], right[k], live[k] = j1, j2, True
+        for j in (j1, j2):
+            sets[j] = None; dead[j] = True; live[j] = False
+        for ja, jb in ((j1, j2), (j2, j1)):
+            lst, nbr[ja] = nbr[ja], []
+            for l in lst:
+                if l == jb or dead[l]:
+                    continue
+                s = jaccard(sets[l], sets[k])
+                if s != 0:
+                    heapq.heappush(heap, (-float(s), l, k))
+                add_nbr(l, k); add_nbr(k, l)
+    rest = [(1 + len(sets[j]), j) for j in range(nxt) if live[j]]
+    heapq.heapify(rest)
+    while len(rest) > 1:
+        a = heapq.heappop(rest); b = heapq.heappop(rest)
+        k = nxt; nxt += 1
+        left[k], right[k] = a[1], b[1]
+        heapq.heappush(rest, (a[0] + b[0], k))
+    assert nxt == N
+    parent_idxs = np.zeros(N, np.int32); js = np.zeros(N, np.int32)
+    parent_of = [0] * N
+    stack, pos = [rest[0][1]], 0
+    while stack:
+        v = stack.pop()
+        parent_idxs[pos] = parent_of[v]
+        js[pos] = leaf_tx[v] if left[v] < 0 else 0
+        pos += 1
+        if left[v] >= 0:
+            parent_of[left[v]] = parent_of[right[v]] = pos
+            stack.append(left[v]); stack.append(right[v])
+    return parent_idxs, js
+
+
 # ------------------------------------------------------------------ ptt
 class PTT:
     def __init__(self, parent_idxs, js):

@@ -19,6 +19,7 @@ from .api import (  # noqa: F401
     RNASeqSample,
     approximate_likelihood,
     exact_factorization,
+    hclust,
     hsb,
     inv_hsb,
     inv_hsb_grad,

@@ -255,6 +255,18 @@ class Handle:
         self.check(self.lib.polee_comm_init(self.h, C.c_int32(nranks), C.c_int32(rank), C.c_char_p(unique_id)))
 
 
+def hclust(sample):
+    """PolyaTreeTransform(X, :cluster) -> (node_parent_idxs, node_js): hclust + order_nodes (src/hclust.jl:193-319,
+    361-389) on the host; ties broken by an explicit rule (the reference's are unspecified)."""
+    lib = L.load_library()
+    N = 2 * sample.n - 1
+    pi, js = np.zeros(N, np.int32), np.zeros(N, np.int32)
+    rc = lib.polee_hclust(C.c_int64(sample.m), C.c_int64(sample.n), _p(sample.colptr), _p(sample.rowval), _p(pi), _p(js))
+    if rc != 0:
+        raise L.PoleeError(rc, "polee_hclust failed")
+    return pi, js
+
+
 def exact_factorization(sample, device=0):
     """tools/exact-factorization.jl:31-68 on the device: (compressed RNASeqSample, counts).  Feed the pair to
     approximate_likelihood(..., ks=counts) / Handle.set_sample(sample, ks): same likelihood, fewer rows to stream."""
@@ -417,8 +429,9 @@ def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, us
     OptimizePTTApprox).
 
     tree_topology = (node_parent_idxs, node_js), what the reference reads from tree_topology_input_filename
-    (:428-433).  The reference otherwise builds the tree on the host with hclust (stays Julia, north_star); this
-    mirror accepts treemethod "sequential" without a topology and requires one for "cluster"/"random".
+    (:428-433).  Without one the tree is built as the reference does at :435: "sequential" -> list_nodes, "cluster" ->
+    the hclust restatement (polee_hclust, host code; tie-breaking is unpinned in the reference); "random"
+    needs a topology (Julia's RNG stream cannot be reproduced).
     gene_transcripts = {gene_id: [1-based transcript indices]} is the map the reference derives from the transcript
     metadata when gene_noninformative is set (:476-487); without it the flag is dropped with a warning (:489-492).
     """
@@ -436,11 +449,13 @@ def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, us
     if not isinstance(approx, LogitSkewNormalPTTApprox):
         raise TypeError("alternative approximations stay on the reference's Julia path (SURVEY 2a)")
     built_here = tree_topology is None
-    if built_here:
-        if approx.treemethod != "sequential":
-            raise ValueError("treemethod %r needs tree_topology=(node_parent_idxs, node_js): hclust stays on the host "
-                             "side of the boundary" % (approx.treemethod,))
-        tree_topology = sequential_tree(sample.n)
+    if built_here:                      # PolyaTreeTransform(X, approx.treemethod)  (:435, ptt.jl:35-52)
+        if approx.treemethod == "sequential":
+            tree_topology = sequential_tree(sample.n)
+        elif approx.treemethod == "cluster":
+            tree_topology = hclust(sample)
+        else:
+            raise ValueError("treemethod %r needs tree_topology=(node_parent_idxs, node_js)" % (approx.treemethod,))
     h = Handle(device=device, num_steps=num_steps, num_mc_samples=num_mc_samples, gradonly=gradonly,
                use_efflen_jacobian=use_efflen_jacobian, seed=seed,
                noise_mode=L.NOISE_INJECTED if noise is not None else L.NOISE_PHILOX,

@@ -176,3 +176,49 @@ def test_h5min_prep_roundtrip_and_reference_files(tmp_path):
     assert np.array_equal(lm["rowval"], fx.rowval) and np.array_equal(lm["nzval"], fx.nzval)
     pp = h5min.read_prep(os.path.join(ref, "mBr_M_6w_1.prep.h5"))
     assert np.array_equal(pp["mu"], fx.mu) and np.array_equal(pp["node_js"], fx.js) and pp["n"] == fx.n
+
+
+def test_hclust_host_restatement(oracle):
+    """polee_hclust (C++ host code behind the C ABI, no GPU) against the independent Python restatement of
+    hclust + order_nodes (src/hclust.jl:193-319, 361-389) under the same explicit tie policy: identical trees; the
+    tree is a valid PolyaTreeTransform input (every transcript once, DFS order, right branch first); transcripts that
+    share reads end up closer in the tree than transcripts that do not."""
+    import polee_b200 as pb
+    from polee_b200 import synth
+    fx = Fixture()
+    cases = [(fx.m, fx.n, fx.colptr, fx.rowval)]
+    s = synth.to_numpy_sample(synth.make_sample(6000, 400, seed=3))
+    cases.append((s["m"], s["n"], s["colptr"], s["rowval"]))
+    for m, n, colptr, rowval in cases:
+        smp = pb.RNASeqSample(m, n, colptr, rowval, np.ones(len(rowval), np.float32), np.ones(n, np.float32))
+        pi, js = pb.hclust(smp)
+        pi_o, js_o = oracle.hclust_tree(m, n, colptr, rowval)
+        assert np.array_equal(pi, pi_o) and np.array_equal(js, js_o)
+        N = 2 * n - 1
+        assert pi[0] == 0 and np.all(pi[1:] >= 1) and np.all(pi[1:] < np.arange(2, N + 1))      # parents precede children
+        assert sorted(js[js > 0]) == list(range(1, n + 1)) and (js == 0).sum() == n - 1
+        kids = np.bincount(pi[1:], minlength=N + 1)
+        assert np.all(kids[1:][js == 0] == 2) and np.all(kids[1:][js > 0] == 0)
+        t = oracle.PTT(pi, js)                                                                  # the reference's constructor rule
+        assert t.n == n
+    # the two isoforms sharing the most reads in the fixture are siblings or cousins: tree distance <= 4
+    depth = np.zeros(len(pi) + 1, int)
+    for i in range(2, len(pi) + 1):
+        depth[i] = depth[pi[i - 1]] + 1
+    import scipy.sparse as sp
+    X = sp.csc_matrix((np.ones(len(rowval)), rowval.astype(np.int64) - 1, colptr.astype(np.int64) - 1), shape=(m, n))
+    G = (X.T @ X).toarray().astype(float)
+    sz = np.diag(G).copy()
+    np.fill_diagonal(G, 0)
+    a, b = np.unravel_index(np.argmax(G / (sz[:, None] + sz[None, :] - G + 1e-9)), G.shape)
+    pos = {int(j): i + 1 for i, j in enumerate(js) if j > 0}
+
+    def ancestors(i):
+        out = []
+        while i:
+            out.append(i)
+            i = pi[i - 1]
+        return out
+    A, B = ancestors(pos[a + 1]), ancestors(pos[b + 1])
+    common = next(x for x in A if x in B)
+    assert (A.index(common) + B.index(common)) <= 4
