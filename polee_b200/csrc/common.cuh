@@ -328,10 +328,13 @@ inline cudaError_t copy_sync(cudaStream_t st, void *dst, const void *src, size_t
     return e == cudaSuccess ? cudaStreamSynchronize(st) : e;
 }
 
-constexpr int MAX_DYN_SMEM = 227 * 1024;
+constexpr int MAX_SMEM_PER_CTA = 227 * 1024;  // sm_100: opt-in limit, static + dynamic
 template <typename F>
 inline cudaError_t allow_max_smem(F func) {
-    return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, func);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM_PER_CTA - (int)a.sharedSizeBytes);
 }
 
 // Device-wide synchronisation (explicit, or implied by cudaFree / cudaMalloc) is not permitted while ANY stream of the

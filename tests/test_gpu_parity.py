@@ -205,8 +205,14 @@ def test_sequential_treemethod_and_output_topology(pb, fx):
     pi, js = sequential_tree(fx.n)
     assert np.array_equal(out["node_parent_idxs"], pi) and np.array_equal(out["node_js"], js)   # l-a.jl:618-621
     assert all(np.all(np.isfinite(out[k])) for k in ("mu", "omega", "alpha"))
-    with pytest.raises(ValueError):
-        pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox("cluster"), _sample(pb, fx))
+    with pytest.raises(ValueError):                                      # Julia's RNG stream cannot be reproduced
+        pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox("random"), _sample(pb, fx))
+    # treemethod "cluster" (the reference's default, l-a.jl:435): the tree comes from the hclust restatement and is
+    # returned with the parameters; the fit on it is as good as on the reference's own tree for this matrix
+    clu = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox("cluster"), _sample(pb, fx), num_steps=150)
+    hp, hj = pb.hclust(_sample(pb, fx))
+    assert np.array_equal(clu["node_parent_idxs"], hp) and np.array_equal(clu["node_js"], hj)
+    assert all(np.all(np.isfinite(clu[k])) for k in ("mu", "omega", "alpha"))
 
 
 @pytest.mark.parametrize("exact", [True, False])
