@@ -663,16 +663,16 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
     h->m = m; h->n = n; h->nnz = nnz;
 
     // Two layouts.  "split" (SELL slabs for K1 + re-sorted CSC for K2) streams the matrix twice and round-trips w
-    // through HBM; it is HBM-bound and the faster one when columns are long.  "fused" (row tiles, one pass, w stays in
-    // shared memory) moves ~40 % of the bytes but is bound by the shared-memory pipe; it wins when the columns of this
-    // rank's block are short (K2's <= 256-entry segments run underfilled), i.e. on small samples and on the row blocks
-    // of a >= 4-way partition of a large one (measured at C3: 0.80 vs 0.77 ms on 1 GPU, 0.135 vs 0.158 ms per 1/8
-    // block).  POLEE_LAYOUT=split|fused overrides; exact_accumulation always uses the reference-order split kernels.
+    // through HBM; both kernels are HBM-bound (0.84 / 0.82 of peak).  "fused" (row tiles, one pass, w stays in shared
+    // memory) moves ~40 % of the bytes, builds in less than half the time and takes half the memory; it is bound by
+    // the shared-memory pipe and the CTA barriers instead.  Measured at C3, likelihood pass of the rank-0 block of an
+    // N-way partition, fused vs split: N = 1 0.750 vs 0.767 ms, 2: 0.397 vs 0.417, 4: 0.216 vs 0.245, 8: 0.127 vs 0.158.
+    // Fused is therefore the default whenever the row order has the locality it needs (the builder declines
+    // otherwise: position-sorted rows, as the reference produces them, have it); POLEE_LAYOUT=split|fused overrides;
+    // exact_accumulation always uses the reference-order split kernels.
     {
         const char *lay = getenv("POLEE_LAYOUT");
-        const bool forced = lay && std::string(lay) == "fused";
-        const bool short_columns = (double)nnz < 256.0 * (double)n;
-        const bool want_fused = !h->o.exact_accumulation && !(lay && std::string(lay) == "split") && (forced || short_columns);
+        const bool want_fused = !h->o.exact_accumulation && !(lay && std::string(lay) == "split");
         if (want_fused) {
             int rc = setup_fused_from_device_csc(h, m, n, nnz, d_colptr, d_rowval, d_nzval, d_ks, colptr, vals_ready_or_null);
             if (rc) return rc;
