@@ -86,9 +86,9 @@ __host__ __device__ inline BlobLayout blob_layout(const FusedHdr &hd) {
     L.bytes = L.lcolA + ((hd.EA + 15u) & ~15u);
     return L;
 }
-// second stage: g[col] = sum of the (tile, column) partials of the column, in tile order.  A unit is <= FT_UNIT
-// partials of one column (one warp); columns with more than one unit are finished by a second small launch.
-constexpr int FT_UNIT = 256;
+// second stage: g[col] = sum of the partials of the column, in tile order.  A unit is <= FT_UNIT partials of one
+// column (KP lanes); columns with more than one unit are finished by a second small launch.
+constexpr int FT_UNIT = 64;
 struct FusedUnit {
     uint32_t col, begin, end;  // partials [begin, end) (the partial array is ordered by column)
     int32_t out;               // -1: writes g[col]; >= 0: writes the level-2 slot

@@ -332,28 +332,33 @@ __global__ void __launch_bounds__(FC_THREADS, 3)
     }
 }
 
-// g[col] (or a level-2 slot) = sum of <= FT_UNIT (tile, column) partials, in tile order.  One warp per unit.
+// g[col] (or a level-2 slot) = sum of <= FT_UNIT partials of one column (contiguous in the column-ordered partial
+// array), in tile order.  KP lanes per unit (lane = draw), 32 / KP units per warp: most columns own a handful of
+// partials, so a whole warp per unit would mostly wait on its own three dependent loads.
 template <int KP>
 __global__ void __launch_bounds__(256)
     k_fused_combine1(const FusedUnit *__restrict__ units, int n_units, const float *__restrict__ partial,
                      double *__restrict__ g, double *__restrict__ lvl2) {
-    const int unit = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-    if (unit >= n_units) return;
-    const int lane = threadIdx.x & 31;
     constexpr int G = 32 / KP;
-    const int grp = lane / KP, k = lane % KP;
+    const int warp_global = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    const int unit = warp_global * G + lane / KP, k = lane % KP;
+    if (unit >= n_units) return;
     const FusedUnit u = units[unit];
-    double a = 0.0;
-#pragma unroll 4
-    for (uint32_t i = u.begin + grp; i < u.end; i += G) a += (double)partial[(size_t)i * KP + k];
-#pragma unroll
-    for (int o = 16; o >= KP; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
-    if (grp == 0) {
-        if (u.out < 0)
-            g[(size_t)u.col * KP + k] = a;
-        else
-            lvl2[(size_t)u.out * KP + k] = a;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four loads in flight; added in a fixed order
+    uint32_t i = u.begin;
+    for (; i + 4 <= u.end; i += 4) {
+        a0 += (double)partial[(size_t)i * KP + k];
+        a1 += (double)partial[(size_t)(i + 1) * KP + k];
+        a2 += (double)partial[(size_t)(i + 2) * KP + k];
+        a3 += (double)partial[(size_t)(i + 3) * KP + k];
     }
+    for (; i < u.end; ++i) a0 += (double)partial[(size_t)i * KP + k];
+    const double a = (a0 + a1) + (a2 + a3);
+    if (u.out < 0)
+        g[(size_t)u.col * KP + k] = a;
+    else
+        lvl2[(size_t)u.out * KP + k] = a;
 }
 
 template <int KP>
@@ -402,7 +407,8 @@ int launch_fused_t(polee_handle *h, const float *x, double *g, bool want_lp, dou
     }
 #undef FK_LAUNCH
     if (h->ft_nunits > 0) {
-        const int blocks = (h->ft_nunits + 7) / 8;
+        const int units_per_block = 8 * (32 / KP);
+        const int blocks = (h->ft_nunits + units_per_block - 1) / units_per_block;
         k_fused_combine1<KP><<<blocks, 256, 0, h->stream>>>(h->ft_units, h->ft_nunits, h->ft_partial, g, h->ft_lvl2);
     }
     if (h->ft_nmulti > 0) {
