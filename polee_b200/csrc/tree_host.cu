@@ -33,15 +33,19 @@ static void make_sched(const std::vector<std::vector<int32_t>> &bins_nodes, cons
     out.lvl_off.clear();
     out.sch_node.clear();
     max_levels = 0;
+    size_t total = 0;
+    for (const auto &bn : bins_nodes) total += bn.size();
+    out.sch_node.reserve(total);
+    std::vector<int32_t> cnt, cur;  // reused across bins
     for (const auto &bn : bins_nodes) {
         int nl = 0;
         for (int32_t v : bn) nl = std::max(nl, level_of[v] + 1);
-        std::vector<int32_t> cnt(nl + 1, 0);
+        cnt.assign(nl + 1, 0);
         for (int32_t v : bn) cnt[level_of[v] + 1]++;
         for (int l = 0; l < nl; ++l) cnt[l + 1] += cnt[l];
         int32_t base = (int32_t)out.sch_node.size();
         out.sch_node.resize(base + bn.size());
-        std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1);
+        cur.assign(cnt.begin(), cnt.end() - 1);
         for (int32_t v : bn) out.sch_node[base + cur[level_of[v]]++] = v;
         for (int l = 0; l <= nl; ++l) out.lvl_off.push_back(base + cnt[l]);
         out.bin_lvl_ptr.push_back((int32_t)out.lvl_off.size());
@@ -121,6 +125,7 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
         if (is_top[r] || (parent[r] >= 0 && !is_top[parent[r]])) continue;  // r is a bottom root
         if (bins.empty() || cur_fill + size[r] > bin_nodes) {
             bins.emplace_back();
+            bins.back().reserve((size_t)bin_nodes);
             cur_fill = 0;
         }
         cur_fill += size[r];
@@ -151,6 +156,7 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
     for (const auto &bn : bins)
         for (int32_t v : bn)
             if (parent[v] < 0 || is_top[parent[v]]) slot_of[v] = parent[v] < 0 ? -1 : n_slots++;
+    std::vector<int32_t> local_scratch;
     auto make_ssched = [&](const std::vector<std::vector<int32_t>> &bins_nodes, bool is_top_sched, SSchedHost &out) {
         out.bin_off.assign(1, 0);
         out.bin_lvl_ptr.assign(1, 0);
@@ -158,11 +164,15 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
         out.recs.clear();
         out.max_bin_nodes = 0;
         out.max_bin_levels = 0;
-        std::vector<int32_t> local(N, -1);
+        local_scratch.assign(N, -1);
+        std::vector<int32_t> &local = local_scratch;
+        size_t total = 0;
+        for (const auto &bn0 : bins_nodes) total += bn0.size();
+        out.recs.reserve(total + (is_top_sched ? (size_t)n_slots + 1 : 0));
+        std::vector<int32_t> bn, cnt, cur, order;  // reused across bins
         for (const auto &bn0 : bins_nodes) {
             // members: the bin's nodes (+ for the top bin: the bottom roots hanging off it, as exchange leaves)
-            std::vector<int32_t> bn(bn0);
-            std::vector<int32_t> lvl_local(bn.size());
+            bn.assign(bn0.begin(), bn0.end());
             if (is_top_sched)
                 for (int32_t v : bn0)
                     if (nodes[v].leaf < 0)
@@ -171,10 +181,11 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
             auto lvl = [&](int32_t v) { return is_top_sched ? depth[v] : level_of[v]; };
             int nl = 0;
             for (int32_t v : bn) nl = std::max(nl, lvl(v) + 1);
-            std::vector<int32_t> cnt(nl + 1, 0);
+            cnt.assign(nl + 1, 0);
             for (int32_t v : bn) cnt[lvl(v) + 1]++;
             for (int l = 0; l < nl; ++l) cnt[l + 1] += cnt[l];
-            std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1), order(bn.size());
+            cur.assign(cnt.begin(), cnt.end() - 1);
+            order.resize(bn.size());
             for (int32_t v : bn) {
                 local[v] = cur[lvl(v)]++;
                 order[local[v]] = v;
