@@ -122,6 +122,9 @@ extern "C" int polee_create(polee_handle **out, const polee_opts *opts) {
     h->K = o.num_mc_samples;
     h->KP = pad_k(h->K);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         polee::dmalloc((void **)&h->d_step, sizeof(StepCtl)) != cudaSuccess ||
         polee::dmalloc((void **)&h->d_bad_step, sizeof(int)) != cudaSuccess) {
         delete h;
@@ -154,6 +157,9 @@ extern "C" int polee_destroy(polee_handle *h) {
     release_gene_buffers(h);
     polee::dfree(h->gene_ptr); polee::dfree(h->gene_tx);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -473,8 +479,14 @@ static int launch_step_sequence(polee_handle *h, bool do_adam, bool next_reparam
     const bool apply_eff = lsn ? (h->o.use_efflen_jacobian != 0) : true;
     int rc;
     if ((rc = launch_tree_fwd(h, KP, 1, apply_eff, want_vals))) return rc;
-    if ((rc = launch_mid(h, KP, do_adam ? 1 : 0))) return rc;
+    // k3_mid (the S reduction and the step counters) depends only on the tree pass and is needed only by the backward
+    // pass: it runs on a side stream beside the likelihood pass (a fork / join that the graph capture records too)
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    if ((rc = launch_mid(h, KP, do_adam ? 1 : 0, h->side_stream))) return rc;
+    CK(cudaEventRecord(h->ev_join, h->side_stream));
     if ((rc = launch_likelihood(h, KP, want_vals))) return rc;
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
 #ifdef POLEE_WITH_NCCL
     if (h->nranks > 1) {
         size_t count = (size_t)(h->n + (want_vals ? 1 : 0)) * KP;

@@ -203,6 +203,8 @@ struct polee_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of nzval / ks overlapping the layout build
     cudaEvent_t copy_done = nullptr;
+    cudaStream_t side_stream = nullptr;  // k3_mid runs beside the likelihood pass (fork / join inside the step graph)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int K = 0, KP = 0;  // draws, padded draws (power of two)
 
     // ---- matrix
@@ -373,7 +375,7 @@ int ensure_work_buffers(polee_handle *h, int KP);
 void release_work_buffers(polee_handle *h);
 int launch_reparam_fwd(polee_handle *h, int KP, int K, const float *noise, int64_t noise_steps, int want_ladj);
 int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_ladj);
-int launch_mid(polee_handle *h, int KP, int advance);
+int launch_mid(polee_handle *h, int KP, int advance, cudaStream_t st = nullptr);
 int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, double *xgrad_out);
 int launch_update(polee_handle *h, int KP, int K, bool do_adam, float *grad_out);
 int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bool do_reparam, const float *noise,

@@ -836,8 +836,8 @@ int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_l
     return POLEE_OK;
 }
 
-int launch_mid(polee_handle *h, int KP, int advance) {
-    k3_mid<<<1, 1024, 0, h->stream>>>(h->S_partial, h->n_tree_ctas, KP, h->S, h->d_step, advance);
+int launch_mid(polee_handle *h, int KP, int advance, cudaStream_t st) {
+    k3_mid<<<1, 1024, 0, st ? st : h->stream>>>(h->S_partial, h->n_tree_ctas, KP, h->S, h->d_step, advance);
     return POLEE_OK;
 }
 
