@@ -781,6 +781,11 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
     const int64_t n = h->n, nm1 = n - 1;
     float *d_noise = nullptr;
     double *d_xg = nullptr;
+    struct Release {  // the temporaries go back to the cache on every exit path
+        float *&a;
+        double *&b;
+        ~Release() { polee::dfree(a); polee::dfree(b); }
+    } release{d_noise, d_xg};
     CK(polee::dmalloc((void **)&d_noise, sizeof(float) * (size_t)K * std::max<int64_t>(nm1, 1)));
     CK(polee::dmalloc((void **)&d_xg, sizeof(double) * (size_t)n * KP));
     CK(polee::copy_sync(h->stream, d_noise, zs0, sizeof(float) * (size_t)K * nm1, cudaMemcpyHostToDevice));
@@ -808,8 +813,7 @@ extern "C" int polee_lsn_draws(polee_handle *h, const float *zs0, int32_t K, flo
     }
     polee::copy_sync(h->stream, h->d_step, &saved, sizeof(saved), cudaMemcpyHostToDevice);
     cudaMemsetAsync(h->d_bad_step, 0, sizeof(int), h->stream);
-    polee::dfree(d_noise);
-    polee::dfree(d_xg);
+    cudaStreamSynchronize(h->stream);
     return rc;
 }
 

@@ -8,6 +8,8 @@
 //     callers keep cudaFree's semantics;
 //   * blocks are never zeroed: callers clear what they need (as with cudaMalloc);
 //   * when cudaMalloc fails the cache of that device is released and the allocation retried;
+//   * the cache of a device is released when it grows past POLEE_CACHE_MAX_GB (default 48 GB: samples of very
+//     different sizes would otherwise pile up blocks nobody asks for again);
 //   * polee_trim_memory() returns everything to the driver; POLEE_NO_CACHE=1 turns the cache off.
 #include "common.cuh"
 
@@ -116,6 +118,8 @@ cudaError_t dfree(void *p) {
     if (cur != blk.device) cudaSetDevice(cur);
     g_free[blk.device].emplace(blk.bytes, p);
     g_cached_bytes[blk.device] += blk.bytes;
+    static const size_t cap = (size_t)(getenv("POLEE_CACHE_MAX_GB") ? atof(getenv("POLEE_CACHE_MAX_GB")) : 48.0) << 30;
+    if (g_cached_bytes[blk.device] > cap) trim_locked(blk.device);
     return e;
 }
 
