@@ -285,6 +285,7 @@ struct polee_handle {
     double *xd = nullptr;                 // [n][KP] Float64(x): K1's gather table
     float *w = nullptr;                   // [m_pad][KP]
     double *g = nullptr;                  // [n][KP]  (all-reduced across ranks)
+    float *g32 = nullptr;                 // [n][KP]  Float32 image of g for the all-reduce (multi-rank only)
     double *seg_partial = nullptr;        // [n_slots][KP]
     double *S_partial = nullptr;          // [n_tree_ctas][KP]
     double *S = nullptr;                  // [KP] sum_j x_j / efflen_j      (then lp[KP] follows in g_tail)
@@ -367,6 +368,8 @@ int launch_fused(polee_handle *h, const float *x, double *g, bool want_lp, doubl
 // sparse_kernels.cu
 int launch_k1(polee_handle *h, const float *x, const double *xd, float *w, bool want_lp, double *lp_partial, int KP);
 int launch_widen_x(polee_handle *h, const float *x, double *xd, int KP);
+int launch_narrow(polee_handle *h, const double *in, float *out, size_t count);
+int launch_widen(polee_handle *h, const float *in, double *out, size_t count);
 int launch_k2(polee_handle *h, const float *w, double *g, int KP);
 int launch_reduce_lp(polee_handle *h, const double *lp_partial, double *lp, int KP);
 

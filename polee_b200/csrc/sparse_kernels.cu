@@ -592,6 +592,11 @@ __global__ void k_widen_f32(const float *__restrict__ in, double *__restrict__ o
         out[i] = (double)in[i];
 }
 
+__global__ void k_narrow_f64(const double *__restrict__ in, float *__restrict__ out, size_t count) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (float)in[i];
+}
+
 template <int KP>
 int launch_k1_t(polee_handle *h, const float *x, const double *xd, float *w, bool want_lp, double *lp_partial) {
     if (h->n_row_tiles == 0) return POLEE_OK;
@@ -690,6 +695,16 @@ int launch_k2(polee_handle *h, const float *w, double *g, int KP) {
 int launch_widen_x(polee_handle *h, const float *x, double *xd, int KP) {
     const size_t count = (size_t)h->n * KP;
     k_widen_f32<<<(unsigned)std::min<size_t>((count + 255) / 256, 4096), 256, 0, h->stream>>>(x, xd, count);
+    return POLEE_OK;
+}
+
+// the gradient crosses NVLink as Float32 (half the bytes of the all-reduce): narrow before, widen after
+int launch_narrow(polee_handle *h, const double *in, float *out, size_t count) {
+    k_narrow_f64<<<(unsigned)std::min<size_t>((count + 255) / 256, 4096), 256, 0, h->stream>>>(in, out, count);
+    return POLEE_OK;
+}
+int launch_widen(polee_handle *h, const float *in, double *out, size_t count) {
+    k_widen_f32<<<(unsigned)std::min<size_t>((count + 255) / 256, 4096), 256, 0, h->stream>>>(in, out, count);
     return POLEE_OK;
 }
 

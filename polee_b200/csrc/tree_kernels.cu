@@ -610,9 +610,9 @@ __global__ void k3_elbo(int K, int KP, const double *__restrict__ lp, const doub
 
 void release_work_buffers(polee_handle *h) {
     void *ptrs[] = {h->zs0, h->zs, h->ys, h->ygrad, h->us, h->G, h->root_us, h->root_G, h->x, h->xd, h->w, h->g, h->seg_partial, h->S_partial,
-                    h->S, h->lp_partial, h->ladj_partial, h->grad_out, h->ft_partial, h->ft_lvl2};
+                    h->S, h->lp_partial, h->ladj_partial, h->grad_out, h->ft_partial, h->ft_lvl2, h->g32};
     for (void *p : ptrs) polee::dfree(p);
-    h->ft_partial = nullptr; h->ft_lvl2 = nullptr;
+    h->ft_partial = nullptr; h->ft_lvl2 = nullptr; h->g32 = nullptr;
     h->zs0 = h->zs = nullptr; h->ys = h->ygrad = h->us = nullptr; h->G = nullptr; h->x = h->w = nullptr; h->xd = nullptr; h->root_us = nullptr; h->root_G = nullptr;
     h->g = h->seg_partial = h->S_partial = h->S = h->lp_partial = h->ladj_partial = nullptr;
     h->grad_out = nullptr;
@@ -648,6 +648,7 @@ int ensure_work_buffers(polee_handle *h, int KP) {
     CK(cudaMemsetAsync(h->S_partial, 0, sizeof(double) * h->n_tree_ctas * KP, h->stream));
     CK(cudaMemsetAsync(h->ladj_partial, 0, sizeof(double) * (2 * (size_t)elem_ctas(h, KP) + h->n_tree_ctas) * KP, h->stream));
     CK(cudaMemsetAsync(h->g, 0, sizeof(double) * (n + 1) * KP, h->stream));
+    if (h->nranks > 1) CK(polee::dmalloc((void **)&h->g32, sizeof(float) * (n + 1) * KP));
     if (h->have_matrix) {
         CK(polee::dmalloc((void **)&h->w, sizeof(float) * std::max<int64_t>(h->m_pad, 1) * KP));
         CK(cudaMemsetAsync(h->w, 0, sizeof(float) * std::max<int64_t>(h->m_pad, 1) * KP, h->stream));
