@@ -201,6 +201,21 @@ def test_hclust_host_restatement(oracle):
         assert np.all(kids[1:][js == 0] == 2) and np.all(kids[1:][js > 0] == 0)
         t = oracle.PTT(pi, js)                                                                  # the reference's constructor rule
         assert t.n == n
+    # degenerate inputs: a single transcript, two transcripts, empty columns (transcripts without compatible reads end up
+    # in the "remainder" joins, hclust.jl:243-262)
+    def mk(m, n, cols):
+        colptr, rowval = [1], []
+        for c in cols:
+            rowval += sorted(c)
+            colptr.append(len(rowval) + 1)
+        return pb.RNASeqSample(m, n, np.array(colptr, np.uint32), np.array(rowval, np.uint32),
+                               np.ones(len(rowval), np.float32), np.ones(n, np.float32))
+    for smp in (mk(3, 1, [[1, 2, 3]]), mk(3, 2, [[1, 2], [2, 3]]), mk(4, 5, [[1, 2], [], [2, 3], [], [4]]),
+                mk(2, 3, [[], [1, 2], []])):
+        pi2, js2 = pb.hclust(smp)
+        po, jo = oracle.hclust_tree(smp.m, smp.n, smp.colptr, smp.rowval)
+        assert np.array_equal(pi2, po) and np.array_equal(js2, jo)
+        assert sorted(js2[js2 > 0]) == list(range(1, smp.n + 1)) and pi2[0] == 0
     # the two isoforms sharing the most reads in the fixture are siblings or cousins: tree distance <= 4
     depth = np.zeros(len(pi) + 1, int)
     for i in range(2, len(pi) + 1):
