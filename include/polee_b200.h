@@ -127,10 +127,18 @@ int polee_set_noise(polee_handle *h, const float *noise, int64_t num_steps); /* 
 int polee_get_elbo(polee_handle *h, double *elbo_traj, int32_t nsteps);
 /* stream the handle's kernels run on (cudaStream_t as void*), for CUDA-event timing by the caller */
 void *polee_stream(polee_handle *h);
-/* algorithmic bytes and launch counts of one ADAM step (SURVEY 8d formulas) */
+/* bytes one ADAM step streams with the device layouts in use, and its launch count:
+ * bytes_k1 = the likelihood pass (all of it when the equivalence-class or the fused layout is in use, then
+ * bytes_k2 = 0; K1 / K2 of the split layout otherwise), bytes_k3 = tree + reparameterisation + ADAM */
 int polee_step_stats(polee_handle *h, double *bytes_k1, double *bytes_k2, double *bytes_k3, int32_t *launches);
+/* which device layouts hold the matrix (a1-a2: replaces Xt = SparseMatrixCSC(transpose(X)),
+ * likelihood-approximation.jl:407): info[0..5] = rows, entries, classes, tasks, blob bytes, partials of the
+ * equivalence-class layout; info[6..7] = rows, entries of the general layouts; info[8] = their kind (0 none,
+ * 1 split, 2 fused); info[9] = padded row slots of the class layout.  count <= 10 values are written. */
+int polee_layout_info(polee_handle *h, int64_t *info, int32_t count);
 /* time (ms, CUDA events on the handle's stream) of `reps` launches of one named kernel group:
- * which = 1 (K1 forward SpMM), 2 (K2 transposed gradient), 3 (K3 tree+reparam+ADAM) */
+ * which = 1 (the likelihood pass; K1 alone on the pure split layout), 2 (K2 of the pure split layout),
+ * 3 (K3 tree+reparam+ADAM) */
 int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, float *ms_avg);
 
 /* Random.rand!(als::ApproxLikelihoodSampler, xs)  src/approx-sampler.jl:37-44 (used by `polee sample`,

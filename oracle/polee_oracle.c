@@ -21,6 +21,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* torch.distributed.run exports OMP_NUM_THREADS=1; the reference's launcher uses every core (polee:8-12) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* =============================== sparse.jl =============================== */
 
 /* sparse.jl:6-21.  `y[j] = zero(T)` then `y[j] += x[i] * nzval[k]`: the product of two Float32

@@ -188,6 +188,7 @@ void orc_inv_hsb_grad(int64_t B, int64_t n, const double *y_grad, const float *l
                       const int32_t *leaf, float *backprops);                 /* hsb_ops.cpp:338-392 */
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

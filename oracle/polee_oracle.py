@@ -91,6 +91,18 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n=None):
+    """Use n OpenMP threads (default: every core this process may run on -- the reference's wrapper script starts
+    Julia with all cores, polee:8-12; torch.distributed.run would otherwise pin OMP_NUM_THREADS to 1)."""
+    if n is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 # ------------------------------------------------------------------ sparse / likelihood
 def transpose_csc(m, n, colptr, rowval, nzval):
     nnz = len(rowval)

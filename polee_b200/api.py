@@ -185,6 +185,15 @@ class Handle:
         self.check(self.lib.polee_step_stats(self.h, C.byref(b[0]), C.byref(b[1]), C.byref(b[2]), C.byref(nl)))
         return {"bytes_k1": b[0].value, "bytes_k2": b[1].value, "bytes_k3": b[2].value, "launches": nl.value}
 
+    def layout_info(self):
+        v = (C.c_int64 * 10)()
+        self.check(self.lib.polee_layout_info(self.h, v, C.c_int32(10)))
+        keys = ("ec_rows", "ec_nnz", "ec_classes", "ec_tasks", "ec_blob_bytes", "ec_partials", "general_rows",
+                "general_nnz", "general_kind", "ec_row_slots")
+        out = dict(zip(keys, (int(x) for x in v)))
+        out["general_kind"] = ("none", "split", "fused")[out["general_kind"]]
+        return out
+
     def time_kernel(self, which, reps):
         ms = C.c_float()
         self.check(self.lib.polee_time_kernel(self.h, C.c_int32(which), C.c_int32(reps), C.byref(ms)))

@@ -437,7 +437,7 @@ static int ready_for_steps(polee_handle *h) {
         // the reference reads xls, which only effective_length_jacobian_adjustment! fills (likelihood.jl:98-101), and
         // the factored / OptimizePTT entries have no gene prior (likelihood-approximation.jl:248-251, :149-151)
         if (h->gene_n != h->n) return h->fail(POLEE_EINVAL, "gene groups were set for a different n");
-        if (h->o.approx != POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT || h->row_weight)
+        if (h->o.approx != POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT || h->row_weight || h->ft_row_weight || h->ec_slot_weight)
             return h->fail(POLEE_EINVAL, "gene groups: the prior exists only in the unweighted LogitSkewNormalPTTApprox fit");
         if (!h->o.use_efflen_jacobian)
             return h->fail(POLEE_EINVAL, "gene groups need use_efflen_jacobian (the prior reads the scaled abundances it computes)");
@@ -454,16 +454,22 @@ static int ready_for_steps(polee_handle *h) {
     return POLEE_OK;
 }
 
-// log-likelihood gradient of the KP draws in h->x: the fused single pass, or K1 + K2 on the split layout
+// log-likelihood gradient of the KP draws in h->x: the equivalence-class pass, plus -- for the rows it did not take, or
+// for all rows when it is switched off -- the fused single pass or K1 + K2 on the split layout
 static int launch_likelihood(polee_handle *h, int KP, bool want_lp) {
     int rc;
-    if (h->fused) {
-        if ((rc = launch_fused(h, h->x, h->g, want_lp, h->lp_partial, nullptr, KP))) return rc;
-    } else {
-        if ((rc = launch_k1(h, h->x, h->xd, h->w, want_lp, h->lp_partial, KP))) return rc;
-        if ((rc = launch_k2(h, h->w, h->g, KP))) return rc;
+    const bool general = h->gm > 0 || h->ec_tasks == 0;
+    double *lp_out = h->g + (size_t)h->n * KP;
+    if (general) {
+        if (h->fused) {
+            if ((rc = launch_fused(h, h->x, h->g, want_lp, h->lp_partial, nullptr, KP))) return rc;
+        } else {
+            if ((rc = launch_k1(h, h->x, h->xd, h->w, want_lp, h->lp_partial, KP))) return rc;
+            if ((rc = launch_k2(h, h->w, h->g, KP))) return rc;
+        }
+        if (want_lp && (rc = launch_reduce_lp(h, h->lp_partial, lp_out, KP))) return rc;
     }
-    if (want_lp && (rc = launch_reduce_lp(h, h->lp_partial, h->g + (size_t)h->n * KP, KP))) return rc;
+    if (h->ec_tasks > 0 && (rc = launch_ec(h, h->x, h->g, general, want_lp, lp_out, nullptr, KP))) return rc;
     return POLEE_OK;
 }
 
@@ -686,29 +692,52 @@ extern "C" int polee_frag_prob_recip(polee_handle *h, const float *xs, float *w)
     int KP, rc;
     if ((rc = use_kp(h, 1, &KP))) return rc;
     if ((rc = upload_kmajor<float>(h, xs, 1, KP, h->n, h->x, 1.0f))) return rc;
-    if (h->fused) {  // rows keep their original order in the fused layout
-        float *d_w = nullptr;
+    const bool general = h->gm > 0 || h->ec_tasks == 0;
+    float *d_w = nullptr;
+    struct Release {
+        float *&p;
+        ~Release() { polee::dfree(p); }
+    } release{d_w};
+    if (h->ec_tasks > 0) {  // the class layout scatters 1/p to the rows' original positions
         CK(polee::dmalloc((void **)&d_w, sizeof(float) * (size_t)h->m * KP));
+        CK(cudaMemsetAsync(d_w, 0, sizeof(float) * (size_t)h->m * KP, h->stream));
+        if ((rc = launch_ec(h, h->x, h->g, false, false, nullptr, d_w, KP))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+        std::vector<float> wp((size_t)h->m * KP);
+        CK(polee::copy_sync(h->stream, wp.data(), d_w, sizeof(float) * wp.size(), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < h->m; ++i) w[i] = wp[(size_t)i * KP];
+        polee::dfree(d_w);
+        d_w = nullptr;
+    }
+    if (!general) return POLEE_OK;
+    // the general layouts hold gm rows (all of them, or the rest rows, whose original positions are in rest_row)
+    std::vector<float> wr((size_t)h->gm);
+    if (h->fused) {  // rows keep their order in the fused layout
+        CK(polee::dmalloc((void **)&d_w, sizeof(float) * (size_t)h->gm * KP));
         rc = launch_fused(h, h->x, h->g, false, h->lp_partial, d_w, KP);
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (!rc && e != cudaSuccess) rc = h->fail(POLEE_ECUDA, std::string("frag_prob_recip: ") + cudaGetErrorString(e));
-        if (!rc) {
-            std::vector<float> wp((size_t)h->m * KP);
-            e = polee::copy_sync(h->stream, wp.data(), d_w, sizeof(float) * wp.size(), cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) rc = h->fail(POLEE_ECUDA, std::string("frag_prob_recip: ") + cudaGetErrorString(e));
-            for (int64_t i = 0; i < h->m; ++i) w[i] = wp[(size_t)i * KP];
-        }
-        polee::dfree(d_w);
-        return rc;
+        if (rc) return rc;
+        std::vector<float> wp((size_t)h->gm * KP);
+        CK(polee::copy_sync(h->stream, wp.data(), d_w, sizeof(float) * wp.size(), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < h->gm; ++i) wr[i] = wp[(size_t)i * KP];
+    } else {
+        if ((rc = launch_widen_x(h, h->x, h->xd, KP))) return rc;
+        if ((rc = launch_k1(h, h->x, h->xd, h->w, false, h->lp_partial, KP))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+        std::vector<float> wp(h->m_pad);
+        std::vector<uint32_t> perm(h->gm);
+        CK(polee::copy_sync(h->stream, wp.data(), h->w, sizeof(float) * h->m_pad, cudaMemcpyDeviceToHost));
+        CK(polee::copy_sync(h->stream, perm.data(), h->row_perm, sizeof(uint32_t) * h->gm, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < h->gm; ++i) wr[i] = wp[perm[i]];
     }
-    if ((rc = launch_widen_x(h, h->x, h->xd, KP))) return rc;
-    if ((rc = launch_k1(h, h->x, h->xd, h->w, false, h->lp_partial, KP))) return rc;
-    CK(cudaStreamSynchronize(h->stream));
-    std::vector<float> wp(h->m_pad);
-    std::vector<uint32_t> perm(h->m);
-    CK(polee::copy_sync(h->stream, wp.data(), h->w, sizeof(float) * h->m_pad, cudaMemcpyDeviceToHost));
-    CK(polee::copy_sync(h->stream, perm.data(), h->row_perm, sizeof(uint32_t) * h->m, cudaMemcpyDeviceToHost));
-    for (int64_t i = 0; i < h->m; ++i) w[i] = wp[perm[i]];
+    if (h->rest_row) {
+        std::vector<uint32_t> rr((size_t)h->gm);
+        CK(polee::copy_sync(h->stream, rr.data(), h->rest_row, sizeof(uint32_t) * h->gm, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < h->gm; ++i) w[rr[i]] = wr[i];
+    } else {
+        std::copy(wr.begin(), wr.end(), w);
+    }
     return POLEE_OK;
 }
 
@@ -859,26 +888,49 @@ extern "C" int polee_step_stats(polee_handle *h, double *b1, double *b2, double 
     if (!h->have_matrix || !h->have_tree) return h->fail(POLEE_EINVAL, "step_stats: set the matrix and the tree first");
     // SURVEY 8(d) / BASELINE.md section 2 formulas with the padded draw count actually streamed
     const double nnz = (double)h->nnz, m = (double)h->m, n = (double)h->n, K = (double)h->KP, N = 2 * n - 1;
-    if (h->fused) {
-        // one pass: the matrix once (val + col + the 16-bit column-major permutation), row offsets, x, and the
-        // (tile, column) partials written and read back; b2 = 0 tells the caller there is no second sparse kernel
-        if (b1) *b1 = (double)h->ft_blob_bytes + (double)h->ft_parts * (K * 4 * 2 + 4) + K * n * 8;
-        if (b2) *b2 = 0;
-    } else {
-        if (b1) *b1 = nnz * 8 + (m + 1) * 4 + K * n * 4 + K * m * 4;
-        if (b2) *b2 = nnz * 8 + (n + 1) * 4 + K * m * 4 + K * n * 4;
+    // bytes the likelihood pass really streams per step with the layouts in use (what `roofline.moved` is checked against
+    // ncu's dram bytes); b2 = 0 tells the caller there is no second sparse kernel
+    const double gm = (double)h->gm, gnnz = (double)h->gnnz;
+    double e1 = 0, e2 = 0;
+    if (h->ec_tasks > 0)  // task blobs once + (task, column) partials written and read back + x gathers + g
+        e1 = (double)h->ec_blob_bytes + (double)h->ec_parts * (K * 8 * 2 + 4) + K * n * 4 + K * n * 8;
+    if (h->gm > 0 || h->ec_tasks == 0) {
+        if (h->fused) {
+            e1 += (double)h->ft_blob_bytes + (double)h->ft_parts * (K * 4 * 2 + 4) + K * n * 8;
+        } else {
+            e1 += gnnz * 8 + (gm + 1) * 4 + K * n * 4 + K * gm * 4;
+            e2 = gnnz * 8 + (n + 1) * 4 + K * gm * 4 + K * n * 4;
+        }
     }
+    if (b1) *b1 = e1;
+    if (b2) *b2 = e2;
+    (void)nnz; (void)m;
     if (b3) *b3 = (n - 1) * 72 + N * 16 + K * n * 8;
     if (launches) {
         const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
         const bool vals = lsn && !h->o.gradonly;
-        const int sparse_launches = h->fused ? 1 + (h->ft_nunits > 0) + (h->ft_nmulti > 0)
-                                             : (h->n_row_tiles > 0) + (h->n_segs > 0) + (h->n_multi > 0);
+        int sparse_launches = 0;
+        if (h->gm > 0 || h->ec_tasks == 0)
+            sparse_launches += h->fused ? 1 + (h->ft_nunits > 0) + (h->ft_nmulti > 0)
+                                        : (h->n_row_tiles > 0) + (h->n_segs > 0) + (h->n_multi > 0);
+        if (h->ec_tasks > 0) sparse_launches += 1 + (h->ec_nunits > 0) + (h->ec_nmulti > 0);
         int L = (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*mid*/ + sparse_launches +
                 (h->td.top.nbins > 0) + (h->td.bottom.nbins > 0) + 1 /*update + reparam*/;
         if (vals) L += 2;
         *launches = L;
     }
+    return POLEE_OK;
+}
+
+// Which layouts hold the matrix: info[0..9] = {rows, entries, classes, tasks, blob bytes, partials} of the
+// equivalence-class layout, {rows, entries} of the general layouts, general layout kind (0 none, 1 split, 2 fused),
+// padded row slots of the class layout.
+extern "C" int polee_layout_info(polee_handle *h, int64_t *info, int32_t count) {
+    CHECK_H(h);
+    if (!info || count < 1) return h->fail(POLEE_EINVAL, "layout_info: bad arguments");
+    const int64_t v[10] = {h->ec_rows, h->ec_nnz, h->ec_classes, (int64_t)h->ec_tasks, (int64_t)h->ec_blob_bytes, h->ec_parts,
+                           h->gm, h->gnnz, (int64_t)((h->gm > 0 || h->ec_tasks == 0) ? (h->fused ? 2 : 1) : 0), h->ec_slots};
+    for (int i = 0; i < count && i < 10; ++i) info[i] = v[i];
     return POLEE_OK;
 }
 
@@ -896,11 +948,11 @@ extern "C" int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, f
     const float *noise = h->o.noise_mode == POLEE_NOISE_INJECTED ? h->noise : nullptr;
     CK(cudaEventRecord(e0, h->stream));
     for (int r = 0; r < reps && !rc; ++r) {
-        if (which == 1) {
-            rc = h->fused ? launch_fused(h, h->x, h->g, false, h->lp_partial, nullptr, KP)
-                          : launch_k1(h, h->x, h->xd, h->w, false, h->lp_partial, KP);
+        if (which == 1) {  // the whole likelihood pass, except on the pure split layout (K1 here, K2 under which == 2)
+            rc = (h->ec_tasks > 0 || h->fused) ? launch_likelihood(h, KP, false)
+                                               : launch_k1(h, h->x, h->xd, h->w, false, h->lp_partial, KP);
         } else if (which == 2) {
-            if (!h->fused) rc = launch_k2(h, h->w, h->g, KP);  // fused layout: there is no second sparse kernel
+            if (h->ec_tasks == 0 && !h->fused) rc = launch_k2(h, h->w, h->g, KP);  // otherwise: no second sparse kernel
         } else if (which == 3) {
             rc = launch_tree_fwd(h, KP, 1, 1, 0);
             if (!rc) rc = launch_mid(h, KP, 0);

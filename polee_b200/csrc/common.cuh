@@ -86,6 +86,42 @@ __host__ __device__ inline BlobLayout blob_layout(const FusedHdr &hd) {
     L.bytes = L.lcolA + ((hd.EA + 15u) & ~15u);
     return L;
 }
+// ---- equivalence-class layout ("ec"): the default likelihood layout.
+// Fragments (rows) compatible with the same set of transcripts form an equivalence class -- the unit salmon / kallisto
+// collapse to counts; Polee keeps every fragment's own conditional probabilities (src/rnaseq_sample.jl:104), so a class
+// of R rows and L transcripts is a DENSE R x L block of Float32 values sharing ONE list of L column ids.  Position-sorted
+// reads (src/rnaseq_sample.jl:399-419) make classes large (fixture: 496 classes for 19 743 rows).  The layout stores the
+// column ids once per task and the values alone per entry (4 B/entry + padding instead of 8 B twice), and both sparse
+// passes of a step become small dense products with the K draws as the third dimension:
+//     p[r][k] = sum_l V[r][l] x[c_l][k]          (pAt_mul_B!,    src/sparse.jl:6-21)
+//     g[c_l][k] += sum_r V[r][l] / p[r][k]       (pAt_mulinv_B!, src/sparse.jl:25-40)
+// both accumulated in Float64 (FP64 tensor-core MMA m8n8k4, DMMA).  A class is cut into blocks of 32 rows and tasks of
+// <= nbt(L) blocks; one warp = one task at a time, streamed by one bulk copy:
+//     EcHdr | cols u32[Lp] | dest u32[Lp] | V f32[nb][Lp/4][4][32]          (Lp = L rounded up to 4)
+// V is stored in MMA fragment order: chunk (lc, mt) = columns 4lc..4lc+3 x rows 8mt..8mt+7 of the block, element
+// (row, l) at ((row % 8) * 4 + l % 4) ^ ((lc & 1) << 4) -- one conflict-free 128-byte shared-memory read per MMA in
+// both passes.  dest[l] = slot of the task's Float64 partial for column l in a partial array ordered by column; a
+// second small launch adds each column's partials in a fixed order (no atomics).  Classes with fewer than EC_MIN_ROWS
+// rows or rows longer than EC_MAX_L go to the general layouts below ("rest" rows).
+constexpr uint32_t EC_MAX_L = 64;
+constexpr uint32_t EC_MIN_ROWS_DEFAULT = 12;
+constexpr uint32_t EC_V_BYTES = 8192;       // V bytes per task (<= one shared-memory stage)
+constexpr uint32_t EC_STAGE_BYTES = 16 + 2 * 4 * EC_MAX_L + EC_V_BYTES;   // 8720
+__host__ __device__ inline uint32_t ec_lp(uint32_t L) { return (L + 3u) & ~3u; }
+__host__ __device__ inline uint32_t ec_nbt(uint32_t L) {   // blocks per task
+    const uint32_t v = EC_V_BYTES / (ec_lp(L) * 128u);
+    return v < 1u ? 1u : (v > 16u ? 16u : v);
+}
+__host__ __device__ inline uint32_t ec_hdr_bytes(uint32_t L) { return 16u + 8u * ec_lp(L); }
+__host__ __device__ inline uint32_t ec_task_bytes(uint32_t L, uint32_t nb) { return ec_hdr_bytes(L) + nb * ec_lp(L) * 128u; }
+struct EcHdr {
+    uint32_t L, nb, rows, slot0;  // columns, blocks, valid rows of the task, first row slot (row_of_slot / weights)
+};
+struct EcTaskDesc {
+    uint64_t off;    // byte offset of the task blob
+    uint32_t bytes;  // multiple of 16
+    uint32_t pad;
+};
 // second stage: g[col] = sum of the partials of the column, in tile order.  A unit is <= FT_UNIT partials of one
 // column (KP lanes); columns with more than one unit are finished by a second small launch.
 constexpr int FT_UNIT = 64;
@@ -243,6 +279,26 @@ struct polee_handle {
     double *ft_lvl2 = nullptr;       // [ft_nlvl2][KP]           (work buffer)
     int ft_grid = 0;
 
+    // equivalence-class layout (the default; rows it cannot take go to the general layouts above as "rest" rows)
+    unsigned char *ec_blob = nullptr;
+    polee::EcTaskDesc *ec_desc = nullptr;
+    int ec_tasks = 0;
+    int64_t ec_rows = 0, ec_nnz = 0, ec_slots = 0, ec_classes = 0;  // rows / entries / padded row slots / classes it holds
+    uint64_t ec_blob_bytes = 0;
+    int64_t ec_parts = 0;               // (task, column) partials
+    uint32_t *ec_row_of_slot = nullptr; // original row of every row slot, 0xFFFFFFFF = padding
+    float *ec_slot_weight = nullptr;    // ks per row slot (nullable)
+    polee::FusedUnit *ec_units = nullptr;
+    int ec_nunits = 0;
+    polee::FusedMulti *ec_multi = nullptr;
+    int ec_nmulti = 0, ec_nlvl2 = 0;
+    double *ec_partial = nullptr;       // [ec_parts][KP]   (work buffer)
+    double *ec_lvl2 = nullptr;          // [ec_nlvl2][KP]   (work buffer)
+    double *ec_lp_partial = nullptr;    // [ec_tasks][KP]   (work buffer)
+    int ec_grid = 0;
+    int64_t gm = 0, gnnz = 0;           // rows / entries of the general ("rest") layouts; m, nnz are the whole matrix
+    uint32_t *rest_row = nullptr;       // [gm] original row of every rest row (nullptr: rest = whole matrix)
+
     // ---- per-sample vectors
     float *efflen = nullptr;      // [n]
     float *efflen_adj = nullptr;  // Float32(n * (1/efflen))  likelihood.jl:105
@@ -360,6 +416,22 @@ void release_matrix(polee_handle *h);
 int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t nnz, const uint32_t *d_colptr,
                                 const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
                                 const std::vector<uint32_t> &colptr, cudaEvent_t vals_ready_or_null);
+
+// ec_setup.cu / ec_kernels.cu
+struct EcRest {  // the rows the class layout did not take, as a CSC of their own (device arrays owned by the struct)
+    int64_t m = 0, nnz = 0;
+    uint32_t *colptr = nullptr, *rowval = nullptr;
+    float *nzval = nullptr;
+    int64_t *ks = nullptr;
+    ~EcRest();
+};
+int setup_ec_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t nnz, const uint32_t *d_colptr,
+                             const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
+                             cudaEvent_t vals_ready_or_null, EcRest *rest);
+void release_ec(polee_handle *h);
+int ec_grid(polee_handle *h, int KP);
+// g (+)= X_ec^T (1 / X_ec x); add_to_g: the general layouts already wrote their share of g
+int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool want_lp, double *lp_out, float *w_out, int KP);
 
 // fused_kernels.cu
 int fused_grid(polee_handle *h, int KP);

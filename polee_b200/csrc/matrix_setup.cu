@@ -400,6 +400,8 @@ void release_matrix(polee_handle *h) {
     h->row_weight = nullptr; h->csc_row = nullptr; h->csc_val = nullptr; h->segs = nullptr; h->multi = nullptr;
     h->n_row_tiles = 0; h->n_segs = 0; h->n_multi = 0; h->n_slots = 0; h->m_pad = 0;
     release_fused(h);
+    release_ec(h);
+    h->gm = h->gnnz = 0;
     h->have_matrix = false;
 }
 
@@ -642,25 +644,14 @@ int setup_fused_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t n
     return POLEE_OK;
 }
 
-int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const uint32_t *d_colptr,
+// The general layouts ("split" / "fused") of m rows -- the whole matrix, or the rows the equivalence-class layout
+// did not take.
+static int setup_general_layouts(polee_handle *h, int64_t m, int64_t n, int64_t nnz, const uint32_t *d_colptr,
                                  const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
-                                 const uint32_t *h_colptr_or_null, cudaEvent_t vals_ready_or_null) {
-    release_matrix(h);
-    if (m < 1 || n < 1) return h->fail(POLEE_EINVAL, "set_matrix: m and n must be >= 1");
-    if (m >= (int64_t)0xFFFFFF00u) return h->fail(POLEE_EINVAL, "set_matrix: m exceeds UInt32 row ids");
+                                 const std::vector<uint32_t> &colptr, cudaEvent_t vals_ready_or_null) {
     cudaStream_t st = h->stream;
     PhaseTimer pt(st);
-    pt.mark("inputs resident (H2D)");
-    std::vector<uint32_t> colptr(n + 1);
-    if (h_colptr_or_null)
-        std::copy(h_colptr_or_null, h_colptr_or_null + n + 1, colptr.begin());
-    else
-        CK(polee::copy_sync(h->stream, colptr.data(), d_colptr, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost));
-    if (colptr[0] != 1) return h->fail(POLEE_EINVAL, "set_matrix: colptr must be 1-based (colptr[1] == 1)");
-    for (int64_t j = 0; j < n; ++j)
-        if (colptr[j + 1] < colptr[j]) return h->fail(POLEE_EINVAL, "set_matrix: colptr is not non-decreasing");
-    const int64_t nnz = (int64_t)colptr[n] - 1;
-    h->m = m; h->n = n; h->nnz = nnz;
+    h->gm = m; h->gnnz = nnz;
 
     // Two layouts.  "split" (SELL slabs for K1 + re-sorted CSC for K2) streams the matrix twice and round-trips w
     // through HBM; both kernels are HBM-bound (0.84 / 0.82 of peak).  "fused" (row tiles, one pass, w stays in shared
@@ -889,6 +880,63 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
     pt.mark("descriptor upload");
     h->have_matrix = true;
     return POLEE_OK;
+}
+
+int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const uint32_t *d_colptr,
+                                 const uint32_t *d_rowval, const float *d_nzval, const int64_t *d_ks,
+                                 const uint32_t *h_colptr_or_null, cudaEvent_t vals_ready_or_null) {
+    release_matrix(h);
+    if (m < 1 || n < 1) return h->fail(POLEE_EINVAL, "set_matrix: m and n must be >= 1");
+    if (m > (int64_t)INT32_MAX) return h->fail(POLEE_EINVAL, "set_matrix: m exceeds 2^31 - 1 rows");
+    cudaStream_t st = h->stream;
+    PhaseTimer pt(st);
+    pt.mark("inputs resident (H2D)");
+    std::vector<uint32_t> colptr(n + 1);
+    if (h_colptr_or_null)
+        std::copy(h_colptr_or_null, h_colptr_or_null + n + 1, colptr.begin());
+    else
+        CK(polee::copy_sync(h->stream, colptr.data(), d_colptr, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost));
+    if (colptr[0] != 1) return h->fail(POLEE_EINVAL, "set_matrix: colptr must be 1-based (colptr[1] == 1)");
+    for (int64_t j = 0; j < n; ++j)
+        if (colptr[j + 1] < colptr[j]) return h->fail(POLEE_EINVAL, "set_matrix: colptr is not non-decreasing");
+    const int64_t nnz = (int64_t)colptr[n] - 1;
+    if (nnz > (int64_t)INT32_MAX) return h->fail(POLEE_EINVAL, "set_matrix: more than 2^31 - 1 entries (partition the rows over ranks)");
+    h->m = m; h->n = n; h->nnz = nnz;
+    h->gm = 0; h->gnnz = 0;
+
+    // Three layouts.  "ec" (equivalence classes, ec_setup.cu / ec_kernels.cu) is the default: rows with the same
+    // transcript set are stored as dense blocks (values only) and both sparse products run as Float64 MMAs in one
+    // pass.  Rows it does not take (small classes, very long rows) -- or all rows with POLEE_LAYOUT=split|fused, and
+    // always with exact_accumulation (reference summation order, bit-identical frag_probs) -- use the general layouts:
+    // "fused" (row tiles, one pass, Float32 inside a tile) where the row order has the locality it needs, else
+    // "split" (SELL slabs for K1 + re-sorted CSC for K2, two passes, w through HBM).
+    const char *lay = getenv("POLEE_LAYOUT");
+    const bool want_ec = !h->o.exact_accumulation && !(lay && (std::string(lay) == "split" || std::string(lay) == "fused"));
+    uint32_t *d_colptr_own = nullptr;
+    struct Own {
+        uint32_t *&p;
+        ~Own() { polee::dfree(p); }
+    } own{d_colptr_own};
+    if (!d_colptr) {
+        CK(polee::dmalloc((void **)&d_colptr_own, sizeof(uint32_t) * (n + 1)));
+        CK(cudaMemcpyAsync(d_colptr_own, colptr.data(), 4 * (n + 1), cudaMemcpyHostToDevice, st));
+        d_colptr = d_colptr_own;
+    }
+    if (want_ec) {
+        EcRest rest;
+        int rc = setup_ec_from_device_csc(h, m, n, nnz, d_colptr, d_rowval, d_nzval, d_ks, vals_ready_or_null, &rest);
+        if (rc) return rc;
+        if (h->ec_tasks > 0) {
+            if (rest.m == 0) {
+                h->have_matrix = true;
+                return POLEE_OK;
+            }
+            std::vector<uint32_t> rcolptr(n + 1);
+            CK(polee::copy_sync(h->stream, rcolptr.data(), rest.colptr, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost));
+            return setup_general_layouts(h, rest.m, n, rest.nnz, rest.colptr, rest.rowval, rest.nzval, rest.ks, rcolptr, nullptr);
+        }
+    }
+    return setup_general_layouts(h, m, n, nnz, d_colptr, d_rowval, d_nzval, d_ks, colptr, vals_ready_or_null);
 }
 
 }  // namespace polee

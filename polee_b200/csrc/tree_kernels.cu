@@ -610,9 +610,11 @@ __global__ void k3_elbo(int K, int KP, const double *__restrict__ lp, const doub
 
 void release_work_buffers(polee_handle *h) {
     void *ptrs[] = {h->zs0, h->zs, h->ys, h->ygrad, h->us, h->G, h->root_us, h->root_G, h->x, h->xd, h->w, h->g, h->seg_partial, h->S_partial,
-                    h->S, h->lp_partial, h->ladj_partial, h->grad_out, h->ft_partial, h->ft_lvl2, h->g32};
+                    h->S, h->lp_partial, h->ladj_partial, h->grad_out, h->ft_partial, h->ft_lvl2, h->g32,
+                    h->ec_partial, h->ec_lvl2, h->ec_lp_partial};
     for (void *p : ptrs) polee::dfree(p);
     h->ft_partial = nullptr; h->ft_lvl2 = nullptr; h->g32 = nullptr;
+    h->ec_partial = h->ec_lvl2 = h->ec_lp_partial = nullptr;
     h->zs0 = h->zs = nullptr; h->ys = h->ygrad = h->us = nullptr; h->G = nullptr; h->x = h->w = nullptr; h->xd = nullptr; h->root_us = nullptr; h->root_G = nullptr;
     h->g = h->seg_partial = h->S_partial = h->S = h->lp_partial = h->ladj_partial = nullptr;
     h->grad_out = nullptr;
@@ -658,6 +660,12 @@ int ensure_work_buffers(polee_handle *h, int KP) {
             CK(polee::dmalloc((void **)&h->ft_partial, sizeof(float) * std::max<int64_t>(h->ft_parts, 1) * KP));
             CK(polee::dmalloc((void **)&h->ft_lvl2, sizeof(double) * std::max(h->ft_nlvl2, 1) * KP));
             h->ft_grid = fused_grid(h, KP);
+        }
+        if (h->ec_tasks > 0) {
+            CK(polee::dmalloc((void **)&h->ec_partial, sizeof(double) * std::max<int64_t>(h->ec_parts, 1) * KP));
+            CK(polee::dmalloc((void **)&h->ec_lvl2, sizeof(double) * std::max(h->ec_nlvl2, 1) * KP));
+            CK(polee::dmalloc((void **)&h->ec_lp_partial, sizeof(double) * (size_t)h->ec_tasks * KP));
+            h->ec_grid = ec_grid(h, KP);
         }
     }
     h->work_KP = KP;

@@ -1,5 +1,6 @@
-"""GPU tests at BASELINE.json sizes through size-independent properties (the oracle is too slow there):
-identity sum_j x_j g_j = m, determinism, agreement between K-batched and one-at-a-time evaluation."""
+"""GPU tests at BASELINE.json sizes: the likelihood and its gradient against the oracle, elementwise, for every device
+layout (equivalence classes = the default, fused row tiles, split, exact accumulation), plus size-independent
+properties: identity sum_j x_j g_j = m, determinism, agreement between K-batched and one-at-a-time evaluation."""
 import numpy as np
 import pytest
 
@@ -13,6 +14,18 @@ def _device_sample(m, n, seed, **kw):
     colptr = s["colptr"].to(torch.int32)
     rowval = s["rowval"].to(torch.int32)
     return s, colptr, rowval
+
+
+LAYOUTS = {"ec": {}, "fused": {"POLEE_LAYOUT": "fused"}, "split": {"POLEE_LAYOUT": "split"}, "exact": {}}
+
+
+def _layout_handle(pb, layout, monkeypatch, K, m, n, colptr, rowval, nzval):
+    monkeypatch.delenv("POLEE_LAYOUT", raising=False)
+    for k, v in LAYOUTS[layout].items():
+        monkeypatch.setenv(k, v)
+    h = pb.Handle(num_mc_samples=K, num_steps=3, exact_accumulation=(layout == "exact"))
+    h.set_matrix_device(m, n, colptr.data_ptr(), rowval.data_ptr(), nzval.data_ptr())
+    return h
 
 
 def test_config2_shape_vs_oracle(oracle):
@@ -44,21 +57,58 @@ def test_config2_shape_vs_oracle(oracle):
     torch.cuda.empty_cache()
 
 
-def test_config3_shape_properties():
-    """C3: m = 30 M, n = 200 k, K = 8 on one B200: gradient identity, determinism, batched == single."""
+@pytest.fixture(scope="module")
+def c3_sample():
     import torch
-    import polee_b200 as pb
     from polee_b200 import synth
-    m, n, K = 30_000_000, 200_000, 8
+    m, n = 30_000_000, 200_000
     s, colptr, rowval = _device_sample(m, n, 20260003)
-    efflens = s["efflens"].cpu().numpy()
+    ns = synth.to_numpy_sample(s)
     tree = synth.balanced_tree(n, s["gene_sizes"].cpu().numpy())
+    yield s, colptr, rowval, ns, tree
+    del s, colptr, rowval
+    torch.cuda.empty_cache()
+
+
+def test_config3_vs_oracle_all_layouts(oracle, c3_sample, monkeypatch):
+    """C3 (the headline config: m = 30 M, n = 200 k, K = 8): ONE loglik_grad per device layout, lp and x_grad of two of
+    the eight draws against the oracle elementwise (north_star: 1e-5 relative; the oracle needs < 1 s per draw)."""
+    import polee_b200 as pb
+    s, colptr, rowval, ns, tree = c3_sample
+    m, n, K = s["m"], s["n"], 8
+    xs = np.random.default_rng(0).dirichlet(np.ones(n), K).astype(np.float32).clip(1e-10)
+    M = oracle.Model(m, n, ns["colptr"], ns["rowval"], ns["nzval"])
+    ref = {k: M.log_likelihood(xs[k], gradonly=False) for k in (0, 5)}
+    got = {}
+    for layout in ("ec", "fused", "split", "exact"):
+        h = _layout_handle(pb, layout, monkeypatch, K, m, n, colptr, rowval, s["nzval"])
+        h.set_tree(*tree)
+        info = h.layout_info()
+        if layout == "ec":
+            assert info["ec_rows"] > 0.9 * m, info             # the class layout takes nearly every row of C3
+        else:
+            assert info["ec_rows"] == 0 and info["general_kind"] == ("fused" if layout == "fused" else "split"), info
+        lp, g = h.loglik_grad(xs, gradonly=False)
+        h.close()
+        for k, (lp_o, g_o) in ref.items():
+            assert abs(lp[k] - lp_o) <= 1e-8 * abs(lp_o), (layout, k)
+            nz = g_o != 0
+            assert np.array_equal(g[k][~nz], g_o[~nz]), layout
+            err = float(np.max(np.abs(g[k][nz] - g_o[nz]) / g_o[nz]))
+            assert err <= 1e-5, (layout, k, err)
+        got[layout] = g
+    assert np.max(np.abs(got["ec"] - got["exact"]) / np.maximum(got["exact"], 1e-300)) <= 1e-6
+
+
+def test_config3_shape_properties(c3_sample):
+    """C3 on one B200, default layout: gradient identity, determinism, batched == single, a finite fit."""
+    import polee_b200 as pb
+    s, colptr, rowval, ns, tree = c3_sample
+    m, n, K = s["m"], s["n"], 8
     h = pb.Handle(num_mc_samples=K, num_steps=3)
     h.set_matrix_device(m, n, colptr.data_ptr(), rowval.data_ptr(), s["nzval"].data_ptr())
     nnz = s["nnz"]
-    del s, colptr, rowval
-    torch.cuda.empty_cache()
-    h.set_efflens(efflens)
+    h.set_efflens(ns["efflens"])
     h.set_tree(*tree)
     rng = np.random.default_rng(0)
     xs = rng.dirichlet(np.ones(n), K).astype(np.float32).clip(1e-10)
@@ -95,24 +145,38 @@ def test_config5_many_samples_replicas():
         assert all(np.array_equal(a[k], b[k]) for k in ("mu", "omega", "alpha"))
 
 
-def test_config4_shape_long_rows_properties():
-    """C4 shape (heavy multi-mapping: 10 % of the rows span 64-512 transcripts), scaled to one GPU's test budget:
-    m = 4 M, n = 250 k, nnz ~ 120 M; gradient identity, determinism and a finite fit."""
+def test_config4_shape_long_rows_vs_oracle(oracle, monkeypatch):
+    """C4 shape (heavy multi-mapping: 10 % of the rows span 64-512 transcripts), one rank's share of the 8-GPU config:
+    m = 4 M, n = 250 k, nnz ~ 120 M.  Every layout that accepts long rows against the oracle elementwise, then the
+    gradient identity, determinism and a finite fit on the default layout."""
     import torch
     import polee_b200 as pb
     from polee_b200 import synth
     m, n, K = 4_000_000, 250_000, 8
     s, colptr, rowval = _device_sample(m, n, 20260004, long_rows=True)
     assert s["nnz"] > 100_000_000
-    efflens = s["efflens"].cpu().numpy()
+    ns = synth.to_numpy_sample(s)
     tree = synth.balanced_tree(n, s["gene_sizes"].cpu().numpy())
+    xs = np.random.default_rng(0).dirichlet(np.ones(n), K).astype(np.float32).clip(1e-10)
+    M = oracle.Model(m, n, ns["colptr"], ns["rowval"], ns["nzval"])
+    ref = {k: M.log_likelihood(xs[k], gradonly=False) for k in (2,)}
+    for layout in ("ec", "split", "exact"):
+        h = _layout_handle(pb, layout, monkeypatch, K, m, n, colptr, rowval, s["nzval"])
+        h.set_tree(*tree)
+        lp, g = h.loglik_grad(xs, gradonly=False)
+        h.close()
+        for k, (lp_o, g_o) in ref.items():
+            assert abs(lp[k] - lp_o) <= 1e-8 * abs(lp_o), (layout, k)
+            nz = g_o != 0
+            err = float(np.max(np.abs(g[k][nz] - g_o[nz]) / g_o[nz]))
+            assert err <= 1e-5, (layout, k, err)
+    monkeypatch.delenv("POLEE_LAYOUT", raising=False)
     h = pb.Handle(num_mc_samples=K, num_steps=3)
     h.set_matrix_device(m, n, colptr.data_ptr(), rowval.data_ptr(), s["nzval"].data_ptr())
     del s, colptr, rowval
     torch.cuda.empty_cache()
-    h.set_efflens(efflens)
+    h.set_efflens(ns["efflens"])
     h.set_tree(*tree)
-    xs = np.random.default_rng(0).dirichlet(np.ones(n), K).astype(np.float32).clip(1e-10)
     lp, g = h.loglik_grad(xs, gradonly=False)
     ident = (xs.astype(np.float64) * g).sum(1)
     assert np.max(np.abs(ident - m)) <= 1e-5 * m
