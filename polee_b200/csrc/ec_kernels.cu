@@ -9,11 +9,12 @@
 // done with the FP64 tensor-core MMA (mma.sync m8n8k4 f64 -> SASS DMMA).  The MMA is used for its operand layout, not
 // for its peak (DMMA and DFMA both measure 37 TFLOP/s on B200, tools/ubench/fp64_rates.cu): the accumulator fragment
 // spreads the L x K column sums over the lanes, so a task needs L/4 registers of accumulators instead of L x K per lane
-// and NO cross-lane reduction, and each MMA consumes one conflict-free 128-byte shared-memory read of values.
+// and NO cross-lane reduction, each MMA consumes one conflict-free 128-byte shared-memory read of values, and with the
+// p pass computed transposed the reciprocals are already the g pass's B fragments (w never leaves the registers).
 // Products are exact (Float32 x Float32 in Float64), sums are Float64 throughout -- at least the reference's
 // "Float32 product, Float64 accumulation"  -- and 1/p is MUFU.RCP64H + one Newton step (8.5e-13).
 //
-// Every warp is its own pipeline: it owns a ring of EC_STAGES shared-memory stages fed by 1-D bulk copies
+// Every warp is its own pipeline: it owns EC_STAGES shared-memory stages fed by 1-D bulk copies
 // (cp.async.bulk -> UBLKCP) completing on mbarriers, takes tasks gw, gw + G, gw + 2G, ... (static, so results do not
 // depend on scheduling), and never synchronises with another warp.  Output: one Float64 partial per (task, column) at
 // its slot of the column-ordered partial array; k_ec_combine1/2 add each column's partials in a fixed order.
@@ -28,17 +29,18 @@ namespace polee {
 
 namespace {
 
-constexpr int EC_WARPS = 8;
+constexpr int EC_WARPS = 11;
+constexpr int EC_STAGES = 2;
 constexpr uint32_t EC_STAGE_STRIDE = (EC_STAGE_BYTES + 127u) & ~127u;
+constexpr uint32_t EC_CTL_BYTES = 384;  // 128 bytes of zeros (the "no such chunk" operand) + the mbarriers
 
 template <int KP>
 struct EcCfg {
-    static constexpr int NT = KP > 8 ? KP / 8 : 1;          // 8-draw tiles (the MMA's N)
-    static constexpr int STAGES = KP > 8 ? 2 : 3;
-    static constexpr uint32_t W_BYTES = 32u * 8u * NT * 8u;  // w of one block: [32 rows][8 NT] Float64
-    static constexpr uint32_t WARP_BYTES = STAGES * EC_STAGE_STRIDE + W_BYTES;
-    static constexpr uint32_t SMEM = EC_WARPS * WARP_BYTES + 256u;  // + the mbarriers
+    static constexpr int NT = KP > 8 ? KP / 8 : 1;  // 8-draw tiles (the MMA's M in the p pass, N in the g pass)
+    static constexpr uint32_t WARP_BYTES = EC_STAGES * EC_STAGE_STRIDE;
+    static constexpr uint32_t SMEM = EC_WARPS * WARP_BYTES + EC_CTL_BYTES;
 };
+static_assert(EC_WARPS * EC_STAGES * 8 <= EC_CTL_BYTES - 128, "mbarrier block");
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -46,153 +48,174 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-// 1 / p: MUFU.RCP64H seed (9e-7) + one Newton step (8.5e-13 measured).  p = 0 / inf / NaN keep the seed's inf / 0 / NaN.
+// 1 / p: MUFU.RCP64H seed (9e-7) + one Newton step (8.5e-13 measured, tools/ubench/fp64_rates.cu).
+// p = 0 gives NaN where the reference's 1/p gives Inf: non-finite either way (-> POLEE_ENONFINITE).
 __device__ __forceinline__ double rcp64(double p) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
     const double e = fma(-p, r, 1.0);
-    return (e == e) ? fma(r, e, r) : r;
+    return fma(r, e, r);
 }
 
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
+// Float32 -> Float64 with three integer instructions instead of F2F (which shares the 16-lane XU pipe with MUFU):
+// exact for normal numbers of either sign; +0 becomes 2^-127 (only the layout's zero padding is 0, and a 1e-39
+// addend to a row sum >= 1e-22 is far below Float64 resolution); Inf / NaN become large finite numbers -- the g pass
+// converts the same values with F2F, so a non-finite matrix entry still poisons the gradient and is reported.
+__device__ __forceinline__ double widen_bits(float f) {
+    const uint32_t u = __float_as_uint(f);
+    const uint32_t hi = (((u >> 3) & 0x0FFFFFFFu) + 0x38000000u) | (u & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(u << 29));
 }
 
-// One task.  MAXLC = compile-time bound on the task's 4-column chunks (L <= 4 * MAXLC); loops are fully unrolled and
-// guarded by the (warp-uniform) real counts so that every fragment lives in a register.
-template <int KP, int MAXLC, bool LP, bool WEIGHTED, bool WRITE_W>
-__device__ __forceinline__ void ec_task(const unsigned char *__restrict__ stage, double *__restrict__ w_sm, int task,
-                                        const float *__restrict__ xf, double *__restrict__ partial,
+// One task.  NLC = the task's 4-column chunks; EXACT: nlc == NLC (no guards at all), else nlc <= NLC and the fully
+// unrolled loops are guarded by the warp-uniform real count.
+//
+// p pass, transposed:  p^T[k][r] = sum_l x^T[k][l] V^T[l][r]   (M = 8 draws, N = 8 rows, K = 4 columns per MMA)
+//     A (row g, col t) = x[column 4 lc + t][draw g]                    -- registers, loaded once per task
+//     B (row t, col g) = V[row 8 j + g][column 4 lc + t]               -- one 128-byte chunk (lc, j), lane order
+//     C: thread (g, t) holds p[rows 8 j + 2 t, 8 j + 2 t + 1][draw g]
+// g pass:  D[l][k] += sum_r V^T[l][r] w[r][k]                   (M = 8 columns, N = 8 draws, K = 4 rows per MMA)
+//     the four K slots of MMA (j, i) are the rows 8 j + 2 t + i, t = 0..3, so that
+//     B (row t, col g) = w[row 8 j + 2 t + i][draw g] = 1 / (the thread's own C fragment)  -- no data movement
+//     A (row g, col t) = V[row 8 j + 2 t + i][column 8 lt + g]          -- chunk (2 lt + (g >> 2), j)
+//     D: thread (g, t) holds g[column 8 lt + g][draws 2 t, 2 t + 1]
+template <int KP, int NLC, bool EXACT, bool LP, bool WEIGHTED, bool WRITE_W>
+__device__ __forceinline__ void ec_task(const unsigned char *__restrict__ stage, const float *__restrict__ zero_chunk,
+                                        int task, const float *__restrict__ xf, double *__restrict__ partial,
                                         const float *__restrict__ slot_weight, const uint32_t *__restrict__ row_of_slot,
                                         double *__restrict__ lp_partial, float *__restrict__ w_out, int lane) {
     constexpr int NT = EcCfg<KP>::NT;
-    constexpr int MAXLT = (MAXLC + 1) / 2;
-    constexpr int WROW = 8 * NT;  // doubles per row of w_sm
+    constexpr int NLT = (NLC + 1) / 2;
     const EcHdr hd = *reinterpret_cast<const EcHdr *>(stage);
-    const uint32_t L = hd.L, Lp = ec_lp(L), nlc = Lp >> 2, nlt = (nlc + 1u) >> 1;
+    const uint32_t L = hd.L, Lp = ec_lp(L), nlc = EXACT ? (uint32_t)NLC : (Lp >> 2), nlt = (nlc + 1u) >> 1;
     const uint32_t *cols = reinterpret_cast<const uint32_t *>(stage + 16);
     const uint32_t *dest = cols + Lp;
     const float *V = reinterpret_cast<const float *>(stage + 16 + 8u * Lp);
     const int g = lane >> 2, t = lane & 3;
 
-    // x of the task's columns as B fragments: (k-row = column 4 lc + t, n = draw g)
-    double xb[MAXLC][NT];
+    double xa[NLC][NT];
 #pragma unroll
-    for (int lc = 0; lc < MAXLC; ++lc) {
+    for (int lc = 0; lc < NLC; ++lc) {
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) xb[lc][nt] = 0.0;
-        if ((uint32_t)lc < nlc) {
+        for (int nt = 0; nt < NT; ++nt) xa[lc][nt] = 0.0;
+        if (EXACT || (uint32_t)lc < nlc) {
             const uint32_t col = cols[lc * 4 + t];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
-                if (nt * 8 + g < KP) xb[lc][nt] = (double)__ldg(xf + (size_t)col * KP + nt * 8 + g);
+                if (nt * 8 + g < KP) xa[lc][nt] = (double)__ldg(xf + (size_t)col * KP + nt * 8 + g);
         }
     }
-    constexpr int CH = MAXLT >= 4 ? 1 : 2;  // independent accumulator chains per tile (hide the MMA latency)
-    double d[MAXLT][NT][CH][2];  // [column tile][draw tile][chain][fragment]
+    double d[NLT][NT][2][2];  // [column tile][draw tile][chain i][fragment]
 #pragma unroll
-    for (int lt = 0; lt < MAXLT; ++lt)
+    for (int lt = 0; lt < NLT; ++lt)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
+        for (int nt = 0; nt < NT; ++nt) d[lt][nt][0][0] = d[lt][nt][0][1] = d[lt][nt][1][0] = d[lt][nt][1][1] = 0.0;
+    double lpv[NT];
 #pragma unroll
-            for (int c2 = 0; c2 < CH; ++c2) d[lt][nt][c2][0] = d[lt][nt][c2][1] = 0.0;
-    double lpv[NT][2];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) lpv[nt][0] = lpv[nt][1] = 0.0;
+    for (int nt = 0; nt < NT; ++nt) lpv[nt] = 0.0;
 
-    // position of this lane's A-fragment element inside a 32-float chunk
-    const uint32_t posA = (uint32_t)lane;                                             // p pass: (row g, column t)
-    const uint32_t posG0 = (uint32_t)(((t * 4) + (g & 3)) ^ ((g >> 2) << 4));          // g pass, even row chunk
-    const uint32_t posG1 = (uint32_t)((((4 + t) * 4) + (g & 3)) ^ ((g >> 2) << 4));    // g pass, odd row chunk
+    // g pass: element offsets inside a chunk (floats), and which chunk of a column tile this lane reads
+    const uint32_t posG0 = (uint32_t)(((2 * t) * 4 + (g & 3)) ^ ((g >> 2) << 4));
+    const uint32_t posG1 = (uint32_t)(((2 * t + 1) * 4 + (g & 3)) ^ ((g >> 2) << 4));
 
     for (uint32_t b = 0; b < hd.nb; ++b) {
         const float *Vb = V + (size_t)b * Lp * 32u;
-        // ---------------- p = V x  (rows 8 mt + g, draws 2 t, 2 t + 1)
+        // ---------------- p^T = x^T V^T
         double c[4][NT][2];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+            for (int nt = 0; nt < NT; ++nt) c[j][nt][0] = c[j][nt][1] = 0.0;
 #pragma unroll
-        for (int lc = 0; lc < MAXLC; ++lc) {
-            if ((uint32_t)lc < nlc) {
-                const float *ch = Vb + lc * 128 + (posA ^ ((lc & 1) << 4));
+        for (int lc = 0; lc < NLC; ++lc) {
+            if (EXACT || (uint32_t)lc < nlc) {
+                const float *ch = Vb + lc * 128 + ((uint32_t)lane ^ ((lc & 1) << 4));
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
-                    const double a = (double)ch[mt * 32];
+                for (int j = 0; j < 4; ++j) {
+                    const double v = widen_bits(ch[j * 32]);
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) dmma(c[mt][nt], a, xb[lc][nt]);
+                    for (int nt = 0; nt < NT; ++nt) dmma(c[j][nt], xa[lc][nt], v);
                 }
             }
         }
-        // ---------------- w = 1 / p (x ks), log p
+        // ---------------- w = 1 / p (x ks), log p: c becomes w in place
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-            const uint32_t row = mt * 8 + g;
-            const bool valid = b * 32u + row < hd.rows;
-            double wt = 1.0;
-            if (WEIGHTED) wt = valid ? (double)slot_weight[hd.slot0 + b * 32u + row] : 0.0;
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                double w0 = valid ? rcp64(c[mt][nt][0]) : 0.0;
-                double w1 = valid ? rcp64(c[mt][nt][1]) : 0.0;
-                if (WEIGHTED) {
-                    w0 *= wt;
-                    w1 *= wt;
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (LP) {
+                        const uint32_t row = b * 32u + 8 * j + 2 * t + i;
+                        if (row < hd.rows && nt * 8 + g < KP)
+                            lpv[nt] += WEIGHTED ? (double)slot_weight[hd.slot0 + row] * log(c[j][nt][i]) : log(c[j][nt][i]);
+                    }
+                    c[j][nt][i] = rcp64(c[j][nt][i]);
                 }
-                if (LP && valid) {
-                    if (nt * 8 + 2 * t < KP) lpv[nt][0] += WEIGHTED ? wt * log(c[mt][nt][0]) : log(c[mt][nt][0]);
-                    if (nt * 8 + 2 * t + 1 < KP) lpv[nt][1] += WEIGHTED ? wt * log(c[mt][nt][1]) : log(c[mt][nt][1]);
+        if (WEIGHTED) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t row = b * 32u + 8 * j + 2 * t + i;
+                    const double wt = row < hd.rows ? (double)slot_weight[hd.slot0 + row] : 0.0;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) c[j][nt][i] *= wt;
                 }
-                *reinterpret_cast<double2 *>(w_sm + row * WROW + nt * 8 + 2 * t) = make_double2(w0, w1);
-                if (WRITE_W && valid) {
-                    const size_t r0 = (size_t)row_of_slot[hd.slot0 + b * 32u + row] * KP;
-                    if (nt * 8 + 2 * t < KP) w_out[r0 + nt * 8 + 2 * t] = (float)w0;
-                    if (nt * 8 + 2 * t + 1 < KP) w_out[r0 + nt * 8 + 2 * t + 1] = (float)w1;
-                }
-            }
         }
-        __syncwarp();
-        // ---------------- g += V^T w  (columns 8 lt + g, draws 2 t, 2 t + 1)
-        double wb[8][NT];
+        if (b * 32u + 32u > hd.rows || KP < 8) {  // padding rows (last block of a class) and padding draws: w = 0
 #pragma unroll
-        for (int rc = 0; rc < 8; ++rc)
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) wb[rc][nt] = w_sm[(rc * 4 + t) * WROW + nt * 8 + g];
+                for (int i = 0; i < 2; ++i) {
+                    const bool rok = b * 32u + 8 * j + 2 * t + i < hd.rows;
 #pragma unroll
-        for (int lt = 0; lt < MAXLT; ++lt) {
-            if ((uint32_t)lt < nlt) {
+                    for (int nt = 0; nt < NT; ++nt)
+                        if (!rok || nt * 8 + g >= KP) c[j][nt][i] = 0.0;
+                }
+        }
+        if (WRITE_W) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t row = b * 32u + 8 * j + 2 * t + i;
+                    if (row < hd.rows) {
+                        const size_t r0 = (size_t)row_of_slot[hd.slot0 + row] * KP;
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+                            if (nt * 8 + g < KP) w_out[r0 + nt * 8 + g] = (float)c[j][nt][i];
+                    }
+                }
+        }
+        // ---------------- g += V^T w
+#pragma unroll
+        for (int lt = 0; lt < NLT; ++lt) {
+            if (EXACT || (uint32_t)lt < nlt) {
                 const uint32_t lc = 2u * lt + (uint32_t)(g >> 2);
-                const bool has = lc < nlc;
-                const float *ch = Vb + (has ? lc : 0u) * 128u;
+                const float *ch = (lc < nlc) ? Vb + lc * 128u : zero_chunk;
+                const uint32_t jstep = (lc < nlc) ? 32u : 0u;
 #pragma unroll
-                for (int rc = 0; rc < 8; ++rc) {
-                    const float av = ch[(rc >> 1) * 32 + ((rc & 1) ? posG1 : posG0)];
-                    const double a = has ? (double)av : 0.0;
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) dmma(d[lt][nt][rc & (CH - 1)], a, wb[rc][nt]);
-                }
+                    for (int i = 0; i < 2; ++i) {
+                        const double a = (double)ch[j * jstep + (i ? posG1 : posG0)];
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) dmma(d[lt][nt][i], a, c[j][nt][i]);
+                    }
             }
         }
-        __syncwarp();
     }
 
     // ---------------- the task's column partials -> their slots of the column-ordered partial array
 #pragma unroll
-    for (int lt = 0; lt < MAXLT; ++lt) {
+    for (int lt = 0; lt < NLT; ++lt) {
         const uint32_t l = lt * 8 + g;
-        if ((uint32_t)lt < nlt && l < L) {
+        if ((EXACT || (uint32_t)lt < nlt) && l < L) {
             double *out = partial + (size_t)dest[l] * KP;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const double v0 = CH == 2 ? d[lt][nt][0][0] + d[lt][nt][CH - 1][0] : d[lt][nt][0][0];
-                const double v1 = CH == 2 ? d[lt][nt][0][1] + d[lt][nt][CH - 1][1] : d[lt][nt][0][1];
+                const double v0 = d[lt][nt][0][0] + d[lt][nt][1][0], v1 = d[lt][nt][0][1] + d[lt][nt][1][1];
                 if constexpr (KP >= 2) {
                     if (nt * 8 + 2 * t < KP) *reinterpret_cast<double2 *>(out + nt * 8 + 2 * t) = make_double2(v0, v1);
                 } else {
@@ -201,17 +224,14 @@ __device__ __forceinline__ void ec_task(const unsigned char *__restrict__ stage,
             }
         }
     }
-    if (LP) {
+    if (LP) {  // lanes (g, t = 0..3) hold partial sums of draw g
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                double v = lpv[nt][i];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                if (g == 0 && nt * 8 + 2 * t + i < KP) lp_partial[(size_t)task * KP + nt * 8 + 2 * t + i] = v;
-            }
+        for (int nt = 0; nt < NT; ++nt) {
+            double v = lpv[nt];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t == 0 && nt * 8 + g < KP) lp_partial[(size_t)task * KP + nt * 8 + g] = v;
+        }
     }
 }
 
@@ -221,24 +241,22 @@ __global__ void __launch_bounds__(EC_WARPS * 32, 1)
              const float *__restrict__ xf, double *__restrict__ partial, const float *__restrict__ slot_weight,
              const uint32_t *__restrict__ row_of_slot, double *__restrict__ lp_partial, float *__restrict__ w_out) {
     using Cfg = EcCfg<KP>;
-    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ __align__(128) unsigned char smraw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *mine = smraw + 256 + (size_t)warp * Cfg::WARP_BYTES;
-    double *w_sm = reinterpret_cast<double *>(mine + STAGES * EC_STAGE_STRIDE);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smraw) + warp * STAGES;
-    static_assert(EC_WARPS * STAGES * 8 <= 256, "mbarrier block");
+    const float *zero_chunk = reinterpret_cast<const float *>(smraw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smraw + 128) + warp * EC_STAGES;
+    unsigned char *mine = smraw + EC_CTL_BYTES + (size_t)warp * Cfg::WARP_BYTES;
     const int gw = blockIdx.x * EC_WARPS + warp, G = gridDim.x * EC_WARPS;
+    if (threadIdx.x < 32) reinterpret_cast<float *>(smraw)[threadIdx.x] = 0.0f;
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < EC_STAGES; ++s) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
-    // prologue: the first STAGES tasks of this warp
-    if (lane == 0) {
+    __syncthreads();  // the only block-wide barrier: zero chunk + mbarriers visible
+    if (lane == 0) {  // prologue: the first EC_STAGES tasks of this warp
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < EC_STAGES; ++s) {
             const int tk = gw + s * G;
             if (tk < n_tasks) {
                 const EcTaskDesc dd = desc[tk];
@@ -251,27 +269,29 @@ __global__ void __launch_bounds__(EC_WARPS * 32, 1)
     uint32_t phase = 0;
     for (int tk = gw; tk < n_tasks; tk += G) {
         // descriptor of the task that will reuse this stage, fetched while the current one is processed
-        const int nxt = tk + STAGES * G;
+        const int nxt = tk + EC_STAGES * G;
         EcTaskDesc dn{0, 0, 0};
         if (lane == 0 && nxt < n_tasks) dn = desc[nxt];
         mbar_wait(&bars[s], (phase >> s) & 1u);
         phase ^= 1u << s;
         const unsigned char *stage = mine + s * EC_STAGE_STRIDE;
-        const uint32_t L = reinterpret_cast<const EcHdr *>(stage)->L;
-        if (L <= 8)
-            ec_task<KP, 2, LP, WEIGHTED, WRITE_W>(stage, w_sm, tk, xf, partial, slot_weight, row_of_slot, lp_partial, w_out, lane);
-        else if (L <= 16)
-            ec_task<KP, 4, LP, WEIGHTED, WRITE_W>(stage, w_sm, tk, xf, partial, slot_weight, row_of_slot, lp_partial, w_out, lane);
-        else if (L <= 32)
-            ec_task<KP, 8, LP, WEIGHTED, WRITE_W>(stage, w_sm, tk, xf, partial, slot_weight, row_of_slot, lp_partial, w_out, lane);
-        else
-            ec_task<KP, 16, LP, WEIGHTED, WRITE_W>(stage, w_sm, tk, xf, partial, slot_weight, row_of_slot, lp_partial, w_out, lane);
+        const uint32_t nlc = ec_lp(reinterpret_cast<const EcHdr *>(stage)->L) >> 2;
+#define EC_CALL(N, EX) ec_task<KP, N, EX, LP, WEIGHTED, WRITE_W>(stage, zero_chunk, tk, xf, partial, slot_weight, row_of_slot, lp_partial, w_out, lane)
+        switch (nlc) {
+            case 1: EC_CALL(1, true); break;
+            case 2: EC_CALL(2, true); break;
+            case 3: EC_CALL(3, true); break;
+            case 4: EC_CALL(4, true); break;
+            default:
+                if (nlc <= 8) EC_CALL(8, false); else EC_CALL(16, false);
+        }
+#undef EC_CALL
         __syncwarp();  // every lane is done reading the stage
         if (lane == 0 && nxt < n_tasks) {
             mbar_expect_tx(&bars[s], dn.bytes);
             bulk_g2s(mine + s * EC_STAGE_STRIDE, blob + dn.off, dn.bytes, &bars[s]);
         }
-        s = (s + 1 == STAGES) ? 0 : s + 1;
+        s = (s + 1 == EC_STAGES) ? 0 : s + 1;
     }
 }
 

@@ -349,7 +349,8 @@ int setup_ec_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t nnz,
         return sc.alloc((char **)&d_tmp, tmp_bytes);
     };
     uint32_t min_rows = EC_MIN_ROWS_DEFAULT;
-    if (const char *e = getenv("POLEE_EC_MIN_ROWS")) min_rows = (uint32_t)std::max(1, atoi(e));
+    const char *min_rows_env = getenv("POLEE_EC_MIN_ROWS");
+    if (min_rows_env) min_rows = (uint32_t)std::max(1, atoi(min_rows_env));
 
     // ---- 1. CSR order
     uint32_t *row_len, *row_ptr, *col_of, *key_row, *val_e, *row_sorted, *a_csc, *col_csr;
@@ -403,9 +404,11 @@ int setup_ec_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t nnz,
     CK(cub::DeviceRadixSort::SortPairs(nullptr, need, leader, leader_s, gid_iota, cls_s, (int)n_classes, 0, 32, st));
     CK(ensure_tmp(need));
     CK(cub::DeviceRadixSort::SortPairs(d_tmp, need, leader, leader_s, gid_iota, cls_s, (int)n_classes, 0, ec_bits_for((uint64_t)m), st));
-    k_ec_class_meta<<<grid_for(nc1), TPB, 0, st>>>(n_classes, cls_s, leader_s, cstart, row_len, min_rows, order_of_class, cls_L,
-                                                    cls_nt, cls_nb, cls_bytes, cls_parts, cls_rows, cls_ent);
-    {
+    uint32_t n_tasks = 0, n_blocks = 0, n_parts = 0, ec_rows = 0;
+    uint64_t total_bytes = 0, ec_ent = 0;
+    auto build_table = [&](uint32_t min_r) -> int {
+        k_ec_class_meta<<<grid_for(nc1), TPB, 0, st>>>(n_classes, cls_s, leader_s, cstart, row_len, min_r, order_of_class, cls_L,
+                                                        cls_nt, cls_nb, cls_bytes, cls_parts, cls_rows, cls_ent);
         size_t need2 = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, need, cls_nt, task0, (int)nc1, st));
         CK(cub::DeviceScan::ExclusiveSum(nullptr, need2, cls_bytes, byte0, (int)nc1, st));
@@ -416,16 +419,26 @@ int setup_ec_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t nnz,
         CK(cub::DeviceScan::ExclusiveSum(d_tmp, need, cls_rows, rows0, (int)nc1, st));
         CK(cub::DeviceScan::ExclusiveSum(d_tmp, need2, cls_bytes, byte0, (int)nc1, st));
         CK(cub::DeviceScan::ExclusiveSum(d_tmp, need2, cls_ent, ent0, (int)nc1, st));
+        CK(cudaMemcpyAsync(&n_tasks, task0 + n_classes, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&n_blocks, blk0 + n_classes, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&n_parts, part0 + n_classes, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ec_rows, rows0 + n_classes, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&total_bytes, byte0 + n_classes, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ec_ent, ent0 + n_classes, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return POLEE_OK;
+    };
+    // Small classes pay for their padding (a block is 32 rows whatever the class holds), but taking EVERY class spares
+    // the step the general kernels altogether (their launches alone cost as much as ~0.5 GB of streaming): take all
+    // classes when the padded layout stays below the 8 bytes per entry ONE pass of the general layouts streams, else
+    // only classes of >= EC_MIN_ROWS_DEFAULT rows.  POLEE_EC_MIN_ROWS overrides.
+    {
+        int rc = build_table(min_rows_env ? min_rows : 1u);
+        if (rc) return rc;
+        if (!min_rows_env && (double)total_bytes > 8.0 * (double)ec_ent) {
+            if ((rc = build_table(min_rows))) return rc;
+        }
     }
-    uint32_t n_tasks = 0, n_blocks = 0, n_parts = 0, ec_rows = 0;
-    uint64_t total_bytes = 0, ec_ent = 0;
-    CK(cudaMemcpyAsync(&n_tasks, task0 + n_classes, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&n_blocks, blk0 + n_classes, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&n_parts, part0 + n_classes, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&ec_rows, rows0 + n_classes, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&total_bytes, byte0 + n_classes, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&ec_ent, ent0 + n_classes, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
     pt.mark("ec: class table");
     if (getenv("POLEE_SETUP_TIMING"))
         fprintf(stderr, "[polee setup] ec: %u classes; %u rows (%.1f %%) / %llu entries (%.1f %%) in %u tasks, %u blocks, %.1f MB "
