@@ -4,7 +4,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpolee_b200.so")
+# POLEE_B200_LIB: an experimental build (csrc/Makefile VARIANT=...) instead of the real library
+LIB_PATH = os.environ.get("POLEE_B200_LIB") or os.path.join(_HERE, "libpolee_b200.so")
 
 POLEE_OK, POLEE_EINVAL, POLEE_ECUDA, POLEE_EBADTREE, POLEE_ENONFINITE, POLEE_ENCCL, POLEE_ENOMEM = range(7)
 APPROX_LSN_PTT, APPROX_OPTIMIZE_PTT = 0, 1

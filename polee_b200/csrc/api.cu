@@ -456,7 +456,7 @@ static int ready_for_steps(polee_handle *h) {
 
 // log-likelihood gradient of the KP draws in h->x: the equivalence-class pass, plus -- for the rows it did not take, or
 // for all rows when it is switched off -- the fused single pass or K1 + K2 on the split layout
-static int launch_likelihood(polee_handle *h, int KP, bool want_lp) {
+static int launch_likelihood(polee_handle *h, int KP, int K, bool want_lp) {
     int rc;
     const bool general = h->gm > 0 || h->ec_tasks == 0;
     double *lp_out = h->g + (size_t)h->n * KP;
@@ -469,7 +469,7 @@ static int launch_likelihood(polee_handle *h, int KP, bool want_lp) {
         }
         if (want_lp && (rc = launch_reduce_lp(h, h->lp_partial, lp_out, KP))) return rc;
     }
-    if (h->ec_tasks > 0 && (rc = launch_ec(h, h->x, h->g, general, want_lp, lp_out, nullptr, KP))) return rc;
+    if (h->ec_tasks > 0 && (rc = launch_ec(h, h->x, h->g, general, want_lp, lp_out, nullptr, KP, K))) return rc;
     return POLEE_OK;
 }
 
@@ -491,7 +491,7 @@ static int launch_step_sequence(polee_handle *h, bool do_adam, bool next_reparam
     CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
     if ((rc = launch_mid(h, KP, do_adam ? 1 : 0, h->side_stream))) return rc;
     CK(cudaEventRecord(h->ev_join, h->side_stream));
-    if ((rc = launch_likelihood(h, KP, want_vals))) return rc;
+    if ((rc = launch_likelihood(h, KP, K, want_vals))) return rc;
     CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
 #ifdef POLEE_WITH_NCCL
     if (h->nranks > 1) {
@@ -669,7 +669,7 @@ extern "C" int polee_loglik_grad(polee_handle *h, const float *xs, int32_t K, in
     if ((rc = use_kp(h, K, &KP))) return rc;
     if ((rc = upload_kmajor<float>(h, xs, K, KP, h->n, h->x, 1.0f))) return rc;
     if ((rc = launch_widen_x(h, h->x, h->xd, KP))) return rc;
-    if ((rc = launch_likelihood(h, KP, !gradonly))) return rc;
+    if ((rc = launch_likelihood(h, KP, K, !gradonly))) return rc;
     CK(cudaGetLastError());
     if (x_grad && (rc = download_kmajor<double, double>(h, h->g, K, KP, h->n, x_grad))) return rc;
     if (lp) {
@@ -701,7 +701,7 @@ extern "C" int polee_frag_prob_recip(polee_handle *h, const float *xs, float *w)
     if (h->ec_tasks > 0) {  // the class layout scatters 1/p to the rows' original positions
         CK(polee::dmalloc((void **)&d_w, sizeof(float) * (size_t)h->m * KP));
         CK(cudaMemsetAsync(d_w, 0, sizeof(float) * (size_t)h->m * KP, h->stream));
-        if ((rc = launch_ec(h, h->x, h->g, false, false, nullptr, d_w, KP))) return rc;
+        if ((rc = launch_ec(h, h->x, h->g, false, false, nullptr, d_w, KP, 1))) return rc;
         CK(cudaStreamSynchronize(h->stream));
         std::vector<float> wp((size_t)h->m * KP);
         CK(polee::copy_sync(h->stream, wp.data(), d_w, sizeof(float) * wp.size(), cudaMemcpyDeviceToHost));
@@ -949,7 +949,7 @@ extern "C" int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, f
     CK(cudaEventRecord(e0, h->stream));
     for (int r = 0; r < reps && !rc; ++r) {
         if (which == 1) {  // the whole likelihood pass, except on the pure split layout (K1 here, K2 under which == 2)
-            rc = (h->ec_tasks > 0 || h->fused) ? launch_likelihood(h, KP, false)
+            rc = (h->ec_tasks > 0 || h->fused) ? launch_likelihood(h, KP, K, false)
                                                : launch_k1(h, h->x, h->xd, h->w, false, h->lp_partial, KP);
         } else if (which == 2) {
             if (h->ec_tasks == 0 && !h->fused) rc = launch_k2(h, h->w, h->g, KP);  // otherwise: no second sparse kernel

@@ -92,31 +92,48 @@ __host__ __device__ inline BlobLayout blob_layout(const FusedHdr &hd) {
 // of R rows and L transcripts is a DENSE R x L block of Float32 values sharing ONE list of L column ids.  Position-sorted
 // reads (src/rnaseq_sample.jl:399-419) make classes large (fixture: 496 classes for 19 743 rows).  The layout stores the
 // column ids once per task and the values alone per entry (4 B/entry + padding instead of 8 B twice), and both sparse
-// passes of a step become small dense products with the K draws as the third dimension:
+// passes of a step are done on the block while it sits in shared memory, for the K draws at once:
 //     p[r][k] = sum_l V[r][l] x[c_l][k]          (pAt_mul_B!,    src/sparse.jl:6-21)
 //     g[c_l][k] += sum_r V[r][l] / p[r][k]       (pAt_mulinv_B!, src/sparse.jl:25-40)
-// both accumulated in Float64 (FP64 tensor-core MMA m8n8k4, DMMA).  A class is cut into blocks of 32 rows and tasks of
-// <= nbt(L) blocks; one warp = one task at a time, streamed by one bulk copy:
-//     EcHdr | cols u32[Lp] | dest u32[Lp] | V f32[nb][Lp/4][4][32]          (Lp = L rounded up to 4)
-// V is stored in MMA fragment order: chunk (lc, mt) = columns 4lc..4lc+3 x rows 8mt..8mt+7 of the block, element
-// (row, l) at ((row % 8) * 4 + l % 4) ^ ((lc & 1) << 4) -- one conflict-free 128-byte shared-memory read per MMA in
-// both passes.  dest[l] = slot of the task's Float64 partial for column l in a partial array ordered by column; a
-// second small launch adds each column's partials in a fixed order (no atomics).  Classes with fewer than EC_MIN_ROWS
-// rows or rows longer than EC_MAX_L go to the general layouts below ("rest" rows).
+// A class is cut into blocks of 32 lanes = 32 / q rows x q column slices of LH = ceil(L / q) <= 8 columns (q = 1, 2, 4,
+// 8 for L <= 8, 16, 32, 64), and into tasks of <= nbt(L) blocks; one warp = one task at a time, streamed by one bulk copy:
+//     EcHdr | cols u32[q LH] | dest u32[q LH] | pad to 16 | V f32[nb][LH][32]
+// V element (block b, column j of the slice, lane) = value of row b * (32 / q) + lane / q, column (lane % q) * LH + j
+// (0 where that column is padding): lane-major, so a warp reads a block's column j with one conflict-free 128-byte
+// shared-memory read and nothing is padded when L <= 8.  dest[l] = slot of the task's partial for column l in a partial
+// array ordered by column; a second small launch adds each column's partials in a fixed order (no atomics).  Classes
+// with fewer than EC_MIN_ROWS rows (when that policy is on) or rows longer than EC_MAX_L go to the general layouts
+// below ("rest" rows).
 constexpr uint32_t EC_MAX_L = 64;
 constexpr uint32_t EC_MIN_ROWS_DEFAULT = 12;
-constexpr uint32_t EC_V_BYTES = 8192;       // V bytes per task (<= one shared-memory stage)
+#ifndef POLEE_EC_V_BYTES
+#define POLEE_EC_V_BYTES 8192
+#endif
+constexpr uint32_t EC_V_BYTES = POLEE_EC_V_BYTES;   // V bytes per task (<= one shared-memory stage)
+constexpr uint32_t EC_MAX_NBT = 32;         // blocks per task (bounds the Float32 chains of the f32 arithmetic)
 constexpr uint32_t EC_STAGE_BYTES = 16 + 2 * 4 * EC_MAX_L + EC_V_BYTES;   // 8720
-__host__ __device__ inline uint32_t ec_lp(uint32_t L) { return (L + 3u) & ~3u; }
+__host__ __device__ inline uint32_t ec_q(uint32_t L) { return L <= 8u ? 1u : (L <= 16u ? 2u : (L <= 32u ? 4u : 8u)); }
+__host__ __device__ inline uint32_t ec_lh(uint32_t L) { const uint32_t q = ec_q(L); return (L + q - 1u) / q; }
 __host__ __device__ inline uint32_t ec_nbt(uint32_t L) {   // blocks per task
-    const uint32_t v = EC_V_BYTES / (ec_lp(L) * 128u);
-    return v < 1u ? 1u : (v > 16u ? 16u : v);
+    const uint32_t v = EC_V_BYTES / (ec_lh(L) * 128u);
+    return v < 1u ? 1u : (v > EC_MAX_NBT ? EC_MAX_NBT : v);
 }
-__host__ __device__ inline uint32_t ec_hdr_bytes(uint32_t L) { return 16u + 8u * ec_lp(L); }
-__host__ __device__ inline uint32_t ec_task_bytes(uint32_t L, uint32_t nb) { return ec_hdr_bytes(L) + nb * ec_lp(L) * 128u; }
+__host__ __device__ inline uint32_t ec_hdr_bytes(uint32_t L) { return (16u + 8u * ec_q(L) * ec_lh(L) + 15u) & ~15u; }
+__host__ __device__ inline uint32_t ec_task_bytes(uint32_t L, uint32_t nb) { return ec_hdr_bytes(L) + nb * ec_lh(L) * 128u; }
+#ifndef POLEE_EC_DEFAULT_F32
+#define POLEE_EC_DEFAULT_F32 false
+#endif
 struct EcHdr {
-    uint32_t L, nb, rows, slot0;  // columns, blocks, valid rows of the task, first row slot (row_of_slot / weights)
+    uint32_t pk, nb, rows, slot0;  // L | LH << 8 | q << 16 | log2(q) << 24; blocks; valid rows; first row slot (row_of_slot / weights)
 };
+__host__ __device__ inline uint32_t ec_pack(uint32_t L) {
+    const uint32_t q = ec_q(L), lq = q == 1u ? 0u : (q == 2u ? 1u : (q == 4u ? 2u : 3u));
+    return L | (ec_lh(L) << 8) | (q << 16) | (lq << 24);
+}
+__host__ __device__ inline uint32_t ec_pk_l(uint32_t pk) { return pk & 0xFFu; }
+__host__ __device__ inline uint32_t ec_pk_lh(uint32_t pk) { return (pk >> 8) & 0xFFu; }
+__host__ __device__ inline uint32_t ec_pk_q(uint32_t pk) { return (pk >> 16) & 0xFFu; }
+__host__ __device__ inline uint32_t ec_pk_lq(uint32_t pk) { return pk >> 24; }
 struct EcTaskDesc {
     uint64_t off;    // byte offset of the task blob
     uint32_t bytes;  // multiple of 16
@@ -296,6 +313,7 @@ struct polee_handle {
     double *ec_lvl2 = nullptr;          // [ec_nlvl2][KP]   (work buffer)
     double *ec_lp_partial = nullptr;    // [ec_tasks][KP]   (work buffer)
     int ec_grid = 0;
+    int ec_kind_end[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // tasks are ordered by LH, 8 first: end of each run
     int64_t gm = 0, gnnz = 0;           // rows / entries of the general ("rest") layouts; m, nnz are the whole matrix
     uint32_t *rest_row = nullptr;       // [gm] original row of every rest row (nullptr: rest = whole matrix)
 
@@ -431,7 +449,8 @@ int setup_ec_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t nnz,
 void release_ec(polee_handle *h);
 int ec_grid(polee_handle *h, int KP);
 // g (+)= X_ec^T (1 / X_ec x); add_to_g: the general layouts already wrote their share of g
-int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool want_lp, double *lp_out, float *w_out, int KP);
+int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool want_lp, double *lp_out, float *w_out, int KP, int K);
+bool ec_math_f32();  // POLEE_EC_MATH=f32|f64
 
 // fused_kernels.cu
 int fused_grid(polee_handle *h, int KP);

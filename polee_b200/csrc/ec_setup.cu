@@ -8,7 +8,7 @@
 //   2. a 64-bit hash of every row's transcript-id list, a stable sort of the rows by hash, an exact comparison of
 //      neighbours (a collision can only split a class, never merge two) -> classes; classes ordered by first row;
 //   3. classes with >= EC_MIN_ROWS rows and 1..EC_MAX_L transcripts are cut into blocks of 32 rows and tasks of
-//      <= ec_nbt(L) blocks; one blob per task (header, column ids, partial slots, values in MMA fragment order);
+//      <= ec_nbt(L) blocks; one blob per task (header, column ids, partial slots, values lane-major);
 //   4. the (task, column) partials are ordered by column (stable radix sort) -> `dest` slots + the second-stage list;
 //   5. every other row ("rest") is emitted as a compact CSC of its own for the general layouts (matrix_setup.cu).
 #include <algorithm>
@@ -126,10 +126,11 @@ __global__ void k_ec_class_meta(uint32_t n_classes, const uint32_t *__restrict__
         uint32_t nb = 0, nt = 0;
         uint64_t bytes = 0;
         if (dense) {
-            nb = (R + 31u) / 32u;
+            const uint32_t rpb = 32u / ec_q(L);  // rows per block
+            nb = (R + rpb - 1u) / rpb;
             const uint32_t nbt = ec_nbt(L);
             nt = (nb + nbt - 1u) / nbt;
-            bytes = (uint64_t)nt * ec_hdr_bytes(L) + (uint64_t)nb * ec_lp(L) * 128ull;
+            bytes = (uint64_t)nt * ec_hdr_bytes(L) + (uint64_t)nb * ec_lh(L) * 128ull;
         }
         cls_nt[c] = nt; cls_nb[c] = nb; cls_bytes[c] = bytes; cls_parts[c] = nt * L;
         cls_rows[c] = dense ? R : 0u;
@@ -159,13 +160,14 @@ __global__ void k_ec_task_init(uint32_t n_tasks, uint32_t n_classes, const uint3
         const uint64_t off = byte0[c] + (uint64_t)j * ec_task_bytes(L, nbt);
         desc[t] = EcTaskDesc{off, ec_task_bytes(L, nb), 0u};
         EcHdr hd;
-        hd.L = L; hd.nb = nb;
-        hd.rows = min(nb * 32u, cls_rows[c] - j * nbt * 32u);
+        hd.pk = ec_pack(L); hd.nb = nb;
+        const uint32_t rpb = 32u / ec_q(L);
+        hd.rows = min(nb * rpb, cls_rows[c] - j * nbt * rpb);
         hd.slot0 = (blk0[c] + j * nbt) * 32u;
         unsigned char *b = blob + off;
         *reinterpret_cast<EcHdr *>(b) = hd;
         uint32_t *cols = reinterpret_cast<uint32_t *>(b + 16);
-        const uint32_t q0 = row_ptr[leader_s[c]], Lp = ec_lp(L);
+        const uint32_t q0 = row_ptr[leader_s[c]], Lp = ec_q(L) * ec_lh(L);
         for (uint32_t l = 0; l < Lp; ++l) {
             const uint32_t col = l < L ? col_csr[q0 + l] : 0u;  // padding columns point at column 0 (their values are 0)
             cols[l] = col;
@@ -183,8 +185,19 @@ __global__ void k_ec_dest(uint32_t n_parts, const uint32_t *__restrict__ plist, 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_parts; i += gridDim.x * blockDim.x) {
         const uint32_t pid = plist[i], t = part_task[pid];
         unsigned char *b = blob + desc[t].off;
-        const uint32_t L = reinterpret_cast<const EcHdr *>(b)->L;
-        reinterpret_cast<uint32_t *>(b + 16 + 4 * ec_lp(L))[pid - task_part0[t]] = i;
+        const uint32_t L = ec_pk_l(reinterpret_cast<const EcHdr *>(b)->pk);
+        reinterpret_cast<uint32_t *>(b + 16 + 4 * ec_q(L) * ec_lh(L))[pid - task_part0[t]] = i;
+    }
+}
+
+// processing order of the tasks: by (LH, q) descending, so that the warps of an SM run the same instantiation of the
+// kernel's block loop at the same time (its eight instantiations do not fit the instruction cache together) and the
+// most expensive tasks come first.  Only the descriptors move; blobs, partial slots and results do not depend on it.
+__global__ void k_ec_task_key(uint32_t n_tasks, const EcTaskDesc *__restrict__ desc, const unsigned char *__restrict__ blob,
+                              uint32_t *key) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tasks; t += gridDim.x * blockDim.x) {
+        const uint32_t pk = reinterpret_cast<const EcHdr *>(blob + desc[t].off)->pk;
+        key[t] = 31u - ((ec_pk_lh(pk) - 1u) * 4u + ec_pk_lq(pk));
     }
 }
 
@@ -210,7 +223,8 @@ __global__ void k_ec_rows(int64_t m, const uint32_t *__restrict__ row_s, const u
             slot_of_row[i] = 0xFFFFFFFFu;
         } else {
             rest_flag[i] = 0u;
-            const uint32_t slot = blk0[c] * 32u + ((uint32_t)p - cstart[g]);
+            const uint32_t rpb = 32u / ec_q(cls_L[c]), rc = (uint32_t)p - cstart[g];  // row of the class
+            const uint32_t slot = (blk0[c] + rc / rpb) * 32u + rc % rpb;
             slot_of_row[i] = slot;
             row_of_slot[slot] = i;
             if (slot_weight) slot_weight[slot] = (float)ks[i];
@@ -218,7 +232,7 @@ __global__ void k_ec_rows(int64_t m, const uint32_t *__restrict__ row_s, const u
     }
 }
 
-// one thread per CSR position: the value goes to its place in the task blob (MMA fragment order, see common.cuh)
+// one thread per CSR position: the value goes to its place in the task blob (lane-major, see common.cuh)
 __global__ void k_ec_fill(int64_t nnz, const uint32_t *__restrict__ row_sorted, const uint32_t *__restrict__ a_csc,
                           const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ slot_of_row,
                           const uint32_t *__restrict__ rpos, const uint32_t *__restrict__ gid_incl,
@@ -230,14 +244,13 @@ __global__ void k_ec_fill(int64_t nnz, const uint32_t *__restrict__ row_sorted, 
         const uint32_t slot = slot_of_row[i];
         if (slot == 0xFFFFFFFFu) continue;
         const uint32_t c = order_of_class[gid_incl[rpos[i]] - 1u];
-        const uint32_t L = cls_L[c], Lp = ec_lp(L), nbt = ec_nbt(L);
-        const uint32_t blk = slot / 32u - blk0[c], row = slot & 31u;
+        const uint32_t L = cls_L[c], qq = ec_q(L), LH = ec_lh(L), nbt = ec_nbt(L);
+        const uint32_t blk = slot / 32u - blk0[c], row = slot & 31u;  // row of the block, < 32 / qq
         const uint32_t j = blk / nbt, b = blk % nbt;
         const uint32_t l = (uint32_t)q - row_ptr[i];
-        const uint32_t lc = l >> 2, mt = row >> 3;
-        const uint32_t pos = (((row & 7u) << 2) | (l & 3u)) ^ ((lc & 1u) << 4);
+        const uint32_t hs = l / LH, jl = l - hs * LH, lane = row * qq + hs;
         const uint64_t off = byte0[c] + (uint64_t)j * ec_task_bytes(L, nbt) + ec_hdr_bytes(L) +
-                             4ull * ((uint64_t)b * Lp * 32u + (lc * 4u + mt) * 32u + pos);
+                             4ull * (((uint64_t)b * LH + jl) * 32u + lane);
         *reinterpret_cast<float *>(blob + off) = nzval[a_csc[q]];
     }
 }
@@ -480,6 +493,34 @@ int setup_ec_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t nnz,
     k_ec_dest<<<grid_for(n_parts), TPB, 0, st>>>(n_parts, plist, part_task, task_part0, h->ec_desc, h->ec_blob);
     std::vector<uint32_t> cnt(n);
     CK(cudaMemcpyAsync(cnt.data(), col_cnt, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    {   // processing order (see k_ec_task_key); stable, so tasks of one kind keep the matrix order
+        uint32_t *tkey, *tkey_s;
+        EcTaskDesc *desc_sorted = nullptr;
+        CK(sc.alloc(&tkey, n_tasks)); CK(sc.alloc(&tkey_s, n_tasks));
+        CK(polee::dmalloc((void **)&desc_sorted, sizeof(EcTaskDesc) * n_tasks));
+        k_ec_task_key<<<grid_for(n_tasks), TPB, 0, st>>>(n_tasks, h->ec_desc, h->ec_blob, tkey);
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, tkey, tkey_s, h->ec_desc, desc_sorted, (int)n_tasks, 0, 5, st);
+        if (e == cudaSuccess) e = ensure_tmp(need);
+        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(d_tmp, need, tkey, tkey_s, h->ec_desc, desc_sorted, (int)n_tasks, 0, 5, st);
+        if (e != cudaSuccess) {
+            polee::dfree(desc_sorted);
+            CK(e);
+        }
+        uint32_t *kcnt;
+        CK(sc.alloc(&kcnt, 32));
+        CK(cudaMemsetAsync(kcnt, 0, sizeof(uint32_t) * 32, st));
+        k_ec_count_keys<<<grid_for(n_tasks), TPB, 0, st>>>(tkey, n_tasks, kcnt);
+        uint32_t hk[32];
+        CK(cudaMemcpyAsync(hk, kcnt, sizeof(hk), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        polee::dfree(h->ec_desc);
+        h->ec_desc = desc_sorted;
+        int run_end = 0;
+        for (int lh = 8; lh >= 1; --lh) {  // key = 31 - ((LH - 1) * 4 + lq)
+            for (int lq = 0; lq < 4; ++lq) run_end += (int)hk[31 - ((lh - 1) * 4 + lq)];
+            h->ec_kind_end[8 - lh] = run_end;
+        }
+    }
 
     // ---- 5. the rest rows
     CK(cub::DeviceScan::ExclusiveSum(nullptr, need, rest_flag, rest_id, (int)(m + 1), st));
