@@ -52,11 +52,16 @@ typedef struct polee_opts {
     int32_t device;              /* CUDA device ordinal */
     int32_t approx;              /* POLEE_APPROX_* */
     int32_t num_steps;           /* LIKAP_NUM_STEPS = 500 */
-    int32_t num_mc_samples;      /* LIKAP_NUM_MC_SAMPLES = 6 (K); 1..32 */
+    int32_t num_mc_samples;      /* LIKAP_NUM_MC_SAMPLES = 6 (K); 1..16 */
     int32_t gradonly;            /* Val(gradonly) = true: skip log-likelihood / ELBO values */
     int32_t use_efflen_jacobian; /* true */
     int32_t noise_mode;          /* POLEE_NOISE_* */
-    int32_t exact_accumulation;  /* 0 (default): fast mixed f32/f64 sparse kernels; 1: reference-order all-f64 sums */
+    int32_t exact_accumulation;  /* arithmetic of the two sparse products (src/sparse.jl:6-40):
+                                  * 0 (default): class layout, Float32 FMAs inside a task (a row's <= 64 terms; <= 32
+                                  *    rows per lane + a 5-level lane tree per column), Float64 across tasks;
+                                  * 1: general layouts, Float32 products summed in Float64 in the reference's order
+                                  *    (frag_probs bit-identical to the reference);
+                                  * 2: class layout, every product and sum in Float64 */
     uint64_t seed;               /* Random.seed! default 123456789, main.jl:123-127 */
     double max_step_mu;          /* ss_max_mu_step    = 2e-1, likelihood-approximation.jl:421 */
     double max_step_omega;       /* ss_max_omega_step = 2e-1 */

@@ -120,9 +120,6 @@ __host__ __device__ inline uint32_t ec_nbt(uint32_t L) {   // blocks per task
 }
 __host__ __device__ inline uint32_t ec_hdr_bytes(uint32_t L) { return (16u + 8u * ec_q(L) * ec_lh(L) + 15u) & ~15u; }
 __host__ __device__ inline uint32_t ec_task_bytes(uint32_t L, uint32_t nb) { return ec_hdr_bytes(L) + nb * ec_lh(L) * 128u; }
-#ifndef POLEE_EC_DEFAULT_F32
-#define POLEE_EC_DEFAULT_F32 false
-#endif
 struct EcHdr {
     uint32_t pk, nb, rows, slot0;  // L | LH << 8 | q << 16 | log2(q) << 24; blocks; valid rows; first row slot (row_of_slot / weights)
 };
@@ -450,7 +447,7 @@ void release_ec(polee_handle *h);
 int ec_grid(polee_handle *h, int KP);
 // g (+)= X_ec^T (1 / X_ec x); add_to_g: the general layouts already wrote their share of g
 int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool want_lp, double *lp_out, float *w_out, int KP, int K);
-bool ec_math_f32();  // POLEE_EC_MATH=f32|f64
+bool ec_math_f32(const polee_handle *h);  // opts.exact_accumulation / POLEE_EC_MATH
 
 // fused_kernels.cu
 int fused_grid(polee_handle *h, int KP);

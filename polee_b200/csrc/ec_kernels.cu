@@ -74,12 +74,10 @@ __device__ __forceinline__ double ec_rcp<double>(double p) {
     const double e = fma(-p, r, 1.0);
     return fma(r, e, r);
 }
-// MUFU.RCP (1 ulp) + one Newton step
+// MUFU.RCP alone: 1 ulp, the same order as the Float32 rounding of the sums around it
 template <>
 __device__ __forceinline__ float ec_rcp<float>(float p) {
-    const float r = rcp_approx(p);
-    const float e = fmaf(-p, r, 1.0f);
-    return fmaf(r, e, r);
+    return rcp_approx(p);
 }
 
 // a[k] += s * b[k]
@@ -242,8 +240,8 @@ __device__ __forceinline__ void ec_xstore(T *__restrict__ xbuf, uint32_t idx, ui
     }
 }
 
-// UB rows of one lane at a time (UB blocks of the task): p, w = 1 / p, a += v w.
-template <typename T, int KD, int LH, int UB, bool FULL>
+// UB rows of one lane at a time (UB blocks of the task): p, w = 1 / p, a += v w.  CHECK: the rows may be padding.
+template <typename T, int KD, int LH, int UB, bool CHECK, bool FULL>
 __device__ __forceinline__ void ec_rows(const float *__restrict__ vb, const T *__restrict__ xs, uint32_t q, uint32_t row0,
                                         uint32_t nr, uint32_t rows, uint32_t slot, uint32_t h, int kb, const EcArgs &A,
                                         T (&acc)[LH][KD], double (&lpv)[KD]) {
@@ -286,7 +284,7 @@ __device__ __forceinline__ void ec_rows(const float *__restrict__ vb, const T *_
     }
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
-        const bool valid = row0 + u * nr < rows;
+        const bool valid = !CHECK || row0 + u * nr < rows;
         T w[KD];
 #pragma unroll
         for (int k = 0; k < KD; ++k) w[k] = valid ? ec_rcp<T>(p[u][k]) : (T)0;  // padding rows: p = 0, w = 0
@@ -448,14 +446,16 @@ __device__ __forceinline__ void ec_run(EcWarp &W, int end, unsigned char *__rest
             double lpv[KD];
 #pragma unroll
             for (int k = 0; k < KD; ++k) lpv[k] = 0.0;
+            const uint32_t nb_full = hd.rows >> (5u - lq);  // blocks without padding rows
             uint32_t b = 0;
 #pragma unroll 1
-            for (; b + UB <= hd.nb; b += UB)
-                ec_rows<T, KD, LH, UB, FULL>(V + b * (LH * 32u), xs, q, b * nr + rho, nr, hd.rows, hd.slot0 + b * 32u + rho, h, kb, A,
-                                             acc, lpv);
-            if (b < hd.nb)
-                ec_rows<T, KD, LH, 1, FULL>(V + b * (LH * 32u), xs, q, b * nr + rho, nr, hd.rows, hd.slot0 + b * 32u + rho, h, kb, A,
-                                            acc, lpv);
+            for (; b + UB <= nb_full; b += UB)
+                ec_rows<T, KD, LH, UB, false, FULL>(V + b * (LH * 32u), xs, q, b * nr + rho, nr, hd.rows, hd.slot0 + b * 32u + rho, h,
+                                                    kb, A, acc, lpv);
+#pragma unroll 1
+            for (; b < hd.nb; ++b)
+                ec_rows<T, KD, LH, 1, true, FULL>(V + b * (LH * 32u), xs, q, b * nr + rho, nr, hd.rows, hd.slot0 + b * 32u + rho, h,
+                                                  kb, A, acc, lpv);
             if (bt + 1 == nbatch && has_next) {
                 mbar_wait_u32(W.bar_u32 + s1 * 8u, (W.phase >> s1) & 1u);
                 W.xpre = ec_xload<KD>(mine + s1 * EC_STAGE_STRIDE, A, 0, (uint32_t)lane);
@@ -653,13 +653,14 @@ int launch_combine_kp(polee_handle *h, double *g, bool add_to_g, int KP) {
 
 }  // namespace
 
-// POLEE_EC_MATH=f32|f64 selects the arithmetic of the class kernel (see the header of this file); read once.
-bool ec_math_f32() {
-    static const bool f32 = [] {
+// The arithmetic of the class kernel (see the header of this file): Float32 runs by default, Float64 with
+// opts.exact_accumulation == 2; POLEE_EC_MATH=f32|f64 overrides both (experiments).
+bool ec_math_f32(const polee_handle *h) {
+    static const int env = [] {
         const char *e = getenv("POLEE_EC_MATH");
-        return e ? !strcmp(e, "f32") : POLEE_EC_DEFAULT_F32;
+        return !e ? -1 : (!strcmp(e, "f32") ? 1 : 0);
     }();
-    return f32;
+    return env >= 0 ? env == 1 : h->o.exact_accumulation != 2;
 }
 
 int ec_grid(polee_handle *h, int KP) {
@@ -676,7 +677,7 @@ int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool wa
     A.lp_partial = h->ec_lp_partial; A.w_out = w_out; A.KP = KP;
     A.flags = (want_lp ? EC_FLAG_LP : 0u) | (w_out ? EC_FLAG_WRITE_W : 0u);
     if (K < 1 || K > KP) K = KP;
-    const bool f32 = ec_math_f32();
+    const bool f32 = ec_math_f32(h);
     int rc = f32 ? launch_lik_kd<float>(h, A, K) : launch_lik_kd<double>(h, A, K);
     if (rc) return rc;
     rc = f32 ? launch_combine_kp<float>(h, g, add_to_g, KP) : launch_combine_kp<double>(h, g, add_to_g, KP);

@@ -911,7 +911,7 @@ int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const ui
     // "fused" (row tiles, one pass, Float32 inside a tile) where the row order has the locality it needs, else
     // "split" (SELL slabs for K1 + re-sorted CSC for K2, two passes, w through HBM).
     const char *lay = getenv("POLEE_LAYOUT");
-    const bool want_ec = !h->o.exact_accumulation && !(lay && (std::string(lay) == "split" || std::string(lay) == "fused"));
+    const bool want_ec = h->o.exact_accumulation != 1 && !(lay && (std::string(lay) == "split" || std::string(lay) == "fused"));
     uint32_t *d_colptr_own = nullptr;
     struct Own {
         uint32_t *&p;

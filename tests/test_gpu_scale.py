@@ -1,5 +1,6 @@
 """GPU tests at BASELINE.json sizes: the likelihood and its gradient against the oracle, elementwise, for every device
-layout (equivalence classes = the default, fused row tiles, split, exact accumulation), plus size-independent
+layout and arithmetic (equivalence classes in Float32 = the default and in Float64, fused row tiles, split,
+reference-order accumulation), plus size-independent
 properties: identity sum_j x_j g_j = m, determinism, agreement between K-batched and one-at-a-time evaluation."""
 import numpy as np
 import pytest
@@ -16,14 +17,16 @@ def _device_sample(m, n, seed, **kw):
     return s, colptr, rowval
 
 
-LAYOUTS = {"ec": {}, "fused": {"POLEE_LAYOUT": "fused"}, "split": {"POLEE_LAYOUT": "split"}, "exact": {}}
+LAYOUTS = {"ec": {}, "ec64": {}, "fused": {"POLEE_LAYOUT": "fused"}, "split": {"POLEE_LAYOUT": "split"}, "exact": {}}
+EXACT_MODE = {"exact": 1, "ec64": 2}   # opts.exact_accumulation (include/polee_b200.h)
 
 
 def _layout_handle(pb, layout, monkeypatch, K, m, n, colptr, rowval, nzval):
     monkeypatch.delenv("POLEE_LAYOUT", raising=False)
+    monkeypatch.delenv("POLEE_EC_MATH", raising=False)
     for k, v in LAYOUTS[layout].items():
         monkeypatch.setenv(k, v)
-    h = pb.Handle(num_mc_samples=K, num_steps=3, exact_accumulation=(layout == "exact"))
+    h = pb.Handle(num_mc_samples=K, num_steps=3, exact_accumulation=EXACT_MODE.get(layout, 0))
     h.set_matrix_device(m, n, colptr.data_ptr(), rowval.data_ptr(), nzval.data_ptr())
     return h
 
@@ -80,11 +83,11 @@ def test_config3_vs_oracle_all_layouts(oracle, c3_sample, monkeypatch):
     M = oracle.Model(m, n, ns["colptr"], ns["rowval"], ns["nzval"])
     ref = {k: M.log_likelihood(xs[k], gradonly=False) for k in (0, 5)}
     got = {}
-    for layout in ("ec", "fused", "split", "exact"):
+    for layout in ("ec", "ec64", "fused", "split", "exact"):
         h = _layout_handle(pb, layout, monkeypatch, K, m, n, colptr, rowval, s["nzval"])
         h.set_tree(*tree)
         info = h.layout_info()
-        if layout == "ec":
+        if layout in ("ec", "ec64"):
             assert info["ec_rows"] > 0.9 * m, info             # the class layout takes nearly every row of C3
         else:
             assert info["ec_rows"] == 0 and info["general_kind"] == ("fused" if layout == "fused" else "split"), info
@@ -97,7 +100,8 @@ def test_config3_vs_oracle_all_layouts(oracle, c3_sample, monkeypatch):
             err = float(np.max(np.abs(g[k][nz] - g_o[nz]) / g_o[nz]))
             assert err <= 1e-5, (layout, k, err)
         got[layout] = g
-    assert np.max(np.abs(got["ec"] - got["exact"]) / np.maximum(got["exact"], 1e-300)) <= 1e-6
+    assert np.max(np.abs(got["ec"] - got["exact"]) / np.maximum(got["exact"], 1e-300)) <= 2e-6
+    assert np.max(np.abs(got["ec64"] - got["exact"]) / np.maximum(got["exact"], 1e-300)) <= 2e-7
 
 
 def test_config3_shape_properties(c3_sample):
@@ -160,7 +164,7 @@ def test_config4_shape_long_rows_vs_oracle(oracle, monkeypatch):
     xs = np.random.default_rng(0).dirichlet(np.ones(n), K).astype(np.float32).clip(1e-10)
     M = oracle.Model(m, n, ns["colptr"], ns["rowval"], ns["nzval"])
     ref = {k: M.log_likelihood(xs[k], gradonly=False) for k in (2,)}
-    for layout in ("ec", "split", "exact"):
+    for layout in ("ec", "ec64", "split", "exact"):
         h = _layout_handle(pb, layout, monkeypatch, K, m, n, colptr, rowval, s["nzval"])
         h.set_tree(*tree)
         lp, g = h.loglik_grad(xs, gradonly=False)
