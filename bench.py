@@ -14,7 +14,11 @@ value   : steady-state evals/s with the matrix resident in HBM (CUDA events on t
 e2e     : the same metric through the public API with HOST buffers: one whole approximate_likelihood call
           (upload of the CSC arrays from pinned host memory, device-side layout conversion, 500 ADAM steps,
           download of mu/omega/alpha), evals / wall seconds
-roofline: dominant sparse kernel, algorithmic bytes (SURVEY 8d formula) / CUDA-event time vs the measured HBM peak
+roofline: dominant kernel (the one-pass class kernel k_ec_lik on the default layout): algorithmic bytes (SURVEY 8d
+          formula: B_K1 + B_K2, what the reference's two passes stream) / CUDA-event time vs the measured HBM peak,
+          AND the bytes the kernel really moves (`moved_gbs`, `frac_moved`: the layout stores each value once, no
+          indices per entry, so it moves ~6x fewer bytes than the formula charges; `frac` can therefore exceed 1)
+parity  : (N = 1) lp and x_grad of one draw on the bench matrix, device vs oracle (the checker, never measured)
 cpu_baseline: the oracle (C restatement of the reference's multithreaded Julia loops) on the host cores
 """
 import argparse
@@ -37,6 +41,15 @@ CONFIGS = {
     "c3-small": (3_000_000, 200_000, 8, False, 20260003),
 }
 FIT_STEPS = 500  # LIKAP_NUM_STEPS (src/constants.jl:64): what one approximate_likelihood call runs
+
+
+DTYPE = ("f32 products and in-task sums (<= 64 terms per row, <= 32 rows per lane + 5-level lane tree per column), f64 across "
+         "tasks, f64 tree / ADAM arithmetic on f32 state")
+
+
+def workload(cfg, m, n, nnz, K):
+    """config.workload: the same string in both arms."""
+    return "%s: %d fragments x %d transcripts, nnz %d, K=%d draws/step, balanced-by-gene tree" % (cfg, m, n, nnz, K)
 
 
 def measured_peak():
@@ -200,6 +213,20 @@ def run_ours(args):
         else:
             host = {"colptr": pin(colptr_d, torch.int32).view(np.uint32), "rowval": pin(rowval_d, torch.int32).view(np.uint32),
                     "nzval": pin(nzval_d, torch.float32)}
+    # N > 1: rank 0 also fits the WHOLE matrix for 3 steps on its own (same seed => same device noise), the reference
+    # point of `multi_rank_parity`
+    full_params = None
+    if world > 1 and rank == 0:
+        hf = pb.Handle(device=local, num_mc_samples=K, num_steps=3, seed=args.seed)
+        hf.set_matrix_device(m, n, s["colptr"].to(torch.int32).data_ptr(), s["rowval"].to(torch.int32).data_ptr(),
+                             s["nzval"].data_ptr())
+        hf.set_efflens(efflens)
+        hf.set_tree(*tree)
+        hf.init_params()
+        hf.run_steps(3)
+        hf.sync()
+        full_params = np.concatenate(hf.get_params()).astype(np.float64)
+        hf.close()
     del s
     torch.cuda.empty_cache()
 
@@ -214,6 +241,21 @@ def run_ours(args):
         dist.broadcast_object_list(uid, src=0)
         h.comm_init(world, rank, uid[0])
     stats = h.step_stats()
+    multi = None
+    if world > 1:   # correctness of the row-partitioned fit, carried by the same line as its speed
+        h.init_params()
+        h.run_steps(3)
+        h.sync()
+        vec = torch.tensor(np.concatenate(h.get_params()).astype(np.float64), device=dev)
+        vmax, vmin = vec.clone(), vec.clone()
+        dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(vmin, op=dist.ReduceOp.MIN)
+        multi = {"steps": 3, "identical_across_ranks": bool((vmax == vmin).all().item())}
+        if rank == 0:
+            multi["max_abs_param_diff_vs_single_rank"] = float(np.max(np.abs(vec.cpu().numpy() - full_params)))
+            multi["what"] = ("mu/omega/alpha after 3 ADAM steps (device noise, same seed): row-partitioned over %d ranks vs "
+                             "the whole matrix on rank 0 alone; the ranks differ from the single-rank fit only by the "
+                             "summation order of the all-reduced gradient" % world)
 
     stream = torch.cuda.ExternalStream(h.stream(), device=dev)
 
@@ -247,6 +289,7 @@ def run_ours(args):
 
     # ---- per-kernel durations (CUDA events on the handle's stream, back-to-back launches; inputs >> L2)
     reps = max(5, min(50, args.steps))
+    info = h.layout_info()
     t_k1, t_k2, t_k3 = (h.time_kernel(w, reps) for w in (1, 2, 3))
     peak, peak_src = measured_peak()
     # algorithmic bytes of THIS rank's launches (SURVEY 8d formula, local nnz / rows, padded draw count KP)
@@ -255,36 +298,59 @@ def run_ours(args):
         KP *= 2
     b_k1 = nnz_loc * 8 + (m_loc + 1) * 4 + KP * n * 4 + KP * m_loc * 4
     b_k2 = nnz_loc * 8 + (n + 1) * 4 + KP * m_loc * 4 + KP * n * 4
-    fused = stats["bytes_k2"] == 0      # this rank's block uses the fused row-tile layout (one sparse pass per step)
-    if fused:
-        # ONE launch does the work of K1 and K2, so its algorithmic bytes are SURVEY 8(d)'s B_K1 + B_K2 (matrix twice +
-        # the w round trip); what it really moves is far less (`traffic`, `moved_gbs`: w never leaves the SM) -- it is
-        # bound by the shared-memory pipe and the CTA barriers, not by HBM (profiles/README.md)
-        b_f = stats["bytes_k1"]
-        achieved = (b_k1 + b_k2) / (t_k1 * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k12_fused_rowtiles", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    onepass = stats["bytes_k2"] == 0    # one sparse pass per step: the class layout (default) or fused row tiles
+    step_ms = ms / args.steps
+    if onepass:
+        # ONE launch does the work of the reference's two passes, so its algorithmic bytes are SURVEY 8(d)'s
+        # B_K1 + B_K2 (indices + values twice + the w round trip); what it really moves is far less (`moved_gbs`,
+        # `traffic`): values once, no per-entry indices, w never leaves the registers.
+        if info["ec_rows"] > 0:
+            kname, layout = "k_ec_lik", "equivalence classes (dense per-class blocks, one sparse pass per step)"
+            t_dom = h.time_kernel(4, reps)
+            share = float(info["ec_nnz"]) / max(1, nnz_loc)
+            if info["general_rows"] > 0:
+                layout += " + %s layout for %d rest rows" % (info["general_kind"], info["general_rows"])
+        else:
+            kname, layout, t_dom, share = "k12_fused_rowtiles", "fused row tiles (one sparse pass per step)", t_k1, 1.0
+        achieved = share * (b_k1 + b_k2) / (t_dom * 1e-3) / 1e9
+        moved = stats["bytes_k1"] / t_k1 / 1e6
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                    "note": "achieved = algorithmic bytes of K1 + K2 (SURVEY 8d) / time of the one fused pass incl. its "
-                            "second stage; moved_gbs = bytes the pass actually streams / same time",
-                    "kernels_ms": {"k12_fused_rowtiles": round(t_k1, 4), "k3_tree_reparam_adam": round(t_k3, 4)},
-                    "kernels_gbs": {"k12_fused_rowtiles": round(achieved, 1)},
-                    "moved_gbs": round(b_f / t_k1 / 1e6, 1),
-                    "step_gbs": round((b_k1 + b_k2 + stats["bytes_k3"]) / (ms / args.steps) / 1e6, 1)}
-        dom = ("k12_fused_rowtiles", b_f, t_k1)
+                    "note": "achieved = algorithmic bytes of K1 + K2 (SURVEY 8d; the kernel does both) / its average launch "
+                            "time; moved_gbs = bytes the whole likelihood pass really streams / its time (frac_moved = "
+                            "that / peak)",
+                    "kernels_ms": {kname: round(t_dom, 4), "likelihood_pass_incl_second_stage": round(t_k1, 4),
+                                   "k3_tree_reparam_adam": round(t_k3, 4)},
+                    "kernels_gbs": {kname: round(achieved, 1)},
+                    "moved_gbs": round(moved, 1), "frac_moved": round(moved / peak, 4),
+                    "step_gbs": round((b_k1 + b_k2 + stats["bytes_k3"]) / step_ms / 1e6, 1),
+                    "share_of_step": round(t_dom / step_ms, 3)}
+        dom = (kname, stats["bytes_k1"], t_dom)
     else:
+        layout = "split (SELL slabs for K1 + re-sorted CSC for K2)"
         dom = ("k1_sell_fwd", b_k1, t_k1) if t_k1 >= t_k2 else ("k2_csc_grad", b_k2, t_k2)
         achieved = dom[1] / (dom[2] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                     "kernels_ms": {"k1_sell_fwd": round(t_k1, 4), "k2_csc_grad": round(t_k2, 4), "k3_tree_reparam_adam": round(t_k3, 4)},
                     "kernels_gbs": {"k1_sell_fwd": round(b_k1 / t_k1 / 1e6, 1), "k2_csc_grad": round(b_k2 / t_k2 / 1e6, 1)},
-                    "step_gbs": round((b_k1 + b_k2 + stats["bytes_k3"]) / (ms / args.steps) / 1e6, 1)}
+                    "step_gbs": round((b_k1 + b_k2 + stats["bytes_k3"]) / step_ms / 1e6, 1),
+                    "share_of_step": round(dom[2] / step_ms, 3)}
     tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.config)
-    if os.path.exists(tr) and world == 1:  # the capture is of the whole-sample launch
+    if os.path.exists(tr) and world == 1:  # dram bytes of one launch from a committed `ncu --set full` capture (static)
         try:
-            roofline["traffic"] = json.load(open(tr)).get(dom[0])
+            t = json.load(open(tr))
+            roofline["traffic"] = t.get(dom[0])
+            roofline["traffic_source"] = "static: %s" % t.get("source", "profiles/traffic_%s.json" % args.config)
         except Exception:
             pass
+
+    # ---- parity on the bench matrix (N = 1): one draw, device vs oracle -- the oracle is the checker here
+    parity = None
+    xs_par = lp_par = g_par = None
+    if host is not None and world == 1 and not args.no_cpu:
+        xs_par = np.random.default_rng(7).dirichlet(np.ones(n)).astype(np.float32).clip(1e-10)
+        lp_par, g_par = h.loglik_grad(xs_par, gradonly=False)
 
     # ---- e2e: one whole fit through the public API from HOST buffers
     e2e = None
@@ -292,27 +358,33 @@ def run_ours(args):
     if host is not None and world == 1:
         h.close()
         torch.cuda.empty_cache()
+        pbapi.trim_memory(local)           # cold device allocator: what a one-shot `polee prep-sample` process sees
         sample = pb.RNASeqSample(m, n, host["colptr"], host["rowval"], host["nzval"], efflens)
-        for rep in range(2):   # first call warms the CUDA context / allocator; the second is reported
+        t_fits = []
+        for rep in range(2):   # [0]: cold (no cached device memory), [1]: warm (`polee prep` over many samples)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             out = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), sample, tree_topology=tree, num_steps=FIT_STEPS,
                                             num_mc_samples=K, seed=args.seed, device=local)
-            t_fit = time.perf_counter() - t0
+            t_fits.append(time.perf_counter() - t0)
         assert np.all(np.isfinite(out["mu"]))
         h2d = host["colptr"].nbytes + host["rowval"].nbytes + host["nzval"].nbytes + efflens.nbytes + 2 * 4 * (2 * n - 1)
-        e2e = {"value": round(K * FIT_STEPS / t_fit, 1), "unit": "evals/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(3 * 4 * (n - 1)), "fit_time_s": round(t_fit, 4), "adam_steps_per_fit": FIT_STEPS,
+        e2e = {"value": round(K * FIT_STEPS / t_fits[0], 1), "unit": "evals/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(3 * 4 * (n - 1)), "fit_time_s": round(t_fits[0], 4),
+               "warm_value": round(K * FIT_STEPS / t_fits[1], 1), "warm_fit_time_s": round(t_fits[1], 4),
+               "adam_steps_per_fit": FIT_STEPS,
                "step": "one approximate_likelihood call: CSC upload from pinned host memory + device layout build + "
-                       "%d ADAM steps x %d draws + parameter download" % (FIT_STEPS, K)}
+                       "%d ADAM steps x %d draws + parameter download; value = the first call with an empty device-memory "
+                       "cache, warm_value = the next call (cached allocations, as in `polee prep` over many samples)"
+                       % (FIT_STEPS, K)}
         if not args.no_cpu:
-            cpu = cpu_baseline(m, n, K, host, efflens, tree, budget_s=args.cpu_budget)
+            cpu, parity = cpu_baseline(m, n, K, host, efflens, tree, budget_s=args.cpu_budget, check=(xs_par, lp_par, g_par))
     elif host is not None:
         # N > 1: every rank re-feeds its own row block from host memory into its (comm-initialised) handle and runs
         # the whole 500-step fit; wall time, max over ranks
         block = pb.RNASeqSample(m_loc, n, host["colptr"], host["rowval"], host["nzval"], efflens)
         h.opts.num_steps = FIT_STEPS
-        t_fit = None
+        t_fits = []
         for rep in range(2):
             barrier()
             t0 = time.perf_counter()
@@ -324,14 +396,17 @@ def run_ours(args):
             out = h.get_params()
             tt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_fit = float(tt.item())
+            t_fits.append(float(tt.item()))
         h2d = host["colptr"].nbytes + host["rowval"].nbytes + host["nzval"].nbytes + efflens.nbytes + 2 * 4 * (2 * n - 1)
         hb = torch.tensor([h2d], device=dev, dtype=torch.float64)
         dist.all_reduce(hb)
-        e2e = {"value": round(K * FIT_STEPS / t_fit, 1), "unit": "evals/s", "h2d_bytes_per_step": int(hb.item()),
-               "d2h_bytes_per_step": int(3 * 4 * (n - 1)), "fit_time_s": round(t_fit, 4), "adam_steps_per_fit": FIT_STEPS,
+        e2e = {"value": round(K * FIT_STEPS / t_fits[0], 1), "unit": "evals/s", "h2d_bytes_per_step": int(hb.item()),
+               "d2h_bytes_per_step": int(3 * 4 * (n - 1)), "fit_time_s": round(t_fits[0], 4),
+               "warm_value": round(K * FIT_STEPS / t_fits[1], 1), "warm_fit_time_s": round(t_fits[1], 4),
+               "adam_steps_per_fit": FIT_STEPS,
                "step": "every rank: its row block's CSC upload from pinned host memory + layout build + %d ADAM steps x %d "
-                       "draws (one all-reduce each) + parameter download; wall time, max over ranks" % (FIT_STEPS, K)}
+                       "draws (one all-reduce each) + parameter download; wall time, max over ranks; value = first call, "
+                       "warm_value = second" % (FIT_STEPS, K)}
         h.close()
     else:
         h.close()
@@ -339,18 +414,21 @@ def run_ours(args):
 
     if rank == 0:
         line = {"metric": "elbo_grad_evals_per_sec", "value": round(evals_per_s, 1), "unit": "evals/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 storage, f64 accumulate",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE,
                 "data": "synthetic (polee-synth-v1, seed %d)" % CONFIGS[args.config][4],
-                "config": {"workload": "%s: %d fragments x %d transcripts, nnz %d, K=%d draws/step, balanced-by-gene tree; "
-                                       "row-partitioned into %d equal-nnz block(s)" % (args.config, m, n, nnz_total, K, world),
-                           "l2": "inputs (%.1f GB/step streamed) are far larger than the 126 MB L2; no flush needed"
-                                 % ((stats["bytes_k1"] if fused else b_k1 + b_k2) / 1e9),
-                           "layout": "fused row tiles (one sparse pass per step)" if fused else "split (SELL slabs for K1 + re-sorted CSC for K2)",
-                           "noise": "device Philox"},
+                "config": {"workload": workload(args.config, m, n, nnz_total, K)},
+                "details": {"partition": "rows in %d contiguous equal-nnz block(s), one per rank" % world,
+                            "l2": "inputs (%.2f GB/step streamed) are far larger than the 126 MB L2; no flush needed"
+                                  % (stats["bytes_k1"] / 1e9 if onepass else (b_k1 + b_k2) / 1e9),
+                            "layout": layout, "noise": "device Philox"},
                 "clocks": clocks, "gpu_launches": int(stats["launches"] * args.steps), "roofline": roofline}
+        if multi is not None:
+            line["multi_rank_parity"] = multi
         if e2e:
             line["e2e"] = e2e
+        if parity:
+            line["parity"] = parity
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -359,10 +437,22 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(m, n, K, host, efflens, tree, budget_s=25.0, warm=0):
+def cpu_baseline(m, n, K, host, efflens, tree, budget_s=25.0, warm=0, check=None):
     """The oracle (C/OpenMP restatement of the reference's Julia loops) on the host cores: whole ADAM steps of
-    K draws on the SAME matrix, as many as fit in the budget (at least one)."""
+    K draws on the SAME matrix, as many as fit in the budget (at least one).  With check = (xs, lp, x_grad) of one
+    device evaluation it also returns the parity block (device vs oracle on that draw)."""
     from oracle import polee_oracle as O
+    O.set_num_threads()   # all cores (the reference's wrapper policy, polee:8-12), whatever OMP_NUM_THREADS says
+    parity = None
+    if check is not None and check[0] is not None:
+        xs, lp_d, g_d = check
+        lp_o, g_o = O.Model(m, n, host["colptr"], host["rowval"], host["nzval"]).log_likelihood(xs, gradonly=False)
+        nz = g_o != 0
+        parity = {"lp_relerr": float(abs(lp_d[0] - lp_o) / abs(lp_o)),
+                  "x_grad_relerr": float(np.max(np.abs(g_d[0][nz] - g_o[nz]) / g_o[nz])),
+                  "zero_columns_equal": bool(np.array_equal(g_d[0][~nz], g_o[~nz])), "tolerance": 1e-5,
+                  "what": "one draw x ~ Dirichlet(1) on the bench matrix: device loglik_grad (default arithmetic) vs the "
+                          "oracle (Float32 products, Float64 sums in the reference's order); max over the non-empty columns"}
     st = O.FitStepper(m, n, host["colptr"], host["rowval"], host["nzval"], efflens, tree[0], tree[1], num_mc_samples=K)
     for _ in range(warm):
         st.step()
@@ -377,7 +467,7 @@ def cpu_baseline(m, n, K, host, efflens, tree, budget_s=25.0, warm=0):
     st.close()
     return {"value": round(K * steps / el, 3), "unit": "evals/s", "cores": O.num_threads(), "kind": "port",
             "sample": "%d full ADAM step(s) of %d draws on the same %d x %d matrix (setup/transposition excluded), "
-                      "%.1f s" % (steps, K, m, n, el)}
+                      "%.1f s" % (steps, K, m, n, el)}, parity
 
 
 def run_reference(args):
@@ -395,6 +485,7 @@ def run_reference(args):
     nnz = s["nnz"]
     del s
     from oracle import polee_oracle as O
+    cores = O.set_num_threads()   # all cores: torch.distributed.run exports OMP_NUM_THREADS=1
     st = O.FitStepper(m, n, ns["colptr"], ns["rowval"], ns["nzval"], ns["efflens"], tree[0], tree[1], num_mc_samples=K)
     budget = args.cpu_budget * 4
     t_w = time.perf_counter()
@@ -414,16 +505,16 @@ def run_reference(args):
     el = time.perf_counter() - t0
     st.close()
     v = round(K * steps / el, 3)
-    cores = O.num_threads()
     sample = "%d of the %d requested ADAM steps (x %d draws) on the full matrix within a %.0f s budget; %d warm-up" % (
         steps, args.steps, K, budget, done_w)
     print(json.dumps({
         "impl": "reference", "metric": "elbo_grad_evals_per_sec", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": done_w, "ms_per_step": round(el / steps * 1e3, 2), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32 storage, f64 accumulate", "data": "synthetic (polee-synth-v1, seed %d)" % seed,
-        "config": {"workload": "%s: %d fragments x %d transcripts, nnz %d, K=%d draws/step, balanced-by-gene tree" % (
-            args.config, m, n, nnz, K), "note": "CPU restatement of the reference's multithreaded Julia path "
-            "(oracle/polee_oracle.c, OpenMP static chunks = Threads.@threads); Julia itself is not available"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 products, f64 sums (the reference's arithmetic)",
+        "data": "synthetic (polee-synth-v1, seed %d)" % seed,
+        "config": {"workload": workload(args.config, m, n, nnz, K)},
+        "details": {"note": "CPU restatement of the reference's multithreaded Julia path (oracle/polee_oracle.c, OpenMP "
+                            "static chunks = Threads.@threads) on %d threads; Julia itself is not available" % cores},
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 

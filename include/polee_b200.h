@@ -143,7 +143,7 @@ int polee_step_stats(polee_handle *h, double *bytes_k1, double *bytes_k2, double
 int polee_layout_info(polee_handle *h, int64_t *info, int32_t count);
 /* time (ms, CUDA events on the handle's stream) of `reps` launches of one named kernel group:
  * which = 1 (the likelihood pass; K1 alone on the pure split layout), 2 (K2 of the pure split layout),
- * 3 (K3 tree+reparam+ADAM) */
+ * 3 (K3 tree+reparam+ADAM), 4 (the class kernel alone, without the second stage that adds its partials) */
 int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, float *ms_avg);
 
 /* Random.rand!(als::ApproxLikelihoodSampler, xs)  src/approx-sampler.jl:37-44 (used by `polee sample`,

@@ -893,7 +893,7 @@ extern "C" int polee_step_stats(polee_handle *h, double *b1, double *b2, double 
     const double gm = (double)h->gm, gnnz = (double)h->gnnz;
     double e1 = 0, e2 = 0;
     if (h->ec_tasks > 0)  // task blobs once + (task, column) partials written and read back + x gathers + g
-        e1 = (double)h->ec_blob_bytes + (double)h->ec_parts * (K * 8 * 2 + 4) + K * n * 4 + K * n * 8;
+        e1 = (double)h->ec_blob_bytes + (double)h->ec_parts * (K * (ec_math_f32(h) ? 4 : 8) * 2 + 4) + K * n * 4 + K * n * 8;
     if (h->gm > 0 || h->ec_tasks == 0) {
         if (h->fused) {
             e1 += (double)h->ft_blob_bytes + (double)h->ft_parts * (K * 4 * 2 + 4) + K * n * 8;
@@ -958,8 +958,10 @@ extern "C" int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, f
             if (!rc) rc = launch_mid(h, KP, 0);
             if (!rc) rc = launch_tree_bwd(h, KP, lsn, true, nullptr);
             if (!rc) rc = launch_elem(h, KP, K, true, false, true, noise, std::max<int64_t>(h->noise_steps, 1), 0, nullptr);
+        } else if (which == 4) {  // the class kernel alone (without the second stage that adds its partials)
+            if (h->ec_tasks > 0) rc = launch_ec(h, h->x, h->g, false, false, nullptr, nullptr, KP, K, true);
         } else {
-            rc = h->fail(POLEE_EINVAL, "time_kernel: which must be 1, 2 or 3");
+            rc = h->fail(POLEE_EINVAL, "time_kernel: which must be 1..4");
         }
     }
     CK(cudaEventRecord(e1, h->stream));

@@ -446,7 +446,8 @@ int setup_ec_from_device_csc(polee_handle *h, int64_t m, int64_t n, int64_t nnz,
 void release_ec(polee_handle *h);
 int ec_grid(polee_handle *h, int KP);
 // g (+)= X_ec^T (1 / X_ec x); add_to_g: the general layouts already wrote their share of g
-int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool want_lp, double *lp_out, float *w_out, int KP, int K);
+int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool want_lp, double *lp_out, float *w_out, int KP, int K,
+              bool lik_only = false);  // lik_only: the class kernel without its second stage (measurement)
 bool ec_math_f32(const polee_handle *h);  // opts.exact_accumulation / POLEE_EC_MATH
 
 // fused_kernels.cu

@@ -671,7 +671,8 @@ int ec_grid(polee_handle *h, int KP) {
 }
 
 // K = the draws asked for (<= KP, the draws the [item][KP] buffers carry)
-int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool want_lp, double *lp_out, float *w_out, int KP, int K) {
+int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool want_lp, double *lp_out, float *w_out, int KP, int K,
+              bool lik_only) {
     EcArgs A;
     A.xf = x; A.partial = h->ec_partial; A.slot_weight = h->ec_slot_weight; A.row_of_slot = h->ec_row_of_slot;
     A.lp_partial = h->ec_lp_partial; A.w_out = w_out; A.KP = KP;
@@ -679,7 +680,7 @@ int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool wa
     if (K < 1 || K > KP) K = KP;
     const bool f32 = ec_math_f32(h);
     int rc = f32 ? launch_lik_kd<float>(h, A, K) : launch_lik_kd<double>(h, A, K);
-    if (rc) return rc;
+    if (rc || lik_only) return rc;
     rc = f32 ? launch_combine_kp<float>(h, g, add_to_g, KP) : launch_combine_kp<double>(h, g, add_to_g, KP);
     if (rc) return rc;
     if (want_lp && lp_out) k_ec_reduce_lp<<<1, 1024, 0, h->stream>>>(h->ec_lp_partial, h->ec_tasks, KP, lp_out, add_to_g ? 1 : 0);
