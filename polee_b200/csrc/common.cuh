@@ -169,6 +169,11 @@ struct StepCtl {
     int step_upd;  // same, as seen by the update kernel (set by k3_mid)
 };
 
+constexpr int64_t PATH_MAX_ENTRIES = 64ll << 20;  // sum of node depths up to which root paths are built
+constexpr int PATH_GROUP = 128;                  // nodes per path group (one CTA)
+constexpr int PATH_SLOTS = 32;                   // node slots per CTA (threads = PATH_SLOTS x KP, PATH_GROUP / PATH_SLOTS nodes each)
+constexpr int PATH_MAX_GANC = 1024;              // distinct ancestors a group may have
+
 // Tree node, 0-based; leaf < 0 <=> internal node (then k = index among internal nodes in node order).
 struct TreeNode {
     int32_t left, right, k, leaf;
@@ -220,6 +225,14 @@ struct TreeHost {
     std::vector<int32_t> chain_leaf;  // [n]: leaf id hanging off spine node k (k < n-1), [n-1] = the last leaf
     int top_nodes = 0;
     int max_depth = 0;
+    // Root -> node paths for the path-product forward kernel, per group of PATH_GROUP consecutive nodes (neighbours in
+    // DFS order share most of their ancestors): the group's distinct ancestors `ganc` -- first the gcp[g] entries of the
+    // path prefix all its nodes share, root first, then the others -- as (k << 1 | 1 if the path continues into the
+    // LEFT child; only meaningful in the prefix), and per node the rest of its path `nsuf` as
+    // (index into the group's ganc list) << 1 | left.  Empty when the tree is too deep for it.
+    std::vector<uint32_t> ganc_ptr, ganc, gcp, nsuf_ptr;
+    std::vector<uint16_t> nsuf;
+    int max_ganc = 0, max_gsuf = 0;  // most distinct ancestors / suffix entries of a group
     // returns "" or an error text
     std::string build_from_lrf(int64_t n, const int32_t *left, const int32_t *right, const int32_t *leaf,
                                int bin_nodes);
@@ -237,6 +250,9 @@ struct TreeDev {
     bool caterpillar = false;
     int32_t *chain_leaf = nullptr;
     bool smem_path = false;  // shared-memory kernels usable (top part fits one CTA per draw)
+    uint32_t *ganc_ptr = nullptr, *ganc = nullptr, *gcp = nullptr, *nsuf_ptr = nullptr;  // root paths (nullptr: not built)
+    uint16_t *nsuf = nullptr;
+    int n_groups = 0, max_ganc = 0, max_gsuf = 0;
     void release();
 };
 

@@ -93,6 +93,71 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
     }
     for (int64_t i = N - 1; i >= 1; --i) size[parent[i]] += size[i];
 
+    // ---- root -> node paths, grouped (see TreeHost)
+    ganc_ptr.clear(); ganc.clear(); gcp.clear(); nsuf_ptr.clear(); nsuf.clear();
+    max_ganc = max_gsuf = 0;
+    {
+        int64_t total = 0;
+        for (int64_t i = 0; i < N; ++i) total += depth[i];
+        bool ok = total <= PATH_MAX_ENTRIES && n >= 2;
+        std::vector<uint32_t> path_ptr, path_ent;
+        if (ok) {
+            path_ptr.resize(N + 1);
+            path_ent.resize((size_t)total);
+            uint32_t pos = 0;
+            for (int64_t i = 0; i < N; ++i) {  // parents precede their children (checked above)
+                path_ptr[i] = pos;
+                if (i > 0) {
+                    const int32_t pa = parent[i];
+                    const uint32_t pb = path_ptr[pa], pl = (uint32_t)depth[pa];
+                    std::copy(path_ent.begin() + pb, path_ent.begin() + pb + pl, path_ent.begin() + pos);
+                    pos += pl;
+                    path_ent[pos++] = ((uint32_t)nodes[pa].k << 1) | (nodes[pa].left == (int32_t)i ? 1u : 0u);
+                }
+            }
+            path_ptr[N] = pos;
+            const int64_t ng = (N + PATH_GROUP - 1) / PATH_GROUP;
+            std::vector<int32_t> local_of_k((size_t)std::max<int64_t>(n - 1, 1), -1), stamp((size_t)std::max<int64_t>(n - 1, 1), -1);
+            ganc_ptr.reserve(ng + 1); gcp.reserve(ng); nsuf_ptr.reserve(N + 1);
+            for (int64_t g = 0; g < ng && ok; ++g) {
+                const int64_t i0 = g * PATH_GROUP, i1 = std::min<int64_t>(N, i0 + PATH_GROUP);
+                uint32_t cp = (uint32_t)depth[i0];  // longest common prefix of the group's paths
+                for (int64_t i = i0 + 1; i < i1; ++i) {
+                    const uint32_t len = std::min<uint32_t>(cp, (uint32_t)depth[i]);
+                    uint32_t c = 0;
+                    while (c < len && path_ent[path_ptr[i0] + c] == path_ent[path_ptr[i] + c]) ++c;
+                    cp = c;
+                }
+                ganc_ptr.push_back((uint32_t)ganc.size());
+                gcp.push_back(cp);
+                const size_t base = ganc.size(), sbase = nsuf.size();
+                for (uint32_t c = 0; c < cp; ++c) ganc.push_back(path_ent[path_ptr[i0] + c]);
+                for (int64_t i = i0; i < i1; ++i) {
+                    nsuf_ptr.push_back((uint32_t)nsuf.size());
+                    for (uint32_t c = cp; c < (uint32_t)depth[i]; ++c) {
+                        const uint32_t en = path_ent[path_ptr[i] + c], k = en >> 1;
+                        if (stamp[k] != (int32_t)g) {
+                            stamp[k] = (int32_t)g;
+                            local_of_k[k] = (int32_t)(ganc.size() - base);
+                            ganc.push_back(k << 1);
+                        }
+                        nsuf.push_back((uint16_t)(((uint32_t)local_of_k[k] << 1) | (en & 1u)));
+                    }
+                }
+                const int na = (int)(ganc.size() - base);
+                max_ganc = std::max(max_ganc, na);
+                max_gsuf = std::max(max_gsuf, (int)(nsuf.size() - sbase));
+                if (na > PATH_MAX_GANC || nsuf.size() - sbase > 16384) ok = false;
+            }
+            ganc_ptr.push_back((uint32_t)ganc.size());
+            nsuf_ptr.push_back((uint32_t)nsuf.size());
+        }
+        if (!ok) {
+            ganc_ptr.clear(); ganc.clear(); gcp.clear(); nsuf_ptr.clear(); nsuf.clear();
+            max_ganc = max_gsuf = 0;
+        }
+    }
+
     // ---- caterpillar ("list") tree?
     caterpillar = n >= 2;
     for (int64_t i = 0; i < N && caterpillar; ++i) {
@@ -275,6 +340,10 @@ void TreeDev::release() {
     polee::dfree(chain_leaf);
     chain_leaf = nullptr;
     caterpillar = false;
+    polee::dfree(ganc_ptr); polee::dfree(ganc); polee::dfree(gcp); polee::dfree(nsuf_ptr); polee::dfree(nsuf);
+    ganc_ptr = ganc = gcp = nsuf_ptr = nullptr;
+    nsuf = nullptr;
+    n_groups = max_ganc = max_gsuf = 0;
     for (SSchedDev *s : {&s_top, &s_bottom}) {
         polee::dfree(s->bin_off);
         polee::dfree(s->bin_lvl_ptr);
@@ -341,6 +410,21 @@ std::string upload_tree(const TreeHost &th, TreeDev &td) {
         dss[s]->nbins = hss[s]->nbins();
         dss[s]->max_bin_nodes = hss[s]->max_bin_nodes;
         dss[s]->max_bin_levels = hss[s]->max_bin_levels;
+    }
+    if (e == cudaSuccess && !th.ganc_ptr.empty()) {
+        auto upv = [&](const void *src, size_t bytes, void **dst) {
+            cudaError_t ee = polee::dmalloc(dst, std::max<size_t>(bytes, 4));
+            if (ee == cudaSuccess && bytes) ee = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+            return ee;
+        };
+        e = upv(th.ganc_ptr.data(), 4 * th.ganc_ptr.size(), (void **)&td.ganc_ptr);
+        if (e == cudaSuccess) e = upv(th.ganc.data(), 4 * th.ganc.size(), (void **)&td.ganc);
+        if (e == cudaSuccess) e = upv(th.gcp.data(), 4 * th.gcp.size(), (void **)&td.gcp);
+        if (e == cudaSuccess) e = upv(th.nsuf_ptr.data(), 4 * th.nsuf_ptr.size(), (void **)&td.nsuf_ptr);
+        if (e == cudaSuccess) e = upv(th.nsuf.data(), 2 * th.nsuf.size(), (void **)&td.nsuf);
+        td.n_groups = (int)th.gcp.size();
+        td.max_ganc = th.max_ganc;
+        td.max_gsuf = th.max_gsuf;
     }
     td.n_slots = th.n_slots;
     td.caterpillar = th.caterpillar;

@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
                  const int32_t *__restrict__ lvl_off, const SNode *__restrict__ recs, const double *__restrict__ ys,
                  const double *__restrict__ root_us, float2 *__restrict__ root_G, const double *__restrict__ g,
                  const float *__restrict__ efflen_adj, const double *__restrict__ S, double *__restrict__ ygrad,
-                 double *__restrict__ xgrad_out) {
+                 double *__restrict__ xgrad_out, const double *__restrict__ us_k) {
+    // us_k != nullptr: u of every internal node by k, as the path-product forward kernel left it (then nothing is
+    // recomputed here and root_us is not read)
     extern __shared__ __align__(16) unsigned char smraw[];
     const int q0 = bin_off[blockIdx.x], nb = bin_off[blockIdx.x + 1] - q0;
     SNode *rec_s = reinterpret_cast<SNode *>(smraw);
@@ -322,6 +324,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
             v0[u] = 0.0; uv[u] = 1.0; adj[u] = 0.0f; gx[u] = make_float2(0.f, 0.f);
             if (r[u].k_or_leaf >= 0) {
                 v0[u] = ys[(size_t)r[u].k_or_leaf * KP + k];
+                if (us_k) uv[u] = us_k[(size_t)r[u].k_or_leaf * KP + k];
             } else if (r[u].k_or_leaf == INT32_MIN) {
                 gx[u] = root_G[(size_t)r[u].slot * KP + k];
             } else if (r[u].k_or_leaf != INT32_MIN + 1) {
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 v0[u] = g[(size_t)leaf * KP + k];
                 if (efflen_adj) adj[u] = __int_as_float(r[u].right);
             }
-            if (r[u].slot >= 0 && r[u].k_or_leaf != INT32_MIN) uv[u] = root_us[(size_t)r[u].slot * KP + k];
+            if (!us_k && r[u].slot >= 0 && r[u].k_or_leaf != INT32_MIN) uv[u] = root_us[(size_t)r[u].slot * KP + k];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -346,13 +349,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 if (xgrad_out) xgrad_out[(size_t)leaf * KP + k] = gv;
                 G_s[p * KPC + kk] = make_float2((float)gv, 0.0f);
             }
-            if (r[u].slot >= -1 && r[u].k_or_leaf != INT32_MIN) us_s[p * KPC + kk] = uv[u];
+            if (us_k ? r[u].k_or_leaf >= 0 : (r[u].slot >= -1 && r[u].k_or_leaf != INT32_MIN)) us_s[p * KPC + kk] = uv[u];
         }
     }
     __syncthreads();
 
     // forward recompute of u (same operations as k3s_tree_fwd -> same bits)
-    for (int l = 0; l < nlev; ++l) {
+    for (int l = 0; l < (us_k ? 0 : nlev); ++l) {
         const int lo = lvl_s[l], hi = lvl_s[l + 1];
         for (int p = lo + slot_t; p < hi; p += NPP) {
             const SNode r = rec_s[p];
@@ -392,6 +395,91 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
         __syncthreads();
     }
+}
+
+// transform! (src/ptt.jl:125-158) as path products: u_i is the product, from the root down, of y (into a left child) or
+// 1 - y (into a right child) -- the very multiplications the reference's index-order sweep performs on the way to node
+// i, in the same order, so every u (and x) has the reference's bits; but no node waits for another, so there are no
+// levels and no exchange between kernels.  One CTA = one group of PATH_GROUP consecutive nodes x KP draws: the y of the
+// group's distinct ancestors are gathered into shared memory once (neighbours in DFS order share nearly all of them),
+// then a thread = (PATH_GROUP / PATH_SLOTS nodes, one draw) multiplies along the group's common path prefix once and
+// along each of its nodes' own suffixes.  Internal nodes store u by k for the backward kernels, leaves produce x.
+template <int KP>
+__global__ void __launch_bounds__(PATH_SLOTS *KP, 2048 / (PATH_SLOTS * KP) > 16 ? 16 : 2048 / (PATH_SLOTS * KP))
+    k3p_tree_fwd(int64_t N, const TreeNode *__restrict__ nodes, const uint32_t *__restrict__ ganc_ptr,
+                 const uint32_t *__restrict__ ganc, const uint32_t *__restrict__ gcp, const uint32_t *__restrict__ nsuf_ptr,
+                 const uint16_t *__restrict__ nsuf, const double *__restrict__ ys, double *__restrict__ us_k,
+                 float *__restrict__ x, double *__restrict__ xd, int clamp_x, const float *__restrict__ efflen,
+                 double *__restrict__ S_partial, int want_ladj, double *__restrict__ ladj_partial) {
+    constexpr int THREADS = PATH_SLOTS * KP, NPT = PATH_GROUP / PATH_SLOTS;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ double red[THREADS];
+    const int k = threadIdx.x % KP, t = threadIdx.x / KP;
+    // everything that does not depend on another load first
+    const uint32_t a0 = ganc_ptr[blockIdx.x], na = ganc_ptr[blockIdx.x + 1] - a0, cp = gcp[blockIdx.x];
+    const int64_t g0 = (int64_t)blockIdx.x * PATH_GROUP, i0 = g0 + t;
+    const int64_t g1 = g0 + PATH_GROUP < N ? g0 + PATH_GROUP : N;
+    const uint32_t s0 = nsuf_ptr[g0], ns = nsuf_ptr[g1] - s0;  // the group's suffix entries are contiguous
+    TreeNode nd[NPT];
+    uint32_t sb[NPT], se[NPT];
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+        const int64_t i = i0 + j * PATH_SLOTS;
+        nd[j] = TreeNode{-1, -1, -1, -1};
+        sb[j] = se[j] = 0;
+        if (i < N) {
+            nd[j] = nodes[i];
+            sb[j] = nsuf_ptr[i] - s0;
+            se[j] = nsuf_ptr[i + 1] - s0;
+        }
+    }
+    // shared memory: yy[2 a + side][KP] = y of ancestor a (side 1: the path goes left) or 1 - y (side 0: right), so a
+    // path step is one load and one multiply; pre[a] = 2 a + side of the common prefix; suf[] = the group's suffixes
+    double *yy_s = reinterpret_cast<double *>(smraw);                          // [2 na][KP]
+    uint16_t *pre_s = reinterpret_cast<uint16_t *>(yy_s + (size_t)2 * na * KP);  // [cp]
+    uint16_t *suf_s = pre_s + ((cp + 7u) & ~7u);                                 // [ns]
+    for (uint32_t a = t; a < na; a += PATH_SLOTS) {
+        const uint32_t en = ganc[a0 + a];
+        if (k == 0 && a < cp) pre_s[a] = (uint16_t)((a << 1) | (en & 1u));
+        const double y = ys[(size_t)(en >> 1) * KP + k];
+        yy_s[(2 * a + 1) * KP + k] = y;
+        yy_s[(2 * a) * KP + k] = __dsub_rn(1.0, y);
+    }
+    for (uint32_t e = threadIdx.x; e < ns; e += THREADS) suf_s[e] = nsuf[s0 + e];
+    float ef[NPT];
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) ef[j] = (efflen && nd[j].leaf >= 0) ? efflen[nd[j].leaf] : 1.0f;
+    __syncthreads();
+    const double *yk = yy_s + k;
+    double up = 1.0;  // the group's common prefix
+#pragma unroll 4
+    for (uint32_t a = 0; a < cp; ++a) up = __dmul_rn(yk[(uint32_t)pre_s[a] * KP], up);
+    double sacc = 0.0, lacc = 0.0;
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+        if (i0 + j * PATH_SLOTS >= N) continue;
+        double u = up;
+#pragma unroll 4
+        for (uint32_t e = sb[j]; e < se[j]; ++e) u = __dmul_rn(yk[(uint32_t)suf_s[e] * KP], u);
+        if (nd[j].leaf >= 0) {
+            float xv = (float)u;
+            double d = (double)xv;
+            xv = (float)(d > 1e-16 ? d : 1e-16);  // ptt.jl:136-137
+            if (clamp_x) {                         // clamp!(xs, 1e-10, 1 - 1e-10) on a Float32 vector
+                d = (double)xv;
+                d = fmin(fmax(d, 1e-10), 1.0 - 1e-10);
+                xv = (float)d;
+            }
+            x[(size_t)nd[j].leaf * KP + k] = xv;
+            xd[(size_t)nd[j].leaf * KP + k] = (double)xv;
+            if (efflen) sacc = __dadd_rn(sacc, (double)__fdiv_rn(xv, ef[j]));
+        } else {
+            us_k[(size_t)nd[j].k * KP + k] = u;
+            if (want_ladj) lacc += log(u);
+        }
+    }
+    if (S_partial) block_reduce_kc<KP, THREADS>(sacc, red, S_partial + (size_t)blockIdx.x * KP);
+    if (want_ladj) block_reduce_kc<KP, THREADS>(lacc, red, ladj_partial + (size_t)blockIdx.x * KP);
 }
 
 // Leaf records carry the leaf's effective length (left) and Float32(n / efflen) (right) as raw Float32 bits, so the
@@ -631,7 +719,7 @@ int ensure_work_buffers(polee_handle *h, int KP) {
     release_work_buffers(h);
     const int64_t n = h->n, nm1 = std::max<int64_t>(n - 1, 1), N = 2 * n - 1;
     h->tree_grid = std::max(1, std::min(h->td.s_bottom.nbins * std::max(1, KP / std::min(KP, 4)), 2 * h->num_sms));
-    h->n_tree_ctas = 1 + std::max(h->td.bottom.nbins, h->tree_grid);
+    h->n_tree_ctas = std::max(1 + std::max(h->td.bottom.nbins, h->tree_grid), h->td.n_groups);
     CK(polee::dmalloc((void **)&h->zs0, sizeof(float) * nm1 * KP));
     CK(polee::dmalloc((void **)&h->zs, sizeof(float) * nm1 * KP));
     CK(polee::dmalloc((void **)&h->ys, sizeof(double) * nm1 * KP));
@@ -720,6 +808,15 @@ static void set_smem_attr(F func, size_t bytes) {
     allow_max_smem(func);  // per-function, process-wide: see common.cuh
 }
 
+// the path-product forward kernel (k3p_tree_fwd) is used whenever the tree's root paths were built (not for very deep
+// trees) and the shared-memory backward kernels, which read its u, are; POLEE_TREE_FWD=levels keeps the level kernels
+static bool smem_path_ok(const polee_handle *h, int KP);
+static bool chain_path(const polee_handle *h);
+static bool path_fwd_ok(const polee_handle *h) {
+    static const bool off = getenv("POLEE_TREE_FWD") && !strcmp(getenv("POLEE_TREE_FWD"), "levels");
+    return !off && h->td.ganc_ptr != nullptr && !chain_path(h) && smem_path_ok(h, h->work_KP);
+}
+
 // bottom-forest launch variants (draws per CTA, threads, min CTAs/SM); POLEE_TREE_VARIANT picks one at run time
 static int tree_variant() {
     static int v = -1;
@@ -748,7 +845,7 @@ static void launch_bwd_bottom_v(polee_handle *h, const float *adj, double *xgrad
     set_smem_attr(fn, smem);
     fn<<<dim3(td.s_bottom.nbins, KP / KPC), THREADS, smem, h->stream>>>(
         td.s_bottom.bin_off, td.s_bottom.bin_lvl_ptr, td.s_bottom.lvl_off, td.s_bottom.recs, h->ys, h->root_us, h->root_G, h->g,
-        adj, h->S, h->ygrad, xgrad_out);
+        adj, h->S, h->ygrad, xgrad_out, path_fwd_ok(h) ? h->us : nullptr);
 }
 
 template <int KP>
@@ -796,7 +893,7 @@ static int launch_tree_bwd_smem(polee_handle *h, const float *adj, double *xgrad
         set_smem_attr(fn, smem);
         fn<<<dim3(td.s_top.nbins, KP), S_TOP_THREADS, smem, h->stream>>>(
             td.s_top.bin_off, td.s_top.bin_lvl_ptr, td.s_top.lvl_off, td.s_top.recs, h->ys, h->root_us, h->root_G, h->g, adj,
-            h->S, h->ygrad, xgrad_out);
+            h->S, h->ygrad, xgrad_out, path_fwd_ok(h) ? h->us : nullptr);
     }
     return POLEE_OK;
 }
@@ -827,6 +924,14 @@ int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_l
     const float *eff = want_S ? h->efflen : nullptr;
     double *Sp = want_S ? h->S_partial : nullptr;
     if (chain_path(h)) return launch_chain_fwd(h, KP, clamp_x, eff, Sp, want_ladj, ladj_tree);
+    if (path_fwd_ok(h)) {
+        const size_t smem = (size_t)td.max_ganc * (16 * KP + 2) + 16 + 2 * (size_t)td.max_gsuf;
+        if (smem > 40 * 1024) DISPATCH_KP(KP, allow_max_smem(k3p_tree_fwd<KPC>));
+        DISPATCH_KP(KP, (k3p_tree_fwd<KPC><<<td.n_groups, PATH_SLOTS * KPC, smem, h->stream>>>(
+                            td.N, td.nodes, td.ganc_ptr, td.ganc, td.gcp, td.nsuf_ptr, td.nsuf, h->ys, h->us, h->x, h->xd, clamp_x,
+                            eff, Sp, want_ladj, ladj_tree)));
+        return POLEE_OK;
+    }
     if (smem_path_ok(h, KP)) {
         int rc = POLEE_OK;
         DISPATCH_KP(KP, rc = launch_tree_fwd_smem<KPC>(h, clamp_x, eff, Sp, want_ladj, ladj_tree));
