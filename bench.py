@@ -68,7 +68,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index, period_s=0.004):
         self.gpu = gpu_index
-        self.period = period_s
+        self.period = float(os.environ.get("POLEE_BENCH_CLOCK_PERIOD_MS", period_s * 1e3)) * 1e-3
         self.sm, self.reasons = [], set()
         self.sm_max = None
         self.stop = threading.Event()
@@ -124,13 +124,17 @@ class ClockSampler:
             self.stop.wait(self.period)
 
     def __enter__(self):
+        mode = os.environ.get("POLEE_BENCH_CLOCKS", "")
+        if mode == "off" or (mode == "rank0" and int(os.environ.get("RANK", "0")) != 0):
+            return self
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.t.join(timeout=6)
+        if self.t is not None:
+            self.t.join(timeout=6)
 
     def summary(self):
         if not self.sm:
@@ -269,9 +273,15 @@ def run_ours(args):
     h.init_params()
     h.run_steps(args.warmup)
     h.sync()
+    # NVML inside the timed window: one query costs nothing at N = 1, but eight processes querying at once stall each
+    # other's launches for milliseconds (measured: 0.81 ms/step instead of 0.29 at N = 8 with a 20-step window), so at
+    # N > 1 rank 0 alone samples; the sampler is also created BEFORE the barrier (nvmlInit takes a rank-dependent time).
+    if world > 1:
+        os.environ.setdefault("POLEE_BENCH_CLOCKS", "rank0")
+    sampler = ClockSampler(local)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with sampler as clk:
         with torch.cuda.stream(stream):
             e0.record(stream)
         h.run_steps(args.steps)
