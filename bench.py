@@ -39,6 +39,12 @@ CONFIGS = {
     "c2": (1 << 20, 20_000, 1, False, 20260002),
     "c3": (30_000_000, 200_000, 8, False, 20260003),
     "c3-small": (3_000_000, 200_000, 8, False, 20260003),
+    # C4 (heavy multi-mapping, only ever exists as per-rank blocks) and C5 (64 whole samples, one per GPU at a time):
+    # see run_c4 / run_c5
+    "c4": (100_000_000, 250_000, 8, True, 20260004),
+    "c4-small": (8_000_000, 250_000, 8, True, 20260004),
+    "c5": (30_000_000, 200_000, 8, False, 20260005),
+    "c5-small": (2_000_000, 200_000, 8, False, 20260005),
 }
 FIT_STEPS = 500  # LIKAP_NUM_STEPS (src/constants.jl:64): what one approximate_likelihood call runs
 
@@ -447,6 +453,194 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _dist_setup(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    return world, rank, local, dev
+
+
+def run_c4(args):
+    """BASELINE config 4: 100 M fragments x 250 k transcripts with heavy multi-mapping (10 % of the rows span 64-512
+    transcripts), row-partitioned over the ranks with one NCCL all-reduce per step.  The matrix never exists as a whole:
+    every rank generates its own block of m / N rows on its GPU (same transcriptome, its own rows: synth row_seed)."""
+    import torch
+    import torch.distributed as dist
+    import polee_b200 as pb
+    from polee_b200 import api as pbapi, synth
+    world, rank, local, dev = _dist_setup(args)
+    m, n, K, long_rows, seed = CONFIGS[args.config]
+    m_loc = m // world
+    if m_loc * 40 > 2**31 - 1:
+        raise SystemExit("%s needs more ranks: %d rows per rank would exceed 2^31 entries" % (args.config, m_loc))
+    s = synth.make_sample(m_loc, n, seed=seed, device=dev, long_rows=True, row_seed=seed * 1000 + rank)
+    tree = synth.balanced_tree(n, s["gene_sizes"].cpu().numpy())
+    efflens = s["efflens"].cpu().numpy()
+    nnz_loc = s["nnz"]
+    colptr_d, rowval_d, nzval_d = s["colptr"].to(torch.int32), s["rowval"].to(torch.int32), s["nzval"]
+    del s
+    torch.cuda.empty_cache()
+    h = pb.Handle(device=local, num_mc_samples=K, num_steps=max(args.steps + args.warmup, 1), seed=args.seed)
+    t0 = time.perf_counter()
+    h.set_matrix_device(m_loc, n, colptr_d.data_ptr(), rowval_d.data_ptr(), nzval_d.data_ptr())
+    torch.cuda.synchronize()
+    t_layout = time.perf_counter() - t0
+    del colptr_d, rowval_d, nzval_d
+    torch.cuda.empty_cache()
+    h.set_efflens(efflens)
+    h.set_tree(*tree)
+    if world > 1:
+        uid = [pbapi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(world, rank, uid[0])
+        os.environ.setdefault("POLEE_BENCH_CLOCKS", "rank0")
+    stats, info = h.step_stats(), h.layout_info()
+    stream = torch.cuda.ExternalStream(h.stream(), device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    h.init_params()
+    h.run_steps(args.warmup)
+    h.sync()
+    sampler = ClockSampler(local)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler as clk:
+        e0.record(stream)
+        h.run_steps(args.steps)
+        e1.record(stream)
+        h.sync()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    tot = torch.tensor([float(nnz_loc), float(info["ec_nnz"]), float(info["general_nnz"])], device=dev, dtype=torch.float64)
+    tmax = torch.tensor([ms, t_layout], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms, t_layout = float(tmax[0].item()), float(tmax[1].item())
+    out = h.get_params()
+    finite = bool(all(np.all(np.isfinite(v)) for v in out))
+    reps = max(5, min(20, args.steps))
+    t_k1, t_k2, t_k3 = (h.time_kernel(w, reps) for w in (1, 2, 3))
+    t_ec = h.time_kernel(4, reps) if info["ec_rows"] > 0 else 0.0
+    peak, peak_src = measured_peak()
+    KP = 8
+    gm, gnnz = info["general_rows"], info["general_nnz"]
+    b_k1 = gnnz * 8 + (gm + 1) * 4 + KP * n * 4 + KP * gm * 4      # the general (split) layout's two passes: SURVEY 8d
+    b_k2 = gnnz * 8 + (n + 1) * 4 + KP * gm * 4 + KP * n * 4
+    h.close()
+    if rank == 0:
+        nnz_total = int(tot[0].item())
+        # dominant kernel: the long rows (> 64 transcripts) take the general split layout; K2 of it streams the most
+        cand = {"k1_sell_fwd": (b_k1, t_k1 - t_ec - 0.0), "k2_csc_grad": (b_k2, t_k2)}
+        if t_k2 <= 0:   # fused / class-only layouts: report the whole pass
+            cand = {"likelihood_pass": (stats["bytes_k1"], t_k1)}
+        kname = max(cand, key=lambda k: cand[k][1])
+        ach = cand[kname][0] / max(cand[kname][1], 1e-9) / 1e6
+        line = {"metric": "elbo_grad_evals_per_sec", "value": round(K * args.steps / (ms * 1e-3), 1), "unit": "evals/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE,
+                "data": "synthetic (polee-synth-v1, seed %d; every rank generates its own row block on its GPU)" % seed,
+                "config": {"workload": workload(args.config, m_loc * world, n, nnz_total, K)},
+                "details": {"partition": "%d ranks x %d rows each (same transcriptome, independent rows)" % (world, m_loc),
+                            "layout": "class layout: %.1f %% of the entries; general %s layout (rows longer than 64 "
+                                      "transcripts): %.1f %%" % (100 * tot[1].item() / nnz_total, info["general_kind"],
+                                                                 100 * tot[2].item() / nnz_total),
+                            "layout_build_s": round(t_layout, 3), "finite_fit": finite,
+                            "e2e": "not run: the per-rank blocks (%.1f GB of CSC each) are generated on the device"
+                                   % (nnz_loc * 8 / 1e9)},
+                "clocks": clk.summary(), "gpu_launches": int(stats["launches"] * args.steps),
+                "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                             "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                             "kernels_ms": {"likelihood_pass_class+k1": round(t_k1, 4), "k_ec_lik": round(t_ec, 4),
+                                            "k2_csc_grad": round(t_k2, 4), "k3_tree_reparam_adam": round(t_k3, 4)},
+                             "note": "rank 0's launches; bytes = SURVEY 8(d) formula on the rows of the general layout"}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_c5(args):
+    """BASELINE config 5: batch prep of 64 GTEx-shaped samples, whole samples per GPU (replicas only, no collective;
+    src/main.jl:590-631 is the loop).  Every rank fits its share of the samples one after another through the public
+    API from pinned HOST buffers (upload + layout build + 500 ADAM steps + download); a sample's synthetic generation
+    (which stands in for the reference's BAM parsing) is outside the timed sum.  value = aggregate evals/s."""
+    import torch
+    import torch.distributed as dist
+    import polee_b200 as pb
+    from polee_b200 import synth
+    world, rank, local, dev = _dist_setup(args)
+    m0, n, K, _, seed = CONFIGS[args.config]
+    n_samples = args.samples
+    rng = np.random.default_rng(seed)
+    sizes = np.clip(m0 * np.exp(0.35 * rng.standard_normal(n_samples)), m0 / 2, m0 * 2).astype(np.int64)  # depth spread +-2x
+    mine = list(range(rank, n_samples, world))
+    pin = lambda t, dt: torch.empty(t.shape, dtype=dt, pin_memory=True).copy_(t.to(dt)).numpy()  # noqa: E731
+    t_sum, evals, h2d, nnz_sum = 0.0, 0, 0, 0
+    fits = []
+    with ClockSampler(local, period_s=0.05) as clk:
+        for i in mine:
+            s = synth.make_sample(int(sizes[i]), n, seed=seed + 1 + i, device=dev)
+            tree = synth.balanced_tree(n, s["gene_sizes"].cpu().numpy())
+            host = {"colptr": pin(s["colptr"], torch.int32).view(np.uint32), "rowval": pin(s["rowval"], torch.int32).view(np.uint32),
+                    "nzval": pin(s["nzval"], torch.float32)}
+            efflens = s["efflens"].cpu().numpy()
+            nnz_sum += s["nnz"]
+            del s
+            torch.cuda.empty_cache()
+            sample = pb.RNASeqSample(int(sizes[i]), n, host["colptr"], host["rowval"], host["nzval"], efflens)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), sample, tree_topology=tree, num_steps=FIT_STEPS,
+                                            num_mc_samples=K, seed=args.seed + i, device=local)
+            dt = time.perf_counter() - t0
+            assert np.all(np.isfinite(out["mu"]))
+            fits.append(dt)
+            t_sum += dt
+            evals += K * FIT_STEPS
+            h2d += host["colptr"].nbytes + host["rowval"].nbytes + host["nzval"].nbytes + efflens.nbytes + 2 * 4 * (2 * n - 1)
+    agg = torch.tensor([float(evals), float(h2d), float(nnz_sum), float(len(mine))], device=dev, dtype=torch.float64)
+    tmax = torch.tensor([t_sum], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(agg)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    T = float(tmax.item())
+    if rank == 0:
+        v = agg[0].item() / T
+        line = {"metric": "elbo_grad_evals_per_sec", "value": round(v, 1), "unit": "evals/s", "n_gpus": world,
+                "steps": FIT_STEPS, "warmup": 0, "ms_per_step": round(T / (len(mine) * FIT_STEPS) * 1e3, 4),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
+                "data": "synthetic (polee-synth-v1, seeds %d..%d)" % (seed + 1, seed + n_samples),
+                "config": {"workload": "%s: %d samples, m ~ LogNormal around %d (x0.5..x2), %d transcripts, K=%d, %d ADAM steps "
+                                       "each; whole samples per GPU, no collective" % (args.config, n_samples, m0, n, K, FIT_STEPS)},
+                "details": {"samples_per_s": round(agg[3].item() / T, 3), "job_time_s": round(T, 3),
+                            "rank0_fit_times_s": [round(x, 3) for x in fits], "total_nnz": int(agg[2].item()),
+                            "timed": "sum over a rank's samples of the approximate_likelihood wall time from pinned host "
+                                     "buffers (upload, layout build, fit, download); max over ranks"},
+                "clocks": clk.summary(), "gpu_launches": None,
+                "e2e": {"value": round(v, 1), "unit": "evals/s", "h2d_bytes_per_step": int(agg[1].item() / agg[3].item()),
+                        "d2h_bytes_per_step": int(3 * 4 * (n - 1)),
+                        "step": "here a step = one whole sample (the e2e path IS the measured path of this config)"}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def cpu_baseline(m, n, K, host, efflens, tree, budget_s=25.0, warm=0, check=None):
     """The oracle (C/OpenMP restatement of the reference's Julia loops) on the host cores: whole ADAM steps of
     K draws on the SAME matrix, as many as fit in the budget (at least one).  With check = (xs, lp, x_grad) of one
@@ -489,7 +683,19 @@ def run_reference(args):
     from polee_b200 import synth
     m, n, K, long_rows, seed = CONFIGS[args.config]
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    s = synth.make_sample(m, n, seed=seed, device=dev, long_rows=long_rows)
+    scale, scale_note = 1.0, ""
+    if args.config.startswith("c4"):
+        # the whole C4 matrix does not fit the host: time the block of ONE of 8 ranks (1/8 of the rows, the same
+        # generator the GPU arm uses) and divide -- every loop of the path is linear in the rows
+        parts = 8
+        s = synth.make_sample(m // parts, n, seed=seed, device=dev, long_rows=True, row_seed=seed * 1000)
+        scale, scale_note = 1.0 / parts, "; timed on 1/%d of the rows (one rank's block), value = that / %d" % (parts, parts)
+    elif args.config.startswith("c5"):
+        s = synth.make_sample(m, n, seed=seed + 1, device=dev)   # one sample of the median size: samples are sequential on a CPU
+        scale_note = "; one median-size sample (the CPU fits samples one after another, so evals/s is per sample)"
+    else:
+        s = synth.make_sample(m, n, seed=seed, device=dev, long_rows=long_rows)
+    m = s["m"]
     tree = synth.balanced_tree(n, s["gene_sizes"].cpu().numpy())
     ns = synth.to_numpy_sample(s)
     nnz = s["nnz"]
@@ -514,9 +720,9 @@ def run_reference(args):
             break
     el = time.perf_counter() - t0
     st.close()
-    v = round(K * steps / el, 3)
-    sample = "%d of the %d requested ADAM steps (x %d draws) on the full matrix within a %.0f s budget; %d warm-up" % (
-        steps, args.steps, K, budget, done_w)
+    v = round(K * steps / el * scale, 3)
+    sample = "%d of the %d requested ADAM steps (x %d draws) on the full matrix within a %.0f s budget; %d warm-up%s" % (
+        steps, args.steps, K, budget, done_w, scale_note)
     print(json.dumps({
         "impl": "reference", "metric": "elbo_grad_evals_per_sec", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": done_w, "ms_per_step": round(el / steps * 1e3, 2), "higher_is_better": True,
@@ -540,10 +746,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--samples", type=int, default=64, help="c5: number of samples")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.config.startswith("c4"):
+        run_c4(args)
+    elif args.config.startswith("c5"):
+        run_c5(args)
     else:
         run_ours(args)
 

@@ -31,14 +31,23 @@ def _gene_layout(n, gen, device, mean_gene_size=6.0):
     return sizes, starts
 
 
-def make_sample(m, n, seed=20260002, device="cpu", long_rows=False, patterns_per_gene=4, incl_prob=0.5):
+def make_sample(m, n, seed=20260002, device="cpu", long_rows=False, patterns_per_gene=4, incl_prob=0.5, row_seed=None):
     """Returns dict with CSC arrays (1-based, torch int64 on `device`), nzval, efflens, gene layout.
 
     mean row length ~ 4 with the defaults; long_rows=True additionally turns 10 % of the rows into
-    "repeat-family" rows spanning 64-512 transcripts (BASELINE config C4)."""
+    "repeat-family" rows spanning 64-512 transcripts (BASELINE config C4).
+
+    row_seed: draw everything that belongs to the ROWS (their genes, patterns, values) from a second generator, so
+    that blocks of rows made with different row_seed share the transcriptome (genes, effective lengths, abundances,
+    pattern pools, repeat families) of `seed` -- how a rank makes its own block of C4 without the whole matrix ever
+    existing anywhere.  None (default): one generator for everything, the sequence the golden fixtures were made with."""
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
+    genr = gen
+    if row_seed is not None:
+        genr = torch.Generator(device=dev)
+        genr.manual_seed(row_seed)
     f64, i64 = torch.float64, torch.int64
 
     sizes, starts = _gene_layout(n, gen, dev)
@@ -56,7 +65,7 @@ def make_sample(m, n, seed=20260002, device="cpu", long_rows=False, patterns_per
 
     # fragments grouped by gene, in gene order
     cdf = torch.cumsum(gprob, 0)
-    ug = torch.rand(m, generator=gen, device=dev, dtype=f64)
+    ug = torch.rand(m, generator=genr, device=dev, dtype=f64)
     row_gene = torch.searchsorted(cdf, ug).clamp_max(G - 1)
     row_gene, _ = torch.sort(row_gene)
 
@@ -74,7 +83,7 @@ def make_sample(m, n, seed=20260002, device="cpu", long_rows=False, patterns_per
     nzb = bits.reshape(G * P, 64).nonzero()                   # sorted by (pattern, bit)
     pat_tx = starts[nzb[:, 0] // P] + nzb[:, 1]
 
-    row_pat = row_gene * P + torch.randint(0, P, (m,), generator=gen, device=dev)
+    row_pat = row_gene * P + torch.randint(0, P, (m,), generator=genr, device=dev)
     row_len = pat_len[row_pat]
 
     fam_ptr = fam_tx = None
@@ -88,8 +97,8 @@ def make_sample(m, n, seed=20260002, device="cpu", long_rows=False, patterns_per
         jitter = torch.randint(0, 8, (pos.numel(),), generator=gen, device=dev)
         fam_tx = (torch.repeat_interleave(fstart, flen) + pos * 8 + jitter).clamp_max(n - 1)
         # clamp can create duplicates at the very end of the id range: make ids strictly increasing per family
-        is_long = torch.rand(m, generator=gen, device=dev) < 0.10
-        row_fam = torch.randint(0, F, (m,), generator=gen, device=dev)
+        is_long = torch.rand(m, generator=genr, device=dev) < 0.10
+        row_fam = torch.randint(0, F, (m,), generator=genr, device=dev)
         row_len = torch.where(is_long, flen[row_fam], row_len)
 
     row_ptr = torch.cumsum(row_len, 0) - row_len
@@ -109,8 +118,8 @@ def make_sample(m, n, seed=20260002, device="cpu", long_rows=False, patterns_per
         ent_row, ent_col = ent_row[keep], ent_col[keep]
         nnz = int(ent_row.numel())
 
-    f_i = 1e-4 + (5e-3 - 1e-4) * torch.rand(m, generator=gen, device=dev, dtype=f64)
-    val = f_i[ent_row] * torch.exp(1.5 * torch.randn(nnz, generator=gen, device=dev, dtype=f64)) / efflen[ent_col].to(f64)
+    f_i = 1e-4 + (5e-3 - 1e-4) * torch.rand(m, generator=genr, device=dev, dtype=f64)
+    val = f_i[ent_row] * torch.exp(1.5 * torch.randn(nnz, generator=genr, device=dev, dtype=f64)) / efflen[ent_col].to(f64)
     val = val.clamp_min(1.0001e-12).to(torch.float32)
 
     # CSR (row-major, ascending transcript inside a row) -> CSC: stable sort by column
