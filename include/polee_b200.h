@@ -126,6 +126,12 @@ int polee_fit_optimize_ptt(polee_handle *h, float *xs /* n */);
 int polee_init_params(polee_handle *h);                 /* :451-456, resets ADAM state and step counter */
 int polee_run_steps(polee_handle *h, int32_t nsteps);   /* asynchronous: enqueue nsteps ADAM steps */
 int polee_sync(polee_handle *h);                        /* wait + surface POLEE_ENONFINITE */
+/* Progress of polee_run_steps / polee_fit: cb(steps_done, num_steps, user) is called on the calling thread each time
+ * another `every` ADAM steps have FINISHED on the device (the steps are otherwise enqueued without waiting), so that
+ * the reference's "Optimizing" progress bar (likelihood-approximation.jl:495, :574: next!(prog) once per step) keeps
+ * moving.  cb == NULL removes it. */
+typedef void (*polee_progress_fn)(int32_t steps_done, int32_t num_steps, void *user);
+int polee_set_progress(polee_handle *h, polee_progress_fn cb, void *user, int32_t every);
 int polee_get_params(polee_handle *h, float *mu, float *omega, float *alpha);
 int polee_set_params(polee_handle *h, const float *mu, const float *omega, const float *alpha);
 int polee_set_noise(polee_handle *h, const float *noise, int64_t num_steps); /* INJECTED mode buffer */

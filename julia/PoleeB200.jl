@@ -64,6 +64,7 @@ function with_handle(f, opts::PoleeOpts)
     try
         return f(h)
     finally
+        delete!(progress_bars, h)
         ccall((:polee_destroy, LIB), Cint, (Ptr{Cvoid},), h)
     end
 end
@@ -108,11 +109,6 @@ function approximate_likelihood_b200(approx::Polee.LogitSkewNormalPTTApprox, sam
                                      tree_topology_output_filename=nothing,
                                      gene_noninformative::Bool=false,
                                      use_efflen_jacobian::Bool=true) where {gradonly}
-    if tree_topology_output_filename !== nothing
-        # the YAML tree dump (l-a.jl:578-613) walks the host-side HClustNode objects; enable!() has overwritten
-        # the CPU method, so run that diagnostic without PoleeB200 loaded.
-        error("PoleeB200: --write-tree-topology is only available on the CPU path")
-    end
     # gene_id -> transcript indexes, exactly as l-a.jl:476-493
     gene_transcripts = Dict{String,Vector{Int}}()
     if gene_noninformative
@@ -129,12 +125,14 @@ function approximate_likelihood_b200(approx::Polee.LogitSkewNormalPTTApprox, sam
     end
     X = sample.X
     m, n = size(X)
+    tree_nodes_ref = Vector{Polee.HClustNode}[]
     if tree_topology_input_filename !== nothing            # l-a.jl:428-433
         input = Polee.h5open(tree_topology_input_filename)
         t = Polee.PolyaTreeTransform(read(input["node_parent_idxs"]), read(input["node_js"]))
         close(input)
     else
-        t = Polee.PolyaTreeTransform(X, approx.treemethod)  # hclust stays on the host (l-a.jl:435)
+        # hclust stays on the host (l-a.jl:435); the node objects are kept for --write-tree-topology (l-a.jl:426)
+        t = Polee.PolyaTreeTransform(X, approx.treemethod, tree_nodes_ref)
     end
     o = default_opts()
     o.device = device_for_this_task()
@@ -152,10 +150,14 @@ function approximate_likelihood_b200(approx::Polee.LogitSkewNormalPTTApprox, sam
         set_efflens!(h, sample.effective_lengths)
         pj = set_tree!(h, t)
         gene_noninformative && set_gene_groups!(h, gene_transcripts)
+        with_progress_bar(h, Polee.LIKAP_NUM_STEPS)        # the "Optimizing" bar of l-a.jl:495,574
         check(h, ccall((:polee_fit, LIB), Cint,
                        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Ptr{Float32}),
                        h, mu, omega, alpha, C_NULL, C_NULL))
         pj
+    end
+    if tree_topology_output_filename !== nothing && !isempty(tree_nodes_ref)
+        write_tree_topology(tree_topology_output_filename, tree_nodes_ref[1], sample, mu, omega, alpha)
     end
     params = Dict{String,Vector}("mu" => mu, "omega" => omega, "alpha" => alpha)
     if tree_topology_input_filename === nothing             # l-a.jl:618-621
@@ -163,6 +165,53 @@ function approximate_likelihood_b200(approx::Polee.LogitSkewNormalPTTApprox, sam
         params["node_js"] = js
     end
     return params
+end
+
+# The reference advances a ProgressMeter bar once per ADAM step (l-a.jl:495, :574).  The library enqueues the steps
+# without waiting, so it reports back every PROGRESS_EVERY finished steps through polee_set_progress.
+const PROGRESS_EVERY = 25
+const progress_bars = Dict{Ptr{Cvoid},Any}()
+function progress_thunk(done::Int32, total::Int32, user::Ptr{Cvoid})::Cvoid
+    bar = get(progress_bars, user, nothing)
+    bar === nothing || Polee.ProgressMeter.update!(bar, Int(done))
+    return nothing
+end
+function with_progress_bar(h::Ptr{Cvoid}, nsteps::Integer)
+    progress_bars[h] = Polee.Progress(nsteps, 0.25, "Optimizing ", 60)
+    cb = @cfunction(progress_thunk, Cvoid, (Int32, Int32, Ptr{Cvoid}))
+    check(h, ccall((:polee_set_progress, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32), h, cb, h, PROGRESS_EVERY))
+end
+
+"""
+The optional tree diagnostics of `--write-tree-topology` (the YAML the reference prints at l-a.jl:578-613), from the
+host-side cluster nodes and the fitted parameters.  Field names, order and values follow the reference's output,
+including that its `right:` line carries the LEFT child's id (l-a.jl:603).
+"""
+function write_tree_topology(filename, nodes, sample, mu, omega, alpha)
+    names = [t.metadata.name for t in sample.ts]
+    md = sample.transcript_metadata
+    genes = [get(md.gene_name, get(md.gene_id, nm, ""), "") for nm in names]
+    id_of = IdDict{Polee.HClustNode,Int}(node => i for (i, node) in enumerate(nodes))
+    open(filename, "w") do io
+        println(io, "nodes:")
+        k = 0
+        for (i, node) in enumerate(nodes)
+            println(io, "  - id: node", i)
+            println(io, "    read_count: ", node.read_count)
+            if node.j == 0
+                k += 1
+                println(io, "    mu: ", mu[k])
+                println(io, "    sigma: ", exp(omega[k]))
+                println(io, "    alpha: ", alpha[k])
+                println(io, "    child_jaccard: ", node.child_jaccard)
+                println(io, "    left: node", id_of[node.left_child])
+                println(io, "    right: node", id_of[node.left_child])
+            else
+                println(io, "    transcript_id: ", names[node.j])
+                println(io, "    gene_name: ", genes[node.j])
+            end
+        end
+    end
 end
 
 """Factored (salmon) variant, `src/likelihood-approximation.jl:248-392`."""

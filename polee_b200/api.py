@@ -163,6 +163,17 @@ class Handle:
     def sync(self):
         self.check(self.lib.polee_sync(self.h))
 
+    def set_progress(self, callback, every=25):
+        """callback(steps_done, num_steps) after every `every` finished ADAM steps (the reference's progress bar,
+        likelihood-approximation.jl:495,574); None removes it."""
+        if callback is None:
+            self._progress = None
+            self.check(self.lib.polee_set_progress(self.h, None, None, C.c_int32(0)))
+            return
+        fn_t = C.CFUNCTYPE(None, C.c_int32, C.c_int32, C.c_void_p)
+        self._progress = fn_t(lambda done, total, user: callback(int(done), int(total)))  # keep the thunk alive
+        self.check(self.lib.polee_set_progress(self.h, self._progress, None, C.c_int32(every)))
+
     def get_params(self):
         nm1 = self.n - 1
         mu, om, al = (np.zeros(nm1, np.float32) for _ in range(3))
@@ -439,8 +450,8 @@ def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, us
 
     tree_topology = (node_parent_idxs, node_js), what the reference reads from tree_topology_input_filename
     (:428-433).  Without one the tree is built as the reference does at :435: "sequential" -> list_nodes, "cluster" ->
-    the hclust restatement (polee_hclust, host code; tie-breaking is unpinned in the reference); "random"
-    needs a topology (Julia's RNG stream cannot be reproduced).
+    the hclust restatement (polee_hclust, host code; tie-breaking is unpinned in the reference); "random" ->
+    rand_tree_nodes restated on a seeded numpy generator (same distribution; Julia's RNG stream cannot be reproduced).
     gene_transcripts = {gene_id: [1-based transcript indices]} is the map the reference derives from the transcript
     metadata when gene_noninformative is set (:476-487); without it the flag is dropped with a warning (:489-492).
     """
@@ -463,8 +474,13 @@ def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, us
             tree_topology = sequential_tree(sample.n)
         elif approx.treemethod == "cluster":
             tree_topology = hclust(sample)
+        elif approx.treemethod == "random":
+            # rand_tree_nodes (src/hclust.jl:439-454): the same procedure (join two random subtrees until one is left)
+            # on numpy's generator seeded with `seed` -- Julia's RNG stream cannot be reproduced, the distribution can
+            from . import synth
+            tree_topology = synth.random_tree(sample.n, seed=seed)
         else:
-            raise ValueError("treemethod %r needs tree_topology=(node_parent_idxs, node_js)" % (approx.treemethod,))
+            raise ValueError("%r is not a supported Polya tree transform heuristic" % (approx.treemethod,))
     h = Handle(device=device, num_steps=num_steps, num_mc_samples=num_mc_samples, gradonly=gradonly,
                use_efflen_jacobian=use_efflen_jacobian, seed=seed,
                noise_mode=L.NOISE_INJECTED if noise is not None else L.NOISE_PHILOX,

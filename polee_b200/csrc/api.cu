@@ -238,6 +238,7 @@ extern "C" int polee_set_efflens(polee_handle *h, const float *efflens) {
     if (!efflens) return h->fail(POLEE_EINVAL, "set_efflens: null pointer");
     int64_t n = h->have_matrix ? h->n : (h->have_tree ? h->td.n : 0);
     if (n < 1) return h->fail(POLEE_EINVAL, "set_efflens: set the matrix or the tree first (n unknown)");
+    drop_graph(h);  // a captured step holds the old buffers' addresses
     polee::dfree(h->efflen); polee::dfree(h->efflen_adj);
     h->efflen = h->efflen_adj = nullptr;
     std::vector<float> adj(n);
@@ -574,7 +575,20 @@ extern "C" int polee_run_steps(polee_handle *h, int32_t nsteps) {
     for (int s = 0; s < nsteps; ++s) {
         if ((rc = enqueue_step(h))) return rc;
         h->steps_enqueued++;
+        if (h->progress_cb && h->progress_every > 0 && (h->steps_enqueued % h->progress_every == 0 || s + 1 == nsteps)) {
+            CK(cudaStreamSynchronize(h->stream));  // the bar reports finished steps, not enqueued ones
+            h->progress_cb(h->steps_enqueued, h->o.num_steps, h->progress_user);
+        }
     }
+    return POLEE_OK;
+}
+
+extern "C" int polee_set_progress(polee_handle *h, polee_progress_fn cb, void *user, int32_t every) {
+    CHECK_H(h);
+    if (cb && every < 1) return h->fail(POLEE_EINVAL, "set_progress: every must be >= 1");
+    h->progress_cb = cb;
+    h->progress_user = user;
+    h->progress_every = cb ? every : 0;
     return POLEE_OK;
 }
 
@@ -641,6 +655,9 @@ static int use_kp(polee_handle *h, int K, int *KP) {
     if (K < 1 || K > 16) return h->fail(POLEE_EINVAL, "K must be in 1..16");
     *KP = pad_k(K);
     drop_graph(h);
+    // every piecewise entry point comes through here and overwrites (or re-creates) ys / zs0 / x / g: the next
+    // polee_run_steps must produce its own reparameterisation again instead of stepping on the caller's values
+    h->reparam_ready = false;
     return ensure_work_buffers(h, *KP);
 }
 

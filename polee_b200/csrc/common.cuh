@@ -358,6 +358,9 @@ struct polee_handle {
     polee::StepCtl *d_step = nullptr;  // device step counters
     int *d_bad_step = nullptr;         // first step with a non-finite gradient, 0 = none
     int steps_enqueued = 0;
+    polee_progress_fn progress_cb = nullptr;  // polee_set_progress
+    void *progress_user = nullptr;
+    int progress_every = 0;
     bool reparam_ready = false;  // ys / zs0 of the next step have been produced (fused update + reparam kernel)
 
     // ---- per-step work buffers (layouts [item][KP])

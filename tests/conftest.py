@@ -14,6 +14,30 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with `pytest -m gpu` under gpurun)")
 
 
+def _have_b200():
+    """True when libpolee_b200 sees an sm_100 device (gpu-marked tests are skipped otherwise, e.g. a plain
+    `pytest tests` on the CPU-only build box)."""
+    try:
+        import ctypes as C
+        from polee_b200 import _lib as L
+        lib = L.load_library()
+        cc = (C.c_int32 * 2)()
+        sms = C.c_int32()
+        mem = C.c_int64()
+        rc = lib.polee_device_info(C.c_int32(0), cc, C.byref(sms), C.byref(mem))
+        return rc == 0 and cc[0] == 10
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if any("gpu" in it.keywords for it in items) and not _have_b200():
+        skip = pytest.mark.skip(reason="no sm_100 device visible to libpolee_b200")
+        for it in items:
+            if "gpu" in it.keywords:
+                it.add_marker(skip)
+
+
 class Fixture:
     """The reference's one golden pair: likelihood-matrix.h5 (input) and prep.h5 (tree + fit)."""
 

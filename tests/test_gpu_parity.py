@@ -183,6 +183,63 @@ def test_fit_trajectory_matches_oracle_with_injected_noise(pb, fx, oracle, K, st
         assert np.abs(dev0[key] - ora[key]).max() <= 2e-4, key
 
 
+def test_piecewise_calls_between_steps_do_not_disturb_the_fit(pb, fx):
+    """run_steps(a); <piecewise entry points, same and different K>; run_steps(b) == run_steps(a + b): the piecewise
+    calls overwrite (or re-create) the step's work buffers, so the next step must redo its own reparameterisation."""
+    K, a, b = 6, 7, 9
+    noise = np.random.default_rng(3).normal(size=(a + b, K, fx.n - 1)).astype(np.float32)
+
+    def make():
+        h = pb.Handle(num_mc_samples=K, num_steps=a + b, noise_mode=1)
+        h.set_sample(_sample(pb, fx))
+        h.set_tree(fx.parent_idxs, fx.js)
+        h.set_noise(noise, a + b)
+        h.init_params()
+        return h
+
+    h = make()
+    h.run_steps(a + b)
+    h.sync()
+    want = h.get_params()
+    h.close()
+    rng = np.random.default_rng(4)
+    for Kp in (K, 3, 1):
+        h = make()
+        h.run_steps(a)
+        h.sync()
+        ys = rng.uniform(0.2, 0.8, size=(Kp, fx.n - 1))
+        xs, _ = h.ptt_transform(ys)
+        h.loglik_grad(xs, gradonly=False)
+        h.ptt_transform_gradients(ys, rng.normal(size=(Kp, fx.n)))
+        h.run_steps(b)
+        h.sync()
+        got = h.get_params()
+        h.close()
+        for w, g in zip(want, got):
+            assert np.array_equal(w, g), Kp
+
+
+def test_progress_callback_and_random_treemethod(pb, fx):
+    """polee_set_progress reports finished steps (the reference's "Optimizing" bar, l-a.jl:495,574); treemethod
+    "random" (rand_tree_nodes, src/hclust.jl:439-454) builds a seeded random tree and returns its topology."""
+    seen = []
+    h = pb.Handle(num_mc_samples=6, num_steps=60)
+    h.set_sample(_sample(pb, fx))
+    h.set_tree(fx.parent_idxs, fx.js)
+    h.set_progress(lambda done, total: seen.append((done, total)), every=25)
+    h.fit()
+    assert seen == [(25, 60), (50, 60), (60, 60)]
+    h.set_progress(None)
+    h.close()
+    a = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox("random"), _sample(pb, fx), num_steps=20, seed=5)
+    b = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox("random"), _sample(pb, fx), num_steps=20, seed=5)
+    assert a["node_parent_idxs"].shape == (2 * fx.n - 1,) and np.array_equal(np.sort(a["node_js"][a["node_js"] > 0]), np.arange(1, fx.n + 1))
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    assert all(np.all(np.isfinite(a[k])) for k in ("mu", "omega", "alpha"))
+    with pytest.raises(ValueError):
+        pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox("nonsense"), _sample(pb, fx), num_steps=2)
+
+
 def test_default_fit_reproduces_reference_prep_file(pb, fx, oracle):
     """Device Philox noise, default options: lands where the reference's own prep.h5 does (SURVEY 8c tolerance)."""
     from conftest import sample_loglik
