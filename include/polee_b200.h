@@ -204,6 +204,14 @@ int polee_hsb_with_plan(const polee_hsb_plan *plan, int64_t B, const float *y_lo
 int polee_inv_hsb_with_plan(const polee_hsb_plan *plan, int64_t B, const float *x, double *y, float *ladj);
 int polee_inv_hsb_grad_with_plan(const polee_hsb_plan *plan, int64_t B, const double *y_grad, const float *ladj_grad,
                                  const double *y, float *backprops);
+/* Device-resident forms of the three ops: every tensor is a device pointer on the plan's device, the work is enqueued on
+ * `stream` (a cudaStream_t; NULL = the legacy stream) and nothing is copied or allocated per call (scratch lives in the
+ * plan).  This is what a DEVICE_GPU registration of the ops binds (the reference registers DEVICE_CPU only,
+ * hsb_ops.cpp:120, 249, 402); polee_b200/tf/hsb_ops_b200.cpp registers both. */
+int polee_hsb_device(const polee_hsb_plan *plan, int64_t B, const float *d_y_logit, float *d_x, void *stream);
+int polee_inv_hsb_device(const polee_hsb_plan *plan, int64_t B, const float *d_x, double *d_y, float *d_ladj, void *stream);
+int polee_inv_hsb_grad_device(const polee_hsb_plan *plan, int64_t B, const double *d_y_grad, const float *d_ladj_grad,
+                              const double *d_y, float *d_backprops, void *stream);
 const char *polee_hsb_last_error(void);
 /* make_inverse_ptt_params(node_parent_idxs, node_js)  src/ptt.jl:293-309 (host helper, exact ints) */
 int polee_make_inverse_ptt_params(int64_t num_nodes, const int32_t *node_parent_idxs, const int32_t *node_js,

@@ -142,10 +142,16 @@ class OpKernelContext {
   std::vector<DataType> output_types;
   DeviceBase dev;
   Status status;
+  // GPU-registered kernels (DEVICE_GPU): the harness supplies the output buffers (device memory) and the stream
+  std::vector<void*> output_prealloc;
+  void* gpu_stream = nullptr;
   const Tensor& input(int i) { return *inputs[i]; }
   Status allocate_output(int i, const TensorShape& s, Tensor** out) {
     if ((int)outputs.size() <= i) outputs.resize(i + 1);
-    outputs[i].reset(new Tensor(output_types[i], s));
+    if (i < (int)output_prealloc.size() && output_prealloc[i])
+      outputs[i].reset(new Tensor(output_types[i], s, output_prealloc[i]));
+    else
+      outputs[i].reset(new Tensor(output_types[i], s));
     *out = outputs[i].get();
     return Status::OK();
   }
@@ -254,7 +260,9 @@ class KernelDefBuilder {
  public:
   explicit KernelDefBuilder(const char* op) : op_(op) {}
   KernelDefBuilder& Device(const char* d) { device_ = d; return *this; }
+  KernelDefBuilder& HostMemory(const char* arg) { host_args_.push_back(arg); return *this; }
   std::string op_, device_;
+  std::vector<std::string> host_args_;
 };
 inline KernelDefBuilder Name(const char* op) { return KernelDefBuilder(op); }
 

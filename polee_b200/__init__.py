@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     LIKAP_NUM_STEPS,
     ApproxLikelihoodSampler,
     Handle,
+    HsbPlan,
     LogitSkewNormalPTTApprox,
     OptimizePTTApprox,
     PolyaTreeTransform,

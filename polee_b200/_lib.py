@@ -37,7 +37,7 @@ EXPORTS = [
     "polee_sync", "polee_set_progress", "polee_get_params", "polee_set_params", "polee_set_noise", "polee_get_elbo", "polee_stream",
     "polee_step_stats", "polee_layout_info", "polee_time_kernel", "polee_sample", "polee_loglik_grad", "polee_frag_prob_recip", "polee_ptt_transform",
     "polee_ptt_transform_gradients", "polee_ptt_inverse_transform", "polee_lsn_draws", "polee_hsb", "polee_inv_hsb",
-    "polee_inv_hsb_grad", "polee_hsb_plan_create", "polee_hsb_plan_destroy", "polee_hsb_with_plan",
+    "polee_inv_hsb_grad", "polee_hsb_device", "polee_inv_hsb_device", "polee_inv_hsb_grad_device", "polee_hsb_plan_create", "polee_hsb_plan_destroy", "polee_hsb_with_plan",
     "polee_inv_hsb_with_plan", "polee_inv_hsb_grad_with_plan", "polee_hsb_last_error",
     "polee_make_inverse_ptt_params", "polee_exact_factorization", "polee_hclust", "polee_partition_rows", "polee_comm_unique_id", "polee_comm_init",
 ]

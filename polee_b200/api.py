@@ -588,3 +588,41 @@ def inv_hsb_grad(y_grad, ladj_grad, y, ladj, left_index, right_index, leaf_index
     _hsb_check(L.load_library().polee_inv_hsb_grad(C.c_int32(device), C.c_int64(B), C.c_int64(n), _p(y_grad),
                                                    _p(ladj_grad), _p(y), _p(l), _p(r), _p(f), C.c_int64(ib), _p(bp)))
     return bp
+
+
+class HsbPlan:
+    """The validated, level-scheduled tree(s) of the three HSB ops resident on the device (polee_hsb_plan_*), with the
+    device-resident entry points (polee_*_device): every tensor argument is a DEVICE pointer (int), the work is
+    enqueued on `stream` (a cudaStream_t as int; 0 = the legacy stream) and nothing is copied -- what the DEVICE_GPU
+    registration of the TF ops binds (polee_b200/tf/hsb_ops_b200.cpp)."""
+
+    def __init__(self, n, left_index, right_index, leaf_index, device=0):
+        N = 2 * n - 1
+        arrs = [_c(a, np.int32).reshape(-1, N) for a in (left_index, right_index, leaf_index)]
+        self.n, self.idx_batch = n, arrs[0].shape[0]
+        self.lib = L.load_library()
+        self.p = C.c_void_p()
+        _hsb_check(self.lib.polee_hsb_plan_create(C.byref(self.p), C.c_int32(device), C.c_int64(n), C.c_int64(self.idx_batch),
+                                                  _p(arrs[0]), _p(arrs[1]), _p(arrs[2])))
+
+    def close(self):
+        if self.p:
+            self.lib.polee_hsb_plan_destroy(self.p)
+            self.p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def hsb_device(self, B, d_y_logit, d_x, stream=0):
+        _hsb_check(self.lib.polee_hsb_device(self.p, C.c_int64(B), C.c_void_p(d_y_logit), C.c_void_p(d_x), C.c_void_p(stream)))
+
+    def inv_hsb_device(self, B, d_x, d_y, d_ladj, stream=0):
+        _hsb_check(self.lib.polee_inv_hsb_device(self.p, C.c_int64(B), C.c_void_p(d_x), C.c_void_p(d_y), C.c_void_p(d_ladj),
+                                                 C.c_void_p(stream)))
+
+    def inv_hsb_grad_device(self, B, d_y_grad, d_ladj_grad, d_y, d_backprops, stream=0):
+        _hsb_check(self.lib.polee_inv_hsb_grad_device(self.p, C.c_int64(B), C.c_void_p(d_y_grad), C.c_void_p(d_ladj_grad),
+                                                      C.c_void_p(d_y), C.c_void_p(d_backprops), C.c_void_p(stream)))

@@ -135,15 +135,16 @@ extern "C" int polee_create(polee_handle **out, const polee_opts *opts) {
 }
 
 static void release_params(polee_handle *h) {
-    float *ptrs[] = {h->mu, h->omega, h->alpha, h->m_mu, h->m_omega, h->m_alpha, h->v_mu, h->v_omega, h->v_alpha};
+    float *ptrs[] = {h->mu, h->omega, h->alpha, h->m_mu, h->m_omega, h->m_alpha, h->v_mu, h->v_omega, h->v_alpha, h->mu0_dev};
     for (float *p : ptrs) polee::dfree(p);
-    h->mu = h->omega = h->alpha = h->m_mu = h->m_omega = h->m_alpha = h->v_mu = h->v_omega = h->v_alpha = nullptr;
+    h->mu = h->omega = h->alpha = h->m_mu = h->m_omega = h->m_alpha = h->v_mu = h->v_omega = h->v_alpha = h->mu0_dev = nullptr;
 }
 
 extern "C" int polee_destroy(polee_handle *h) {
     if (!h) return POLEE_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (getenv("POLEE_SETUP_TIMING")) polee::dreport("handle lifetime");
     drop_graph(h);
 #ifdef POLEE_WITH_NCCL
     if (h->comm) nccl_api().CommDestroy(h->comm);
@@ -293,7 +294,7 @@ extern "C" int polee_set_gene_groups(polee_handle *h, int64_t num_genes, const i
 static int alloc_params(polee_handle *h) {
     release_params(h);
     const int64_t nm1 = std::max<int64_t>(h->td.n - 1, 1);
-    float **ptrs[] = {&h->mu, &h->omega, &h->alpha, &h->m_mu, &h->m_omega, &h->m_alpha, &h->v_mu, &h->v_omega, &h->v_alpha};
+    float **ptrs[] = {&h->mu, &h->omega, &h->alpha, &h->m_mu, &h->m_omega, &h->m_alpha, &h->v_mu, &h->v_omega, &h->v_alpha, &h->mu0_dev};
     for (float **p : ptrs) {
         CK(polee::dmalloc((void **)p, sizeof(float) * nm1));
         CK(cudaMemsetAsync(*p, 0, sizeof(float) * nm1, h->stream));
@@ -313,18 +314,41 @@ struct HostPhaseTimer {
     }
 };
 
+// inverse_transform!(t, fill(1.0f0/n, n), ys); map!(logit, mu, ys)   likelihood-approximation.jl:451-453, on the device:
+// fills h->mu0_dev (polee_init_params starts every fit from it)
+static int initial_mu_device(polee_handle *h) {
+    const int64_t n = h->td.n, N = h->td.N;
+    if (n < 2) return POLEE_OK;
+    float *x0 = nullptr;
+    double *us = nullptr, *ys = nullptr;
+    struct Release {
+        float *&a;
+        double *&b, *&c;
+        ~Release() { polee::dfree(a); polee::dfree(b); polee::dfree(c); }
+    } release{x0, us, ys};
+    CK(polee::dmalloc((void **)&x0, sizeof(float) * n));
+    CK(polee::dmalloc((void **)&us, sizeof(double) * N));
+    CK(polee::dmalloc((void **)&ys, sizeof(double) * (n - 1)));
+    int rc = launch_fill_f32(h, x0, n, 1.0f / (float)n);
+    if (!rc) rc = launch_tree_inv(h, 1, x0, us, ys, nullptr, nullptr);
+    if (!rc) rc = launch_init_params(h, ys, 1);
+    cudaError_t e = cudaStreamSynchronize(h->stream);  // the temporaries go back to the cache below
+    if (!rc && e != cudaSuccess) rc = h->fail(POLEE_ECUDA, std::string("initial mu: ") + cudaGetErrorString(e));
+    return rc;
+}
+
 static int finish_tree(polee_handle *h, const std::string &err, HostPhaseTimer &pt) {
     if (!err.empty()) return h->fail(POLEE_EBADTREE, err);
     pt.mark("validate + schedule (host)");
     std::string e2 = upload_tree(h->th, h->td);
     if (!e2.empty()) return h->fail(POLEE_ECUDA, e2);
     pt.mark("upload");
-    h->th.initial_mu(h->mu0);
-    pt.mark("initial mu (host)");
     h->have_tree = true;
     int rc = alloc_params(h);
     if (rc) return rc;
     if ((rc = patch_leaf_records(h))) return rc;
+    if ((rc = initial_mu_device(h))) return rc;
+    pt.mark("initial mu (device)");
     rc = polee_init_params(h);
     pt.mark("params alloc + init");
     return rc;
@@ -367,10 +391,8 @@ extern "C" int polee_init_params(polee_handle *h) {
     if (!h->have_tree) return h->fail(POLEE_EINVAL, "init_params: set the tree first");
     const int64_t nm1 = h->td.n - 1;
     if (nm1 > 0) {
-        std::vector<float> om(nm1, logf(0.1f)), al(nm1, 0.0f);  // likelihood-approximation.jl:455-456
-        CK(polee::copy_sync(h->stream, h->mu, h->mu0.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
-        CK(polee::copy_sync(h->stream, h->omega, om.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
-        CK(polee::copy_sync(h->stream, h->alpha, al.data(), sizeof(float) * nm1, cudaMemcpyHostToDevice));
+        int rc = launch_init_params(h, nullptr, 1);  // mu0, log(0.1f0), 0: likelihood-approximation.jl:451-456
+        if (rc) return rc;
         float *st[] = {h->m_mu, h->m_omega, h->m_alpha, h->v_mu, h->v_omega, h->v_alpha};
         for (float *p : st) CK(cudaMemsetAsync(p, 0, sizeof(float) * nm1, h->stream));
     }
@@ -796,26 +818,29 @@ extern "C" int polee_ptt_transform_gradients(polee_handle *h, const double *ys, 
     return download_kmajor<double, float>(h, h->ygrad, K, KP, h->n - 1, y_grad);
 }
 
-// inverse_transform!  ptt.jl:257-285.  Bottom-up sums are a host-side O(n) sweep per draw: this entry
-// point exists for initialisation and tests, not for the per-step path (the fit never calls it per step).
+// inverse_transform!  ptt.jl:257-285 on the device (k3_tree_inv: level-synchronous bottom-up sums, the reference's
+// association; ladj accumulated in the reference's order)
 extern "C" int polee_ptt_inverse_transform(polee_handle *h, const float *xs, int32_t K, double *ys, double *ladj) {
     CHECK_H(h);
     if (!h->have_tree) return h->fail(POLEE_EINVAL, "no tree: call polee_set_tree first");
-    const TreeHost &t = h->th;
-    std::vector<double> us(t.N);
-    for (int k = 0; k < K; ++k) {
-        double l = 0.0;
-        for (int64_t i = t.N - 1; i >= 0; --i) {
-            const TreeNode &nd = t.nodes[i];
-            if (nd.leaf >= 0) {
-                us[i] = (double)xs[(size_t)k * t.n + nd.leaf];
-            } else {
-                us[i] = us[nd.left] + us[nd.right];
-                l -= (double)logf((float)us[i]);
-                ys[(size_t)k * (t.n - 1) + nd.k] = us[nd.left] / us[i];
-            }
-        }
-        if (ladj) ladj[k] = l;
+    if (!xs || !ys) return h->fail(POLEE_EINVAL, "ptt_inverse_transform: null pointer");
+    h->n = h->td.n;
+    int KP, rc;
+    if ((rc = use_kp(h, K, &KP))) return rc;
+    const int64_t n = h->td.n, nm1 = n - 1;
+    if (nm1 < 1) {
+        if (ladj) for (int k = 0; k < K; ++k) ladj[k] = 0.0;
+        return POLEE_OK;
+    }
+    // work buffers of the step double as scratch: x <- xs, us (by node), ygrad <- ys, zs <- log u, S <- ladj
+    if ((rc = upload_kmajor<float>(h, xs, K, KP, n, h->x, 1.0f))) return rc;
+    if ((rc = launch_tree_inv(h, KP, h->x, h->us, h->ygrad, h->zs, ladj ? h->S : nullptr))) return rc;
+    CK(cudaGetLastError());
+    if ((rc = download_kmajor<double, double>(h, h->ygrad, K, KP, nm1, ys))) return rc;
+    if (ladj) {
+        std::vector<double> l(KP);
+        CK(polee::copy_sync(h->stream, l.data(), h->S, sizeof(double) * KP, cudaMemcpyDeviceToHost));
+        std::copy(l.begin(), l.begin() + K, ladj);
     }
     return POLEE_OK;
 }

@@ -174,6 +174,18 @@ constexpr int PATH_GROUP = 128;                  // nodes per path group (one CT
 constexpr int PATH_SLOTS = 32;                   // node slots per CTA (threads = PATH_SLOTS x KP, PATH_GROUP / PATH_SLOTS nodes each)
 constexpr int PATH_MAX_GANC = 1024;              // distinct ancestors a group may have
 
+// DFS-run forward kernel (k3d_tree_fwd): a thread walks DFS_RUN consecutive nodes of a tree stored in DFS pre-order
+constexpr int DFS_RUN = 64;            // nodes per thread
+constexpr int DFS_RUNS_PER_CTA = 16;   // runs per CTA (threads = DFS_RUNS_PER_CTA x KP)
+constexpr int DFS_CTA_NODES = DFS_RUN * DFS_RUNS_PER_CTA;
+constexpr int DFS_MAX_DEPTH = 96;      // deeper trees keep the path-product / level kernels
+struct DNode {
+    int32_t k_or_leaf;  // >= 0: internal node, index k; < 0: leaf, transcript = -1 - v
+    uint32_t meta;      // depth | (1u << 31 if the node is its parent's LEFT child, i.e. the child that comes second)
+    float efflen;       // leaves: the transcript's effective length (patched in once the lengths are known)
+    uint32_t pad;
+};
+
 // Tree node, 0-based; leaf < 0 <=> internal node (then k = index among internal nodes in node order).
 struct TreeNode {
     int32_t left, right, k, leaf;
@@ -233,12 +245,18 @@ struct TreeHost {
     std::vector<uint32_t> ganc_ptr, ganc, gcp, nsuf_ptr;
     std::vector<uint16_t> nsuf;
     int max_ganc = 0, max_gsuf = 0;  // most distinct ancestors / suffix entries of a group
+    // DFS-run forward (trees in DFS pre-order, the order order_nodes emits, src/hclust.jl:361-389; then the root paths
+    // above are not built): per node a DNode; per run of DFS_RUN nodes the ancestors of its first node, root first, as
+    // (k << 1) | 1 if the path continues into the LEFT child; per CTA the number of internal nodes before its first node
+    bool preorder = false;
+    std::vector<DNode> dnodes;
+    std::vector<uint32_t> drun_anc_ptr, drun_anc;
+    std::vector<int32_t> dcta_k0;
+    int dfs_max_nk = 0;
     // returns "" or an error text
     std::string build_from_lrf(int64_t n, const int32_t *left, const int32_t *right, const int32_t *leaf,
                                int bin_nodes);
     std::string build_from_parents(int64_t n, const int32_t *parent_idxs, const int32_t *js, int bin_nodes);
-    // inverse_transform!(t, fill(1f0/n, n), ys) -> mu = Float32(logit(ys))  (likelihood-approximation.jl:451-453)
-    void initial_mu(std::vector<float> &mu) const;
 };
 
 struct TreeDev {
@@ -253,6 +271,10 @@ struct TreeDev {
     uint32_t *ganc_ptr = nullptr, *ganc = nullptr, *gcp = nullptr, *nsuf_ptr = nullptr;  // root paths (nullptr: not built)
     uint16_t *nsuf = nullptr;
     int n_groups = 0, max_ganc = 0, max_gsuf = 0;
+    DNode *dnodes = nullptr;  // DFS-run forward (nullptr: not available for this tree)
+    uint32_t *drun_anc_ptr = nullptr, *drun_anc = nullptr;
+    int32_t *dcta_k0 = nullptr;
+    int dfs_ctas = 0, dfs_max_nk = 0, max_depth = 0;
     void release();
 };
 
@@ -349,7 +371,7 @@ struct polee_handle {
     polee::TreeHost th;
     polee::TreeDev td;
     bool have_tree = false;
-    std::vector<float> mu0;
+    float *mu0_dev = nullptr;  // mu the fit starts from (inverse_transform! of the uniform composition), [n-1]
 
     // ---- parameters / ADAM state: [n-1] each
     float *mu = nullptr, *omega = nullptr, *alpha = nullptr;
@@ -440,6 +462,7 @@ cudaError_t dmalloc(void **p, size_t bytes);
 cudaError_t dfree(void *p);
 void dtrim(int device);  // -1 = every device
 size_t dcached_bytes(int device);
+void dreport(const char *what);  // POLEE_SETUP_TIMING: allocator statistics since the last report, to stderr
 
 // matrix_setup.cu
 int setup_matrix_from_device_csc(polee_handle *h, int64_t m, int64_t n, const uint32_t *d_colptr,
@@ -487,6 +510,9 @@ void release_work_buffers(polee_handle *h);
 int launch_reparam_fwd(polee_handle *h, int KP, int K, const float *noise, int64_t noise_steps, int want_ladj);
 int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_ladj);
 int launch_mid(polee_handle *h, int KP, int advance, cudaStream_t st = nullptr);
+int launch_tree_inv(polee_handle *h, int KP, const float *x_dev, double *us_tmp, double *ys_out, float *logu_tmp, double *ladj_out);
+int launch_init_params(polee_handle *h, const double *ys0, int KP);
+int launch_fill_f32(polee_handle *h, float *p, int64_t count, float v);
 int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, double *xgrad_out);
 int launch_update(polee_handle *h, int KP, int K, bool do_adam, float *grad_out);
 int launch_elem(polee_handle *h, int KP, int K, bool do_update, bool do_adam, bool do_reparam, const float *noise,

@@ -25,6 +25,11 @@ struct polee_hsb_plan {
     int nbins[2] = {0, 0};
     int32_t *desc_order = nullptr;  // [ntrees][n-1] internal node ids in descending node order (ladj emulation)
     std::string err;
+    // scratch of the device-resident entry points (u, v / log u per row), grown on demand and kept with the plan so a
+    // training step allocates nothing; calls on one plan are serialised by `mu`
+    mutable std::mutex mu;
+    mutable double *scr[2] = {nullptr, nullptr};
+    mutable size_t scr_count[2] = {0, 0};
 };
 
 namespace {
@@ -106,15 +111,54 @@ __global__ void __launch_bounds__(HSB_THREADS)
     }
 }
 
-// `ladj_i[0] -= log(u_data[j])` for j = 2n-2 .. 0 with a FLOAT accumulator (hsb_ops.cpp:211,234):
-// the rounding sequence is order dependent, so it is replayed serially, one thread per row.
-__global__ void k4_ladj_serial(int64_t B, int64_t nm1, const double *__restrict__ logu, float *__restrict__ ladj) {
-    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+// `ladj_i[0] -= log(u_data[j])` for j = 2n-2 .. 0 with a FLOAT accumulator (hsb_ops.cpp:211,234): every step rounds,
+// acc <- Float32(Float64(acc) - log u), so the result depends on the order and the chain cannot simply be re-associated.
+// It can be SPECULATED, though: while acc stays in one binade (and no step is an exact tie) a step moves acc by a whole
+// number of its ulps, q_k = rint(-log u_k / ulp), whatever acc is.  One warp per row takes 32 steps at a time: the lanes
+// form q_k, a shuffle scan gives the 32 candidate values, and every lane then checks ITS step with the reference's own
+// rule from its predecessor's candidate.  The steps before the first mismatch are exact by induction; the mismatching
+// step (a binade change, a tie, acc == 0, non-finite values) is redone by the scalar rule, and the warp goes on from there.
+__global__ void __launch_bounds__(128) k4_ladj_chain(int64_t B, int64_t nm1, const double *__restrict__ logu, float *__restrict__ ladj) {
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (row >= B) return;
-    float acc = 0.0f;
     const double *lu = logu + (size_t)row * nm1;
-    for (int64_t k = nm1 - 1; k >= 0; --k) acc = (float)__dsub_rn((double)acc, lu[k]);
-    ladj[row] = acc;
+    float acc = 0.0f;
+    int64_t k = nm1 - 1;  // next step (descending, as the reference's loop)
+    // the next 32 values are requested before the current ones are used: a chunk that verifies completely (the normal
+    // case) never waits for memory
+    double l_next = (k - lane >= 0) ? lu[k - lane] : 0.0;
+    while (k >= 0) {
+        const int cnt = k + 1 < 32 ? (int)(k + 1) : 32;
+        const double l = l_next;
+        l_next = (k - 32 - lane >= 0) ? lu[k - 32 - lane] : 0.0;
+        int e = 0;
+        (void)frexpf(fabsf(acc), &e);  // |acc| = f 2^e, f in [0.5, 1): ulp(acc) = 2^(e - 24)
+        const bool fin = acc != 0.0f && isfinite(acc);
+        const double ulp = fin ? ldexp(1.0, e - 24) : 0.0, inv_ulp = fin ? ldexp(1.0, 24 - e) : 0.0;
+        double P = lane < cnt ? rint(-l * inv_ulp) : 0.0;  // this step in ulps (a power-of-two scaling: exact); then the scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, P, o);
+            if (lane >= o) P += t;
+        }
+        const float cand = (float)((double)acc + ulp * P);
+        float pred = __shfl_up_sync(0xffffffffu, cand, 1);
+        if (lane == 0) pred = acc;
+        const bool ok = lane >= cnt || (float)__dsub_rn((double)pred, l) == cand;  // the reference's step, exactly
+        const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+        const int f = bad ? __ffs((int)bad) - 1 : 32;  // first step that did not verify
+        if (f > 0) acc = __shfl_sync(0xffffffffu, cand, f - 1);
+        int done = f < cnt ? f : cnt;
+        if (f < cnt) {
+            const double lf = __shfl_sync(0xffffffffu, l, f);
+            acc = (float)__dsub_rn((double)acc, lf);
+            ++done;
+        }
+        k -= done;
+        if (done != 32 && k >= 0) l_next = (k - lane >= 0) ? lu[k - lane] : 0.0;  // the prefetch assumed a full chunk
+    }
+    if (lane == 0) ladj[row] = acc;
 }
 
 // InvHSBGradOp::Compute  hsb_ops.cpp:338-392 (top-down)
@@ -197,6 +241,7 @@ int polee_hsb_plan_destroy(polee_hsb_plan *p) {
     cudaSetDevice(p->device);
     polee::dfree(p->nodes);
     polee::dfree(p->desc_order);
+    polee::dfree(p->scr[0]); polee::dfree(p->scr[1]);
     for (int s = 0; s < 2; ++s) {
         polee::dfree(p->bin_lvl_ptr[s]); polee::dfree(p->lvl_off[s]); polee::dfree(p->sch_node[s]); polee::dfree(p->bin_tree[s]);
     }
@@ -266,22 +311,90 @@ static Sched sched_of(const polee_hsb_plan *p, int s) {
     return Sched{p->bin_lvl_ptr[s], p->lvl_off[s], p->sch_node[s], p->bin_tree[s]};
 }
 
-int polee_hsb_with_plan(const polee_hsb_plan *p, int64_t B, const float *y_logit, float *x) {
+static int plan_scratch(const polee_hsb_plan *p, int which, size_t count, double **out) {
+    if (p->scr_count[which] < count) {
+        HCK(cudaDeviceSynchronize());  // an earlier call on another stream may still use the old block
+        polee::dfree(p->scr[which]);
+        p->scr[which] = nullptr;
+        p->scr_count[which] = 0;
+        HCK(polee::dmalloc((void **)&p->scr[which], count * sizeof(double)));
+        p->scr_count[which] = count;
+    }
+    *out = p->scr[which];
+    return POLEE_OK;
+}
+
+// ---- device-resident forms: tensors already in device memory, work enqueued on the caller's stream (what a TF
+// DEVICE_GPU kernel has: hsb_ops.cpp:120, 249, 402 register the ops for DEVICE_CPU only)
+int polee_hsb_device(const polee_hsb_plan *p, int64_t B, const float *d_y_logit, float *d_x, void *stream) {
     int rc = check_plan(p, B);
     if (rc) return rc;
+    if (!d_y_logit || !d_x) return hsb_fail(POLEE_EINVAL, "hsb: null pointer");
+    std::lock_guard<std::mutex> lk(p->mu);
+    cudaStream_t st = (cudaStream_t)stream;
     const int shared = p->ntrees == 1;
-    DevBuf db;
-    float *d_yl, *d_x;
     double *d_us;
-    HCK(db.upload(&d_yl, y_logit, (size_t)B * (p->n - 1)));
-    HCK(db.alloc(&d_x, (size_t)B * p->n));
-    HCK(db.alloc(&d_us, (size_t)B * p->N));
+    if ((rc = plan_scratch(p, 0, (size_t)B * p->N, &d_us))) return rc;
     for (int s = 0; s < 2; ++s)
         if (p->nbins[s] > 0) {
             dim3 grid(p->nbins[s], shared ? (unsigned)B : 1u);
-            k4_hsb_fwd<<<grid, HSB_THREADS>>>(sched_of(p, s), shared, p->nodes, p->n, p->N, d_yl, d_us, d_x);
+            k4_hsb_fwd<<<grid, HSB_THREADS, 0, st>>>(sched_of(p, s), shared, p->nodes, p->n, p->N, d_y_logit, d_us, d_x);
         }
     HCK(cudaGetLastError());
+    return POLEE_OK;
+}
+
+int polee_inv_hsb_device(const polee_hsb_plan *p, int64_t B, const float *d_x, double *d_y, float *d_ladj, void *stream) {
+    int rc = check_plan(p, B);
+    if (rc) return rc;
+    if (!d_x || !d_y || !d_ladj) return hsb_fail(POLEE_EINVAL, "inv_hsb: null pointer");
+    std::lock_guard<std::mutex> lk(p->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int shared = p->ntrees == 1;
+    const int64_t nm1 = p->n - 1;
+    double *d_us, *d_logu;
+    if ((rc = plan_scratch(p, 0, (size_t)B * p->N, &d_us))) return rc;
+    if ((rc = plan_scratch(p, 1, (size_t)B * p->N, &d_logu))) return rc;
+    for (int s = 1; s >= 0; --s)  // bottom bins first, then the top
+        if (p->nbins[s] > 0) {
+            dim3 grid(p->nbins[s], shared ? (unsigned)B : 1u);
+            k4_inv_hsb<<<grid, HSB_THREADS, 0, st>>>(sched_of(p, s), shared, p->nodes, p->n, p->N, d_x, d_us, d_y, d_logu);
+        }
+    k4_ladj_chain<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(B, nm1, d_logu, d_ladj);  // one warp per row
+    HCK(cudaGetLastError());
+    return POLEE_OK;
+}
+
+int polee_inv_hsb_grad_device(const polee_hsb_plan *p, int64_t B, const double *d_y_grad, const float *d_ladj_grad,
+                              const double *d_y, float *d_backprops, void *stream) {
+    int rc = check_plan(p, B);
+    if (rc) return rc;
+    if (!d_y_grad || !d_ladj_grad || !d_y || !d_backprops) return hsb_fail(POLEE_EINVAL, "inv_hsb_grad: null pointer");
+    std::lock_guard<std::mutex> lk(p->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int shared = p->ntrees == 1;
+    double *d_us, *d_vs;
+    if ((rc = plan_scratch(p, 0, (size_t)B * p->N, &d_us))) return rc;
+    if ((rc = plan_scratch(p, 1, (size_t)B * p->N, &d_vs))) return rc;
+    for (int s = 0; s < 2; ++s)
+        if (p->nbins[s] > 0) {
+            dim3 grid(p->nbins[s], shared ? (unsigned)B : 1u);
+            k4_inv_hsb_grad<<<grid, HSB_THREADS, 0, st>>>(sched_of(p, s), shared, p->nodes, p->n, p->N, d_y_grad, d_ladj_grad, d_y,
+                                                          d_us, d_vs, d_backprops);
+        }
+    HCK(cudaGetLastError());
+    return POLEE_OK;
+}
+
+// ---- host-tensor forms (the DEVICE_CPU registration of the shim): upload, the device form on the legacy stream, download
+int polee_hsb_with_plan(const polee_hsb_plan *p, int64_t B, const float *y_logit, float *x) {
+    int rc = check_plan(p, B);
+    if (rc) return rc;
+    DevBuf db;
+    float *d_yl, *d_x;
+    HCK(db.upload(&d_yl, y_logit, (size_t)B * (p->n - 1)));
+    HCK(db.alloc(&d_x, (size_t)B * p->n));
+    if ((rc = polee_hsb_device(p, B, d_yl, d_x, nullptr))) return rc;
     HCK(cudaMemcpy(x, d_x, sizeof(float) * (size_t)B * p->n, cudaMemcpyDeviceToHost));
     return POLEE_OK;
 }
@@ -289,23 +402,14 @@ int polee_hsb_with_plan(const polee_hsb_plan *p, int64_t B, const float *y_logit
 int polee_inv_hsb_with_plan(const polee_hsb_plan *p, int64_t B, const float *x, double *y, float *ladj) {
     int rc = check_plan(p, B);
     if (rc) return rc;
-    const int shared = p->ntrees == 1;
     const int64_t nm1 = p->n - 1;
     DevBuf db;
     float *d_x, *d_ladj;
-    double *d_us, *d_y, *d_logu;
+    double *d_y;
     HCK(db.upload(&d_x, x, (size_t)B * p->n));
-    HCK(db.alloc(&d_us, (size_t)B * p->N));
     HCK(db.alloc(&d_y, (size_t)B * nm1));
-    HCK(db.alloc(&d_logu, (size_t)B * nm1));
     HCK(db.alloc(&d_ladj, (size_t)B));
-    for (int s = 1; s >= 0; --s)  // bottom bins first, then the top
-        if (p->nbins[s] > 0) {
-            dim3 grid(p->nbins[s], shared ? (unsigned)B : 1u);
-            k4_inv_hsb<<<grid, HSB_THREADS>>>(sched_of(p, s), shared, p->nodes, p->n, p->N, d_x, d_us, d_y, d_logu);
-        }
-    k4_ladj_serial<<<(unsigned)((B + 63) / 64), 64>>>(B, nm1, d_logu, d_ladj);
-    HCK(cudaGetLastError());
+    if ((rc = polee_inv_hsb_device(p, B, d_x, d_y, d_ladj, nullptr))) return rc;
     if (nm1 > 0) HCK(cudaMemcpy(y, d_y, sizeof(double) * (size_t)B * nm1, cudaMemcpyDeviceToHost));
     HCK(cudaMemcpy(ladj, d_ladj, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost));
     return POLEE_OK;
@@ -315,24 +419,15 @@ int polee_inv_hsb_grad_with_plan(const polee_hsb_plan *p, int64_t B, const doubl
                                  const double *y, float *backprops) {
     int rc = check_plan(p, B);
     if (rc) return rc;
-    const int shared = p->ntrees == 1;
     const int64_t nm1 = p->n - 1;
     DevBuf db;
-    double *d_yg, *d_y, *d_us, *d_vs;
+    double *d_yg, *d_y;
     float *d_lg, *d_bp;
     HCK(db.upload(&d_yg, y_grad, (size_t)B * nm1));
     HCK(db.upload(&d_y, y, (size_t)B * nm1));
     HCK(db.upload(&d_lg, ladj_grad, (size_t)B));
-    HCK(db.alloc(&d_us, (size_t)B * p->N));
-    HCK(db.alloc(&d_vs, (size_t)B * p->N));
     HCK(db.alloc(&d_bp, (size_t)B * p->n));
-    for (int s = 0; s < 2; ++s)
-        if (p->nbins[s] > 0) {
-            dim3 grid(p->nbins[s], shared ? (unsigned)B : 1u);
-            k4_inv_hsb_grad<<<grid, HSB_THREADS>>>(sched_of(p, s), shared, p->nodes, p->n, p->N, d_yg, d_lg, d_y, d_us,
-                                                   d_vs, d_bp);
-        }
-    HCK(cudaGetLastError());
+    if ((rc = polee_inv_hsb_grad_device(p, B, d_yg, d_lg, d_y, d_bp, nullptr))) return rc;
     HCK(cudaMemcpy(backprops, d_bp, sizeof(float) * (size_t)B * p->n, cudaMemcpyDeviceToHost));
     return POLEE_OK;
 }

@@ -13,6 +13,8 @@
 //   * polee_trim_memory() returns everything to the driver; POLEE_NO_CACHE=1 turns the cache off.
 #include "common.cuh"
 
+#include <chrono>
+#include <cstdio>
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -30,6 +32,9 @@ std::mutex g_mu;
 std::unordered_map<void *, Live> g_live;                 // blocks handed out
 std::map<int, std::multimap<size_t, void *>> g_free;     // device -> size -> cached block
 std::map<int, size_t> g_cached_bytes;
+// POLEE_SETUP_TIMING: what the driver allocator cost since the last report
+size_t g_stat_calls = 0, g_stat_bytes = 0, g_stat_hits = 0;
+double g_stat_seconds = 0.0;
 
 }  // namespace
 
@@ -79,12 +84,17 @@ cudaError_t dmalloc(void **p, size_t bytes) {
             g_live[*p] = Live{it->first, device};
             g_cached_bytes[device] -= it->first;
             fl.erase(it);
+            ++g_stat_hits;
             return cudaSuccess;
         }
     }
     {
         std::unique_lock<std::shared_mutex> cap(capture_mutex());
+        const auto t0 = std::chrono::steady_clock::now();
         e = cudaMalloc(p, want);
+        g_stat_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        ++g_stat_calls;
+        g_stat_bytes += want;
     }
     if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();  // clear the sticky-free error, release the cache, retry once
@@ -126,6 +136,14 @@ cudaError_t dfree(void *p) {
 void dtrim(int device) {
     std::lock_guard<std::mutex> lk(g_mu);
     trim_locked(device);
+}
+
+void dreport(const char *what) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    fprintf(stderr, "[polee alloc] %-28s cudaMalloc: %zu calls, %.3f GB, %.1f ms; served from the cache: %zu\n", what, g_stat_calls,
+            g_stat_bytes / 1e9, g_stat_seconds * 1e3, g_stat_hits);
+    g_stat_calls = g_stat_bytes = g_stat_hits = 0;
+    g_stat_seconds = 0.0;
 }
 
 size_t dcached_bytes(int device) {

@@ -93,10 +93,49 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
     }
     for (int64_t i = N - 1; i >= 1; --i) size[parent[i]] += size[i];
 
-    // ---- root -> node paths, grouped (see TreeHost)
+    // ---- DFS pre-order?  (right child = next node, left child = the node after the right subtree)
+    preorder = n >= 2 && max_depth <= DFS_MAX_DEPTH;
+    for (int64_t i = 0; i < N && preorder; ++i)
+        if (nodes[i].leaf < 0) preorder = nodes[i].right == i + 1 && nodes[i].left == i + 1 + size[i + 1];
+    dnodes.clear(); drun_anc_ptr.clear(); drun_anc.clear(); dcta_k0.clear();
+    dfs_max_nk = 0;
+    if (preorder) {
+        dnodes.resize(N);
+        for (int64_t i = 0; i < N; ++i) {
+            const bool is_left = i > 0 && nodes[parent[i]].left == (int32_t)i;
+            dnodes[i].k_or_leaf = nodes[i].leaf >= 0 ? -1 - nodes[i].leaf : nodes[i].k;
+            dnodes[i].meta = (uint32_t)depth[i] | (is_left ? 0x80000000u : 0u);
+            dnodes[i].efflen = 1.0f;
+            dnodes[i].pad = 0u;
+        }
+        const int64_t nruns = (N + DFS_RUN - 1) / DFS_RUN;
+        drun_anc_ptr.reserve(nruns + 1);
+        std::vector<uint32_t> path;
+        for (int64_t r = 0; r < nruns; ++r) {
+            drun_anc_ptr.push_back((uint32_t)drun_anc.size());
+            path.clear();
+            for (int32_t v = (int32_t)(r * DFS_RUN); parent[v] >= 0; v = parent[v])
+                path.push_back(((uint32_t)nodes[parent[v]].k << 1) | (nodes[parent[v]].left == v ? 1u : 0u));
+            drun_anc.insert(drun_anc.end(), path.rbegin(), path.rend());
+        }
+        drun_anc_ptr.push_back((uint32_t)drun_anc.size());
+        const int64_t nctas = (N + DFS_CTA_NODES - 1) / DFS_CTA_NODES;
+        dcta_k0.reserve(nctas + 1);
+        int32_t kc = 0;
+        for (int64_t i = 0; i < N; ++i) {
+            if (i % DFS_CTA_NODES == 0) dcta_k0.push_back(kc);
+            if (nodes[i].leaf < 0) ++kc;
+        }
+        dcta_k0.push_back(kc);
+        for (int64_t c = 0; c < nctas; ++c) dfs_max_nk = std::max(dfs_max_nk, dcta_k0[c + 1] - dcta_k0[c]);
+    }
+
+    // ---- root -> node paths, grouped (see TreeHost); not needed when the DFS-run kernel serves the tree
     ganc_ptr.clear(); ganc.clear(); gcp.clear(); nsuf_ptr.clear(); nsuf.clear();
     max_ganc = max_gsuf = 0;
-    {
+    static const bool dfs_off = getenv("POLEE_TREE_FWD") && strcmp(getenv("POLEE_TREE_FWD"), "dfs") != 0;
+    if (dfs_off) { preorder = false; dnodes.clear(); drun_anc_ptr.clear(); drun_anc.clear(); dcta_k0.clear(); }
+    if (!preorder) {
         int64_t total = 0;
         for (int64_t i = 0; i < N; ++i) total += depth[i];
         bool ok = total <= PATH_MAX_ENTRIES && n >= 2;
@@ -311,24 +350,6 @@ std::string TreeHost::build_from_parents(int64_t n_, const int32_t *parent_idxs,
     return build_from_lrf(n_, l.data(), r.data(), f.data(), bin_nodes);
 }
 
-// inverse_transform!(t, fill(1.0f0/n, n), ys); map!(logit, mu, ys)   likelihood-approximation.jl:451-453
-// (us = Float64 sums of Float64(1f0/n) in the reference's bottom-up order, ptt.jl:257-285)
-void TreeHost::initial_mu(std::vector<float> &mu) const {
-    std::vector<double> us(N);
-    mu.assign(n > 1 ? n - 1 : 0, 0.0f);
-    const double leafv = (double)(1.0f / (float)n);
-    for (int64_t i = N - 1; i >= 0; --i) {
-        const TreeNode &nd = nodes[i];
-        if (nd.leaf >= 0) {
-            us[i] = leafv;
-        } else {
-            us[i] = us[nd.left] + us[nd.right];
-            double y = us[nd.left] / us[i];
-            mu[nd.k] = (float)std::log(y / (1.0 - y));
-        }
-    }
-}
-
 void TreeDev::release() {
     polee::dfree(nodes);
     for (TreeSchedDev *s : {&top, &bottom}) {
@@ -343,6 +364,9 @@ void TreeDev::release() {
     polee::dfree(ganc_ptr); polee::dfree(ganc); polee::dfree(gcp); polee::dfree(nsuf_ptr); polee::dfree(nsuf);
     ganc_ptr = ganc = gcp = nsuf_ptr = nullptr;
     nsuf = nullptr;
+    polee::dfree(dnodes); polee::dfree(drun_anc_ptr); polee::dfree(drun_anc); polee::dfree(dcta_k0);
+    dnodes = nullptr; drun_anc_ptr = drun_anc = nullptr; dcta_k0 = nullptr;
+    dfs_ctas = dfs_max_nk = 0;
     n_groups = max_ganc = max_gsuf = 0;
     for (SSchedDev *s : {&s_top, &s_bottom}) {
         polee::dfree(s->bin_off);
@@ -425,6 +449,21 @@ std::string upload_tree(const TreeHost &th, TreeDev &td) {
         td.n_groups = (int)th.gcp.size();
         td.max_ganc = th.max_ganc;
         td.max_gsuf = th.max_gsuf;
+    }
+    td.max_depth = th.max_depth;
+    if (e == cudaSuccess && th.preorder) {
+        auto upv = [&](const void *src, size_t bytes, void **dst) {
+            cudaError_t ee = polee::dmalloc(dst, std::max<size_t>(bytes, 4));
+            if (ee == cudaSuccess && bytes) ee = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+            return ee;
+        };
+        e = upv(th.dnodes.data(), sizeof(DNode) * th.dnodes.size(), (void **)&td.dnodes);
+        if (e == cudaSuccess) e = upv(th.drun_anc_ptr.data(), 4 * th.drun_anc_ptr.size(), (void **)&td.drun_anc_ptr);
+        if (e == cudaSuccess) e = upv(th.drun_anc.data(), 4 * th.drun_anc.size(), (void **)&td.drun_anc);
+        if (e == cudaSuccess) e = upv(th.dcta_k0.data(), 4 * th.dcta_k0.size(), (void **)&td.dcta_k0);
+        td.dfs_ctas = (int)th.dcta_k0.size() - 1;
+        td.dfs_max_nk = th.dfs_max_nk;
+        td.n_groups = std::max(td.n_groups, td.dfs_ctas);  // sizes the per-CTA partial sums (S, ladj)
     }
     td.n_slots = th.n_slots;
     td.caterpillar = th.caterpillar;

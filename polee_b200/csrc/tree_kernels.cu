@@ -28,7 +28,7 @@ namespace polee {
 namespace {
 
 constexpr int TREE_THREADS = 256;
-constexpr int ELEM_THREADS = 128;  // k3_elem: one thread per internal node; small CTAs keep the tail wave short
+constexpr int ELEM_THREADS = 256;  // k3_elem: one lane per (internal node, draw)
 constexpr int TOP_THREADS = 1024;
 
 // ---------------------------------------------------------------- noise ("polee-philox-v1")
@@ -179,6 +179,92 @@ __global__ void __launch_bounds__(THREADS)
         }
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------- inverse transform
+// inverse_transform! (src/ptt.jl:257-285): u_i = x_leaf at a leaf, u_left + u_right at an internal node (one Float64
+// add per node, the association the reference's descending-index sweep has, so the same bits), y_k = u_left / u_i and
+// logu_k = log(Float32(u_i)).  Level-synchronous from the deepest level up, one CTA per schedule bin (bottom forests,
+// then the top part).  us is indexed by node here.
+template <int KP, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    k3_tree_inv(const int32_t *__restrict__ bin_lvl_ptr, const int32_t *__restrict__ lvl_off,
+                const int32_t *__restrict__ sch_node, const TreeNode *__restrict__ nodes, const float *__restrict__ x,
+                double *__restrict__ us, double *__restrict__ ys, float *__restrict__ logu) {
+    const int k = threadIdx.x % KP, slot = threadIdx.x / KP;
+    constexpr int NPP = THREADS / KP;
+    const int l0 = bin_lvl_ptr[blockIdx.x], l1 = bin_lvl_ptr[blockIdx.x + 1] - 1;
+    for (int l = l1 - 1; l >= l0; --l) {
+        const int lo = lvl_off[l], hi = lvl_off[l + 1];
+        for (int q = lo + slot; q < hi; q += NPP) {
+            const int node = sch_node[q];
+            const TreeNode nd = nodes[node];
+            if (nd.leaf >= 0) {
+                us[(size_t)node * KP + k] = (double)x[(size_t)nd.leaf * KP + k];
+            } else {
+                const double ul = us[(size_t)nd.left * KP + k], ur = us[(size_t)nd.right * KP + k];
+                const double ui = __dadd_rn(ul, ur);
+                us[(size_t)node * KP + k] = ui;
+                ys[(size_t)nd.k * KP + k] = __ddiv_rn(ul, ui);
+                if (logu) logu[(size_t)nd.k * KP + k] = logf((float)ui);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// The same sweep for caterpillar (:sequential) trees, whose depth is n: one thread per draw walks the nodes in the
+// reference's own order (descending index), children before parents by construction of the node order.
+__global__ void k3_tree_inv_serial(int64_t N, int KP, const TreeNode *__restrict__ nodes, const float *__restrict__ x,
+                                   double *us, double *__restrict__ ys, float *__restrict__ logu) {
+    const int k = threadIdx.x;
+    if (k >= KP) return;
+    for (int64_t i = N - 1; i >= 0; --i) {
+        const TreeNode nd = nodes[i];
+        if (nd.leaf >= 0) {
+            us[(size_t)i * KP + k] = (double)x[(size_t)nd.leaf * KP + k];
+        } else {
+            const double ul = us[(size_t)nd.left * KP + k], ur = us[(size_t)nd.right * KP + k];
+            const double ui = __dadd_rn(ul, ur);
+            us[(size_t)i * KP + k] = ui;
+            ys[(size_t)nd.k * KP + k] = __ddiv_rn(ul, ui);
+            if (logu) logu[(size_t)nd.k * KP + k] = logf((float)ui);
+        }
+    }
+}
+
+// ladj = - sum_k log(Float32(u_k)), a Float64 accumulator fed in the reference's order (descending node index =
+// descending k, ptt.jl:265-281): one thread per draw, the loads do not depend on the chain of adds
+__global__ void k3_inv_ladj(int64_t nm1, int KP, const float *__restrict__ logu, double *__restrict__ ladj) {
+    const int k = threadIdx.x;
+    if (k >= KP) return;
+    double l = 0.0;
+#pragma unroll 8
+    for (int64_t i = nm1 - 1; i >= 0; --i) l = __dsub_rn(l, (double)logu[(size_t)i * KP + k]);
+    ladj[k] = l;
+}
+
+__global__ void k3_fill_f32(float *__restrict__ p, int64_t count, float v) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < count) p[i] = v;
+}
+
+// mu = Float32(logit(y)) in Float64 (map!(logit, mu, ys), likelihood-approximation.jl:453), omega = log(0.1f0), alpha = 0
+__global__ void k3_init_params(int64_t nm1, int KP, const double *__restrict__ ys, float omega0, float *__restrict__ mu0,
+                               float *__restrict__ mu, float *__restrict__ omega, float *__restrict__ alpha) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nm1) return;
+    float v;
+    if (ys) {
+        const double y = ys[(size_t)i * KP];
+        v = (float)log(__ddiv_rn(y, __dsub_rn(1.0, y)));
+        mu0[i] = v;
+    } else {
+        v = mu0[i];
+    }
+    mu[i] = v;
+    omega[i] = omega0;
+    alpha[i] = 0.0f;
 }
 
 // ================================================================ shared-memory tree kernels
@@ -482,6 +568,109 @@ __global__ void __launch_bounds__(PATH_SLOTS *KP, 2048 / (PATH_SLOTS * KP) > 16 
     if (want_ladj) block_reduce_kc<KP, THREADS>(lacc, red, ladj_partial + (size_t)blockIdx.x * KP);
 }
 
+// transform! (src/ptt.jl:125-158) for trees stored in DFS pre-order (what order_nodes emits: a node, its right subtree,
+// its left subtree): a thread = (run of DFS_RUN consecutive nodes, one draw) walks its nodes in index order exactly as
+// the reference's sweep does.  At an internal node it forms both children's u (the reference's two multiplications): the
+// right child is the next node and takes its value from a register, the left child's value waits in a per-thread stack
+// indexed by depth (shared memory, [depth][thread]: conflict-free) until the walk comes back to it.  The stack a run
+// starts with is what the serial sweep would hold there: the thread multiplies down the root path of its first node
+// (ancestor list prepared on the host) and parks the left values of the ancestors it passes on the right.  Every u is
+// therefore the reference's product chain from the root -- the same bits -- at ~20 instructions per node instead of a
+// path product per node, with no levels, no barriers between levels and no exchange between kernels.  The CTA's nodes and
+// the y of its internal nodes (consecutive k: one contiguous slice of ys) are staged in shared memory by coalesced loads.
+template <int KP>
+__global__ void __launch_bounds__(DFS_RUNS_PER_CTA *KP)
+    k3d_tree_fwd(int64_t N, const DNode *__restrict__ dnodes, const uint32_t *__restrict__ run_anc_ptr,
+                 const uint32_t *__restrict__ run_anc, const int32_t *__restrict__ cta_k0, const double *__restrict__ ys,
+                 double *__restrict__ us_k, float *__restrict__ x, double *__restrict__ xd, int clamp_x,
+                 const float *__restrict__ efflen, double *__restrict__ S_partial, int want_ladj,
+                 double *__restrict__ ladj_partial, int stack_levels, int max_nk) {
+    constexpr int THREADS = DFS_RUNS_PER_CTA * KP, RS = DFS_RUN + 1;  // record stride of a run (odd: no bank conflicts)
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ double red[THREADS];
+    double *stack = reinterpret_cast<double *>(smraw);                      // [stack_levels][THREADS]
+    double *ys_s = stack + (size_t)stack_levels * THREADS;                  // [max_nk][KP]
+    DNode *rec_s = reinterpret_cast<DNode *>(ys_s + (size_t)max_nk * KP);   // [DFS_RUNS_PER_CTA][RS]
+    const int k = threadIdx.x % KP, rl = threadIdx.x / KP;
+    const int64_t c0 = (int64_t)blockIdx.x * DFS_CTA_NODES;
+    const int nn = (int)(N - c0 < DFS_CTA_NODES ? N - c0 : DFS_CTA_NODES);
+    const int k0 = cta_k0[blockIdx.x], nk = cta_k0[blockIdx.x + 1] - k0;
+    // ---- stage the CTA's y slice and node records (coalesced)
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(ys + (size_t)k0 * KP);  // k0 KP doubles: 16-byte aligned for KP >= 2
+        double2 *dst = reinterpret_cast<double2 *>(ys_s);
+        const int nv = KP >= 2 ? nk * KP / 2 : 0;
+#pragma unroll 4
+        for (int idx = threadIdx.x; idx < nv; idx += THREADS) dst[idx] = src[idx];
+        if (KP < 2)
+            for (int idx = threadIdx.x; idx < nk * KP; idx += THREADS) ys_s[idx] = ys[(size_t)k0 * KP + idx];
+        const int4 *rsrc = reinterpret_cast<const int4 *>(dnodes + c0);
+        int4 *rdst = reinterpret_cast<int4 *>(rec_s);
+#pragma unroll 4
+        for (int idx = threadIdx.x; idx < nn; idx += THREADS) rdst[(idx / DFS_RUN) * RS + idx % DFS_RUN] = rsrc[idx];
+    }
+    // ---- the run's starting state: down the root path of its first node
+    const int64_t i0 = c0 + (int64_t)rl * DFS_RUN;
+    const int cnt = i0 < N ? (int)(N - i0 < DFS_RUN ? N - i0 : DFS_RUN) : 0;
+    double *st = stack + threadIdx.x;
+    double u = 1.0;
+    if (cnt > 0) {
+        const int64_t run = i0 / DFS_RUN;
+        const uint32_t a0 = run_anc_ptr[run], na = run_anc_ptr[run + 1] - a0;
+        for (uint32_t a = 0; a < na; a += 8) {
+            uint32_t en[8];
+            double yv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) en[j] = a + j < na ? run_anc[a0 + a + j] : 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) yv[j] = a + j < na ? ys[(size_t)(en[j] >> 1) * KP + k] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (a + j < na) {
+                    const double ul = __dmul_rn(yv[j], u), ur = __dmul_rn(__dsub_rn(1.0, yv[j]), u);
+                    if (en[j] & 1u) {
+                        u = ul;  // into the left child: its right sibling's subtree lies before this run
+                    } else {
+                        st[(size_t)(a + j + 1) * THREADS] = ul;  // the left child (depth a + j + 1) comes later
+                        u = ur;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- the run, in node order
+    double sacc = 0.0, lacc = 0.0, carry = 0.0;
+    const DNode *rr = rec_s + rl * RS;
+    for (int j = 0; j < cnt; ++j) {
+        const DNode r = rr[j];
+        const uint32_t d = r.meta & 0x7fffffffu;
+        if (j > 0) u = (r.meta >> 31) ? st[(size_t)d * THREADS] : carry;
+        if (r.k_or_leaf >= 0) {
+            const double y = ys_s[(r.k_or_leaf - k0) * KP + k];
+            st[(size_t)(d + 1) * THREADS] = __dmul_rn(y, u);
+            carry = __dmul_rn(__dsub_rn(1.0, y), u);
+            us_k[(size_t)r.k_or_leaf * KP + k] = u;
+            if (want_ladj) lacc += log(u);
+        } else {
+            const int leaf = -1 - r.k_or_leaf;
+            float xv = (float)u;
+            double dd = (double)xv;
+            xv = (float)(dd > 1e-16 ? dd : 1e-16);  // ptt.jl:136-137
+            if (clamp_x) {                           // clamp!(xs, 1e-10, 1 - 1e-10) on a Float32 vector
+                dd = (double)xv;
+                dd = fmin(fmax(dd, 1e-10), 1.0 - 1e-10);
+                xv = (float)dd;
+            }
+            x[(size_t)leaf * KP + k] = xv;
+            if (xd) xd[(size_t)leaf * KP + k] = (double)xv;
+            if (efflen) sacc = __dadd_rn(sacc, (double)__fdiv_rn(xv, r.efflen));  // the record carries efflen[leaf]
+        }
+    }
+    if (S_partial) block_reduce_kc<KP, THREADS>(sacc, red, S_partial + (size_t)blockIdx.x * KP);
+    if (want_ladj) block_reduce_kc<KP, THREADS>(lacc, red, ladj_partial + (size_t)blockIdx.x * KP);
+}
+
 // Leaf records carry the leaf's effective length (left) and Float32(n / efflen) (right) as raw Float32 bits, so the
 // level loops never touch global memory for them.
 __global__ void k_patch_leaf_recs(SNode *recs, int count, const float *__restrict__ efflen, const float *__restrict__ adj) {
@@ -494,6 +683,13 @@ __global__ void k_patch_leaf_recs(SNode *recs, int count, const float *__restric
         r.right = __float_as_int(adj[leaf]);
         recs[q] = r;
     }
+}
+
+__global__ void k_patch_dnodes(DNode *recs, int64_t count, const float *__restrict__ efflen) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    const int32_t v = recs[q].k_or_leaf;
+    if (v < 0) recs[q].efflen = efflen[-1 - v];
 }
 
 // ---------------------------------------------------------------- reparameterisation backward + ADAM
@@ -521,10 +717,15 @@ __device__ __forceinline__ void adam_one(float &param, float &m, float &v, doubl
     param = (float)__dadd_rn((double)param, delta);
 }
 
-// One thread per internal node; both halves of the step boundary in one pass over the parameters:
-//   UPDATE  (step s):   logit-normal + sinh-arcsinh backward accumulated over the K draws in draw order, /K, finite
-//                       check, ADAM ascent with step clamp
-//   REPARAM (step s+1): noise -> zs -> ys for the next step's tree forward
+// Both halves of the step boundary in one pass over the parameters.  A CTA owns ELEM_THREADS / KP consecutive nodes
+// and works in two arrangements: per-DRAW work (the terms of the backward pass, noise, zs -> ys) runs one lane per
+// (node, draw) -- the KP lanes of a node sit next to each other, so ys / ygrad / zs0 move coalesced -- and per-NODE
+// work (exp / sinh / cosh of the parameters, the accumulation over the draws, ADAM) runs one lane per node, or per
+// (parameter, node), with the two sides meeting in shared memory:
+//   UPDATE  (step s):   every (node, draw) lane forms its draw's terms of the logit-normal + sinh-arcsinh backward;
+//                       one lane per (parameter, node) adds them in draw order with the reference's roundings, divides
+//                       by K, checks for non-finite values and does that parameter's ADAM ascent with step clamp
+//   REPARAM (step s+1): noise -> zs -> ys per (node, draw) lane from the updated parameters
 // sinh(alpha + asinh z0) is evaluated as z0 cosh(alpha) + sqrt(1 + z0^2) sinh(alpha) (and cosh(c), tanh(c)
 // likewise from cosh/sinh(alpha)): the same real function as the reference's Float32 expression with two
 // transcendentals per NODE instead of four per DRAW; the difference is a few Float32 ulp.
@@ -537,36 +738,63 @@ __global__ void __launch_bounds__(ELEM_THREADS)
             const StepCtl *__restrict__ ctl, AdamCfg cfg, int *__restrict__ bad_step, float *__restrict__ grad_out,
             const float *__restrict__ noise, int64_t noise_steps, uint64_t seed, int fast_noise, int want_ladj,
             double *__restrict__ ladj_partial /* [2][gridDim.x][KP] */, int step0_fixed, int clamp_y) {
-    __shared__ double sm[ELEM_THREADS];
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    constexpr int NODES = ELEM_THREADS / KP;   // nodes per CTA
+    constexpr int TS = NODES + 1;              // stride of a draw's row of terms (odd: conflict-free per-node reads)
+    __shared__ double sm_d[2][KP * TS > ELEM_THREADS ? KP * TS : ELEM_THREADS];  // mu terms [draw][node]; ladj reductions
+    __shared__ float sm_f[3][KP * TS];         // omega term, alpha terms [draw][node]
+    __shared__ float nd_par[3][NODES];         // mu, omega, alpha of the CTA's nodes
+    __shared__ float nd_tr[4][NODES];          // exp(omega), sinh(alpha), cosh(alpha), 1 / exp(omega)
+    __shared__ double adam_c[3];               // learning rate, 1 - beta1^t, 1 - beta2^t
+    const int k = threadIdx.x % KP, nl = threadIdx.x / KP;
+    const int64_t node0 = blockIdx.x * (int64_t)NODES, i = node0 + nl;
     const bool live = i < nm1;
-    float p_mu = 0.f, p_om = 0.f, p_al = 0.f;
-    if (live) {
-        p_mu = mu[i];
-        if (mode == 0) { p_om = omega[i]; p_al = alpha[i]; }
-    }
 
-    if (do_update && live) {
-        const int step = ctl->step_upd;
-        // adam_learning_rate(step_num - 1)  l-a.jl:107-110, 497
-        const double lr = fmax(1e-3, 1.0 * exp(-2e-2 * (double)(step - 1)));
-        const double m_denom = 1.0 - pow(0.7, (double)step), v_denom = 1.0 - pow(0.9, (double)step);
-        if (mode == 1) {  // OptimizePTTApprox: z_grad = y (1 - y) y_grad, Float64 (l-a.jl:211-213)
-            const double y = ys[(size_t)i * KP];
-            const double zg = __dmul_rn(__dmul_rn(y, __dsub_rn(1.0, y)), ygrad[(size_t)i * KP]);
-            if (grad_out) grad_out[i] = (float)zg;
-            if (!isfinite(zg)) atomicCAS(bad_step, 0, step);
-            if (do_adam) {
-                float mm = m_mu[i], vv = v_mu[i];
-                adam_one(p_mu, mm, vv, zg, 0.0f, false, step, lr, m_denom, v_denom, cfg.max_step_z);
-                m_mu[i] = mm; v_mu[i] = vv; mu[i] = p_mu;
+    // ---- per node: parameters and their transcendentals
+    if (threadIdx.x < NODES && node0 + threadIdx.x < nm1) {
+        const int64_t ii = node0 + threadIdx.x;
+        const float pm = mu[ii];
+        nd_par[0][threadIdx.x] = pm;
+        if (mode == 0) {
+            const float po = omega[ii], pa = alpha[ii], sg = expf(po);
+            nd_par[1][threadIdx.x] = po;
+            nd_par[2][threadIdx.x] = pa;
+            nd_tr[0][threadIdx.x] = sg;
+            nd_tr[1][threadIdx.x] = sinhf(pa);
+            nd_tr[2][threadIdx.x] = coshf(pa);
+            nd_tr[3][threadIdx.x] = __fdiv_rn(1.0f, sg);
+        }
+    }
+    int step = 0;
+    if (do_update) {
+        step = ctl->step_upd;
+        if (threadIdx.x == ELEM_THREADS - 1) {
+            adam_c[0] = fmax(1e-3, 1.0 * exp(-2e-2 * (double)(step - 1)));  // adam_learning_rate(step_num - 1)  l-a.jl:107-110, 497
+            adam_c[1] = 1.0 - pow(0.7, (double)step);
+            adam_c[2] = 1.0 - pow(0.9, (double)step);
+        }
+    }
+    __syncthreads();
+
+    if (do_update) {
+        const double lr = adam_c[0], m_denom = adam_c[1], v_denom = adam_c[2];
+        if (mode == 1) {  // OptimizePTTApprox (K = 1): z_grad = y (1 - y) y_grad, Float64 (l-a.jl:211-213)
+            if (live && k == 0) {
+                float p_mu = nd_par[0][nl];
+                const double y = ys[(size_t)i * KP];
+                const double zg = __dmul_rn(__dmul_rn(y, __dsub_rn(1.0, y)), ygrad[(size_t)i * KP]);
+                if (grad_out) grad_out[i] = (float)zg;
+                if (!isfinite(zg)) atomicCAS(bad_step, 0, step);
+                if (do_adam) {
+                    float mm = m_mu[i], vv = v_mu[i];
+                    adam_one(p_mu, mm, vv, zg, 0.0f, false, step, lr, m_denom, v_denom, cfg.max_step_z);
+                    m_mu[i] = mm; v_mu[i] = vv; mu[i] = p_mu;
+                    nd_par[0][nl] = p_mu;
+                }
             }
+            __syncthreads();
         } else {
-            const float sigma = expf(p_om);
-            const float sa = sinhf(p_al), ca = coshf(p_al);
-            const float inv_sigma = __fdiv_rn(1.0f, sigma);
-            float mu_g = 0.0f, om_g = 0.0f, al_g = 0.0f;
-            for (int k = 0; k < K; ++k) {
+            if (live && k < K) {  // this draw's terms
+                const float sigma = nd_tr[0][nl], sa = nd_tr[1][nl], ca = nd_tr[2][nl], inv_sigma = nd_tr[3][nl];
                 const double y = ys[(size_t)i * KP + k];
                 const double yg = ygrad[(size_t)i * KP + k];  // already rounded to Float32
                 const float z0 = zs0[(size_t)i * KP + k];
@@ -577,118 +805,132 @@ __global__ void __launch_bounds__(ELEM_THREADS)
                 const double d = __dmul_rn(y, __dsub_rn(1.0, y));
                 const double omy2 = __dsub_rn(1.0, __dmul_rn(2.0, y));
                 // logit_normal_transform_gradients! (8-arg)  logitnormal.jl:38-55; sigma_grad / z_grad restart per draw
-                mu_g = (float)__dadd_rn((double)mu_g, __dmul_rn(d, yg));
                 float sg = (float)__dmul_rn(__dmul_rn(d, z), yg);
                 float zg = (float)__dmul_rn(__dmul_rn(d, (double)sigma), yg);
-                mu_g = (float)__dadd_rn((double)mu_g, omy2);
                 sg = (float)__dadd_rn((double)sg, __dadd_rn((double)inv_sigma, __dmul_rn(z, omy2)));
                 zg = (float)__dadd_rn((double)zg, __dmul_rn((double)sigma, omy2));
+                const int t = k * TS + nl;
+                sm_d[0][t] = __dmul_rn(d, yg);  // mu_grad += d y_grad; mu_grad += 1 - 2 y
+                sm_d[1][t] = omy2;
+                sm_f[0][t] = __fmul_rn(sigma, sg);  // omega chain rule  l-a.jl:547-549
                 // sinh_asinh_transform_gradients!  sinh_arcsinh.jl:29-38: cosh(c) z_grad + tanh(c)
-                al_g = __fadd_rn(al_g, __fmul_rn(ch, zg));
-                al_g = __fadd_rn(al_g, __fdiv_rn(zf, ch));
-                // omega chain rule  l-a.jl:547-549
-                om_g = __fadd_rn(om_g, __fmul_rn(sigma, sg));
+                sm_f[1][t] = __fmul_rn(ch, zg);
+                sm_f[2][t] = __fdiv_rn(zf, ch);
             }
-            const float Kf = (float)K;
-            mu_g = __fdiv_rn(mu_g, Kf);  // l-a.jl:552-556
-            om_g = __fdiv_rn(om_g, Kf);
-            al_g = __fdiv_rn(al_g, Kf);
-            if (!(isfinite(mu_g) && isfinite(om_g) && isfinite(al_g))) atomicCAS(bad_step, 0, step);
-            if (grad_out) {
-                grad_out[i] = mu_g;
-                grad_out[nm1 + i] = om_g;
-                grad_out[2 * nm1 + i] = al_g;
+            __syncthreads();
+            // one lane per (parameter, node): p = 0 mu, 1 omega, 2 alpha
+            for (int t = threadIdx.x; t < 3 * NODES; t += ELEM_THREADS) {
+                const int p = t / NODES, nn = t - p * NODES;
+                const int64_t ii = node0 + nn;
+                if (ii >= nm1) continue;
+                float g = 0.0f;  // the Float32 accumulator of the reference, fed in draw order
+                if (p == 0) {
+                    for (int kk = 0; kk < K; ++kk) {
+                        g = (float)__dadd_rn((double)g, sm_d[0][kk * TS + nn]);
+                        g = (float)__dadd_rn((double)g, sm_d[1][kk * TS + nn]);
+                    }
+                } else if (p == 1) {
+                    for (int kk = 0; kk < K; ++kk) g = __fadd_rn(g, sm_f[0][kk * TS + nn]);
+                } else {
+                    for (int kk = 0; kk < K; ++kk) {
+                        g = __fadd_rn(g, sm_f[1][kk * TS + nn]);
+                        g = __fadd_rn(g, sm_f[2][kk * TS + nn]);
+                    }
+                }
+                g = __fdiv_rn(g, (float)K);  // l-a.jl:552-556
+                if (!isfinite(g)) atomicCAS(bad_step, 0, step);
+                if (grad_out) grad_out[(size_t)p * nm1 + ii] = g;
+                if (do_adam) {
+                    float *par = p == 0 ? mu : (p == 1 ? omega : alpha);
+                    float *ms = p == 0 ? m_mu : (p == 1 ? m_omega : m_alpha);
+                    float *vs = p == 0 ? v_mu : (p == 1 ? v_omega : v_alpha);
+                    float pv = nd_par[p][nn];
+                    float mm = ms[ii], vv = vs[ii];
+                    adam_one(pv, mm, vv, (double)g, __fmul_rn(g, g), true, step, lr, m_denom, v_denom,
+                             p == 0 ? cfg.max_step_mu : (p == 1 ? cfg.max_step_omega : cfg.max_step_alpha));
+                    ms[ii] = mm; vs[ii] = vv; par[ii] = pv;
+                    nd_par[p][nn] = pv;
+                }
             }
-            if (do_adam) {
-                float mm = m_mu[i], vv = v_mu[i];
-                adam_one(p_mu, mm, vv, (double)mu_g, __fmul_rn(mu_g, mu_g), true, step, lr, m_denom, v_denom, cfg.max_step_mu);
-                m_mu[i] = mm; v_mu[i] = vv; mu[i] = p_mu;
-                mm = m_omega[i]; vv = v_omega[i];
-                adam_one(p_om, mm, vv, (double)om_g, __fmul_rn(om_g, om_g), true, step, lr, m_denom, v_denom, cfg.max_step_omega);
-                m_omega[i] = mm; v_omega[i] = vv; omega[i] = p_om;
-                mm = m_alpha[i]; vv = v_alpha[i];
-                adam_one(p_al, mm, vv, (double)al_g, __fmul_rn(al_g, al_g), true, step, lr, m_denom, v_denom, cfg.max_step_alpha);
-                m_alpha[i] = mm; v_alpha[i] = vv; alpha[i] = p_al;
+            __syncthreads();
+            if (do_adam && do_reparam) {  // transcendentals of the updated parameters
+                if (threadIdx.x < NODES && node0 + threadIdx.x < nm1) {
+                    const float sg = expf(nd_par[1][threadIdx.x]), pa = nd_par[2][threadIdx.x];
+                    nd_tr[0][threadIdx.x] = sg;
+                    nd_tr[1][threadIdx.x] = sinhf(pa);
+                    nd_tr[2][threadIdx.x] = coshf(pa);
+                }
+                __syncthreads();
             }
         }
     }
 
     if (!do_reparam) return;
-    double l_skew[KP], l_ln[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) { l_skew[k] = 0.0; l_ln[k] = 0.0; }
+    double l_skew = 0.0, l_ln = 0.0;
     if (live) {
+        const float p_mu = nd_par[0][nl];
         if (mode == 1) {
-            const float e = expf(-p_mu);
-            ys[(size_t)i * KP] = (double)__fdiv_rn(1.0f, __fadd_rn(1.0f, e));  // ys = logistic(zs), no clamp (l-a.jl:196)
-            zs0[(size_t)i * KP] = 0.0f;
+            if (k == 0) {
+                const float e = expf(-p_mu);
+                ys[(size_t)i * KP] = (double)__fdiv_rn(1.0f, __fadd_rn(1.0f, e));  // ys = logistic(zs), no clamp (l-a.jl:196)
+                zs0[(size_t)i * KP] = 0.0f;
+            }
         } else {
             const int step0 = step0_fixed >= 0 ? step0_fixed : ctl->step_fwd - 1;  // 0-based index of the step of these draws
-            const float sigma = expf(p_om);
-            const float sa = sinhf(p_al), ca = coshf(p_al);
-#pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                float z0 = 0.0f;
-                if (k < K) {
-                    if (noise) z0 = noise[((size_t)(step0 % noise_steps) * K + k) * (size_t)nm1 + i];
-                    else z0 = philox_normal(seed, (uint32_t)i, (uint32_t)k, (uint32_t)step0, fast_noise);
-                }
-                const float r = sqrtf(fmaf(z0, z0, 1.0f));
-                const float zf = fmaf(z0, ca, r * sa);
-                const float xx = __fadd_rn(p_mu, __fmul_rn(zf, sigma));
-                const float e = expf(-xx);
-                const float y32 = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
-                double y = (double)y32;
-                if (want_ladj && k < K) {
-                    const float ch = fmaf(ca, r, sa * z0);
-                    l_skew[k] = (double)logf(ch) - (double)logf(r);  // log cosh(c) - 0.5 log1p(z0^2)
-                    l_ln[k] = log(__dmul_rn(__dmul_rn((double)sigma, y), __dsub_rn(1.0, y)));
-                }
-                if (clamp_y) y = fmin(fmax(y, 1e-10), 1.0 - 1e-10);
-                zs0[(size_t)i * KP + k] = z0;
-                ys[(size_t)i * KP + k] = y;
+            const float sigma = nd_tr[0][nl], sa = nd_tr[1][nl], ca = nd_tr[2][nl];
+            float z0 = 0.0f;
+            if (k < K) {
+                if (noise) z0 = noise[((size_t)(step0 % noise_steps) * K + k) * (size_t)nm1 + i];
+                else z0 = philox_normal(seed, (uint32_t)i, (uint32_t)k, (uint32_t)step0, fast_noise);
             }
+            const float r = sqrtf(fmaf(z0, z0, 1.0f));
+            const float zf = fmaf(z0, ca, r * sa);
+            const float xx = __fadd_rn(p_mu, __fmul_rn(zf, sigma));
+            const float e = expf(-xx);
+            const float y32 = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+            double y = (double)y32;
+            if (want_ladj && k < K) {
+                const float ch = fmaf(ca, r, sa * z0);
+                l_skew = (double)logf(ch) - (double)logf(r);  // log cosh(c) - 0.5 log1p(z0^2)
+                l_ln = log(__dmul_rn(__dmul_rn((double)sigma, y), __dsub_rn(1.0, y)));
+            }
+            if (clamp_y) y = fmin(fmax(y, 1e-10), 1.0 - 1e-10);
+            zs0[(size_t)i * KP + k] = z0;
+            ys[(size_t)i * KP + k] = y;
         }
     }
     if (want_ladj) {
-        // per-draw block sums, fixed order
-        for (int k = 0; k < KP; ++k) {
-            sm[threadIdx.x] = l_skew[k];
-            __syncthreads();
-            for (int span = ELEM_THREADS / 2; span >= 1; span >>= 1) {
-                if ((int)threadIdx.x < span) sm[threadIdx.x] += sm[threadIdx.x + span];
-                __syncthreads();
-            }
-            if (threadIdx.x == 0) ladj_partial[(size_t)blockIdx.x * KP + k] = sm[0];
-            __syncthreads();
-            sm[threadIdx.x] = l_ln[k];
-            __syncthreads();
-            for (int span = ELEM_THREADS / 2; span >= 1; span >>= 1) {
-                if ((int)threadIdx.x < span) sm[threadIdx.x] += sm[threadIdx.x + span];
-                __syncthreads();
-            }
-            if (threadIdx.x == 0) ladj_partial[((size_t)gridDim.x + blockIdx.x) * KP + k] = sm[0];
-            __syncthreads();
-        }
+        // per-draw block sums over the CTA's nodes, fixed order
+        __syncthreads();
+        block_reduce_k<KP, ELEM_THREADS>(l_skew, sm_d[0], ladj_partial + (size_t)blockIdx.x * KP);
+        block_reduce_k<KP, ELEM_THREADS>(l_ln, sm_d[0], ladj_partial + ((size_t)gridDim.x + blockIdx.x) * KP);
     }
 }
 
 // ELBO of the step being updated: mean over the K draws of lp + the three log-Jacobians
 // (the reference ASSIGNS per draw and divides by K, l-a.jl:540,561 -- a quirk; this is the mean).
-__global__ void k3_elbo(int K, int KP, const double *__restrict__ lp, const double *__restrict__ ladj_partial,
-                        int n_elem_ctas, int n_tree_parts, const StepCtl *__restrict__ ctl, double *__restrict__ elbo,
-                        int max_steps) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(256) k3_elbo(int K, int KP, const double *__restrict__ lp, const double *__restrict__ ladj_partial,
+                                               int n_elem_ctas, int n_tree_parts, const StepCtl *__restrict__ ctl,
+                                               double *__restrict__ elbo, int max_steps) {
+    // one CTA; the partial sums of a draw (two per k3_elem CTA, one per tree CTA: contiguous rows of ladj_partial) are
+    // added thread-strided and then by a shared-memory tree: a fixed order
+    __shared__ double sm[256];
+    const int total = 2 * n_elem_ctas + n_tree_parts;
     double tot = 0.0;
     for (int k = 0; k < K; ++k) {
-        double s = lp ? lp[k] : 0.0;
-        for (int t = 0; t < 2 * n_elem_ctas; ++t) s += ladj_partial[(size_t)t * KP + k];
-        const double *tp = ladj_partial + (size_t)2 * n_elem_ctas * KP;
-        for (int t = 0; t < n_tree_parts; ++t) s += tp[(size_t)t * KP + k];
-        tot += s;
+        double s = 0.0;
+        for (int t = threadIdx.x; t < total; t += 256) s += ladj_partial[(size_t)t * KP + k];
+        sm[threadIdx.x] = s;
+        __syncthreads();
+        for (int span = 128; span >= 1; span >>= 1) {
+            if ((int)threadIdx.x < span) sm[threadIdx.x] += sm[threadIdx.x + span];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) tot += (lp ? lp[k] : 0.0) + sm[0];
+        __syncthreads();
     }
     const int step = ctl->step_upd;
-    if (step >= 1 && step <= max_steps) elbo[step - 1] = tot / (double)K;
+    if (threadIdx.x == 0 && step >= 1 && step <= max_steps) elbo[step - 1] = tot / (double)K;
 }
 
 }  // namespace
@@ -710,8 +952,8 @@ void release_work_buffers(polee_handle *h) {
 }
 
 int elem_ctas(polee_handle *h, int KP) {
-    (void)KP;
-    return (int)std::max<int64_t>(1, (h->n - 1 + ELEM_THREADS - 1) / ELEM_THREADS);
+    const int nodes = ELEM_THREADS / KP;  // k3_elem: one lane per (internal node, draw)
+    return (int)std::max<int64_t>(1, (h->n - 1 + nodes - 1) / nodes);
 }
 
 int ensure_work_buffers(polee_handle *h, int KP) {
@@ -777,6 +1019,7 @@ int patch_leaf_records(polee_handle *h) {
         if (count > 0)
             k_patch_leaf_recs<<<(count + 255) / 256, 256, 0, h->stream>>>(sd->recs, count, h->efflen, h->efflen_adj);
     }
+    if (h->td.dnodes) k_patch_dnodes<<<(unsigned)((h->td.N + 255) / 256), 256, 0, h->stream>>>(h->td.dnodes, h->td.N, h->efflen);
     CK(cudaGetLastError());
     return POLEE_OK;
 }
@@ -816,6 +1059,18 @@ static bool path_fwd_ok(const polee_handle *h) {
     static const bool off = getenv("POLEE_TREE_FWD") && !strcmp(getenv("POLEE_TREE_FWD"), "levels");
     return !off && h->td.ganc_ptr != nullptr && !chain_path(h) && smem_path_ok(h, h->work_KP);
 }
+// the DFS-run forward kernel (k3d_tree_fwd): trees in DFS pre-order of moderate depth (tree_host.cu builds its inputs
+// only then); like the path-product kernel it leaves u by k for the shared-memory backward kernels
+static size_t dfs_fwd_smem(const polee_handle *h, int KP) {
+    const size_t threads = (size_t)DFS_RUNS_PER_CTA * KP;
+    return (size_t)(h->td.max_depth + 2) * threads * 8 + (size_t)((std::max(h->td.dfs_max_nk, 1) + 1) & ~1) * KP * 8 +
+           (size_t)DFS_RUNS_PER_CTA * (DFS_RUN + 1) * sizeof(DNode);
+}
+static bool dfs_fwd_ok(const polee_handle *h) {
+    return h->td.dnodes != nullptr && !chain_path(h) && smem_path_ok(h, h->work_KP) && h->work_KP <= 16 &&
+           dfs_fwd_smem(h, h->work_KP) <= 200 * 1024;
+}
+static bool fwd_leaves_us_by_k(const polee_handle *h) { return dfs_fwd_ok(h) || path_fwd_ok(h); }
 
 // bottom-forest launch variants (draws per CTA, threads, min CTAs/SM); POLEE_TREE_VARIANT picks one at run time
 static int tree_variant() {
@@ -845,7 +1100,7 @@ static void launch_bwd_bottom_v(polee_handle *h, const float *adj, double *xgrad
     set_smem_attr(fn, smem);
     fn<<<dim3(td.s_bottom.nbins, KP / KPC), THREADS, smem, h->stream>>>(
         td.s_bottom.bin_off, td.s_bottom.bin_lvl_ptr, td.s_bottom.lvl_off, td.s_bottom.recs, h->ys, h->root_us, h->root_G, h->g,
-        adj, h->S, h->ygrad, xgrad_out, path_fwd_ok(h) ? h->us : nullptr);
+        adj, h->S, h->ygrad, xgrad_out, fwd_leaves_us_by_k(h) ? h->us : nullptr);
 }
 
 template <int KP>
@@ -893,7 +1148,7 @@ static int launch_tree_bwd_smem(polee_handle *h, const float *adj, double *xgrad
         set_smem_attr(fn, smem);
         fn<<<dim3(td.s_top.nbins, KP), S_TOP_THREADS, smem, h->stream>>>(
             td.s_top.bin_off, td.s_top.bin_lvl_ptr, td.s_top.lvl_off, td.s_top.recs, h->ys, h->root_us, h->root_G, h->g, adj,
-            h->S, h->ygrad, xgrad_out, path_fwd_ok(h) ? h->us : nullptr);
+            h->S, h->ygrad, xgrad_out, fwd_leaves_us_by_k(h) ? h->us : nullptr);
     }
     return POLEE_OK;
 }
@@ -924,6 +1179,16 @@ int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_l
     const float *eff = want_S ? h->efflen : nullptr;
     double *Sp = want_S ? h->S_partial : nullptr;
     if (chain_path(h)) return launch_chain_fwd(h, KP, clamp_x, eff, Sp, want_ladj, ladj_tree);
+    if (dfs_fwd_ok(h)) {
+        // the Float64 copy of x is the gather table of the split layout's K1 only
+        double *xd = (!h->have_matrix || ((h->gm > 0 || h->ec_tasks == 0) && !h->fused)) ? h->xd : nullptr;
+        const size_t smem = dfs_fwd_smem(h, KP);
+        if (smem > 40 * 1024) DISPATCH_KP(KP, allow_max_smem(k3d_tree_fwd<KPC>));
+        DISPATCH_KP(KP, (k3d_tree_fwd<KPC><<<td.dfs_ctas, DFS_RUNS_PER_CTA * KPC, smem, h->stream>>>(
+                            td.N, td.dnodes, td.drun_anc_ptr, td.drun_anc, td.dcta_k0, h->ys, h->us, h->x, xd, clamp_x, eff, Sp,
+                            want_ladj, ladj_tree, td.max_depth + 2, (std::max(td.dfs_max_nk, 1) + 1) & ~1)));
+        return POLEE_OK;
+    }
     if (path_fwd_ok(h)) {
         const size_t smem = (size_t)td.max_ganc * (16 * KP + 2) + 16 + 2 * (size_t)td.max_gsuf;
         if (smem > 40 * 1024) DISPATCH_KP(KP, allow_max_smem(k3p_tree_fwd<KPC>));
@@ -989,9 +1254,47 @@ int launch_update(polee_handle *h, int KP, int K, bool do_adam, float *grad_out)
 }
 
 int launch_elbo(polee_handle *h, int KP, int K, bool have_lp) {
-    k3_elbo<<<1, 32, 0, h->stream>>>(K, KP, have_lp ? h->g + (size_t)h->n * KP : nullptr, h->ladj_partial,
+    k3_elbo<<<1, 256, 0, h->stream>>>(K, KP, have_lp ? h->g + (size_t)h->n * KP : nullptr, h->ladj_partial,
                                      elem_ctas(h, KP), h->n_tree_ctas, h->d_step, h->elbo,
                                      h->o.num_steps);
+    return POLEE_OK;
+}
+
+
+// inverse_transform! of the KP draws in x_dev ([n][KP] Float32) -> ys_out ([n-1][KP] Float64) and, when ladj_out is
+// given, ladj[KP].  us_tmp: [2n-1][KP] Float64 scratch (indexed by node); logu_tmp: [n-1][KP] Float32 scratch (needed
+// only with ladj_out).
+int launch_tree_inv(polee_handle *h, int KP, const float *x_dev, double *us_tmp, double *ys_out, float *logu_tmp, double *ladj_out) {
+    const TreeDev &td = h->td;
+    float *logu = ladj_out ? logu_tmp : nullptr;
+    if (td.n < 2) return POLEE_OK;
+    if (chain_path(h)) {
+        k3_tree_inv_serial<<<1, 32, 0, h->stream>>>(td.N, KP, td.nodes, x_dev, us_tmp, ys_out, logu);
+    } else {
+        if (td.bottom.nbins > 0) {
+            DISPATCH_KP(KP, (k3_tree_inv<KPC, TREE_THREADS><<<td.bottom.nbins, TREE_THREADS, 0, h->stream>>>(
+                                td.bottom.bin_lvl_ptr, td.bottom.lvl_off, td.bottom.sch_node, td.nodes, x_dev, us_tmp, ys_out, logu)));
+        }
+        if (td.top.nbins > 0) {
+            DISPATCH_KP(KP, (k3_tree_inv<KPC, TOP_THREADS><<<td.top.nbins, TOP_THREADS, 0, h->stream>>>(
+                                td.top.bin_lvl_ptr, td.top.lvl_off, td.top.sch_node, td.nodes, x_dev, us_tmp, ys_out, logu)));
+        }
+    }
+    if (ladj_out) k3_inv_ladj<<<1, 32, 0, h->stream>>>(td.n - 1, KP, logu, ladj_out);
+    return POLEE_OK;
+}
+
+int launch_fill_f32(polee_handle *h, float *p, int64_t count, float v) {
+    if (count > 0) k3_fill_f32<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(p, count, v);
+    return POLEE_OK;
+}
+
+// the starting point of the fit (likelihood-approximation.jl:451-456) from ys0 = inverse_transform!(fill(1f0/n)) when
+// given (it also fills mu0), else from the stored mu0
+int launch_init_params(polee_handle *h, const double *ys0, int KP) {
+    const int64_t nm1 = h->td.n - 1;
+    if (nm1 < 1) return POLEE_OK;
+    k3_init_params<<<(unsigned)((nm1 + 255) / 256), 256, 0, h->stream>>>(nm1, KP, ys0, logf(0.1f), h->mu0_dev, h->mu, h->omega, h->alpha);
     return POLEE_OK;
 }
 

@@ -9,9 +9,11 @@
 // TensorFlow is not installed in the build image; `make -C tests/tf_shim check` compiles this file against a stub
 // of the TF op API (the same stub that builds the reference's own op file) and the GPU tests drive it that way.
 //
-// The kernels are registered for DEVICE_CPU on purpose: the tensors TF hands over are host tensors (as for the
-// reference op) and the library does its own device transfers; registering a DEVICE_GPU kernel that consumes
-// device tensors in place is a follow-up.
+// Every op is registered twice.  DEVICE_CPU (what the reference registers, hsb_ops.cpp:120, 249, 402): TF hands over
+// host tensors and the library does its own transfers (polee_*_with_plan).  DEVICE_GPU: the data tensors are device
+// memory and are consumed and produced in place on the op's CUDA stream (polee_*_device; no copy, no allocation per
+// call); only the three index tensors are pinned to host memory (HostMemory), because the tree plan is built from them
+// on the host once and cached.
 #include "tensorflow/core/framework/op.h"
 #include "tensorflow/core/framework/op_kernel.h"
 #include "tensorflow/core/framework/shape_inference.h"
@@ -22,6 +24,19 @@
 #include <mutex>
 
 #include "polee_b200.h"
+
+#ifdef POLEE_TF_STUB_CORE_H
+// the stand-in API of the test build carries the stream in the context
+static void* polee_tf_stream(tensorflow::OpKernelContext* c) { return c->gpu_stream; }
+#else
+// real TensorFlow (build with the CUDA toolkit's headers on the include path): the op's compute stream
+#define EIGEN_USE_GPU
+#include "tensorflow/core/framework/tensor.h"
+#include "unsupported/Eigen/CXX11/Tensor"
+static void* polee_tf_stream(tensorflow::OpKernelContext* c) {
+    return (void*)c->eigen_device<Eigen::GpuDevice>().stream();
+}
+#endif
 
 using namespace tensorflow;
 
@@ -100,6 +115,7 @@ REGISTER_OP("HSB")
         return Status::OK();
     });
 
+template <bool ON_DEVICE>
 class HSBOpB200 : public OpKernel {
    public:
     explicit HSBOpB200(OpKernelConstruction* context) : OpKernel(context) {}
@@ -113,11 +129,15 @@ class HSBOpB200 : public OpKernel {
                                      &context->input(2).flat_inner_dims<int32>()(0, 0),
                                      &context->input(3).flat_inner_dims<int32>()(0, 0), &err);
         if (!p) OP_REQUIRES_OK(context, fail(err));
-        if (polee_hsb_with_plan(p, B, &y_logit.flat_inner_dims<float>()(0, 0), &x->flat_inner_dims<float>()(0, 0)) != POLEE_OK)
-            OP_REQUIRES_OK(context, fail(polee_hsb_last_error()));
+        const float* in = &y_logit.flat_inner_dims<float>()(0, 0);
+        float* out = &x->flat_inner_dims<float>()(0, 0);
+        const int rc = ON_DEVICE ? polee_hsb_device(p, B, in, out, polee_tf_stream(context)) : polee_hsb_with_plan(p, B, in, out);
+        if (rc != POLEE_OK) OP_REQUIRES_OK(context, fail(polee_hsb_last_error()));
     }
 };
-REGISTER_KERNEL_BUILDER(Name("HSB").Device(DEVICE_CPU), HSBOpB200);
+REGISTER_KERNEL_BUILDER(Name("HSB").Device(DEVICE_CPU), HSBOpB200<false>);
+REGISTER_KERNEL_BUILDER(Name("HSB").Device(DEVICE_GPU).HostMemory("left_index").HostMemory("right_index").HostMemory("leaf_index"),
+                        HSBOpB200<true>);
 
 REGISTER_OP("InvHSB")
     .Input("x: float32")
@@ -139,6 +159,7 @@ REGISTER_OP("InvHSB")
         return Status::OK();
     });
 
+template <bool ON_DEVICE>
 class InvHSBOpB200 : public OpKernel {
    public:
     explicit InvHSBOpB200(OpKernelConstruction* context) : OpKernel(context) {}
@@ -153,12 +174,16 @@ class InvHSBOpB200 : public OpKernel {
                                      &context->input(2).flat_inner_dims<int32>()(0, 0),
                                      &context->input(3).flat_inner_dims<int32>()(0, 0), &err);
         if (!p) OP_REQUIRES_OK(context, fail(err));
-        if (polee_inv_hsb_with_plan(p, B, &x.flat_inner_dims<float>()(0, 0), &y->flat_inner_dims<double>()(0, 0),
-                                    &ladj->flat_inner_dims<float>()(0, 0)) != POLEE_OK)
-            OP_REQUIRES_OK(context, fail(polee_hsb_last_error()));
+        const float* in = &x.flat_inner_dims<float>()(0, 0);
+        double* yo = &y->flat_inner_dims<double>()(0, 0);
+        float* lo = &ladj->flat_inner_dims<float>()(0, 0);
+        const int rc = ON_DEVICE ? polee_inv_hsb_device(p, B, in, yo, lo, polee_tf_stream(context)) : polee_inv_hsb_with_plan(p, B, in, yo, lo);
+        if (rc != POLEE_OK) OP_REQUIRES_OK(context, fail(polee_hsb_last_error()));
     }
 };
-REGISTER_KERNEL_BUILDER(Name("InvHSB").Device(DEVICE_CPU), InvHSBOpB200);
+REGISTER_KERNEL_BUILDER(Name("InvHSB").Device(DEVICE_CPU), InvHSBOpB200<false>);
+REGISTER_KERNEL_BUILDER(Name("InvHSB").Device(DEVICE_GPU).HostMemory("left_index").HostMemory("right_index").HostMemory("leaf_index"),
+                        InvHSBOpB200<true>);
 
 REGISTER_OP("InvHSBGrad")
     .Input("y_grad: float64")
@@ -182,6 +207,7 @@ REGISTER_OP("InvHSBGrad")
         return Status::OK();
     });
 
+template <bool ON_DEVICE>
 class InvHSBGradOpB200 : public OpKernel {
    public:
     explicit InvHSBGradOpB200(OpKernelConstruction* context) : OpKernel(context) {}
@@ -197,10 +223,15 @@ class InvHSBGradOpB200 : public OpKernel {
                                      &context->input(5).flat_inner_dims<int32>()(0, 0),
                                      &context->input(6).flat_inner_dims<int32>()(0, 0), &err);
         if (!p) OP_REQUIRES_OK(context, fail(err));
-        if (polee_inv_hsb_grad_with_plan(p, B, &y_grad.flat_inner_dims<double>()(0, 0),
-                                         &ladj_grad.flat_inner_dims<float>()(0, 0), &y.flat_inner_dims<double>()(0, 0),
-                                         &bp->flat_inner_dims<float>()(0, 0)) != POLEE_OK)
-            OP_REQUIRES_OK(context, fail(polee_hsb_last_error()));
+        const double* yg = &y_grad.flat_inner_dims<double>()(0, 0);
+        const float* lg = &ladj_grad.flat_inner_dims<float>()(0, 0);
+        const double* yv = &y.flat_inner_dims<double>()(0, 0);
+        float* out = &bp->flat_inner_dims<float>()(0, 0);
+        const int rc = ON_DEVICE ? polee_inv_hsb_grad_device(p, B, yg, lg, yv, out, polee_tf_stream(context))
+                                 : polee_inv_hsb_grad_with_plan(p, B, yg, lg, yv, out);
+        if (rc != POLEE_OK) OP_REQUIRES_OK(context, fail(polee_hsb_last_error()));
     }
 };
-REGISTER_KERNEL_BUILDER(Name("InvHSBGrad").Device(DEVICE_CPU), InvHSBGradOpB200);
+REGISTER_KERNEL_BUILDER(Name("InvHSBGrad").Device(DEVICE_CPU), InvHSBGradOpB200<false>);
+REGISTER_KERNEL_BUILDER(Name("InvHSBGrad").Device(DEVICE_GPU).HostMemory("left_index").HostMemory("right_index").HostMemory("leaf_index"),
+                        InvHSBGradOpB200<true>);

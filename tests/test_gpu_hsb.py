@@ -83,3 +83,76 @@ def test_tf_shim_through_stub_tensorflow():
         assert shim.shim_inv_hsb_grad(C.c_int64(B), C.c_int64(n), p(yg), p(lg), p(yy), p(la), p(L), p(R), p(F), p(bp),
                                       C.c_int(1)) == 0
         assert np.array_equal(bp, g("backprops"))
+
+
+def test_hsb_device_resident_entry_points():
+    """polee_*_device: device tensors in and out on a caller's stream, no copies (what a DEVICE_GPU registration binds);
+    identical to the host-tensor forms, shared and per-row trees."""
+    import torch
+    import polee_b200 as pb
+    v = np.load(os.path.join(GOLDEN, "hsb_reference_vectors.npz"))
+    st = torch.cuda.Stream()
+    for case in ("fixture_shared", "per_row"):
+        g = lambda k: np.ascontiguousarray(v["%s__%s" % (case, k)])  # noqa: E731
+        yl = g("y_logit")
+        B, n = yl.shape[0], yl.shape[1] + 1
+        idx = [g("left"), g("right"), g("leaf")]
+        if case == "fixture_shared":
+            idx = [a[:1] for a in idx]
+        plan = pb.HsbPlan(n, *idx)
+        dev = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+        with torch.cuda.stream(st):
+            d_yl, d_x = dev(yl), torch.empty((B, n), dtype=torch.float32, device="cuda")
+            d_xin = dev(g("x"))
+            d_y = torch.empty((B, n - 1), dtype=torch.float64, device="cuda")
+            d_ladj = torch.empty((B, 1), dtype=torch.float32, device="cuda")
+            d_yg, d_lg, d_yy = dev(g("y_grad")), dev(g("ladj_grad")), dev(g("y"))
+            d_bp = torch.empty((B, n), dtype=torch.float32, device="cuda")
+            for rep in range(2):                                     # the second call reuses the plan's scratch
+                plan.hsb_device(B, d_yl.data_ptr(), d_x.data_ptr(), st.cuda_stream)
+                plan.inv_hsb_device(B, d_xin.data_ptr(), d_y.data_ptr(), d_ladj.data_ptr(), st.cuda_stream)
+                plan.inv_hsb_grad_device(B, d_yg.data_ptr(), d_lg.data_ptr(), d_yy.data_ptr(), d_bp.data_ptr(), st.cuda_stream)
+        st.synchronize()
+        assert np.array_equal(d_x.cpu().numpy(), pb.hsb(yl, *idx))
+        y_h, ladj_h = pb.inv_hsb(g("x"), *idx)
+        assert np.array_equal(d_y.cpu().numpy(), y_h) and np.array_equal(d_ladj.cpu().numpy(), ladj_h)
+        assert np.array_equal(d_y.cpu().numpy(), g("y")) and relerr(d_ladj.cpu().numpy(), g("ladj")) <= 1e-6
+        assert np.array_equal(d_bp.cpu().numpy(), g("backprops"))
+        plan.close()
+
+
+def test_tf_shim_gpu_registration_through_stub_tensorflow():
+    """The shim's DEVICE_GPU kernels (index tensors in HostMemory, data tensors consumed and produced in device memory on
+    the op's stream), driven through the stub TF API with torch-owned device buffers."""
+    import ctypes as C
+    import torch
+    from conftest import ROOT
+    path = os.path.join(ROOT, "tests", "tf_shim", "libshim_hsb_ops_stubtf.so")
+    import polee_b200  # noqa: F401
+    shim = C.CDLL(path)
+    v = np.load(os.path.join(GOLDEN, "hsb_reference_vectors.npz"))
+    P = C.c_void_p
+    p = lambda a: a.ctypes.data_as(P)  # noqa: E731
+    d = lambda t: P(t.data_ptr())  # noqa: E731
+    st = torch.cuda.Stream()
+    for case in ("fixture_shared", "per_row"):
+        g = lambda k: np.ascontiguousarray(v["%s__%s" % (case, k)])  # noqa: E731
+        L, R, F, yl = g("left"), g("right"), g("leaf"), g("y_logit")
+        B, n = yl.shape[0], yl.shape[1] + 1
+        with torch.cuda.stream(st):
+            t_yl, t_x = torch.from_numpy(yl).cuda(), torch.zeros((B, n), dtype=torch.float32, device="cuda")
+            assert shim.shim_hsb_gpu(C.c_int64(B), C.c_int64(n), d(t_yl), p(L), p(R), p(F), d(t_x), P(st.cuda_stream)) == 0
+            t_xin = torch.from_numpy(g("x")).cuda()
+            t_y = torch.zeros((B, n - 1), dtype=torch.float64, device="cuda")
+            t_ladj = torch.zeros((B, 1), dtype=torch.float32, device="cuda")
+            assert shim.shim_inv_hsb_gpu(C.c_int64(B), C.c_int64(n), d(t_xin), p(L), p(R), p(F), d(t_y), d(t_ladj),
+                                         P(st.cuda_stream)) == 0
+            t_yg, t_lg = torch.from_numpy(g("y_grad")).cuda(), torch.from_numpy(g("ladj_grad")).cuda()
+            t_yy, t_la = torch.from_numpy(g("y")).cuda(), torch.from_numpy(g("ladj")).cuda()
+            t_bp = torch.zeros((B, n), dtype=torch.float32, device="cuda")
+            assert shim.shim_inv_hsb_grad_gpu(C.c_int64(B), C.c_int64(n), d(t_yg), d(t_lg), d(t_yy), d(t_la), p(L), p(R), p(F),
+                                              d(t_bp), P(st.cuda_stream)) == 0
+        st.synchronize()
+        assert relerr(t_x.cpu().numpy(), g("x")) <= 1e-6
+        assert np.array_equal(t_y.cpu().numpy(), g("y")) and relerr(t_ladj.cpu().numpy(), g("ladj")) <= 1e-6
+        assert np.array_equal(t_bp.cpu().numpy(), g("backprops"))

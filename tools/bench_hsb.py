@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """K4 measurement: the three HSB ops (SURVEY 8d "K4 bytes") at B = 64 RNA-seq samples x n = 200 000 transcripts,
-shared tree and a tree per row, through the C ABI with HOST buffers (what the TF op hands over), next to the
+shared tree and a tree per row, through the C ABI with HOST buffers (what the DEVICE_CPU op hands over) and with
+DEVICE buffers on a stream (polee_*_device, what the DEVICE_GPU op hands over; CUDA events), next to the
 reference's own CPU op (oracle/_ref, the unmodified hsb_ops.cpp over the stub TF API) on the box's host cores.
 
     python tools/bench_hsb.py [--B 64] [--n 200000] [--reps 5]
@@ -70,6 +71,34 @@ def main():
         t_hsb = timeit(lambda: lib.polee_hsb_with_plan(plan, C.c_int64(B), p(y_logit), p(x)))
         t_inv = timeit(lambda: lib.polee_inv_hsb_with_plan(plan, C.c_int64(B), p(x), p(y), p(ladj)))
         t_grad = timeit(lambda: lib.polee_inv_hsb_grad_with_plan(plan, C.c_int64(B), p(yg), p(lg), p(y), p(bp)))
+        # device-resident forms: CUDA events on a torch stream, tensors already in HBM
+        import torch
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            d_yl, d_x = torch.from_numpy(y_logit).cuda(), torch.empty((B, n), dtype=torch.float32, device="cuda")
+            d_y = torch.empty((B, n - 1), dtype=torch.float64, device="cuda")
+            d_ladj = torch.empty((B, 1), dtype=torch.float32, device="cuda")
+            d_yg, d_lg = torch.from_numpy(yg).cuda(), torch.from_numpy(lg).cuda()
+            d_bp = torch.empty((B, n), dtype=torch.float32, device="cuda")
+        S = P(st.cuda_stream)
+        dp = lambda t: P(t.data_ptr())  # noqa: E731
+
+        def dev_time(fn):
+            fn(); fn()
+            st.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(a.reps):
+                fn()
+            e1.record(st)
+            st.synchronize()
+            return e0.elapsed_time(e1) / a.reps * 1e-3
+
+        d_hsb = dev_time(lambda: lib.polee_hsb_device(plan, C.c_int64(B), dp(d_yl), dp(d_x), S))
+        d_inv = dev_time(lambda: lib.polee_inv_hsb_device(plan, C.c_int64(B), dp(d_x), dp(d_y), dp(d_ladj), S))
+        d_grad = dev_time(lambda: lib.polee_inv_hsb_grad_device(plan, C.c_int64(B), dp(d_yg), dp(d_lg), dp(d_y), dp(d_bp), S))
+        assert np.array_equal(d_x.cpu().numpy(), x) and np.array_equal(d_y.cpu().numpy(), y)
+        dev_t = {"hsb": d_hsb, "inv_hsb": d_inv, "inv_hsb_grad": d_grad}
         lib.polee_hsb_plan_destroy(plan)
         # reference CPU op (needs [B, 2n-1] index tensors)
         Lb, Rb, Fb = (np.ascontiguousarray(np.broadcast_to(v, (B, N))) for v in (Lx, Rx, Fx))
@@ -84,7 +113,9 @@ def main():
                "inv_hsb_grad": B * (n - 1) * 16 + B * 4 + B * n * 4 + idx_bytes}
         for op, t in (("hsb", t_hsb), ("inv_hsb", t_inv), ("inv_hsb_grad", t_grad)):
             print(json.dumps({"op": op, "trees": mode, "B": B, "n": n, "ms_host_to_host": round(t * 1e3, 2),
-                              "algorithmic_GB": round(alg[op] / 1e9, 4), "GBps_incl_pcie": round(alg[op] / t / 1e9, 1),
+                              "ms_device_resident": round(dev_t[op] * 1e3, 3),
+                              "algorithmic_GB": round(alg[op] / 1e9, 4), "GBps_device_resident": round(alg[op] / dev_t[op] / 1e9, 1),
+                              "GBps_incl_pcie": round(alg[op] / t / 1e9, 1),
                               "plan_create_ms": round(t_plan * 1e3, 1),
                               "reference_cpu_ms": round(ref.get(op, float("nan")) * 1e3, 1), "cpu_threads": a.cpu_threads}))
 

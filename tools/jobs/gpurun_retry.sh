@@ -1,0 +1,9 @@
+#!/bin/bash
+# usage: gpurun_retry.sh <log> <gpurun args...> -- retries while the pod answers "busy" (exit code 3, nothing charged)
+log=$1; shift
+for i in $(seq 1 20); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1; rc=$?
+  [ $rc -ne 3 ] && exit $rc
+  sleep 90
+done
+exit 3
