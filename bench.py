@@ -246,10 +246,9 @@ def run_ours(args):
     torch.cuda.empty_cache()
     h.set_efflens(efflens)
     h.set_tree(*tree)
+    allreduce = None
     if world > 1:
-        uid = [pbapi.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        h.comm_init(world, rank, uid[0])
+        allreduce = pbapi.connect_ranks(h, dist)
     stats = h.step_stats()
     multi = None
     if world > 1:   # correctness of the row-partitioned fit, carried by the same line as its speed
@@ -435,7 +434,10 @@ def run_ours(args):
                 "data": "synthetic (polee-synth-v1, seed %d)" % CONFIGS[args.config][4],
                 "config": {"workload": workload(args.config, m, n, nnz_total, K)},
                 "details": {"partition": "rows in %d contiguous equal-nnz block(s), one per rank" % world,
-                            "l2": "inputs (%.2f GB/step streamed) are far larger than the 126 MB L2; no flush needed"
+                            "allreduce": ("none (one rank)" if world == 1 else
+                                          "one kernel over NVLink peer memory (reduce-scatter by loads, all-gather by stores)"
+                                          if allreduce == "peer" else "ncclAllReduce (Float32) between narrow / widen kernels"),
+                                                        "l2": "inputs (%.2f GB/step streamed) are far larger than the 126 MB L2; no flush needed"
                                   % (stats["bytes_k1"] / 1e9 if onepass else (b_k1 + b_k2) / 1e9),
                             "layout": layout, "noise": "device Philox"},
                 "clocks": clocks, "gpu_launches": int(stats["launches"] * args.steps), "roofline": roofline}
@@ -498,10 +500,9 @@ def run_c4(args):
     torch.cuda.empty_cache()
     h.set_efflens(efflens)
     h.set_tree(*tree)
+    allreduce = None
     if world > 1:
-        uid = [pbapi.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        h.comm_init(world, rank, uid[0])
+        allreduce = pbapi.connect_ranks(h, dist)
         os.environ.setdefault("POLEE_BENCH_CLOCKS", "rank0")
     stats, info = h.step_stats(), h.layout_info()
     stream = torch.cuda.ExternalStream(h.stream(), device=dev)
@@ -556,7 +557,10 @@ def run_c4(args):
                 "data": "synthetic (polee-synth-v1, seed %d; every rank generates its own row block on its GPU)" % seed,
                 "config": {"workload": workload(args.config, m_loc * world, n, nnz_total, K)},
                 "details": {"partition": "%d ranks x %d rows each (same transcriptome, independent rows)" % (world, m_loc),
-                            "layout": "class layout: %.1f %% of the entries; general %s layout (rows longer than 64 "
+                            "allreduce": ("none (one rank)" if world == 1 else
+                                          "one kernel over NVLink peer memory (reduce-scatter by loads, all-gather by stores)"
+                                          if allreduce == "peer" else "ncclAllReduce (Float32) between narrow / widen kernels"),
+                                                        "layout": "class layout: %.1f %% of the entries; general %s layout (rows longer than 64 "
                                       "transcripts): %.1f %%" % (100 * tot[1].item() / nnz_total, info["general_kind"],
                                                                  100 * tot[2].item() / nnz_total),
                             "layout_build_s": round(t_layout, 3), "finite_fit": finite,

@@ -243,6 +243,14 @@ int polee_partition_rows(int64_t m, int64_t n, const uint32_t *colptr, const uin
                          int64_t *row_bounds /* nparts+1, 0-based half-open */);
 int polee_comm_unique_id(char id[128]);
 int polee_comm_init(polee_handle *h, int32_t nranks, int32_t rank, const char id[128]);
+/* Optional, after polee_comm_init and once n is known (matrix or tree set), on a box whose GPUs reach each other over
+ * NVLink / NVSwitch: the per-step all-reduce then runs as ONE kernel over peer memory (narrow, reduce-scatter by loads,
+ * all-gather by stores, widen; all ranks get bit-identical sums) instead of narrow -> ncclAllReduce -> widen.  Every rank
+ * calls polee_comm_peer_export (its CUDA IPC handle, 64 bytes), the host gathers the nranks handles in rank order by
+ * whatever transport it has, every rank calls polee_comm_peer_import with all of them.  If the import fails (no peer
+ * access) the NCCL path stays in use.  POLEE_ALLREDUCE=nccl | f64 selects the NCCL variants at run time. */
+int polee_comm_peer_export(polee_handle *h, char handle[64]);
+int polee_comm_peer_import(polee_handle *h, const char *handles /* nranks x 64 bytes; NULL: drop the mapping, back to NCCL */);
 
 #ifdef __cplusplus
 }

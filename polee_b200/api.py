@@ -271,6 +271,26 @@ class Handle:
         return xs
 
     # ---- multi-GPU
+    def comm_peer_export(self):
+        """This rank's CUDA IPC handle (64 bytes) for the peer-memory all-reduce; see comm_peer_import."""
+        buf = C.create_string_buffer(64)
+        self.check(self.lib.polee_comm_peer_export(self.h, buf))
+        return buf.raw
+
+    def comm_peer_import(self, handles):
+        """handles: the 64-byte handles of all ranks, in rank order (gathered by the caller, e.g. with
+        torch.distributed.all_gather_object).  Returns False (and keeps the NCCL all-reduce) when peer access is not
+        available."""
+        if handles is None:   # back to the NCCL all-reduce
+            self.check(self.lib.polee_comm_peer_import(self.h, None))
+            return False
+        blob = b"".join(handles)
+        rc = self.lib.polee_comm_peer_import(self.h, C.c_char_p(blob))
+        if rc == L.POLEE_ECUDA:
+            return False
+        self.check(rc)
+        return True
+
     def comm_init(self, nranks, rank, unique_id):
         self.check(self.lib.polee_comm_init(self.h, C.c_int32(nranks), C.c_int32(rank), C.c_char_p(unique_id)))
 
@@ -318,6 +338,29 @@ def comm_unique_id():
     if rc != 0:
         raise L.PoleeError(rc, "ncclGetUniqueId failed")
     return buf.raw
+
+
+def connect_ranks(h, dist):
+    """Join the handles of a row-partitioned fit (one process per GPU, `dist` = an initialised torch.distributed):
+    NCCL communicator (polee_comm_init) and, unless POLEE_ALLREDUCE=nccl|f64, the peer-memory all-reduce
+    (polee_comm_peer_export / _import; the IPC handles travel through dist.all_gather_object).  Returns "peer" or "nccl":
+    which all-reduce the step graph will use.  Call after the matrix or the tree is set."""
+    import os
+    world, rank = dist.get_world_size(), dist.get_rank()
+    uid = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    h.comm_init(world, rank, uid[0])
+    if world < 2 or os.environ.get("POLEE_ALLREDUCE", "") in ("nccl", "f64"):
+        return "nccl"
+    handles = [None] * world
+    dist.all_gather_object(handles, h.comm_peer_export())
+    ok = h.comm_peer_import(handles)
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok))   # every rank must take the same path
+    if not all(flags):
+        h.comm_peer_import(None)   # drop this rank's mapping too: all ranks stay on NCCL
+        return "nccl"
+    return "peer"
 
 
 def partition_rows(sample, nparts):

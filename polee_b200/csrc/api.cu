@@ -140,6 +140,8 @@ static void release_params(polee_handle *h) {
     h->mu = h->omega = h->alpha = h->m_mu = h->m_omega = h->m_alpha = h->v_mu = h->v_omega = h->v_alpha = h->mu0_dev = nullptr;
 }
 
+void polee::drop_step_graph(polee_handle *h) { drop_graph(h); }
+
 extern "C" int polee_destroy(polee_handle *h) {
     if (!h) return POLEE_OK;
     cudaSetDevice(h->device);
@@ -147,6 +149,7 @@ extern "C" int polee_destroy(polee_handle *h) {
     if (getenv("POLEE_SETUP_TIMING")) polee::dreport("handle lifetime");
     drop_graph(h);
 #ifdef POLEE_WITH_NCCL
+    polee::peer_release(h);
     if (h->comm) nccl_api().CommDestroy(h->comm);
 #endif
     release_work_buffers(h);
@@ -522,9 +525,15 @@ static int launch_step_sequence(polee_handle *h, bool do_adam, bool next_reparam
         // positive Float32-accurate terms, so nothing is lost that the 1e-5 gate could see); the K log-likelihood
         // sums, when requested, stay Float64.  POLEE_ALLREDUCE=f64 keeps the whole buffer in Float64.
         static const bool f64 = getenv("POLEE_ALLREDUCE") && !strcmp(getenv("POLEE_ALLREDUCE"), "f64");
+        static const bool nccl_only = getenv("POLEE_ALLREDUCE") && !strcmp(getenv("POLEE_ALLREDUCE"), "nccl");
         const size_t count = (size_t)h->n * KP;
-        ncclResult_t r;
-        if (f64 || !h->g32) {
+        ncclResult_t r = ncclSuccess;
+        if (h->peer_ready && !f64 && !nccl_only) {
+            // one kernel over NVLink peer memory (peer_allreduce.cu): narrow, reduce-scatter by loads, all-gather by
+            // stores, widen; the K log-likelihood sums, when requested, still go through NCCL as Float64
+            if ((rc = polee::launch_peer_allreduce(h, h->g, count))) return rc;
+            if (want_vals) r = nccl_api().AllReduce(h->g + count, h->g + count, KP, ncclDouble, ncclSum, h->comm, h->stream);
+        } else if (f64 || !h->g32) {
             r = nccl_api().AllReduce(h->g, h->g, count + (want_vals ? KP : 0), ncclDouble, ncclSum, h->comm, h->stream);
         } else {
             if ((rc = launch_narrow(h, h->g, h->g32, count))) return rc;
@@ -620,6 +629,7 @@ extern "C" int polee_sync(polee_handle *h) {
     CK(cudaGetLastError());
     int bad = 0;
     CK(polee::copy_sync(h->stream, &bad, h->d_bad_step, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad == polee::PEER_ERR_TIMEOUT) return h->fail(POLEE_ENCCL, "peer all-reduce: a rank did not arrive within the time limit");
     if (bad) return h->fail(POLEE_ENONFINITE, "non-finite gradient at step " + std::to_string(bad));
     return POLEE_OK;
 }
@@ -1056,6 +1066,7 @@ extern "C" int polee_comm_init(polee_handle *h, int32_t nranks, int32_t rank, co
     if (!nccl_api().ok) return h->fail(POLEE_ENCCL, "libnccl.so.2 could not be loaded");
     drop_graph(h);
     release_work_buffers(h);  // the multi-rank step needs the Float32 all-reduce buffer
+    polee::peer_release(h);
     if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     h->nranks = nranks;
     h->rank = rank;

@@ -419,6 +419,12 @@ struct polee_handle {
 
 #ifdef POLEE_WITH_NCCL
     ncclComm_t comm = nullptr;
+    // peer-memory all-reduce (peer_allreduce.cu): this rank's block, every rank's block as mapped here, floats per half
+    void *peer_local = nullptr;
+    void *peer_base[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t peer_cap = 0;
+    bool peer_ready = false;
 #endif
     int nranks = 1, rank = 0;
 
@@ -526,6 +532,11 @@ int launch_elbo(polee_handle *h, int KP, int K, bool have_lp);
 int ensure_gene_buffers(polee_handle *h, int KP);
 void release_gene_buffers(polee_handle *h);
 int launch_gene_prior(polee_handle *h, int KP);
+constexpr int PEER_MAX_RANKS = 16;
+constexpr int PEER_ERR_TIMEOUT = -1001;  // lands in d_bad_step when a peer never arrives
+void peer_release(polee_handle *h);
+int launch_peer_allreduce(polee_handle *h, double *g, size_t count);
+void drop_step_graph(polee_handle *h);
 
 // tree_chain.cu (caterpillar trees)
 int launch_chain_fwd(polee_handle *h, int KP, int clamp_x, const float *eff, double *Sp, int want_ladj, double *ladj_tree);

@@ -114,49 +114,78 @@ __global__ void __launch_bounds__(HSB_THREADS)
 // `ladj_i[0] -= log(u_data[j])` for j = 2n-2 .. 0 with a FLOAT accumulator (hsb_ops.cpp:211,234): every step rounds,
 // acc <- Float32(Float64(acc) - log u), so the result depends on the order and the chain cannot simply be re-associated.
 // It can be SPECULATED, though: while acc stays in one binade (and no step is an exact tie) a step moves acc by a whole
-// number of its ulps, q_k = rint(-log u_k / ulp), whatever acc is.  One warp per row takes 32 steps at a time: the lanes
-// form q_k, a shuffle scan gives the 32 candidate values, and every lane then checks ITS step with the reference's own
-// rule from its predecessor's candidate.  The steps before the first mismatch are exact by induction; the mismatching
+// number of its ulps, q_k = rint(-log u_k / ulp), whatever acc is.  One warp per row takes 256 steps at a time: the lanes
+// form q_k for 8 steps each, a shuffle scan gives the 256 candidate values, and every lane then checks ITS steps with the
+// reference's own rule from the predecessor's candidate.  The steps before the first mismatch are exact by induction; the mismatching
 // step (a binade change, a tie, acc == 0, non-finite values) is redone by the scalar rule, and the warp goes on from there.
+constexpr int LADJ_S = 8;  // steps per lane and iteration: a warp speculates 32 x 8 = 256 steps at a time
 __global__ void __launch_bounds__(128) k4_ladj_chain(int64_t B, int64_t nm1, const double *__restrict__ logu, float *__restrict__ ladj) {
     const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
     const double *lu = logu + (size_t)row * nm1;
     float acc = 0.0f;
-    int64_t k = nm1 - 1;  // next step (descending, as the reference's loop)
-    // the next 32 values are requested before the current ones are used: a chunk that verifies completely (the normal
-    // case) never waits for memory
-    double l_next = (k - lane >= 0) ? lu[k - lane] : 0.0;
+    int64_t k = nm1 - 1;  // next step (descending, as the reference's loop); lane j, slot i takes step k - (LADJ_S j + i)
     while (k >= 0) {
-        const int cnt = k + 1 < 32 ? (int)(k + 1) : 32;
-        const double l = l_next;
-        l_next = (k - 32 - lane >= 0) ? lu[k - 32 - lane] : 0.0;
+        const int64_t left = k + 1;
+        const int cnt = left < 32 * LADJ_S ? (int)left : 32 * LADJ_S;
+        double l[LADJ_S];
+#pragma unroll
+        for (int i = 0; i < LADJ_S; ++i) {
+            const int s = lane * LADJ_S + i;
+            l[i] = s < cnt ? lu[k - s] : 0.0;
+        }
         int e = 0;
         (void)frexpf(fabsf(acc), &e);  // |acc| = f 2^e, f in [0.5, 1): ulp(acc) = 2^(e - 24)
         const bool fin = acc != 0.0f && isfinite(acc);
         const double ulp = fin ? ldexp(1.0, e - 24) : 0.0, inv_ulp = fin ? ldexp(1.0, 24 - e) : 0.0;
-        double P = lane < cnt ? rint(-l * inv_ulp) : 0.0;  // this step in ulps (a power-of-two scaling: exact); then the scan
+        double q[LADJ_S], tot = 0.0;  // the steps in ulps (a power-of-two scaling: exact), prefix sums inside the lane
+#pragma unroll
+        for (int i = 0; i < LADJ_S; ++i) {
+            tot += (lane * LADJ_S + i < cnt) ? rint(-l[i] * inv_ulp) : 0.0;
+            q[i] = tot;
+        }
+        double P = tot;  // inclusive scan of the lane totals
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const double t = __shfl_up_sync(0xffffffffu, P, o);
             if (lane >= o) P += t;
         }
-        const float cand = (float)((double)acc + ulp * P);
-        float pred = __shfl_up_sync(0xffffffffu, cand, 1);
+        const double before = P - tot;  // ulps taken by the lanes below
+        float cand[LADJ_S];
+#pragma unroll
+        for (int i = 0; i < LADJ_S; ++i) cand[i] = (float)((double)acc + ulp * (before + q[i]));
+        float pred = __shfl_up_sync(0xffffffffu, cand[LADJ_S - 1], 1);
         if (lane == 0) pred = acc;
-        const bool ok = lane >= cnt || (float)__dsub_rn((double)pred, l) == cand;  // the reference's step, exactly
-        const unsigned bad = __ballot_sync(0xffffffffu, !ok);
-        const int f = bad ? __ffs((int)bad) - 1 : 32;  // first step that did not verify
-        if (f > 0) acc = __shfl_sync(0xffffffffu, cand, f - 1);
+        int first_bad = LADJ_S;  // first slot of this lane whose step does not verify by the reference's own rule
+#pragma unroll
+        for (int i = LADJ_S - 1; i >= 0; --i) {
+            const float p = i == 0 ? pred : cand[i - 1];
+            const bool ok = lane * LADJ_S + i >= cnt || (float)__dsub_rn((double)p, l[i]) == cand[i];
+            if (!ok) first_bad = i;
+        }
+        const unsigned bad = __ballot_sync(0xffffffffu, first_bad < LADJ_S);
+        const int bl = bad ? __ffs((int)bad) - 1 : 32;                       // first lane with a mismatch
+        const int bi = __shfl_sync(0xffffffffu, first_bad, bl < 32 ? bl : 0);
+        const int f = bl < 32 ? bl * LADJ_S + bi : 32 * LADJ_S;              // first step that did not verify
+        if (f > 0) {                                                         // steps 0 .. f-1 are exact: take step f-1's value
+            const int sl = (f - 1) / LADJ_S, si = (f - 1) % LADJ_S;
+            float v = cand[0];
+#pragma unroll
+            for (int i = 1; i < LADJ_S; ++i) v = si == i ? cand[i] : v;
+            acc = __shfl_sync(0xffffffffu, v, sl);
+        }
         int done = f < cnt ? f : cnt;
-        if (f < cnt) {
-            const double lf = __shfl_sync(0xffffffffu, l, f);
+        if (f < cnt) {                                                       // the mismatching step, by the scalar rule
+            const int sl = f / LADJ_S, si = f % LADJ_S;
+            double v = l[0];
+#pragma unroll
+            for (int i = 1; i < LADJ_S; ++i) v = si == i ? l[i] : v;
+            const double lf = __shfl_sync(0xffffffffu, v, sl);
             acc = (float)__dsub_rn((double)acc, lf);
             ++done;
         }
         k -= done;
-        if (done != 32 && k >= 0) l_next = (k - lane >= 0) ? lu[k - lane] : 0.0;  // the prefetch assumed a full chunk
     }
     if (lane == 0) ladj[row] = acc;
 }

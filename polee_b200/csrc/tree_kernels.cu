@@ -22,6 +22,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "device_utils.cuh"
 
 namespace polee {
 
@@ -595,19 +596,27 @@ __global__ void __launch_bounds__(DFS_RUNS_PER_CTA *KP)
     const int64_t c0 = (int64_t)blockIdx.x * DFS_CTA_NODES;
     const int nn = (int)(N - c0 < DFS_CTA_NODES ? N - c0 : DFS_CTA_NODES);
     const int k0 = cta_k0[blockIdx.x], nk = cta_k0[blockIdx.x + 1] - k0;
-    // ---- stage the CTA's y slice and node records (coalesced)
-    {
-        const double2 *src = reinterpret_cast<const double2 *>(ys + (size_t)k0 * KP);  // k0 KP doubles: 16-byte aligned for KP >= 2
-        double2 *dst = reinterpret_cast<double2 *>(ys_s);
-        const int nv = KP >= 2 ? nk * KP / 2 : 0;
-#pragma unroll 4
-        for (int idx = threadIdx.x; idx < nv; idx += THREADS) dst[idx] = src[idx];
-        if (KP < 2)
-            for (int idx = threadIdx.x; idx < nk * KP; idx += THREADS) ys_s[idx] = ys[(size_t)k0 * KP + idx];
-        const int4 *rsrc = reinterpret_cast<const int4 *>(dnodes + c0);
-        int4 *rdst = reinterpret_cast<int4 *>(rec_s);
-#pragma unroll 4
-        for (int idx = threadIdx.x; idx < nn; idx += THREADS) rdst[(idx / DFS_RUN) * RS + idx % DFS_RUN] = rsrc[idx];
+    // ---- stage the CTA's y slice (one contiguous piece of ys) and node records with 1-D bulk copies (TMA) completing
+    // on an mbarrier; they are in flight while the threads walk the root paths
+    __shared__ uint64_t bar;
+    const bool bulk = KP >= 2;  // 16-byte granularity: k0 KP and nk KP doubles are even then
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, (uint32_t)(nk * KP * 8 + nn * (int)sizeof(DNode)));
+            if (nk > 0) bulk_g2s(ys_s, ys + (size_t)k0 * KP, (uint32_t)(nk * KP * 8), &bar);
+            for (int q = 0; q * DFS_RUN < nn; ++q) {
+                const int len = nn - q * DFS_RUN < DFS_RUN ? nn - q * DFS_RUN : DFS_RUN;
+                bulk_g2s(rec_s + q * RS, dnodes + c0 + (int64_t)q * DFS_RUN, (uint32_t)(len * sizeof(DNode)), &bar);
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < nk * KP; idx += THREADS) ys_s[idx] = ys[(size_t)k0 * KP + idx];
+        for (int idx = threadIdx.x; idx < nn; idx += THREADS) rec_s[(idx / DFS_RUN) * RS + idx % DFS_RUN] = dnodes[c0 + idx];
     }
     // ---- the run's starting state: down the root path of its first node
     const int64_t i0 = c0 + (int64_t)rl * DFS_RUN;
@@ -615,17 +624,18 @@ __global__ void __launch_bounds__(DFS_RUNS_PER_CTA *KP)
     double *st = stack + threadIdx.x;
     double u = 1.0;
     if (cnt > 0) {
+        constexpr int AB = 16;  // ancestors per batch: their y are all requested before the first product
         const int64_t run = i0 / DFS_RUN;
         const uint32_t a0 = run_anc_ptr[run], na = run_anc_ptr[run + 1] - a0;
-        for (uint32_t a = 0; a < na; a += 8) {
-            uint32_t en[8];
-            double yv[8];
+        for (uint32_t a = 0; a < na; a += AB) {
+            uint32_t en[AB];
+            double yv[AB];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) en[j] = a + j < na ? run_anc[a0 + a + j] : 0u;
+            for (int j = 0; j < AB; ++j) en[j] = a + j < na ? run_anc[a0 + a + j] : 0u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) yv[j] = a + j < na ? ys[(size_t)(en[j] >> 1) * KP + k] : 0.0;
+            for (int j = 0; j < AB; ++j) yv[j] = a + j < na ? ys[(size_t)(en[j] >> 1) * KP + k] : 0.0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < AB; ++j) {
                 if (a + j < na) {
                     const double ul = __dmul_rn(yv[j], u), ur = __dmul_rn(__dsub_rn(1.0, yv[j]), u);
                     if (en[j] & 1u) {
@@ -638,18 +648,26 @@ __global__ void __launch_bounds__(DFS_RUNS_PER_CTA *KP)
             }
         }
     }
-    __syncthreads();
-    // ---- the run, in node order
+    if (bulk) mbar_wait(&bar, 0);
+    else __syncthreads();
+    // ---- the run, in node order.  The record and the y of the NEXT node are fetched before the current node is
+    // worked on, so that only the products (and the stack read of a left child) are on the thread's critical path
     double sacc = 0.0, lacc = 0.0, carry = 0.0;
     const DNode *rr = rec_s + rl * RS;
+    DNode rn = cnt > 0 ? rr[0] : DNode{-1, 0u, 1.0f, 0u};
+    double yn = (cnt > 0 && rn.k_or_leaf >= 0) ? ys_s[(rn.k_or_leaf - k0) * KP + k] : 0.0;
     for (int j = 0; j < cnt; ++j) {
-        const DNode r = rr[j];
+        const DNode r = rn;
+        const double y = yn, omy = __dsub_rn(1.0, yn);
+        if (j + 1 < cnt) {
+            rn = rr[j + 1];
+            yn = rn.k_or_leaf >= 0 ? ys_s[(rn.k_or_leaf - k0) * KP + k] : 0.0;
+        }
         const uint32_t d = r.meta & 0x7fffffffu;
         if (j > 0) u = (r.meta >> 31) ? st[(size_t)d * THREADS] : carry;
         if (r.k_or_leaf >= 0) {
-            const double y = ys_s[(r.k_or_leaf - k0) * KP + k];
             st[(size_t)(d + 1) * THREADS] = __dmul_rn(y, u);
-            carry = __dmul_rn(__dsub_rn(1.0, y), u);
+            carry = __dmul_rn(omy, u);
             us_k[(size_t)r.k_or_leaf * KP + k] = u;
             if (want_ladj) lacc += log(u);
         } else {

@@ -326,6 +326,20 @@ def test_optimize_ptt(pb, fx, oracle, exact):
     assert np.median(np.abs(xd[big] - xo[big]) / xo[big]) < (1e-3 if exact else 1e-2)
 
 
+@pytest.mark.parametrize("exact", [0, 1])
+def test_optimize_ptt_first_steps_tight(pb, fx, oracle, exact):
+    """OptimizePTTApprox step by step (l-a.jl:149-242): after 1, 2 and 3 ADAM steps the device's x equals the oracle's
+    elementwise -- before the depth-312 chain has had time to amplify last-bit differences of the gradient."""
+    for steps in (1, 2, 3):
+        xo = oracle.fit_optimize_ptt(fx.m, fx.n, fx.colptr, fx.rowval, fx.nzval, fx.efflens, steps)
+        h = pb.Handle(approx=1, num_steps=steps, exact_accumulation=exact)
+        h.set_sample(_sample(pb, fx))
+        xd = h.fit_optimize_ptt()
+        h.close()
+        err = np.max(np.abs(xd.astype(np.float64) - xo) / np.maximum(xo, 1e-30))
+        assert err <= (2e-6 if exact else 2e-5), (steps, err)
+
+
 def test_synthetic_sample_all_paths(pb, small_synth, oracle):
     s = small_synth
     K = 8

@@ -24,9 +24,7 @@ block = pbapi.row_block(whole, bounds[rank], bounds[rank + 1])
 h = pb.Handle(device=local, num_steps=steps, num_mc_samples=8, seed=4242)
 h.set_sample(block)
 h.set_tree(*tree)
-uid = [pbapi.comm_unique_id() if rank == 0 else None]
-dist.broadcast_object_list(uid, src=0)
-h.comm_init(world, rank, uid[0])
+allreduce = pbapi.connect_ranks(h, dist)
 h.init_params()
 h.run_steps(steps)
 h.sync()

@@ -31,9 +31,7 @@ h.set_matrix_device(m_loc, n, cp.data_ptr(), rv.data_ptr(), nz.data_ptr())
 h.set_efflens(efflens)
 h.set_tree(*tree)
 if world > 1:
-    uid = [pbapi.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    h.comm_init(world, rank, uid[0])
+    allreduce = pbapi.connect_ranks(h, dist)
 h.init_params()
 stream = torch.cuda.ExternalStream(h.stream(), device=dev)
 torch.cuda.synchronize()
