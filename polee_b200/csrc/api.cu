@@ -55,6 +55,12 @@ static std::mutex g_err_mu;
     if (cudaSetDevice((h)->device) != cudaSuccess) return (h)->fail(POLEE_ECUDA, "cudaSetDevice failed")
 
 constexpr int TREE_BIN_NODES = 512;
+// nodes per bottom bin of the tree schedule (POLEE_TREE_BIN_NODES: experiments)
+static int tree_bin_nodes() {
+    const char *e = getenv("POLEE_TREE_BIN_NODES");
+    const int v = e ? atoi(e) : TREE_BIN_NODES;
+    return v >= 32 && v <= 8192 ? v : TREE_BIN_NODES;
+}
 
 static void drop_graph(polee_handle *h) {
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
@@ -126,7 +132,9 @@ extern "C" int polee_create(polee_handle **out, const polee_opts *opts) {
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         polee::dmalloc((void **)&h->d_step, sizeof(StepCtl)) != cudaSuccess ||
-        polee::dmalloc((void **)&h->d_bad_step, sizeof(int)) != cudaSuccess) {
+        polee::dmalloc((void **)&h->d_bad_step, sizeof(int)) != cudaSuccess ||
+        polee::dmalloc((void **)&h->d_leafS_counter, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemsetAsync(h->d_leafS_counter, 0, sizeof(unsigned int), h->stream) != cudaSuccess) {
         delete h;
         return fail(POLEE_ECUDA, "stream / control block allocation failed");
     }
@@ -157,7 +165,7 @@ extern "C" int polee_destroy(polee_handle *h) {
     release_params(h);
     h->td.release();
     polee::dfree(h->efflen); polee::dfree(h->efflen_adj); polee::dfree(h->elbo); polee::dfree(h->noise);
-    polee::dfree(h->d_step); polee::dfree(h->d_bad_step);
+    polee::dfree(h->d_step); polee::dfree(h->d_bad_step); polee::dfree(h->d_leafS_counter);
     release_gene_buffers(h);
     polee::dfree(h->gene_ptr); polee::dfree(h->gene_tx);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
@@ -365,7 +373,7 @@ extern "C" int polee_set_tree(polee_handle *h, int64_t n, const int32_t *node_pa
     release_work_buffers(h);
     h->have_tree = false;
     HostPhaseTimer pt;
-    return finish_tree(h, h->th.build_from_parents(n, node_parent_idxs, node_js, TREE_BIN_NODES), pt);
+    return finish_tree(h, h->th.build_from_parents(n, node_parent_idxs, node_js, tree_bin_nodes()), pt);
 }
 
 extern "C" int polee_set_tree_sequential(polee_handle *h, int64_t n) {

@@ -182,8 +182,6 @@ constexpr int DFS_MAX_DEPTH = 96;      // deeper trees keep the path-product / l
 struct DNode {
     int32_t k_or_leaf;  // >= 0: internal node, index k; < 0: leaf, transcript = -1 - v
     uint32_t meta;      // depth | (1u << 31 if the node is its parent's LEFT child, i.e. the child that comes second)
-    float efflen;       // leaves: the transcript's effective length (patched in once the lengths are known)
-    uint32_t pad;
 };
 
 // Tree node, 0-based; leaf < 0 <=> internal node (then k = index among internal nodes in node order).
@@ -379,10 +377,12 @@ struct polee_handle {
     float *v_mu = nullptr, *v_omega = nullptr, *v_alpha = nullptr;
     polee::StepCtl *d_step = nullptr;  // device step counters
     int *d_bad_step = nullptr;         // first step with a non-finite gradient, 0 = none
+    unsigned int *d_leafS_counter = nullptr;  // k3_leaf_S: CTAs finished (the last one reduces; it resets the counter)
     int steps_enqueued = 0;
     polee_progress_fn progress_cb = nullptr;  // polee_set_progress
     void *progress_user = nullptr;
     int progress_every = 0;
+    bool S_deferred = false;  // the forward kernel left S = sum_j x_j / efflen_j to k3_leaf_S (launched by launch_mid)
     bool reparam_ready = false;  // ys / zs0 of the next step have been produced (fused update + reparam kernel)
 
     // ---- per-step work buffers (layouts [item][KP])

@@ -100,13 +100,11 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
     dnodes.clear(); drun_anc_ptr.clear(); drun_anc.clear(); dcta_k0.clear();
     dfs_max_nk = 0;
     if (preorder) {
-        dnodes.resize(N);
+        dnodes.assign(N + 1, DNode{-1, 0u});  // one padding record: the kernel copies records in pairs
         for (int64_t i = 0; i < N; ++i) {
             const bool is_left = i > 0 && nodes[parent[i]].left == (int32_t)i;
             dnodes[i].k_or_leaf = nodes[i].leaf >= 0 ? -1 - nodes[i].leaf : nodes[i].k;
             dnodes[i].meta = (uint32_t)depth[i] | (is_left ? 0x80000000u : 0u);
-            dnodes[i].efflen = 1.0f;
-            dnodes[i].pad = 0u;
         }
         const int64_t nruns = (N + DFS_RUN - 1) / DFS_RUN;
         drun_anc_ptr.reserve(nruns + 1);

@@ -29,7 +29,7 @@ namespace polee {
 namespace {
 
 constexpr int TREE_THREADS = 256;
-constexpr int ELEM_THREADS = 256;  // k3_elem: one lane per (internal node, draw)
+constexpr int ELEM_THREADS = 128;  // k3_elem: one thread per internal node; small CTAs keep the tail wave short
 constexpr int TOP_THREADS = 1024;
 
 // ---------------------------------------------------------------- noise ("polee-philox-v1")
@@ -583,10 +583,9 @@ template <int KP>
 __global__ void __launch_bounds__(DFS_RUNS_PER_CTA *KP)
     k3d_tree_fwd(int64_t N, const DNode *__restrict__ dnodes, const uint32_t *__restrict__ run_anc_ptr,
                  const uint32_t *__restrict__ run_anc, const int32_t *__restrict__ cta_k0, const double *__restrict__ ys,
-                 double *__restrict__ us_k, float *__restrict__ x, double *__restrict__ xd, int clamp_x,
-                 const float *__restrict__ efflen, double *__restrict__ S_partial, int want_ladj,
+                 double *__restrict__ us_k, float *__restrict__ x, double *__restrict__ xd, int clamp_x, int want_ladj,
                  double *__restrict__ ladj_partial, int stack_levels, int max_nk) {
-    constexpr int THREADS = DFS_RUNS_PER_CTA * KP, RS = DFS_RUN + 1;  // record stride of a run (odd: no bank conflicts)
+    constexpr int THREADS = DFS_RUNS_PER_CTA * KP, RS = DFS_RUN + 2;  // record stride of a run: 16-byte aligned, 4 banks apart
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ double red[THREADS];
     double *stack = reinterpret_cast<double *>(smraw);                      // [stack_levels][THREADS]
@@ -607,10 +606,12 @@ __global__ void __launch_bounds__(DFS_RUNS_PER_CTA *KP)
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar, (uint32_t)(nk * KP * 8 + nn * (int)sizeof(DNode)));
+            // 8-byte records, 16-byte copies: an odd tail takes the padding record the host appended
+            const int nn2 = (nn + 1) & ~1;
+            mbar_expect_tx(&bar, (uint32_t)(nk * KP * 8 + nn2 * (int)sizeof(DNode)));
             if (nk > 0) bulk_g2s(ys_s, ys + (size_t)k0 * KP, (uint32_t)(nk * KP * 8), &bar);
-            for (int q = 0; q * DFS_RUN < nn; ++q) {
-                const int len = nn - q * DFS_RUN < DFS_RUN ? nn - q * DFS_RUN : DFS_RUN;
+            for (int q = 0; q * DFS_RUN < nn2; ++q) {
+                const int len = nn2 - q * DFS_RUN < DFS_RUN ? nn2 - q * DFS_RUN : DFS_RUN;
                 bulk_g2s(rec_s + q * RS, dnodes + c0 + (int64_t)q * DFS_RUN, (uint32_t)(len * sizeof(DNode)), &bar);
             }
         }
@@ -652,9 +653,9 @@ __global__ void __launch_bounds__(DFS_RUNS_PER_CTA *KP)
     else __syncthreads();
     // ---- the run, in node order.  The record and the y of the NEXT node are fetched before the current node is
     // worked on, so that only the products (and the stack read of a left child) are on the thread's critical path
-    double sacc = 0.0, lacc = 0.0, carry = 0.0;
+    double lacc = 0.0, carry = 0.0;
     const DNode *rr = rec_s + rl * RS;
-    DNode rn = cnt > 0 ? rr[0] : DNode{-1, 0u, 1.0f, 0u};
+    DNode rn = cnt > 0 ? rr[0] : DNode{-1, 0u};
     double yn = (cnt > 0 && rn.k_or_leaf >= 0) ? ys_s[(rn.k_or_leaf - k0) * KP + k] : 0.0;
     for (int j = 0; j < cnt; ++j) {
         const DNode r = rn;
@@ -672,21 +673,84 @@ __global__ void __launch_bounds__(DFS_RUNS_PER_CTA *KP)
             if (want_ladj) lacc += log(u);
         } else {
             const int leaf = -1 - r.k_or_leaf;
-            float xv = (float)u;
-            double dd = (double)xv;
-            xv = (float)(dd > 1e-16 ? dd : 1e-16);  // ptt.jl:136-137
-            if (clamp_x) {                           // clamp!(xs, 1e-10, 1 - 1e-10) on a Float32 vector
-                dd = (double)xv;
-                dd = fmin(fmax(dd, 1e-10), 1.0 - 1e-10);
-                xv = (float)dd;
-            }
+            // xs[j] = max(us[i], 1e-16) stored as Float32 (ptt.jl:136-137), then clamp!(xs, 1e-10, 1 - 1e-10) on the Float32
+            // vector (l-a.jl:526).  In Float32 alone: a Float32 lies below the Float64 bound exactly when it lies below the
+            // bound rounded to Float32, and Float32(1 - 1e-10) is 1, so these are the reference's values bit for bit
+            float xv = fmaxf((float)u, (float)1e-16);
+            if (clamp_x) xv = fminf(fmaxf(xv, (float)1e-10), 1.0f);
             x[(size_t)leaf * KP + k] = xv;
             if (xd) xd[(size_t)leaf * KP + k] = (double)xv;
-            if (efflen) sacc = __dadd_rn(sacc, (double)__fdiv_rn(xv, r.efflen));  // the record carries efflen[leaf]
         }
     }
-    if (S_partial) block_reduce_kc<KP, THREADS>(sacc, red, S_partial + (size_t)blockIdx.x * KP);
     if (want_ladj) block_reduce_kc<KP, THREADS>(lacc, red, ladj_partial + (size_t)blockIdx.x * KP);
+}
+
+// S_k = sum_j x_jk / efflen_j (effective_length_jacobian_adjustment!, likelihood.jl:96-100: Float32 quotients, Float64
+// sum) and the step bookkeeping of k3_mid, for the forward kernels that leave S out of their node loop.  A warp adds
+// LEAF_S_PER_WARP transcripts (all loads of a batch in flight, fixed order) and writes one partial row; the CTA that
+// finishes last adds the partial rows, again in a fixed order.  Small on purpose (128 threads, ~1 KB of shared memory):
+// it runs on the side stream in the registers and shared memory the likelihood kernel leaves free on every SM.
+constexpr int LEAF_S_THREADS = 128, LEAF_S_PER_WARP = 256;
+template <int KP>
+__global__ void __launch_bounds__(LEAF_S_THREADS)
+    k3_leaf_S(int64_t n, const float *__restrict__ x, const float *__restrict__ efflen, double *__restrict__ S_partial,
+              int nwarps, double *__restrict__ S, StepCtl *ctl, int advance, unsigned int *counter) {
+    constexpr int LPW = 32 / KP;  // transcripts per warp-wide step
+    constexpr int UN = 8;
+    __shared__ double red[LEAF_S_THREADS];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, k = lane % KP, slot = lane / KP;
+    const int w = (int)((blockIdx.x * (size_t)LEAF_S_THREADS + threadIdx.x) >> 5);
+    if (w < nwarps) {
+        const int64_t j0 = (int64_t)w * LEAF_S_PER_WARP, j1 = j0 + LEAF_S_PER_WARP < n ? j0 + LEAF_S_PER_WARP : n;
+        double sacc = 0.0;
+        for (int64_t jb = j0 + slot; jb < j1; jb += (int64_t)UN * LPW) {
+            float xv[UN], ev[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int64_t j = jb + (int64_t)u * LPW;
+                xv[u] = j < j1 ? x[(size_t)j * KP + k] : 0.0f;
+                ev[u] = j < j1 ? efflen[j] : 1.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) sacc = __dadd_rn(sacc, (double)__fdiv_rn(xv[u], ev[u]));
+        }
+#pragma unroll
+        for (int o = KP; o < 32; o <<= 1) sacc = __dadd_rn(sacc, __shfl_xor_sync(0xffffffffu, sacc, o));
+        if (lane < KP) S_partial[(size_t)w * KP + k] = sacc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // the last CTA: S[k] = sum over the warps' partial rows
+    constexpr int SLOTS = LEAF_S_THREADS / KP;
+    const int kk = threadIdx.x % KP, ss = threadIdx.x / KP;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int t = ss;
+    for (; t + 3 * SLOTS < nwarps; t += 4 * SLOTS) {
+        a0 += __ldcg(S_partial + (size_t)t * KP + kk);
+        a1 += __ldcg(S_partial + (size_t)(t + SLOTS) * KP + kk);
+        a2 += __ldcg(S_partial + (size_t)(t + 2 * SLOTS) * KP + kk);
+        a3 += __ldcg(S_partial + (size_t)(t + 3 * SLOTS) * KP + kk);
+    }
+    for (; t < nwarps; t += SLOTS) a0 += __ldcg(S_partial + (size_t)t * KP + kk);
+    red[threadIdx.x] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    for (int span = SLOTS / 2; span >= 1; span >>= 1) {
+        if (ss < span) red[threadIdx.x] += red[threadIdx.x + span * KP];
+        __syncthreads();
+    }
+    if (threadIdx.x < KP) S[threadIdx.x] = red[threadIdx.x];
+    if (threadIdx.x == 0) {
+        *counter = 0u;
+        if (advance) {
+            ctl->step_upd = ctl->step_fwd;
+            ctl->step_fwd = ctl->step_fwd + 1;
+        }
+    }
 }
 
 // Leaf records carry the leaf's effective length (left) and Float32(n / efflen) (right) as raw Float32 bits, so the
@@ -701,13 +765,6 @@ __global__ void k_patch_leaf_recs(SNode *recs, int count, const float *__restric
         r.right = __float_as_int(adj[leaf]);
         recs[q] = r;
     }
-}
-
-__global__ void k_patch_dnodes(DNode *recs, int64_t count, const float *__restrict__ efflen) {
-    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (q >= count) return;
-    const int32_t v = recs[q].k_or_leaf;
-    if (v < 0) recs[q].efflen = efflen[-1 - v];
 }
 
 // ---------------------------------------------------------------- reparameterisation backward + ADAM
@@ -735,15 +792,10 @@ __device__ __forceinline__ void adam_one(float &param, float &m, float &v, doubl
     param = (float)__dadd_rn((double)param, delta);
 }
 
-// Both halves of the step boundary in one pass over the parameters.  A CTA owns ELEM_THREADS / KP consecutive nodes
-// and works in two arrangements: per-DRAW work (the terms of the backward pass, noise, zs -> ys) runs one lane per
-// (node, draw) -- the KP lanes of a node sit next to each other, so ys / ygrad / zs0 move coalesced -- and per-NODE
-// work (exp / sinh / cosh of the parameters, the accumulation over the draws, ADAM) runs one lane per node, or per
-// (parameter, node), with the two sides meeting in shared memory:
-//   UPDATE  (step s):   every (node, draw) lane forms its draw's terms of the logit-normal + sinh-arcsinh backward;
-//                       one lane per (parameter, node) adds them in draw order with the reference's roundings, divides
-//                       by K, checks for non-finite values and does that parameter's ADAM ascent with step clamp
-//   REPARAM (step s+1): noise -> zs -> ys per (node, draw) lane from the updated parameters
+// One thread per internal node; both halves of the step boundary in one pass over the parameters:
+//   UPDATE  (step s):   logit-normal + sinh-arcsinh backward accumulated over the K draws in draw order, /K, finite
+//                       check, ADAM ascent with step clamp
+//   REPARAM (step s+1): noise -> zs -> ys for the next step's tree forward
 // sinh(alpha + asinh z0) is evaluated as z0 cosh(alpha) + sqrt(1 + z0^2) sinh(alpha) (and cosh(c), tanh(c)
 // likewise from cosh/sinh(alpha)): the same real function as the reference's Float32 expression with two
 // transcendentals per NODE instead of four per DRAW; the difference is a few Float32 ulp.
@@ -756,63 +808,37 @@ __global__ void __launch_bounds__(ELEM_THREADS)
             const StepCtl *__restrict__ ctl, AdamCfg cfg, int *__restrict__ bad_step, float *__restrict__ grad_out,
             const float *__restrict__ noise, int64_t noise_steps, uint64_t seed, int fast_noise, int want_ladj,
             double *__restrict__ ladj_partial /* [2][gridDim.x][KP] */, int step0_fixed, int clamp_y) {
-    constexpr int NODES = ELEM_THREADS / KP;   // nodes per CTA
-    constexpr int TS = NODES + 1;              // stride of a draw's row of terms (odd: conflict-free per-node reads)
-    __shared__ double sm_d[2][KP * TS > ELEM_THREADS ? KP * TS : ELEM_THREADS];  // mu terms [draw][node]; ladj reductions
-    __shared__ float sm_f[3][KP * TS];         // omega term, alpha terms [draw][node]
-    __shared__ float nd_par[3][NODES];         // mu, omega, alpha of the CTA's nodes
-    __shared__ float nd_tr[4][NODES];          // exp(omega), sinh(alpha), cosh(alpha), 1 / exp(omega)
-    __shared__ double adam_c[3];               // learning rate, 1 - beta1^t, 1 - beta2^t
-    const int k = threadIdx.x % KP, nl = threadIdx.x / KP;
-    const int64_t node0 = blockIdx.x * (int64_t)NODES, i = node0 + nl;
+    __shared__ double sm[ELEM_THREADS];
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool live = i < nm1;
-
-    // ---- per node: parameters and their transcendentals
-    if (threadIdx.x < NODES && node0 + threadIdx.x < nm1) {
-        const int64_t ii = node0 + threadIdx.x;
-        const float pm = mu[ii];
-        nd_par[0][threadIdx.x] = pm;
-        if (mode == 0) {
-            const float po = omega[ii], pa = alpha[ii], sg = expf(po);
-            nd_par[1][threadIdx.x] = po;
-            nd_par[2][threadIdx.x] = pa;
-            nd_tr[0][threadIdx.x] = sg;
-            nd_tr[1][threadIdx.x] = sinhf(pa);
-            nd_tr[2][threadIdx.x] = coshf(pa);
-            nd_tr[3][threadIdx.x] = __fdiv_rn(1.0f, sg);
-        }
+    float p_mu = 0.f, p_om = 0.f, p_al = 0.f;
+    if (live) {
+        p_mu = mu[i];
+        if (mode == 0) { p_om = omega[i]; p_al = alpha[i]; }
     }
-    int step = 0;
-    if (do_update) {
-        step = ctl->step_upd;
-        if (threadIdx.x == ELEM_THREADS - 1) {
-            adam_c[0] = fmax(1e-3, 1.0 * exp(-2e-2 * (double)(step - 1)));  // adam_learning_rate(step_num - 1)  l-a.jl:107-110, 497
-            adam_c[1] = 1.0 - pow(0.7, (double)step);
-            adam_c[2] = 1.0 - pow(0.9, (double)step);
-        }
-    }
-    __syncthreads();
 
-    if (do_update) {
-        const double lr = adam_c[0], m_denom = adam_c[1], v_denom = adam_c[2];
-        if (mode == 1) {  // OptimizePTTApprox (K = 1): z_grad = y (1 - y) y_grad, Float64 (l-a.jl:211-213)
-            if (live && k == 0) {
-                float p_mu = nd_par[0][nl];
-                const double y = ys[(size_t)i * KP];
-                const double zg = __dmul_rn(__dmul_rn(y, __dsub_rn(1.0, y)), ygrad[(size_t)i * KP]);
-                if (grad_out) grad_out[i] = (float)zg;
-                if (!isfinite(zg)) atomicCAS(bad_step, 0, step);
-                if (do_adam) {
-                    float mm = m_mu[i], vv = v_mu[i];
-                    adam_one(p_mu, mm, vv, zg, 0.0f, false, step, lr, m_denom, v_denom, cfg.max_step_z);
-                    m_mu[i] = mm; v_mu[i] = vv; mu[i] = p_mu;
-                    nd_par[0][nl] = p_mu;
-                }
+    if (do_update && live) {
+        const int step = ctl->step_upd;
+        // adam_learning_rate(step_num - 1)  l-a.jl:107-110, 497
+        const double lr = fmax(1e-3, 1.0 * exp(-2e-2 * (double)(step - 1)));
+        const double m_denom = 1.0 - pow(0.7, (double)step), v_denom = 1.0 - pow(0.9, (double)step);
+        if (mode == 1) {  // OptimizePTTApprox: z_grad = y (1 - y) y_grad, Float64 (l-a.jl:211-213)
+            const double y = ys[(size_t)i * KP];
+            const double zg = __dmul_rn(__dmul_rn(y, __dsub_rn(1.0, y)), ygrad[(size_t)i * KP]);
+            if (grad_out) grad_out[i] = (float)zg;
+            if (!isfinite(zg)) atomicCAS(bad_step, 0, step);
+            if (do_adam) {
+                float mm = m_mu[i], vv = v_mu[i];
+                adam_one(p_mu, mm, vv, zg, 0.0f, false, step, lr, m_denom, v_denom, cfg.max_step_z);
+                m_mu[i] = mm; v_mu[i] = vv; mu[i] = p_mu;
             }
-            __syncthreads();
         } else {
-            if (live && k < K) {  // this draw's terms
-                const float sigma = nd_tr[0][nl], sa = nd_tr[1][nl], ca = nd_tr[2][nl], inv_sigma = nd_tr[3][nl];
+            const float sigma = expf(p_om);
+            const float sa = sinhf(p_al), ca = coshf(p_al);
+            const float inv_sigma = __fdiv_rn(1.0f, sigma);
+            float mu_g = 0.0f, om_g = 0.0f, al_g = 0.0f;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
                 const double y = ys[(size_t)i * KP + k];
                 const double yg = ygrad[(size_t)i * KP + k];  // already rounded to Float32
                 const float z0 = zs0[(size_t)i * KP + k];
@@ -823,105 +849,99 @@ __global__ void __launch_bounds__(ELEM_THREADS)
                 const double d = __dmul_rn(y, __dsub_rn(1.0, y));
                 const double omy2 = __dsub_rn(1.0, __dmul_rn(2.0, y));
                 // logit_normal_transform_gradients! (8-arg)  logitnormal.jl:38-55; sigma_grad / z_grad restart per draw
+                mu_g = (float)__dadd_rn((double)mu_g, __dmul_rn(d, yg));
                 float sg = (float)__dmul_rn(__dmul_rn(d, z), yg);
                 float zg = (float)__dmul_rn(__dmul_rn(d, (double)sigma), yg);
+                mu_g = (float)__dadd_rn((double)mu_g, omy2);
                 sg = (float)__dadd_rn((double)sg, __dadd_rn((double)inv_sigma, __dmul_rn(z, omy2)));
                 zg = (float)__dadd_rn((double)zg, __dmul_rn((double)sigma, omy2));
-                const int t = k * TS + nl;
-                sm_d[0][t] = __dmul_rn(d, yg);  // mu_grad += d y_grad; mu_grad += 1 - 2 y
-                sm_d[1][t] = omy2;
-                sm_f[0][t] = __fmul_rn(sigma, sg);  // omega chain rule  l-a.jl:547-549
                 // sinh_asinh_transform_gradients!  sinh_arcsinh.jl:29-38: cosh(c) z_grad + tanh(c)
-                sm_f[1][t] = __fmul_rn(ch, zg);
-                sm_f[2][t] = __fdiv_rn(zf, ch);
+                al_g = __fadd_rn(al_g, __fmul_rn(ch, zg));
+                al_g = __fadd_rn(al_g, __fdiv_rn(zf, ch));
+                // omega chain rule  l-a.jl:547-549
+                om_g = __fadd_rn(om_g, __fmul_rn(sigma, sg));
             }
-            __syncthreads();
-            // one lane per (parameter, node): p = 0 mu, 1 omega, 2 alpha
-            for (int t = threadIdx.x; t < 3 * NODES; t += ELEM_THREADS) {
-                const int p = t / NODES, nn = t - p * NODES;
-                const int64_t ii = node0 + nn;
-                if (ii >= nm1) continue;
-                float g = 0.0f;  // the Float32 accumulator of the reference, fed in draw order
-                if (p == 0) {
-                    for (int kk = 0; kk < K; ++kk) {
-                        g = (float)__dadd_rn((double)g, sm_d[0][kk * TS + nn]);
-                        g = (float)__dadd_rn((double)g, sm_d[1][kk * TS + nn]);
-                    }
-                } else if (p == 1) {
-                    for (int kk = 0; kk < K; ++kk) g = __fadd_rn(g, sm_f[0][kk * TS + nn]);
-                } else {
-                    for (int kk = 0; kk < K; ++kk) {
-                        g = __fadd_rn(g, sm_f[1][kk * TS + nn]);
-                        g = __fadd_rn(g, sm_f[2][kk * TS + nn]);
-                    }
-                }
-                g = __fdiv_rn(g, (float)K);  // l-a.jl:552-556
-                if (!isfinite(g)) atomicCAS(bad_step, 0, step);
-                if (grad_out) grad_out[(size_t)p * nm1 + ii] = g;
-                if (do_adam) {
-                    float *par = p == 0 ? mu : (p == 1 ? omega : alpha);
-                    float *ms = p == 0 ? m_mu : (p == 1 ? m_omega : m_alpha);
-                    float *vs = p == 0 ? v_mu : (p == 1 ? v_omega : v_alpha);
-                    float pv = nd_par[p][nn];
-                    float mm = ms[ii], vv = vs[ii];
-                    adam_one(pv, mm, vv, (double)g, __fmul_rn(g, g), true, step, lr, m_denom, v_denom,
-                             p == 0 ? cfg.max_step_mu : (p == 1 ? cfg.max_step_omega : cfg.max_step_alpha));
-                    ms[ii] = mm; vs[ii] = vv; par[ii] = pv;
-                    nd_par[p][nn] = pv;
-                }
+            const float Kf = (float)K;
+            mu_g = __fdiv_rn(mu_g, Kf);  // l-a.jl:552-556
+            om_g = __fdiv_rn(om_g, Kf);
+            al_g = __fdiv_rn(al_g, Kf);
+            if (!(isfinite(mu_g) && isfinite(om_g) && isfinite(al_g))) atomicCAS(bad_step, 0, step);
+            if (grad_out) {
+                grad_out[i] = mu_g;
+                grad_out[nm1 + i] = om_g;
+                grad_out[2 * nm1 + i] = al_g;
             }
-            __syncthreads();
-            if (do_adam && do_reparam) {  // transcendentals of the updated parameters
-                if (threadIdx.x < NODES && node0 + threadIdx.x < nm1) {
-                    const float sg = expf(nd_par[1][threadIdx.x]), pa = nd_par[2][threadIdx.x];
-                    nd_tr[0][threadIdx.x] = sg;
-                    nd_tr[1][threadIdx.x] = sinhf(pa);
-                    nd_tr[2][threadIdx.x] = coshf(pa);
-                }
-                __syncthreads();
+            if (do_adam) {
+                float mm = m_mu[i], vv = v_mu[i];
+                adam_one(p_mu, mm, vv, (double)mu_g, __fmul_rn(mu_g, mu_g), true, step, lr, m_denom, v_denom, cfg.max_step_mu);
+                m_mu[i] = mm; v_mu[i] = vv; mu[i] = p_mu;
+                mm = m_omega[i]; vv = v_omega[i];
+                adam_one(p_om, mm, vv, (double)om_g, __fmul_rn(om_g, om_g), true, step, lr, m_denom, v_denom, cfg.max_step_omega);
+                m_omega[i] = mm; v_omega[i] = vv; omega[i] = p_om;
+                mm = m_alpha[i]; vv = v_alpha[i];
+                adam_one(p_al, mm, vv, (double)al_g, __fmul_rn(al_g, al_g), true, step, lr, m_denom, v_denom, cfg.max_step_alpha);
+                m_alpha[i] = mm; v_alpha[i] = vv; alpha[i] = p_al;
             }
         }
     }
 
     if (!do_reparam) return;
-    double l_skew = 0.0, l_ln = 0.0;
+    double l_skew[KP], l_ln[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) { l_skew[k] = 0.0; l_ln[k] = 0.0; }
     if (live) {
-        const float p_mu = nd_par[0][nl];
         if (mode == 1) {
-            if (k == 0) {
-                const float e = expf(-p_mu);
-                ys[(size_t)i * KP] = (double)__fdiv_rn(1.0f, __fadd_rn(1.0f, e));  // ys = logistic(zs), no clamp (l-a.jl:196)
-                zs0[(size_t)i * KP] = 0.0f;
-            }
+            const float e = expf(-p_mu);
+            ys[(size_t)i * KP] = (double)__fdiv_rn(1.0f, __fadd_rn(1.0f, e));  // ys = logistic(zs), no clamp (l-a.jl:196)
+            zs0[(size_t)i * KP] = 0.0f;
         } else {
             const int step0 = step0_fixed >= 0 ? step0_fixed : ctl->step_fwd - 1;  // 0-based index of the step of these draws
-            const float sigma = nd_tr[0][nl], sa = nd_tr[1][nl], ca = nd_tr[2][nl];
-            float z0 = 0.0f;
-            if (k < K) {
-                if (noise) z0 = noise[((size_t)(step0 % noise_steps) * K + k) * (size_t)nm1 + i];
-                else z0 = philox_normal(seed, (uint32_t)i, (uint32_t)k, (uint32_t)step0, fast_noise);
+            const float sigma = expf(p_om);
+            const float sa = sinhf(p_al), ca = coshf(p_al);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                float z0 = 0.0f;
+                if (k < K) {
+                    if (noise) z0 = noise[((size_t)(step0 % noise_steps) * K + k) * (size_t)nm1 + i];
+                    else z0 = philox_normal(seed, (uint32_t)i, (uint32_t)k, (uint32_t)step0, fast_noise);
+                }
+                const float r = sqrtf(fmaf(z0, z0, 1.0f));
+                const float zf = fmaf(z0, ca, r * sa);
+                const float xx = __fadd_rn(p_mu, __fmul_rn(zf, sigma));
+                const float e = expf(-xx);
+                const float y32 = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+                double y = (double)y32;
+                if (want_ladj && k < K) {
+                    const float ch = fmaf(ca, r, sa * z0);
+                    l_skew[k] = (double)logf(ch) - (double)logf(r);  // log cosh(c) - 0.5 log1p(z0^2)
+                    l_ln[k] = log(__dmul_rn(__dmul_rn((double)sigma, y), __dsub_rn(1.0, y)));
+                }
+                if (clamp_y) y = fmin(fmax(y, 1e-10), 1.0 - 1e-10);
+                zs0[(size_t)i * KP + k] = z0;
+                ys[(size_t)i * KP + k] = y;
             }
-            const float r = sqrtf(fmaf(z0, z0, 1.0f));
-            const float zf = fmaf(z0, ca, r * sa);
-            const float xx = __fadd_rn(p_mu, __fmul_rn(zf, sigma));
-            const float e = expf(-xx);
-            const float y32 = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
-            double y = (double)y32;
-            if (want_ladj && k < K) {
-                const float ch = fmaf(ca, r, sa * z0);
-                l_skew = (double)logf(ch) - (double)logf(r);  // log cosh(c) - 0.5 log1p(z0^2)
-                l_ln = log(__dmul_rn(__dmul_rn((double)sigma, y), __dsub_rn(1.0, y)));
-            }
-            if (clamp_y) y = fmin(fmax(y, 1e-10), 1.0 - 1e-10);
-            zs0[(size_t)i * KP + k] = z0;
-            ys[(size_t)i * KP + k] = y;
         }
     }
     if (want_ladj) {
-        // per-draw block sums over the CTA's nodes, fixed order
-        __syncthreads();
-        block_reduce_k<KP, ELEM_THREADS>(l_skew, sm_d[0], ladj_partial + (size_t)blockIdx.x * KP);
-        block_reduce_k<KP, ELEM_THREADS>(l_ln, sm_d[0], ladj_partial + ((size_t)gridDim.x + blockIdx.x) * KP);
+        // per-draw block sums, fixed order
+        for (int k = 0; k < KP; ++k) {
+            sm[threadIdx.x] = l_skew[k];
+            __syncthreads();
+            for (int span = ELEM_THREADS / 2; span >= 1; span >>= 1) {
+                if ((int)threadIdx.x < span) sm[threadIdx.x] += sm[threadIdx.x + span];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) ladj_partial[(size_t)blockIdx.x * KP + k] = sm[0];
+            __syncthreads();
+            sm[threadIdx.x] = l_ln[k];
+            __syncthreads();
+            for (int span = ELEM_THREADS / 2; span >= 1; span >>= 1) {
+                if ((int)threadIdx.x < span) sm[threadIdx.x] += sm[threadIdx.x + span];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) ladj_partial[((size_t)gridDim.x + blockIdx.x) * KP + k] = sm[0];
+            __syncthreads();
+        }
     }
 }
 
@@ -970,8 +990,8 @@ void release_work_buffers(polee_handle *h) {
 }
 
 int elem_ctas(polee_handle *h, int KP) {
-    const int nodes = ELEM_THREADS / KP;  // k3_elem: one lane per (internal node, draw)
-    return (int)std::max<int64_t>(1, (h->n - 1 + nodes - 1) / nodes);
+    (void)KP;
+    return (int)std::max<int64_t>(1, (h->n - 1 + ELEM_THREADS - 1) / ELEM_THREADS);
 }
 
 int ensure_work_buffers(polee_handle *h, int KP) {
@@ -980,6 +1000,7 @@ int ensure_work_buffers(polee_handle *h, int KP) {
     const int64_t n = h->n, nm1 = std::max<int64_t>(n - 1, 1), N = 2 * n - 1;
     h->tree_grid = std::max(1, std::min(h->td.s_bottom.nbins * std::max(1, KP / std::min(KP, 4)), 2 * h->num_sms));
     h->n_tree_ctas = std::max(1 + std::max(h->td.bottom.nbins, h->tree_grid), h->td.n_groups);
+    h->n_tree_ctas = std::max(h->n_tree_ctas, (int)((n + LEAF_S_PER_WARP - 1) / LEAF_S_PER_WARP));  // k3_leaf_S: a row per warp
     CK(polee::dmalloc((void **)&h->zs0, sizeof(float) * nm1 * KP));
     CK(polee::dmalloc((void **)&h->zs, sizeof(float) * nm1 * KP));
     CK(polee::dmalloc((void **)&h->ys, sizeof(double) * nm1 * KP));
@@ -1037,7 +1058,6 @@ int patch_leaf_records(polee_handle *h) {
         if (count > 0)
             k_patch_leaf_recs<<<(count + 255) / 256, 256, 0, h->stream>>>(sd->recs, count, h->efflen, h->efflen_adj);
     }
-    if (h->td.dnodes) k_patch_dnodes<<<(unsigned)((h->td.N + 255) / 256), 256, 0, h->stream>>>(h->td.dnodes, h->td.N, h->efflen);
     CK(cudaGetLastError());
     return POLEE_OK;
 }
@@ -1082,7 +1102,7 @@ static bool path_fwd_ok(const polee_handle *h) {
 static size_t dfs_fwd_smem(const polee_handle *h, int KP) {
     const size_t threads = (size_t)DFS_RUNS_PER_CTA * KP;
     return (size_t)(h->td.max_depth + 2) * threads * 8 + (size_t)((std::max(h->td.dfs_max_nk, 1) + 1) & ~1) * KP * 8 +
-           (size_t)DFS_RUNS_PER_CTA * (DFS_RUN + 1) * sizeof(DNode);
+           (size_t)DFS_RUNS_PER_CTA * (DFS_RUN + 2) * sizeof(DNode);
 }
 static bool dfs_fwd_ok(const polee_handle *h) {
     return h->td.dnodes != nullptr && !chain_path(h) && smem_path_ok(h, h->work_KP) && h->work_KP <= 16 &&
@@ -1203,8 +1223,9 @@ int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_l
         const size_t smem = dfs_fwd_smem(h, KP);
         if (smem > 40 * 1024) DISPATCH_KP(KP, allow_max_smem(k3d_tree_fwd<KPC>));
         DISPATCH_KP(KP, (k3d_tree_fwd<KPC><<<td.dfs_ctas, DFS_RUNS_PER_CTA * KPC, smem, h->stream>>>(
-                            td.N, td.dnodes, td.drun_anc_ptr, td.drun_anc, td.dcta_k0, h->ys, h->us, h->x, xd, clamp_x, eff, Sp,
+                            td.N, td.dnodes, td.drun_anc_ptr, td.drun_anc, td.dcta_k0, h->ys, h->us, h->x, xd, clamp_x,
                             want_ladj, ladj_tree, td.max_depth + 2, (std::max(td.dfs_max_nk, 1) + 1) & ~1)));
+        h->S_deferred = want_S != 0;  // launch_mid adds S = sum_j x_j / efflen_j (k3_leaf_S) beside the likelihood pass
         return POLEE_OK;
     }
     if (path_fwd_ok(h)) {
@@ -1234,6 +1255,15 @@ int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_l
 }
 
 int launch_mid(polee_handle *h, int KP, int advance, cudaStream_t st) {
+    if (h->S_deferred) {  // S and the bookkeeping in one small kernel (k3_leaf_S)
+        h->S_deferred = false;
+        const int nwarps = (int)((h->n + LEAF_S_PER_WARP - 1) / LEAF_S_PER_WARP);
+        if (nwarps > h->n_tree_ctas) return h->fail(POLEE_EINVAL, "internal: S partial buffer too small");
+        const int ctas = (nwarps * 32 + LEAF_S_THREADS - 1) / LEAF_S_THREADS;
+        DISPATCH_KP(KP, (k3_leaf_S<KPC><<<ctas, LEAF_S_THREADS, 0, st ? st : h->stream>>>(
+                            h->n, h->x, h->efflen, h->S_partial, nwarps, h->S, h->d_step, advance, h->d_leafS_counter)));
+        return POLEE_OK;
+    }
     k3_mid<<<1, 1024, 0, st ? st : h->stream>>>(h->S_partial, h->n_tree_ctas, KP, h->S, h->d_step, advance);
     return POLEE_OK;
 }
