@@ -49,8 +49,15 @@ CONFIGS = {
 FIT_STEPS = 500  # LIKAP_NUM_STEPS (src/constants.jl:64): what one approximate_likelihood call runs
 
 
-DTYPE = ("f32 products and in-task sums (<= 64 terms per row, <= 32 rows per lane + 5-level lane tree per column), f64 across "
-         "tasks, f64 tree / ADAM arithmetic on f32 state")
+DTYPES = {
+    0: ("f32 products and in-task sums (<= 64 terms per row, <= 32 rows per lane + 5-level lane tree per column), f64 across "
+        "tasks, f64 tree / ADAM arithmetic on f32 state"),
+    1: ("--exact 1: f32 products summed in f64 in the reference's order (frag_probs bit-identical to the reference, split "
+        "SELL + CSC kernels), f64 gradient sums, f64 tree / ADAM arithmetic on f32 state"),
+    2: ("--exact 2: class kernel in f64 throughout (exact products, f64 row and column sums: at least north_star's 'fp32 "
+        "with fp64 accumulation'), f64 tree / ADAM arithmetic on f32 state"),
+}
+DTYPE = DTYPES[0]
 
 
 def workload(cfg, m, n, nnz, K):
@@ -227,7 +234,7 @@ def run_ours(args):
     # point of `multi_rank_parity`
     full_params = None
     if world > 1 and rank == 0:
-        hf = pb.Handle(device=local, num_mc_samples=K, num_steps=3, seed=args.seed)
+        hf = pb.Handle(device=local, num_mc_samples=K, num_steps=3, seed=args.seed, exact_accumulation=args.exact)
         hf.set_matrix_device(m, n, s["colptr"].to(torch.int32).data_ptr(), s["rowval"].to(torch.int32).data_ptr(),
                              s["nzval"].data_ptr())
         hf.set_efflens(efflens)
@@ -240,7 +247,8 @@ def run_ours(args):
     del s
     torch.cuda.empty_cache()
 
-    h = pb.Handle(device=local, num_mc_samples=K, num_steps=max(args.steps + args.warmup, 1), seed=args.seed)
+    h = pb.Handle(device=local, num_mc_samples=K, num_steps=max(args.steps + args.warmup, 1), seed=args.seed,
+                  exact_accumulation=args.exact)
     h.set_matrix_device(m_loc, n, colptr_d.data_ptr(), rowval_d.data_ptr(), nzval_d.data_ptr())
     del colptr_d, rowval_d, nzval_d
     torch.cuda.empty_cache()
@@ -306,6 +314,13 @@ def run_ours(args):
     reps = max(5, min(50, args.steps))
     info = h.layout_info()
     t_k1, t_k2, t_k3 = (h.time_kernel(w, reps) for w in (1, 2, 3))
+    t_ar = None
+    if world > 1:   # the all-reduce alone, all ranks in lockstep (a rank's time includes waiting for the slowest peer)
+        torch.cuda.synchronize()
+        dist.barrier()
+        tt = torch.tensor([h.time_kernel(5, 10)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ar = float(tt.item())
     peak, peak_src = measured_peak()
     # algorithmic bytes of THIS rank's launches (SURVEY 8d formula, local nnz / rows, padded draw count KP)
     KP = 1
@@ -340,6 +355,8 @@ def run_ours(args):
                     "moved_gbs": round(moved, 1), "frac_moved": round(moved / peak, 4),
                     "step_gbs": round((b_k1 + b_k2 + stats["bytes_k3"]) / step_ms / 1e6, 1),
                     "share_of_step": round(t_dom / step_ms, 3)}
+        if t_ar is not None:
+            roofline["kernels_ms"]["allreduce_g (max over ranks, incl. waiting for the slowest rank)"] = round(t_ar, 4)
         dom = (kname, stats["bytes_k1"], t_dom)
     else:
         layout = "split (SELL slabs for K1 + re-sorted CSC for K2)"
@@ -380,7 +397,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             out = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), sample, tree_topology=tree, num_steps=FIT_STEPS,
-                                            num_mc_samples=K, seed=args.seed, device=local)
+                                            num_mc_samples=K, seed=args.seed, device=local, exact_accumulation=args.exact)
             t_fits.append(time.perf_counter() - t0)
         assert np.all(np.isfinite(out["mu"]))
         h2d = host["colptr"].nbytes + host["rowval"].nbytes + host["nzval"].nbytes + efflens.nbytes + 2 * 4 * (2 * n - 1)
@@ -430,7 +447,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": "elbo_grad_evals_per_sec", "value": round(evals_per_s, 1), "unit": "evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4),
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPES[args.exact],
                 "data": "synthetic (polee-synth-v1, seed %d)" % CONFIGS[args.config][4],
                 "config": {"workload": workload(args.config, m, n, nnz_total, K)},
                 "details": {"partition": "rows in %d contiguous equal-nnz block(s), one per rank" % world,
@@ -747,6 +764,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--seed", type=int, default=123456789)
+    ap.add_argument("--exact", type=int, default=0, choices=[0, 1, 2],
+                    help="opts.exact_accumulation: 0 default arithmetic, 1 reference-order Float64 accumulation (split kernels), "
+                         "2 class kernel in Float64")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)

@@ -507,28 +507,11 @@ static int launch_likelihood(polee_handle *h, int KP, int K, bool want_lp) {
     return POLEE_OK;
 }
 
-// The launch sequence of one step (SURVEY 3a inner loop, batched over the K draws).  ys / zs0 of the step are
-// produced by the previous step's fused update+reparam kernel (or by ensure_reparam for the first step):
-//   tree fwd (top, bottom) -> mid -> K1 -> K2 (+combine) -> [lp reduce] -> [all-reduce] -> tree bwd (bottom, top)
-//   -> [elbo] -> update(step s) + reparam(step s+1)
-static int launch_step_sequence(polee_handle *h, bool do_adam, bool next_reparam, float *grad_out, double *xgrad_out,
-                                const float *noise, int64_t noise_steps) {
-    const int KP = h->KP, K = h->K;
-    const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
-    const bool want_vals = lsn && !h->o.gradonly;
-    const bool apply_eff = lsn ? (h->o.use_efflen_jacobian != 0) : true;
-    int rc;
-    if ((rc = launch_tree_fwd(h, KP, 1, apply_eff, want_vals))) return rc;
-    // k3_mid (the S reduction and the step counters) depends only on the tree pass and is needed only by the backward
-    // pass: it runs on a side stream beside the likelihood pass (a fork / join that the graph capture records too)
-    CK(cudaEventRecord(h->ev_fork, h->stream));
-    CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-    if ((rc = launch_mid(h, KP, do_adam ? 1 : 0, h->side_stream))) return rc;
-    CK(cudaEventRecord(h->ev_join, h->side_stream));
-    if ((rc = launch_likelihood(h, KP, K, want_vals))) return rc;
-    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+// the per-step sum of g (and, when requested, of the K log-likelihood sums) over the ranks of a row-partitioned fit
+static int launch_allreduce(polee_handle *h, int KP, bool want_vals) {
 #ifdef POLEE_WITH_NCCL
     if (h->nranks > 1) {
+        int rc;
         // The gradient crosses NVLink as Float32 (6.4 MB instead of 12.8 MB at C3; every rank's partial g is a sum of
         // positive Float32-accurate terms, so nothing is lost that the 1e-5 gate could see); the K log-likelihood
         // sums, when requested, stay Float64.  POLEE_ALLREDUCE=f64 keeps the whole buffer in Float64.
@@ -552,7 +535,33 @@ static int launch_step_sequence(polee_handle *h, bool do_adam, bool next_reparam
         }
         if (r != ncclSuccess) return h->fail(POLEE_ENCCL, std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r));
     }
+#else
+    (void)h; (void)KP; (void)want_vals;
 #endif
+    return POLEE_OK;
+}
+
+// The launch sequence of one step (SURVEY 3a inner loop, batched over the K draws).  ys / zs0 of the step are
+// produced by the previous step's fused update+reparam kernel (or by ensure_reparam for the first step):
+//   tree fwd (top, bottom) -> mid -> K1 -> K2 (+combine) -> [lp reduce] -> [all-reduce] -> tree bwd (bottom, top)
+//   -> [elbo] -> update(step s) + reparam(step s+1)
+static int launch_step_sequence(polee_handle *h, bool do_adam, bool next_reparam, float *grad_out, double *xgrad_out,
+                                const float *noise, int64_t noise_steps) {
+    const int KP = h->KP, K = h->K;
+    const bool lsn = h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT;
+    const bool want_vals = lsn && !h->o.gradonly;
+    const bool apply_eff = lsn ? (h->o.use_efflen_jacobian != 0) : true;
+    int rc;
+    if ((rc = launch_tree_fwd(h, KP, 1, apply_eff, want_vals))) return rc;
+    // k3_mid (the S reduction and the step counters) depends only on the tree pass and is needed only by the backward
+    // pass: it runs on a side stream beside the likelihood pass (a fork / join that the graph capture records too)
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    if ((rc = launch_mid(h, KP, do_adam ? 1 : 0, h->side_stream))) return rc;
+    CK(cudaEventRecord(h->ev_join, h->side_stream));
+    if ((rc = launch_likelihood(h, KP, K, want_vals))) return rc;
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if ((rc = launch_allreduce(h, KP, want_vals))) return rc;
     if (h->n_genes > 0 && (rc = launch_gene_prior(h, KP))) return rc;
     if ((rc = launch_tree_bwd(h, KP, lsn, apply_eff, xgrad_out))) return rc;
     if (want_vals && (rc = launch_elbo(h, KP, K, true))) return rc;
@@ -1020,8 +1029,10 @@ extern "C" int polee_time_kernel(polee_handle *h, int32_t which, int32_t reps, f
             if (!rc) rc = launch_elem(h, KP, K, true, false, true, noise, std::max<int64_t>(h->noise_steps, 1), 0, nullptr);
         } else if (which == 4) {  // the class kernel alone (without the second stage that adds its partials)
             if (h->ec_tasks > 0) rc = launch_ec(h, h->x, h->g, false, false, nullptr, nullptr, KP, K, true);
+        } else if (which == 5) {  // the all-reduce of g alone (every rank must make the same call)
+            rc = launch_allreduce(h, KP, false);
         } else {
-            rc = h->fail(POLEE_EINVAL, "time_kernel: which must be 1..4");
+            rc = h->fail(POLEE_EINVAL, "time_kernel: which must be 1..5");
         }
     }
     CK(cudaEventRecord(e1, h->stream));

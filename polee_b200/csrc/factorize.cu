@@ -162,7 +162,8 @@ extern "C" int polee_exact_factorization(int32_t device, int64_t m, int64_t n, c
                                          float *nzval_out, int64_t *counts_out, int64_t *nnz_out) {
     if (!colptr || !rowval || !nzval || !m_unique || !colptr_out || !rowval_out || !nzval_out || !counts_out || !nnz_out)
         return POLEE_EINVAL;
-    if (m < 1 || n < 1 || colptr[0] != 1 || m >= (int64_t)0xFFFFFF00u) return POLEE_EINVAL;
+    // the CUB sorts and scans take int item counts
+    if (m < 1 || n < 1 || colptr[0] != 1 || m > (int64_t)INT32_MAX || (int64_t)colptr[n] - 1 > (int64_t)INT32_MAX) return POLEE_EINVAL;
     for (int64_t j = 0; j < n; ++j)
         if (colptr[j + 1] < colptr[j]) return POLEE_EINVAL;
     const int64_t nnz = (int64_t)colptr[n] - 1;

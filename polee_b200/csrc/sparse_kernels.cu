@@ -11,11 +11,10 @@
 //   exact (1): each product x*v is rounded to Float32 and summed in Float64 in ascending-transcript order,
 //              exactly as the reference does -> p is bit-identical to the reference's frag_probs; g is a
 //              Float64 FMA per entry.  (v1 K1 kernel: direct global loads.)
-//   fast  (0, default): K1 accumulates Float64(v) * Float64(x) with one DFMA per (entry, draw) -- exact
-//              products, Float64 sums, |dp/p| <= 2^-24 * row entries from not rounding the products;
-//              K2 accumulates a lane's <= 8 products of a segment in Float32 and everything above that in
-//              Float64.  Both stay ~1e-7 relative, 50x inside the 1e-5 gate; the f32->f64 conversions that
-//              kept the XU pipe 40 % busy in v1 (profiles/r01_v1_*) are gone.
+//   fast  (0, default): K1 sums a row's products in Float32 batches of four (rows of <= 4 entries entirely in
+//              Float32, one MUFU.RCP per draw) and the batches in Float64; K2 accumulates a lane's <= 8 products of a
+//              segment in Float32 and everything above that in Float64.  Both stay <= 3e-7 relative of the oracle,
+//              30x inside the 1e-5 gate.
 // w is stored as Float32 (one rounding, <= 2^-24 relative).  Deterministic either way: no atomics, fixed
 // reduction trees.  Tensor cores are not used: nothing here is a dense contraction.
 #include <algorithm>
