@@ -193,6 +193,49 @@ def equal_nnz_bounds(s, parts):
     return b
 
 
+def run_oneshot_child(args):
+    """`bench.py --oneshot-child`: a fresh process that builds the same sample, makes ONE approximate_likelihood call from
+    pinned host buffers and prints its wall time -- what a one-shot `polee prep-sample` pays (nothing cached on the device,
+    kernels not yet loaded).  The parent bench process reports it as e2e.value."""
+    import torch
+    import polee_b200 as pb
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    s, tree, K = generate(args.config, dev)
+    m, n = s["m"], s["n"]
+    pin = lambda t, dt: torch.empty(t.shape, dtype=dt, pin_memory=True).copy_(t.to(dt)).numpy()  # noqa: E731
+    colptr, rowval = pin(s["colptr"], torch.int32).view(np.uint32), pin(s["rowval"], torch.int32).view(np.uint32)
+    nzval, efflens = pin(s["nzval"], torch.float32), s["efflens"].cpu().numpy()
+    del s
+    torch.cuda.empty_cache()
+    sample = pb.RNASeqSample(m, n, colptr, rowval, nzval, efflens)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), sample, tree_topology=tree, num_steps=FIT_STEPS,
+                                    num_mc_samples=K, seed=args.seed, device=local, exact_accumulation=args.exact)
+    t = time.perf_counter() - t0
+    print(json.dumps({"oneshot_fit_time_s": t, "finite": bool(np.all(np.isfinite(out["mu"])))}), flush=True)
+
+
+def oneshot_fit_time(args):
+    """Run run_oneshot_child in a fresh process; None when that is not possible (the caller then falls back to the
+    in-process measurement)."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--oneshot-child", "--config", args.config, "--seed", str(args.seed),
+           "--exact", str(args.exact)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        for ln in reversed(out.stdout.splitlines()):
+            if ln.startswith("{") and "oneshot_fit_time_s" in ln:
+                d = json.loads(ln)
+                return float(d["oneshot_fit_time_s"]) if d.get("finite") else None
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -401,14 +444,22 @@ def run_ours(args):
             t_fits.append(time.perf_counter() - t0)
         assert np.all(np.isfinite(out["mu"]))
         h2d = host["colptr"].nbytes + host["rowval"].nbytes + host["nzval"].nbytes + efflens.nbytes + 2 * 4 * (2 * n - 1)
-        e2e = {"value": round(K * FIT_STEPS / t_fits[0], 1), "unit": "evals/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(3 * 4 * (n - 1)), "fit_time_s": round(t_fits[0], 4),
+        # the one-shot figure: the first call of a FRESH process (nothing cached, kernels not yet loaded, CUDA graph not
+        # yet built) -- what `polee prep-sample` pays.  If the child process cannot run, the first call after the
+        # device-memory cache of this process was emptied stands in for it.
+        t_one = oneshot_fit_time(args)
+        t_cold = t_one if t_one is not None else t_fits[0]
+        e2e = {"value": round(K * FIT_STEPS / t_cold, 1), "unit": "evals/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(3 * 4 * (n - 1)), "fit_time_s": round(t_cold, 4),
+               "fit_time_source": ("first call of a fresh process (bench.py --oneshot-child)" if t_one is not None else
+                                   "first call of this process after its device-memory cache was emptied"),
+               "trimmed_cache_fit_time_s": round(t_fits[0], 4),
                "warm_value": round(K * FIT_STEPS / t_fits[1], 1), "warm_fit_time_s": round(t_fits[1], 4),
                "adam_steps_per_fit": FIT_STEPS,
                "step": "one approximate_likelihood call: CSC upload from pinned host memory + device layout build + "
-                       "%d ADAM steps x %d draws + parameter download; value = the first call with an empty device-memory "
-                       "cache, warm_value = the next call (cached allocations, as in `polee prep` over many samples)"
-                       % (FIT_STEPS, K)}
+                       "%d ADAM steps x %d draws + parameter download; value = the one-shot call (see fit_time_source), "
+                       "warm_value = a later call of the same process (cached device allocations, as in `polee prep` over "
+                       "many samples)" % (FIT_STEPS, K)}
         if not args.no_cpu:
             cpu, parity = cpu_baseline(m, n, K, host, efflens, tree, budget_s=args.cpu_budget, check=(xs_par, lp_par, g_par))
     elif host is not None:
@@ -767,13 +818,16 @@ def main():
     ap.add_argument("--exact", type=int, default=0, choices=[0, 1, 2],
                     help="opts.exact_accumulation: 0 default arithmetic, 1 reference-order Float64 accumulation (split kernels), "
                          "2 class kernel in Float64")
+    ap.add_argument("--oneshot-child", action="store_true", help="internal: one fit in this fresh process, print its time")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--samples", type=int, default=64, help="c5: number of samples")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.oneshot_child:
+        run_oneshot_child(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.config.startswith("c4"):
         run_c4(args)
