@@ -248,6 +248,10 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    # The one-shot end-to-end figure comes from a fresh child process that has the GPU to itself, so it runs BEFORE this
+    # process creates its CUDA context: with a second context on the device (and memory it has just freed) the child's
+    # cudaMalloc calls -- 8 GB of set-up scratch -- take 140-240 ms instead of 20 (profiles/r02_cold_fit.log).
+    t_oneshot = oneshot_fit_time(args) if (world == 1 and not args.no_e2e) else None
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
@@ -447,11 +451,12 @@ def run_ours(args):
         # the one-shot figure: the first call of a FRESH process (nothing cached, kernels not yet loaded, CUDA graph not
         # yet built) -- what `polee prep-sample` pays.  If the child process cannot run, the first call after the
         # device-memory cache of this process was emptied stands in for it.
-        t_one = oneshot_fit_time(args)
+        t_one = t_oneshot
         t_cold = t_one if t_one is not None else t_fits[0]
         e2e = {"value": round(K * FIT_STEPS / t_cold, 1), "unit": "evals/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(3 * 4 * (n - 1)), "fit_time_s": round(t_cold, 4),
-               "fit_time_source": ("first call of a fresh process (bench.py --oneshot-child)" if t_one is not None else
+               "fit_time_source": ("first call of a fresh process that has the GPU to itself (bench.py --oneshot-child, run "
+                                   "before this process creates its CUDA context)" if t_one is not None else
                                    "first call of this process after its device-memory cache was emptied"),
                "trimmed_cache_fit_time_s": round(t_fits[0], 4),
                "warm_value": round(K * FIT_STEPS / t_fits[1], 1), "warm_fit_time_s": round(t_fits[1], 4),
