@@ -24,7 +24,7 @@ namespace polee {
 namespace {
 
 constexpr int PEER_THREADS = 512;
-constexpr int PEER_MAX_CTAS = 96;  // co-resident with room to spare (148 SMs): the CTAs spin on each other
+constexpr int PEER_MAX_CTAS = 128;  // co-resident with room to spare (148 SMs): the CTAs spin on each other
 constexpr long long PEER_TIMEOUT_CYCLES = 1ll << 32;  // ~2 s
 
 struct PeerArgs {
@@ -84,15 +84,38 @@ __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(const PeerArgs 
     // slice s of the vectors belongs to rank s
     const size_t per = ((ntiles + A.P - 1) / A.P) * tile;  // vectors per slice, whole tiles
 
+    // Every phase works on batches of UB tiles: all loads of a batch are issued before its first store (the loops carry no
+    // dependence, but the compiler cannot know that `g`, `send` and `recv` never overlap)
+    constexpr int UB = 4;
+
     // ---- 1. narrow my tiles (of every slice)
-    for (size_t t = c; t < ntiles; t += G) {
-        const size_t v = t * tile + threadIdx.x;
-        if (v < nvec) {
-            if constexpr (V == 4) {
-                const double2 a = reinterpret_cast<const double2 *>(A.g)[2 * v], b = reinterpret_cast<const double2 *>(A.g)[2 * v + 1];
-                reinterpret_cast<float4 *>(send)[v] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
-            } else {
-                send[v] = (float)A.g[v];
+    for (size_t t = c; t < ntiles; t += (size_t)G * UB) {
+        if constexpr (V == 4) {
+            double2 a[UB], b[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const size_t v = (t + (size_t)u * G) * tile + threadIdx.x;
+                if (v < nvec) {
+                    a[u] = reinterpret_cast<const double2 *>(A.g)[2 * v];
+                    b[u] = reinterpret_cast<const double2 *>(A.g)[2 * v + 1];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const size_t v = (t + (size_t)u * G) * tile + threadIdx.x;
+                if (v < nvec) reinterpret_cast<float4 *>(send)[v] = make_float4((float)a[u].x, (float)a[u].y, (float)b[u].x, (float)b[u].y);
+            }
+        } else {
+            double a[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const size_t v = (t + (size_t)u * G) * tile + threadIdx.x;
+                if (v < nvec) a[u] = A.g[v];
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const size_t v = (t + (size_t)u * G) * tile + threadIdx.x;
+                if (v < nvec) send[v] = (float)a[u];
             }
         }
     }
@@ -130,15 +153,33 @@ __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(const PeerArgs 
     signal_and_wait(A, 1, ep);
 
     // ---- 3. widen my tiles (of every slice)
-    for (size_t t = c; t < ntiles; t += G) {
-        const size_t v = t * tile + threadIdx.x;
-        if (v < nvec) {
-            if constexpr (V == 4) {
-                const float4 a = __ldcg(reinterpret_cast<const float4 *>(recv) + v);
-                reinterpret_cast<double2 *>(A.g)[2 * v] = make_double2((double)a.x, (double)a.y);
-                reinterpret_cast<double2 *>(A.g)[2 * v + 1] = make_double2((double)a.z, (double)a.w);
-            } else {
-                A.g[v] = (double)__ldcg(recv + v);
+    for (size_t t = c; t < ntiles; t += (size_t)G * UB) {
+        if constexpr (V == 4) {
+            float4 a[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const size_t v = (t + (size_t)u * G) * tile + threadIdx.x;
+                if (v < nvec) a[u] = __ldcg(reinterpret_cast<const float4 *>(recv) + v);
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const size_t v = (t + (size_t)u * G) * tile + threadIdx.x;
+                if (v < nvec) {
+                    reinterpret_cast<double2 *>(A.g)[2 * v] = make_double2((double)a[u].x, (double)a[u].y);
+                    reinterpret_cast<double2 *>(A.g)[2 * v + 1] = make_double2((double)a[u].z, (double)a[u].w);
+                }
+            }
+        } else {
+            float a[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const size_t v = (t + (size_t)u * G) * tile + threadIdx.x;
+                if (v < nvec) a[u] = __ldcg(recv + v);
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const size_t v = (t + (size_t)u * G) * tile + threadIdx.x;
+                if (v < nvec) A.g[v] = (double)a[u];
             }
         }
     }
