@@ -94,9 +94,10 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
     for (int64_t i = N - 1; i >= 1; --i) size[parent[i]] += size[i];
 
     // ---- DFS pre-order?  (right child = next node, left child = the node after the right subtree)
-    preorder = n >= 2 && max_depth <= DFS_MAX_DEPTH;
-    for (int64_t i = 0; i < N && preorder; ++i)
-        if (nodes[i].leaf < 0) preorder = nodes[i].right == i + 1 && nodes[i].left == i + 1 + size[i + 1];
+    bool preorder_nodes = n >= 2;
+    for (int64_t i = 0; i < N && preorder_nodes; ++i)
+        if (nodes[i].leaf < 0) preorder_nodes = nodes[i].right == i + 1 && nodes[i].left == i + 1 + size[i + 1];
+    preorder = preorder_nodes && max_depth <= DFS_MAX_DEPTH;
     dnodes.clear(); drun_anc_ptr.clear(); drun_anc.clear(); dcta_k0.clear();
     dfs_max_nk = 0;
     if (preorder) {
@@ -231,6 +232,13 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
             cur_fill = 0;
         }
         cur_fill += size[r];
+        if (preorder_nodes) {  // a subtree is the contiguous index range [r, r + size): the order the stack walk below gives
+            for (int32_t v = (int32_t)r; v < (int32_t)(r + size[r]); ++v) {
+                level_of[v] = depth[v] - depth[r];
+                bins.back().push_back(v);
+            }
+            continue;
+        }
         stack.assign(1, (int32_t)r);
         while (!stack.empty()) {
             int32_t v = stack.back();

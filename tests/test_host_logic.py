@@ -237,3 +237,57 @@ def test_hclust_host_restatement(oracle):
     A, B = ancestors(pos[a + 1]), ancestors(pos[b + 1])
     common = next(x for x in A if x in B)
     assert (A.index(common) + B.index(common)) <= 4
+
+
+def test_speculative_replay_of_a_float32_accumulator_is_exact():
+    """The algorithm of k4_ladj_chain (hsb_ops.cu), restated in numpy: InvHSB's `ladj -= log(u)` is a Float32
+    accumulator fed with Float64 terms (src/tensorflow_ext/hsb_ops.cpp:211,234), i.e. a chain of roundings
+    acc <- Float32(Float64(acc) - l).  While acc stays in one binade a step moves it by rint(-l / ulp) ulps whatever acc
+    is, so a block of steps can be formed by a prefix sum and then VERIFIED step by step with the reference's own rule;
+    the steps before the first mismatch are exact by induction, the mismatching one is redone by the scalar rule.
+    Checked here against the plain serial loop, bit for bit, on data with binade crossings, ties, zeros, sign changes
+    and non-finite values."""
+    def serial(ls):
+        acc = np.float32(0)
+        for l in ls:
+            acc = np.float32(np.float64(acc) - l)
+        return acc
+
+    def speculative(ls, width=256):
+        acc, k, scalar_steps = np.float32(0), 0, 0
+        with np.errstate(all="ignore"):
+            while k < len(ls):
+                l = ls[k:k + width]
+                fin = acc != 0 and np.isfinite(acc)
+                e = np.frexp(np.abs(acc))[1] if fin else 0
+                ulp, inv_ulp = (np.ldexp(1.0, e - 24), np.ldexp(1.0, 24 - e)) if fin else (0.0, 0.0)
+                P = np.cumsum(np.rint(-l * inv_ulp))
+                cand = (np.float64(acc) + ulp * P).astype(np.float32)
+                pred = np.concatenate([[acc], cand[:-1]]).astype(np.float32)
+                ok = (pred.astype(np.float64) - l).astype(np.float32) == cand
+                f = len(l) if ok.all() else int(np.argmin(ok))
+                if f > 0:
+                    acc = cand[f - 1]
+                if f < len(l):
+                    acc = np.float32(np.float64(acc) - l[f])
+                    scalar_steps += 1
+                    f += 1
+                k += f
+        return acc, scalar_steps
+
+    rng = np.random.default_rng(11)
+    cases = {
+        "log u of a simplex (what InvHSB feeds it)": np.log(rng.dirichlet(np.ones(20000) * 0.3).clip(1e-300)),
+        "mixed signs and magnitudes": rng.normal(size=5000) * 10.0 ** rng.integers(-12, 6, 5000),
+        "ties: multiples of half an ulp": np.ldexp(rng.integers(-8, 9, 4000).astype(np.float64), -20) + 0.0,
+        "zeros and tiny terms": np.where(rng.random(3000) < 0.5, 0.0, rng.normal(size=3000) * 1e-30),
+        "an infinity in the middle": np.concatenate([rng.normal(size=300), [-np.inf], rng.normal(size=300)]),
+    }
+    for name, ls in cases.items():
+        ls = np.ascontiguousarray(ls, np.float64)
+        with np.errstate(all="ignore"):
+            want = serial(ls)
+        got, scalar_steps = speculative(ls)
+        assert want.tobytes() == got.tobytes() or (np.isnan(want) and np.isnan(got)), name
+        if name.startswith("log u"):
+            assert scalar_steps < 200, scalar_steps   # binade changes and the first steps only: ~80 x fewer chain steps
