@@ -111,6 +111,14 @@ int polee_set_gene_groups(polee_handle *h, int64_t num_genes, const int64_t *gen
 int polee_set_tree(polee_handle *h, int64_t n, const int32_t *node_parent_idxs, const int32_t *node_js);
 /* list_nodes(n) tree of PolyaTreeTransform(X, :sequential)  src/hclust.jl:477-489 */
 int polee_set_tree_sequential(polee_handle *h, int64_t n);
+/* The sample of one approximate_likelihood call in ONE call: polee_set_matrix_csc + polee_set_efflens + polee_set_tree
+ * (the three inputs likelihood-approximation.jl:404-435 takes from the RNASeqSample and the PolyaTreeTransform), same
+ * arguments, same resulting state.  The host-side tree preparation runs on a second host thread while the calling
+ * thread uploads the matrix and the device builds its layout, so the set-up costs max(matrix, tree) instead of their
+ * sum.  A bad tree is reported (POLEE_EBADTREE) after the matrix has been set. */
+int polee_set_sample(polee_handle *h, int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,
+                     const float *nzval, const int64_t *ks /* m or NULL */, const float *efflens /* n */,
+                     const int32_t *node_parent_idxs, const int32_t *node_js);
 
 /* ------------------------------------------------------------------ the fit
  * approximate_likelihood(::LogitSkewNormalPTTApprox, sample; ...)  likelihood-approximation.jl:395-624

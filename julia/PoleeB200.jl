@@ -95,6 +95,20 @@ function set_tree!(h, t::Polee.PolyaTreeTransform)
     return parent_idxs, js
 end
 
+# matrix + effective lengths + tree in one call: the library prepares the tree on a second host thread while this one
+# uploads X and the device builds its layout (polee_set_sample, include/polee_b200.h)
+function set_sample!(h, X::SparseMatrixCSC{Float32,UInt32}, efflens::Vector{Float32}, t::Polee.PolyaTreeTransform,
+                     ks::Union{Nothing,Vector{Int}}=nothing)
+    m, n = size(X)
+    parent_idxs = Vector{Int32}(t.index[4, :])
+    js = Vector{Int32}(t.index[1, :])
+    check(h, ccall((:polee_set_sample, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, Int64, Ptr{UInt32}, Ptr{UInt32}, Ptr{Float32}, Ptr{Int64}, Ptr{Float32},
+                    Ptr{Int32}, Ptr{Int32}),
+                   h, m, n, X.colptr, X.rowval, X.nzval, ks === nothing ? C_NULL : ks, efflens, parent_idxs, js))
+    return parent_idxs, js
+end
+
 function device_for_this_task()
     return Int32(parse(Int, get(ENV, "POLEE_B200_DEVICE", "0")))
 end
@@ -146,9 +160,7 @@ function approximate_likelihood_b200(approx::Polee.LogitSkewNormalPTTApprox, sam
     omega = Vector{Float32}(undef, n - 1)
     alpha = Vector{Float32}(undef, n - 1)
     parent_idxs, js = with_handle(o) do h
-        set_matrix!(h, X)
-        set_efflens!(h, sample.effective_lengths)
-        pj = set_tree!(h, t)
+        pj = set_sample!(h, X, sample.effective_lengths, t)
         gene_noninformative && set_gene_groups!(h, gene_transcripts)
         with_progress_bar(h, Polee.LIKAP_NUM_STEPS)        # the "Optimizing" bar of l-a.jl:495,574
         check(h, ccall((:polee_fit, LIB), Cint,
@@ -229,9 +241,7 @@ function approximate_likelihood_b200(approx::Polee.LogitSkewNormalPTTApprox, t::
     omega = Vector{Float32}(undef, n - 1)
     alpha = Vector{Float32}(undef, n - 1)
     with_handle(o) do h
-        set_matrix!(h, SparseMatrixCSC{Float32,UInt32}(X), Vector{Int}(ks))
-        set_efflens!(h, Vector{Float32}(efflens))
-        set_tree!(h, t)
+        set_sample!(h, SparseMatrixCSC{Float32,UInt32}(X), Vector{Float32}(efflens), t, Vector{Int}(ks))
         check(h, ccall((:polee_fit, LIB), Cint,
                        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Ptr{Float32}),
                        h, mu, omega, alpha, C_NULL, C_NULL))

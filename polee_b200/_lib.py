@@ -33,7 +33,7 @@ EXPORTS = [
     "polee_opts_default", "polee_create", "polee_destroy", "polee_trim_memory", "polee_last_error", "polee_device_info",
     "polee_set_matrix_csc", "polee_set_matrix_csc_device", "polee_set_efflens", "polee_set_gene_groups",
     "polee_set_tree",
-    "polee_set_tree_sequential", "polee_fit", "polee_fit_optimize_ptt", "polee_init_params", "polee_run_steps",
+    "polee_set_tree_sequential", "polee_set_sample", "polee_fit", "polee_fit_optimize_ptt", "polee_init_params", "polee_run_steps",
     "polee_sync", "polee_set_progress", "polee_get_params", "polee_set_params", "polee_set_noise", "polee_get_elbo", "polee_stream",
     "polee_step_stats", "polee_layout_info", "polee_time_kernel", "polee_sample", "polee_loglik_grad", "polee_frag_prob_recip", "polee_ptt_transform",
     "polee_ptt_transform_gradients", "polee_ptt_inverse_transform", "polee_lsn_draws", "polee_hsb", "polee_inv_hsb",

@@ -99,8 +99,19 @@ class Handle:
             raise L.PoleeError(rc, self.lib.polee_last_error(self.h).decode())
 
     # ---- inputs
-    def set_sample(self, sample, ks=None):
+    def set_sample(self, sample, ks=None, tree_topology=None):
+        """sample.X, sample.effective_lengths and -- when given -- the tree (node_parent_idxs, node_js): with a tree this
+        is ONE polee_set_sample call (host tree preparation on a second thread beside the matrix upload / layout build),
+        without it polee_set_matrix_csc + polee_set_efflens as before."""
         ksa = None if ks is None else _c(ks, np.int64)
+        if tree_topology is not None:
+            pi, js = _c(tree_topology[0], np.int32), _c(tree_topology[1], np.int32)
+            assert pi.shape == js.shape and len(js) == 2 * sample.n - 1
+            self.check(self.lib.polee_set_sample(self.h, C.c_int64(sample.m), C.c_int64(sample.n), _p(sample.colptr),
+                                                 _p(sample.rowval), _p(sample.nzval), _p(ksa),
+                                                 _p(sample.effective_lengths), _p(pi), _p(js)))
+            self.m, self.n = sample.m, sample.n
+            return
         self.check(self.lib.polee_set_matrix_csc(self.h, C.c_int64(sample.m), C.c_int64(sample.n), _p(sample.colptr),
                                                  _p(sample.rowval), _p(sample.nzval), _p(ksa)))
         self.m, self.n = sample.m, sample.n
@@ -529,8 +540,7 @@ def approximate_likelihood(approx, sample, gradonly=True, tree_topology=None, us
                noise_mode=L.NOISE_INJECTED if noise is not None else L.NOISE_PHILOX,
                exact_accumulation=exact_accumulation)
     try:
-        h.set_sample(sample, ks)
-        h.set_tree(*tree_topology)
+        h.set_sample(sample, ks, tree_topology)
         if gene_noninformative:
             h.set_gene_groups(gene_transcripts)
         params = h.fit(noise=noise, want_elbo=want_elbo)

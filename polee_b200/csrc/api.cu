@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include <chrono>
+#include <thread>
 
 using namespace polee;
 
@@ -374,6 +375,39 @@ extern "C" int polee_set_tree(polee_handle *h, int64_t n, const int32_t *node_pa
     h->have_tree = false;
     HostPhaseTimer pt;
     return finish_tree(h, h->th.build_from_parents(n, node_parent_idxs, node_js, tree_bin_nodes()), pt);
+}
+
+// One RNASeqSample in one call: what polee_set_matrix_csc + polee_set_efflens + polee_set_tree do, with the host-side
+// tree work (validation, child pointers, the kernels' schedules: pure host code over h->th, ~25 ms at 200 k transcripts)
+// on a second host thread while this thread uploads the matrix and waits for the device to build its layout.  The
+// device half of the tree (upload, initial mu) follows once both are done.  Same state, same results.
+extern "C" int polee_set_sample(polee_handle *h, int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,
+                                const float *nzval, const int64_t *ks, const float *efflens,
+                                const int32_t *node_parent_idxs, const int32_t *node_js) {
+    CHECK_H(h);
+    if (!node_parent_idxs || !node_js || !efflens) return h->fail(POLEE_EINVAL, "set_sample: null pointer");
+    drop_graph(h);
+    release_work_buffers(h);
+    h->have_tree = false;  // nothing on this thread reads h->th / h->td until the worker has been joined
+    HostPhaseTimer pt;
+    std::string tree_err;
+    const int bin_nodes = tree_bin_nodes();
+    struct Joiner {
+        std::thread t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } worker{std::thread([&]() {
+        try {
+            tree_err = h->th.build_from_parents(n, node_parent_idxs, node_js, bin_nodes);
+        } catch (const std::exception &e) {
+            tree_err = std::string("tree: ") + e.what();
+        }
+    })};
+    int rc = polee_set_matrix_csc(h, m, n, colptr, rowval, nzval, ks);
+    if (!rc) rc = polee_set_efflens(h, efflens);
+    pt.mark("matrix + efflens (this thread)");
+    worker.t.join();
+    if (rc) return rc;
+    return finish_tree(h, tree_err, pt);
 }
 
 extern "C" int polee_set_tree_sequential(polee_handle *h, int64_t n) {

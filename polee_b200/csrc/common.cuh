@@ -184,6 +184,29 @@ struct DNode {
     uint32_t meta;      // depth | (1u << 31 if the node is its parent's LEFT child, i.e. the child that comes second)
 };
 
+// DFS-range backward kernel (k3d_tree_bwd): a CTA owns a span of <= DFS_CTA_NODES consecutive nodes made of whole
+// bottom subtrees (+ the top nodes interleaved between them, which it skips); a thread owns a run of DFS_BRUN nodes.
+//   tier 1: nodes whose subtree lies inside their run -- the thread walks its run backwards with a LIFO stack;
+//   tier 2: the other non-top nodes of the span -- a short level-synchronous sweep over the CTA's shared-memory slots;
+//   top   : nodes with more than DFS_CTA_NODES descendants -- the one-CTA-per-draw top kernel, as before.
+// DNode.meta of a span record: bit 0 internal node of tier 1; bit 1 its G is exported (the parent is not tier 1);
+// bit 2 exported to the global exchange slot (the parent is a top node) instead of a slot of the CTA;
+// bits 3..13 leaves: index among the span's leaves; bits 14..31 the slot.
+constexpr int DFS_BRUN = 32;
+constexpr int DFS_BRUNS = DFS_CTA_NODES / DFS_BRUN;  // runs per span = node slots of a CTA
+constexpr uint32_t BN_T1INT = 1u, BN_EXPORT = 2u, BN_GLOBAL = 4u;
+struct T2Node {
+    int32_t k;        // index among internal nodes
+    int32_t sl, sr;   // CTA slots holding the children's G
+    int32_t out;      // >= 0: CTA slot of this node's G; < 0: global exchange slot -1 - out; INT32_MIN: nobody needs it
+};
+struct BSpan {
+    int32_t s0, nn;        // first node, nodes
+    int32_t k0, nk;        // first internal-node index of the span, internal nodes (tier 1, tier 2 and interleaved top nodes)
+    int32_t t2_off, nt2;   // tier-2 records
+    int32_t lvl_off, nlev; // level offsets (nlev + 1 entries, relative to t2_off)
+};
+
 // Tree node, 0-based; leaf < 0 <=> internal node (then k = index among internal nodes in node order).
 struct TreeNode {
     int32_t left, right, k, leaf;
@@ -247,6 +270,13 @@ struct TreeHost {
     // above are not built): per node a DNode; per run of DFS_RUN nodes the ancestors of its first node, root first, as
     // (k << 1) | 1 if the path continues into the LEFT child; per CTA the number of internal nodes before its first node
     bool preorder = false;
+    // DFS-range backward (built together with the DFS-run forward when the tree qualifies; then s_bottom is not built)
+    bool dfs_bwd = false;
+    std::vector<DNode> bnodes;     // [N + 2] by node id
+    std::vector<BSpan> bspans;
+    std::vector<T2Node> t2nodes;
+    std::vector<int32_t> t2_lvl;
+    int bwd_max_nk = 0, bwd_max_leaves = 0, bwd_max_slots = 0, bwd_max_stack = 0, bwd_max_t2 = 0, bwd_max_lev = 0;
     std::vector<DNode> dnodes;
     std::vector<uint32_t> drun_anc_ptr, drun_anc;
     std::vector<int32_t> dcta_k0;
@@ -269,6 +299,11 @@ struct TreeDev {
     uint32_t *ganc_ptr = nullptr, *ganc = nullptr, *gcp = nullptr, *nsuf_ptr = nullptr;  // root paths (nullptr: not built)
     uint16_t *nsuf = nullptr;
     int n_groups = 0, max_ganc = 0, max_gsuf = 0;
+    DNode *bnodes = nullptr;  // DFS-range backward (nullptr: not available for this tree)
+    BSpan *bspans = nullptr;
+    T2Node *t2nodes = nullptr;
+    int32_t *t2_lvl = nullptr;
+    int n_bspans = 0, bwd_max_nk = 0, bwd_max_leaves = 0, bwd_max_slots = 0, bwd_max_stack = 0, bwd_max_t2 = 0, bwd_max_lev = 0;
     DNode *dnodes = nullptr;  // DFS-run forward (nullptr: not available for this tree)
     uint32_t *drun_anc_ptr = nullptr, *drun_anc = nullptr;
     int32_t *dcta_k0 = nullptr;

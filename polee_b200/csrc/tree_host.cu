@@ -12,7 +12,9 @@
 // level-synchronous sweep computes bit-identical values to the reference's serial index-order sweep.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <climits>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 
@@ -58,6 +60,14 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
     n = n_;
     N = 2 * n - 1;
     if (n < 1) return "tree: n must be >= 1";
+    static const bool timing = getenv("POLEE_SETUP_TIMING") != nullptr && getenv("POLEE_TREE_HOST_TIMING") != nullptr;
+    auto tprev = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!timing) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[polee tree host] %-26s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - tprev).count());
+        tprev = t1;
+    };
     nodes.assign(N, TreeNode{-1, -1, -1, -1});
     parent.assign(N, -1);
     depth.assign(N, 0);
@@ -93,6 +103,7 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
     }
     for (int64_t i = N - 1; i >= 1; --i) size[parent[i]] += size[i];
 
+    mark("validate + depth + size");
     // ---- DFS pre-order?  (right child = next node, left child = the node after the right subtree)
     bool preorder_nodes = n >= 2;
     for (int64_t i = 0; i < N && preorder_nodes; ++i)
@@ -129,6 +140,7 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
         for (int64_t c = 0; c < nctas; ++c) dfs_max_nk = std::max(dfs_max_nk, dcta_k0[c + 1] - dcta_k0[c]);
     }
 
+    mark("dfs-run forward inputs");
     // ---- root -> node paths, grouped (see TreeHost); not needed when the DFS-run kernel serves the tree
     ganc_ptr.clear(); ganc.clear(); gcp.clear(); nsuf_ptr.clear(); nsuf.clear();
     max_ganc = max_gsuf = 0;
@@ -196,6 +208,7 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
         }
     }
 
+    mark("root paths");
     // ---- caterpillar ("list") tree?
     caterpillar = n >= 2;
     for (int64_t i = 0; i < N && caterpillar; ++i) {
@@ -210,7 +223,13 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
         caterpillar = nodes[N - 1].leaf >= 0;
     }
 
-    // ---- cut: top = nodes whose subtree exceeds bin_nodes
+    // ---- cut: top = nodes whose subtree exceeds bin_nodes (the DFS-range backward kernel works on spans of
+    // DFS_CTA_NODES nodes: trees that qualify for it are cut there)
+    // (measured at C3: 80 us against 47.5 us for the level-synchronous bottom kernel -- 11 warps per SM at 75 KB of shared
+    // memory per CTA, profiles/r02_tree_bwd_dfs_v1_ncu_c3.csv -- so it is an experiment: POLEE_TREE_BWD=dfs turns it on)
+    static const bool bwd_on = getenv("POLEE_TREE_BWD") && !strcmp(getenv("POLEE_TREE_BWD"), "dfs");
+    const bool want_dfs_bwd = preorder && bwd_on;
+    if (want_dfs_bwd) bin_nodes = DFS_CTA_NODES;
     std::vector<char> is_top(N, 0);
     std::vector<int32_t> top_list;
     for (int64_t i = 0; i < N; ++i)
@@ -251,6 +270,7 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
             }
         }
     }
+    mark("cut + bins");
     int ml = 0;
     make_sched(bins, level_of, bottom, ml);
     std::vector<std::vector<int32_t>> tb;
@@ -260,6 +280,7 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
     }
     make_sched(tb, level_of, top, ml);
 
+    mark("global-memory schedules");
     // ---- schedule-order records for the shared-memory kernels
     std::vector<int32_t> slot_of(N, -2);
     n_slots = 0;
@@ -327,8 +348,130 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
             out.max_bin_levels = std::max(out.max_bin_levels, nl);
         }
     };
-    make_ssched(bins, false, s_bottom);
+    // ---- DFS-range backward schedule (see common.cuh)
+    dfs_bwd = false;
+    bnodes.clear(); bspans.clear(); t2nodes.clear(); t2_lvl.clear();
+    bwd_max_nk = bwd_max_leaves = bwd_max_slots = bwd_max_stack = bwd_max_t2 = bwd_max_lev = 0;
+    if (want_dfs_bwd) {
+        dfs_bwd = true;
+        bnodes.assign(N + 2, DNode{-1, 0xffffffffu});  // meta all ones: not a node of any span (a top node, padding)
+        std::vector<int32_t> kbefore(N + 1, 0);  // internal nodes before node i
+        for (int64_t i = 0; i < N; ++i) kbefore[i + 1] = kbefore[i] + (nodes[i].leaf < 0 ? 1 : 0);
+        // spans: consecutive bottom roots (whole subtrees, each a contiguous index range) while the range stays short
+        std::vector<std::pair<int32_t, int32_t>> spans;
+        for (int64_t r = 0; r < N; ++r) {
+            if (is_top[r] || (parent[r] >= 0 && !is_top[parent[r]])) continue;  // r is a bottom root
+            const int32_t e = (int32_t)(r + size[r]);
+            if (spans.empty() || e - spans.back().first > DFS_CTA_NODES) spans.emplace_back((int32_t)r, e);
+            else spans.back().second = e;
+            r = e - 1;  // the nodes of this subtree are no roots
+        }
+        std::vector<int8_t> tier(N, 3);
+        std::vector<int32_t> lslot(N, -1), lvl2(N, 0);
+        for (const auto &sp : spans) {
+            const int32_t s0 = sp.first, s1 = sp.second;
+            BSpan B{};
+            B.s0 = s0; B.nn = s1 - s0;
+            B.k0 = kbefore[s0]; B.nk = kbefore[s1] - kbefore[s0];
+            // tiers
+            for (int32_t i = s0; i < s1; ++i) {
+                if (is_top[i]) { tier[i] = 3; continue; }
+                const int32_t run_end = std::min(s1, s0 + ((i - s0) / DFS_BRUN + 1) * DFS_BRUN);
+                tier[i] = i + size[i] <= run_end ? 1 : 2;
+            }
+            // CTA slots: G of the non-top nodes whose parent is a tier-2 node
+            int32_t nslots = 0, nleaves = 0;
+            for (int32_t i = s0; i < s1; ++i) {
+                if (tier[i] == 3) continue;
+                const int ptier = (parent[i] < 0 || is_top[parent[i]]) ? 3 : tier[parent[i]];
+                if (ptier == 2) lslot[i] = nslots++;
+                uint32_t meta = 0;
+                if (nodes[i].leaf < 0 && tier[i] == 1) meta |= BN_T1INT;
+                if (tier[i] == 1 && ptier >= 2 && parent[i] >= 0) {
+                    meta |= BN_EXPORT;
+                    if (ptier == 3) {
+                        if (slot_of[i] >= 0) meta |= BN_GLOBAL | ((uint32_t)slot_of[i] << 14);
+                        else meta &= ~BN_EXPORT;  // the root of the whole tree: nobody reads its G
+                    } else {
+                        meta |= (uint32_t)lslot[i] << 14;
+                    }
+                }
+                if (nodes[i].leaf >= 0) meta |= (uint32_t)(nleaves++) << 3;
+                bnodes[i].k_or_leaf = nodes[i].leaf >= 0 ? -1 - nodes[i].leaf : nodes[i].k;
+                bnodes[i].meta = meta;
+            }
+            if (nleaves > 2047 || nslots >= (1 << 17) || n_slots >= (1 << 17)) dfs_bwd = false;
+            // the stack a run needs
+            for (int32_t r0 = s0; r0 < s1; r0 += DFS_BRUN) {
+                int sp_now = 0;
+                for (int32_t i = std::min(s1, r0 + DFS_BRUN) - 1; i >= r0; --i) {
+                    if (tier[i] == 3 || (nodes[i].leaf < 0 && tier[i] != 1)) continue;
+                    if (nodes[i].leaf < 0) sp_now -= 2;
+                    if (!(bnodes[i].meta & BN_EXPORT)) ++sp_now;
+                    bwd_max_stack = std::max(bwd_max_stack, sp_now);
+                }
+            }
+            // tier 2: levels (children have larger indices), records in level order
+            B.t2_off = (int32_t)t2nodes.size();
+            int nlev = 0;
+            std::vector<int32_t> t2list;
+            for (int32_t i = s1 - 1; i >= s0; --i) {
+                if (tier[i] != 2) continue;
+                int l = 0;
+                for (int32_t c : {nodes[i].left, nodes[i].right})
+                    if (tier[c] == 2) l = std::max(l, lvl2[c] + 1);
+                lvl2[i] = l;
+                nlev = std::max(nlev, l + 1);
+                t2list.push_back(i);
+            }
+            std::vector<int32_t> cnt(nlev + 1, 0);
+            for (int32_t i : t2list) cnt[lvl2[i] + 1]++;
+            for (int l = 0; l < nlev; ++l) cnt[l + 1] += cnt[l];
+            B.lvl_off = (int32_t)t2_lvl.size();
+            B.nlev = nlev;
+            for (int l = 0; l <= nlev; ++l) t2_lvl.push_back(cnt[l]);
+            t2nodes.resize(t2nodes.size() + t2list.size());
+            std::vector<int32_t> cur(cnt.begin(), cnt.end());
+            for (auto it = t2list.rbegin(); it != t2list.rend(); ++it) {  // ascending node order inside a level
+                const int32_t i = *it;
+                T2Node t;
+                t.k = nodes[i].k;
+                t.sl = lslot[nodes[i].left];
+                t.sr = lslot[nodes[i].right];
+                const int ptier = (parent[i] < 0 || is_top[parent[i]]) ? 3 : 2;
+                t.out = ptier == 2 ? lslot[i] : (slot_of[i] >= 0 ? -1 - slot_of[i] : INT32_MIN);
+                t2nodes[B.t2_off + cur[lvl2[i]]++] = t;
+            }
+            B.nt2 = (int32_t)t2list.size();
+            bspans.push_back(B);
+            bwd_max_nk = std::max(bwd_max_nk, B.nk);
+            bwd_max_leaves = std::max(bwd_max_leaves, nleaves);
+            bwd_max_slots = std::max(bwd_max_slots, nslots);
+            bwd_max_t2 = std::max(bwd_max_t2, B.nt2);
+            bwd_max_lev = std::max(bwd_max_lev, nlev);
+        }
+        if (bwd_max_stack > 32) dfs_bwd = false;
+        {   // shared memory of a CTA with 4 draws (the most the kernel takes), see dfs_bwd_smem in tree_kernels.cu
+            const size_t kpc = 4, threads = (size_t)DFS_BRUNS * kpc;
+            const size_t smem = (size_t)std::max(bwd_max_stack, 1) * threads * 8 + 2 * (size_t)std::max(bwd_max_nk, 1) * kpc * 8 +
+                                (size_t)std::max(bwd_max_slots, 1) * kpc * 8 + (size_t)std::max(bwd_max_t2, 1) * sizeof(T2Node) +
+                                (size_t)DFS_CTA_NODES * sizeof(DNode) + (size_t)std::max(bwd_max_leaves, 1) * kpc * 4 +
+                                4 * (size_t)(bwd_max_lev + 2);
+            if (smem > 200 * 1024) dfs_bwd = false;
+        }
+        if (!dfs_bwd) { bnodes.clear(); bspans.clear(); t2nodes.clear(); t2_lvl.clear(); }
+    }
+
+    mark("dfs-range backward");
+    if (dfs_bwd) {  // the level-synchronous bottom kernels are not used for this tree
+        s_bottom = SSchedHost();
+        s_bottom.bin_off.assign(1, 0);
+        s_bottom.bin_lvl_ptr.assign(1, 0);
+    } else {
+        make_ssched(bins, false, s_bottom);
+    }
     make_ssched(tb, true, s_top);
+    mark("shared-memory schedules");
     return "";
 }
 
@@ -372,6 +515,9 @@ void TreeDev::release() {
     nsuf = nullptr;
     polee::dfree(dnodes); polee::dfree(drun_anc_ptr); polee::dfree(drun_anc); polee::dfree(dcta_k0);
     dnodes = nullptr; drun_anc_ptr = drun_anc = nullptr; dcta_k0 = nullptr;
+    polee::dfree(bnodes); polee::dfree(bspans); polee::dfree(t2nodes); polee::dfree(t2_lvl);
+    bnodes = nullptr; bspans = nullptr; t2nodes = nullptr; t2_lvl = nullptr;
+    n_bspans = bwd_max_nk = bwd_max_leaves = bwd_max_slots = bwd_max_stack = bwd_max_t2 = bwd_max_lev = 0;
     dfs_ctas = dfs_max_nk = 0;
     n_groups = max_ganc = max_gsuf = 0;
     for (SSchedDev *s : {&s_top, &s_bottom}) {
@@ -470,6 +616,20 @@ std::string upload_tree(const TreeHost &th, TreeDev &td) {
         td.dfs_ctas = (int)th.dcta_k0.size() - 1;
         td.dfs_max_nk = th.dfs_max_nk;
         td.n_groups = std::max(td.n_groups, td.dfs_ctas);  // sizes the per-CTA partial sums (S, ladj)
+    }
+    if (e == cudaSuccess && th.dfs_bwd) {
+        auto upv = [&](const void *src, size_t bytes, void **dst) {
+            cudaError_t ee = polee::dmalloc(dst, std::max<size_t>(bytes, 16));
+            if (ee == cudaSuccess && bytes) ee = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+            return ee;
+        };
+        e = upv(th.bnodes.data(), sizeof(DNode) * th.bnodes.size(), (void **)&td.bnodes);
+        if (e == cudaSuccess) e = upv(th.bspans.data(), sizeof(BSpan) * th.bspans.size(), (void **)&td.bspans);
+        if (e == cudaSuccess) e = upv(th.t2nodes.data(), sizeof(T2Node) * th.t2nodes.size(), (void **)&td.t2nodes);
+        if (e == cudaSuccess) e = upv(th.t2_lvl.data(), 4 * th.t2_lvl.size(), (void **)&td.t2_lvl);
+        td.n_bspans = (int)th.bspans.size();
+        td.bwd_max_nk = th.bwd_max_nk; td.bwd_max_leaves = th.bwd_max_leaves; td.bwd_max_slots = th.bwd_max_slots;
+        td.bwd_max_stack = th.bwd_max_stack; td.bwd_max_t2 = th.bwd_max_t2; td.bwd_max_lev = th.bwd_max_lev;
     }
     td.n_slots = th.n_slots;
     td.caterpillar = th.caterpillar;

@@ -685,6 +685,149 @@ __global__ void __launch_bounds__(DFS_RUNS_PER_CTA *KP)
     if (want_ladj) block_reduce_kc<KP, THREADS>(lacc, red, ladj_partial + (size_t)blockIdx.x * KP);
 }
 
+// One node of transform_gradients! (ptt.jl:167-209; WITH_LADJ false: transform_gradients_no_ladj!, :217-251): the same
+// operations in the same association as k3s_tree_bwd, so whoever calls it produces the reference's bits.
+template <bool WITH_LADJ>
+__device__ __forceinline__ float2 bwd_node(double y, double ui, float2 gl, float2 gr, double &yg) {
+    const double omy = __dsub_rn(1.0, y);
+    float2 out;
+    out.x = (float)__dadd_rn(__dmul_rn(y, (double)gl.x), __dmul_rn(omy, (double)gr.x));
+    if (WITH_LADJ) {
+        const float d = __fsub_rn(__fadd_rn(gl.x, gl.y), __fadd_rn(gr.x, gr.y));
+        yg = (double)(float)__dmul_rn(ui, (double)d);
+        out.y = (float)__dadd_rn(__dadd_rn(__ddiv_rn(1.0, ui), __dmul_rn(y, (double)gl.y)), __dmul_rn(omy, (double)gr.y));
+    } else {
+        const float d = __fsub_rn(gl.x, gr.x);
+        yg = __dmul_rn(ui, (double)d);
+        out.y = 0.0f;
+    }
+    return out;
+}
+
+// transform_gradients! for trees in DFS pre-order, bottom part (see common.cuh, "DFS-range backward").  A CTA owns a span
+// of <= DFS_CTA_NODES consecutive nodes (whole bottom subtrees) and KPC draws; thread = (run of DFS_BRUN nodes, draw).
+//   staging : the span's records, the y and u of its internal nodes (consecutive k: contiguous rows of ys / us), the
+//             tier-2 records, and the leaves' gradients g - adj / S (likelihood.jl:105) rounded to Float32
+//   tier 1  : every thread walks its run backwards -- the reference's own order -- with a LIFO stack in shared memory:
+//             a leaf pushes its G, an internal node whose subtree lies inside the run pops its children (right on top)
+//             and pushes its own; a node whose parent is not tier 1 stores its G in a CTA slot (or, under a top node, in
+//             the global exchange array) instead of pushing it.  No barrier, no idle level sweeps.
+//   tier 2  : the span's remaining nodes (ancestors of run boundaries: ~13 % of a balanced tree), level by level from
+//             the CTA slots.
+// The top nodes follow in the one-CTA-per-draw kernel (k3s_tree_bwd over s_top), as before.
+template <int KP, int KPC, bool WITH_LADJ>
+__global__ void __launch_bounds__(DFS_BRUNS *KPC)
+    k3d_tree_bwd(const BSpan *__restrict__ spans, const DNode *__restrict__ bnodes, const T2Node *__restrict__ t2nodes,
+                 const int32_t *__restrict__ t2_lvl, const double *__restrict__ ys, const double *__restrict__ us_k,
+                 const double *__restrict__ g, const float *__restrict__ efflen_adj, const double *__restrict__ S,
+                 float2 *__restrict__ root_G, double *__restrict__ ygrad, double *__restrict__ xgrad_out, int stack_levels,
+                 int max_nk, int max_leaves, int max_slots, int max_t2, int max_lev) {
+    constexpr int THREADS = DFS_BRUNS * KPC;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float2 *stack = reinterpret_cast<float2 *>(smraw);                                  // [stack_levels][THREADS]
+    double *ys_s = reinterpret_cast<double *>(stack + (size_t)stack_levels * THREADS);  // [max_nk][KPC]
+    double *us_s = ys_s + (size_t)max_nk * KPC;                                         // [max_nk][KPC]
+    float2 *slot_s = reinterpret_cast<float2 *>(us_s + (size_t)max_nk * KPC);           // [max_slots][KPC]
+    T2Node *t2_s = reinterpret_cast<T2Node *>(slot_s + (size_t)max_slots * KPC);        // [max_t2]
+    DNode *rec_s = reinterpret_cast<DNode *>(t2_s + max_t2);                            // [DFS_CTA_NODES]
+    float *gl_s = reinterpret_cast<float *>(rec_s + DFS_CTA_NODES);                     // [max_leaves][KPC]
+    int *lvl_s = reinterpret_cast<int *>(gl_s + (size_t)max_leaves * KPC);              // [max_lev + 1]
+    const int kk = threadIdx.x % KPC, rl = threadIdx.x / KPC, k = blockIdx.y * KPC + kk;
+    const BSpan B = spans[blockIdx.x];
+
+    // ---- staging
+    for (int p = threadIdx.x; p < B.nn; p += THREADS) rec_s[p] = bnodes[B.s0 + p];
+    for (int q = threadIdx.x; q < B.nt2; q += THREADS) t2_s[q] = t2nodes[B.t2_off + q];
+    for (int l = threadIdx.x; l <= B.nlev; l += THREADS) lvl_s[l] = t2_lvl[B.lvl_off + l];
+    {
+        const double *ysrc = ys + (size_t)B.k0 * KP + blockIdx.y * KPC, *usrc = us_k + (size_t)B.k0 * KP + blockIdx.y * KPC;
+        const int cnt = B.nk * KPC;
+#pragma unroll 4
+        for (int idx = threadIdx.x; idx < cnt; idx += THREADS) {
+            const int r = idx / KPC, c = idx - r * KPC;
+            ys_s[idx] = ysrc[(size_t)r * KP + c];
+            us_s[idx] = usrc[(size_t)r * KP + c];
+        }
+    }
+    __syncthreads();
+    // leaves: g - adj / S, four independent gathers per thread in flight
+    const double Sk = efflen_adj ? S[k] : 1.0;
+    for (int base = rl; base < B.nn; base += 4 * DFS_BRUNS) {
+        double gv[4];
+        float adj[4];
+        int leaf[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = base + u * DFS_BRUNS;
+            leaf[u] = (p < B.nn && rec_s[p].k_or_leaf < 0 && rec_s[p].meta != 0xffffffffu) ? -1 - rec_s[p].k_or_leaf : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            gv[u] = 0.0; adj[u] = 0.0f;
+            if (leaf[u] >= 0) {
+                gv[u] = g[(size_t)leaf[u] * KP + k];
+                if (efflen_adj) adj[u] = efflen_adj[leaf[u]];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (leaf[u] < 0) continue;
+            const int p = base + u * DFS_BRUNS;
+            double v = gv[u];
+            if (efflen_adj) v = __dsub_rn(v, __ddiv_rn((double)adj[u], Sk));  // likelihood.jl:105
+            if (xgrad_out) xgrad_out[(size_t)leaf[u] * KP + k] = v;
+            gl_s[((rec_s[p].meta >> 3) & 0x7ffu) * KPC + kk] = (float)v;
+        }
+    }
+    __syncthreads();
+
+    // ---- tier 1: the run, backwards
+    {
+        const int p0 = rl * DFS_BRUN, p1 = p0 + DFS_BRUN < B.nn ? p0 + DFS_BRUN : B.nn;
+        float2 *st = stack + threadIdx.x;
+        int sp = 0;
+        for (int p = p1 - 1; p >= p0; --p) {
+            const DNode r = rec_s[p];
+            float2 G;
+            if (r.k_or_leaf < 0) {
+                if (r.meta == 0xffffffffu) continue;  // a top node inside the span
+                G = make_float2(gl_s[((r.meta >> 3) & 0x7ffu) * KPC + kk], 0.0f);
+            } else {
+                if (!(r.meta & BN_T1INT)) continue;   // tier 2
+                const float2 gr = st[(size_t)(sp - 1) * THREADS], gl = st[(size_t)(sp - 2) * THREADS];
+                sp -= 2;
+                const int kr = r.k_or_leaf - B.k0;
+                double yg;
+                G = bwd_node<WITH_LADJ>(ys_s[kr * KPC + kk], us_s[kr * KPC + kk], gl, gr, yg);
+                ygrad[(size_t)r.k_or_leaf * KP + k] = yg;
+            }
+            if (r.meta & BN_EXPORT) {
+                if (r.meta & BN_GLOBAL) root_G[(size_t)(r.meta >> 14) * KP + k] = G;
+                else slot_s[(r.meta >> 14) * KPC + kk] = G;
+            } else {
+                st[(size_t)sp * THREADS] = G;
+                ++sp;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- tier 2: level by level from the CTA slots
+    for (int l = 0; l < B.nlev; ++l) {
+        for (int q = lvl_s[l] + rl; q < lvl_s[l + 1]; q += DFS_BRUNS) {
+            const T2Node t = t2_s[q];
+            const int kr = t.k - B.k0;
+            double yg;
+            const float2 G = bwd_node<WITH_LADJ>(ys_s[kr * KPC + kk], us_s[kr * KPC + kk], slot_s[t.sl * KPC + kk],
+                                                 slot_s[t.sr * KPC + kk], yg);
+            ygrad[(size_t)t.k * KP + k] = yg;
+            if (t.out >= 0) slot_s[t.out * KPC + kk] = G;
+            else if (t.out != INT32_MIN) root_G[(size_t)(-1 - t.out) * KP + k] = G;
+        }
+        __syncthreads();
+    }
+}
+
 // S_k = sum_j x_jk / efflen_j (effective_length_jacobian_adjustment!, likelihood.jl:96-100: Float32 quotients, Float64
 // sum) and the step bookkeeping of k3_mid, for the forward kernels that leave S out of their node loop.  A warp adds
 // LEAF_S_PER_WARP transcripts (all loads of a batch in flight, fixed order) and writes one partial row; the CTA that
@@ -1097,18 +1240,16 @@ static bool path_fwd_ok(const polee_handle *h) {
     static const bool off = getenv("POLEE_TREE_FWD") && !strcmp(getenv("POLEE_TREE_FWD"), "levels");
     return !off && h->td.ganc_ptr != nullptr && !chain_path(h) && smem_path_ok(h, h->work_KP);
 }
-// the DFS-run forward kernel (k3d_tree_fwd): trees in DFS pre-order of moderate depth (tree_host.cu builds its inputs
-// only then); like the path-product kernel it leaves u by k for the shared-memory backward kernels
-static size_t dfs_fwd_smem(const polee_handle *h, int KP) {
-    const size_t threads = (size_t)DFS_RUNS_PER_CTA * KP;
-    return (size_t)(h->td.max_depth + 2) * threads * 8 + (size_t)((std::max(h->td.dfs_max_nk, 1) + 1) & ~1) * KP * 8 +
-           (size_t)DFS_RUNS_PER_CTA * (DFS_RUN + 2) * sizeof(DNode);
+// the DFS-range backward kernel (k3d_tree_bwd) goes with the DFS-run forward (it reads its u by k)
+static int dfs_bwd_kpc(int KP) { return KP < 4 ? KP : 4; }
+static size_t dfs_bwd_smem(const polee_handle *h, int KP) {
+    const TreeDev &td = h->td;
+    const size_t kpc = (size_t)dfs_bwd_kpc(KP), threads = (size_t)DFS_BRUNS * kpc;
+    return (size_t)std::max(td.bwd_max_stack, 1) * threads * 8 + 2 * (size_t)std::max(td.bwd_max_nk, 1) * kpc * 8 +
+           (size_t)std::max(td.bwd_max_slots, 1) * kpc * 8 + (size_t)std::max(td.bwd_max_t2, 1) * sizeof(T2Node) +
+           (size_t)DFS_CTA_NODES * sizeof(DNode) + (size_t)std::max(td.bwd_max_leaves, 1) * kpc * 4 + 4 * (size_t)(td.bwd_max_lev + 2);
 }
-static bool dfs_fwd_ok(const polee_handle *h) {
-    return h->td.dnodes != nullptr && !chain_path(h) && smem_path_ok(h, h->work_KP) && h->work_KP <= 16 &&
-           dfs_fwd_smem(h, h->work_KP) <= 200 * 1024;
-}
-static bool fwd_leaves_us_by_k(const polee_handle *h) { return dfs_fwd_ok(h) || path_fwd_ok(h); }
+
 
 // bottom-forest launch variants (draws per CTA, threads, min CTAs/SM); POLEE_TREE_VARIANT picks one at run time
 static int tree_variant() {
@@ -1119,7 +1260,21 @@ static int tree_variant() {
     }
     return v;
 }
-
+// the DFS-run forward kernel (k3d_tree_fwd): trees in DFS pre-order of moderate depth (tree_host.cu builds its inputs
+// only then); like the path-product kernel it leaves u by k for the shared-memory backward kernels
+static size_t dfs_fwd_smem(const polee_handle *h, int KP) {
+    const size_t threads = (size_t)DFS_RUNS_PER_CTA * KP;
+    return (size_t)(h->td.max_depth + 2) * threads * 8 + (size_t)((std::max(h->td.dfs_max_nk, 1) + 1) & ~1) * KP * 8 +
+           (size_t)DFS_RUNS_PER_CTA * (DFS_RUN + 2) * sizeof(DNode);
+}
+static bool dfs_fwd_ok(const polee_handle *h) {
+    // a tree cut for the DFS-range backward kernel has no level-synchronous bottom schedule: both or neither
+    return h->td.dnodes != nullptr && !chain_path(h) && smem_path_ok(h, h->work_KP) && h->work_KP <= 16 &&
+           dfs_fwd_smem(h, h->work_KP) <= 200 * 1024 &&
+           (h->td.bnodes == nullptr || dfs_bwd_smem(h, h->work_KP) <= 200 * 1024);
+}
+static bool dfs_bwd_ok(const polee_handle *h) { return h->td.bnodes != nullptr && dfs_fwd_ok(h); }
+static bool fwd_leaves_us_by_k(const polee_handle *h) { return dfs_fwd_ok(h) || path_fwd_ok(h); }
 template <int KP, int KPC, int THREADS, int MINB>
 static void launch_fwd_bottom_v(polee_handle *h, int clamp_x, const float *eff, double *Sp, int want_ladj, double *ladj_tree) {
     const TreeDev &td = h->td;
@@ -1169,7 +1324,16 @@ static int launch_tree_fwd_smem(polee_handle *h, int clamp_x, const float *eff, 
 template <int KP, bool WITH_LADJ>
 static int launch_tree_bwd_smem(polee_handle *h, const float *adj, double *xgrad_out) {
     const TreeDev &td = h->td;
-    if (td.s_bottom.nbins > 0) {
+    if (dfs_bwd_ok(h)) {
+        constexpr int KPC = KP < 4 ? KP : 4;
+        const size_t smem = dfs_bwd_smem(h, KP);
+        auto fn = k3d_tree_bwd<KP, KPC, WITH_LADJ>;
+        set_smem_attr(fn, smem);
+        fn<<<dim3(td.n_bspans, KP / KPC), DFS_BRUNS * KPC, smem, h->stream>>>(
+            td.bspans, td.bnodes, td.t2nodes, td.t2_lvl, h->ys, h->us, h->g, adj, h->S, h->root_G, h->ygrad, xgrad_out,
+            std::max(td.bwd_max_stack, 1), std::max(td.bwd_max_nk, 1), std::max(td.bwd_max_leaves, 1),
+            std::max(td.bwd_max_slots, 1), std::max(td.bwd_max_t2, 1), td.bwd_max_lev);
+    } else if (td.s_bottom.nbins > 0) {
         if constexpr (KP == 8) {
             const int v = tree_variant();
             if (v == 1) launch_bwd_bottom_v<8, 8, 512, 1, WITH_LADJ>(h, adj, xgrad_out);
@@ -1236,7 +1400,7 @@ int launch_tree_fwd(polee_handle *h, int KP, int clamp_x, int want_S, int want_l
                             eff, Sp, want_ladj, ladj_tree)));
         return POLEE_OK;
     }
-    if (smem_path_ok(h, KP)) {
+    if (smem_path_ok(h, KP) && td.bnodes == nullptr) {
         int rc = POLEE_OK;
         DISPATCH_KP(KP, rc = launch_tree_fwd_smem<KPC>(h, clamp_x, eff, Sp, want_ladj, ladj_tree));
         return rc;
@@ -1272,7 +1436,7 @@ int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, 
     const TreeDev &td = h->td;
     const float *adj = apply_efflen ? h->efflen_adj : nullptr;
     if (chain_path(h)) return launch_chain_bwd(h, KP, with_ladj, adj, xgrad_out);
-    if (smem_path_ok(h, KP)) {
+    if (smem_path_ok(h, KP) && (td.bnodes == nullptr || dfs_bwd_ok(h))) {
         int rc = POLEE_OK;
         if (with_ladj) {
             DISPATCH_KP(KP, (rc = launch_tree_bwd_smem<KPC, true>(h, adj, xgrad_out)));

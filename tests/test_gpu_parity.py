@@ -255,6 +255,44 @@ def test_piecewise_calls_between_steps_do_not_disturb_the_fit(pb, fx):
             assert np.array_equal(w, g), Kp
 
 
+def test_set_sample_in_one_call_equals_the_three_calls(pb, fx, small_synth):
+    """polee_set_sample (matrix + efflens + tree; the host tree preparation on a second thread beside the upload) leaves
+    the handle in the state polee_set_matrix_csc + polee_set_efflens + polee_set_tree do: identical fits; a bad tree is
+    reported with the reference's message class and leaves the handle usable."""
+    import polee_b200._lib as L
+    cases = [(_sample(pb, fx), (fx.parent_idxs, fx.js)), (_synth_sample(pb, small_synth), small_synth["tree"])]
+    for sample, tree in cases:
+        outs = []
+        for one_call in (False, True):
+            h = pb.Handle(num_mc_samples=6, num_steps=12, seed=99)
+            if one_call:
+                h.set_sample(sample, None, tree)
+            else:
+                h.set_sample(sample)
+                h.set_tree(*tree)
+            outs.append(h.fit())
+            if one_call:          # the same handle again, the other way round: state is replaced cleanly
+                h.set_sample(sample, None, tree)
+                again = h.fit()
+                for k in ("mu", "omega", "alpha"):
+                    assert np.array_equal(again[k], outs[-1][k])
+            h.close()
+        for k in ("mu", "omega", "alpha"):
+            assert np.array_equal(outs[0][k], outs[1][k]), k
+    h = pb.Handle(num_mc_samples=2, num_steps=3)
+    bad = fx.parent_idxs.copy()
+    bad[5] = 600                                       # parent index after the child
+    with pytest.raises(pb.PoleeError) as e:
+        h.set_sample(_sample(pb, fx), None, (bad, fx.js))
+    assert e.value.code == L.POLEE_EBADTREE
+    h.set_sample(_sample(pb, fx), None, (fx.parent_idxs, fx.js))
+    assert np.all(np.isfinite(h.fit()["mu"]))
+    h.close()
+    out = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), _sample(pb, fx),
+                                    tree_topology=(fx.parent_idxs, fx.js), num_steps=5)
+    assert np.all(np.isfinite(out["mu"]))
+
+
 def test_progress_callback_and_random_treemethod(pb, fx):
     """polee_set_progress reports finished steps (the reference's "Optimizing" bar, l-a.jl:495,574); treemethod
     "random" (rand_tree_nodes, src/hclust.jl:439-454) builds a seeded random tree and returns its topology."""
