@@ -39,6 +39,7 @@ CONFIGS = {
     "c2": (1 << 20, 20_000, 1, False, 20260002),
     "c3": (30_000_000, 200_000, 8, False, 20260003),
     "c3-small": (3_000_000, 200_000, 8, False, 20260003),
+    "c3-k6": (30_000_000, 200_000, 6, False, 20260003),   # the C3 matrix at the reference's default K (constants.jl:65)
     # C4 (heavy multi-mapping, only ever exists as per-rank blocks) and C5 (64 whole samples, one per GPU at a time):
     # see run_c4 / run_c5
     "c4": (100_000_000, 250_000, 8, True, 20260004),
@@ -210,6 +211,8 @@ def run_oneshot_child(args):
     del s
     torch.cuda.empty_cache()
     sample = pb.RNASeqSample(m, n, colptr, rowval, nzval, efflens)
+    import gc
+    gc.collect()   # the generator's garbage is not part of the call
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     out = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), sample, tree_topology=tree, num_steps=FIT_STEPS,
@@ -440,7 +443,9 @@ def run_ours(args):
         pbapi.trim_memory(local)           # cold device allocator: what a one-shot `polee prep-sample` process sees
         sample = pb.RNASeqSample(m, n, host["colptr"], host["rowval"], host["nzval"], efflens)
         t_fits = []
+        import gc
         for rep in range(2):   # [0]: cold (no cached device memory), [1]: warm (`polee prep` over many samples)
+            gc.collect()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             out = pb.approximate_likelihood(pb.LogitSkewNormalPTTApprox(), sample, tree_topology=tree, num_steps=FIT_STEPS,

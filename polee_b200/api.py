@@ -17,6 +17,8 @@ the device.  Everything computes on the GPU through the C ABI; nothing here is a
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from . import _lib as L
@@ -104,6 +106,10 @@ class Handle:
         is ONE polee_set_sample call (host tree preparation on a second thread beside the matrix upload / layout build),
         without it polee_set_matrix_csc + polee_set_efflens as before."""
         ksa = None if ks is None else _c(ks, np.int64)
+        if tree_topology is not None and os.environ.get("POLEE_SET_SAMPLE", "") == "3calls":   # experiments: the old sequence
+            self.set_sample(sample, ks)
+            self.set_tree(*tree_topology)
+            return
         if tree_topology is not None:
             pi, js = _c(tree_topology[0], np.int32), _c(tree_topology[1], np.int32)
             assert pi.shape == js.shape and len(js) == 2 * sample.n - 1

@@ -99,6 +99,18 @@ extern "C" int polee_device_info(int32_t device, int32_t *sm, int32_t *num_sms, 
     return POLEE_OK;
 }
 
+// POLEE_SETUP_TIMING=1: where polee_create / polee_set_tree / polee_set_sample spend their time
+struct HostPhaseTimer {
+    bool on = getenv("POLEE_SETUP_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[polee tree ] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 extern "C" int polee_create(polee_handle **out, const polee_opts *opts) {
     if (!out) return POLEE_EINVAL;
     *out = nullptr;
@@ -112,20 +124,26 @@ extern "C" int polee_create(polee_handle **out, const polee_opts *opts) {
     if (o.num_mc_samples < 1 || o.num_mc_samples > 16) return fail(POLEE_EINVAL, "num_mc_samples must be in 1..16");
     if (o.approx == POLEE_APPROX_OPTIMIZE_PTT) o.num_mc_samples = 1;
     if (o.num_steps < 0) return fail(POLEE_EINVAL, "num_steps must be >= 0");
+    HostPhaseTimer pt;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         return fail(POLEE_ECUDA, std::string("no CUDA device (libpolee_b200 has no CPU fallback): ") +
                                      cudaGetErrorString(e));
     if (o.device < 0 || o.device >= count) return fail(POLEE_EINVAL, "device ordinal out of range");
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, o.device) != cudaSuccess) return fail(POLEE_ECUDA, "cudaGetDeviceProperties failed");
-    if (p.major != 10) return fail(POLEE_ECUDA, "libpolee_b200 is built for sm_100a only (B200); found another GPU");
+    // two attribute queries, not cudaGetDeviceProperties: that call also asks the driver for clocks and the like and was
+    // measured taking 3 - 290 ms on a GPU that had just gone idle (profiles/README.md, round 2, e2e set-up)
+    int cc_major = 0, sm_count = 0;
+    if (cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, o.device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, o.device) != cudaSuccess)
+        return fail(POLEE_ECUDA, "cudaDeviceGetAttribute failed");
+    if (cc_major != 10) return fail(POLEE_ECUDA, "libpolee_b200 is built for sm_100a only (B200); found another GPU");
     if (cudaSetDevice(o.device) != cudaSuccess) return fail(POLEE_ECUDA, "cudaSetDevice failed");
+    pt.mark("create: device queries");
     polee_handle *h = new polee_handle();
     h->o = o;
     h->device = o.device;
-    h->num_sms = p.multiProcessorCount;
+    h->num_sms = sm_count;
     h->K = o.num_mc_samples;
     h->KP = pad_k(h->K);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -139,6 +157,7 @@ extern "C" int polee_create(polee_handle **out, const polee_opts *opts) {
         delete h;
         return fail(POLEE_ECUDA, "stream / control block allocation failed");
     }
+    pt.mark("create: streams + control");
     *out = h;
     return POLEE_OK;
 }
@@ -314,18 +333,6 @@ static int alloc_params(polee_handle *h) {
     return POLEE_OK;
 }
 
-// POLEE_SETUP_TIMING=1: where polee_set_tree spends its time
-struct HostPhaseTimer {
-    bool on = getenv("POLEE_SETUP_TIMING") != nullptr;
-    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    void mark(const char *what) {
-        if (!on) return;
-        auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[polee tree ] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        t0 = t1;
-    }
-};
-
 // inverse_transform!(t, fill(1.0f0/n, n), ys); map!(logit, mu, ys)   likelihood-approximation.jl:451-453, on the device:
 // fills h->mu0_dev (polee_init_params starts every fit from it)
 static int initial_mu_device(polee_handle *h) {
@@ -402,10 +409,19 @@ extern "C" int polee_set_sample(polee_handle *h, int64_t m, int64_t n, const uin
             tree_err = std::string("tree: ") + e.what();
         }
     })};
+    // a third thread loads the kernels of the ADAM step (lazy module loading would otherwise do that at their first
+    // launch, with the device idle); POLEE_PRELOAD=0 turns it off
+    static const bool preload = !(getenv("POLEE_PRELOAD") && !strcmp(getenv("POLEE_PRELOAD"), "0"));
+    Joiner loader{preload && h->o.approx == POLEE_APPROX_LOGIT_SKEW_NORMAL_PTT ? std::thread([h]() {
+        if (cudaSetDevice(h->device) != cudaSuccess) return;
+        polee::preload_ec_kernels(h, h->KP, h->K);
+        polee::preload_tree_kernels(h->KP);
+    }) : std::thread()};
     int rc = polee_set_matrix_csc(h, m, n, colptr, rowval, nzval, ks);
     if (!rc) rc = polee_set_efflens(h, efflens);
     pt.mark("matrix + efflens (this thread)");
     worker.t.join();
+    if (loader.t.joinable()) loader.t.join();
     if (rc) return rc;
     return finish_tree(h, tree_err, pt);
 }
@@ -629,22 +645,27 @@ static int enqueue_step(polee_handle *h) {
     if (!h->graph_warm) {
         // the first step of a handle runs uncaptured: every kernel it needs is then loaded before a capture starts
         // (lazy module loading allocates, which a capture does not tolerate)
+        HostPhaseTimer pt;
         rc = launch_step_sequence(h, true, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
         if (rc) return rc;
         CK(cudaGetLastError());
         h->graph_warm = true;
+        pt.mark("first step: enqueue (uncaptured)");
         return POLEE_OK;
     }
     if (!h->graph_exec) {
         // Relaxed: other host threads (one handle per thread in `polee prep`) may allocate, free or synchronise while
         // this thread records; the handle's streams are non-blocking, so nothing they do can join this capture.
+        HostPhaseTimer pt;
         std::shared_lock<std::shared_mutex> cap(polee::capture_mutex());  // no device-wide sync anywhere meanwhile
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
         rc = launch_step_sequence(h, true, true, nullptr, nullptr, noise, std::max<int64_t>(h->noise_steps, 1));
         cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
         if (rc) return rc;
         if (e != cudaSuccess) return h->fail(POLEE_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        pt.mark("second step: capture");
         CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+        pt.mark("graph instantiate");
     }
     CK(cudaGraphLaunch(h->graph_exec, h->stream));
     return POLEE_OK;
@@ -652,8 +673,11 @@ static int enqueue_step(polee_handle *h) {
 
 extern "C" int polee_run_steps(polee_handle *h, int32_t nsteps) {
     CHECK_H(h);
+    HostPhaseTimer pt;
+    pt.on = pt.on && !h->graph_warm;
     int rc = ready_for_steps(h);
     if (rc) return rc;
+    pt.mark("run_steps: work buffers");
     for (int s = 0; s < nsteps; ++s) {
         if ((rc = enqueue_step(h))) return rc;
         h->steps_enqueued++;

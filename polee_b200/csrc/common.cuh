@@ -531,6 +531,8 @@ int ec_grid(polee_handle *h, int KP);
 // g (+)= X_ec^T (1 / X_ec x); add_to_g: the general layouts already wrote their share of g
 int launch_ec(polee_handle *h, const float *x, double *g, bool add_to_g, bool want_lp, double *lp_out, float *w_out, int KP, int K,
               bool lik_only = false);  // lik_only: the class kernel without its second stage (measurement)
+void preload_ec_kernels(const polee_handle *h, int KP, int K);  // lazy-loading warm-up, see tree_kernels.cu
+void preload_tree_kernels(int KP);
 bool ec_math_f32(const polee_handle *h);  // opts.exact_accumulation / POLEE_EC_MATH
 
 // fused_kernels.cu

@@ -651,7 +651,42 @@ int launch_combine_kp(polee_handle *h, double *g, bool add_to_g, int KP) {
     return POLEE_OK;
 }
 
+template <typename T, int KD>
+void preload_lik_kd() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_ec_lik<T, KD, false>);
+}
+template <typename P>
+void preload_combine(int KP) {
+    cudaFuncAttributes a;
+    switch (KP) {
+        case 1: cudaFuncGetAttributes(&a, k_ec_combine1<P, 1>); cudaFuncGetAttributes(&a, k_ec_combine2<1>); break;
+        case 2: cudaFuncGetAttributes(&a, k_ec_combine1<P, 2>); cudaFuncGetAttributes(&a, k_ec_combine2<2>); break;
+        case 4: cudaFuncGetAttributes(&a, k_ec_combine1<P, 4>); cudaFuncGetAttributes(&a, k_ec_combine2<4>); break;
+        case 8: cudaFuncGetAttributes(&a, k_ec_combine1<P, 8>); cudaFuncGetAttributes(&a, k_ec_combine2<8>); break;
+        case 16: cudaFuncGetAttributes(&a, k_ec_combine1<P, 16>); cudaFuncGetAttributes(&a, k_ec_combine2<16>); break;
+        default: break;
+    }
+}
+template <typename T>
+void preload_ec(int KP, int K) {
+    if (K > 8) preload_lik_kd<T, 8>();
+    else if (K == 1) preload_lik_kd<T, 1>();
+    else if (K == 2) preload_lik_kd<T, 2>();
+    else if (K <= 4) preload_lik_kd<T, 4>();
+    else if (K <= 6) preload_lik_kd<T, 6>();
+    else preload_lik_kd<T, 8>();
+    preload_combine<T>(KP);
+}
+
 }  // namespace
+
+// see preload_tree_kernels (tree_kernels.cu): the class kernel and its second stage, gradient-only variant
+void preload_ec_kernels(const polee_handle *h, int KP, int K) {
+    if (ec_math_f32(h)) preload_ec<float>(KP, K);
+    else preload_ec<double>(KP, K);
+    cudaGetLastError();
+}
 
 // The arithmetic of the class kernel (see the header of this file): Float32 runs by default, Float64 with
 // opts.exact_accumulation == 2; POLEE_EC_MATH=f32|f64 overrides both (experiments).

@@ -1461,6 +1461,32 @@ int launch_tree_bwd(polee_handle *h, int KP, bool with_ladj, bool apply_efflen, 
     return POLEE_OK;
 }
 
+// Under CUDA's lazy module loading a kernel's code is loaded at its first launch (a few hundred microseconds to
+// milliseconds each, the device idle meanwhile).  polee_set_sample calls this from a helper thread while the matrix is on
+// its way to the device, so that the first ADAM step finds the kernels of the default step (balanced trees in
+// pre-order, logit-skew-normal fit) resident.  Asking for a kernel's attributes loads it; nothing else happens here.
+template <int KP>
+static void preload_tree_kernels_kp() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k3_elem<KP>);
+    cudaFuncGetAttributes(&a, k3d_tree_fwd<KP>);
+    cudaFuncGetAttributes(&a, k3_leaf_S<KP>);
+    if constexpr (KP == 8) cudaFuncGetAttributes(&a, k3s_tree_bwd<8, 4, 256, 3, true>);
+    else cudaFuncGetAttributes(&a, k3s_tree_bwd<KP, (KP < 8 ? KP : 8), 256, 2, true>);
+    cudaFuncGetAttributes(&a, k3s_tree_bwd<KP, 1, S_TOP_THREADS, 1, true>);
+    cudaGetLastError();
+}
+void preload_tree_kernels(int KP) {
+    switch (KP) {
+        case 1: preload_tree_kernels_kp<1>(); break;
+        case 2: preload_tree_kernels_kp<2>(); break;
+        case 4: preload_tree_kernels_kp<4>(); break;
+        case 8: preload_tree_kernels_kp<8>(); break;
+        case 16: preload_tree_kernels_kp<16>(); break;
+        default: break;
+    }
+}
+
 int launch_update(polee_handle *h, int KP, int K, bool do_adam, float *grad_out) {
     return launch_elem(h, KP, K, true, do_adam, false, nullptr, 1, 0, grad_out, -1, 0, 1);
 }
