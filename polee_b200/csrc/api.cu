@@ -1055,9 +1055,11 @@ extern "C" int polee_step_stats(polee_handle *h, double *b1, double *b2, double 
 extern "C" int polee_layout_info(polee_handle *h, int64_t *info, int32_t count) {
     CHECK_H(h);
     if (!info || count < 1) return h->fail(POLEE_EINVAL, "layout_info: bad arguments");
-    const int64_t v[10] = {h->ec_rows, h->ec_nnz, h->ec_classes, (int64_t)h->ec_tasks, (int64_t)h->ec_blob_bytes, h->ec_parts,
-                           h->gm, h->gnnz, (int64_t)((h->gm > 0 || h->ec_tasks == 0) ? (h->fused ? 2 : 1) : 0), h->ec_slots};
-    for (int i = 0; i < count && i < 10; ++i) info[i] = v[i];
+    const bool dfs_bwd = h->have_tree && h->td.bnodes != nullptr;
+    const int64_t v[12] = {h->ec_rows, h->ec_nnz, h->ec_classes, (int64_t)h->ec_tasks, (int64_t)h->ec_blob_bytes, h->ec_parts,
+                           h->gm, h->gnnz, (int64_t)((h->gm > 0 || h->ec_tasks == 0) ? (h->fused ? 2 : 1) : 0), h->ec_slots,
+                           dfs_bwd ? 1 : 0, dfs_bwd ? (int64_t)h->td.n_bspans : 0};
+    for (int i = 0; i < count && i < 12; ++i) info[i] = v[i];
     return POLEE_OK;
 }
 

@@ -227,7 +227,8 @@ std::string TreeHost::build_from_lrf(int64_t n_, const int32_t *left, const int3
     // DFS_CTA_NODES nodes: trees that qualify for it are cut there)
     // (measured at C3: 80 us against 47.5 us for the level-synchronous bottom kernel -- 11 warps per SM at 75 KB of shared
     // memory per CTA, profiles/r02_tree_bwd_dfs_v1_ncu_c3.csv -- so it is an experiment: POLEE_TREE_BWD=dfs turns it on)
-    static const bool bwd_on = getenv("POLEE_TREE_BWD") && !strcmp(getenv("POLEE_TREE_BWD"), "dfs");
+    const char *bwd_env = getenv("POLEE_TREE_BWD");  // read per tree, so that a test can switch it
+    const bool bwd_on = bwd_env && !strcmp(bwd_env, "dfs");
     const bool want_dfs_bwd = preorder && bwd_on;
     if (want_dfs_bwd) bin_nodes = DFS_CTA_NODES;
     std::vector<char> is_top(N, 0);

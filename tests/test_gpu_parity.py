@@ -674,3 +674,42 @@ def test_exact_factorization_on_device(pb, fx, small_synth, oracle):
         h1.close()
         assert relerr(lp1, lp0) <= 1e-10 and relerr(g1, g0) <= 1e-6
     assert dup[0] > 2 * comp.m * 0.9                                  # the synthetic case really was ~2.5x redundant
+
+
+@pytest.mark.gpu
+def test_dfs_range_backward_experiment_bit_exact(pb, fx, small_synth, oracle, monkeypatch):
+    """The opt-in DFS-range tree backward kernel (POLEE_TREE_BWD=dfs, k3d_tree_bwd: per-thread runs with a LIFO stack,
+    run-crossing nodes level by level from CTA slots, the top part as before) produces the reference's bits, on trees
+    with several spans and a top part, for both ladj variants and through a whole fit (leaf effective-length term)."""
+    from polee_b200 import synth
+    monkeypatch.setenv("POLEE_TREE_BWD", "dfs")
+    rng = np.random.default_rng(5)
+    for name, (pi, js), n in (("balanced", synth.balanced_tree(20001), 20001), ("random", synth.random_tree(6000, 9), 6000),
+                               ("fixture", (fx.parent_idxs, fx.js), fx.n)):
+        t = pb.PolyaTreeTransform(pi, js)
+        info = t.handle.layout_info()
+        assert info["tree_bwd_dfs"] == 1 and (info["tree_bwd_spans"] >= 2 or n < 1000), (name, info)
+        to = oracle.PTT(pi, js)
+        for K in (4, 8):
+            ys = rng.uniform(0.01, 0.99, (K, n - 1))
+            x_grad = rng.normal(size=(K, n)) * 1000
+            t.transform(ys, compute_ladj=False)
+            yg = t.transform_gradients(ys, x_grad)
+            yg0 = t.transform_gradients_no_ladj(ys, x_grad)
+            for k in range(K):
+                to.transform(ys[k], True)   # transform_gradients! reads the us transform! left behind (ptt.jl:167-170)
+                want = to.transform_gradients(ys[k], x_grad[k])
+                assert np.all(np.isfinite(want)) and np.array_equal(yg[k], want), (name, K, k)
+                assert np.array_equal(yg0[k], to.transform_gradients_no_ladj(ys[k], x_grad[k]).astype(np.float32)), (name, K, k)
+    # a whole fit: identical parameters with either backward engine
+    sample, tree = _synth_sample(pb, small_synth), small_synth["tree"]
+    fits = []
+    for engine in ("dfs", "levels"):
+        monkeypatch.setenv("POLEE_TREE_BWD", engine)
+        h = pb.Handle(num_mc_samples=6, num_steps=10, seed=7)
+        h.set_sample(sample, None, tree)
+        assert h.layout_info()["tree_bwd_dfs"] == (1 if engine == "dfs" else 0)
+        fits.append(h.fit())
+        h.close()
+    for k in ("mu", "omega", "alpha"):
+        assert np.array_equal(fits[0][k], fits[1][k]), k
