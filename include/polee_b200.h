@@ -115,7 +115,10 @@ int polee_set_tree_sequential(polee_handle *h, int64_t n);
  * (the three inputs likelihood-approximation.jl:404-435 takes from the RNASeqSample and the PolyaTreeTransform), same
  * arguments, same resulting state.  The host-side tree preparation runs on a second host thread while the calling
  * thread uploads the matrix and the device builds its layout, so the set-up costs max(matrix, tree) instead of their
- * sum.  A bad tree is reported (POLEE_EBADTREE) after the matrix has been set. */
+ * sum; a third short-lived thread loads the ADAM step's kernels meanwhile (CUDA loads a kernel lazily at its first
+ * launch otherwise; POLEE_PRELOAD=0 turns that off).  Both helper threads are plain std::threads that touch nothing of
+ * the caller's and are joined before the call returns.  A bad tree is reported (POLEE_EBADTREE) after the matrix has
+ * been set. */
 int polee_set_sample(polee_handle *h, int64_t m, int64_t n, const uint32_t *colptr, const uint32_t *rowval,
                      const float *nzval, const int64_t *ks /* m or NULL */, const float *efflens /* n */,
                      const int32_t *node_parent_idxs, const int32_t *node_js);
