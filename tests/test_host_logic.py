@@ -48,6 +48,17 @@ def test_no_cpu_fallback_create_fails_without_gpu(lib):
         pb.hsb(np.zeros((1, 2), np.float32), [1, -1, -1, -1, -1], [2, -1, -1, -1, -1], [-1, 0, 1, -1, -1][:5])
 
 
+def test_null_handle_is_an_argument_error_not_a_crash(lib):
+    """Every handle entry point checks its handle first (no device needed to say so): the one-call set-up included."""
+    from polee_b200 import _lib
+    z = C.c_void_p(None)
+    u32, f32, i32 = (C.c_uint32 * 2)(1, 1), (C.c_float * 1)(1.0), (C.c_int32 * 1)(0)
+    assert lib.polee_set_sample(z, C.c_int64(1), C.c_int64(1), u32, u32, f32, None, f32, i32, i32) == _lib.POLEE_EINVAL
+    assert lib.polee_set_tree(z, C.c_int64(1), i32, i32) == _lib.POLEE_EINVAL
+    assert lib.polee_run_steps(z, C.c_int32(1)) == _lib.POLEE_EINVAL
+    assert lib.polee_destroy(z) == _lib.POLEE_OK
+
+
 def test_product_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "polee_b200")):
         for fn in files:
